@@ -1,0 +1,276 @@
+/*
+ * mcfost_b200.h -- C ABI of the B200-native replacement for MCFOST's Monte Carlo
+ * photon-packet loop.
+ *
+ * What it replaces (reference = cpinte/mcfost 4.1.13, paths relative to src/):
+ *   the body of  subroutine mc_photon_loop(lambda_in, p_lambda_in, n_photons2,
+ *   n_phot_lim, nnfot1_start, laffichage)            dust_transfer.f90:439-572
+ *   and everything it calls (emit_packet :1047, propagate_packet :1155,
+ *   physical_length optical_depth.f90:21, cross_cell / index_cell / move_to_grid
+ *   of cylindrical_grid.f90, spherical_grid.f90, Voronoi.f90, save_radiation_field
+ *   radiation_field.f90:31, im_reemission_LTE thermal_emission.f90:710, the
+ *   scattering samplers scattering.f90:1187-1475 and capteur output.f90:294).
+ *
+ * Conventions follow the reference's own C boundary (voro_C, Voronoi.f90:70-96
+ * <-> voro++_wrapper.cpp:41-44): plain pointers and sizes, the CALLER allocates
+ * and owns every host buffer, the callee never frees caller memory, and every
+ * entry point returns an int error code (0 = OK; non-zero -> the Fortran shim
+ * calls error() -> exit(1), messages.f90:27-46).
+ *
+ * Layout: all arrays are Fortran column-major exactly as the reference's module
+ * variables hold them, cell ids are the reference's 1-based ids (virtual cells
+ * n_cells+1..ntot2 for cylindrical/spherical grids, negative ids for Voronoi
+ * walls), wavelength / temperature / grain indices are 1-based.  Fortran
+ * `logical` arrays cross as int32 (0 / non-zero).
+ *
+ * The same structs are consumed by the CPU oracle (oracle/, test infrastructure
+ * only) so that both sides are fed byte-identical inputs.
+ */
+#ifndef MCFOST_B200_H
+#define MCFOST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes ------------------------------------------------------- */
+#define MCB_OK                0
+#define MCB_ERR_NO_DEVICE     1   /* no CUDA device / driver: there is NO CPU fallback */
+#define MCB_ERR_BAD_ARG       2
+#define MCB_ERR_CELL_MAP      3   /* caller's cell_map_{i,j,k} disagree with the analytic numbering */
+#define MCB_ERR_CUDA          4
+#define MCB_ERR_UNSUPPORTED   5   /* a mode flag the library does not implement (yet): fail loudly */
+#define MCB_ERR_STATE         6   /* run called before the uploads it needs */
+
+/* ---- grid kinds (grid.f90:273-367 binds the procedure pointers by kind) */
+#define MCB_GRID_CYL      1   /* lcylindrical, cylindrical_grid.f90 */
+#define MCB_GRID_SPH      2   /* lspherical,   spherical_grid.f90   */
+#define MCB_GRID_VORONOI  3   /* lVoronoi,     Voronoi.f90          */
+
+#define MCB_NANG_SCATT  180   /* nang_scatt, parameters.f90 */
+#define MCB_N_AZ_RT      45   /* n_az_rt, dust_ray_tracing.f90:33 */
+
+typedef struct mcb_handle mcb_handle;   /* opaque; owns all device memory */
+
+/* ------------------------------------------------------------------------
+ * Grid + stars.  Mirrors the module variables of cylindrical_grid.f90:20-41,
+ * Voronoi.f90:23-66 and stars (star(:)%x,y,z,r,icell,out_model).
+ * --------------------------------------------------------------------- */
+typedef struct mcb_grid {
+  int32_t kind;            /* MCB_GRID_* */
+  int32_t l3D;             /* l3D: j runs -nz..-1,1..nz (grid.f90:279-283) */
+  int32_t n_rad, nz, n_az;
+  int32_t n_cells;         /* real cells */
+  double  Rmax2;           /* Rmax**2, cylindrical_grid.f90:254 */
+  double  zmaxmax;         /* maxval(zmax), :494 (cyl only) */
+
+  /* cylindrical / spherical tables */
+  const double *r_lim;          /* (0:n_rad)            */
+  const double *r_lim_2;        /* (0:n_rad)            */
+  const double *r_lim_3;        /* (0:n_rad)  (sph)     */
+  const double *z_lim;          /* (n_rad, nz+2) column-major (cyl) */
+  const double *zmax;           /* (n_rad)              (cyl) */
+  const double *tan_theta_lim;  /* (0:nz)               (sph) */
+  const double *theta_lim;      /* (0:nz)               (sph) */
+  const double *tan_phi_lim;    /* (n_az)               (3D)  */
+  const double *volume;         /* (n_cells)  AU^3      */
+
+  /* optional: the reference's own numbering, used ONLY to verify that the
+   * library's analytic numbering (build_cylindrical_cell_mapping,
+   * cylindrical_grid.f90:45-179) matches; may be NULL. length n_cells_tot */
+  int32_t        n_cells_tot;   /* ntot2 (real + virtual); 0 if maps are NULL */
+  const int32_t *cell_map_i, *cell_map_j, *cell_map_k;
+
+  /* Voronoi (kind==3): Voronoi(:)%xyz,h,first/last_neighbour,flags */
+  const double  *vor_xyz;          /* (3, n_cells) */
+  const double  *vor_h;            /* (n_cells)    */
+  const int32_t *vor_first, *vor_last;   /* (n_cells) 1-based into neighbours_list */
+  const int32_t *vor_was_cut, *vor_is_star, *vor_is_star_neighbour; /* (n_cells) */
+  const int32_t *neighbours_list;  /* 1-based cell ids; <0 = -wall id */
+  int64_t        n_neighbours_tot;
+  float          wall_x[6][4];     /* wall(i)%x1,x2,x3,x4 (real) */
+  double         cutting_distance_o_h;   /* PS%cutting_distance_o_h */
+
+  /* stars */
+  int32_t        n_stars;
+  const double  *star_xyzr;        /* (4, n_stars): x,y,z,r  [AU] */
+  const int32_t *star_icell;       /* (n_stars) star(:)%icell */
+  const int32_t *star_out_model;   /* (n_stars) star(:)%out_model */
+} mcb_grid;
+
+/* ------------------------------------------------------------------------
+ * Dust opacity / scattering / thermal tables.
+ * p_n_cells = n_cells if lvariable_dust else 1 (grid.f90:292-296).
+ * --------------------------------------------------------------------- */
+typedef struct mcb_opacity {
+  int32_t n_lambda;
+  int32_t p_n_cells;
+  int32_t p_n_lambda_pos;     /* n_lambda or 1 (scattering.f90:39-66) */
+  int32_t n_T;
+
+  const double *kappa;            /* (p_n_cells, n_lambda)  AU^-1  dust_prop.f90:17 */
+  const double *kappa_abs_LTE;    /* (p_n_cells, n_lambda)  */
+  const double *kappa_factor;     /* (n_cells)   dust_prop.f90:951-955 */
+  const float  *tab_albedo_pos;   /* (p_n_cells, n_lambda)  grains.f90:62 */
+  const float  *tab_g_pos;        /* (p_n_cells, n_lambda)  */
+
+  /* method-2 scattering tables, (0:180, p_n_cells, p_n_lambda_pos), real */
+  const float *prob_s11_pos;
+  const float *tab_s11_pos;
+  const float *tab_s12_o_s11_pos, *tab_s22_o_s11_pos, *tab_s33_o_s11_pos,
+              *tab_s34_o_s11_pos, *tab_s44_o_s11_pos;   /* NULL unless lsepar_pola */
+
+  /* Bjorkman & Wood tables (thermal_emission.f90:404-644) */
+  const double *log_Qcool_minus_extra_heating;  /* (n_T, p_n_cells) */
+  const double *kdB_dT_CDF;                     /* (n_lambda, n_T, p_n_cells) */
+  const float  *tab_Temp;                       /* (n_T)  Temperature.f90:23-39 */
+  float  T_min;                                 /* parameters: T_min */
+} mcb_opacity;
+
+/* ------------------------------------------------------------------------
+ * Emission tables (repartition_energie thermal_emission.f90:1771,
+ * repartition_wl_em :315, stars.f90:495-605).  Re-uploaded whenever the
+ * Fortran side recomputes them (each temperature iteration / wavelength).
+ * --------------------------------------------------------------------- */
+typedef struct mcb_emission {
+  const double *spectre_emission_cumul;  /* (0:n_lambda)           */
+  const double *frac_E_stars;            /* (n_lambda)             */
+  const double *frac_E_disk;             /* (n_lambda)             */
+  const double *prob_E_cell;             /* (0:n_cells, n_lambda)  */
+  const float  *CDF_E_star;              /* (n_lambda, 0:n_stars)  */
+  double  L_packet_th;                   /* thermal_emission.f90:355-356 */
+  double  E_paquet;                      /* Stokes(1) at emission  */
+  double  R_ISM;                         /* stars.f90:728-787      */
+  double  centre_ISM[3];
+} mcb_emission;
+
+/* ------------------------------------------------------------------------
+ * One mc_photon_loop call.  The six leading members are the subroutine's own
+ * dummy arguments (dust_transfer.f90:439-454); the rest are the module-level
+ * mode flags / scalars it reads.
+ * --------------------------------------------------------------------- */
+typedef struct mcb_run_params {
+  int32_t lambda_in;        /* 1-based */
+  int32_t p_lambda_in;      /* 1-based; frozen for the whole call (:490-502) */
+  int32_t n_photons2;
+  float   n_phot_lim;
+  int32_t nnfot1_start;     /* 1-based first chunk */
+  int32_t laffichage;       /* progress bar: ignored on device */
+
+  int32_t n_photons_loop;   /* 128, read_param.f90:145 */
+  /* mode flags (parameters.f90) */
+  int32_t letape_th, lmono, lmono0;
+  int32_t lscatt_ray_tracing1, lscatt_ray_tracing2;
+  int32_t lsepar_pola, lsepar_contrib;
+  int32_t lscattering_method1;   /* must be 0 (method 2) for now */
+  int32_t lmethod_aniso1;        /* 1: tabulated s11 (Mie), 0: HG */
+  int32_t lisotropic;
+  int32_t l_sym_centrale, l_sym_axiale;
+  int32_t lonly_LTE;             /* must be 1 for now */
+  int32_t lxJ_abs_step1;         /* xJ_abs tally during the thermal step */
+  int32_t lxJ_abs;               /* xJ_abs tally during SED step */
+  /* detectors (read_param.f90:180-184) */
+  int32_t N_thet, N_phi, capt_sup;
+  /* rt1 observer directions (dust_ray_tracing.f90: tab_u_rt etc.) */
+  int32_t RT_n_incl, RT_n_az;
+  const double *tab_u_rt;   /* (RT_n_incl, RT_n_az) */
+  const double *tab_v_rt;   /* (RT_n_incl, RT_n_az) */
+  const double *tab_w_rt;   /* (RT_n_incl)          */
+  /* RNG: Philox4x32-10 key; counter = (draw block, packet id, call_index).
+   * seed defaults to the reference's 269753 (random_numbers.f90:19). */
+  uint64_t seed;
+  uint32_t call_index;      /* distinguishes successive calls (iteration / lambda) */
+  /* multi-GPU: this process handles chunks c with (c-1) % n_ranks == rank and
+   * the running-temperature feedback scales the local tally by n_ranks, like
+   * the reference's x nb_proc (thermal_emission.f90:670). */
+  int32_t rank, n_ranks;
+  int32_t reset_tallies;    /* 1: zero all device tallies before the call */
+} mcb_run_params;
+
+/* ------------------------------------------------------------------------
+ * Tallies returned to the caller (any pointer may be NULL = not wanted).
+ * Shapes are the reference's with the trailing nb_proc dimension removed:
+ * the shim stores them in the id=1 slice and zeroes the others.
+ * --------------------------------------------------------------------- */
+typedef struct mcb_tallies {
+  double  *xKJ_abs;          /* (n_cells)              radiation_field.f90:20 */
+  double  *xJ_abs;           /* (n_cells, n_lambda)    :22 */
+  int32_t *xT_ech;           /* (n_cells)              thermal_emission.f90:49 */
+  double  *n_phot_envoyes;   /* (n_lambda)             */
+  double  *sed, *sed_q, *sed_u, *sed_v, *n_phot_sed;                 /* (n_lambda,N_thet,N_phi) */
+  double  *sed_star, *sed_star_scat, *sed_disk, *sed_disk_scat;      /* output.f90:573-589 */
+  float   *xI_scatt;         /* (45, 2, N_type_flux, RT_n_incl*RT_n_az, n_cells) real, dust_ray_tracing.f90:33 */
+  int32_t  N_type_flux;      /* 1, 4 (pola), 5/8 (contrib) as in the reference */
+  /* diagnostics (not in the reference): */
+  double  *stats;            /* [8]: packets, cell-steps, interactions, scatterings,
+                                absorptions, killed, escaped, dark-zone bounces */
+} mcb_tallies;
+
+/* ---- life cycle -------------------------------------------------------- */
+int  mcfost_b200_init(int device, mcb_handle **h);
+void mcfost_b200_finalize(mcb_handle *h);
+const char *mcfost_b200_last_error(const mcb_handle *h);
+
+int mcfost_b200_upload_grid(mcb_handle *h, const mcb_grid *g);
+/* l_dark_zone(n_cells) (cylindrical_grid.f90:38); may change per wavelength
+ * in SED mode (dust_transfer.f90:919). NULL = no dark zone. */
+int mcfost_b200_upload_dark_zone(mcb_handle *h, const int32_t *l_dark_zone);
+int mcfost_b200_upload_opacity(mcb_handle *h, const mcb_opacity *o);
+int mcfost_b200_upload_emission(mcb_handle *h, const mcb_emission *e);
+
+/* The drop-in for mc_photon_loop: blocking; copies tallies D2H into `out`. */
+int mcfost_b200_run(mcb_handle *h, const mcb_run_params *r, mcb_tallies *out);
+
+/* Split form used for device-timed benchmarking and multi-GPU reductions:
+ * launch only (asynchronous on the handle's stream), expose the packed device
+ * tally buffer (fp64 block then fp32 block) so the host layer can all-reduce
+ * it in place (one NCCL call), then download. */
+int mcfost_b200_launch(mcb_handle *h, const mcb_run_params *r);
+int mcfost_b200_sync(mcb_handle *h);
+int mcfost_b200_tally_buffers(mcb_handle *h, void **d_f64, int64_t *n_f64,
+                              void **d_f32, int64_t *n_f32);
+int mcfost_b200_download(mcb_handle *h, const mcb_run_params *r, mcb_tallies *out);
+/* device time of the last launch in ms (CUDA events on the handle's stream) */
+int mcfost_b200_last_kernel_ms(mcb_handle *h, float *ms);
+/* cudaStream_t of the handle, as an integer, so torch can wait on it */
+int mcfost_b200_stream(mcb_handle *h, uint64_t *stream);
+
+/* ---- deterministic sub-kernels (parity tests; also the building blocks of
+ * define_dark_zone / integ_tau).  One ray per thread.
+ * All arrays are HOST pointers of length n. ------------------------------ */
+/* cross_cell (grid.f90:16-22 procedure pointer): one cell crossing */
+int mcfost_b200_cross_cell(mcb_handle *h, int64_t n,
+        const double *x0, const double *y0, const double *z0,
+        const double *u, const double *v, const double *w,
+        const int32_t *icell, const int32_t *previous_cell,
+        double *x1, double *y1, double *z1, int32_t *next_cell,
+        double *l, double *l_contrib, double *l_void_before);
+/* index_cell: point location */
+int mcfost_b200_index_cell(mcb_handle *h, int64_t n,
+        const double *x, const double *y, const double *z, int32_t *icell);
+/* move_to_grid: entry from outside; x,y,z updated in place */
+int mcfost_b200_move_to_grid(mcb_handle *h, int64_t n,
+        double *x, double *y, double *z,
+        const double *u, const double *v, const double *w,
+        int32_t *icell, int32_t *lintersect);
+/* optical_length_tot (optical_depth.f90:248-324): tau to the grid edge along
+ * fixed rays at wavelength index lambda (1-based) */
+int mcfost_b200_optical_length_tot(mcb_handle *h, int64_t n, int32_t lambda,
+        const double *x, const double *y, const double *z,
+        const double *u, const double *v, const double *w,
+        const int32_t *icell, double *tau_tot, double *lmin, double *lmax,
+        int32_t *n_steps);
+/* physical_length (optical_depth.f90:21-182) with Stokes = 0 (no tallies), as
+ * define_dark_zone uses it (optical_depth.f90:1536): walk to optical depth
+ * tau. x,y,z,u,v,w,icell updated in place like the reference's inout args. */
+int mcfost_b200_physical_length(mcb_handle *h, int64_t n, int32_t lambda,
+        double *x, double *y, double *z, double *u, double *v, double *w,
+        int32_t *icell, const float *tau, float *ltot,
+        int32_t *flag_sortie, int32_t *lpacket_alive);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCFOST_B200_H */

@@ -1,0 +1,630 @@
+"""Synthetic inputs for the photon-packet path.
+
+The reference's own inputs (MCFOST_UTILS optical constants, stellar spectra)
+are not available offline, so the benchmark / parity problems are generated
+here: the *grid* and the *thermal / emission tables* restate the
+reference's setup routines so that the arrays handed across the C ABI have
+exactly the layout and meaning the Fortran side would hand over; the *dust
+optics* are a documented analytic stand-in.
+
+This module is setup code -- it is on neither side of the parity check (both
+the CUDA path and the oracle consume the arrays it produces).
+
+Restated reference routines (paths relative to reference src/):
+  * define_cylindrical_grid            cylindrical_grid.f90:183-676
+  * disk density (power-law Gaussian)  density.f90:58-200
+  * init_lambda                        wavelengths.f90:22-71
+  * init_tab_Temp                      Temperature.f90:23-39
+  * init_reemission                    thermal_emission.f90:404-644
+  * repartition_energie                thermal_emission.f90:1771-1949
+  * repartition_wl_em                  thermal_emission.f90:315-360
+  * calc_local_scattering_matrices     dust_prop.f90:1037-1243 (normalisations)
+  * define_dark_zone                   optical_depth.f90:1425-1651
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+
+import numpy as np
+
+from .abi import MCB_GRID_CYL, MCB_GRID_SPH, MCB_GRID_VORONOI, NANG_SCATT
+
+# constants.f90
+PI = 3.141592653589793238462643383279502884197
+HP = 6.626070040e-34
+KB = 1.38064852e-23
+C_LIGHT = 299792458.0
+THERMAL_CONST = float(np.float32(C_LIGHT * HP / KB))   # `real, parameter :: thermal_const`
+RSUN_TO_AU = 6.957e8 / 149597870700.0
+CUTOFF = 7.0                                           # parameters.f90:111
+
+
+@dataclass
+class DiskZone:
+    """disk_zone_type fields used by the grid / density builders."""
+    rin: float = 1.0
+    rout: float = 300.0
+    edge: float = 0.0
+    sclht: float = 10.0      # scale height at rref [AU]
+    rref: float = 100.0
+    exp_beta: float = 1.125  # flaring exponent
+    surf: float = -0.5       # surface-density exponent
+    dust_mass: float = 1.0e-3
+
+    @property
+    def rmin(self):
+        return self.rin - 5.0 * self.edge
+
+
+class Problem(SimpleNamespace):
+    """Bag of arrays named exactly like the reference's module variables."""
+
+
+# ---------------------------------------------------------------------------
+# grid
+# ---------------------------------------------------------------------------
+def _radial_grid(n_rad, n_rad_in, zones):
+    """tab_r(1:n_rad+1), cylindrical_grid.f90:258-368 (single region, log grid)."""
+    rmin = min(z.rmin for z in zones)
+    rmax = max(z.rout for z in zones)
+    n_rad_in = max(n_rad_in, 1)
+    tab_r = np.zeros(n_rad + 2)  # 1-based
+    R0 = rmin
+    tab_r[1] = R0
+    ln_delta_r = (1.0 / float(n_rad - n_rad_in + 1)) * np.log(rmax / R0)
+    delta_r = np.exp(ln_delta_r)
+    puiss = 0.0
+    for z in zones:
+        p = 1 + z.surf - z.exp_beta
+        if p > puiss:
+            puiss = p
+    if puiss == 0.0:
+        for i in range(2, 2 + n_rad_in):
+            tab_r[i] = np.exp(np.log(R0) - (np.log(R0) - np.log(R0 * delta_r))
+                              * (2.0 ** (i - 1) - 1.0) / (2.0 ** n_rad_in - 1.0))
+    else:
+        for i in range(2, 2 + n_rad_in):
+            tab_r[i] = (R0 ** puiss - (R0 ** puiss - (R0 * delta_r) ** puiss)
+                        * (2.0 ** (i - 1 + 1) - 1.0) / (2.0 ** (n_rad_in + 1) - 1.0)) ** (1.0 / puiss)
+    for i in range(2 + n_rad_in, n_rad + 2):
+        tab_r[i] = tab_r[i - 1] * delta_r
+    return rmin, rmax, tab_r
+
+
+def cell_numbering(n_rad, nz, n_az, l3D):
+    """build_cylindrical_cell_mapping (cylindrical_grid.f90:45-179) in numpy:
+    returns cell_map_i/j/k (1-based ids, length ntot2) -- handed over the ABI so
+    the library can verify its analytic numbering."""
+    j_start = -nz if l3D else 1
+    ci, cj, ck = [], [], []
+    for k in range(1, n_az + 1):
+        for j in range(j_start, nz + 1):
+            if j == 0:
+                continue
+            for i in range(1, n_rad + 1):
+                ci.append(i); cj.append(j); ck.append(k)
+    jstart2 = min(1, j_start) - 1
+    jend2 = nz + 1
+    for k in range(1, n_az + 1):
+        for j in (jstart2, jend2):
+            for i in range(0, n_rad + 2):
+                ci.append(i); cj.append(j); ck.append(k)
+    for k in range(1, n_az + 1):
+        for j in range(j_start, nz + 1):
+            if j == 0:
+                continue
+            for i in (0, n_rad + 1):
+                ci.append(i); cj.append(j); ck.append(k)
+    return (np.array(ci, np.int32), np.array(cj, np.int32), np.array(ck, np.int32))
+
+
+def cylindrical_grid(n_rad=100, nz=70, n_az=1, n_rad_in=20, zones=None, l3D=False):
+    zones = zones or [DiskZone()]
+    P = Problem()
+    P.kind, P.l3D = MCB_GRID_CYL, int(l3D)
+    P.n_rad, P.nz, P.n_az = n_rad, nz, n_az
+    P.n_cells = n_rad * nz * n_az * (2 if l3D else 1)
+    rmin, rmax, tab_r = _radial_grid(n_rad, n_rad_in, zones)
+    P.Rmax2 = rmax * rmax
+    tab_r2 = tab_r * tab_r
+    tab_r3 = tab_r2 * tab_r
+    r_lim = np.zeros(n_rad + 1); r_lim_2 = np.zeros(n_rad + 1); r_lim_3 = np.zeros(n_rad + 1)
+    r_lim[0], r_lim_2[0], r_lim_3[0] = rmin, rmin ** 2, rmin ** 3
+    for i in range(1, n_rad + 1):
+        r_lim[i], r_lim_2[i], r_lim_3[i] = tab_r[i + 1], tab_r2[i + 1], tab_r3[i + 1]
+    P.r_lim, P.r_lim_2, P.r_lim_3 = r_lim, r_lim_2, r_lim_3
+    # zmax, cell_height, z_lim  (:416-494)
+    zmax = np.zeros(n_rad)
+    rcyl_c = np.zeros(n_rad)
+    for i in range(1, n_rad + 1):
+        rcyl = 0.5 * (r_lim[i] + r_lim[i - 1])
+        rcyl_c[i - 1] = rcyl
+        H = 0.0
+        for z in zones:
+            if z.rmin < rcyl < z.rout:
+                hz = z.sclht * (rcyl / z.rref) ** z.exp_beta
+                H = max(H, hz)
+        zmax[i - 1] = CUTOFF * H
+    for i in range(n_rad):          # interpolation between zones (:433-455)
+        if zmax[i] < np.finfo(np.float32).tiny:
+            lo = max(ii for ii in range(i) if zmax[ii] > 0)
+            hi = min(ii for ii in range(i + 1, n_rad) if zmax[ii] > 0)
+            frac = (np.log(rcyl_c[i]) - np.log(rcyl_c[lo])) / (np.log(rcyl_c[hi]) - np.log(rcyl_c[lo]))
+            zmax[i] = np.exp(np.log(zmax[hi]) * frac + np.log(zmax[lo]) * (1.0 - frac))
+    cell_height = zmax / float(np.float32(nz))
+    z_lim = np.zeros((n_rad, nz + 2), order="F")
+    for j in range(1, nz + 1):
+        z_lim[:, j - 1] = (float(j) - 1.0) * cell_height
+    z_lim[:, nz] = zmax
+    z_lim[:, nz + 1] = float(np.float32(1.0e30))
+    P.zmax, P.z_lim, P.zmaxmax = zmax, z_lim, float(zmax.max())
+    # volumes (:479-491, 625): note the routine's local fp32 pi (:191)
+    pi32 = float(np.float32(3.1415926535))
+    V = np.zeros((n_rad, nz))
+    for i in range(1, n_rad + 1):
+        if (tab_r2[i + 1] - tab_r2[i]) > 1.0e-6 * tab_r2[i]:
+            dr2 = 2.0 * pi32 * (tab_r2[i + 1] - tab_r2[i])
+        else:
+            dr2 = 4.0 * pi32 * rcyl_c[i - 1] * (tab_r[i + 1] - tab_r[i])
+        V[i - 1, :] = dr2 * cell_height[i - 1]
+    z_c = z_lim[:, :nz] + 0.5 * cell_height[:, None]
+    if l3D:
+        V = V * 0.5 / float(np.float32(n_az))
+        # tan_phi_lim (:586-600) in fp32 like the reference
+        d_phi = np.float32(2.0) * np.float32(3.1415926535) / np.float32(n_az)
+        tan_phi = np.zeros(n_az)
+        for k in range(1, n_az + 1):
+            phi = np.float32(d_phi * np.float32(k))
+            m = np.float32(np.mod(np.float32(phi - np.float32(0.5) * np.float32(3.1415926535)), np.float32(3.1415926535)))
+            tan_phi[k - 1] = 1.0e300 if abs(m) < 1.0e-6 else float(np.tan(np.float32(phi)))
+        P.tan_phi_lim = tan_phi
+    else:
+        P.tan_phi_lim = np.zeros(max(n_az, 1))
+    ci, cj, ck = cell_numbering(n_rad, nz, n_az, l3D)
+    P.cell_map_i, P.cell_map_j, P.cell_map_k = ci, cj, ck
+    P.n_cells_tot = len(ci)
+    nc = P.n_cells
+    ii, jj, kk = ci[:nc] - 1, cj[:nc], ck[:nc]
+    ja = np.abs(jj) - 1
+    P.volume = V[ii, ja].copy()
+    P.r_grid = rcyl_c[ii].copy()
+    P.z_grid = np.where(jj > 0, z_c[ii, ja], -z_c[ii, ja])
+    dphi = 2.0 * PI / n_az
+    P.phi_grid = (dphi * (kk - 0.5)) if l3D else np.zeros(nc)
+    P.tan_theta_lim = None; P.theta_lim = None
+    P.zones = zones
+    return P
+
+
+def spherical_grid(n_rad=60, nz=30, n_az=1, n_rad_in=5, rin=10.0, rout=200.0, l3D=False):
+    """define_cylindrical_grid, lspherical branch (:496-580), uniform in cos."""
+    zone = DiskZone(rin=rin, rout=rout, surf=-1.0, exp_beta=1.0)
+    P = Problem()
+    P.kind, P.l3D = MCB_GRID_SPH, int(l3D)
+    P.n_rad, P.nz, P.n_az = n_rad, nz, n_az
+    P.n_cells = n_rad * nz * n_az * (2 if l3D else 1)
+    rmin, rmax, tab_r = _radial_grid(n_rad, n_rad_in, [zone])
+    P.Rmax2 = rmax * rmax
+    r_lim = np.zeros(n_rad + 1)
+    r_lim[0] = rmin
+    r_lim[1:] = tab_r[2:n_rad + 2]
+    P.r_lim, P.r_lim_2, P.r_lim_3 = r_lim, r_lim ** 2, r_lim ** 3
+    P.r_lim_2[1:] = (tab_r * tab_r)[2:n_rad + 2]
+    P.r_lim_3[1:] = (tab_r * tab_r * tab_r)[2:n_rad + 2]
+    w_lim = np.zeros(nz + 1); theta_lim = np.zeros(nz + 1); tan_theta_lim = np.zeros(nz + 1)
+    tan_theta_lim[0] = 1.0e-10
+    w_lim[nz] = 1.0; theta_lim[nz] = PI / 2.0; tan_theta_lim[nz] = 1.0e30
+    for j in range(1, nz):
+        w = float(j) / float(nz)
+        w_lim[j] = w
+        c = np.sqrt(1.0 - w * w)
+        tan_theta_lim[j] = w / c
+        theta_lim[j] = np.arctan(tan_theta_lim[j])
+    P.tan_theta_lim, P.theta_lim, P.w_lim = tan_theta_lim, theta_lim, w_lim
+    dcos = 1.0 / float(np.float32(nz))
+    pi32 = float(np.float32(3.1415926535))
+    V = np.zeros((n_rad, nz)); rg = np.zeros((n_rad, nz)); zg = np.zeros((n_rad, nz))
+    tab_r3 = tab_r ** 3
+    for i in range(1, n_rad + 1):
+        rsph = np.sqrt(r_lim[i] * r_lim[i - 1])
+        for j in range(1, nz + 1):
+            w = 0.5 * (w_lim[j] + w_lim[j - 1])
+            rg[i - 1, j - 1] = rsph * np.sqrt(1.0 - w * w)
+            zg[i - 1, j - 1] = rsph * w
+        Vi = 4.0 / 3.0 * pi32 * (tab_r3[i + 1] - tab_r3[i])
+        V[i - 1, :] = Vi * dcos
+    if l3D:
+        V = V * 0.5 / float(np.float32(n_az))
+        d_phi = np.float32(2.0) * np.float32(3.1415926535) / np.float32(n_az)
+        tan_phi = np.zeros(n_az)
+        for k in range(1, n_az + 1):
+            phi = np.float32(d_phi * np.float32(k))
+            m = np.float32(np.mod(np.float32(phi - np.float32(0.5) * np.float32(3.1415926535)), np.float32(3.1415926535)))
+            tan_phi[k - 1] = 1.0e300 if abs(m) < 1.0e-6 else float(np.tan(np.float32(phi)))
+        P.tan_phi_lim = tan_phi
+    else:
+        P.tan_phi_lim = np.zeros(max(n_az, 1))
+    ci, cj, ck = cell_numbering(n_rad, nz, n_az, l3D)
+    P.cell_map_i, P.cell_map_j, P.cell_map_k = ci, cj, ck
+    P.n_cells_tot = len(ci)
+    nc = P.n_cells
+    ii, jj, kk = ci[:nc] - 1, cj[:nc], ck[:nc]
+    ja = np.abs(jj) - 1
+    P.volume = V[ii, ja].copy()
+    P.r_grid = rg[ii, ja].copy()
+    P.z_grid = np.where(jj > 0, zg[ii, ja], -zg[ii, ja])
+    P.phi_grid = np.zeros(nc)
+    P.z_lim = np.zeros((n_rad, nz + 2), order="F"); P.zmax = np.ones(n_rad); P.zmaxmax = 0.0
+    P.zones = [zone]
+    return P
+
+
+# ---------------------------------------------------------------------------
+# physics tables
+# ---------------------------------------------------------------------------
+def init_lambda(n_lambda=50, lambda_min=0.1, lambda_max=3000.0):
+    """wavelengths.f90:41-57 (tab_lambda is `real` in the reference)."""
+    delta = np.exp((1.0 / n_lambda) * np.log(lambda_max / lambda_min))
+    lam = np.zeros(n_lambda); lsup = np.zeros(n_lambda); linf = np.zeros(n_lambda)
+    linf[0] = lambda_min; lam[0] = lambda_min * np.sqrt(delta); lsup[0] = lambda_min * delta
+    for i in range(1, n_lambda):
+        lam[i] = lam[i - 1] * delta
+        lsup[i] = lsup[i - 1] * delta
+        linf[i] = lsup[i - 1]
+    return lam, lsup - linf
+
+
+def init_tab_Temp(n_T=100, T_min=1.0, T_max=3000.0):
+    """Temperature.f90:23-39."""
+    delta_T = np.exp((1.0 / n_T) * np.log(T_max / T_min))
+    t = np.zeros(n_T, np.float32)
+    t[0] = T_min * np.sqrt(delta_T)
+    for k in range(1, n_T):
+        t[k] = np.float32(delta_T * t[k - 1])
+    return t
+
+
+def disk_density(P, zones):
+    """Power-law Gaussian disk, density.f90:147-185 evaluated at cell centres,
+    normalised to the zone dust mass (arbitrary units: only ratios are used)."""
+    rho = np.zeros(P.n_cells)
+    for z in zones:
+        r, zz = P.r_grid, P.z_grid
+        fact = (r / z.rref) ** (z.surf - z.exp_beta)
+        coeff = 2.0 * (r / z.rref) ** (2 * z.exp_beta)
+        d = fact * np.exp(-((zz / z.sclht) ** 2) / coeff)
+        d = np.where((r > z.rout) | (r < z.rmin), 0.0, d)
+        m = float(np.sum(d * P.volume))
+        rho += d * (z.dust_mass / m)
+    return rho
+
+
+def synthetic_optics(lam, pola=True, isotropic=False):
+    """Documented stand-in for Mie theory on Draine silicates:
+    kappa_ext ~ 1/lambda beyond 1 um (flat below), albedo 0.5 -> 0 across
+    1-100 um, HG asymmetry 0.6 -> 0, Mueller matrix = HG s11 x Rayleigh-like
+    polarisation.  Returned per wavelength, unit extinction at lambda <= 1 um."""
+    n = len(lam)
+    kext = np.where(lam > 1.0, 1.0 / lam, 1.0)
+    x = np.clip(np.log10(np.maximum(lam, 1.0)) / 2.0, 0.0, 1.0)
+    albedo = 0.5 * (1.0 - x)
+    g = 0.0 * lam if isotropic else 0.6 * (1.0 - x)
+    theta = np.arange(NANG_SCATT + 1) * PI / NANG_SCATT
+    mu = np.cos(theta)
+    s11 = np.zeros((NANG_SCATT + 1, n))
+    for l in range(n):
+        s11[:, l] = (1.0 - g[l] ** 2) * (1.0 + g[l] ** 2 - 2.0 * g[l] * mu) ** (-1.5)
+    pmax = 0.4
+    s12_o = -pmax * (1.0 - mu * mu) / (1.0 + mu * mu)
+    s22_o = np.ones_like(mu)
+    s33_o = 2.0 * mu / (1.0 + mu * mu)
+    s34_o = 0.1 * np.sin(theta) ** 2 * mu      # small circular-polarisation term so V is exercised
+    s44_o = s33_o.copy()
+    return kext, albedo, g, s11, (s12_o, s22_o, s33_o, s34_o, s44_o) if pola else None
+
+
+def scattering_tables(P, s11, albedo, kappa, pola_tabs):
+    """calc_local_scattering_matrices normalisations, dust_prop.f90:1141-1178,
+    for p_n_cells = 1 and p_n_lambda_pos = n_lambda."""
+    n_lambda = s11.shape[1]
+    dtheta = PI / float(np.float32(NANG_SCATT))
+    theta = np.arange(NANG_SCATT + 1, dtype=np.float64)
+    theta = np.float32(theta).astype(np.float64) * dtheta
+    prob = np.zeros((NANG_SCATT + 1, 1, n_lambda), np.float32, order="F")
+    tab = np.zeros((NANG_SCATT + 1, 1, n_lambda), np.float32, order="F")
+    for l in range(n_lambda):
+        ksca = float(kappa[l] * albedo[l])
+        s = s11[:, l].astype(np.float64)
+        if ksca > float(np.finfo(np.float32).tiny):
+            norm = np.sum(s[1:NANG_SCATT] * np.sin(theta[1:NANG_SCATT]) * dtheta)
+            s = (s * ksca / norm).astype(np.float32)      # tab_s11_pos normalised to k_sca_tot
+            p = np.zeros(NANG_SCATT + 1, np.float32)
+            for a in range(2, NANG_SCATT + 1):
+                p[a] = np.float32(p[a - 1] + np.float32(float(s[a]) * np.sin(theta[a]) * dtheta))
+            p[1:] = np.float32(p[1:] + np.float32(ksca - float(p[NANG_SCATT])))
+            p = np.float32(p / np.float32(ksca))
+            prob[:, 0, l] = p
+            tab[:, 0, l] = np.float32(s.astype(np.float64) * dtheta / (ksca * 2.0 * PI))
+        else:
+            prob[:, 0, l] = 1.0
+            prob[0, 0, l] = 0.0
+            tab[:, 0, l] = 1.0
+    out = dict(prob_s11_pos=prob, tab_s11_pos=tab)
+    names = ("tab_s12_o_s11_pos", "tab_s22_o_s11_pos", "tab_s33_o_s11_pos", "tab_s34_o_s11_pos", "tab_s44_o_s11_pos")
+    for nm, t in zip(names, pola_tabs or [None] * 5):
+        if t is None:
+            out[nm] = None
+        else:
+            a = np.zeros((NANG_SCATT + 1, 1, n_lambda), np.float32, order="F")
+            a[:, 0, :] = np.float32(t)[:, None]
+            out[nm] = a
+    return out
+
+
+def init_reemission(P):
+    """thermal_emission.f90:404-550 (high-memory LTE branch, no extra heating)."""
+    n_T, n_lambda, pnc = P.n_T, P.n_lambda, P.p_n_cells
+    cst_E = 2.0 * HP * C_LIGHT ** 2 * 4.0 * PI
+    wl = P.tab_lambda * 1.0e-6
+    dwl = P.tab_delta_lambda * 1.0e-6
+    B = np.zeros((n_lambda, n_T)); dB = np.zeros((n_lambda, n_T))
+    for t in range(n_T):
+        cst = THERMAL_CONST / float(P.tab_Temp[t])
+        cst_wl = cst / wl
+        ok = cst_wl < 500.0
+        ce = np.exp(np.where(ok, cst_wl, 1.0))
+        b = np.where(ok, 1.0 / ((wl ** 5) * (ce - 1.0)) * dwl, 0.0)
+        B[:, t] = b
+        dB[:, t] = np.where(ok, b * cst_wl * ce / (ce - 1.0), 0.0)
+    logQ = np.zeros((n_T, pnc), order="F")
+    cdf = np.zeros((n_lambda, n_T, pnc), order="F")
+    kabs = P.kappa_abs_LTE.reshape(pnc, n_lambda)
+    tiny_dp = np.finfo(np.float64).tiny
+    for ic in range(pnc):
+        Qcool0 = 0.0
+        for t in range(n_T):
+            integ = 0.0
+            for l in range(n_lambda):
+                integ = integ + kabs[ic, l] * B[l, t]
+            Qcool = integ * cst_E
+            if t == 0:
+                Qcool0 = Qcool
+            q = Qcool - Qcool0
+            logQ[t, ic] = np.log(q) if q > tiny_dp else -1000.0
+            integ3 = np.zeros(n_lambda + 1)
+            for l in range(1, n_lambda + 1):
+                integ3[l] = integ3[l - 1] + kabs[ic, l - 1] * dB[l - 1, t]
+            if integ3[n_lambda] > tiny_dp:
+                cdf[:, t, ic] = integ3[1:] / integ3[n_lambda]
+    P.log_Qcool_minus_extra_heating = logQ
+    P.kdB_dT_CDF = cdf
+    return P
+
+
+def star_energy(P):
+    """Blackbody branch of stars.f90:549-556 + :581-605 (E_stars, CDF_E_star)."""
+    wl = P.tab_lambda * 1.0e-6
+    n_stars = P.n_stars
+    prob = np.zeros((P.n_lambda, n_stars))
+    for i in range(n_stars):
+        surface = 4.0 * PI * P.star_xyzr[3, i] ** 2
+        cst_wl = THERMAL_CONST / (P.star_T[i] * wl)
+        tiny32 = float(np.finfo(np.float32).tiny)
+        prob[:, i] = np.where(cst_wl < 500.0, surface / ((wl ** 5) * (np.exp(np.minimum(cst_wl, 500.0)) - 1.0)), tiny32)
+    cdf = np.zeros((P.n_lambda, n_stars + 1), np.float32, order="F")
+    for i in range(n_stars):
+        cdf[:, i + 1] = np.float32(cdf[:, i] + np.float32(prob[:, i]))
+    P.E_stars = cdf[:, n_stars].astype(np.float64)        # `real` E_stars
+    P.CDF_E_star = np.asfortranarray(cdf / cdf[:, n_stars:n_stars + 1])
+    return P
+
+
+def repartition_energie(P, Tdust=None):
+    """thermal_emission.f90:1771-1949 (LTE only) for every wavelength, then
+    repartition_wl_em (:315-360).  Tdust defaults to reset_temperature's 1 K."""
+    nc, nl = P.n_cells, P.n_lambda
+    Tdust = np.ones(nc) if Tdust is None else np.asarray(Tdust, np.float64)
+    wl = P.tab_lambda * 1.0e-6
+    cst_wl_max = float(np.float32(np.log(np.finfo(np.float32).max) - 1.0e-4))
+    kabs = P.kappa_abs_LTE.reshape(P.p_n_cells, nl)
+    dark = P.l_dark_zone.astype(bool)
+    prob = np.zeros((nc + 1, nl), order="F")
+    E_disk = np.zeros(nl)
+    for l in range(nl):
+        cst = THERMAL_CONST / (np.maximum(Tdust, 1e-300) * wl[l])
+        k = kabs[:, l] if P.p_n_cells > 1 else kabs[0, l]
+        ok = (~dark) & (Tdust >= float(np.finfo(np.float32).tiny)) & (cst < cst_wl_max)
+        E = np.where(ok, 4.0 * k * P.kappa_factor * P.volume / ((wl[l] ** 5) * (np.exp(np.where(ok, cst, 1.0)) - 1.0)), 0.0)
+        E_disk[l] = E.sum()
+        c = np.concatenate(([0.0], np.cumsum(E)))
+        prob[:, l] = c / c[nc] if c[nc] > np.finfo(np.float64).tiny else 0.0
+    E_ISM = np.zeros(nl)
+    tot = P.E_stars + E_disk + E_ISM
+    P.E_disk = E_disk
+    P.frac_E_stars = P.E_stars / tot
+    P.frac_E_disk = (P.E_stars + E_disk) / tot
+    P.prob_E_cell = prob
+    dwl = P.tab_delta_lambda * 1.0e-6
+    cum = np.concatenate(([0.0], np.cumsum(tot * dwl)))
+    P.spectre_emission_cumul = cum / cum[nl]
+    L_tot = 2.0 * PI * HP * C_LIGHT ** 2 * float(np.sum(tot * dwl))
+    P.L_tot = L_tot
+    P.L_packet_th = L_tot / float(np.float32(P.n_photons_loop) * np.float32(P.n_photons_eq_th))
+    return P
+
+
+def define_dark_zone(P, lambda_idx, tau_max=1500.0, physical_length=None):
+    """optical_depth.f90:1425-1651 for the 2D cylindrical case.
+
+    Step 4 of the reference shoots 11 rays per cell with physical_length();
+    ``physical_length`` is a callable implementing that walk (the CUDA library's
+    deterministic kernel in production, the oracle in CPU tests):
+        physical_length(lambda_1based, x,y,z,u,v,w, icell, tau, dark) ->
+            flag_sortie (bool array)
+    With ``physical_length=None`` only steps 1-3 are applied and a cell is dark
+    if it is deeper than tau_max radially (both ways) and vertically (a
+    conservative superset check used for quick tests)."""
+    n_rad, nz = P.n_rad, P.nz
+    assert P.kind == MCB_GRID_CYL and not P.l3D
+    kap = P.kappa.reshape(P.p_n_cells, P.n_lambda)[0, lambda_idx - 1] * P.kappa_factor   # (n_cells)
+    cm = lambda i, j: (i - 1) + n_rad * (j - 1)      # 0-based id of real cell (i,j)
+    ri_in, ri_out = n_rad, 1
+    s = 0.0
+    for i in range(1, n_rad + 1):
+        s += kap[cm(i, 1)] * (P.r_lim[i] - P.r_lim[i - 1])
+        if s > tau_max:
+            ri_in = i
+            break
+    s = 0.0
+    for i in range(n_rad, 0, -1):
+        s += kap[cm(i, 1)] * (P.r_lim[i] - P.r_lim[i - 1])
+        if s > tau_max:
+            ri_out = i
+            break
+    if ri_out == n_rad:
+        ri_out = n_rad - 1
+    zj_sup = np.zeros(n_rad + 1, np.int64)
+    for i in range(ri_in, ri_out + 1):
+        s = 0.0
+        for j in range(nz, 0, -1):
+            s += kap[cm(i, j)] * (P.z_lim[i - 1, j] - P.z_lim[i - 1, j - 1])
+            if s > tau_max:
+                zj_sup[i] = j
+                break
+    dark = np.zeros(P.n_cells, np.int32)
+    nb_angle = 11
+    for i in range(max(ri_in, 2), ri_out + 1):
+        top = int(zj_sup[i])
+        if top < 1:
+            continue
+        if physical_length is None:
+            for j in range(top, 0, -1):
+                dark[cm(i, j)] = 1
+            continue
+        js = np.arange(top, 0, -1)
+        ic = np.array([cm(i, j) for j in js])
+        ang = np.float32(PI) * (np.arange(1, nb_angle + 1, dtype=np.float32) / np.float32(nb_angle + 1))   # `real :: angle`
+        x0 = np.repeat(P.r_grid[ic], nb_angle); z0 = np.repeat(P.z_grid[ic], nb_angle)
+        u0 = np.tile(np.cos(ang).astype(np.float64), len(js)); w0 = np.tile(np.sin(ang).astype(np.float64), len(js))
+        y0 = np.zeros_like(x0); v0 = np.zeros_like(x0)
+        icell = np.repeat(ic + 1, nb_angle).astype(np.int32)
+        sortie = physical_length(lambda_idx, x0, y0, z0, u0, v0, w0, icell, np.full(len(x0), tau_max, np.float32), dark)
+        sortie = np.asarray(sortie, bool).reshape(len(js), nb_angle)
+        trapped = ~sortie.all(axis=1)
+        if trapped.any():
+            jtop = js[np.argmax(trapped)]            # first (highest) j with a non-exiting ray
+            for jj in range(1, jtop + 1):
+                dark[cm(i, jj)] = 1
+    # region edges are never dark (:1640-1645)
+    for j in range(1, nz + 1):
+        dark[cm(1, j)] = 0
+        dark[cm(n_rad, j)] = 0
+    return dark
+
+
+# ---------------------------------------------------------------------------
+# the benchmark configurations
+# ---------------------------------------------------------------------------
+def _finish(P, zones, n_lambda, n_T, tau_mid, pola, isotropic, n_photons_eq_th, star_T, star_R):
+    P.n_lambda, P.n_T = n_lambda, n_T
+    P.tab_lambda, P.tab_delta_lambda = init_lambda(n_lambda)
+    P.tab_lambda = np.float32(P.tab_lambda).astype(np.float64)          # `real` tables in the reference
+    P.tab_delta_lambda = np.float32(P.tab_delta_lambda).astype(np.float64)
+    P.T_min, P.T_max = 1.0, 3000.0
+    P.tab_Temp = init_tab_Temp(n_T, P.T_min, P.T_max)
+    P.n_photons_loop, P.n_photons_eq_th = 128, n_photons_eq_th
+    # star at the origin (inside the inner edge => virtual cell (0,1,1))
+    P.n_stars = 1
+    P.star_xyzr = np.asfortranarray(np.array([[0.0], [0.0], [0.0], [star_R * RSUN_TO_AU]]))
+    P.star_T = np.array([star_T])
+    P.star_out_model = np.zeros(1, np.int32)
+    # density and opacities (lvariable_dust = .false. => p_n_cells = 1)
+    rho = disk_density(P, zones)
+    P.p_n_cells, P.p_n_lambda_pos = 1, n_lambda
+    rho0 = rho[0]
+    P.kappa_factor = rho / rho0
+    kext, albedo, g, s11, pol = synthetic_optics(P.tab_lambda, pola=pola, isotropic=isotropic)
+    # scale so that the radial midplane optical depth at 0.81 um is tau_mid
+    l_seuil = int(np.argmax(P.tab_lambda > 0.81)) + 1
+    P.lambda_seuil = l_seuil
+    if P.kind == MCB_GRID_CYL:
+        mid = np.array([(i - 1) + P.n_rad * (0 if not P.l3D else P.nz) for i in range(1, P.n_rad + 1)])
+    else:
+        mid = np.arange(P.n_rad)
+    col = float(np.sum(P.kappa_factor[mid] * (P.r_lim[1:] - P.r_lim[:-1])))
+    k0 = tau_mid / (col * kext[l_seuil - 1])
+    P.kappa = np.asfortranarray((k0 * kext).reshape(1, n_lambda))
+    P.tab_albedo_pos = np.asfortranarray(np.float32(albedo).reshape(1, n_lambda))
+    P.tab_g_pos = np.asfortranarray(np.float32(g).reshape(1, n_lambda))
+    P.kappa_abs_LTE = np.asfortranarray(P.kappa * (1.0 - P.tab_albedo_pos.astype(np.float64)))
+    for k, v in scattering_tables(P, s11, albedo, P.kappa[0], pol).items():
+        setattr(P, k, v)
+    init_reemission(P)
+    star_energy(P)
+    P.l_dark_zone = np.zeros(P.n_cells, np.int32)
+    P.E_paquet = 1.0
+    P.R_ISM = 0.0
+    P.centre_ISM = (0.0, 0.0, 0.0)
+    return P
+
+
+def locate_stars(P, index_cell):
+    """stars_cell_indices (stars.f90:789-808): star(:)%icell via index_cell.
+    ``index_cell(x,y,z) -> 1-based ids`` comes from whichever side is being set up."""
+    xyz = P.star_xyzr
+    P.star_icell = np.asarray(index_cell(xyz[0].copy(), xyz[1].copy(), xyz[2].copy()), np.int32)
+    return P
+
+
+def star_icell_analytic(P):
+    """For a star at the origin inside r_lim(0): the virtual cell (0,1,1) =
+    first virtual id of the numbering (cylindrical_grid.f90:123-141)."""
+    nj = 2 * P.nz if P.l3D else P.nz
+    if P.l3D:
+        # j = -nz-1 row comes first, then j = nz+1 row: (0, 1, 1) is in neither; it is in
+        # the second virtual block (i in {0, n_rad+1}, j over real rows)
+        base = P.n_cells + 2 * (P.n_rad + 2) * P.n_az
+        return base + 2 * P.nz + 1          # j=-nz..-1 (2 ids each) then j=1, i=0
+    base = P.n_cells + 2 * (P.n_rad + 2) * P.n_az
+    return base + 1                         # j=1, i=0
+
+
+def ref41_like(n_photons_eq_th=1000, tau_mid=1.0e5, pola=True, n_rad=100, nz=70, n_rad_in=20,
+               n_lambda=50, n_T=100, dark_zone=True, physical_length=None, isotropic=False):
+    """G1: ref4.1.para geometry (cylindrical 100x70x1, disk 1-300 AU, H=10 AU at
+    100 AU, beta=1.125, p=-0.5, star 5000 K / 2 Rsun blackbody, 50 wavelengths
+    0.1-3000 um, n_T=100) with the synthetic optics."""
+    zones = [DiskZone()]
+    P = cylindrical_grid(n_rad, nz, 1, n_rad_in, zones, l3D=False)
+    _finish(P, zones, n_lambda, n_T, tau_mid, pola, isotropic, n_photons_eq_th, 5000.0, 2.0)
+    P.star_icell = np.array([star_icell_analytic(P)], np.int32)
+    if dark_zone:
+        P.l_dark_zone = define_dark_zone(P, P.lambda_seuil, 1500.0, physical_length)
+    repartition_energie(P)
+    P.name = "ref4.1-like (G1)"
+    return P
+
+
+def ref41_3d_like(n_photons_eq_th=1000, tau_mid=1.0e3, n_rad=100, nz=50, n_az=72, n_rad_in=20,
+                  n_lambda=50, n_T=100, pola=False):
+    """G4: ref4.1_3D.para geometry: 100 x (2x50) x 72 = 720 000 cells, no dark zone
+    (dust_transfer.f90:290-293)."""
+    zones = [DiskZone()]
+    P = cylindrical_grid(n_rad, nz, n_az, n_rad_in, zones, l3D=True)
+    _finish(P, zones, n_lambda, n_T, tau_mid, pola, False, n_photons_eq_th, 5000.0, 2.0)
+    P.star_icell = np.array([star_icell_analytic(P)], np.int32)
+    repartition_energie(P)
+    P.name = "ref4.1_3D-like (G4)"
+    return P
+
+
+def spherical_shell(n_photons_eq_th=1000, tau_mid=10.0, n_rad=60, nz=30, n_az=1, l3D=False,
+                    n_lambda=50, n_T=100, pola=False, isotropic=False):
+    """debris.para-style spherical grid (test_data/debris/debris.para:15)."""
+    P = spherical_grid(n_rad, nz, n_az, 5, 10.0, 200.0, l3D=l3D)
+    _finish(P, P.zones, n_lambda, n_T, tau_mid, pola, isotropic, n_photons_eq_th, 5000.0, 2.0)
+    P.star_icell = np.array([star_icell_analytic(P)], np.int32)
+    repartition_energie(P)
+    P.name = "spherical shell"
+    return P

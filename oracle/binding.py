@@ -1,0 +1,173 @@
+"""ctypes binding of the CPU oracle (oracle/oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  Nothing under mcfost_b200/
+imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from mcfost_b200 import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD = os.path.join(HERE, "_build")
+
+
+def build(fast_native=False):
+    """Compile the oracle (g++).  fast_native=True rebuilds the timing flavour
+    with -march=native on the machine that will run it."""
+    args = ["make", "-s", "-C", HERE]
+    if fast_native:
+        subprocess.run(["rm", "-f", os.path.join(BUILD, "liboracle_fast.so")], check=False)
+        args.append("MARCH=-march=native")
+    subprocess.run(args, check=True)
+
+
+def _load(name):
+    path = os.path.join(BUILD, name)
+    if not os.path.exists(path):
+        build()
+    lib = C.CDLL(path)
+    lib.oracle_create.restype = C.c_void_p
+    lib.oracle_last_error.restype = C.c_char_p
+    lib.oracle_last_error.argtypes = [C.c_void_p]
+    for fn in ("oracle_destroy", "oracle_set_grid", "oracle_set_dark_zone", "oracle_set_opacity",
+               "oracle_set_emission", "oracle_n_cells_tot"):
+        getattr(lib, fn).argtypes = [C.c_void_p] + ([C.c_void_p] if fn not in ("oracle_destroy", "oracle_n_cells_tot") else [])
+    lib.oracle_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """Reference-order CPU implementation of mc_photon_loop and its callees."""
+
+    def __init__(self, P, fast=False):
+        self.lib = _load("liboracle_fast.so" if fast else "liboracle.so")
+        self.h = C.c_void_p(self.lib.oracle_create())
+        self.P = P
+        self._g = abi.make_grid(P)
+        self._o = abi.make_opacity(P)
+        self._e = abi.make_emission(P) if hasattr(P, "prob_E_cell") else None
+        self._check(self.lib.oracle_set_grid(self.h, self._g.ref()))
+        self._check(self.lib.oracle_set_opacity(self.h, self._o.ref()))
+        if self._e is not None:
+            self._check(self.lib.oracle_set_emission(self.h, self._e.ref()))
+        self.set_dark_zone(getattr(P, "l_dark_zone", None))
+
+    def __del__(self):
+        try:
+            self.lib.oracle_destroy(self.h)
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"oracle error {rc}: {self.lib.oracle_last_error(self.h).decode()}")
+
+    def set_dark_zone(self, dz):
+        self._dz = None if dz is None else np.ascontiguousarray(dz, np.int32)
+        self._check(self.lib.oracle_set_dark_zone(self.h, _p(self._dz)))
+
+    def set_emission(self, P):
+        self._e = abi.make_emission(P)
+        self._check(self.lib.oracle_set_emission(self.h, self._e.ref()))
+
+    @property
+    def n_cells_tot(self):
+        return self.lib.oracle_n_cells_tot(self.h)
+
+    def cell_maps(self):
+        n = self.n_cells_tot
+        ci, cj, ck, le = (np.zeros(n, np.int32) for _ in range(4))
+        self.lib.oracle_get_cell_maps(self.h, _p(ci), _p(cj), _p(ck), _p(le))
+        return ci, cj, ck, le
+
+    # ---- mc_photon_loop ---------------------------------------------------
+    def run(self, n_threads=0, rec=None, n_xI=0, xJ=False, **params):
+        r = abi.make_run(**params)
+        P = self.P
+        t = abi.Tallies(P.n_cells, P.n_lambda, r.struct.N_thet, r.struct.N_phi, xJ=xJ, n_xI=n_xI)
+        rec_a = None if rec is None else np.ascontiguousarray(rec, np.float64)
+        self._check(self.lib.oracle_run(self.h, r.ref(), t.ref(), int(n_threads), _p(rec_a),
+                                        0 if rec_a is None else len(rec_a)))
+        return t
+
+    # ---- deterministic sub-kernels ----------------------------------------
+    @staticmethod
+    def _f64(*arrs):
+        return [np.ascontiguousarray(a, np.float64).copy() for a in arrs]
+
+    def cross_cell(self, x0, y0, z0, u, v, w, icell, previous_cell=None):
+        x0, y0, z0, u, v, w = self._f64(x0, y0, z0, u, v, w)
+        n = len(x0)
+        icell = np.ascontiguousarray(icell, np.int32)
+        prev = np.zeros(n, np.int32) if previous_cell is None else np.ascontiguousarray(previous_cell, np.int32)
+        x1, y1, z1, l, lc, lv = (np.zeros(n) for _ in range(6))
+        nxt = np.zeros(n, np.int32)
+        self._check(self.lib.oracle_cross_cell(self.h, C.c_int64(n), _p(x0), _p(y0), _p(z0), _p(u), _p(v), _p(w),
+                                               _p(icell), _p(prev), _p(x1), _p(y1), _p(z1), _p(nxt), _p(l), _p(lc), _p(lv)))
+        return dict(x1=x1, y1=y1, z1=z1, next_cell=nxt, l=l, l_contrib=lc, l_void_before=lv)
+
+    def index_cell(self, x, y, z):
+        x, y, z = self._f64(x, y, z)
+        ic = np.zeros(len(x), np.int32)
+        self._check(self.lib.oracle_index_cell(self.h, C.c_int64(len(x)), _p(x), _p(y), _p(z), _p(ic)))
+        return ic
+
+    def move_to_grid(self, x, y, z, u, v, w):
+        x, y, z, u, v, w = self._f64(x, y, z, u, v, w)
+        n = len(x)
+        ic = np.zeros(n, np.int32); li = np.zeros(n, np.int32)
+        self._check(self.lib.oracle_move_to_grid(self.h, C.c_int64(n), _p(x), _p(y), _p(z), _p(u), _p(v), _p(w), _p(ic), _p(li)))
+        return dict(x=x, y=y, z=z, icell=ic, lintersect=li)
+
+    def optical_length_tot(self, lam, x, y, z, u, v, w, icell):
+        x, y, z, u, v, w = self._f64(x, y, z, u, v, w)
+        n = len(x)
+        icell = np.ascontiguousarray(icell, np.int32)
+        tau, lmin, lmax = (np.zeros(n) for _ in range(3))
+        ns = np.zeros(n, np.int32)
+        self._check(self.lib.oracle_optical_length_tot(self.h, C.c_int64(n), C.c_int32(lam), _p(x), _p(y), _p(z), _p(u), _p(v), _p(w),
+                                                       _p(icell), _p(tau), _p(lmin), _p(lmax), _p(ns)))
+        return dict(tau_tot=tau, lmin=lmin, lmax=lmax, n_steps=ns)
+
+    def physical_length(self, lam, x, y, z, u, v, w, icell, tau, dark=None):
+        if dark is not None:
+            self.set_dark_zone(dark)
+        x, y, z, u, v, w = self._f64(x, y, z, u, v, w)
+        n = len(x)
+        icell = np.ascontiguousarray(icell, np.int32).copy()
+        tau = np.ascontiguousarray(tau, np.float32)
+        ltot = np.zeros(n, np.float32); fs = np.zeros(n, np.int32); alive = np.zeros(n, np.int32)
+        self._check(self.lib.oracle_physical_length(self.h, C.c_int64(n), C.c_int32(lam), _p(x), _p(y), _p(z), _p(u), _p(v), _p(w),
+                                                    _p(icell), _p(tau), _p(ltot), _p(fs), _p(alive)))
+        return dict(x=x, y=y, z=z, u=u, v=v, w=w, icell=icell, ltot=ltot, flag_sortie=fs, lpacket_alive=alive)
+
+    def dark_zone_walker(self):
+        """Callable for synthetic.define_dark_zone (step 4 ray walk)."""
+        def walk(lam, x, y, z, u, v, w, icell, tau, dark):
+            return self.physical_length(lam, x, y, z, u, v, w, icell, tau, dark)["flag_sortie"].astype(bool)
+        return walk
+
+
+def philox(ctr, key):
+    lib = _load("liboracle.so")
+    c = np.asarray(ctr, np.uint32); k = np.asarray(key, np.uint32); o = np.zeros(4, np.uint32)
+    lib.oracle_philox(_p(c), _p(k), _p(o))
+    return o
+
+
+def rng_stream(seed, call_index, packet, n):
+    lib = _load("liboracle.so")
+    o = np.zeros(n)
+    lib.oracle_rng_stream(C.c_uint64(seed), C.c_uint32(call_index), C.c_uint64(packet), C.c_int(n), _p(o))
+    return o

@@ -1,0 +1,76 @@
+/*
+ * ORACLE (test infrastructure only -- never linked into the product path).
+ *
+ * Philox4x32-10 counter-based RNG (Salmon et al., SC'11, "Parallel random
+ * numbers: as easy as 1, 2, 3"; Random123 v1.09).  Replaces the reference's
+ * SPRNG 2.0b 64-bit LCG streams (random_numbers.f90:19-30, one stream per
+ * OpenMP thread, dust_transfer.f90:125-128): sequence parity with SPRNG is a
+ * stated non-goal (BASELINE.json north_star), so the oracle and the CUDA path
+ * both use this generator, keyed per packet, which makes packet trajectories
+ * reproducible and independent of thread / GPU count.
+ *
+ * Stream definition (shared with mcfost_b200/csrc/philox.cuh):
+ *   key     = (seed_lo, seed_hi)
+ *   counter = (block, packet_lo, packet_hi, call_index)
+ *   packet  = (chunk-1) * 2^40 + index_in_chunk (0-based)
+ *   each 128-bit block yields two uniform doubles in [0,1):
+ *       d0 = ((w1 >> 5) * 2^26 + (w0 >> 6)) * 2^-53,  d1 likewise from (w3, w2)
+ *   which the callers cast to fp32 exactly where the reference assigns
+ *   sprng() to a `real` (so rand can round to 1.0, dust_transfer.f90:1209).
+ */
+#ifndef ORACLE_PHILOX_H
+#define ORACLE_PHILOX_H
+#include <stdint.h>
+
+static inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+  uint32_t k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)M0 * c0;
+    uint64_t p1 = (uint64_t)M1 * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+static inline double philox_u01(uint32_t lo, uint32_t hi) {
+  return (double)(((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+typedef struct PacketRng {
+  /* recorded stream (deterministic unit tests): if rec != 0, values are
+     replayed cyclically instead of generated */
+  const double *rec;
+  int64_t n_rec, i_rec;
+  uint32_t key[2];
+  uint32_t ctr[4];     /* ctr[0] = next block index */
+  double   spare;
+  int      have_spare;
+  int64_t  n_draws;
+} PacketRng;
+
+static inline void rng_seed_packet(PacketRng *g, uint64_t seed, uint32_t call_index, uint64_t packet) {
+  g->key[0] = (uint32_t)seed; g->key[1] = (uint32_t)(seed >> 32);
+  g->ctr[0] = 0; g->ctr[1] = (uint32_t)packet; g->ctr[2] = (uint32_t)(packet >> 32); g->ctr[3] = call_index;
+  g->have_spare = 0; g->n_draws = 0;
+}
+
+/* the analogue of sprng(stream(id)): a double in [0,1) */
+static inline double rng_next(PacketRng *g) {
+  g->n_draws++;
+  if (g->rec) { double v = g->rec[g->i_rec % g->n_rec]; g->i_rec++; return v; }
+  if (g->have_spare) { g->have_spare = 0; return g->spare; }
+  uint32_t o[4];
+  philox4x32_10(g->ctr, g->key, o);
+  g->ctr[0]++;
+  g->spare = philox_u01(o[2], o[3]);
+  g->have_spare = 1;
+  return philox_u01(o[0], o[1]);
+}
+#endif
