@@ -1,0 +1,244 @@
+"""Host-side mirror of the reference interface for the photon-packet path.
+
+``PhotonLoop.mc_photon_loop(lambda_in, p_lambda_in, n_photons2, n_phot_lim,
+nnfot1_start, laffichage)`` has the reference's own argument list
+(src/dust_transfer.f90:439-454); the module-level state the Fortran routine
+reads (grid, opacity and emission tables, mode flags) is the ``Problem`` object
+plus keyword flags.  Everything is executed by the CUDA library through the C
+ABI of include/mcfost_b200.h -- there is no CPU fallback: if the shared library
+or a CUDA device is missing, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libmcfost_b200.so")
+
+# every symbol include/mcfost_b200.h declares
+EXPORTS = (
+    "mcfost_b200_init", "mcfost_b200_finalize", "mcfost_b200_last_error",
+    "mcfost_b200_upload_grid", "mcfost_b200_upload_dark_zone", "mcfost_b200_upload_opacity",
+    "mcfost_b200_upload_emission", "mcfost_b200_run", "mcfost_b200_launch", "mcfost_b200_sync",
+    "mcfost_b200_tally_buffers", "mcfost_b200_download", "mcfost_b200_last_kernel_ms", "mcfost_b200_stream",
+    "mcfost_b200_cross_cell", "mcfost_b200_index_cell", "mcfost_b200_move_to_grid",
+    "mcfost_b200_optical_length_tot", "mcfost_b200_physical_length",
+)
+
+
+class McfostB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mcfost_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the CUDA library; raises if it was not built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise McfostB200Error(-1, f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = C.CDLL(LIB_PATH)
+        lib.mcfost_b200_last_error.restype = C.c_char_p
+        lib.mcfost_b200_last_error.argtypes = [C.c_void_p]
+        lib.mcfost_b200_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        lib.mcfost_b200_finalize.argtypes = [C.c_void_p]
+        lib.mcfost_b200_finalize.restype = None
+        for fn in ("mcfost_b200_upload_grid", "mcfost_b200_upload_dark_zone", "mcfost_b200_upload_opacity",
+                   "mcfost_b200_upload_emission", "mcfost_b200_launch"):
+            getattr(lib, fn).argtypes = [C.c_void_p, C.c_void_p]
+        lib.mcfost_b200_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mcfost_b200_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mcfost_b200_sync.argtypes = [C.c_void_p]
+        lib.mcfost_b200_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        lib.mcfost_b200_stream.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        lib.mcfost_b200_tally_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                                  C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class _DeviceArray:
+    """__cuda_array_interface__ view of a library-owned device buffer (so that
+    torch.as_tensor(..., device='cuda') can all-reduce it in place with NCCL)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PhotonLoop:
+    """One CUDA device running the photon-packet loop for one model."""
+
+    def __init__(self, P, device=0, rank=0, n_ranks=1):
+        self.lib = load_library()
+        self.P = P
+        self.rank, self.n_ranks = int(rank), int(n_ranks)
+        self.h = C.c_void_p()
+        rc = self.lib.mcfost_b200_init(int(device), C.byref(self.h))
+        if rc != 0:
+            raise McfostB200Error(rc, self.lib.mcfost_b200_last_error(None).decode())
+        self._g = abi.make_grid(P)
+        self._check(self.lib.mcfost_b200_upload_grid(self.h, self._g.ref()))
+        self._o = abi.make_opacity(P)
+        self._check(self.lib.mcfost_b200_upload_opacity(self.h, self._o.ref()))
+        self.upload_dark_zone(getattr(P, "l_dark_zone", None))
+        self._e = None
+        if hasattr(P, "prob_E_cell"):
+            self.upload_emission(P)
+        self._last_run = None
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.mcfost_b200_finalize(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise McfostB200Error(rc, self.lib.mcfost_b200_last_error(self.h).decode())
+
+    # ---- uploads ------------------------------------------------------------
+    def upload_dark_zone(self, dz):
+        a = None if dz is None else np.ascontiguousarray(dz, np.int32)
+        self._check(self.lib.mcfost_b200_upload_dark_zone(self.h, _p(a)))
+
+    def upload_emission(self, P):
+        self._e = abi.make_emission(P)
+        self._check(self.lib.mcfost_b200_upload_emission(self.h, self._e.ref()))
+
+    # ---- the drop-in --------------------------------------------------------
+    def _params(self, lambda_in, p_lambda_in, n_photons2, n_phot_lim, nnfot1_start, laffichage, flags):
+        flags = dict(flags)
+        flags.setdefault("rank", self.rank)
+        flags.setdefault("n_ranks", self.n_ranks)
+        flags.setdefault("n_photons_loop", getattr(self.P, "n_photons_loop", 128))
+        return abi.make_run(lambda_in=lambda_in, p_lambda_in=p_lambda_in, n_photons2=n_photons2,
+                            n_phot_lim=n_phot_lim, nnfot1_start=nnfot1_start, laffichage=int(laffichage), **flags)
+
+    def _tallies(self, r, want_xI=True):
+        P = self.P
+        xJ = bool(r.struct.lxJ_abs_step1 if r.struct.letape_th else r.struct.lxJ_abs)
+        n_xI = 0
+        if want_xI and (not r.struct.letape_th) and r.struct.lscatt_ray_tracing1:
+            ntf = (4 if r.struct.lsepar_pola else 1) + (4 if r.struct.lsepar_contrib else 0)
+            n_xI = abi.N_AZ_RT * 2 * ntf * r.struct.RT_n_incl * r.struct.RT_n_az * P.n_cells
+        return abi.Tallies(P.n_cells, P.n_lambda, r.struct.N_thet, r.struct.N_phi, xJ=xJ, n_xI=n_xI)
+
+    def mc_photon_loop(self, lambda_in=1, p_lambda_in=1, n_photons2=1000, n_phot_lim=1.0e30, nnfot1_start=1,
+                       laffichage=False, **flags):
+        """Blocking call with the reference's argument list; returns the tallies
+        (host numpy arrays shaped like the reference's, without the nb_proc dim)."""
+        r = self._params(lambda_in, p_lambda_in, n_photons2, n_phot_lim, nnfot1_start, laffichage, flags)
+        t = self._tallies(r)
+        self._check(self.lib.mcfost_b200_run(self.h, r.ref(), t.ref()))
+        self._last_run = r
+        return t
+
+    # ---- split form (bench / multi-GPU) ------------------------------------
+    def launch(self, lambda_in=1, p_lambda_in=1, n_photons2=1000, n_phot_lim=1.0e30, nnfot1_start=1, **flags):
+        r = self._params(lambda_in, p_lambda_in, n_photons2, n_phot_lim, nnfot1_start, False, flags)
+        self._check(self.lib.mcfost_b200_launch(self.h, r.ref()))
+        self._last_run = r
+        return r
+
+    def sync(self):
+        self._check(self.lib.mcfost_b200_sync(self.h))
+
+    def download(self, r=None, want_xI=True):
+        r = r or self._last_run
+        t = self._tallies(r, want_xI)
+        self._check(self.lib.mcfost_b200_download(self.h, r.ref(), t.ref()))
+        return t
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self._check(self.lib.mcfost_b200_last_kernel_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def stream(self):
+        s = C.c_uint64()
+        self._check(self.lib.mcfost_b200_stream(self.h, C.byref(s)))
+        return int(s.value)
+
+    def tally_buffers(self):
+        """(fp64 device view, fp32 device view or None) of the packed tally buffers."""
+        p64, n64, p32, n32 = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int64()
+        self._check(self.lib.mcfost_b200_tally_buffers(self.h, C.byref(p64), C.byref(n64), C.byref(p32), C.byref(n32)))
+        a64 = _DeviceArray(p64.value, n64.value, "<f8")
+        a32 = _DeviceArray(p32.value, n32.value, "<f4") if n32.value else None
+        return a64, a32
+
+    # ---- deterministic sub-kernels -----------------------------------------
+    @staticmethod
+    def _f64(*arrs):
+        return [np.ascontiguousarray(a, np.float64).copy() for a in arrs]
+
+    def cross_cell(self, x0, y0, z0, u, v, w, icell, previous_cell=None):
+        x0, y0, z0, u, v, w = self._f64(x0, y0, z0, u, v, w)
+        n = len(x0)
+        icell = np.ascontiguousarray(icell, np.int32)
+        prev = np.zeros(n, np.int32) if previous_cell is None else np.ascontiguousarray(previous_cell, np.int32)
+        x1, y1, z1, l, lc, lv = (np.zeros(n) for _ in range(6))
+        nxt = np.zeros(n, np.int32)
+        self._check(self.lib.mcfost_b200_cross_cell(self.h, C.c_int64(n), _p(x0), _p(y0), _p(z0), _p(u), _p(v), _p(w),
+                                                    _p(icell), _p(prev), _p(x1), _p(y1), _p(z1), _p(nxt), _p(l), _p(lc), _p(lv)))
+        return dict(x1=x1, y1=y1, z1=z1, next_cell=nxt, l=l, l_contrib=lc, l_void_before=lv)
+
+    def index_cell(self, x, y, z):
+        x, y, z = self._f64(x, y, z)
+        ic = np.zeros(len(x), np.int32)
+        self._check(self.lib.mcfost_b200_index_cell(self.h, C.c_int64(len(x)), _p(x), _p(y), _p(z), _p(ic)))
+        return ic
+
+    def move_to_grid(self, x, y, z, u, v, w):
+        x, y, z, u, v, w = self._f64(x, y, z, u, v, w)
+        n = len(x)
+        ic = np.zeros(n, np.int32); li = np.zeros(n, np.int32)
+        self._check(self.lib.mcfost_b200_move_to_grid(self.h, C.c_int64(n), _p(x), _p(y), _p(z), _p(u), _p(v), _p(w), _p(ic), _p(li)))
+        return dict(x=x, y=y, z=z, icell=ic, lintersect=li)
+
+    def optical_length_tot(self, lam, x, y, z, u, v, w, icell):
+        x, y, z, u, v, w = self._f64(x, y, z, u, v, w)
+        n = len(x)
+        icell = np.ascontiguousarray(icell, np.int32)
+        tau, lmin, lmax = (np.zeros(n) for _ in range(3))
+        ns = np.zeros(n, np.int32)
+        self._check(self.lib.mcfost_b200_optical_length_tot(self.h, C.c_int64(n), C.c_int32(lam), _p(x), _p(y), _p(z), _p(u), _p(v), _p(w),
+                                                            _p(icell), _p(tau), _p(lmin), _p(lmax), _p(ns)))
+        return dict(tau_tot=tau, lmin=lmin, lmax=lmax, n_steps=ns)
+
+    def physical_length(self, lam, x, y, z, u, v, w, icell, tau, dark=None):
+        if dark is not None:
+            self.upload_dark_zone(dark)
+        x, y, z, u, v, w = self._f64(x, y, z, u, v, w)
+        n = len(x)
+        icell = np.ascontiguousarray(icell, np.int32).copy()
+        tau = np.ascontiguousarray(tau, np.float32)
+        ltot = np.zeros(n, np.float32); fs = np.zeros(n, np.int32); alive = np.zeros(n, np.int32)
+        self._check(self.lib.mcfost_b200_physical_length(self.h, C.c_int64(n), C.c_int32(lam), _p(x), _p(y), _p(z), _p(u), _p(v), _p(w),
+                                                         _p(icell), _p(tau), _p(ltot), _p(fs), _p(alive)))
+        return dict(x=x, y=y, z=z, u=u, v=v, w=w, icell=icell, ltot=ltot, flag_sortie=fs, lpacket_alive=alive)
+
+    def dark_zone_walker(self):
+        """Step-4 ray walk of define_dark_zone (optical_depth.f90:1519-1550) on the GPU."""
+        def walk(lam, x, y, z, u, v, w, icell, tau, dark):
+            return self.physical_length(lam, x, y, z, u, v, w, icell, tau, dark)["flag_sortie"].astype(bool)
+        return walk

@@ -1,0 +1,709 @@
+// Host side of the C ABI declared in include/mcfost_b200.h: device memory
+// ownership, uploads, kernel launches, tally download.  There is NO CPU
+// fallback anywhere in this library: without a CUDA device every entry point
+// fails with MCB_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mcfost_b200.h"
+#include "transport.cuh"
+
+using namespace mcb;
+
+struct mcb_handle {
+  int device = 0;
+  int n_sm = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevModel m;
+  GridKind gk = GK_CYL2D;
+  bool has_grid = false, has_op = false, has_em = false, launched = false;
+  std::map<std::string, void*> bufs;      // named device allocations
+  std::map<std::string, size_t> buf_bytes;
+  int64_t n_tally = 0, n_xI = 0;
+  bool lay_xJ = false;
+  int lay_nsed = -1;
+  int n_photons_loop_alloc = 0;
+  int n_type_flux = 1;
+  char err[512] = {0};
+};
+
+static char g_err[256] = {0};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      snprintf(h->err, sizeof h->err, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return MCB_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+static int fail(mcb_handle* h, int code, const char* msg) {
+  snprintf(h->err, sizeof h->err, "%s", msg);
+  return code;
+}
+
+// (re)allocate a named device buffer and optionally fill it from host memory
+template <class T>
+static int put(mcb_handle* h, const char* name, const T* src, size_t n, const T** dst) {
+  *dst = nullptr;
+  if (!src || n == 0) return MCB_OK;
+  size_t bytes = n * sizeof(T);
+  void*& p = h->bufs[name];
+  if (p && h->buf_bytes[name] != bytes) { cudaFree(p); p = nullptr; }
+  if (!p) { CK(cudaMalloc(&p, bytes)); h->buf_bytes[name] = bytes; }
+  CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  *dst = (const T*)p;
+  return MCB_OK;
+}
+template <class T>
+static int reserve(mcb_handle* h, const char* name, size_t n, T** dst) {
+  size_t bytes = (n ? n : 1) * sizeof(T);
+  void*& p = h->bufs[name];
+  if (p && h->buf_bytes[name] != bytes) { cudaFree(p); p = nullptr; }
+  if (!p) { CK(cudaMalloc(&p, bytes)); h->buf_bytes[name] = bytes; }
+  *dst = (T*)p;
+  return MCB_OK;
+}
+
+extern "C" {
+
+const char* mcfost_b200_last_error(const mcb_handle* h) { return h ? h->err : g_err; }
+
+int mcfost_b200_init(int device, mcb_handle** out) {
+  if (!out) return MCB_ERR_BAD_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    snprintf(g_err, sizeof g_err, "no CUDA device (%s); mcfost_b200 has no CPU fallback", cudaGetErrorString(e));
+    return MCB_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) { snprintf(g_err, sizeof g_err, "device %d out of range (0..%d)", device, n - 1); return MCB_ERR_BAD_ARG; }
+  mcb_handle* h = new mcb_handle();
+  memset(&h->m, 0, sizeof h->m);
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return MCB_ERR_CUDA; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  h->n_sm = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MCB_ERR_CUDA; }
+  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  *out = h;
+  return MCB_OK;
+}
+
+void mcfost_b200_finalize(mcb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto& kv : h->bufs) if (kv.second) cudaFree(kv.second);
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int mcfost_b200_stream(mcb_handle* h, uint64_t* s) { if (!h || !s) return MCB_ERR_BAD_ARG; *s = (uint64_t)(uintptr_t)h->stream; return MCB_OK; }
+
+// ---------------------------------------------------------------------------
+int mcfost_b200_upload_grid(mcb_handle* h, const mcb_grid* g) {
+  if (!h || !g) return MCB_ERR_BAD_ARG;
+  CK(cudaSetDevice(h->device));
+  DevModel& m = h->m;
+  if (g->kind < MCB_GRID_CYL || g->kind > MCB_GRID_VORONOI) return fail(h, MCB_ERR_BAD_ARG, "unknown grid kind");
+  if (g->n_stars > MAX_STARS) return fail(h, MCB_ERR_UNSUPPORTED, "more than 8 stars");
+  m.kind = g->kind; m.l3D = g->l3D; m.n_rad = g->n_rad; m.nz = g->nz; m.n_az = g->n_az; m.n_cells = g->n_cells;
+  m.nj = g->l3D ? 2 * g->nz : g->nz;
+  m.Rmax2 = g->Rmax2; m.zmaxmax = g->zmaxmax;
+  int rc;
+  if (g->kind != MCB_GRID_VORONOI) {
+    const int expect = g->n_rad * m.nj * g->n_az;
+    if (expect != g->n_cells) return fail(h, MCB_ERR_BAD_ARG, "n_cells does not match n_rad*nz*n_az");
+    h->gk = g->kind == MCB_GRID_CYL ? (g->l3D ? GK_CYL3D : GK_CYL2D) : (g->l3D ? GK_SPH3D : GK_SPH2D);
+    if (!g->r_lim_2) return fail(h, MCB_ERR_BAD_ARG, "r_lim_2 missing");
+    if ((rc = put(h, "r_lim_2", g->r_lim_2, (size_t)g->n_rad + 1, &m.r_lim_2))) return rc;
+    if ((rc = put(h, "r_lim_3", g->r_lim_3, (size_t)g->n_rad + 1, &m.r_lim_3))) return rc;
+    if (g->kind == MCB_GRID_CYL) {
+      if (!g->z_lim || !g->zmax) return fail(h, MCB_ERR_BAD_ARG, "z_lim / zmax missing");
+      if ((rc = put(h, "z_lim", g->z_lim, (size_t)g->n_rad * (g->nz + 2), &m.z_lim))) return rc;
+      if ((rc = put(h, "zmax", g->zmax, (size_t)g->n_rad, &m.zmax))) return rc;
+    } else {
+      if (!g->tan_theta_lim || !g->theta_lim) return fail(h, MCB_ERR_BAD_ARG, "tan_theta_lim / theta_lim missing");
+      if ((rc = put(h, "tan_theta_lim", g->tan_theta_lim, (size_t)g->nz + 1, &m.tan_theta_lim))) return rc;
+      if ((rc = put(h, "theta_lim", g->theta_lim, (size_t)g->nz + 1, &m.theta_lim))) return rc;
+    }
+    if (g->l3D) {
+      if (!g->tan_phi_lim) return fail(h, MCB_ERR_BAD_ARG, "tan_phi_lim missing");
+      if ((rc = put(h, "tan_phi_lim", g->tan_phi_lim, (size_t)g->n_az, &m.tan_phi_lim))) return rc;
+    }
+    // verify the closed-form numbering against the caller's cell maps
+    if (g->cell_map_i && g->cell_map_j && g->cell_map_k && g->n_cells_tot > 0) {
+      for (int id = 1; id <= g->n_cells_tot; ++id) {
+        Cell c = cell_from_id(m, id);
+        if (c.ri != g->cell_map_i[id - 1] || c.zj != g->cell_map_j[id - 1] || c.k != g->cell_map_k[id - 1] || cell_id(m, c) != id) {
+          snprintf(h->err, sizeof h->err, "cell numbering mismatch at id %d: lib (%d,%d,%d) caller (%d,%d,%d)", id, c.ri, c.zj, c.k,
+                   g->cell_map_i[id - 1], g->cell_map_j[id - 1], g->cell_map_k[id - 1]);
+          return MCB_ERR_CELL_MAP;
+        }
+      }
+    }
+  } else {
+    h->gk = GK_VOR;
+    if (!g->vor_xyz || !g->vor_first || !g->vor_last || !g->neighbours_list) return fail(h, MCB_ERR_BAD_ARG, "Voronoi arrays missing");
+    if ((rc = put(h, "vor_xyz", g->vor_xyz, (size_t)3 * g->n_cells, &m.vor_xyz))) return rc;
+    if ((rc = put(h, "vor_h", g->vor_h, (size_t)g->n_cells, &m.vor_h))) return rc;
+    if ((rc = put(h, "vor_first", g->vor_first, (size_t)g->n_cells, &m.vor_first))) return rc;
+    if ((rc = put(h, "vor_last", g->vor_last, (size_t)g->n_cells, &m.vor_last))) return rc;
+    if ((rc = put(h, "neigh", g->neighbours_list, (size_t)g->n_neighbours_tot, &m.neigh))) return rc;
+    std::vector<float4> x32(g->n_cells);
+    std::vector<uint8_t> fl(g->n_cells);
+    for (int i = 0; i < g->n_cells; ++i) {
+      x32[i] = make_float4((float)g->vor_xyz[3 * (size_t)i], (float)g->vor_xyz[3 * (size_t)i + 1], (float)g->vor_xyz[3 * (size_t)i + 2], 0.f);
+      fl[i] = (uint8_t)((g->vor_was_cut && g->vor_was_cut[i] ? 1 : 0) | (g->vor_is_star && g->vor_is_star[i] ? 2 : 0) |
+                        (g->vor_is_star_neighbour && g->vor_is_star_neighbour[i] ? 4 : 0));
+    }
+    if ((rc = put(h, "vor_xyz32", x32.data(), x32.size(), &m.vor_xyz32))) return rc;
+    if ((rc = put(h, "vor_flags", fl.data(), fl.size(), &m.vor_flags))) return rc;
+    CK(cudaStreamSynchronize(h->stream));       // x32 / fl are stack-owned
+    memcpy(m.wall, g->wall_x, sizeof m.wall);
+    m.cut_o_h = g->cutting_distance_o_h;
+  }
+  if ((rc = put(h, "volume", g->volume, (size_t)g->n_cells, &m.volume))) return rc;
+  m.n_stars = g->n_stars;
+  for (int i = 0; i < g->n_stars; ++i) {
+    for (int a = 0; a < 4; ++a) m.star[i][a] = g->star_xyzr[4 * i + a];
+    m.star_icell[i] = g->star_icell ? g->star_icell[i] : 0;
+    m.star_out[i] = g->star_out_model ? g->star_out_model[i] : 0;
+  }
+  // default: no dark zone
+  std::vector<uint8_t> dz((size_t)g->n_cells, 0);
+  if ((rc = put(h, "dark", dz.data(), dz.size(), &m.dark))) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  h->has_grid = true;
+  return MCB_OK;
+}
+
+int mcfost_b200_upload_dark_zone(mcb_handle* h, const int32_t* l_dark_zone) {
+  if (!h) return MCB_ERR_BAD_ARG;
+  if (!h->has_grid) return fail(h, MCB_ERR_STATE, "upload_dark_zone before upload_grid");
+  CK(cudaSetDevice(h->device));
+  std::vector<uint8_t> dz((size_t)h->m.n_cells, 0);
+  if (l_dark_zone) for (int i = 0; i < h->m.n_cells; ++i) dz[i] = l_dark_zone[i] != 0;
+  int rc;
+  if ((rc = put(h, "dark", dz.data(), dz.size(), &h->m.dark))) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
+}
+
+int mcfost_b200_upload_opacity(mcb_handle* h, const mcb_opacity* o) {
+  if (!h || !o) return MCB_ERR_BAD_ARG;
+  if (!h->has_grid) return fail(h, MCB_ERR_STATE, "upload_opacity before upload_grid");
+  CK(cudaSetDevice(h->device));
+  DevModel& m = h->m;
+  if (o->p_n_cells != 1 && o->p_n_cells != m.n_cells) return fail(h, MCB_ERR_BAD_ARG, "p_n_cells must be 1 or n_cells");
+  if (o->p_n_lambda_pos != 1 && o->p_n_lambda_pos != o->n_lambda) return fail(h, MCB_ERR_BAD_ARG, "p_n_lambda_pos must be 1 or n_lambda");
+  m.n_lambda = o->n_lambda; m.p_n_cells = o->p_n_cells; m.p_n_lambda_pos = o->p_n_lambda_pos; m.n_T = o->n_T;
+  m.T_min = o->T_min;
+  const size_t npl = (size_t)o->p_n_cells * o->n_lambda;
+  const size_t npos = (size_t)(NANG + 1) * o->p_n_cells * o->p_n_lambda_pos;
+  int rc;
+  if (!o->kappa || !o->kappa_abs_LTE || !o->kappa_factor || !o->tab_albedo_pos) return fail(h, MCB_ERR_BAD_ARG, "opacity tables missing");
+  if ((rc = put(h, "kappa", o->kappa, npl, &m.kappa))) return rc;
+  if ((rc = put(h, "kappa_abs", o->kappa_abs_LTE, npl, &m.kappa_abs))) return rc;
+  if ((rc = put(h, "kappa_factor", o->kappa_factor, (size_t)m.n_cells, &m.kappa_factor))) return rc;
+  if ((rc = put(h, "albedo", o->tab_albedo_pos, npl, &m.albedo))) return rc;
+  if ((rc = put(h, "gfac", o->tab_g_pos, npl, &m.gfac))) return rc;
+  if ((rc = put(h, "prob_s11", o->prob_s11_pos, npos, &m.prob_s11))) return rc;
+  if ((rc = put(h, "s11", o->tab_s11_pos, npos, &m.s11))) return rc;
+  if ((rc = put(h, "s12", o->tab_s12_o_s11_pos, npos, &m.s12))) return rc;
+  if ((rc = put(h, "s22", o->tab_s22_o_s11_pos, npos, &m.s22))) return rc;
+  if ((rc = put(h, "s33", o->tab_s33_o_s11_pos, npos, &m.s33))) return rc;
+  if ((rc = put(h, "s34", o->tab_s34_o_s11_pos, npos, &m.s34))) return rc;
+  if ((rc = put(h, "s44", o->tab_s44_o_s11_pos, npos, &m.s44))) return rc;
+  if ((rc = put(h, "logQ", o->log_Qcool_minus_extra_heating, (size_t)o->n_T * o->p_n_cells, &m.logQ))) return rc;
+  if ((rc = put(h, "kdB", o->kdB_dT_CDF, (size_t)o->n_lambda * o->n_T * o->p_n_cells, &m.kdB))) return rc;
+  // cos(k*pi/nang_scatt), k = 0..180, with the host libm (scattering.f90:1470-1471 evaluates
+  // cos((real(k,dp)-1)*pi/real(nang_scatt,dp)) per event; tabulated once here)
+  std::vector<double> ct(NANG + 1);
+  for (int k = 0; k <= NANG; ++k) ct[k] = cos(((double)k) * MCB_PI / (double)NANG);
+  if ((rc = put(h, "cos_tab", ct.data(), ct.size(), &m.cos_tab))) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  h->has_op = true;
+  return MCB_OK;
+}
+
+int mcfost_b200_upload_emission(mcb_handle* h, const mcb_emission* e) {
+  if (!h || !e) return MCB_ERR_BAD_ARG;
+  if (!h->has_op) return fail(h, MCB_ERR_STATE, "upload_emission before upload_opacity");
+  CK(cudaSetDevice(h->device));
+  DevModel& m = h->m;
+  int rc;
+  if (!e->frac_E_stars || !e->frac_E_disk || !e->prob_E_cell || !e->CDF_E_star) return fail(h, MCB_ERR_BAD_ARG, "emission tables missing");
+  if ((rc = put(h, "spec_cumul", e->spectre_emission_cumul, (size_t)m.n_lambda + 1, &m.spec_cumul))) return rc;
+  if ((rc = put(h, "frac_star", e->frac_E_stars, (size_t)m.n_lambda, &m.frac_star))) return rc;
+  if ((rc = put(h, "frac_disk", e->frac_E_disk, (size_t)m.n_lambda, &m.frac_disk))) return rc;
+  if ((rc = put(h, "prob_E_cell", e->prob_E_cell, (size_t)(m.n_cells + 1) * m.n_lambda, &m.prob_E_cell))) return rc;
+  if ((rc = put(h, "CDF_E_star", e->CDF_E_star, (size_t)m.n_lambda * (m.n_stars + 1), &m.CDF_E_star))) return rc;
+  m.L_packet_th = e->L_packet_th; m.E_paquet = e->E_paquet; m.R_ISM = e->R_ISM;
+  for (int a = 0; a < 3; ++a) m.cISM[a] = e->centre_ISM[a];
+  CK(cudaStreamSynchronize(h->stream));
+  h->has_em = true;
+  return MCB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+__global__ void fill_int_kernel(int* p, int64_t n, int v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+static int setup_tallies(mcb_handle* h, const mcb_run_params* r, bool lxJ, bool rt1, int n_type_flux) {
+  DevModel& m = h->m;
+  const int n_sed = m.n_lambda * r->N_thet * r->N_phi;
+  bool realloc_ = (h->n_tally == 0) || (h->lay_xJ != lxJ) || (h->lay_nsed != n_sed);
+  TallyLayout L;
+  L.xKJ = 0;
+  L.xJ = m.n_cells;
+  L.n_env = L.xJ + (lxJ ? (int64_t)m.n_cells * m.n_lambda : 0);
+  L.sed = L.n_env + m.n_lambda;
+  L.n_sed = n_sed;
+  L.stats = L.sed + 9 * (int64_t)n_sed;
+  L.total = L.stats + 8;
+  m.lay = L;
+  int rc;
+  if ((rc = reserve(h, "tally", (size_t)L.total, &m.tally))) return rc;
+  if ((rc = reserve(h, "xT_ech", (size_t)m.n_cells, &m.xT_ech))) return rc;
+  const int n_rt = r->RT_n_incl * r->RT_n_az;
+  const int64_t n_xI = rt1 ? (int64_t)N_AZ_RT * 2 * n_type_flux * n_rt * m.n_cells : 0;
+  if (n_xI != h->n_xI) realloc_ = true;
+  if ((rc = reserve(h, "xI", (size_t)n_xI, &m.xI))) return rc;
+  if ((rc = reserve(h, "work", (size_t)(4 + 2 * r->n_photons_loop), &m.work))) return rc;
+  h->n_tally = L.total; h->n_xI = n_xI; h->lay_xJ = lxJ; h->lay_nsed = n_sed; h->n_type_flux = n_type_flux;
+  if (realloc_ || r->reset_tallies) {
+    CK(cudaMemsetAsync(m.tally, 0, (size_t)L.total * sizeof(double), h->stream));
+    if (n_xI) CK(cudaMemsetAsync(m.xI, 0, (size_t)n_xI * sizeof(float), h->stream));
+    fill_int_kernel<<<256, 256, 0, h->stream>>>(m.xT_ech, m.n_cells, 2);      // xT_ech = 2, thermal_emission.f90:119,2164
+  }
+  CK(cudaMemsetAsync(m.work, 0, (size_t)(4 + 2 * r->n_photons_loop) * sizeof(unsigned long long), h->stream));
+  return MCB_OK;
+}
+
+template <class G>
+static int launch_mc(mcb_handle* h, const DevRun& dr) {
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mc_photon_loop_kernel<G>, 128, 0));
+  if (per_sm < 1) per_sm = 1;
+  const int blocks = h->n_sm * per_sm;          // persistent: one wave exactly filling the 148 SMs
+  CK(cudaEventRecord(h->ev0, h->stream));
+  mc_photon_loop_kernel<G><<<blocks, 128, 0, h->stream>>>(h->m, dr);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev1, h->stream));
+  return MCB_OK;
+}
+
+extern "C" {
+
+int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
+  if (!h || !r) return MCB_ERR_BAD_ARG;
+  if (!h->has_grid || !h->has_op || !h->has_em) return fail(h, MCB_ERR_STATE, "run before upload_grid/opacity/emission");
+  CK(cudaSetDevice(h->device));
+  DevModel& m = h->m;
+  // ---- modes this library implements; everything else fails loudly ----
+  if (r->lscattering_method1) return fail(h, MCB_ERR_UNSUPPORTED, "scattering method 1 (per-grain) not implemented");
+  if (!r->lonly_LTE) return fail(h, MCB_ERR_UNSUPPORTED, "nLTE / nRE re-emission not implemented");
+  if (r->lscatt_ray_tracing2) return fail(h, MCB_ERR_UNSUPPORTED, "rt2 (I_spec) accumulator not implemented");
+  if (r->lmono0) return fail(h, MCB_ERR_UNSUPPORTED, "MC image mode (STOKEI maps) not implemented");
+  if (r->n_photons_loop < 1 || r->nnfot1_start < 1 || r->n_photons2 < 0) return fail(h, MCB_ERR_BAD_ARG, "bad packet budget");
+  if (r->lambda_in < 1 || r->lambda_in > m.n_lambda || r->p_lambda_in < 1 || r->p_lambda_in > m.p_n_lambda_pos) return fail(h, MCB_ERR_BAD_ARG, "lambda index out of range");
+  if (r->n_ranks < 1 || r->rank < 0 || r->rank >= r->n_ranks) return fail(h, MCB_ERR_BAD_ARG, "bad rank / n_ranks");
+  if (r->lmethod_aniso1 && (!m.prob_s11)) return fail(h, MCB_ERR_BAD_ARG, "prob_s11_pos missing for lmethod_aniso1");
+  if (!r->lmethod_aniso1 && !m.gfac) return fail(h, MCB_ERR_BAD_ARG, "tab_g_pos missing for HG scattering");
+  if (r->lsepar_pola && r->lmethod_aniso1 && (!m.s12 || !m.s22 || !m.s33 || !m.s34 || !m.s44)) return fail(h, MCB_ERR_BAD_ARG, "Mueller tables missing for lsepar_pola");
+  if (r->letape_th && (!m.logQ || !m.kdB || !m.spec_cumul)) return fail(h, MCB_ERR_BAD_ARG, "thermal tables missing");
+  const bool rt1 = (!r->letape_th) && r->lscatt_ray_tracing1;
+  const int n_rt = r->RT_n_incl * r->RT_n_az;
+  if (rt1) {
+    if (n_rt < 1 || n_rt > MAX_RT) return fail(h, MCB_ERR_UNSUPPORTED, "rt1 needs 1..8 observer directions");
+    if (!r->tab_u_rt || !r->tab_v_rt || !r->tab_w_rt || !m.s11) return fail(h, MCB_ERR_BAD_ARG, "rt1 direction / s11 tables missing");
+  }
+  DevRun dr;
+  memset(&dr, 0, sizeof dr);
+  dr.lambda_in = r->lambda_in; dr.p_lambda_in = r->p_lambda_in; dr.n_photons2 = r->n_photons2;
+  dr.nnfot1_start = r->nnfot1_start; dr.n_photons_loop = r->n_photons_loop; dr.n_phot_lim = r->n_phot_lim;
+  dr.letape_th = r->letape_th; dr.lmono = r->lmono; dr.lsepar_pola = r->lsepar_pola; dr.lsepar_contrib = r->lsepar_contrib;
+  dr.lmethod_aniso1 = r->lmethod_aniso1; dr.lisotropic = r->lisotropic;
+  dr.l_sym_centrale = r->l_sym_centrale; dr.l_sym_axiale = r->l_sym_axiale;
+  dr.rt1 = rt1;
+  dr.lxJ = r->letape_th ? r->lxJ_abs_step1 : r->lxJ_abs;
+  dr.N_thet = r->N_thet; dr.N_phi = r->N_phi; dr.capt_sup = r->capt_sup;
+  dr.n_stokes = r->lsepar_pola ? 4 : 1;
+  dr.n_type_flux = dr.n_stokes + (r->lsepar_contrib ? 4 : 0);      // init_mcfost.f90:1604-1616
+  dr.n_rt = rt1 ? n_rt : 0; dr.RT_n_incl = r->RT_n_incl; dr.RT_n_az = r->RT_n_az;
+  for (int i = 0; i < dr.n_rt; ++i) {
+    dr.rt_u[i] = r->tab_u_rt[i]; dr.rt_v[i] = r->tab_v_rt[i]; dr.rt_w[i] = r->tab_w_rt[i % r->RT_n_incl];
+  }
+  dr.seed = r->seed; dr.call_index = r->call_index;
+  dr.rank = r->rank; dr.n_ranks = r->n_ranks;
+  // chunks nnfot1_start..n_photons_loop dealt round-robin: rank owns chunks with (c-1) % n_ranks == rank
+  int n_local = 0;
+  for (int c = r->nnfot1_start; c <= r->n_photons_loop; ++c) if (((c - 1) % r->n_ranks) == r->rank) ++n_local;
+  dr.n_local_chunks = n_local;
+  dr.count_sent = (r->letape_th || r->lmono0) ? 1 : 0;
+  const double lim = ceil((double)r->n_phot_lim);
+  dr.sent_lim = (lim >= 1.8e19) ? ~0ull : (lim <= 0 ? 0ull : (unsigned long long)lim);
+  dr.n_per_chunk = (unsigned long long)r->n_photons2 < dr.sent_lim ? (unsigned long long)r->n_photons2 : dr.sent_lim;
+  dr.n_packets_total = dr.count_sent ? (unsigned long long)n_local * dr.n_per_chunk : 0ull;
+  dr.nb_proc_equiv = (double)r->n_ranks;
+  int rc = setup_tallies(h, r, dr.lxJ != 0, rt1, dr.n_type_flux);
+  if (rc) return rc;
+  if (n_local == 0 || (dr.count_sent && dr.n_packets_total == 0)) { CK(cudaEventRecord(h->ev0, h->stream)); CK(cudaEventRecord(h->ev1, h->stream)); h->launched = true; return MCB_OK; }
+  switch (h->gk) {
+    case GK_CYL2D: rc = launch_mc<GeomCyl<false>>(h, dr); break;
+    case GK_CYL3D: rc = launch_mc<GeomCyl<true>>(h, dr); break;
+    case GK_SPH2D: rc = launch_mc<GeomSph<false>>(h, dr); break;
+    case GK_SPH3D: rc = launch_mc<GeomSph<true>>(h, dr); break;
+    case GK_VOR:   rc = launch_mc<GeomVor>(h, dr); break;
+  }
+  if (rc) return rc;
+  h->launched = true;
+  return MCB_OK;
+}
+
+int mcfost_b200_sync(mcb_handle* h) {
+  if (!h) return MCB_ERR_BAD_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
+}
+
+int mcfost_b200_last_kernel_ms(mcb_handle* h, float* ms) {
+  if (!h || !ms) return MCB_ERR_BAD_ARG;
+  if (!h->launched) return fail(h, MCB_ERR_STATE, "no launch yet");
+  CK(cudaEventSynchronize(h->ev1));
+  CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return MCB_OK;
+}
+
+int mcfost_b200_tally_buffers(mcb_handle* h, void** d_f64, int64_t* n_f64, void** d_f32, int64_t* n_f32) {
+  if (!h) return MCB_ERR_BAD_ARG;
+  if (!h->n_tally) return fail(h, MCB_ERR_STATE, "no tallies allocated yet");
+  if (d_f64) *d_f64 = h->m.tally;
+  if (n_f64) *n_f64 = h->n_tally;
+  if (d_f32) *d_f32 = h->n_xI ? h->m.xI : nullptr;
+  if (n_f32) *n_f32 = h->n_xI;
+  return MCB_OK;
+}
+
+int mcfost_b200_download(mcb_handle* h, const mcb_run_params* r, mcb_tallies* out) {
+  if (!h || !out) return MCB_ERR_BAD_ARG;
+  if (!h->n_tally) return fail(h, MCB_ERR_STATE, "download before launch");
+  CK(cudaSetDevice(h->device));
+  const DevModel& m = h->m;
+  const TallyLayout& L = m.lay;
+  auto get = [&](double* dst, int64_t off, int64_t n) -> cudaError_t {
+    if (!dst || n <= 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst, m.tally + off, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  };
+  CK(get(out->xKJ_abs, L.xKJ, m.n_cells));
+  if (h->lay_xJ) CK(get(out->xJ_abs, L.xJ, (int64_t)m.n_cells * m.n_lambda));
+  CK(get(out->n_phot_envoyes, L.n_env, m.n_lambda));
+  double* sp[9] = {out->sed, out->sed_q, out->sed_u, out->sed_v, out->n_phot_sed, out->sed_star, out->sed_star_scat, out->sed_disk, out->sed_disk_scat};
+  for (int a = 0; a < 9; ++a) CK(get(sp[a], L.sed + a * L.n_sed, L.n_sed));
+  CK(get(out->stats, L.stats, 8));
+  if (out->xT_ech) CK(cudaMemcpyAsync(out->xT_ech, m.xT_ech, (size_t)m.n_cells * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (out->xI_scatt && h->n_xI) CK(cudaMemcpyAsync(out->xI_scatt, m.xI, (size_t)h->n_xI * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  out->N_type_flux = h->n_type_flux;
+  CK(cudaStreamSynchronize(h->stream));
+  (void)r;
+  return MCB_OK;
+}
+
+int mcfost_b200_run(mcb_handle* h, const mcb_run_params* r, mcb_tallies* out) {
+  int rc = mcfost_b200_launch(h, r);
+  if (rc) return rc;
+  rc = mcfost_b200_sync(h);
+  if (rc) return rc;
+  if (out) rc = mcfost_b200_download(h, r, out);
+  return rc;
+}
+
+}  // extern "C"
+
+// ===========================================================================
+// deterministic sub-kernels: one ray per thread
+// ===========================================================================
+template <class G>
+__global__ void cross_cell_kernel(const __grid_constant__ DevModel m, int64_t n, const double* x0, const double* y0, const double* z0,
+                                  const double* u, const double* v, const double* w, const int* icell, const int* prev,
+                                  double* x1, double* y1, double* z1, int* next_cell, double* l, double* lc, double* lv) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  typename G::CellT c, p, nx;
+  cell_of_id(m, icell[i], c);
+  if (prev[i] != 0) cell_of_id(m, prev[i], p); else null_cell(p);
+  DirInv d = dir_invariants(u[i], v[i], w[i]);
+  double a, b, cc, lcon, lvoid;
+  double ll = G::cross(m, d, x0[i], y0[i], z0[i], u[i], v[i], w[i], c, p, a, b, cc, nx, lcon, lvoid);
+  x1[i] = a; y1[i] = b; z1[i] = cc; next_cell[i] = id_of_cell(m, nx); l[i] = ll; lc[i] = lcon; lv[i] = lvoid;
+}
+
+template <class G>
+__global__ void index_cell_kernel(const __grid_constant__ DevModel m, int64_t n, const double* x, const double* y, const double* z, int* icell) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  icell[i] = id_of_cell(m, G::index(m, x[i], y[i], z[i]));
+}
+
+template <class G>
+__global__ void move_to_grid_kernel(const __grid_constant__ DevModel m, int64_t n, double* x, double* y, double* z,
+                                    const double* u, const double* v, const double* w, int* icell, int* lintersect) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  typename G::CellT c; null_cell(c);
+  double a = x[i], b = y[i], cc = z[i];
+  bool ok = G::move_to_grid(m, a, b, cc, u[i], v[i], w[i], c);
+  lintersect[i] = ok;
+  icell[i] = ok ? id_of_cell(m, c) : 0;
+  if (ok) { x[i] = a; y[i] = b; z[i] = cc; }
+}
+
+// optical_depth.f90:248-324
+template <class G>
+__global__ void optical_length_tot_kernel(const __grid_constant__ DevModel m, int64_t n, int lambda, const double* x, const double* y, const double* z,
+                                          const double* u, const double* v, const double* w, const int* icell,
+                                          double* tau_out, double* lmin_out, double* lmax_out, int* nsteps) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  typename G::CellT c0, c_prev, c1;
+  cell_of_id(m, icell[i], c0); null_cell(c_prev);
+  const double uu = u[i], vv = v[i], ww = w[i];
+  DirInv d = dir_invariants(uu, vv, ww);
+  double x0 = x[i], y0 = y[i], z0 = z[i];
+  double tau_tot = 0.0, lmin = 0.0, ltot = 0.0;
+  int ns = 0;
+  const bool variable_dust = m.p_n_cells != 1;
+  for (;;) {
+    if (G::test_exit(m, c0, x0, y0, z0)) break;
+    const int idx = tally_index(m, c0);
+    double opacity = 0.0;
+    if (idx >= 0) {
+      const int p_icell = variable_dust ? idx + 1 : 1;
+      opacity = __ldg(m.kappa + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)) * __ldg(m.kappa_factor + idx);
+    }
+    double x1, y1, z1, lcon, lvoid;
+    double l = G::cross(m, d, x0, y0, z0, uu, vv, ww, c0, c_prev, x1, y1, z1, c1, lcon, lvoid);
+    ++ns;
+    tau_tot = tau_tot + lcon * opacity;
+    ltot = ltot + l;
+    if (tau_tot < MCB_TINY_REAL) lmin = ltot;
+    c_prev = c0; c0 = c1; x0 = x1; y0 = y1; z0 = z1;
+    if (ns > 100000000) break;
+  }
+  tau_out[i] = (double)(float)tau_tot;      // tau_tot_out is `real`
+  lmin_out[i] = lmin; lmax_out[i] = ltot;
+  if (nsteps) nsteps[i] = ns;
+}
+
+// optical_depth.f90:21-182 with Stokes = 0 (no tallies)
+template <class G>
+__global__ void physical_length_kernel(const __grid_constant__ DevModel m, int64_t n, int lambda, double* x, double* y, double* z,
+                                       double* u, double* v, double* w, int* icell, const float* tau, float* ltot_out,
+                                       int* flag_sortie, int* alive_out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  typename G::CellT c0, c_old, c1;
+  cell_of_id(m, icell[i], c0); null_cell(c_old);
+  int id_old = 0;
+  double uu = u[i], vv = v[i], ww = w[i];
+  DirInv d = dir_invariants(uu, vv, ww);
+  double x0 = x[i], y0 = y[i], z0 = z[i], xo = x0, yo = y0, zo = z0;
+  double extr = (double)tau[i];
+  float ltot = 0.0f;
+  const int i_star_hit = intersect_stars(m, x0, y0, z0, uu, vv, ww);
+  const bool variable_dust = m.p_n_cells != 1;
+  int sortie = 0, alive = 1;
+  for (;;) {
+    if (G::test_exit(m, c0, x0, y0, z0)) { sortie = 1; break; }
+    if (i_star_hit > 0) {
+      typename G::CellT cs; cell_of_id(m, m.star_icell[i_star_hit - 1], cs);
+      if (same_cell(c0, cs)) { alive = 0; sortie = 1; break; }
+    }
+    const int idx = tally_index(m, c0);
+    double opacity = 0.0;
+    if (idx >= 0) {
+      const int p_icell = variable_dust ? idx + 1 : 1;
+      opacity = __ldg(m.kappa + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)) * __ldg(m.kappa_factor + idx);
+      if (__ldg(m.dark + idx)) {
+        u[i] = -uu; v[i] = -vv; w[i] = -ww;
+        icell[i] = id_old; x[i] = xo; y[i] = yo; z[i] = zo;
+        ltot_out[i] = ltot; flag_sortie[i] = 0; alive_out[i] = alive;
+        return;
+      }
+    }
+    double x1, y1, z1, lcon, lvoid;
+    double l = G::cross(m, d, x0, y0, z0, uu, vv, ww, c0, c_old, x1, y1, z1, c1, lcon, lvoid);
+    const double tau_c = lcon * opacity;
+    if (tau_c > extr) {
+      lcon = lcon * (extr / tau_c);
+      l = lvoid + lcon;
+      ltot = (float)((double)ltot + l);
+      double xf = x0 + l * uu, yf = y0 + l * vv, zf = z0 + l * ww;
+      typename G::CellT cf = c0;
+      if (!G::is_vor && m.l3D && m.kind == 1) cf = G::index(m, xf, yf, zf);
+      x[i] = xf; y[i] = yf; z[i] = zf; icell[i] = id_of_cell(m, cf);
+      ltot_out[i] = ltot; flag_sortie[i] = 0; alive_out[i] = alive;
+      return;
+    }
+    extr = extr - tau_c;
+    ltot = (float)((double)ltot + l);
+    id_old = id_of_cell(m, c0);
+    xo = x0; yo = y0; zo = z0; c_old = c0;
+    x0 = x1; y0 = y1; z0 = z1; c0 = c1;
+  }
+  // exit: the reference leaves xio,yio,zio,icell untouched
+  ltot_out[i] = ltot; flag_sortie[i] = sortie; alive_out[i] = alive;
+}
+
+// ---- host wrappers (host pointers in, host pointers out) --------------------
+namespace {
+struct Scratch {
+  mcb_handle* h;
+  std::vector<void*> d;
+  ~Scratch() { for (void* p : d) cudaFree(p); }
+  template <class T> T* in(const T* src, int64_t n) {
+    T* p = nullptr;
+    if (cudaMalloc(&p, (size_t)(n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    d.push_back(p);
+    if (src) cudaMemcpyAsync(p, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+    return p;
+  }
+  template <class T> void out(T* dst, const T* src, int64_t n) {
+    if (dst) cudaMemcpyAsync(dst, src, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, h->stream);
+  }
+};
+}  // namespace
+
+#define DISPATCH(KERNEL, ...)                                                              \
+  switch (h->gk) {                                                                         \
+    case GK_CYL2D: KERNEL<GeomCyl<false>><<<nb, 128, 0, h->stream>>>(__VA_ARGS__); break;  \
+    case GK_CYL3D: KERNEL<GeomCyl<true>><<<nb, 128, 0, h->stream>>>(__VA_ARGS__); break;   \
+    case GK_SPH2D: KERNEL<GeomSph<false>><<<nb, 128, 0, h->stream>>>(__VA_ARGS__); break;  \
+    case GK_SPH3D: KERNEL<GeomSph<true>><<<nb, 128, 0, h->stream>>>(__VA_ARGS__); break;   \
+    case GK_VOR:   KERNEL<GeomVor><<<nb, 128, 0, h->stream>>>(__VA_ARGS__); break;         \
+  }
+
+extern "C" {
+
+int mcfost_b200_cross_cell(mcb_handle* h, int64_t n, const double* x0, const double* y0, const double* z0,
+                           const double* u, const double* v, const double* w, const int32_t* icell, const int32_t* previous_cell,
+                           double* x1, double* y1, double* z1, int32_t* next_cell, double* l, double* l_contrib, double* l_void_before) {
+  if (!h || n < 0) return MCB_ERR_BAD_ARG;
+  if (!h->has_grid) return fail(h, MCB_ERR_STATE, "cross_cell before upload_grid");
+  if (n == 0) return MCB_OK;
+  CK(cudaSetDevice(h->device));
+  Scratch s{h};
+  std::vector<int32_t> zero;
+  if (!previous_cell) { zero.assign((size_t)n, 0); previous_cell = zero.data(); }
+  const double *dx0 = s.in(x0, n), *dy0 = s.in(y0, n), *dz0 = s.in(z0, n), *du = s.in(u, n), *dv = s.in(v, n), *dw = s.in(w, n);
+  const int *dic = s.in(icell, n), *dpr = s.in(previous_cell, n);
+  double *dx1 = s.in<double>(nullptr, n), *dy1 = s.in<double>(nullptr, n), *dz1 = s.in<double>(nullptr, n);
+  double *dl = s.in<double>(nullptr, n), *dlc = s.in<double>(nullptr, n), *dlv = s.in<double>(nullptr, n);
+  int* dnx = s.in<int>(nullptr, n);
+  if (!dnx) return fail(h, MCB_ERR_CUDA, "scratch allocation failed");
+  const unsigned nb = (unsigned)((n + 127) / 128);
+  DISPATCH(cross_cell_kernel, h->m, n, dx0, dy0, dz0, du, dv, dw, dic, dpr, dx1, dy1, dz1, dnx, dl, dlc, dlv);
+  CK(cudaGetLastError());
+  s.out(x1, dx1, n); s.out(y1, dy1, n); s.out(z1, dz1, n); s.out(next_cell, dnx, n); s.out(l, dl, n); s.out(l_contrib, dlc, n); s.out(l_void_before, dlv, n);
+  CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
+}
+
+int mcfost_b200_index_cell(mcb_handle* h, int64_t n, const double* x, const double* y, const double* z, int32_t* icell) {
+  if (!h || n < 0) return MCB_ERR_BAD_ARG;
+  if (!h->has_grid) return fail(h, MCB_ERR_STATE, "index_cell before upload_grid");
+  if (n == 0) return MCB_OK;
+  CK(cudaSetDevice(h->device));
+  Scratch s{h};
+  const double *dx = s.in(x, n), *dy = s.in(y, n), *dz = s.in(z, n);
+  int* dic = s.in<int>(nullptr, n);
+  if (!dic) return fail(h, MCB_ERR_CUDA, "scratch allocation failed");
+  const unsigned nb = (unsigned)((n + 127) / 128);
+  DISPATCH(index_cell_kernel, h->m, n, dx, dy, dz, dic);
+  CK(cudaGetLastError());
+  s.out(icell, dic, n);
+  CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
+}
+
+int mcfost_b200_move_to_grid(mcb_handle* h, int64_t n, double* x, double* y, double* z, const double* u, const double* v, const double* w,
+                             int32_t* icell, int32_t* lintersect) {
+  if (!h || n < 0) return MCB_ERR_BAD_ARG;
+  if (!h->has_grid) return fail(h, MCB_ERR_STATE, "move_to_grid before upload_grid");
+  if (n == 0) return MCB_OK;
+  CK(cudaSetDevice(h->device));
+  Scratch s{h};
+  double *dx = s.in(x, n), *dy = s.in(y, n), *dz = s.in(z, n);
+  const double *du = s.in(u, n), *dv = s.in(v, n), *dw = s.in(w, n);
+  int *dic = s.in<int>(nullptr, n), *dli = s.in<int>(nullptr, n);
+  if (!dli) return fail(h, MCB_ERR_CUDA, "scratch allocation failed");
+  const unsigned nb = (unsigned)((n + 127) / 128);
+  DISPATCH(move_to_grid_kernel, h->m, n, dx, dy, dz, du, dv, dw, dic, dli);
+  CK(cudaGetLastError());
+  s.out(x, dx, n); s.out(y, dy, n); s.out(z, dz, n); s.out(icell, dic, n); s.out(lintersect, dli, n);
+  CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
+}
+
+int mcfost_b200_optical_length_tot(mcb_handle* h, int64_t n, int32_t lambda, const double* x, const double* y, const double* z,
+                                   const double* u, const double* v, const double* w, const int32_t* icell,
+                                   double* tau_tot, double* lmin, double* lmax, int32_t* n_steps) {
+  if (!h || n < 0) return MCB_ERR_BAD_ARG;
+  if (!h->has_grid || !h->has_op) return fail(h, MCB_ERR_STATE, "optical_length_tot before upload_grid/opacity");
+  if (lambda < 1 || lambda > h->m.n_lambda) return fail(h, MCB_ERR_BAD_ARG, "lambda out of range");
+  if (n == 0) return MCB_OK;
+  CK(cudaSetDevice(h->device));
+  Scratch s{h};
+  const double *dx = s.in(x, n), *dy = s.in(y, n), *dz = s.in(z, n), *du = s.in(u, n), *dv = s.in(v, n), *dw = s.in(w, n);
+  const int* dic = s.in(icell, n);
+  double *dt = s.in<double>(nullptr, n), *dmin = s.in<double>(nullptr, n), *dmax = s.in<double>(nullptr, n);
+  int* dns = s.in<int>(nullptr, n);
+  if (!dns) return fail(h, MCB_ERR_CUDA, "scratch allocation failed");
+  const unsigned nb = (unsigned)((n + 127) / 128);
+  DISPATCH(optical_length_tot_kernel, h->m, n, lambda, dx, dy, dz, du, dv, dw, dic, dt, dmin, dmax, dns);
+  CK(cudaGetLastError());
+  s.out(tau_tot, dt, n); s.out(lmin, dmin, n); s.out(lmax, dmax, n); s.out(n_steps, dns, n);
+  CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
+}
+
+int mcfost_b200_physical_length(mcb_handle* h, int64_t n, int32_t lambda, double* x, double* y, double* z, double* u, double* v, double* w,
+                                int32_t* icell, const float* tau, float* ltot, int32_t* flag_sortie, int32_t* lpacket_alive) {
+  if (!h || n < 0) return MCB_ERR_BAD_ARG;
+  if (!h->has_grid || !h->has_op) return fail(h, MCB_ERR_STATE, "physical_length before upload_grid/opacity");
+  if (lambda < 1 || lambda > h->m.n_lambda) return fail(h, MCB_ERR_BAD_ARG, "lambda out of range");
+  if (n == 0) return MCB_OK;
+  CK(cudaSetDevice(h->device));
+  Scratch s{h};
+  double *dx = s.in(x, n), *dy = s.in(y, n), *dz = s.in(z, n), *du = s.in(u, n), *dv = s.in(v, n), *dw = s.in(w, n);
+  int* dic = s.in(icell, n);
+  const float* dtau = s.in(tau, n);
+  float* dl = s.in<float>(nullptr, n);
+  int *dfs = s.in<int>(nullptr, n), *dal = s.in<int>(nullptr, n);
+  if (!dal) return fail(h, MCB_ERR_CUDA, "scratch allocation failed");
+  const unsigned nb = (unsigned)((n + 127) / 128);
+  DISPATCH(physical_length_kernel, h->m, n, lambda, dx, dy, dz, du, dv, dw, dic, dtau, dl, dfs, dal);
+  CK(cudaGetLastError());
+  s.out(x, dx, n); s.out(y, dy, n); s.out(z, dz, n); s.out(u, du, n); s.out(v, dv, n); s.out(w, dw, n);
+  s.out(icell, dic, n); s.out(ltot, dl, n); s.out(flag_sortie, dfs, n); s.out(lpacket_alive, dal, n);
+  CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
+}
+
+}  // extern "C"

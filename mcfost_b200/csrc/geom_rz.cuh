@@ -1,0 +1,499 @@
+// Structured-grid geometry (cylindrical + spherical), device side.
+//
+// B200-native restructuring of the reference routines -- same floating-point
+// operation order (results are bit-identical to the Fortran logic when built
+// with --fmad=false), different data path:
+//   * cells are carried as (ri, zj, k) triples in registers; the reference's
+//     cell_map / cell_map_i/j/k gathers (cylindrical_grid.f90:34-35, 4 dependent
+//     loads per step) are replaced by the closed-form numbering below, which
+//     reproduces build_cylindrical_cell_mapping (cylindrical_grid.f90:45-179);
+//   * direction-only terms (1/(u^2+v^2), 1/w) are hoisted out of the per-cell
+//     loop (the reference's own "TODO: can be calculated outside", :937-953).
+//
+// Reference: cross_cylindrical_cell cylindrical_grid.f90:918-1175,
+// index_cell_cyl :833-890, test_exit_grid_cyl :680-704, move_to_grid_cyl
+// :1284-1411, pos_em_cell_cyl :1415-1466; cross_spherical_cell
+// spherical_grid.f90:182-446, index_cell_sph :48-125, move_to_grid_sph :562-615,
+// pos_em_cell_sph :619-699, test_exit_grid_sph :24-44.
+#pragma once
+#include "model.cuh"
+
+namespace mcb {
+
+struct Cell { int ri, zj, k; };
+
+__device__ __forceinline__ float max_int_f() { return (float)2147483647 * (1.0f - 1.0e-5f); }   // constants.f90:159
+
+// Fortran MODULO(a, p) for p > 0
+__device__ __forceinline__ double fmodulo(double a, double p) {
+  double r = fmod(a, p);
+  if (r != 0.0 && r < 0.0) r += p;
+  return r;
+}
+
+// ---------------- closed-form cell numbering ------------------------------
+__device__ __host__ __forceinline__ int row_index(const DevModel& m, int j) {   // 0-based among real rows
+  return m.l3D ? (j < 0 ? j + m.nz : j + m.nz - 1) : j - 1;
+}
+__device__ __host__ __forceinline__ bool is_real(const DevModel& m, Cell c) {
+  int aj = c.zj < 0 ? -c.zj : c.zj;
+  return c.ri >= 1 && c.ri <= m.n_rad && aj >= 1 && aj <= m.nz;
+}
+// linear 0-based id of a REAL cell (tally index)
+__device__ __host__ __forceinline__ int real_index(const DevModel& m, Cell c) {
+  return (c.ri - 1) + m.n_rad * (row_index(m, c.zj) + m.nj * (c.k - 1));
+}
+// reference 1-based id (real or virtual)
+__device__ __host__ __forceinline__ int cell_id(const DevModel& m, Cell c) {
+  if (is_real(m, c)) return real_index(m, c) + 1;
+  const int jstart2 = m.l3D ? -m.nz - 1 : 0, jend2 = m.nz + 1;
+  if (c.zj == jstart2 || c.zj == jend2) {
+    int row = (c.zj == jstart2) ? 0 : 1;
+    return m.n_cells + (c.k - 1) * 2 * (m.n_rad + 2) + row * (m.n_rad + 2) + c.ri + 1;
+  }
+  int base2 = m.n_cells + m.n_az * 2 * (m.n_rad + 2);
+  return base2 + (c.k - 1) * 2 * m.nj + row_index(m, c.zj) * 2 + (c.ri == 0 ? 1 : 2);
+}
+__device__ __host__ __forceinline__ Cell cell_from_id(const DevModel& m, int id) {
+  Cell c;
+  if (id <= m.n_cells) {
+    int q = id - 1;
+    c.ri = q % m.n_rad + 1; q /= m.n_rad;
+    int jr = q % m.nj; c.k = q / m.nj + 1;
+    c.zj = m.l3D ? (jr < m.nz ? jr - m.nz : jr - m.nz + 1) : jr + 1;
+    return c;
+  }
+  const int jstart2 = m.l3D ? -m.nz - 1 : 0, jend2 = m.nz + 1;
+  int base2 = m.n_cells + m.n_az * 2 * (m.n_rad + 2);
+  if (id <= base2) {
+    int q = id - m.n_cells - 1;
+    c.ri = q % (m.n_rad + 2); q /= (m.n_rad + 2);
+    c.zj = (q % 2 == 0) ? jstart2 : jend2; c.k = q / 2 + 1;
+    return c;
+  }
+  int q = id - base2 - 1;
+  c.ri = (q % 2 == 0) ? 0 : m.n_rad + 1; q /= 2;
+  int jr = q % m.nj; c.k = q / m.nj + 1;
+  c.zj = m.l3D ? (jr < m.nz ? jr - m.nz : jr - m.nz + 1) : jr + 1;
+  return c;
+}
+
+// ---------------- table accessors (1-based like the reference) -------------
+__device__ __forceinline__ double r_lim_2(const DevModel& m, int i) { return __ldg(m.r_lim_2 + i); }
+__device__ __forceinline__ double z_lim(const DevModel& m, int i, int j) { return __ldg(m.z_lim + (i - 1) + m.n_rad * (j - 1)); }
+__device__ __forceinline__ double zmax(const DevModel& m, int i) { return __ldg(m.zmax + (i - 1)); }
+__device__ __forceinline__ double tan_phi_lim(const DevModel& m, int k) { return __ldg(m.tan_phi_lim + (k - 1)); }
+__device__ __forceinline__ double tan_theta_lim(const DevModel& m, int j) { return __ldg(m.tan_theta_lim + j); }
+
+// direction-only invariants of a flight
+struct DirInv { double inv_a, inv_w; };
+__device__ __forceinline__ DirInv dir_invariants(double u, double v, double w) {
+  DirInv d;
+  double a = u * u + v * v;
+  d.inv_a = (a > MCB_TINY_REAL) ? 1.0 / a : MCB_HUGE_REAL;
+  d.inv_w = (fabs(w) > MCB_TINY_REAL) ? 1.0 / w : copysign(MCB_HUGE_DP, w);
+  return d;
+}
+
+__device__ __forceinline__ int phi_index(const DevModel& m, double x, double y) {
+  double phi = fmodulo(atan2(y, x), 2 * MCB_PI);
+  int k = (int)floor(phi / (2 * MCB_PI) * (double)(float)m.n_az) + 1;
+  if (k == m.n_az + 1) k = m.n_az;
+  return k;
+}
+
+// =========================================================================
+// cylindrical
+// =========================================================================
+template <bool L3D>
+struct GeomCyl {
+  static constexpr bool is_vor = false;
+  using CellT = Cell;
+
+  static __device__ __forceinline__ bool test_exit(const DevModel& m, Cell c, double /*x*/, double /*y*/, double z) {
+    if (is_real(m, c)) return false;
+    if (c.ri == m.n_rad + 1) return true;                          // lexit_cell == 1
+    int aj = c.zj < 0 ? -c.zj : c.zj;
+    if (aj == m.nz + 1) return fabs(z) > m.zmaxmax;                // lexit_cell == 2
+    return false;
+  }
+
+  static __device__ __forceinline__ int z_index_f32(const DevModel& m, double z, int ri) {
+    // floor(min(real(abs(z)/zmax(ri)*nz), max_int)) + 1   (cylindrical_grid.f90:868,1116: fp32 cast)
+    float q = (float)(fabs(z) / zmax(m, ri) * m.nz);
+    return (int)floorf(fminf(q, max_int_f())) + 1;
+  }
+
+  static __device__ Cell index(const DevModel& m, double x, double y, double z) {
+    Cell c;
+    double r2 = x * x + y * y;
+    if (r2 < r_lim_2(m, 0)) { c.ri = 0; c.zj = 1; c.k = 1; return c; }
+    if (r2 > m.Rmax2) { c.ri = m.n_rad + 1; c.zj = 1; c.k = 1; return c; }
+    int lo = 0, hi = m.n_rad, ri = (lo + hi) / 2;
+    while (hi - lo > 1) {
+      if (r2 > r_lim_2(m, ri)) lo = ri; else hi = ri;
+      ri = (lo + hi) / 2;
+    }
+    c.ri = ri + 1;
+    int zj = z_index_f32(m, z, c.ri);
+    if (zj > m.nz) zj = m.nz + 1;
+    c.k = 1;
+    if (L3D) {
+      if (z < 0.0) zj = -zj;
+      if (z != 0.0) c.k = phi_index(m, x, y);
+    }
+    c.zj = zj;
+    return c;
+  }
+
+  // one cell crossing; returns l (= l_contrib; l_void_before = 0)
+  static __device__ __forceinline__ double cross(const DevModel& m, DirInv d, double x0, double y0, double z0,
+                                                 double u, double v, double w, Cell c, Cell /*prev*/,
+                                                 double& x1, double& y1, double& z1, Cell& nxt,
+                                                 double& l_contrib, double& l_void) {
+    const double correct_moins = 1.0 - MCB_GRID_PREC, correct_plus = 1.0 + MCB_GRID_PREC;
+    const int ri0 = c.ri, zj0 = c.zj, k0 = c.k;
+    double s, t, t_phi;
+    int delta_rad = 1, delta_zj = 0, delta_phi = 0;
+    const double r_2 = x0 * x0 + y0 * y0;
+    const double b = (x0 * u + y0 * v) * d.inv_a;
+
+    if (ri0 == 0) {
+      double cc = (r_2 - r_lim_2(m, 0)) * d.inv_a;
+      double rac = sqrt(b * b - cc);
+      s = (-b + rac) * correct_plus;
+      t = MCB_HUGE_REAL; t_phi = MCB_HUGE_REAL;
+    } else {
+      // 1) radial wall
+      double dotprod = u * x0 + v * y0, delta;
+      if (dotprod < 0.0) {
+        double cc = (r_2 - r_lim_2(m, ri0 - 1) * correct_moins) * d.inv_a;
+        delta = b * b - cc;
+        if (delta < 0.0) {
+          cc = (r_2 - r_lim_2(m, ri0) * correct_plus) * d.inv_a;
+          delta = fmax(b * b - cc, 0.0);
+        } else delta_rad = -1;
+      } else {
+        double cc = (r_2 - r_lim_2(m, ri0) * correct_plus) * d.inv_a;
+        delta = fmax(b * b - cc, 0.0);
+      }
+      double rac = sqrt(delta);
+      s = (-b - rac) * correct_plus;
+      if (s < 0.0) s = (-b + rac) * correct_plus;
+      else if (s == 0.0) s = MCB_GRID_PREC;
+
+      // 2) horizontal wall
+      dotprod = w * z0;
+      if (dotprod == 0.0) t = (double)1.0e10f;
+      else {
+        const int aj = zj0 < 0 ? -zj0 : zj0;
+        double zlim;
+        if (dotprod > 0.0) {
+          if (aj == m.nz + 1) { delta_zj = 0; zlim = copysign(1.0e10, z0); }
+          else {
+            zlim = copysign(z_lim(m, ri0, aj + 1) * correct_plus, z0);
+            delta_zj = (L3D && z0 < 0.0) ? -1 : 1;
+          }
+        } else {
+          if (L3D) {
+            if (z0 > 0.0) { zlim = z_lim(m, ri0, aj) * correct_moins; delta_zj = (zj0 == 1) ? -2 : -1; }
+            else { zlim = -z_lim(m, ri0, aj) * correct_moins; delta_zj = (zj0 == -1) ? 2 : 1; }
+          } else {
+            if (zj0 == 1) {          // midplane mirror in 2D
+              delta_zj = 1;
+              zlim = (z0 > 0.0) ? -z_lim(m, ri0, 2) * correct_moins : z_lim(m, ri0, 2) * correct_moins;
+            } else {
+              zlim = (z0 > 0.0) ? z_lim(m, ri0, zj0) * correct_moins : -z_lim(m, ri0, zj0) * correct_moins;
+              delta_zj = -1;
+            }
+          }
+        }
+        t = (zlim - z0) * d.inv_w;
+        if (t < 0.0) t = MCB_GRID_PREC;
+      }
+
+      // 3) azimuthal wall
+      if (L3D) {
+        dotprod = x0 * v - y0 * u;
+        if (fabs(dotprod) < (double)1.0e-10f) t_phi = (double)1.0e30f;
+        else {
+          double tan_angle_lim;
+          if (dotprod > 0.0) { tan_angle_lim = tan_phi_lim(m, k0); delta_phi = 1; }
+          else { int km = k0 - 1; if (km == 0) km = m.n_az; tan_angle_lim = tan_phi_lim(m, km); delta_phi = -1; }
+          if (tan_angle_lim > 1.0e299) t_phi = (fabs(u) > (double)1e-6f) ? -x0 / u : (double)1.0e30f;
+          else {
+            double den = v - u * tan_angle_lim;
+            t_phi = (fabs(den) > (double)1.0e-6f) ? -(y0 - x0 * tan_angle_lim) / den : (double)1.0e30f;
+          }
+          if (t_phi < 0.0) t_phi = (double)1.0e30f;
+        }
+      } else t_phi = MCB_HUGE_REAL;
+    }
+
+    double l;
+    if ((s < t) && (s < t_phi)) {
+      l = s;
+      x1 = x0 + s * u; y1 = y0 + s * v; z1 = z0 + s * w;
+      nxt.ri = ri0 + delta_rad;
+      if (nxt.ri == 0) { nxt.zj = 1; nxt.k = 1; }
+      else {
+        if (nxt.ri > m.n_rad) nxt.zj = zj0;
+        else {
+          int zj1 = z_index_f32(m, z1, nxt.ri);
+          if (zj1 > m.nz) zj1 = m.nz + 1;
+          if (L3D && (z1 < 0.0)) zj1 = -zj1;
+          nxt.zj = zj1;
+        }
+        nxt.k = k0;
+        if (L3D && ri0 == 0) {
+          double phi = fmodulo(atan2(y1, x1), 2 * MCB_PI);
+          int k1 = (int)floor(phi * (1.0 / MCB_TWO_PI) * (double)(float)m.n_az) + 1;
+          if (k1 == m.n_az + 1) k1 = m.n_az;
+          nxt.k = k1;
+        }
+      }
+    } else if (t < t_phi) {
+      l = t;
+      x1 = x0 + t * u; y1 = y0 + t * v; z1 = z0 + t * w;
+      nxt.ri = ri0; nxt.zj = zj0 + delta_zj; nxt.k = k0;
+    } else {
+      l = t_phi;
+      double dv = correct_plus * t_phi;
+      x1 = x0 + dv * u; y1 = y0 + dv * v; z1 = z0 + dv * w;
+      nxt.ri = ri0;
+      int zj1 = (int)floor(fabs(z1) / zmax(m, ri0) * m.nz) + 1;       // fp64 here (:1150)
+      if (zj1 > m.nz) zj1 = m.nz + 1;
+      if (z1 < 0.0) zj1 = -zj1;
+      nxt.zj = zj1;
+      int k1 = k0 + delta_phi;
+      if (k1 == 0) k1 = m.n_az;
+      if (k1 == m.n_az + 1) k1 = 1;
+      nxt.k = k1;
+    }
+    if (z1 == 0.0) z1 = L3D ? copysign(MCB_GRID_PREC, w) : MCB_GRID_PREC;
+    l_contrib = l; l_void = 0.0;
+    return l;
+  }
+
+  static __device__ bool move_to_grid(const DevModel& m, double& x, double& y, double& z, double u, double v, double w, Cell& c) {
+    const double correct_moins = 1.0 - 1.0e-10;
+    double x0 = x, y0 = y, z0 = z;
+    DirInv d = dir_invariants(u, v, w);
+    double r_2 = x0 * x0 + y0 * y0;
+    double b = (x0 * u + y0 * v) * d.inv_a;
+    double cc = (r_2 - r_lim_2(m, m.n_rad) * correct_moins) * d.inv_a;
+    double delta = b * b - cc, s1, s2, t1, t2, delta_vol;
+    if (delta < 0.0) { s1 = MCB_HUGE_REAL; s2 = MCB_HUGE_REAL; }
+    else { double rac = sqrt(delta); s1 = -b - rac; s2 = -b + rac; }
+    double dotprod = w * z0;
+    if (fabs(dotprod) < MCB_TINY_REAL) { t1 = MCB_HUGE_REAL; t2 = MCB_HUGE_REAL; }
+    else {
+      double zlim = m.zmaxmax * correct_moins, zlim2 = -(m.zmaxmax * correct_moins);
+      if (!(z0 > 0.0)) { double tmp = zlim; zlim = zlim2; zlim2 = tmp; }
+      t1 = (zlim - z0) * d.inv_w; t2 = (zlim2 - z0) * d.inv_w;
+    }
+    if (t1 > (double)1e20f && s1 > (double)1e20f) return false;
+    if (t1 > s1) {
+      if (t1 > s2) {
+        delta_vol = s1;
+        double z1 = z0 + delta_vol * w;
+        if (fabs(z1) > m.zmaxmax) return false;
+      } else delta_vol = t1;
+    } else {
+      if (t2 < s1) return false;
+      delta_vol = s1;
+    }
+    x = x0 + delta_vol * u; y = y0 + delta_vol * v; z = z0 + delta_vol * w;
+    c = index(m, x, y, z);
+    return true;
+  }
+
+  static __device__ void pos_em_cell(const DevModel& m, Cell c, float rand1, float rand2, float rand3, double& x, double& y, double& z) {
+    const int ri = c.ri, zj = c.zj;
+    double r = sqrt(r_lim_2(m, ri - 1) + rand1 * (r_lim_2(m, ri) - r_lim_2(m, ri - 1)));
+    if (L3D) {
+      if (zj > 0) z = z_lim(m, ri, zj) + rand2 * (z_lim(m, ri, zj + 1) - z_lim(m, ri, zj));
+      else z = -(z_lim(m, ri, -zj) + rand2 * (z_lim(m, ri, -zj + 1) - z_lim(m, ri, -zj)));
+    } else {
+      if (rand2 > 0.5) z = z_lim(m, ri, zj) + (2.0 * (rand2 - 0.5)) * (z_lim(m, ri, zj + 1) - z_lim(m, ri, zj));
+      else z = -(z_lim(m, ri, zj) + (2.0 * rand2) * (z_lim(m, ri, zj + 1) - z_lim(m, ri, zj)));
+    }
+    double phi = 2.0 * MCB_PI * ((double)c.k - 1.0 + rand3) / (double)m.n_az;
+    double sp, cp; sincos(phi, &sp, &cp);
+    x = r * cp; y = r * sp;
+  }
+};
+
+// =========================================================================
+// spherical
+// =========================================================================
+template <bool L3D>
+struct GeomSph {
+  static constexpr bool is_vor = false;
+  using CellT = Cell;
+
+  static __device__ __forceinline__ bool test_exit(const DevModel& m, Cell c, double, double, double) {
+    return (!is_real(m, c)) && (c.ri == m.n_rad + 1);
+  }
+
+  static __device__ void theta_phi_index(const DevModel& m, double x, double y, double z, int& tj, int& pk) {
+    double r02 = x * x + y * y;
+    double tan_theta = (r02 > MCB_TINY_DP) ? fabs(z) / sqrt(r02) : (double)1.0e30f;
+    int lo = 0, hi = m.nz, j = (lo + hi) / 2;
+    while (hi - lo > 1) {
+      if (tan_theta > tan_theta_lim(m, j)) lo = j; else hi = j;
+      j = (lo + hi) / 2;
+    }
+    tj = j + 1; pk = 1;
+    if (L3D) {
+      if (z < 0) tj = -tj;
+      if (z != 0.0) pk = phi_index(m, x, y);
+    }
+  }
+
+  static __device__ Cell index(const DevModel& m, double x, double y, double z) {
+    Cell c;
+    double r2 = x * x + y * y + z * z;
+    // note: the reference forms r2 = (x*x+y*y) + z*z
+    r2 = (x * x + y * y) + z * z;
+    if (r2 < r_lim_2(m, 0)) { c.ri = 0; c.zj = 1; c.k = 1; return c; }
+    if (r2 > m.Rmax2) { c.ri = m.n_rad + 1; c.zj = 1; c.k = 1; return c; }
+    int lo = 0, hi = m.n_rad, ri = (lo + hi) / 2;
+    while (hi - lo > 1) {
+      if (r2 > r_lim_2(m, ri)) lo = ri; else hi = ri;
+      ri = (lo + hi) / 2;
+    }
+    c.ri = ri + 1;
+    theta_phi_index(m, x, y, z, c.zj, c.k);
+    return c;
+  }
+
+  static __device__ __forceinline__ double cone_root(double tan_lim, double x0, double y0, double z0, double u, double v, double w) {
+    const double precision = 1.0e-15;
+    double tan2 = tan_lim * tan_lim;
+    double a_theta = w * w - tan2 * (u * u + v * v);
+    double a_theta_m1 = 1.0 / a_theta;
+    double b_theta = w * z0 - tan2 * (x0 * u + y0 * v);
+    double c_theta = z0 * z0 - tan2 * (x0 * x0 + y0 * y0);
+    double delta = b_theta * b_theta - a_theta * c_theta;
+    if (delta < 0.0) return 1.0e30;
+    double rac = sqrt(delta);
+    double r1 = (-b_theta - rac) * a_theta_m1, r2 = (-b_theta + rac) * a_theta_m1;
+    if (r1 <= precision) return (r2 <= precision) ? 1.0e30 : r2;
+    return (r2 <= precision) ? r1 : fmin(r1, r2);
+  }
+
+  static __device__ __forceinline__ double cross(const DevModel& m, DirInv /*d*/, double x0, double y0, double z0,
+                                                 double u, double v, double w, Cell c, Cell /*prev*/,
+                                                 double& x1, double& y1, double& z1, Cell& nxt,
+                                                 double& l_contrib, double& l_void) {
+    const double correct_moins = 1.0 - MCB_PREC_SPH, correct_plus = 1.0 + MCB_PREC_SPH;
+    const int ri0 = c.ri, tj0 = c.zj, pk0 = c.k;
+    const int atj = tj0 < 0 ? -tj0 : tj0;
+    double s, t, t_phi;
+    int delta_rad = 1, delta_theta = 0, delta_phi = 0;
+    const double r0_2 = (x0 * x0 + y0 * y0) + z0 * z0;
+    const double b = (x0 * u + y0 * v + z0 * w);
+    if (ri0 == 0) {
+      double cc = (r0_2 - r_lim_2(m, 0) * correct_plus);
+      double rac = sqrt(b * b - cc);
+      s = (-b + rac) * correct_plus;
+      t = MCB_HUGE_REAL; t_phi = MCB_HUGE_REAL;
+    } else {
+      double delta;
+      if (b < 0.0) {
+        double cc = (r0_2 - r_lim_2(m, ri0 - 1) * correct_moins);
+        delta = b * b - cc;
+        if (delta < 0.0) { cc = (r0_2 - r_lim_2(m, ri0) * correct_plus); delta = fmax(b * b - cc, 0.0); }
+        else delta_rad = -1;
+      } else {
+        double cc = (r0_2 - r_lim_2(m, ri0) * correct_plus);
+        delta = fmax(b * b - cc, 0.0);
+      }
+      double rac = sqrt(delta);
+      s = -b - rac;
+      if (s < 0.0) s = -b + rac; else if (s == 0.0) s = MCB_GRID_PREC;
+
+      double lim1 = tan_theta_lim(m, atj) * correct_plus, lim2 = tan_theta_lim(m, atj - 1) * correct_moins;
+      if (!(z0 >= 0.0)) { lim1 = -lim1; lim2 = -lim2; }
+      double t1 = cone_root(lim1, x0, y0, z0, u, v, w);
+      double t2 = cone_root(lim2, x0, y0, z0, u, v, w);
+      if (t1 < t2) { t = t1; delta_theta = (atj == m.nz) ? 0 : 1; }
+      else { t = t2; delta_theta = (atj == 1) ? 0 : -1; }
+
+      if (L3D) {
+        double dotprod = x0 * v - y0 * u;
+        if (fabs(dotprod) < (double)1.0e-10f) { t_phi = (double)1.0e30f; delta_phi = 0; }
+        else {
+          double tan_angle_lim;
+          if (dotprod > 0.0) { tan_angle_lim = tan_phi_lim(m, pk0); delta_phi = 1; }
+          else { int km = pk0 - 1; if (km == 0) km = m.n_az; tan_angle_lim = tan_phi_lim(m, km); delta_phi = -1; }
+          if (tan_angle_lim > 1.0e299) t_phi = -x0 / u;
+          else {
+            double den = v - u * tan_angle_lim;
+            if (fabs(den) > (double)1.0e-6f) t_phi = -(y0 - x0 * tan_angle_lim) / den;
+            else { t_phi = (double)1.0e30f; delta_phi = 0; }
+          }
+          if (t_phi < 0.0) { t_phi = (double)1.0e30f; delta_phi = 0; }
+        }
+      } else t_phi = MCB_HUGE_REAL;
+    }
+    double l;
+    if ((s < t) && (s < t_phi)) {
+      l = s;
+      x1 = x0 + s * u; y1 = y0 + s * v; z1 = z0 + s * w;
+      nxt.ri = ri0 + delta_rad; nxt.zj = tj0; nxt.k = pk0;
+      if (ri0 == 0) theta_phi_index(m, x1, y1, z1, nxt.zj, nxt.k);
+      if (nxt.ri == 0) { nxt.zj = 1; nxt.k = 1; }
+    } else if (t < t_phi) {
+      l = t;
+      x1 = x0 + t * u; y1 = y0 + t * v; z1 = z0 + t * w;
+      nxt.ri = ri0; nxt.zj = atj + delta_theta;
+      if (L3D) { if (z1 < 0) nxt.zj = -nxt.zj; }
+      nxt.k = pk0;
+    } else {
+      l = t_phi;
+      double dv = correct_plus * t_phi;
+      x1 = x0 + dv * u; y1 = y0 + dv * v; z1 = z0 + dv * w;
+      nxt.ri = ri0; nxt.zj = tj0;
+      int k1 = pk0 + delta_phi;
+      if (k1 == 0) k1 = m.n_az;
+      if (k1 == m.n_az + 1) k1 = 1;
+      nxt.k = k1;
+    }
+    if (z1 == 0.0) z1 = MCB_GRID_PREC;
+    l_contrib = l; l_void = 0.0;
+    return l;
+  }
+
+  static __device__ bool move_to_grid(const DevModel& m, double& x, double& y, double& z, double u, double v, double w, Cell& c) {
+    const double correct_moins = 1.0 - 1.0e-10;
+    double r0_2 = x * x + y * y + z * z;
+    double b = (x * u + y * v + z * w);
+    double cc = (r0_2 - r_lim_2(m, m.n_rad) * correct_moins);
+    double delta = b * b - cc;
+    if (delta < 0.0) return false;
+    double s1 = -b - sqrt(delta);
+    double x1 = x + s1 * u, y1 = y + s1 * v, z1 = z + s1 * w;
+    c = index(m, x1, y1, z1);
+    x = x1; y = y1; z = z1;
+    return true;
+  }
+
+  static __device__ void pos_em_cell(const DevModel& m, Cell c, float rand1, float rand2, float rand3, double& x, double& y, double& z) {
+    const int ri = c.ri, tj = c.zj, atj = tj < 0 ? -tj : tj;
+    double r3a = __ldg(m.r_lim_3 + ri - 1), r3b = __ldg(m.r_lim_3 + ri);
+    double r = pow(r3a + rand1 * (r3b - r3a), 1.0 / 3.0);
+    double ta = __ldg(m.theta_lim + atj - 1), tb = __ldg(m.theta_lim + atj), theta;
+    if (L3D) theta = ta + rand2 * (tb - ta);
+    else theta = (rand2 > 0.5) ? ta + (2.0 * (rand2 - 0.5)) * (tb - ta) : -(ta + (2.0 * rand2) * (tb - ta));
+    double phi = 2.0 * MCB_PI * ((double)(float)c.k - 1.0 + rand3) / (double)(float)m.n_az;
+    double st, ct, sp, cp;
+    sincos(theta, &st, &ct); sincos(phi, &sp, &cp);
+    z = r * st;
+    double rc = r * ct;
+    x = rc * cp; y = rc * sp;
+  }
+};
+
+}  // namespace mcb

@@ -1,0 +1,153 @@
+// Voronoi-mesh geometry, device side.
+// Reference: cross_Voronoi_cell Voronoi.f90:839-992, distance_to_wall :1289-1317,
+// distance_to_star :1321-1375, move_to_grid_Voronoi :1379-1442,
+// test_exit_grid_Voronoi :1446-1459, is_in_volume :1463-1478,
+// pos_em_cell_voronoi :1510-1543 (emits from the cell centre: the displacement
+// line is commented out, :1539), index_cell_voronoi :1548-1572.
+//
+// The plane tests are fp32 exactly like the reference (`real, dimension(3) ::
+// n, p, r, k`, :860).  Data path: seeds are read from a float4 fp32 copy
+// (one 16-byte vector load per neighbour, the analogue of Voronoi_xyz :61);
+// the per-cell header (first/last neighbour, flags) is read once per crossing.
+#pragma once
+#include "model.cuh"
+
+namespace mcb {
+
+struct GeomVor {
+  static constexpr bool is_vor = true;
+  using CellT = int;
+
+  static __device__ __forceinline__ bool test_exit(const DevModel&, int c, double, double, double) { return c < 0; }
+
+  static __device__ __forceinline__ double distance_to_wall(const DevModel& m, double x, double y, double z,
+                                                            double u, double v, double w, int iwall) {
+    const double n0 = m.wall[iwall - 1][0], n1 = m.wall[iwall - 1][1], n2 = m.wall[iwall - 1][2], d = m.wall[iwall - 1][3];
+    const double p0 = d * fabs(n0), p1 = d * fabs(n1), p2 = d * fabs(n2);
+    const float den = (float)(n0 * u + n1 * v + n2 * w);
+    if (fabsf(den) > FLT_MIN) return (n0 * (p0 - x) + n1 * (p1 - y) + n2 * (p2 - z)) / (double)den;
+    return MCB_HUGE_REAL;
+  }
+  static __device__ __forceinline__ bool is_in_volume(const DevModel& m, double x, double y, double z) {
+    return (x > m.wall[0][3]) && (x < m.wall[1][3]) && (y > m.wall[2][3]) && (y < m.wall[3][3]) && (z > m.wall[4][3]) && (z < m.wall[5][3]);
+  }
+  // O(n_cells) nearest seed with fp32 distances (reference behaviour; only reached on
+  // the rounding fallback of cross and on entry from outside)
+  static __device__ int index(const DevModel& m, double x, double y, double z) {
+    float best = FLT_MAX; int ic = 0;
+    for (int i = 0; i < m.n_cells; ++i) {
+      const double dx = __ldg(m.vor_xyz + 3 * (size_t)i) - x, dy = __ldg(m.vor_xyz + 3 * (size_t)i + 1) - y, dz = __ldg(m.vor_xyz + 3 * (size_t)i + 2) - z;
+      const float d2 = (float)(dx * dx + dy * dy + dz * dz);
+      if (d2 < best) { best = d2; ic = i + 1; }
+    }
+    return ic;
+  }
+  static __device__ __forceinline__ double distance_to_star(const DevModel& m, double x, double y, double z, double u, double v, double w, int& i_star) {
+    double dmin = MCB_HUGE_DP;
+    i_star = 0;
+    for (int i = 0; i < m.n_stars; ++i) {
+      const double dx = x - m.star[i][0], dy = y - m.star[i][1], dz = z - m.star[i][2];
+      const double b = dx * u + dy * v + dz * w;
+      const double c = dx * dx + dy * dy + dz * dz - m.star[i][3] * m.star[i][3];
+      const double delta = b * b - c;
+      if (delta >= 0.) {
+        const double rac = sqrt(delta), s1 = -b - rac;
+        if (s1 < 0) { const double s2 = -b + rac; if (s2 > 0) { dmin = 0.0; i_star = i + 1; } }
+        else if (s1 < dmin) { dmin = s1; i_star = i + 1; }
+      }
+    }
+    return dmin;
+  }
+
+  static __device__ double cross(const DevModel& m, DirInv, double x, double y, double z, double u, double v, double w,
+                                 int icell, int previous_cell, double& x1, double& y1, double& z1, int& next_cell,
+                                 double& s_contrib, double& s_void_before) {
+    const double prec = (double)1e-5f;
+    const float rx = (float)x, ry = (float)y, rz = (float)z, kx = (float)u, ky = (float)v, kz = (float)w;
+    double s = (double)1e30f;
+    next_cell = 0;
+    const float4 rc = __ldg(m.vor_xyz32 + (icell - 1));
+    const int ifirst = __ldg(m.vor_first + icell - 1), ilast = __ldg(m.vor_last + icell - 1);
+    const unsigned flags = __ldg(m.vor_flags + icell - 1);
+    for (int i = ifirst; i <= ilast; ++i) {
+      const int id_n = __ldg(m.neigh + i - 1);
+      if (id_n == previous_cell) continue;
+      double s_tmp;
+      if (id_n > 0) {
+        const float4 rn = __ldg(m.vor_xyz32 + (id_n - 1));
+        const float nx = __fsub_rn(rn.x, rc.x), ny = __fsub_rn(rn.y, rc.y), nz = __fsub_rn(rn.z, rc.z);
+        const float denf = __fadd_rn(__fadd_rn(__fmul_rn(nx, kx), __fmul_rn(ny, ky)), __fmul_rn(nz, kz));
+        if (!(denf > 0.f)) continue;
+        const float px = __fmul_rn(0.5f, __fadd_rn(rn.x, rc.x)), py = __fmul_rn(0.5f, __fadd_rn(rn.y, rc.y)), pz = __fmul_rn(0.5f, __fadd_rn(rn.z, rc.z));
+        const float dot = __fadd_rn(__fadd_rn(__fmul_rn(nx, __fsub_rn(px, rx)), __fmul_rn(ny, __fsub_rn(py, ry))), __fmul_rn(nz, __fsub_rn(pz, rz)));
+        s_tmp = (double)dot / (double)denf;
+        if (s_tmp < 0.) s_tmp = MCB_HUGE_REAL;
+      } else {
+        s_tmp = distance_to_wall(m, x, y, z, u, v, w, -id_n);
+        if (s_tmp < 0.) s_tmp = MCB_HUGE_REAL;
+      }
+      if (s_tmp < s) { s = s_tmp; next_cell = id_n; }
+    }
+    s = s * (1.0 + prec);
+    x1 = x + u * s; y1 = y + v * s; z1 = z + w * s;
+    if (next_cell == 0) {
+      x1 = x; y1 = y; z1 = z; s = 0.0;
+      if (is_in_volume(m, x, y, z)) {
+        next_cell = index(m, x, y, z);
+        if (icell == next_cell) next_cell = -1;
+      } else next_cell = -1;
+    }
+    if (flags & 1u) {       // was_cut
+      const double dx = (double)__fsub_rn(rx, rc.x), dy = (double)__fsub_rn(ry, rc.y), dz = (double)__fsub_rn(rz, rc.z);
+      const double b = dx * (double)kx + dy * (double)ky + dz * (double)kz;
+      const double hc = __ldg(m.vor_h + icell - 1) * m.cut_o_h;
+      const double c = dx * dx + dy * dy + dz * dz - hc * hc;
+      const double delta = b * b - c;
+      if (delta < 0.) { s_void_before = s; s_contrib = 0.0; }
+      else {
+        const double rac = sqrt(delta), s1 = -b - rac, s2 = -b + rac;
+        if (s1 < 0) {
+          if (s2 < 0) { s_void_before = s; s_contrib = 0.0; }
+          else { s_void_before = 0.0; s_contrib = fmin(s2, s); }
+        } else {
+          if (s1 < s) { s_void_before = s1; s_contrib = fmin(s2, s) - s1; }
+          else { s_void_before = s; s_contrib = 0.0; }
+        }
+      }
+    } else { s_void_before = 0.0; s_contrib = s; }
+    if (flags & 4u) {       // is_star_neighbour
+      int i_star;
+      const double d_to_star = distance_to_star(m, x, y, z, u, v, w, i_star);
+      if (i_star > 0 && d_to_star < s) { s_contrib = d_to_star; next_cell = m.star_icell[i_star - 1]; }
+    }
+    return s;
+  }
+
+  static __device__ bool move_to_grid(const DevModel& m, double& x, double& y, double& z, double u, double v, double w, int& c) {
+    const double prec = 1.e-6;
+    double sw[6]; int order[6];
+    for (int iw = 1; iw <= 6; ++iw) {
+      const double l = distance_to_wall(m, x, y, z, u, v, w, iw);
+      sw[iw - 1] = (l >= 0) ? l * (1.0 + prec) : MCB_HUGE_REAL;
+      order[iw - 1] = iw;
+    }
+    for (int a = 1; a < 6; ++a) {      // stable insertion sort
+      int o = order[a]; int b = a - 1;
+      while (b >= 0 && sw[order[b] - 1] > sw[o - 1]) { order[b + 1] = order[b]; --b; }
+      order[b + 1] = o;
+    }
+    for (int i = 0; i < 6; ++i) {
+      const double l = sw[order[i] - 1];
+      const double xt = x + l * u, yt = y + l * v, zt = z + l * w;
+      if (is_in_volume(m, xt, yt, zt)) { x = xt; y = yt; z = zt; c = index(m, x, y, z); return true; }
+    }
+    c = 0;
+    return false;
+  }
+
+  static __device__ void pos_em_cell(const DevModel& m, int c, float, float, float, double& x, double& y, double& z) {
+    x = __ldg(m.vor_xyz + 3 * (size_t)(c - 1)); y = __ldg(m.vor_xyz + 3 * (size_t)(c - 1) + 1); z = __ldg(m.vor_xyz + 3 * (size_t)(c - 1) + 2);
+  }
+};
+
+}  // namespace mcb

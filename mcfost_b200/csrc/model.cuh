@@ -1,0 +1,93 @@
+// Device-side view of everything uploaded through the C ABI (include/mcfost_b200.h).
+// One DevModel per handle, passed to kernels by value as a __grid_constant__
+// parameter (constant bank, broadcast to every warp).
+#pragma once
+#include <cstdint>
+#include <cfloat>
+
+namespace mcb {
+
+constexpr int MAX_STARS = 8;
+constexpr int NANG = 180;      // nang_scatt
+constexpr int N_AZ_RT = 45;    // n_az_rt
+constexpr int MAX_RT = 8;      // max RT_n_incl * RT_n_az observer directions
+
+// numerical constants of the reference (constants.f90:8-14,151-159)
+#define MCB_PI       3.141592653589793238462643383279502884197
+#define MCB_TWO_PI   (2.0 * MCB_PI)
+#define MCB_HALF_PI  (0.5 * MCB_PI)
+#define MCB_TINY_REAL ((double)FLT_MIN)
+#define MCB_HUGE_REAL ((double)FLT_MAX)
+#define MCB_HUGE_DP   DBL_MAX
+#define MCB_TINY_DP   DBL_MIN
+#define MCB_GRID_PREC 1.0e-14            /* cylindrical_grid.f90:16 */
+#define MCB_PREC_SPH  1.0e-7             /* spherical_grid.f90:19   */
+
+enum GridKind { GK_CYL2D = 0, GK_CYL3D = 1, GK_SPH2D = 2, GK_SPH3D = 3, GK_VOR = 4 };
+
+// tally block offsets inside the packed fp64 buffer
+struct TallyLayout {
+  int64_t xKJ, xJ, n_env, sed, stats, total;   // offsets in doubles
+  int64_t n_sed;                               // n_lambda*N_thet*N_phi
+};
+
+struct DevModel {
+  // ---- grid (cylindrical_grid.f90:20-41) --------------------------------
+  int kind, l3D, n_rad, nz, n_az, n_cells, nj;   // nj = rows per azimuth (nz or 2 nz)
+  double Rmax2, zmaxmax;
+  const double *r_lim_2, *r_lim_3, *z_lim, *zmax, *tan_theta_lim, *theta_lim, *tan_phi_lim, *volume;
+  const double *kappa_factor;       // (n_cells)
+  const uint8_t *dark;              // (n_cells) l_dark_zone
+  // ---- Voronoi (Voronoi.f90:23-66) --------------------------------------
+  const double *vor_xyz;            // (3, n_cells) fp64
+  const float4 *vor_xyz32;          // fp32 copy (Voronoi_xyz, :61), one float4 per cell
+  const double *vor_h;
+  const int *vor_first, *vor_last, *neigh;
+  const uint8_t *vor_flags;         // bit0 was_cut, bit1 is_star, bit2 is_star_neighbour
+  float wall[6][4];
+  double cut_o_h;
+  // ---- stars ------------------------------------------------------------
+  int n_stars;
+  double star[MAX_STARS][4];
+  int star_icell[MAX_STARS], star_out[MAX_STARS];
+  // ---- opacity ----------------------------------------------------------
+  int n_lambda, p_n_cells, p_n_lambda_pos, n_T;
+  const double *kappa, *kappa_abs;          // (p_n_cells, n_lambda)
+  const float *albedo, *gfac;               // (p_n_cells, n_lambda)
+  const float *prob_s11, *s11, *s12, *s22, *s33, *s34, *s44;   // (0:180, p_n_cells, p_n_lambda_pos)
+  const double *logQ;                       // (n_T, p_n_cells)
+  const double *kdB;                        // (n_lambda, n_T, p_n_cells)
+  const double *cos_tab;                    // cos(k*pi/180), k = 0..180 (host libm)
+  float T_min;
+  // ---- emission ---------------------------------------------------------
+  const double *spec_cumul, *frac_star, *frac_disk, *prob_E_cell;
+  const float *CDF_E_star;
+  double L_packet_th, E_paquet, R_ISM, cISM[3];
+  // ---- tallies ----------------------------------------------------------
+  double *tally;            // packed fp64 block
+  TallyLayout lay;
+  int *xT_ech;              // (n_cells)
+  float *xI;                // xI_scatt
+  unsigned long long *work; // [0] = next work item
+};
+
+// run parameters broadcast to the kernel
+struct DevRun {
+  int lambda_in, p_lambda_in, n_photons2, nnfot1_start, n_photons_loop;
+  float n_phot_lim;
+  int letape_th, lmono, lsepar_pola, lsepar_contrib, lmethod_aniso1, lisotropic;
+  int l_sym_centrale, l_sym_axiale, rt1, lxJ;
+  int N_thet, N_phi, capt_sup, n_type_flux, n_stokes;
+  int n_rt, RT_n_incl, RT_n_az;
+  double rt_u[MAX_RT], rt_v[MAX_RT], rt_w[MAX_RT];
+  unsigned long long seed;
+  unsigned int call_index;
+  int rank, n_ranks, n_local_chunks;
+  int count_sent;                       // 1: chunk ends after n_photons2 packets SENT (thermal / image), 0: RECEIVED (SED)
+  unsigned long long sent_lim;          // ceil(n_phot_lim) (saturated)
+  unsigned long long n_per_chunk;       // count_sent: min(n_photons2, sent_lim)
+  unsigned long long n_packets_total;   // count_sent: n_local_chunks * min(n_photons2, sent_lim)
+  double nb_proc_equiv;                 // n_ranks: scales the local tally in Temp_LTE
+};
+
+}  // namespace mcb

@@ -254,7 +254,7 @@ def spherical_grid(n_rad=60, nz=30, n_az=1, n_rad_in=5, rin=10.0, rout=200.0, l3
     P.volume = V[ii, ja].copy()
     P.r_grid = rg[ii, ja].copy()
     P.z_grid = np.where(jj > 0, zg[ii, ja], -zg[ii, ja])
-    P.phi_grid = np.zeros(nc)
+    P.phi_grid = (2.0 * PI / n_az * (kk - 0.5)) if l3D else np.zeros(nc)
     P.z_lim = np.zeros((n_rad, nz + 2), order="F"); P.zmax = np.ones(n_rad); P.zmaxmax = 0.0
     P.zones = [zone]
     return P
@@ -526,7 +526,17 @@ def define_dark_zone(P, lambda_idx, tau_max=1500.0, physical_length=None):
 # ---------------------------------------------------------------------------
 # the benchmark configurations
 # ---------------------------------------------------------------------------
-def _finish(P, zones, n_lambda, n_T, tau_mid, pola, isotropic, n_photons_eq_th, star_T, star_R):
+def envelope_density(P, azimuthal=0.0):
+    """Synthetic envelope for the spherical grids: rho ~ r^-1.5 (1 + cos^2(colatitude))
+    with an optional m=1 azimuthal modulation so that phi walls matter in 3D."""
+    rs = np.sqrt(P.r_grid ** 2 + P.z_grid ** 2)
+    rho = rs ** -1.5 * (1.0 + (P.z_grid / rs) ** 2)
+    if azimuthal:
+        rho = rho * (1.0 + azimuthal * np.cos(P.phi_grid))
+    return rho
+
+
+def _finish(P, rho, n_lambda, n_T, tau_mid, pola, isotropic, n_photons_eq_th, star_T, star_R):
     P.n_lambda, P.n_T = n_lambda, n_T
     P.tab_lambda, P.tab_delta_lambda = init_lambda(n_lambda)
     P.tab_lambda = np.float32(P.tab_lambda).astype(np.float64)          # `real` tables in the reference
@@ -540,9 +550,8 @@ def _finish(P, zones, n_lambda, n_T, tau_mid, pola, isotropic, n_photons_eq_th, 
     P.star_T = np.array([star_T])
     P.star_out_model = np.zeros(1, np.int32)
     # density and opacities (lvariable_dust = .false. => p_n_cells = 1)
-    rho = disk_density(P, zones)
     P.p_n_cells, P.p_n_lambda_pos = 1, n_lambda
-    rho0 = rho[0]
+    rho0 = rho[int(np.argmax(rho))]          # icell_not_empty stand-in: the densest cell
     P.kappa_factor = rho / rho0
     kext, albedo, g, s11, pol = synthetic_optics(P.tab_lambda, pola=pola, isotropic=isotropic)
     # scale so that the radial midplane optical depth at 0.81 um is tau_mid
@@ -597,7 +606,7 @@ def ref41_like(n_photons_eq_th=1000, tau_mid=1.0e5, pola=True, n_rad=100, nz=70,
     0.1-3000 um, n_T=100) with the synthetic optics."""
     zones = [DiskZone()]
     P = cylindrical_grid(n_rad, nz, 1, n_rad_in, zones, l3D=False)
-    _finish(P, zones, n_lambda, n_T, tau_mid, pola, isotropic, n_photons_eq_th, 5000.0, 2.0)
+    _finish(P, disk_density(P, zones), n_lambda, n_T, tau_mid, pola, isotropic, n_photons_eq_th, 5000.0, 2.0)
     P.star_icell = np.array([star_icell_analytic(P)], np.int32)
     if dark_zone:
         P.l_dark_zone = define_dark_zone(P, P.lambda_seuil, 1500.0, physical_length)
@@ -607,12 +616,15 @@ def ref41_like(n_photons_eq_th=1000, tau_mid=1.0e5, pola=True, n_rad=100, nz=70,
 
 
 def ref41_3d_like(n_photons_eq_th=1000, tau_mid=1.0e3, n_rad=100, nz=50, n_az=72, n_rad_in=20,
-                  n_lambda=50, n_T=100, pola=False):
+                  n_lambda=50, n_T=100, pola=False, spiral=0.5):
     """G4: ref4.1_3D.para geometry: 100 x (2x50) x 72 = 720 000 cells, no dark zone
     (dust_transfer.f90:290-293)."""
     zones = [DiskZone()]
     P = cylindrical_grid(n_rad, nz, n_az, n_rad_in, zones, l3D=True)
-    _finish(P, zones, n_lambda, n_T, tau_mid, pola, False, n_photons_eq_th, 5000.0, 2.0)
+    rho = disk_density(P, zones)
+    if spiral:      # m=2 spiral perturbation so that azimuthal walls matter
+        rho = rho * (1.0 + spiral * np.cos(2.0 * (P.phi_grid - np.log(P.r_grid))))
+    _finish(P, rho, n_lambda, n_T, tau_mid, pola, False, n_photons_eq_th, 5000.0, 2.0)
     P.star_icell = np.array([star_icell_analytic(P)], np.int32)
     repartition_energie(P)
     P.name = "ref4.1_3D-like (G4)"
@@ -623,7 +635,7 @@ def spherical_shell(n_photons_eq_th=1000, tau_mid=10.0, n_rad=60, nz=30, n_az=1,
                     n_lambda=50, n_T=100, pola=False, isotropic=False):
     """debris.para-style spherical grid (test_data/debris/debris.para:15)."""
     P = spherical_grid(n_rad, nz, n_az, 5, 10.0, 200.0, l3D=l3D)
-    _finish(P, P.zones, n_lambda, n_T, tau_mid, pola, isotropic, n_photons_eq_th, 5000.0, 2.0)
+    _finish(P, envelope_density(P, 0.5 if l3D else 0.0), n_lambda, n_T, tau_mid, pola, isotropic, n_photons_eq_th, 5000.0, 2.0)
     P.star_icell = np.array([star_icell_analytic(P)], np.int32)
     repartition_energie(P)
     P.name = "spherical shell"

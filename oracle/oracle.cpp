@@ -1327,9 +1327,9 @@ struct Oracle {
         rand2 = (float)rng_next(&rng);
         if (r.lmethod_aniso1) {
           angle_diff_theta_pos(p_lambda, p_icell, rand, rand2, itheta, cospsi);
-          if (r.lisotropic) { itheta = 1; cospsi = 2.0 * rand - 1.0; }
+          if (r.lisotropic) { itheta = 1; cospsi = (double)(2.0f * rand - 1.0f); }    // :1325 fp32 expression
           rand = (float)rng_next(&rng);
-          phi = pi * (2.0 * rand - 1.0);
+          phi = pi * (double)(2.0f * rand - 1.0f);                                      // :1329 PI*(2.0*rand-1.0): fp32 inner
           cdapres(cospsi, phi, p.u, p.v, p.w, u1, v1, w1);
           if (r.lsepar_pola) {
             get_Mueller_matrix_per_cell(lambda, itheta, rand2, p_icell, M);
@@ -1337,9 +1337,9 @@ struct Oracle {
           }
         } else {
           hg(tab_g_pos(p_icell, lambda), rand, itheta, cospsi);
-          if (r.lisotropic) { itheta = 1; cospsi = 2.0 * rand - 1.0; }
+          if (r.lisotropic) { itheta = 1; cospsi = (double)(2.0f * rand - 1.0f); }    // :1340
           rand = (float)rng_next(&rng);
-          phi = pi * (2.0 * rand - 1.0);
+          phi = pi * (double)(2.0f * rand - 1.0f);                                      // :1344
           cdapres(cospsi, phi, p.u, p.v, p.w, u1, v1, w1);
         }
         p.u = u1; p.v = v1; p.w = w1;
