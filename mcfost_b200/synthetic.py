@@ -640,3 +640,28 @@ def spherical_shell(n_photons_eq_th=1000, tau_mid=10.0, n_rad=60, nz=30, n_az=1,
     repartition_energie(P)
     P.name = "spherical shell"
     return P
+
+
+# ---------------------------------------------------------------------------
+# caller-side post-processing (stays Fortran in production; numpy here for tests)
+# ---------------------------------------------------------------------------
+def temp_finale(P, xKJ_abs, n_ranks_total_scale=1.0):
+    """Temp_finale + Temp_LTE(id=0), thermal_emission.f90:649-706,870-906:
+    final dust temperature from the merged absorbed-energy tally."""
+    xKJ = np.asarray(xKJ_abs, np.float64) * n_ranks_total_scale
+    Qheat = xKJ * P.L_packet_th / P.volume
+    logQ = P.log_Qcool_minus_extra_heating
+    pnc = P.p_n_cells
+    T = np.full(P.n_cells, float(P.T_min))
+    ltab = np.log(P.tab_Temp.astype(np.float64))
+    ok = Qheat >= np.finfo(np.float64).tiny
+    lq = np.log(np.where(ok, Qheat, 1.0))
+    for ic in np.nonzero(ok)[0]:
+        col = logQ[:, ic if pnc > 1 else 0]
+        if lq[ic] < col[0]:
+            continue
+        Ti = int(np.searchsorted(col, lq[ic], side="left")) + 1      # first Ti with col(Ti) >= lq, 1-based
+        Ti = min(max(Ti, 2), P.n_T)
+        frac = (lq[ic] - col[Ti - 2]) / (col[Ti - 1] - col[Ti - 2])
+        T[ic] = np.exp(ltab[Ti - 1] * frac + ltab[Ti - 2] * (1.0 - frac))
+    return T

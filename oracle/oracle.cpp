@@ -103,6 +103,7 @@ struct Oracle {
   int nb_proc = 1;
   std::vector<ThreadTallies> T;
   int N_type_flux = 1, n_Stokes = 1;
+  double* ev_out = nullptr;      // optional per-packet event counts (instrumentation)
 
   bool lvariable_dust() const { return o.p_n_cells != 1; }
   bool lVoronoi() const { return g.kind == MCB_GRID_VORONOI; }
@@ -1449,6 +1450,7 @@ struct Oracle {
           t.n_phot_envoyes[lambda_local - 1] += 1.0;            // :531 (previous packet's lambda in thermal mode)
           n_phot_envoyes_in_loop += 1.0;
           t.stats[0] += 1;
+          const double ev0 = t.stats[1] + t.stats[2];
           Packet p;
           if (!r.lmono) { float rand = (float)rng_next(&rng); select_wl_em(rand, lambda_local); }
           p.lambda = lambda_local;
@@ -1460,6 +1462,7 @@ struct Oracle {
             if (capt == r.capt_sup) n_phot_sed2 += 1.0;
             t.stats[6] += 1;
           } else if (!p.alive) t.stats[5] += 1;
+          if (ev_out && count_sent) ev_out[(size_t)(nnfot1 - 1) * n_photons2_local + (size_t)(nnfot2 - 1.0)] = t.stats[1] + t.stats[2] - ev0;
         }
       }
     }
@@ -1597,6 +1600,8 @@ void oracle_rng_stream(uint64_t seed, uint32_t call_index, uint64_t packet, int 
   PacketRng g; std::memset(&g, 0, sizeof g); rng_seed_packet(&g, seed, call_index, packet);
   for (int i = 0; i < n; ++i) out[i] = rng_next(&g);
 }
+// instrumentation: per-packet (cell steps + interactions), thermal mode, length n_photons_loop*n_photons2
+void oracle_set_event_buffer(void* h, double* buf) { ((Oracle*)h)->ev_out = buf; }
 int oracle_max_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -1,0 +1,246 @@
+"""GPU parity tests (run on the B200 box with -m gpu): every call goes through the
+C ABI of libmcfost_b200.so; the oracle is only the checker.
+
+Bars (BASELINE.json north_star): deterministic sub-kernels -- cell indices
+bit-exact, lengths within 1e-12 relative (they are in fact required bit-equal
+here); Monte Carlo -- temperature median |dT/T| < 1 %, SED within 3 sigma."""
+import numpy as np
+import pytest
+
+from mcfost_b200 import api, synthetic as S
+from oracle.binding import Oracle
+
+from helpers import rays_in_cells, rays_from_outside, small_problems
+
+pytestmark = pytest.mark.gpu
+
+GRIDS = ["cyl2D", "cyl3D", "sph2D", "sph3D"]
+
+
+@pytest.fixture(scope="module")
+def pairs():
+    out = {}
+    for name in GRIDS:
+        P = small_problems()[name]()
+        out[name] = (P, Oracle(P), api.PhotonLoop(P))       # upload_grid verifies the cell numbering
+    yield out
+    for _, _, g in out.values():
+        g.close()
+
+
+@pytest.mark.parametrize("name", GRIDS)
+def test_index_cell_bit_exact(pairs, name):
+    P, O, G = pairs[name]
+    ic, x, y, z, *_ = rays_in_cells(P, 100000, seed=21)
+    assert np.array_equal(G.index_cell(x, y, z), O.index_cell(x, y, z))
+    # points outside / inside the inner hole / on the axis
+    xs, ys, zs, *_ = rays_from_outside(P, 2000)
+    x2 = np.concatenate([xs, 0.1 * x[:1000], np.zeros(10)]); y2 = np.concatenate([ys, 0.1 * y[:1000], np.zeros(10)])
+    z2 = np.concatenate([zs, 0.1 * z[:1000], np.linspace(-1, 1, 10)])
+    assert np.array_equal(G.index_cell(x2, y2, z2), O.index_cell(x2, y2, z2))
+
+
+@pytest.mark.parametrize("name", GRIDS)
+def test_cross_cell_bit_exact(pairs, name):
+    P, O, G = pairs[name]
+    ic, x, y, z, u, v, w = rays_in_cells(P, 200000, seed=22)
+    o, g = O.cross_cell(x, y, z, u, v, w, ic), G.cross_cell(x, y, z, u, v, w, ic)
+    assert np.array_equal(g["next_cell"], o["next_cell"])
+    for k in ("l", "l_contrib", "l_void_before", "x1", "y1", "z1"):
+        assert np.array_equal(g[k], o[k]), k
+    # second crossing from the exit points (exercises virtual cells and wall-hugging starts)
+    o2 = O.cross_cell(o["x1"], o["y1"], o["z1"], u, v, w, o["next_cell"], ic)
+    g2 = G.cross_cell(o["x1"], o["y1"], o["z1"], u, v, w, o["next_cell"], ic)
+    assert np.array_equal(g2["next_cell"], o2["next_cell"]) and np.array_equal(g2["l"], o2["l"])
+    # axis-aligned / degenerate directions
+    n = 3000
+    uu = np.zeros(n); vv = np.zeros(n); ww = np.zeros(n)
+    uu[:1000] = 1.0; vv[1000:2000] = -1.0; ww[2000:] = np.where(np.arange(1000) % 2 == 0, 1.0, -1.0)
+    o3 = O.cross_cell(x[:n], y[:n], z[:n], uu, vv, ww, ic[:n]); g3 = G.cross_cell(x[:n], y[:n], z[:n], uu, vv, ww, ic[:n])
+    assert np.array_equal(g3["next_cell"], o3["next_cell"]) and np.array_equal(g3["l"], o3["l"])
+
+
+@pytest.mark.parametrize("name", GRIDS)
+def test_move_to_grid_bit_exact(pairs, name):
+    P, O, G = pairs[name]
+    x, y, z, u, v, w = rays_from_outside(P, 50000)
+    o, g = O.move_to_grid(x, y, z, u, v, w), G.move_to_grid(x, y, z, u, v, w)
+    assert np.array_equal(g["lintersect"], o["lintersect"]) and np.array_equal(g["icell"], o["icell"])
+    for k in ("x", "y", "z"):
+        assert np.array_equal(g[k], o[k]), k
+
+
+@pytest.mark.parametrize("name", GRIDS)
+def test_tau_integration_along_fixed_rays(pairs, name):
+    P, O, G = pairs[name]
+    ic, x, y, z, u, v, w = rays_in_cells(P, 30000, seed=23)
+    o = O.optical_length_tot(P.lambda_seuil, x, y, z, u, v, w, ic)
+    g = G.optical_length_tot(P.lambda_seuil, x, y, z, u, v, w, ic)
+    assert np.array_equal(g["n_steps"], o["n_steps"])                  # identical cell walks
+    assert np.allclose(g["tau_tot"], o["tau_tot"], rtol=1e-12, atol=0)
+    assert np.allclose(g["lmax"], o["lmax"], rtol=1e-12, atol=0) and np.allclose(g["lmin"], o["lmin"], rtol=1e-12, atol=0)
+    tau = np.random.default_rng(3).exponential(3.0, len(x)).astype(np.float32)
+    o = O.physical_length(P.lambda_seuil, x, y, z, u, v, w, ic, tau)
+    g = G.physical_length(P.lambda_seuil, x, y, z, u, v, w, ic, tau)
+    for k in ("flag_sortie", "lpacket_alive", "icell"):
+        assert np.array_equal(g[k], o[k]), k
+    for k in ("x", "y", "z", "ltot"):
+        assert np.allclose(g[k], o[k], rtol=1e-12, atol=0), k
+
+
+def test_empty_and_error_paths():
+    P = small_problems()["cyl2D"]()
+    G = api.PhotonLoop(P)
+    e = np.zeros(0)
+    assert len(G.index_cell(e, e, e)) == 0
+    assert len(G.cross_cell(e, e, e, e, e, e, np.zeros(0, np.int32))["l"]) == 0
+    with pytest.raises(api.McfostB200Error) as err:
+        G.mc_photon_loop(1, 1, 10, lonly_LTE=0)
+    assert err.value.code == 5         # MCB_ERR_UNSUPPORTED: fails loudly, no silent fallback
+    with pytest.raises(api.McfostB200Error):
+        G.mc_photon_loop(P.n_lambda + 1, 1, 10)
+    t = G.mc_photon_loop(1, 1, 0)      # zero packets
+    assert t.stats[0] == 0 and t.xKJ_abs.sum() == 0
+    # a corrupted cell map is rejected
+    P2 = small_problems()["cyl2D"]()
+    P2.cell_map_i = P2.cell_map_i.copy(); P2.cell_map_i[3] += 1
+    with pytest.raises(api.McfostB200Error) as err:
+        api.PhotonLoop(P2)
+    assert err.value.code == 3
+    G.close()
+
+
+def test_dark_zone_definition_matches_oracle():
+    """define_dark_zone's ray walk (optical_depth.f90:1519-1550) on the GPU vs the oracle."""
+    P = S.ref41_like(n_photons_eq_th=100, dark_zone=False)
+    O, G = Oracle(P), api.PhotonLoop(P)
+    do = S.define_dark_zone(P, P.lambda_seuil, 1500.0, O.dark_zone_walker())
+    dg = S.define_dark_zone(P, P.lambda_seuil, 1500.0, G.dark_zone_walker())
+    assert do.sum() > 0 and np.array_equal(do, dg)
+    G.close()
+
+
+def _thermal_pair(P, n2):
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(1, 1, n2, 1.0e30, 1, False)
+    G.close()
+    to = Oracle(P, fast=True).run(n_threads=0, n_photons2=n2)
+    return to, tg
+
+
+def test_thermal_ref41_like_statistical_parity():
+    """G1 at the file-default budget (128 x 1000 packets): temperature and escaping SED."""
+    P = S.ref41_like(n_photons_eq_th=1000, dark_zone=False)
+    P.l_dark_zone = S.define_dark_zone(P, P.lambda_seuil, 1500.0, Oracle(P).dark_zone_walker())
+    S.repartition_energie(P)
+    to, tg = _thermal_pair(P, 1000)
+    assert tg.stats[0] == to.stats[0] == 128000 == tg.n_phot_envoyes.sum()
+    assert tg.stats[5] + tg.stats[6] == tg.stats[0]                       # every packet detected or killed
+    assert tg.sed.sum() == pytest.approx(tg.stats[6])                     # energy conservation (E_paquet = 1)
+    To, Tg = S.temp_finale(P, to.xKJ_abs), S.temp_finale(P, tg.xKJ_abs)
+    lit = (to.xKJ_abs > 0) & (tg.xKJ_abs > 0) & (P.l_dark_zone == 0)
+    rel = np.abs(Tg[lit] - To[lit]) / To[lit]
+    assert lit.sum() > 0.9 * (P.l_dark_zone == 0).sum()
+    assert np.median(rel) < 0.01, np.median(rel)                          # north_star bar
+    assert np.percentile(rel, 75) < 0.05                                   # the reference's own MC_similar bar (test_mcfost.py:88)
+    # SED per (lambda, inclination) bin within 3 sigma of packet statistics (Poisson on counts, two samples)
+    no, ng = to.n_phot_sed[:, :, 0], tg.n_phot_sed[:, :, 0]
+    m = (no + ng) > 50
+    zscore = (ng[m] - no[m]) / np.sqrt(no[m] + ng[m])
+    assert np.mean(np.abs(zscore) < 3) > 0.99 and abs(zscore.mean()) < 0.3
+    # global absorbed energy
+    assert abs(tg.xKJ_abs.sum() / to.xKJ_abs.sum() - 1) < 0.01
+
+
+@pytest.mark.parametrize("name", ["cyl3D", "sph2D", "sph3D"])
+def test_thermal_other_grids_statistical_parity(name):
+    P = small_problems()[name]()
+    to, tg = _thermal_pair(P, 400)
+    assert tg.stats[0] == to.stats[0]
+    assert tg.sed.sum() == pytest.approx(tg.stats[6])
+    assert abs(tg.xKJ_abs.sum() / to.xKJ_abs.sum() - 1) < 0.02
+    assert abs(tg.stats[1] / to.stats[1] - 1) < 0.02                      # cell-crossing steps
+    no, ng = to.n_phot_sed.sum(axis=(0, 2)), tg.n_phot_sed.sum(axis=(0, 2))
+    assert (np.abs(ng - no) < 4 * np.sqrt(no + ng) + 1).all()
+
+
+def _sed_kwargs(pola):
+    return dict(letape_th=0, lmono=1, lambda_in=8, p_lambda_in=8, n_photons2=10 ** 9, n_phot_lim=200.0,
+                lscatt_ray_tracing1=1, lsepar_pola=int(pola), lsepar_contrib=1, RT_n_incl=3, RT_n_az=1,
+                tab_u_rt=np.array([[0.0], [0.5], [0.9]]), tab_v_rt=np.zeros((3, 1)),
+                tab_w_rt=np.array([1.0, np.sqrt(0.75), np.sqrt(0.19)]))
+
+
+@pytest.mark.parametrize("pola", [False, True])
+def test_sed_step_matches_oracle_packet_by_packet(pola):
+    """Forced-scattering (lmono) mode has no feedback: with the shared per-packet Philox streams the
+    GPU follows the same trajectories as the oracle; tallies agree up to libm / summation-order noise."""
+    P = small_problems()["cyl2D"]()
+    kw = _sed_kwargs(pola)
+    ntf = (4 if pola else 1) + 4
+    n_xI = 45 * 2 * ntf * 3 * P.n_cells
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(kw.pop("lambda_in"), kw.pop("p_lambda_in"), kw.pop("n_photons2"), kw.pop("n_phot_lim"), 1, False, **kw)
+    G.close()
+    to = Oracle(P).run(n_threads=0, n_xI=n_xI, **_sed_kwargs(pola))
+    assert tg.stats[0] == to.stats[0] == 128 * 200
+    assert abs(tg.stats[1] - to.stats[1]) <= 1e-4 * to.stats[1]           # same walks (a few libm-ulp flips allowed)
+    assert abs(tg.stats[2] - to.stats[2]) <= 1e-4 * to.stats[2]
+    assert np.allclose(tg.n_phot_sed, to.n_phot_sed, atol=3)
+    assert np.allclose(tg.sed.sum(axis=0), to.sed.sum(axis=0), rtol=2e-3)
+    if pola:
+        assert np.abs(tg.sed_q).sum() > 0
+        assert np.allclose(tg.sed_q.sum(axis=(0, 2)), to.sed_q.sum(axis=(0, 2)), rtol=0.02, atol=1e-3 * np.abs(to.sed_q).sum())
+    xg = tg.xI_scatt.reshape((45, 2, ntf, 3, P.n_cells), order="F")
+    xo = to.xI_scatt.reshape((45, 2, ntf, 3, P.n_cells), order="F")
+    assert xo[:, :, 0].sum() > 0
+    # per observer direction and per flux type, summed over cells: fp32 accumulation noise only
+    assert np.allclose(xg.sum(axis=(0, 1, 4)), xo.sum(axis=(0, 1, 4)), rtol=5e-3, atol=1e-6 * np.abs(xo).sum())
+    # cell-resolved for the bright cells
+    cg, co = xg[:, :, 0].sum(axis=(0, 1, 2)), xo[:, :, 0].sum(axis=(0, 1, 2))
+    bright = co > 0.01 * co.max()
+    assert np.allclose(cg[bright], co[bright], rtol=0.02)
+
+
+def test_sed_chunk_termination_counts_received_packets():
+    """SED mode stops a chunk once n_photons2 packets were received in bin capt_sup
+    (dust_transfer.f90:510,529,551); packets in flight finish, so >= the target."""
+    P = small_problems()["cyl2D"]()
+    G = api.PhotonLoop(P)
+    t = G.mc_photon_loop(8, 8, 5, 1.0e4, 1, False, letape_th=0, lmono=1)
+    G.close()
+    recv_bin2 = t.n_phot_sed[7, 1, 0]
+    assert recv_bin2 >= 128 * 5
+    assert t.stats[0] == t.n_phot_envoyes[7] and t.stats[0] < 128 * 1.0e4
+
+
+def test_rank_partition_is_additive():
+    """Two 'ranks' on one device: chunk round-robin + identical Philox streams => tallies add up."""
+    P = small_problems()["cyl2D"]()
+    kw = dict(letape_th=0, lmono=1)
+    G = api.PhotonLoop(P)
+    full = G.mc_photon_loop(8, 8, 10 ** 9, 64.0, 1, False, **kw)
+    a = G.mc_photon_loop(8, 8, 10 ** 9, 64.0, 1, False, rank=0, n_ranks=2, **kw)
+    b = G.mc_photon_loop(8, 8, 10 ** 9, 64.0, 1, False, rank=1, n_ranks=2, **kw)
+    G.close()
+    assert a.stats[0] + b.stats[0] == full.stats[0] == 128 * 64
+    assert np.array_equal(a.n_phot_sed + b.n_phot_sed, full.n_phot_sed)
+    assert np.allclose(a.sed + b.sed, full.sed, rtol=1e-9, atol=1e-12)
+
+
+def test_full_size_properties_ref41():
+    """BASELINE-size run (G1, 128 x 20000 packets): size-independent properties."""
+    P = S.ref41_like(n_photons_eq_th=20000, dark_zone=True)       # steps 1-3 dark zone (superset), fine for properties
+    G = api.PhotonLoop(P)
+    t = G.mc_photon_loop(1, 1, 20000, 1.0e30, 1, False)
+    G.close()
+    assert t.stats[0] == 128 * 20000 == t.n_phot_envoyes.sum()
+    assert t.stats[5] + t.stats[6] == t.stats[0]
+    assert t.sed.sum() == pytest.approx(t.stats[6], rel=1e-9)
+    assert (t.sed_star + t.sed_star_scat + t.sed_disk + t.sed_disk_scat).sum() == pytest.approx(t.sed.sum(), rel=1e-9)
+    assert (t.xKJ_abs[P.l_dark_zone == 1] == 0).all()              # nothing is deposited inside the dark zone
+    assert (t.xT_ech >= 2).all() and (t.xT_ech <= P.n_T).all()
+    T = S.temp_finale(P, t.xKJ_abs)
+    assert 100 < T.max() < 3000
+    # radiative equilibrium: total re-emitted = absorbed => detected energy equals emitted energy
+    assert t.sed.sum() / t.stats[0] > 0.999
