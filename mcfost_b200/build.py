@@ -10,13 +10,12 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libmcfost_b200.so")
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    # bit-exact geometry vs the reference's non-contracted arithmetic (gfortran has no
-    # FMA contraction across statements; see DESIGN.md "precision")
-    "--fmad=false",
-    "-Xcompiler", "-fPIC", "-shared",
-]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+# translation units and their extra flags:
+#   api.cu       host API + deterministic sub-kernels: --fmad=false so that geometry is bit-exact
+#                against the reference's non-contracted arithmetic (DESIGN.md "precision")
+#   mc_kernel.cu the Monte Carlo photon-loop kernel: FMA contraction allowed (statistical path)
+UNITS = [("api.cu", ["--fmad=false"]), ("mc_kernel.cu", [])]
 
 
 def sources():
@@ -35,8 +34,17 @@ def build(force=False, verbose=False):
     if not (force or stale()):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "api.cu")]
-    subprocess.run(cmd, check=True, cwd=CSRC)
+    objs = []
+    procs = []
+    for src, extra in UNITS:
+        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        procs.append((cmd, subprocess.Popen(cmd, cwd=CSRC)))
+        objs.append(obj)
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    subprocess.run(["nvcc", "-shared", "-o", LIB] + objs, check=True, cwd=CSRC)
     return LIB
 
 

@@ -2,75 +2,14 @@
 // ownership, uploads, kernel launches, tally download.  There is NO CPU
 // fallback anywhere in this library: without a CUDA device every entry point
 // fails with MCB_ERR_NO_DEVICE.
-#include <cuda_runtime.h>
 #include <cmath>
-#include <cstdio>
-#include <cstring>
-#include <map>
-#include <string>
-#include <vector>
 
-#include "../../include/mcfost_b200.h"
+#include "handle.cuh"
 #include "transport.cuh"
 
 using namespace mcb;
 
-struct mcb_handle {
-  int device = 0;
-  int n_sm = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  DevModel m;
-  GridKind gk = GK_CYL2D;
-  bool has_grid = false, has_op = false, has_em = false, launched = false;
-  std::map<std::string, void*> bufs;      // named device allocations
-  std::map<std::string, size_t> buf_bytes;
-  int64_t n_tally = 0, n_xI = 0;
-  bool lay_xJ = false;
-  int lay_nsed = -1;
-  int n_photons_loop_alloc = 0;
-  int n_type_flux = 1;
-  char err[512] = {0};
-};
-
 static char g_err[256] = {0};
-
-#define CK(call)                                                                                   \
-  do {                                                                                             \
-    cudaError_t e_ = (call);                                                                       \
-    if (e_ != cudaSuccess) {                                                                       \
-      snprintf(h->err, sizeof h->err, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
-      return MCB_ERR_CUDA;                                                                         \
-    }                                                                                              \
-  } while (0)
-
-static int fail(mcb_handle* h, int code, const char* msg) {
-  snprintf(h->err, sizeof h->err, "%s", msg);
-  return code;
-}
-
-// (re)allocate a named device buffer and optionally fill it from host memory
-template <class T>
-static int put(mcb_handle* h, const char* name, const T* src, size_t n, const T** dst) {
-  *dst = nullptr;
-  if (!src || n == 0) return MCB_OK;
-  size_t bytes = n * sizeof(T);
-  void*& p = h->bufs[name];
-  if (p && h->buf_bytes[name] != bytes) { cudaFree(p); p = nullptr; }
-  if (!p) { CK(cudaMalloc(&p, bytes)); h->buf_bytes[name] = bytes; }
-  CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, h->stream));
-  *dst = (const T*)p;
-  return MCB_OK;
-}
-template <class T>
-static int reserve(mcb_handle* h, const char* name, size_t n, T** dst) {
-  size_t bytes = (n ? n : 1) * sizeof(T);
-  void*& p = h->bufs[name];
-  if (p && h->buf_bytes[name] != bytes) { cudaFree(p); p = nullptr; }
-  if (!p) { CK(cudaMalloc(&p, bytes)); h->buf_bytes[name] = bytes; }
-  *dst = (T*)p;
-  return MCB_OK;
-}
 
 extern "C" {
 
@@ -133,6 +72,21 @@ int mcfost_b200_upload_grid(mcb_handle* h, const mcb_grid* g) {
       if (!g->z_lim || !g->zmax) return fail(h, MCB_ERR_BAD_ARG, "z_lim / zmax missing");
       if ((rc = put(h, "z_lim", g->z_lim, (size_t)g->n_rad * (g->nz + 2), &m.z_lim))) return rc;
       if ((rc = put(h, "zmax", g->zmax, (size_t)g->n_rad, &m.zmax))) return rc;
+      // default vertical grid: z_lim(i,j) = (j-1)*cell_height(i), z_lim(i,nz+1) = zmax(i) (cylindrical_grid.f90:458-465).
+      // If that holds bit-for-bit only cell_height(i) = z_lim(i,2) is needed on the device.
+      bool regular = g->nz >= 2;
+      for (int i = 0; i < g->n_rad && regular; ++i) {
+        const double ch = g->z_lim[i + (size_t)g->n_rad * 1];
+        for (int j = 1; j <= g->nz; ++j) if (g->z_lim[i + (size_t)g->n_rad * (j - 1)] != (double)(j - 1) * ch) { regular = false; break; }
+        if (g->z_lim[i + (size_t)g->n_rad * g->nz] != g->zmax[i]) regular = false;
+      }
+      m.z_regular = regular ? 1 : 0;
+      if (regular) {
+        std::vector<double> ch((size_t)g->n_rad);
+        for (int i = 0; i < g->n_rad; ++i) ch[i] = g->z_lim[i + (size_t)g->n_rad * 1];
+        if ((rc = put(h, "cell_height", ch.data(), ch.size(), &m.cell_height))) return rc;
+        CK(cudaStreamSynchronize(h->stream));
+      }
     } else {
       if (!g->tan_theta_lim || !g->theta_lim) return fail(h, MCB_ERR_BAD_ARG, "tan_theta_lim / theta_lim missing");
       if ((rc = put(h, "tan_theta_lim", g->tan_theta_lim, (size_t)g->nz + 1, &m.tan_theta_lim))) return rc;
@@ -260,6 +214,29 @@ int mcfost_b200_upload_emission(mcb_handle* h, const mcb_emission* e) {
 }  // extern "C"
 
 // ---------------------------------------------------------------------------
+// Shared-memory staging plan (SmemLayout): enabled when the dust is not cell-dependent and
+// two blocks' worth of tables fit next to L1 on one SM.
+static void compute_smem_layout(mcb_handle* h, int /*p_lambda_in*/) {
+  DevModel& m = h->m;
+  SmemLayout L; memset(&L, 0, sizeof L);
+  if (m.p_n_cells == 1 && h->gk != GK_VOR) {
+    int off = 0;
+    auto take = [&](int n_words) { int o = off; off += n_words; return o; };
+    L.r_lim_2 = take(m.n_rad + 1);
+    if (m.kind == MCB_GRID_CYL) { L.zmax = take(m.n_rad); L.zl = take(m.z_regular ? m.n_rad : m.n_rad * (m.nz + 2)); }
+    else L.tan_theta = take(m.nz + 1);
+    if (m.l3D) L.tan_phi = take(m.n_az);
+    L.kappa = take(m.n_lambda); L.kappa_abs = take(m.n_lambda);
+    L.albedo = take((m.n_lambda + 1) / 2); L.gfac = take((m.n_lambda + 1) / 2);
+    L.logQ = take(m.n_T); L.kdB = take(m.n_lambda * m.n_T);
+    L.cos_tab = take(NANG + 1); L.prob_s11 = take((NANG + 2) / 2);
+    L.spec_cumul = take(m.n_lambda + 1); L.frac_star = take(m.n_lambda); L.frac_disk = take(m.n_lambda);
+    L.total_words = off;
+    L.enabled = (off * 8 <= 96 * 1024) && m.logQ && m.kdB && m.spec_cumul;
+  }
+  m.sm = L;
+}
+
 __global__ void fill_int_kernel(int* p, int64_t n, int v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -292,19 +269,6 @@ static int setup_tallies(mcb_handle* h, const mcb_run_params* r, bool lxJ, bool 
     fill_int_kernel<<<256, 256, 0, h->stream>>>(m.xT_ech, m.n_cells, 2);      // xT_ech = 2, thermal_emission.f90:119,2164
   }
   CK(cudaMemsetAsync(m.work, 0, (size_t)(4 + 2 * r->n_photons_loop) * sizeof(unsigned long long), h->stream));
-  return MCB_OK;
-}
-
-template <class G>
-static int launch_mc(mcb_handle* h, const DevRun& dr) {
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mc_photon_loop_kernel<G>, 128, 0));
-  if (per_sm < 1) per_sm = 1;
-  const int blocks = h->n_sm * per_sm;          // persistent: one wave exactly filling the 148 SMs
-  CK(cudaEventRecord(h->ev0, h->stream));
-  mc_photon_loop_kernel<G><<<blocks, 128, 0, h->stream>>>(h->m, dr);
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(h->ev1, h->stream));
   return MCB_OK;
 }
 
@@ -364,13 +328,8 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   int rc = setup_tallies(h, r, dr.lxJ != 0, rt1, dr.n_type_flux);
   if (rc) return rc;
   if (n_local == 0 || (dr.count_sent && dr.n_packets_total == 0)) { CK(cudaEventRecord(h->ev0, h->stream)); CK(cudaEventRecord(h->ev1, h->stream)); h->launched = true; return MCB_OK; }
-  switch (h->gk) {
-    case GK_CYL2D: rc = launch_mc<GeomCyl<false>>(h, dr); break;
-    case GK_CYL3D: rc = launch_mc<GeomCyl<true>>(h, dr); break;
-    case GK_SPH2D: rc = launch_mc<GeomSph<false>>(h, dr); break;
-    case GK_SPH3D: rc = launch_mc<GeomSph<true>>(h, dr); break;
-    case GK_VOR:   rc = launch_mc<GeomVor>(h, dr); break;
-  }
+  compute_smem_layout(h, r->p_lambda_in);
+  rc = mcb_launch_mc(h, dr);
   if (rc) return rc;
   h->launched = true;
   return MCB_OK;

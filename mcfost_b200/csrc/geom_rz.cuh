@@ -79,11 +79,34 @@ __device__ __host__ __forceinline__ Cell cell_from_id(const DevModel& m, int id)
 }
 
 // ---------------- table accessors (1-based like the reference) -------------
-__device__ __forceinline__ double r_lim_2(const DevModel& m, int i) { return __ldg(m.r_lim_2 + i); }
-__device__ __forceinline__ double z_lim(const DevModel& m, int i, int j) { return __ldg(m.z_lim + (i - 1) + m.n_rad * (j - 1)); }
-__device__ __forceinline__ double zmax(const DevModel& m, int i) { return __ldg(m.zmax + (i - 1)); }
-__device__ __forceinline__ double tan_phi_lim(const DevModel& m, int k) { return __ldg(m.tan_phi_lim + (k - 1)); }
-__device__ __forceinline__ double tan_theta_lim(const DevModel& m, int j) { return __ldg(m.tan_theta_lim + j); }
+// SM = true: the table lives in the block's shared-memory staging area (SmemLayout);
+// SM = false: read-only global loads.
+extern __shared__ __align__(16) unsigned char mcb_smem_raw[];
+__device__ __forceinline__ const double* smd() { return reinterpret_cast<const double*>(mcb_smem_raw); }
+template <bool SM> __device__ __forceinline__ double r_lim_2(const DevModel& m, int i) { return SM ? smd()[m.sm.r_lim_2 + i] : __ldg(m.r_lim_2 + i); }
+template <bool SM> __device__ __forceinline__ double zmax(const DevModel& m, int i) { return SM ? smd()[m.sm.zmax + i - 1] : __ldg(m.zmax + (i - 1)); }
+// z_lim(i,j), j = 1..nz+1.  For the default grid z_lim(i,j) = (j-1)*cell_height(i) and z_lim(i,nz+1) = zmax(i)
+// (cylindrical_grid.f90:458-465); upload_grid verifies that bit-for-bit and then only cell_height is kept.
+template <bool SM> __device__ __forceinline__ double z_lim(const DevModel& m, int i, int j) {
+  if (m.z_regular) {
+    if (j == m.nz + 1) return zmax<SM>(m, i);
+    const double ch = SM ? smd()[m.sm.zl + i - 1] : __ldg(m.cell_height + (i - 1));
+    return (double)(j - 1) * ch;
+  }
+  return SM ? smd()[m.sm.zl + (i - 1) + m.n_rad * (j - 1)] : __ldg(m.z_lim + (i - 1) + m.n_rad * (j - 1));
+}
+template <bool SM> __device__ __forceinline__ double tan_phi_lim(const DevModel& m, int k) { return SM ? smd()[m.sm.tan_phi + k - 1] : __ldg(m.tan_phi_lim + (k - 1)); }
+template <bool SM> __device__ __forceinline__ double tan_theta_lim(const DevModel& m, int j) { return SM ? smd()[m.sm.tan_theta + j] : __ldg(m.tan_theta_lim + j); }
+
+// result of the wall-distance half of a crossing (the next-cell half is only needed when the flight goes on)
+struct HitRZ {
+  double l;        // = l_contrib (l_void_before = 0 on structured grids)
+  int which;       // 0 radial, 1 vertical / theta, 2 azimuthal
+  int d_rad, d_j, d_phi;
+};
+
+__device__ __forceinline__ double hit_l_contrib(const HitRZ& h) { return h.l; }
+__device__ __forceinline__ double hit_l_void(const HitRZ&) { return 0.0; }
 
 // direction-only invariants of a flight
 struct DirInv { double inv_a, inv_w; };
@@ -105,8 +128,9 @@ __device__ __forceinline__ int phi_index(const DevModel& m, double x, double y) 
 // =========================================================================
 // cylindrical
 // =========================================================================
-template <bool L3D>
+template <bool L3D, bool SM = false>
 struct GeomCyl {
+  using Hit = HitRZ;
   static constexpr bool is_vor = false;
   using CellT = Cell;
 
@@ -120,18 +144,18 @@ struct GeomCyl {
 
   static __device__ __forceinline__ int z_index_f32(const DevModel& m, double z, int ri) {
     // floor(min(real(abs(z)/zmax(ri)*nz), max_int)) + 1   (cylindrical_grid.f90:868,1116: fp32 cast)
-    float q = (float)(fabs(z) / zmax(m, ri) * m.nz);
+    float q = (float)(fabs(z) / zmax<SM>(m, ri) * m.nz);
     return (int)floorf(fminf(q, max_int_f())) + 1;
   }
 
   static __device__ Cell index(const DevModel& m, double x, double y, double z) {
     Cell c;
     double r2 = x * x + y * y;
-    if (r2 < r_lim_2(m, 0)) { c.ri = 0; c.zj = 1; c.k = 1; return c; }
+    if (r2 < r_lim_2<SM>(m, 0)) { c.ri = 0; c.zj = 1; c.k = 1; return c; }
     if (r2 > m.Rmax2) { c.ri = m.n_rad + 1; c.zj = 1; c.k = 1; return c; }
     int lo = 0, hi = m.n_rad, ri = (lo + hi) / 2;
     while (hi - lo > 1) {
-      if (r2 > r_lim_2(m, ri)) lo = ri; else hi = ri;
+      if (r2 > r_lim_2<SM>(m, ri)) lo = ri; else hi = ri;
       ri = (lo + hi) / 2;
     }
     c.ri = ri + 1;
@@ -146,20 +170,18 @@ struct GeomCyl {
     return c;
   }
 
-  // one cell crossing; returns l (= l_contrib; l_void_before = 0)
-  static __device__ __forceinline__ double cross(const DevModel& m, DirInv d, double x0, double y0, double z0,
-                                                 double u, double v, double w, Cell c, Cell /*prev*/,
-                                                 double& x1, double& y1, double& z1, Cell& nxt,
-                                                 double& l_contrib, double& l_void) {
+  // ---- wall-distance half of cross_cylindrical_cell (:941-1094): which wall, how far ----
+  static __device__ __forceinline__ HitRZ distance(const DevModel& m, DirInv d, double x0, double y0, double z0,
+                                                   double u, double v, double w, Cell c, Cell /*prev*/) {
     const double correct_moins = 1.0 - MCB_GRID_PREC, correct_plus = 1.0 + MCB_GRID_PREC;
     const int ri0 = c.ri, zj0 = c.zj, k0 = c.k;
     double s, t, t_phi;
-    int delta_rad = 1, delta_zj = 0, delta_phi = 0;
+    HitRZ h; h.d_rad = 1; h.d_j = 0; h.d_phi = 0;
     const double r_2 = x0 * x0 + y0 * y0;
     const double b = (x0 * u + y0 * v) * d.inv_a;
 
     if (ri0 == 0) {
-      double cc = (r_2 - r_lim_2(m, 0)) * d.inv_a;
+      double cc = (r_2 - r_lim_2<SM>(m, 0)) * d.inv_a;
       double rac = sqrt(b * b - cc);
       s = (-b + rac) * correct_plus;
       t = MCB_HUGE_REAL; t_phi = MCB_HUGE_REAL;
@@ -167,14 +189,14 @@ struct GeomCyl {
       // 1) radial wall
       double dotprod = u * x0 + v * y0, delta;
       if (dotprod < 0.0) {
-        double cc = (r_2 - r_lim_2(m, ri0 - 1) * correct_moins) * d.inv_a;
+        double cc = (r_2 - r_lim_2<SM>(m, ri0 - 1) * correct_moins) * d.inv_a;
         delta = b * b - cc;
         if (delta < 0.0) {
-          cc = (r_2 - r_lim_2(m, ri0) * correct_plus) * d.inv_a;
+          cc = (r_2 - r_lim_2<SM>(m, ri0) * correct_plus) * d.inv_a;
           delta = fmax(b * b - cc, 0.0);
-        } else delta_rad = -1;
+        } else h.d_rad = -1;
       } else {
-        double cc = (r_2 - r_lim_2(m, ri0) * correct_plus) * d.inv_a;
+        double cc = (r_2 - r_lim_2<SM>(m, ri0) * correct_plus) * d.inv_a;
         delta = fmax(b * b - cc, 0.0);
       }
       double rac = sqrt(delta);
@@ -189,22 +211,22 @@ struct GeomCyl {
         const int aj = zj0 < 0 ? -zj0 : zj0;
         double zlim;
         if (dotprod > 0.0) {
-          if (aj == m.nz + 1) { delta_zj = 0; zlim = copysign(1.0e10, z0); }
+          if (aj == m.nz + 1) { h.d_j = 0; zlim = copysign(1.0e10, z0); }
           else {
-            zlim = copysign(z_lim(m, ri0, aj + 1) * correct_plus, z0);
-            delta_zj = (L3D && z0 < 0.0) ? -1 : 1;
+            zlim = copysign(z_lim<SM>(m, ri0, aj + 1) * correct_plus, z0);
+            h.d_j = (L3D && z0 < 0.0) ? -1 : 1;
           }
         } else {
           if (L3D) {
-            if (z0 > 0.0) { zlim = z_lim(m, ri0, aj) * correct_moins; delta_zj = (zj0 == 1) ? -2 : -1; }
-            else { zlim = -z_lim(m, ri0, aj) * correct_moins; delta_zj = (zj0 == -1) ? 2 : 1; }
+            if (z0 > 0.0) { zlim = z_lim<SM>(m, ri0, aj) * correct_moins; h.d_j = (zj0 == 1) ? -2 : -1; }
+            else { zlim = -z_lim<SM>(m, ri0, aj) * correct_moins; h.d_j = (zj0 == -1) ? 2 : 1; }
           } else {
             if (zj0 == 1) {          // midplane mirror in 2D
-              delta_zj = 1;
-              zlim = (z0 > 0.0) ? -z_lim(m, ri0, 2) * correct_moins : z_lim(m, ri0, 2) * correct_moins;
+              h.d_j = 1;
+              zlim = (z0 > 0.0) ? -z_lim<SM>(m, ri0, 2) * correct_moins : z_lim<SM>(m, ri0, 2) * correct_moins;
             } else {
-              zlim = (z0 > 0.0) ? z_lim(m, ri0, zj0) * correct_moins : -z_lim(m, ri0, zj0) * correct_moins;
-              delta_zj = -1;
+              zlim = (z0 > 0.0) ? z_lim<SM>(m, ri0, zj0) * correct_moins : -z_lim<SM>(m, ri0, zj0) * correct_moins;
+              h.d_j = -1;
             }
           }
         }
@@ -218,8 +240,8 @@ struct GeomCyl {
         if (fabs(dotprod) < (double)1.0e-10f) t_phi = (double)1.0e30f;
         else {
           double tan_angle_lim;
-          if (dotprod > 0.0) { tan_angle_lim = tan_phi_lim(m, k0); delta_phi = 1; }
-          else { int km = k0 - 1; if (km == 0) km = m.n_az; tan_angle_lim = tan_phi_lim(m, km); delta_phi = -1; }
+          if (dotprod > 0.0) { tan_angle_lim = tan_phi_lim<SM>(m, k0); h.d_phi = 1; }
+          else { int km = k0 - 1; if (km == 0) km = m.n_az; tan_angle_lim = tan_phi_lim<SM>(m, km); h.d_phi = -1; }
           if (tan_angle_lim > 1.0e299) t_phi = (fabs(u) > (double)1e-6f) ? -x0 / u : (double)1.0e30f;
           else {
             double den = v - u * tan_angle_lim;
@@ -229,12 +251,27 @@ struct GeomCyl {
         }
       } else t_phi = MCB_HUGE_REAL;
     }
+    if ((s < t) && (s < t_phi)) { h.l = s; h.which = 0; }
+    else if (t < t_phi) { h.l = t; h.which = 1; }
+    else { h.l = t_phi; h.which = 2; }
+    return h;
+  }
 
-    double l;
-    if ((s < t) && (s < t_phi)) {
-      l = s;
-      x1 = x0 + s * u; y1 = y0 + s * v; z1 = z0 + s * w;
-      nxt.ri = ri0 + delta_rad;
+  // exit point on the wall (:1100-1165)
+  static __device__ __forceinline__ void exit_point(const HitRZ& h, double x0, double y0, double z0, double u, double v, double w,
+                                                    double& x1, double& y1, double& z1) {
+    const double dv = (h.which == 2) ? (1.0 + MCB_GRID_PREC) * h.l : h.l;
+    x1 = x0 + dv * u; y1 = y0 + dv * v; z1 = z0 + dv * w;
+  }
+
+  // ---- next-cell half (:1106-1168): only needed when the flight continues past the wall ----
+  static __device__ __forceinline__ void advance(const DevModel& m, const HitRZ& h, double x0, double y0, double z0,
+                                                 double u, double v, double w, Cell c,
+                                                 double& x1, double& y1, double& z1, Cell& nxt) {
+    const int ri0 = c.ri, zj0 = c.zj, k0 = c.k;
+    exit_point(h, x0, y0, z0, u, v, w, x1, y1, z1);
+    if (h.which == 0) {
+      nxt.ri = ri0 + h.d_rad;
       if (nxt.ri == 0) { nxt.zj = 1; nxt.k = 1; }
       else {
         if (nxt.ri > m.n_rad) nxt.zj = zj0;
@@ -252,27 +289,31 @@ struct GeomCyl {
           nxt.k = k1;
         }
       }
-    } else if (t < t_phi) {
-      l = t;
-      x1 = x0 + t * u; y1 = y0 + t * v; z1 = z0 + t * w;
-      nxt.ri = ri0; nxt.zj = zj0 + delta_zj; nxt.k = k0;
+    } else if (h.which == 1) {
+      nxt.ri = ri0; nxt.zj = zj0 + h.d_j; nxt.k = k0;
     } else {
-      l = t_phi;
-      double dv = correct_plus * t_phi;
-      x1 = x0 + dv * u; y1 = y0 + dv * v; z1 = z0 + dv * w;
       nxt.ri = ri0;
-      int zj1 = (int)floor(fabs(z1) / zmax(m, ri0) * m.nz) + 1;       // fp64 here (:1150)
+      int zj1 = (int)floor(fabs(z1) / zmax<SM>(m, ri0) * m.nz) + 1;       // fp64 here (:1150)
       if (zj1 > m.nz) zj1 = m.nz + 1;
       if (z1 < 0.0) zj1 = -zj1;
       nxt.zj = zj1;
-      int k1 = k0 + delta_phi;
+      int k1 = k0 + h.d_phi;
       if (k1 == 0) k1 = m.n_az;
       if (k1 == m.n_az + 1) k1 = 1;
       nxt.k = k1;
     }
     if (z1 == 0.0) z1 = L3D ? copysign(MCB_GRID_PREC, w) : MCB_GRID_PREC;
-    l_contrib = l; l_void = 0.0;
-    return l;
+  }
+
+  // the full cross_cylindrical_cell (deterministic kernels)
+  static __device__ __forceinline__ double cross(const DevModel& m, DirInv d, double x0, double y0, double z0,
+                                                 double u, double v, double w, Cell c, Cell prev,
+                                                 double& x1, double& y1, double& z1, Cell& nxt,
+                                                 double& l_contrib, double& l_void) {
+    HitRZ h = distance(m, d, x0, y0, z0, u, v, w, c, prev);
+    advance(m, h, x0, y0, z0, u, v, w, c, x1, y1, z1, nxt);
+    l_contrib = h.l; l_void = 0.0;
+    return h.l;
   }
 
   static __device__ bool move_to_grid(const DevModel& m, double& x, double& y, double& z, double u, double v, double w, Cell& c) {
@@ -281,7 +322,7 @@ struct GeomCyl {
     DirInv d = dir_invariants(u, v, w);
     double r_2 = x0 * x0 + y0 * y0;
     double b = (x0 * u + y0 * v) * d.inv_a;
-    double cc = (r_2 - r_lim_2(m, m.n_rad) * correct_moins) * d.inv_a;
+    double cc = (r_2 - r_lim_2<SM>(m, m.n_rad) * correct_moins) * d.inv_a;
     double delta = b * b - cc, s1, s2, t1, t2, delta_vol;
     if (delta < 0.0) { s1 = MCB_HUGE_REAL; s2 = MCB_HUGE_REAL; }
     else { double rac = sqrt(delta); s1 = -b - rac; s2 = -b + rac; }
@@ -310,13 +351,13 @@ struct GeomCyl {
 
   static __device__ void pos_em_cell(const DevModel& m, Cell c, float rand1, float rand2, float rand3, double& x, double& y, double& z) {
     const int ri = c.ri, zj = c.zj;
-    double r = sqrt(r_lim_2(m, ri - 1) + rand1 * (r_lim_2(m, ri) - r_lim_2(m, ri - 1)));
+    double r = sqrt(r_lim_2<SM>(m, ri - 1) + rand1 * (r_lim_2<SM>(m, ri) - r_lim_2<SM>(m, ri - 1)));
     if (L3D) {
-      if (zj > 0) z = z_lim(m, ri, zj) + rand2 * (z_lim(m, ri, zj + 1) - z_lim(m, ri, zj));
-      else z = -(z_lim(m, ri, -zj) + rand2 * (z_lim(m, ri, -zj + 1) - z_lim(m, ri, -zj)));
+      if (zj > 0) z = z_lim<SM>(m, ri, zj) + rand2 * (z_lim<SM>(m, ri, zj + 1) - z_lim<SM>(m, ri, zj));
+      else z = -(z_lim<SM>(m, ri, -zj) + rand2 * (z_lim<SM>(m, ri, -zj + 1) - z_lim<SM>(m, ri, -zj)));
     } else {
-      if (rand2 > 0.5) z = z_lim(m, ri, zj) + (2.0 * (rand2 - 0.5)) * (z_lim(m, ri, zj + 1) - z_lim(m, ri, zj));
-      else z = -(z_lim(m, ri, zj) + (2.0 * rand2) * (z_lim(m, ri, zj + 1) - z_lim(m, ri, zj)));
+      if (rand2 > 0.5) z = z_lim<SM>(m, ri, zj) + (2.0 * (rand2 - 0.5)) * (z_lim<SM>(m, ri, zj + 1) - z_lim<SM>(m, ri, zj));
+      else z = -(z_lim<SM>(m, ri, zj) + (2.0 * rand2) * (z_lim<SM>(m, ri, zj + 1) - z_lim<SM>(m, ri, zj)));
     }
     double phi = 2.0 * MCB_PI * ((double)c.k - 1.0 + rand3) / (double)m.n_az;
     double sp, cp; sincos(phi, &sp, &cp);
@@ -327,8 +368,9 @@ struct GeomCyl {
 // =========================================================================
 // spherical
 // =========================================================================
-template <bool L3D>
+template <bool L3D, bool SM = false>
 struct GeomSph {
+  using Hit = HitRZ;
   static constexpr bool is_vor = false;
   using CellT = Cell;
 
@@ -341,7 +383,7 @@ struct GeomSph {
     double tan_theta = (r02 > MCB_TINY_DP) ? fabs(z) / sqrt(r02) : (double)1.0e30f;
     int lo = 0, hi = m.nz, j = (lo + hi) / 2;
     while (hi - lo > 1) {
-      if (tan_theta > tan_theta_lim(m, j)) lo = j; else hi = j;
+      if (tan_theta > tan_theta_lim<SM>(m, j)) lo = j; else hi = j;
       j = (lo + hi) / 2;
     }
     tj = j + 1; pk = 1;
@@ -356,11 +398,11 @@ struct GeomSph {
     double r2 = x * x + y * y + z * z;
     // note: the reference forms r2 = (x*x+y*y) + z*z
     r2 = (x * x + y * y) + z * z;
-    if (r2 < r_lim_2(m, 0)) { c.ri = 0; c.zj = 1; c.k = 1; return c; }
+    if (r2 < r_lim_2<SM>(m, 0)) { c.ri = 0; c.zj = 1; c.k = 1; return c; }
     if (r2 > m.Rmax2) { c.ri = m.n_rad + 1; c.zj = 1; c.k = 1; return c; }
     int lo = 0, hi = m.n_rad, ri = (lo + hi) / 2;
     while (hi - lo > 1) {
-      if (r2 > r_lim_2(m, ri)) lo = ri; else hi = ri;
+      if (r2 > r_lim_2<SM>(m, ri)) lo = ri; else hi = ri;
       ri = (lo + hi) / 2;
     }
     c.ri = ri + 1;
@@ -383,94 +425,112 @@ struct GeomSph {
     return (r2 <= precision) ? r1 : fmin(r1, r2);
   }
 
-  static __device__ __forceinline__ double cross(const DevModel& m, DirInv /*d*/, double x0, double y0, double z0,
-                                                 double u, double v, double w, Cell c, Cell /*prev*/,
-                                                 double& x1, double& y1, double& z1, Cell& nxt,
-                                                 double& l_contrib, double& l_void) {
+  // ---- wall-distance half of cross_spherical_cell (:205-381) ----
+  static __device__ __forceinline__ HitRZ distance(const DevModel& m, DirInv /*d*/, double x0, double y0, double z0,
+                                                   double u, double v, double w, Cell c, Cell /*prev*/) {
     const double correct_moins = 1.0 - MCB_PREC_SPH, correct_plus = 1.0 + MCB_PREC_SPH;
     const int ri0 = c.ri, tj0 = c.zj, pk0 = c.k;
     const int atj = tj0 < 0 ? -tj0 : tj0;
     double s, t, t_phi;
-    int delta_rad = 1, delta_theta = 0, delta_phi = 0;
+    HitRZ h; h.d_rad = 1; h.d_j = 0; h.d_phi = 0;
     const double r0_2 = (x0 * x0 + y0 * y0) + z0 * z0;
     const double b = (x0 * u + y0 * v + z0 * w);
     if (ri0 == 0) {
-      double cc = (r0_2 - r_lim_2(m, 0) * correct_plus);
+      double cc = (r0_2 - r_lim_2<SM>(m, 0) * correct_plus);
       double rac = sqrt(b * b - cc);
       s = (-b + rac) * correct_plus;
       t = MCB_HUGE_REAL; t_phi = MCB_HUGE_REAL;
     } else {
       double delta;
       if (b < 0.0) {
-        double cc = (r0_2 - r_lim_2(m, ri0 - 1) * correct_moins);
+        double cc = (r0_2 - r_lim_2<SM>(m, ri0 - 1) * correct_moins);
         delta = b * b - cc;
-        if (delta < 0.0) { cc = (r0_2 - r_lim_2(m, ri0) * correct_plus); delta = fmax(b * b - cc, 0.0); }
-        else delta_rad = -1;
+        if (delta < 0.0) { cc = (r0_2 - r_lim_2<SM>(m, ri0) * correct_plus); delta = fmax(b * b - cc, 0.0); }
+        else h.d_rad = -1;
       } else {
-        double cc = (r0_2 - r_lim_2(m, ri0) * correct_plus);
+        double cc = (r0_2 - r_lim_2<SM>(m, ri0) * correct_plus);
         delta = fmax(b * b - cc, 0.0);
       }
       double rac = sqrt(delta);
       s = -b - rac;
       if (s < 0.0) s = -b + rac; else if (s == 0.0) s = MCB_GRID_PREC;
 
-      double lim1 = tan_theta_lim(m, atj) * correct_plus, lim2 = tan_theta_lim(m, atj - 1) * correct_moins;
+      double lim1 = tan_theta_lim<SM>(m, atj) * correct_plus, lim2 = tan_theta_lim<SM>(m, atj - 1) * correct_moins;
       if (!(z0 >= 0.0)) { lim1 = -lim1; lim2 = -lim2; }
       double t1 = cone_root(lim1, x0, y0, z0, u, v, w);
       double t2 = cone_root(lim2, x0, y0, z0, u, v, w);
-      if (t1 < t2) { t = t1; delta_theta = (atj == m.nz) ? 0 : 1; }
-      else { t = t2; delta_theta = (atj == 1) ? 0 : -1; }
+      if (t1 < t2) { t = t1; h.d_j = (atj == m.nz) ? 0 : 1; }
+      else { t = t2; h.d_j = (atj == 1) ? 0 : -1; }
 
       if (L3D) {
         double dotprod = x0 * v - y0 * u;
-        if (fabs(dotprod) < (double)1.0e-10f) { t_phi = (double)1.0e30f; delta_phi = 0; }
+        if (fabs(dotprod) < (double)1.0e-10f) { t_phi = (double)1.0e30f; h.d_phi = 0; }
         else {
           double tan_angle_lim;
-          if (dotprod > 0.0) { tan_angle_lim = tan_phi_lim(m, pk0); delta_phi = 1; }
-          else { int km = pk0 - 1; if (km == 0) km = m.n_az; tan_angle_lim = tan_phi_lim(m, km); delta_phi = -1; }
+          if (dotprod > 0.0) { tan_angle_lim = tan_phi_lim<SM>(m, pk0); h.d_phi = 1; }
+          else { int km = pk0 - 1; if (km == 0) km = m.n_az; tan_angle_lim = tan_phi_lim<SM>(m, km); h.d_phi = -1; }
           if (tan_angle_lim > 1.0e299) t_phi = -x0 / u;
           else {
             double den = v - u * tan_angle_lim;
             if (fabs(den) > (double)1.0e-6f) t_phi = -(y0 - x0 * tan_angle_lim) / den;
-            else { t_phi = (double)1.0e30f; delta_phi = 0; }
+            else { t_phi = (double)1.0e30f; h.d_phi = 0; }
           }
-          if (t_phi < 0.0) { t_phi = (double)1.0e30f; delta_phi = 0; }
+          if (t_phi < 0.0) { t_phi = (double)1.0e30f; h.d_phi = 0; }
         }
       } else t_phi = MCB_HUGE_REAL;
     }
-    double l;
-    if ((s < t) && (s < t_phi)) {
-      l = s;
-      x1 = x0 + s * u; y1 = y0 + s * v; z1 = z0 + s * w;
-      nxt.ri = ri0 + delta_rad; nxt.zj = tj0; nxt.k = pk0;
+    if ((s < t) && (s < t_phi)) { h.l = s; h.which = 0; }
+    else if (t < t_phi) { h.l = t; h.which = 1; }
+    else { h.l = t_phi; h.which = 2; }
+    return h;
+  }
+
+  static __device__ __forceinline__ void exit_point(const HitRZ& h, double x0, double y0, double z0, double u, double v, double w,
+                                                    double& x1, double& y1, double& z1) {
+    const double dv = (h.which == 2) ? (1.0 + MCB_PREC_SPH) * h.l : h.l;
+    x1 = x0 + dv * u; y1 = y0 + dv * v; z1 = z0 + dv * w;
+  }
+
+  // ---- next-cell half (:384-439) ----
+  static __device__ __forceinline__ void advance(const DevModel& m, const HitRZ& h, double x0, double y0, double z0,
+                                                 double u, double v, double w, Cell c,
+                                                 double& x1, double& y1, double& z1, Cell& nxt) {
+    const int ri0 = c.ri, tj0 = c.zj, pk0 = c.k;
+    const int atj = tj0 < 0 ? -tj0 : tj0;
+    exit_point(h, x0, y0, z0, u, v, w, x1, y1, z1);
+    if (h.which == 0) {
+      nxt.ri = ri0 + h.d_rad; nxt.zj = tj0; nxt.k = pk0;
       if (ri0 == 0) theta_phi_index(m, x1, y1, z1, nxt.zj, nxt.k);
       if (nxt.ri == 0) { nxt.zj = 1; nxt.k = 1; }
-    } else if (t < t_phi) {
-      l = t;
-      x1 = x0 + t * u; y1 = y0 + t * v; z1 = z0 + t * w;
-      nxt.ri = ri0; nxt.zj = atj + delta_theta;
+    } else if (h.which == 1) {
+      nxt.ri = ri0; nxt.zj = atj + h.d_j;
       if (L3D) { if (z1 < 0) nxt.zj = -nxt.zj; }
       nxt.k = pk0;
     } else {
-      l = t_phi;
-      double dv = correct_plus * t_phi;
-      x1 = x0 + dv * u; y1 = y0 + dv * v; z1 = z0 + dv * w;
       nxt.ri = ri0; nxt.zj = tj0;
-      int k1 = pk0 + delta_phi;
+      int k1 = pk0 + h.d_phi;
       if (k1 == 0) k1 = m.n_az;
       if (k1 == m.n_az + 1) k1 = 1;
       nxt.k = k1;
     }
     if (z1 == 0.0) z1 = MCB_GRID_PREC;
-    l_contrib = l; l_void = 0.0;
-    return l;
+  }
+
+  static __device__ __forceinline__ double cross(const DevModel& m, DirInv d, double x0, double y0, double z0,
+                                                 double u, double v, double w, Cell c, Cell prev,
+                                                 double& x1, double& y1, double& z1, Cell& nxt,
+                                                 double& l_contrib, double& l_void) {
+    HitRZ h = distance(m, d, x0, y0, z0, u, v, w, c, prev);
+    advance(m, h, x0, y0, z0, u, v, w, c, x1, y1, z1, nxt);
+    l_contrib = h.l; l_void = 0.0;
+    return h.l;
   }
 
   static __device__ bool move_to_grid(const DevModel& m, double& x, double& y, double& z, double u, double v, double w, Cell& c) {
     const double correct_moins = 1.0 - 1.0e-10;
     double r0_2 = x * x + y * y + z * z;
     double b = (x * u + y * v + z * w);
-    double cc = (r0_2 - r_lim_2(m, m.n_rad) * correct_moins);
+    double cc = (r0_2 - r_lim_2<SM>(m, m.n_rad) * correct_moins);
     double delta = b * b - cc;
     if (delta < 0.0) return false;
     double s1 = -b - sqrt(delta);

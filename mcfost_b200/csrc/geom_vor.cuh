@@ -14,9 +14,14 @@
 
 namespace mcb {
 
+struct HitVor { double l, l_contrib, l_void; int next; };
+__device__ __forceinline__ double hit_l_contrib(const HitVor& h) { return h.l_contrib; }
+__device__ __forceinline__ double hit_l_void(const HitVor& h) { return h.l_void; }
+
 struct GeomVor {
   static constexpr bool is_vor = true;
   using CellT = int;
+  using Hit = HitVor;
 
   static __device__ __forceinline__ bool test_exit(const DevModel&, int c, double, double, double) { return c < 0; }
 
@@ -59,9 +64,10 @@ struct GeomVor {
     return dmin;
   }
 
-  static __device__ double cross(const DevModel& m, DirInv, double x, double y, double z, double u, double v, double w,
-                                 int icell, int previous_cell, double& x1, double& y1, double& z1, int& next_cell,
-                                 double& s_contrib, double& s_void_before) {
+  // cross_Voronoi_cell (:839-992): the neighbour loop already yields the next cell
+  static __device__ HitVor distance(const DevModel& m, DirInv, double x, double y, double z, double u, double v, double w,
+                                    int icell, int previous_cell) {
+    int next_cell; double s_contrib, s_void_before;
     const double prec = (double)1e-5f;
     const float rx = (float)x, ry = (float)y, rz = (float)z, kx = (float)u, ky = (float)v, kz = (float)w;
     double s = (double)1e30f;
@@ -89,9 +95,8 @@ struct GeomVor {
       if (s_tmp < s) { s = s_tmp; next_cell = id_n; }
     }
     s = s * (1.0 + prec);
-    x1 = x + u * s; y1 = y + v * s; z1 = z + w * s;
     if (next_cell == 0) {
-      x1 = x; y1 = y; z1 = z; s = 0.0;
+      s = 0.0;
       if (is_in_volume(m, x, y, z)) {
         next_cell = index(m, x, y, z);
         if (icell == next_cell) next_cell = -1;
@@ -120,7 +125,26 @@ struct GeomVor {
       const double d_to_star = distance_to_star(m, x, y, z, u, v, w, i_star);
       if (i_star > 0 && d_to_star < s) { s_contrib = d_to_star; next_cell = m.star_icell[i_star - 1]; }
     }
-    return s;
+    HitVor h; h.l = s; h.l_contrib = s_contrib; h.l_void = s_void_before; h.next = next_cell;
+    return h;
+  }
+
+  static __device__ __forceinline__ void exit_point(const HitVor& h, double x, double y, double z, double u, double v, double w,
+                                                    double& x1, double& y1, double& z1) {
+    x1 = x + u * h.l; y1 = y + v * h.l; z1 = z + w * h.l;      // (h.l = 0 on the rounding fallback: the packet does not move)
+  }
+  static __device__ __forceinline__ void advance(const DevModel&, const HitVor& h, double x, double y, double z, double u, double v, double w,
+                                                 int, double& x1, double& y1, double& z1, int& nxt) {
+    exit_point(h, x, y, z, u, v, w, x1, y1, z1);
+    nxt = h.next;
+  }
+  static __device__ double cross(const DevModel& m, DirInv d, double x, double y, double z, double u, double v, double w,
+                                 int icell, int previous_cell, double& x1, double& y1, double& z1, int& next_cell,
+                                 double& s_contrib, double& s_void_before) {
+    HitVor h = distance(m, d, x, y, z, u, v, w, icell, previous_cell);
+    advance(m, h, x, y, z, u, v, w, icell, x1, y1, z1, next_cell);
+    s_contrib = h.l_contrib; s_void_before = h.l_void;
+    return h.l;
   }
 
   static __device__ bool move_to_grid(const DevModel& m, double& x, double& y, double& z, double u, double v, double w, int& c) {

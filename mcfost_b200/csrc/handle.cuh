@@ -1,0 +1,71 @@
+// Shared between api.cu (host API + deterministic kernels, --fmad=false) and
+// mc_kernel.cu (the Monte Carlo photon-loop kernel, FMA contraction allowed).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mcfost_b200.h"
+#include "model.cuh"
+
+struct mcb_handle {
+  int device = 0;
+  int n_sm = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  mcb::DevModel m;
+  mcb::GridKind gk = mcb::GK_CYL2D;
+  bool has_grid = false, has_op = false, has_em = false, launched = false;
+  std::map<std::string, void*> bufs;      // named device allocations
+  std::map<std::string, size_t> buf_bytes;
+  int64_t n_tally = 0, n_xI = 0;
+  bool lay_xJ = false;
+  int lay_nsed = -1;
+  int n_photons_loop_alloc = 0;
+  int n_type_flux = 1;
+  char err[512] = {0};
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      snprintf(h->err, sizeof h->err, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return MCB_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+static int fail(mcb_handle* h, int code, const char* msg) {
+  snprintf(h->err, sizeof h->err, "%s", msg);
+  return code;
+}
+
+// (re)allocate a named device buffer and optionally fill it from host memory
+template <class T>
+static int put(mcb_handle* h, const char* name, const T* src, size_t n, const T** dst) {
+  *dst = nullptr;
+  if (!src || n == 0) return MCB_OK;
+  size_t bytes = n * sizeof(T);
+  void*& p = h->bufs[name];
+  if (p && h->buf_bytes[name] != bytes) { cudaFree(p); p = nullptr; }
+  if (!p) { CK(cudaMalloc(&p, bytes)); h->buf_bytes[name] = bytes; }
+  CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  *dst = (const T*)p;
+  return MCB_OK;
+}
+template <class T>
+static int reserve(mcb_handle* h, const char* name, size_t n, T** dst) {
+  size_t bytes = (n ? n : 1) * sizeof(T);
+  void*& p = h->bufs[name];
+  if (p && h->buf_bytes[name] != bytes) { cudaFree(p); p = nullptr; }
+  if (!p) { CK(cudaMalloc(&p, bytes)); h->buf_bytes[name] = bytes; }
+  *dst = (T*)p;
+  return MCB_OK;
+}
+
+
+// defined in mc_kernel.cu
+int mcb_launch_mc(mcb_handle* h, const mcb::DevRun& dr);

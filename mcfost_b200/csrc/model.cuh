@@ -31,11 +31,26 @@ struct TallyLayout {
   int64_t n_sed;                               // n_lambda*N_thet*N_phi
 };
 
+// Shared-memory staging of the small hot tables (offsets in 8-byte words from the
+// start of dynamic shared memory; float tables are stored widened to their own
+// word-aligned region).  Used by the photon-loop kernel when lvariable_dust is off
+// (p_n_cells == 1) and the tables fit; the per-cell arrays (kappa_factor,
+// l_dark_zone, volume, tallies) stay in global memory behind L1/L2.
+struct SmemLayout {
+  int enabled;
+  int r_lim_2, zmax, zl, tan_phi, tan_theta;          // geometry (zl = cell_height if z is regular else z_lim)
+  int kappa, kappa_abs, albedo, gfac;                 // (n_lambda); albedo/gfac are float regions
+  int logQ, kdB, cos_tab, prob_s11;                   // thermal / scattering (prob_s11: float region, one p_lambda slice)
+  int spec_cumul, frac_star, frac_disk;
+  int total_words;
+};
+
 struct DevModel {
   // ---- grid (cylindrical_grid.f90:20-41) --------------------------------
   int kind, l3D, n_rad, nz, n_az, n_cells, nj;   // nj = rows per azimuth (nz or 2 nz)
+  int z_regular;                                 // z_lim(i,j) == (j-1)*z_lim(i,2) bit-for-bit (default grid, :459-465)
   double Rmax2, zmaxmax;
-  const double *r_lim_2, *r_lim_3, *z_lim, *zmax, *tan_theta_lim, *theta_lim, *tan_phi_lim, *volume;
+  const double *r_lim_2, *r_lim_3, *z_lim, *zmax, *cell_height, *tan_theta_lim, *theta_lim, *tan_phi_lim, *volume;
   const double *kappa_factor;       // (n_cells)
   const uint8_t *dark;              // (n_cells) l_dark_zone
   // ---- Voronoi (Voronoi.f90:23-66) --------------------------------------
@@ -68,7 +83,8 @@ struct DevModel {
   TallyLayout lay;
   int *xT_ech;              // (n_cells)
   float *xI;                // xI_scatt
-  unsigned long long *work; // [0] = next work item
+  unsigned long long *work; // [0] = next work item; [2+2c], [3+2c] = sent / received of local chunk c
+  SmemLayout sm;
 };
 
 // run parameters broadcast to the kernel
@@ -86,7 +102,7 @@ struct DevRun {
   int count_sent;                       // 1: chunk ends after n_photons2 packets SENT (thermal / image), 0: RECEIVED (SED)
   unsigned long long sent_lim;          // ceil(n_phot_lim) (saturated)
   unsigned long long n_per_chunk;       // count_sent: min(n_photons2, sent_lim)
-  unsigned long long n_packets_total;   // count_sent: n_local_chunks * min(n_photons2, sent_lim)
+  unsigned long long n_packets_total;   // count_sent: n_local_chunks * n_per_chunk
   double nb_proc_equiv;                 // n_ranks: scales the local tally in Temp_LTE
 };
 

@@ -16,9 +16,14 @@
 // Execution model (B200): one packet per thread, persistent warps.  Each warp
 // iteration runs the phases FETCH -> TAU -> FLY -> INTERACT under warp-uniform
 // guards so that lanes in the same phase execute together; new packets are
-// claimed from a global counter with one warp-aggregated atomic.  Tallies are
-// L2 atomics (red.global.add.f64); the running cell temperature reads them
-// back with ld.global.cg (L1 is not coherent with L2 atomics).
+// claimed from a global counter with one warp-aggregated atomic.  The small hot
+// tables (radial / vertical walls, kappa(lambda), albedo, log Qcool, the k dB/dT
+// CDF, the s11 CDF, cos table, emission spectra) are staged once per block in
+// shared memory (SmemLayout, ~48 KB for ref4.1) when the dust is not cell-
+// dependent; per-cell arrays stay in global memory behind L1/L2.  Tallies are L2
+// atomics (red.global.add.f64); the running cell temperature reads them back
+// with ld.global.cg (L1 is not coherent with L2 atomics).  The next-cell half of
+// a crossing is skipped when the flight ends inside the cell.
 #pragma once
 #include "model.cuh"
 #include "philox.cuh"
@@ -41,6 +46,47 @@ __device__ __forceinline__ int id_of_cell(const DevModel& m, Cell c) { return ce
 __device__ __forceinline__ int id_of_cell(const DevModel&, int c) { return c; }
 __device__ __forceinline__ void null_cell(Cell& c) { c.ri = -7; c.zj = 0; c.k = 0; }
 __device__ __forceinline__ void null_cell(int& c) { c = 0; }
+
+// ---- opacity / thermal table accessors (SM: shared-memory staging, p_n_cells == 1) ----
+__device__ __forceinline__ const float* smf(int word_off) { return reinterpret_cast<const float*>(smd() + word_off); }
+template <bool SM> __device__ __forceinline__ double t_kappa(const DevModel& m, int p_icell, int lambda) {
+  return SM ? smd()[m.sm.kappa + lambda - 1] : __ldg(m.kappa + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)); }
+template <bool SM> __device__ __forceinline__ double t_kappa_abs(const DevModel& m, int p_icell, int lambda) {
+  return SM ? smd()[m.sm.kappa_abs + lambda - 1] : __ldg(m.kappa_abs + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)); }
+template <bool SM> __device__ __forceinline__ float t_albedo(const DevModel& m, int p_icell, int lambda) {
+  return SM ? smf(m.sm.albedo)[lambda - 1] : __ldg(m.albedo + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)); }
+template <bool SM> __device__ __forceinline__ float t_gfac(const DevModel& m, int p_icell, int lambda) {
+  return SM ? smf(m.sm.gfac)[lambda - 1] : __ldg(m.gfac + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)); }
+template <bool SM> __device__ __forceinline__ double t_logQ(const DevModel& m, int t, int p_icell) {      // t 1-based
+  return SM ? smd()[m.sm.logQ + t - 1] : __ldg(m.logQ + (size_t)m.n_T * (p_icell - 1) + t - 1); }
+template <bool SM> __device__ __forceinline__ double t_kdB(const DevModel& m, int l, int t, int p_icell) {  // l, t 1-based
+  return SM ? smd()[m.sm.kdB + (l - 1) + m.n_lambda * (t - 1)]
+            : __ldg(m.kdB + (size_t)m.n_lambda * ((t - 1) + (size_t)m.n_T * (p_icell - 1)) + (l - 1)); }
+template <bool SM> __device__ __forceinline__ double t_cos(const DevModel& m, int k) { return SM ? smd()[m.sm.cos_tab + k] : __ldg(m.cos_tab + k); }
+template <bool SM> __device__ __forceinline__ float t_prob_s11(const DevModel& m, int k, int p_icell, int p_lambda) {
+  return SM ? smf(m.sm.prob_s11)[k] : __ldg(m.prob_s11 + (size_t)(NANG + 1) * ((p_icell - 1) + (size_t)m.p_n_cells * (p_lambda - 1)) + k); }
+template <bool SM> __device__ __forceinline__ double t_spec_cumul(const DevModel& m, int k) { return SM ? smd()[m.sm.spec_cumul + k] : __ldg(m.spec_cumul + k); }
+template <bool SM> __device__ __forceinline__ double t_frac_star(const DevModel& m, int lambda) { return SM ? smd()[m.sm.frac_star + lambda - 1] : __ldg(m.frac_star + lambda - 1); }
+template <bool SM> __device__ __forceinline__ double t_frac_disk(const DevModel& m, int lambda) { return SM ? smd()[m.sm.frac_disk + lambda - 1] : __ldg(m.frac_disk + lambda - 1); }
+
+// one block-wide copy of the staged tables into shared memory
+__device__ __forceinline__ void stage_tables(const DevModel& m, int p_lambda_in) {
+  double* sd = reinterpret_cast<double*>(mcb_smem_raw);
+  const SmemLayout& L = m.sm;
+  auto cp = [&](int off, const double* src, int n) { if (src) for (int i = threadIdx.x; i < n; i += blockDim.x) sd[off + i] = src[i]; };
+  auto cpf = [&](int off, const float* src, int n) { if (src) { float* d = reinterpret_cast<float*>(sd + off); for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = src[i]; } };
+  cp(L.r_lim_2, m.r_lim_2, m.n_rad + 1);
+  if (m.kind == 1) { cp(L.zmax, m.zmax, m.n_rad); if (m.z_regular) cp(L.zl, m.cell_height, m.n_rad); else cp(L.zl, m.z_lim, m.n_rad * (m.nz + 2)); }
+  else cp(L.tan_theta, m.tan_theta_lim, m.nz + 1);
+  if (m.l3D) cp(L.tan_phi, m.tan_phi_lim, m.n_az);
+  cp(L.kappa, m.kappa, m.n_lambda); cp(L.kappa_abs, m.kappa_abs, m.n_lambda);
+  cpf(L.albedo, m.albedo, m.n_lambda); cpf(L.gfac, m.gfac, m.n_lambda);
+  cp(L.logQ, m.logQ, m.n_T); cp(L.kdB, m.kdB, m.n_lambda * m.n_T);
+  cp(L.cos_tab, m.cos_tab, NANG + 1);
+  if (m.prob_s11) cpf(L.prob_s11, m.prob_s11 + (size_t)(NANG + 1) * (p_lambda_in - 1), NANG + 1);
+  cp(L.spec_cumul, m.spec_cumul, m.n_lambda + 1); cp(L.frac_star, m.frac_star, m.n_lambda); cp(L.frac_disk, m.frac_disk, m.n_lambda);
+  __syncthreads();
+}
 
 // ---- utils.f90:1636-1688 cdapres ------------------------------------------
 __device__ __forceinline__ void cdapres(double cospsi, double sphi, double cphi, double u0, double v0, double w0,
@@ -72,8 +118,8 @@ __device__ __forceinline__ void random_isotropic_direction(Rng& rng, double& u, 
   w = 2.0 * rand - 1.0;
   double uv = sqrt(1.0 - w * w);
   rand = rng.nextf();
-  double phi = MCB_PI * (2.0 * rand - 1.0), sp, cp;
-  sincos(phi, &sp, &cp);
+  double sp, cp;
+  sincospi(2.0 * rand - 1.0, &sp, &cp);       // phi = pi*(2 rand - 1)
   u = uv * cp; v = uv * sp;
 }
 
@@ -96,10 +142,11 @@ __device__ __forceinline__ int intersect_stars(const DevModel& m, double x, doub
 }
 
 // ---- bisection samplers ------------------------------------------------------
+template <bool SM>
 __device__ __forceinline__ int select_wl_em(const DevModel& m, float rand) {          // thermal_emission.f90:364-400
   int kmin = 0, kmax = m.n_lambda, k = (kmin + kmax) / 2;
-  while (__ldg(m.spec_cumul + k) != (double)rand) {
-    if (__ldg(m.spec_cumul + k) < (double)rand) kmin = k; else kmax = k;
+  while (t_spec_cumul<SM>(m, k) != (double)rand) {
+    if (t_spec_cumul<SM>(m, k) < (double)rand) kmin = k; else kmax = k;
     k = (kmin + kmax) / 2;
     if ((kmax - kmin) <= 1) break;
   }
@@ -135,17 +182,17 @@ __device__ __forceinline__ void hg(float g, float rand, int& itheta, double& cos
   if (itheta > NANG) itheta = NANG;
 }
 // ---- scattering.f90:1433-1475 angle_diff_theta_pos ------------------------------
+template <bool SM>
 __device__ __forceinline__ void angle_diff_theta_pos(const DevModel& m, int p_lambda, int p_icell, float rand, float rand2,
                                                      int& itheta, double& cospsi) {
-  const float* p = m.prob_s11 + (size_t)(NANG + 1) * ((p_icell - 1) + (size_t)m.p_n_cells * (p_lambda - 1));
   int kmin = 0, kmax = NANG, k = (kmin + kmax) / 2;
   while ((kmax - kmin) > 1) {
-    if (__ldg(p + k) < rand) kmin = k; else kmax = k;
+    if (t_prob_s11<SM>(m, k, p_icell, p_lambda) < rand) kmin = k; else kmax = k;
     k = (kmin + kmax) / 2;
   }
   k = kmax;
   itheta = k;
-  double c0 = __ldg(m.cos_tab + k - 1), c1 = __ldg(m.cos_tab + k);
+  double c0 = t_cos<SM>(m, k - 1), c1 = t_cos<SM>(m, k);
   cospsi = c0 + rand2 * (c1 - c0);
 }
 
@@ -192,30 +239,28 @@ __device__ __forceinline__ void scatter_stokes(const DevModel& m, int lambda, in
 
 // ---- thermal_emission.f90:649-771 Temp_LTE + im_reemission_LTE (high-memory
 // branch): new wavelength index ------------------------------------------------
+template <bool SM>
 __device__ __forceinline__ int im_reemission_LTE(const DevModel& m, const DevRun& r, int idx, int p_icell, float rand2) {
-  const double* lq = m.logQ + (size_t)m.n_T * (p_icell - 1);
   // running tally: L2-coherent load (the adds are L2 atomics)
   double Qheat = __ldcg(m.tally + m.lay.xKJ + idx) * r.nb_proc_equiv * m.L_packet_th / __ldg(m.volume + idx);
   int Ti = 2;
   double frac_T2 = 0.0;       // `frac` is left undefined by the reference at T_min; 0 chosen (same as the oracle)
   if (!(Qheat < MCB_TINY_DP)) {
     double log_Qheat = log(Qheat);
-    if (!(log_Qheat < __ldg(lq + 0))) {
+    if (!(log_Qheat < t_logQ<SM>(m, 1, p_icell))) {
       Ti = __ldcg(m.xT_ech + idx);
-      while ((__ldg(lq + Ti - 1) < log_Qheat) && (Ti < m.n_T)) ++Ti;
+      while ((t_logQ<SM>(m, Ti, p_icell) < log_Qheat) && (Ti < m.n_T)) ++Ti;
       // another warp may have cached an index computed from a larger running tally: step back down
-      while (Ti > 2 && !(__ldg(lq + Ti - 2) < log_Qheat)) --Ti;
-      double q1 = __ldg(lq + Ti - 2), q2 = __ldg(lq + Ti - 1);
+      while (Ti > 2 && !(t_logQ<SM>(m, Ti - 1, p_icell) < log_Qheat)) --Ti;
+      double q1 = t_logQ<SM>(m, Ti - 1, p_icell), q2 = t_logQ<SM>(m, Ti, p_icell);
       frac_T2 = (log_Qheat - q1) / (q2 - q1);
     }
   }
   atomicMax(m.xT_ech + idx, Ti);
   const double frac_T1 = 1.0 - frac_T2;
-  const double* k1 = m.kdB + (size_t)m.n_lambda * ((Ti - 2) + (size_t)m.n_T * (p_icell - 1));
-  const double* k2 = k1 + m.n_lambda;
   int l1 = 0, l2 = m.n_lambda, l = (l1 + l2) / 2;
   while ((l2 - l1) > 1) {
-    double proba = frac_T1 * __ldg(k1 + l - 1) + frac_T2 * __ldg(k2 + l - 1);
+    double proba = frac_T1 * t_kdB<SM>(m, l, Ti - 1, p_icell) + frac_T2 * t_kdB<SM>(m, l, Ti, p_icell);
     if ((double)rand2 > proba) l1 = l; else l2 = l;
     l = (l1 + l2) / 2;
   }
@@ -323,13 +368,17 @@ __device__ __forceinline__ void deposit_rt1(const DevModel& m, const DevRun& r, 
 // =============================================================================
 // The persistent photon-loop kernel
 // =============================================================================
-template <class G>
-__global__ void __launch_bounds__(128, 4)
+constexpr int MC_BLOCK = 256;
+
+template <class G, bool SM>
+__global__ void __launch_bounds__(MC_BLOCK, 2)
 mc_photon_loop_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevRun r) {
   using CellT = typename G::CellT;
+  using Hit = typename G::Hit;
   const unsigned lane = threadIdx.x & 31;
   const bool thermal = r.letape_th != 0;
   const bool variable_dust = m.p_n_cells != 1;
+  if (SM) stage_tables(m, r.p_lambda_in);
 
   // ---- per-lane packet state ----
   int state = ST_FETCH;
@@ -338,7 +387,7 @@ mc_photon_loop_kernel(const __grid_constant__ DevModel m, const __grid_constant_
   double S[4] = {0, 0, 0, 0};
   int lambda = r.lambda_in;
   CellT cell; null_cell(cell);
-  bool flag_star = false, flag_scatt = false, flag_ISM = false, flag_direct_star = false;
+  bool flag_star = false, flag_scatt = false, flag_ISM = false;
   // flight state (physical_length locals)
   double x0 = 0, y0 = 0, z0 = 0, xo = 0, yo = 0, zo = 0, extr = 0;
   CellT c0, c_old; null_cell(c0); null_cell(c_old);
@@ -346,8 +395,7 @@ mc_photon_loop_kernel(const __grid_constant__ DevModel m, const __grid_constant_
   int i_star_hit = 0;
   Rt1Scratch rt1;
   unsigned long long st_steps = 0, st_int = 0, st_sca = 0, st_abs = 0, st_kill = 0, st_esc = 0, st_bounce = 0, st_pk = 0;
-  // SED-mode chunk bookkeeping
-  int my_chunk = -1;
+  int my_chunk = -1;      // SED-mode chunk bookkeeping
 
   for (;;) {
     const unsigned need = __ballot_sync(0xffffffffu, state == ST_FETCH);
@@ -391,26 +439,24 @@ mc_photon_loop_kernel(const __grid_constant__ DevModel m, const __grid_constant_
         ++st_pk;
         // n_phot_envoyes(lambda) is incremented with the PREVIOUS packet's lambda in thermal mode
         // (dust_transfer.f90:531 precedes :537); on the device packets are unordered, so the count is
-        // attributed to the packet's own emission wavelength (sum over lambda is identical).
-        if (!r.lmono) lambda = select_wl_em(m, rng.nextf());
+        // attributed to the packet's own emission wavelength (the sum over lambda is identical).
+        if (!r.lmono) lambda = select_wl_em<SM>(m, rng.nextf());
         atomicAdd(m.tally + m.lay.n_env + (lambda - 1), 1.0);
         // ---- emit_packet ----
         bool lintersect = true;
         flag_scatt = false;
         float rand = rng.nextf();
-        if ((double)rand <= __ldg(m.frac_star + lambda - 1)) {
+        if ((double)rand <= t_frac_star<SM>(m, lambda)) {
           flag_star = true; flag_ISM = false;
           const int i_star = select_star(m, lambda, rng.nextf());
           const float rand1 = rng.nextf(), rand2 = rng.nextf(), rand3 = rng.nextf(), rand4 = rng.nextf();
           // emit_packet_uniform_sphere
           double zz = 2.0 * rand1 - 1.0;
-          double srw02 = sqrt(1.0 - zz * zz);
-          double argmt = MCB_PI * (2.0 * rand2 - 1.0), sa, ca;
-          sincos(argmt, &sa, &ca);
+          double srw02 = sqrt(1.0 - zz * zz), sa, ca;
+          sincospi(2.0 * rand2 - 1.0, &sa, &ca);            // argmt = pi*(2 rand2 - 1)
           double xx = srw02 * ca, yy = srw02 * sa;
-          double cospsi = (double)sqrtf(rand3);
-          double phi = 2.0 * MCB_PI * rand4, sp, cp;
-          sincos(phi, &sp, &cp);
+          double cospsi = (double)sqrtf(rand3), sp, cp;
+          sincospi(2.0 * (double)rand4, &sp, &cp);          // phi = 2 pi rand4
           cdapres(cospsi, sp, cp, xx, yy, zz, u, v, w);
           const double r_star = m.star[i_star - 1][3] * (1.0 + 1e-6);
           x = xx * r_star + m.star[i_star - 1][0]; y = yy * r_star + m.star[i_star - 1][1]; z = zz * r_star + m.star[i_star - 1][2];
@@ -418,7 +464,7 @@ mc_photon_loop_kernel(const __grid_constant__ DevModel m, const __grid_constant_
           else cell = G::index(m, x, y, z);
           if (m.star_out[i_star - 1]) lintersect = G::move_to_grid(m, x, y, z, u, v, w, cell);
           S[0] = m.E_paquet; S[1] = S[2] = S[3] = 0.0;
-        } else if ((double)rand <= __ldg(m.frac_disk + lambda - 1)) {
+        } else if ((double)rand <= t_frac_disk<SM>(m, lambda)) {
           flag_star = false; flag_ISM = false;
           const int ic = select_cellule(m, lambda, rng.nextf());
           cell_of_id(m, ic, cell);
@@ -432,19 +478,16 @@ mc_photon_loop_kernel(const __grid_constant__ DevModel m, const __grid_constant_
           S[0] = 1.0; S[1] = S[2] = S[3] = 0.0;
           const float rand1 = rng.nextf(), rand2 = rng.nextf();
           double zz = 2.0 * rand1 - 1.0;
-          double srw02 = sqrt(1.0 - zz * zz);
-          double argmt = MCB_PI * (2.0 * rand2 - 1.0), sa, ca;
-          sincos(argmt, &sa, &ca);
+          double srw02 = sqrt(1.0 - zz * zz), sa, ca;
+          sincospi(2.0 * rand2 - 1.0, &sa, &ca);
           double xx = srw02 * ca, yy = srw02 * sa;
           const float rand3 = rng.nextf(), rand4 = rng.nextf();
-          double cospsi = (double)(-sqrtf(rand3));
-          double phi = 2.0 * MCB_PI * rand4, sp, cp;
-          sincos(phi, &sp, &cp);
+          double cospsi = (double)(-sqrtf(rand3)), sp, cp;
+          sincospi(2.0 * (double)rand4, &sp, &cp);
           cdapres(cospsi, sp, cp, xx, yy, zz, u, v, w);
           x = m.cISM[0] + xx * m.R_ISM; y = m.cISM[1] + yy * m.R_ISM; z = m.cISM[2] + zz * m.R_ISM;
           lintersect = G::move_to_grid(m, x, y, z, u, v, w, cell);
         }
-        flag_direct_star = flag_star;
         if (lintersect) state = ST_TAU;
         else {      // packet never enters the model: goes straight to the detector (dust_transfer.f90:545-552)
           if (!flag_ISM) {
@@ -461,7 +504,7 @@ mc_photon_loop_kernel(const __grid_constant__ DevModel m, const __grid_constant_
       const float rand = rng.nextf();
       float tau;
       if (rand == 1.0f) tau = 1.0e30f;
-      else if (rand > 1.0e-6f) tau = -(float)log((double)(1.0f - rand));   // correctly-rounded fp32 -log(1-rand)
+      else if (rand > 1.0e-6f) tau = -logf(1.0f - rand);       // `real` arithmetic in the reference (dust_transfer.f90:1212)
       else tau = rand;
       extr = (double)tau;
       x0 = x; y0 = y; z0 = z; xo = x; yo = y; zo = z;
@@ -495,7 +538,7 @@ mc_photon_loop_kernel(const __grid_constant__ DevModel m, const __grid_constant_
         int p_icell = 1;
         if (idx >= 0) {
           p_icell = variable_dust ? idx + 1 : 1;
-          opacity = __ldg(m.kappa + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)) * __ldg(m.kappa_factor + idx);
+          opacity = t_kappa<SM>(m, p_icell, lambda) * __ldg(m.kappa_factor + idx);
           if (__ldg(m.dark + idx)) {
             // dark-zone bounce (optical_depth.f90:104-112): back to the previous cell's entry point, reversed
             u = -u; v = -v; w = -w;
@@ -505,26 +548,29 @@ mc_photon_loop_kernel(const __grid_constant__ DevModel m, const __grid_constant_
             break;
           }
         }
-        double x1, y1, z1, l_contrib, l_void;
-        CellT c1;
-        double l = G::cross(m, dinv, x0, y0, z0, u, v, w, c0, c_old, x1, y1, z1, c1, l_contrib, l_void);
+        const Hit h = G::distance(m, dinv, x0, y0, z0, u, v, w, c0, c_old);
         ++st_steps;
+        double l_contrib = hit_l_contrib(h), l = h.l;
         const double tau_c = l_contrib * opacity;
         bool lstop = false;
         if (tau_c > extr) {
           lstop = true;
           l_contrib = l_contrib * (extr / tau_c);
-          l = l_void + l_contrib;
+          l = hit_l_void(h) + l_contrib;
         } else extr = extr - tau_c;
         if (idx >= 0) {
           // save_radiation_field
           if (thermal) {
-            atomicAdd(m.tally + m.lay.xKJ + idx, __ldg(m.kappa_abs + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)) * l_contrib * S[0]);
+            atomicAdd(m.tally + m.lay.xKJ + idx, t_kappa_abs<SM>(m, p_icell, lambda) * l_contrib * S[0]);
             if (r.lxJ) atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S[0]);
           } else {
             if (r.lxJ) atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S[0]);
-            if (r.rt1) deposit_rt1(m, r, idx, p_icell, r.p_lambda_in, l_contrib, S, flag_star,
-                                   0.5 * (x0 + x1), 0.5 * (y0 + y1), 0.5 * (z0 + z1), rt1);
+            if (r.rt1) {
+              double x1, y1, z1;
+              G::exit_point(h, x0, y0, z0, u, v, w, x1, y1, z1);
+              deposit_rt1(m, r, idx, p_icell, r.p_lambda_in, l_contrib, S, flag_star,
+                          0.5 * (x0 + x1), 0.5 * (y0 + y1), 0.5 * (z0 + z1), rt1);
+            }
           }
         }
         if (lstop) {
@@ -533,6 +579,9 @@ mc_photon_loop_kernel(const __grid_constant__ DevModel m, const __grid_constant_
           if (!G::is_vor && m.l3D && m.kind == 1) cell = G::index(m, x, y, z);     // optical_depth.f90:162-165
           state = ST_INTERACT;
         } else {
+          double x1, y1, z1;
+          CellT c1;
+          G::advance(m, h, x0, y0, z0, u, v, w, c0, x1, y1, z1, c1);
           xo = x0; yo = y0; zo = z0; c_old = c0;
           x0 = x1; y0 = y1; z0 = z1; c0 = c1;
         }
@@ -542,10 +591,9 @@ mc_photon_loop_kernel(const __grid_constant__ DevModel m, const __grid_constant_
     // ------------------------------------------------------------ INTERACT
     if (state == ST_INTERACT) {
       ++st_int;
-      flag_direct_star = false;
       const int idx = tally_index(m, cell);
       const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
-      const float albedo = __ldg(m.albedo + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1));
+      const float albedo = t_albedo<SM>(m, p_icell, lambda);
       float rand;
       bool dead = false;
       if (r.lmono) {      // forced scattering (dust_transfer.f90:1263-1278)
@@ -564,12 +612,12 @@ mc_photon_loop_kernel(const __grid_constant__ DevModel m, const __grid_constant_
         rand = rng.nextf();
         const float rand2 = rng.nextf();
         int itheta; double cospsi;
-        if (r.lmethod_aniso1) angle_diff_theta_pos(m, r.p_lambda_in, p_icell, rand, rand2, itheta, cospsi);
-        else hg(__ldg(m.gfac + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)), rand, itheta, cospsi);
+        if (r.lmethod_aniso1) angle_diff_theta_pos<SM>(m, r.p_lambda_in, p_icell, rand, rand2, itheta, cospsi);
+        else hg(t_gfac<SM>(m, p_icell, lambda), rand, itheta, cospsi);
         if (r.lisotropic) { itheta = 1; cospsi = (double)__fsub_rn(__fmul_rn(2.0f, rand), 1.0f); }
         rand = rng.nextf();
-        const double phi = MCB_PI * (double)__fsub_rn(__fmul_rn(2.0f, rand), 1.0f);     // PHI = PI*(2.0*rand-1.0): fp32 inner
-        double sp, cp; sincos(phi, &sp, &cp);
+        double sp, cp;
+        sincospi((double)__fsub_rn(__fmul_rn(2.0f, rand), 1.0f), &sp, &cp);     // PHI = PI*(2.0*rand-1.0): fp32 inner
         double u1, v1, w1;
         cdapres(cospsi, sp, cp, u, v, w, u1, v1, w1);
         if (r.lmethod_aniso1 && r.lsepar_pola) scatter_stokes(m, lambda, itheta, rand2, p_icell, S, u, v, w, u1, v1, w1);
@@ -581,7 +629,7 @@ mc_photon_loop_kernel(const __grid_constant__ DevModel m, const __grid_constant_
         flag_star = false; flag_scatt = false; flag_ISM = false;
         (void)rng.nextf();                       // rand1 is drawn but unused in the high-memory LTE branch
         const float rand2 = rng.nextf();
-        lambda = im_reemission_LTE(m, r, idx, p_icell, rand2);
+        lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, rand2);
         random_isotropic_direction(rng, u, v, w);
         S[1] = 0.0; S[2] = 0.0; S[3] = 0.0;
         state = ST_TAU;

@@ -13,10 +13,12 @@
  *   key     = (seed_lo, seed_hi)
  *   counter = (block, packet_lo, packet_hi, call_index)
  *   packet  = (chunk-1) * 2^40 + index_in_chunk (0-based)
- *   each 128-bit block yields two uniform doubles in [0,1):
- *       d0 = ((w1 >> 5) * 2^26 + (w0 >> 6)) * 2^-53,  d1 likewise from (w3, w2)
- *   which the callers cast to fp32 exactly where the reference assigns
- *   sprng() to a `real` (so rand can round to 1.0, dust_transfer.f90:1209).
+ *   each 128-bit block yields four uniform draws, consumed in order w0..w3:
+ *       rand = (w >> 8) * 2^-24          (exactly representable in fp32, in [0,1))
+ *   Every sprng() call site on this path assigns the result to a Fortran `real`
+ *   (fp32), so one 24-bit draw per call carries all the bits the reference keeps
+ *   near 1; the one difference is that rand can never round up to exactly 1.0
+ *   (the reference guards that case explicitly, dust_transfer.f90:1209).
  */
 #ifndef ORACLE_PHILOX_H
 #define ORACLE_PHILOX_H
@@ -39,10 +41,6 @@ static inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], u
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-static inline double philox_u01(uint32_t lo, uint32_t hi) {
-  return (double)(((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6)) * (1.0 / 9007199254740992.0);
-}
-
 typedef struct PacketRng {
   /* recorded stream (deterministic unit tests): if rec != 0, values are
      replayed cyclically instead of generated */
@@ -50,27 +48,28 @@ typedef struct PacketRng {
   int64_t n_rec, i_rec;
   uint32_t key[2];
   uint32_t ctr[4];     /* ctr[0] = next block index */
-  double   spare;
-  int      have_spare;
+  uint32_t buf[4];
+  int      n_buf;      /* unread words left in buf */
   int64_t  n_draws;
 } PacketRng;
 
 static inline void rng_seed_packet(PacketRng *g, uint64_t seed, uint32_t call_index, uint64_t packet) {
   g->key[0] = (uint32_t)seed; g->key[1] = (uint32_t)(seed >> 32);
   g->ctr[0] = 0; g->ctr[1] = (uint32_t)packet; g->ctr[2] = (uint32_t)(packet >> 32); g->ctr[3] = call_index;
-  g->have_spare = 0; g->n_draws = 0;
+  g->n_buf = 0; g->n_draws = 0;
 }
 
-/* the analogue of sprng(stream(id)): a double in [0,1) */
+/* the analogue of sprng(stream(id)): a value in [0,1) (24-bit resolution) */
 static inline double rng_next(PacketRng *g) {
   g->n_draws++;
   if (g->rec) { double v = g->rec[g->i_rec % g->n_rec]; g->i_rec++; return v; }
-  if (g->have_spare) { g->have_spare = 0; return g->spare; }
-  uint32_t o[4];
-  philox4x32_10(g->ctr, g->key, o);
-  g->ctr[0]++;
-  g->spare = philox_u01(o[2], o[3]);
-  g->have_spare = 1;
-  return philox_u01(o[0], o[1]);
+  if (g->n_buf == 0) {
+    philox4x32_10(g->ctr, g->key, g->buf);
+    g->ctr[0]++;
+    g->n_buf = 4;
+  }
+  uint32_t w = g->buf[4 - g->n_buf];
+  g->n_buf--;
+  return (double)(w >> 8) * (1.0 / 16777216.0);
 }
 #endif
