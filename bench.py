@@ -73,9 +73,14 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def make_problem(args, walker_factory=None):
+# ref4.1.para: "T T" = separation of contributions, Stokes parameters (read_param.f90:163);
+# lsepar_pola stays on during the thermal step, so scatterings update the Stokes vector.
+FLAGS = dict(lsepar_pola=1, lsepar_contrib=1)
+
+
+def make_problem(args, walker_factory=None, world=1):
     from mcfost_b200 import synthetic as S
-    P = S.ref41_like(n_photons_eq_th=args.n2, dark_zone=False)
+    P = S.ref41_like(n_photons_eq_th=args.n2 * world, dark_zone=False)      # L_packet_th = L_tot / (128 * n2 * world)
     if walker_factory is not None:
         P.l_dark_zone = S.define_dark_zone(P, P.lambda_seuil, 1500.0, walker_factory(P))
         S.repartition_energie(P)
@@ -88,9 +93,9 @@ def cpu_run(P, n2, threads=0, rank=0, n_ranks=1):
     from oracle.binding import Oracle
     O = Oracle(P, fast=True)
     nthr = threads or O.lib.oracle_max_threads()
-    O.run(n_threads=nthr, n_photons2=max(1, n2 // 50))           # warm-up (thread pool, page faults)
+    O.run(n_threads=nthr, n_photons2=max(1, n2 // 50), **FLAGS)           # warm-up (thread pool, page faults)
     t0 = time.perf_counter()
-    t = O.run(n_threads=nthr, n_photons2=n2)
+    t = O.run(n_threads=nthr, n_photons2=n2, **FLAGS)
     dt = time.perf_counter() - t0
     return float(t.stats[0]), dt, t.stats.copy(), nthr
 
@@ -105,6 +110,7 @@ def reference_arm(args):
     except Exception:
         binding.build()
     from oracle.binding import Oracle
+    args.n2 = args.cpu_n2                      # the sample's own packet count sets L_packet_th
     P = make_problem(args, lambda P: Oracle(P).dark_zone_walker())
     n2 = args.cpu_n2
     times, packets = [], 0.0
@@ -142,7 +148,7 @@ def gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    P = make_problem(args)
+    P = make_problem(args, world=world)
     loop = api.PhotonLoop(P, device=local, rank=rank, n_ranks=world)
     # dark zone via the library's own deterministic ray-walk kernel (define_dark_zone step 4)
     P.l_dark_zone = S.define_dark_zone(P, P.lambda_seuil, 1500.0, loop.dark_zone_walker())
@@ -155,7 +161,7 @@ def gpu_arm(args):
     a64, _ = None, None
 
     def step(call_index, reduce=True):
-        r = loop.launch(1, 1, n2, 1.0e30, 1, call_index=call_index, reset_tallies=1)
+        r = loop.launch(1, 1, n2, 1.0e30, 1, call_index=call_index, reset_tallies=1, **FLAGS)
         if world > 1 and reduce:
             nonlocal a64
             if a64 is None:
@@ -205,7 +211,7 @@ def gpu_arm(args):
     h2d = d2h = 0
     for i in range(e2e_steps):
         loop.upload_emission(P)               # repartition_energie output changes every temperature iteration
-        t = loop.mc_photon_loop(1, 1, n2, 1.0e30, 1, False, call_index=1000 + i)
+        t = loop.mc_photon_loop(1, 1, n2, 1.0e30, 1, False, call_index=1000 + i, **FLAGS)
         h2d = sum(a.nbytes for a in loop._e.keep.values())
         d2h = sum(getattr(t, k).nbytes for k in ("xKJ_abs", "xT_ech", "n_phot_envoyes", "sed", "sed_q", "sed_u", "sed_v", "n_phot_sed",
                                                   "sed_star", "sed_star_scat", "sed_disk", "sed_disk_scat", "stats"))
@@ -228,7 +234,11 @@ def gpu_arm(args):
                 binding.build(fast_native=True)
             except Exception:
                 binding.build()
-            pk, dt, st, nthr = cpu_run(P, args.cpu_n2)
+            import copy
+            Pc = copy.copy(P)
+            Pc.n_photons_eq_th = args.cpu_n2
+            S.repartition_energie(Pc)                 # same model, L_packet_th for the sample's packet count
+            pk, dt, st, nthr = cpu_run(Pc, args.cpu_n2)
             cpu = {"value": pk / dt, "unit": UNIT, "cores": nthr, "kind": "port",
                    "sample": f"oracle-OpenMP (reference restatement), same model, {int(pk)} packets in {dt:.2f} s wall on {nthr} threads"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -241,7 +251,7 @@ def gpu_arm(args):
                 "gpu_launches": int(args.steps * 2),          # mc_photon_loop_kernel + fill_int_kernel (xT_ech reset) per step
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                             "peak_source": peak_src, "kernel": "mc_photon_loop_kernel<GeomCyl<false>>", "kernel_ms": last_ms,
+                             "peak_source": peak_src, "kernel": "mc_photon_loop_kernel<GeomCyl<false,true>,true>", "kernel_ms": last_ms,
                              "note": "algorithmic bytes (SURVEY 8d) / kernel time; tables are L2-resident so the path is latency/atomic-bound, not HBM-bound",
                              "steps_per_s": stats[1] / world / (last_ms * 1e-3), "interactions_per_s": stats[2] / world / (last_ms * 1e-3),
                              "steps_per_packet": stats[1] / stats[0], "interactions_per_packet": stats[2] / stats[0]},

@@ -5,7 +5,7 @@
 #include <cmath>
 
 #include "handle.cuh"
-#include "transport.cuh"
+#include "cells.cuh"
 
 using namespace mcb;
 

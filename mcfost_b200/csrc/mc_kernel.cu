@@ -9,22 +9,25 @@ using namespace mcb;
 
 template <class G, bool SM>
 static int launch_one(mcb_handle* h, const DevRun& dr) {
-  const size_t smem = SM ? (size_t)h->m.sm.total_words * 8 : 0;
+  const size_t smem = (SM ? (size_t)h->m.sm.total_words * 8 : 0) + pool_bytes(dr.lsepar_pola != 0);
   auto kern = mc_photon_loop_kernel<G, SM>;
-  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MC_BLOCK, smem));
-  if (per_sm < 1) per_sm = 1;
-  const int blocks = h->n_sm * per_sm;          // persistent: exactly one resident wave over the 148 SMs
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // model + run parameters -> constant memory, ordered on the handle's stream
+  CK(cudaMemcpyToSymbolAsync(c_m, &h->m, sizeof(DevModel), 0, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyToSymbolAsync(c_r, &dr, sizeof(DevRun), 0, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));          // dr / h->m are host stack / heap values
+  const int blocks = h->n_sm;                     // persistent: one 512-thread block (1024 packets in flight) per SM
   CK(cudaEventRecord(h->ev0, h->stream));
-  kern<<<blocks, MC_BLOCK, smem, h->stream>>>(h->m, dr);
+  kern<<<blocks, MC_BLOCK, smem, h->stream>>>();
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, h->stream));
   return MCB_OK;
 }
 
 int mcb_launch_mc(mcb_handle* h, const DevRun& dr) {
-  const bool sm = h->m.sm.enabled != 0;
+  bool sm = h->m.sm.enabled != 0;
+  // the pool (~127-151 KB) and the staged tables must fit the 227 KB of one SM
+  if (sm && (size_t)h->m.sm.total_words * 8 + pool_bytes(dr.lsepar_pola != 0) > 227 * 1024) sm = false;
   switch (h->gk) {
     case GK_CYL2D: return sm ? launch_one<GeomCyl<false, true>, true>(h, dr) : launch_one<GeomCyl<false, false>, false>(h, dr);
     case GK_CYL3D: return sm ? launch_one<GeomCyl<true, true>, true>(h, dr) : launch_one<GeomCyl<true, false>, false>(h, dr);

@@ -13,39 +13,38 @@
 //   emit_packet_ISM / intersect_stars stars.f90:75-169,728-884, capteur
 //   output.f90:294-595 (SED branch).
 //
-// Execution model (B200): one packet per thread, persistent warps.  Each warp
-// iteration runs the phases FETCH -> TAU -> FLY -> INTERACT under warp-uniform
-// guards so that lanes in the same phase execute together; new packets are
-// claimed from a global counter with one warp-aggregated atomic.  The small hot
-// tables (radial / vertical walls, kappa(lambda), albedo, log Qcool, the k dB/dT
-// CDF, the s11 CDF, cos table, emission spectra) are staged once per block in
-// shared memory (SmemLayout, ~48 KB for ref4.1) when the dust is not cell-
-// dependent; per-cell arrays stay in global memory behind L1/L2.  Tallies are L2
-// atomics (red.global.add.f64); the running cell temperature reads them back
-// with ld.global.cg (L1 is not coherent with L2 atomics).  The next-cell half of
-// a crossing is skipped when the flight ends inside the cell.
+// Execution model (B200): persistent blocks, one per SM, each owning a pool of
+// NP = 1024 packets whose state lives in SHARED MEMORY (structure of arrays,
+// ~124 B per packet).  Work is organised in rounds: every packet sits in exactly
+// one per-phase queue (EMIT, FLY, SCATTER, ABSORB); warps claim 32-entry chunks
+// of a single queue, run that phase for the 32 packets (registers <-> shared
+// memory), and push each packet to the queue of its next phase with one warp-
+// aggregated shared-memory atomic.  This is the "periodic regrouping": every
+// warp instruction is executed by lanes that are all in the same phase, and the
+// RNG state of a packet is just (packet id, event counter), so any thread can
+// continue any packet.  New packets are claimed from a global counter with one
+// warp-aggregated atomic.  The small hot tables (walls, kappa(lambda), albedo,
+// log Qcool, the k dB/dT CDF, the s11 CDF, cos table, emission spectra; ~48 KB
+// for ref4.1) are staged once per block in shared memory when the dust is not
+// cell-dependent; per-cell arrays stay in global memory behind L1/L2.  Tallies
+// are L2 atomics (red.global.add.f64); the running cell temperature reads them
+// back with ld.global.cg (L1 is not coherent with L2 atomics).  The next-cell
+// half of a crossing is skipped when the flight ends inside the cell.
 #pragma once
 #include "model.cuh"
 #include "philox.cuh"
-#include "geom_rz.cuh"
-#include "geom_vor.cuh"
+#include "cells.cuh"
 
 namespace mcb {
 
-enum { ST_FETCH = 0, ST_TAU = 1, ST_FLY = 2, ST_INTERACT = 3, ST_DONE = 4 };
-enum { STAT_PACKETS = 0, STAT_STEPS, STAT_INTERACT, STAT_SCATT, STAT_ABS, STAT_KILLED, STAT_ESCAPED, STAT_BOUNCE };
+// The model and run parameters of the launch in flight live in constant memory (written by
+// mcb_launch_mc on the handle's stream): every phase function reads them through the constant
+// bank without threading pointers through the non-inlined calls.
+__constant__ DevModel c_m;
+__constant__ DevRun c_r;
 
-// ---- cell helpers common to rz and Voronoi -------------------------------
-__device__ __forceinline__ int tally_index(const DevModel& m, Cell c) { return is_real(m, c) ? real_index(m, c) : -1; }
-__device__ __forceinline__ int tally_index(const DevModel& m, int c) { return (c >= 1 && c <= m.n_cells) ? c - 1 : -1; }
-__device__ __forceinline__ bool same_cell(Cell a, Cell b) { return a.ri == b.ri && a.zj == b.zj && a.k == b.k; }
-__device__ __forceinline__ bool same_cell(int a, int b) { return a == b; }
-__device__ __forceinline__ void cell_of_id(const DevModel& m, int id, Cell& c) { c = cell_from_id(m, id); }
-__device__ __forceinline__ void cell_of_id(const DevModel&, int id, int& c) { c = id; }
-__device__ __forceinline__ int id_of_cell(const DevModel& m, Cell c) { return cell_id(m, c); }
-__device__ __forceinline__ int id_of_cell(const DevModel&, int c) { return c; }
-__device__ __forceinline__ void null_cell(Cell& c) { c.ri = -7; c.zj = 0; c.k = 0; }
-__device__ __forceinline__ void null_cell(int& c) { c = 0; }
+enum { Q_EMIT = 0, Q_ABS = 1, Q_SCAT = 2, Q_FLY = 3, NQ = 4, Q_NONE = 7 };     // queue order = claim order (longest phases first)
+enum { STAT_PACKETS = 0, STAT_STEPS, STAT_INTERACT, STAT_SCATT, STAT_ABS, STAT_KILLED, STAT_ESCAPED, STAT_BOUNCE };
 
 // ---- opacity / thermal table accessors (SM: shared-memory staging, p_n_cells == 1) ----
 __device__ __forceinline__ const float* smf(int word_off) { return reinterpret_cast<const float*>(smd() + word_off); }
@@ -112,33 +111,17 @@ __device__ __forceinline__ void rotation(double xi, double yi, double zi, double
   yf = cost * yi - sint * xi;
   zf = sing * zi - w1 * prod;
 }
-// ---- random_numbers.f90:32-51 ---------------------------------------------
-__device__ __forceinline__ void random_isotropic_direction(Rng& rng, double& u, double& v, double& w) {
-  float rand = rng.nextf();
-  w = 2.0 * rand - 1.0;
-  double uv = sqrt(1.0 - w * w);
-  rand = rng.nextf();
-  double sp, cp;
-  sincospi(2.0 * rand - 1.0, &sp, &cp);       // phi = pi*(2 rand - 1)
-  u = uv * cp; v = uv * sp;
-}
+// ---- heavy libm entry points, not inlined: one copy each in the instruction stream ----
+__device__ __noinline__ double mcb_log(double x) { return log(x); }
+__device__ __noinline__ void mcb_sincospi(double x, double* s, double* c) { sincospi(x, s, c); }
 
-// ---- stars.f90:812-884 intersect_stars -> index of the star (0 = none) -----
-__device__ __forceinline__ int intersect_stars(const DevModel& m, double x, double y, double z, double u, double v, double w) {
-  double d_to_star = MCB_HUGE_DP;
-  int i_star = 0;
-  for (int i = 0; i < m.n_stars; ++i) {
-    double dx = x - m.star[i][0], dy = y - m.star[i][1], dz = z - m.star[i][2];
-    double b = dx * u + dy * v + dz * w;
-    double c = (dx * dx + dy * dy + dz * dz) - m.star[i][3] * m.star[i][3];
-    double delta = b * b - c;
-    if (delta >= 0.) {
-      double rac = sqrt(delta), s1 = -b - rac;
-      if (s1 < 0) { double s2 = -b + rac; if (s2 > 0) { d_to_star = 0.0; i_star = i + 1; } }
-      else if (s1 < d_to_star) { d_to_star = s1; i_star = i + 1; }
-    }
-  }
-  return i_star;
+// ---- random_numbers.f90:32-51 (the two draws are passed in) -------------------
+__device__ __forceinline__ void random_isotropic_direction(float rand_w, float rand_phi, double& u, double& v, double& w) {
+  w = 2.0 * rand_w - 1.0;
+  double uv = sqrt(1.0 - w * w);
+  double sp, cp;
+  mcb_sincospi(2.0 * rand_phi - 1.0, &sp, &cp);       // phi = pi*(2 rand - 1)
+  u = uv * cp; v = uv * sp;
 }
 
 // ---- bisection samplers ------------------------------------------------------
@@ -198,8 +181,9 @@ __device__ __forceinline__ void angle_diff_theta_pos(const DevModel& m, int p_la
 
 // ---- scattering.f90:1187-1298 update_Stokes with the per-cell Mueller matrix
 // of get_Mueller_matrix_per_cell (:1328-1350); sparse products written out ------
-__device__ __forceinline__ void scatter_stokes(const DevModel& m, int lambda, int itheta, float frac, int p_icell, double* S,
+__device__ __noinline__ void scatter_stokes(int lambda, int itheta, float frac, int p_icell, double* S,
                                                double u0, double v0, double w0, double u1, double v1, double w1) {
+  const DevModel& m = c_m;
   const size_t q1 = (size_t)itheta + (size_t)(NANG + 1) * ((p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)), q0 = q1 - 1;
   const float frac_m1 = 1.0f - frac;
   const double M11 = (double)1.0f;
@@ -246,7 +230,7 @@ __device__ __forceinline__ int im_reemission_LTE(const DevModel& m, const DevRun
   int Ti = 2;
   double frac_T2 = 0.0;       // `frac` is left undefined by the reference at T_min; 0 chosen (same as the oracle)
   if (!(Qheat < MCB_TINY_DP)) {
-    double log_Qheat = log(Qheat);
+    double log_Qheat = mcb_log(Qheat);
     if (!(log_Qheat < t_logQ<SM>(m, 1, p_icell))) {
       Ti = __ldcg(m.xT_ech + idx);
       while ((t_logQ<SM>(m, Ti, p_icell) < log_Qheat) && (Ti < m.n_T)) ++Ti;
@@ -268,8 +252,9 @@ __device__ __forceinline__ int im_reemission_LTE(const DevModel& m, const DevRun
 }
 
 // ---- output.f90:294-595 capteur, SED branch ------------------------------------
-__device__ __forceinline__ int capteur(const DevModel& m, const DevRun& r, int lambda, double u1, double v1, double w1,
+__device__ __noinline__ int capteur(int lambda, double u1, double v1, double w1,
                                        const double* Sin, bool flag_star, bool flag_scatt) {
+  const DevModel& m = c_m; const DevRun& r = c_r;
   double s0 = Sin[0], s1 = Sin[1], s2 = Sin[2], s3 = Sin[3];
   if (w1 < 0.0) {
     if (r.l_sym_centrale) { u1 = -u1; v1 = -v1; w1 = -w1; s2 = -s2; }
@@ -299,7 +284,8 @@ __device__ __forceinline__ int capteur(const DevModel& m, const DevRun& r, int l
 // ---- dust_ray_tracing.f90:409-476 angles_scatt_rt1 (per flight) ------------------
 struct Rt1Scratch { unsigned char itheta[MAX_RT]; double cosw[MAX_RT], sinw[MAX_RT]; };
 
-__device__ __forceinline__ void angles_scatt_rt1(const DevRun& r, double u, double v, double w, Rt1Scratch& sc) {
+__device__ __noinline__ void angles_scatt_rt1(double u, double v, double w, Rt1Scratch& sc) {
+  const DevRun& r = c_r;
   for (int i = 0; i < r.n_rt; ++i) {
     float cos_scatt = (float)(r.rt_u[i] * u + r.rt_v[i] * v + r.rt_w[i] * w);
     // k = nint(acos(cos_scatt) * real(nang_scatt)/pi): fp32 product, dp division, round half away (q >= 0)
@@ -328,8 +314,9 @@ __device__ __forceinline__ void angles_scatt_rt1(const DevRun& r, double u, doub
 
 // ---- radiation_field.f90:63-89 + dust_ray_tracing.f90:480-632: rt1 scattered
 // specific intensity, fp32 atomics ---------------------------------------------------
-__device__ __forceinline__ void deposit_rt1(const DevModel& m, const DevRun& r, int idx, int p_icell, int p_lambda, double l,
+__device__ __noinline__ void deposit_rt1(int idx, int p_icell, int p_lambda, double l,
                                             const double* S, bool flag_star, double xm, double ym, double zm, const Rt1Scratch& sc) {
+  const DevModel& m = c_m; const DevRun& r = c_r;
   int phi_k = 1, psup = 1;
   if (!m.l3D) {
     double phi_pos = atan2(xm, ym);
@@ -366,285 +353,506 @@ __device__ __forceinline__ void deposit_rt1(const DevModel& m, const DevRun& r, 
 }
 
 // =============================================================================
-// The persistent photon-loop kernel
+// Packet pool in shared memory
 // =============================================================================
-constexpr int MC_BLOCK = 256;
+constexpr int MC_BLOCK = 512;       // threads per block (one block per SM)
+constexpr int NP = 1024;            // packets in flight per block
+constexpr int FLY_STEPS = 4;        // cell crossings per FLY visit
 
+enum { F_PX = 0, F_PY, F_PZ, F_OX, F_OY, F_OZ, F_U, F_V, F_W, F_S0, F_EXTR, F_S1, F_S2, F_S3 };
+enum { U_C0A = 0, U_C0B, U_COA, U_COB, U_PKLO, U_PKHI, U_EV, U_MISC, U_RALB, NU32 = 9 };
+__host__ __device__ constexpr int pool_nf64(bool pola) { return pola ? 14 : 11; }
+
+// bytes of shared memory after the staged tables
+__host__ __device__ constexpr size_t pool_bytes(bool pola) {
+  return (size_t)pool_nf64(pola) * NP * 8 + (size_t)NU32 * NP * 4 + (size_t)2 * NQ * NP * 2 + 64 * 4;
+}
+
+struct Pool {
+  double* f;            // [NF64][NP]
+  uint32_t* u;          // [NU32][NP]
+  unsigned short* q;    // [2][NQ][NP]
+  int* ctl;             // [0..7] qn[parity][queue]; [8..12] chunk prefix; [13] next chunk; [14] total chunks
+  __device__ __forceinline__ double& F(int field, int slot) const { return f[field * NP + slot]; }
+  __device__ __forceinline__ uint32_t& U(int field, int slot) const { return u[field * NP + slot]; }
+  __device__ __forceinline__ unsigned short* Q(int parity, int queue) const { return q + (parity * NQ + queue) * NP; }
+  __device__ __forceinline__ int& QN(int parity, int queue) const { return ctl[parity * NQ + queue]; }
+};
+
+// misc word: lambda (10 bits) | star 1 | scatt 1 | ISM 1 | i_star_hit 4 | chunk 15
+__device__ __forceinline__ uint32_t pack_misc(int lambda, bool star, bool scatt, bool ism, int istar, int chunk) {
+  return (uint32_t)lambda | ((uint32_t)star << 10) | ((uint32_t)scatt << 11) | ((uint32_t)ism << 12) | ((uint32_t)istar << 13) | ((uint32_t)chunk << 17);
+}
+__device__ __forceinline__ int misc_lambda(uint32_t m) { return m & 1023; }
+__device__ __forceinline__ bool misc_star(uint32_t m) { return (m >> 10) & 1; }
+__device__ __forceinline__ bool misc_scatt(uint32_t m) { return (m >> 11) & 1; }
+__device__ __forceinline__ bool misc_ism(uint32_t m) { return (m >> 12) & 1; }
+__device__ __forceinline__ int misc_istar(uint32_t m) { return (m >> 13) & 15; }
+__device__ __forceinline__ int misc_chunk(uint32_t m) { return (int)(m >> 17); }
+
+// cells <-> two 32-bit words
+__device__ __forceinline__ void pack_cell(Cell c, uint32_t& a, uint32_t& b) { a = (uint32_t)c.ri; b = ((uint32_t)c.zj & 0xFFFFu) | ((uint32_t)c.k << 16); }
+__device__ __forceinline__ void unpack_cell(uint32_t a, uint32_t b, Cell& c) { c.ri = (int)a; c.zj = (int)(short)(b & 0xFFFFu); c.k = (int)(b >> 16); }
+__device__ __forceinline__ void pack_cell(int c, uint32_t& a, uint32_t& b) { a = (uint32_t)c; b = 0; }
+__device__ __forceinline__ void unpack_cell(uint32_t a, uint32_t, int& c) { c = (int)a; }
+
+// the pool of this block: right after the staged tables in dynamic shared memory
+template <bool SM> __device__ __forceinline__ Pool make_pool() {
+  Pool P;
+  unsigned char* base = mcb_smem_raw + (SM ? (size_t)c_m.sm.total_words * 8 : 0);
+  const size_t nf = (size_t)pool_nf64(c_r.lsepar_pola != 0);
+  P.f = reinterpret_cast<double*>(base);
+  P.u = reinterpret_cast<uint32_t*>(base + nf * NP * 8);
+  P.q = reinterpret_cast<unsigned short*>(base + nf * NP * 8 + (size_t)NU32 * NP * 4);
+  P.ctl = reinterpret_cast<int*>(base + nf * NP * 8 + (size_t)NU32 * NP * 4 + (size_t)2 * NQ * NP * 2);
+  return P;
+}
+
+struct Stats { unsigned int pk, steps, inter, sca, abs_, kill, esc, bounce; };
+
+// push the packets of this warp to the queues of their next phase (one shared-memory atomic per queue)
+__device__ __forceinline__ void push_next(const Pool& P, int np, int slot, int nextq, unsigned lane) {
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi) {
+    const unsigned mask = __ballot_sync(0xffffffffu, nextq == qi);
+    if (mask == 0) continue;
+    const int leader = __ffs(mask) - 1;
+    int base = 0;
+    if ((int)lane == leader) base = atomicAdd(&P.QN(np, qi), __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (nextq == qi) P.Q(np, qi)[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)slot;
+  }
+}
+
+// ---- begin flight `ev`: tau and the interaction-type draw from block 2*ev (dust_transfer.f90:1208-1215,1280),
+// physical_length preamble (optical_depth.f90:53-68).  Position / direction / cell are already in the pool. ----
+__device__ __forceinline__ void start_flight(const DevModel& m, const DevRun& r, const Pool& P, int slot,
+                                             double x, double y, double z, double u, double v, double w,
+                                             uint32_t pk_lo, uint32_t pk_hi, uint32_t ev, uint32_t& misc) {
+  const uint4 b = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev, pk_lo, pk_hi, r.call_index);
+  const float rand = u01(b.x);
+  float tau;
+  if (rand == 1.0f) tau = 1.0e30f;
+  else if (rand > 1.0e-6f) tau = -logf(1.0f - rand);       // `real` arithmetic in the reference (dust_transfer.f90:1212)
+  else tau = rand;
+  P.F(F_EXTR, slot) = (double)tau;
+  P.U(U_RALB, slot) = __float_as_uint(u01(b.y));
+  P.F(F_OX, slot) = x; P.F(F_OY, slot) = y; P.F(F_OZ, slot) = z;
+  P.U(U_COA, slot) = 0xFFFFFFF9u; P.U(U_COB, slot) = 0;          // null previous cell
+  const int istar = intersect_stars(m, x, y, z, u, v, w);
+  misc = (misc & ~(15u << 13)) | ((uint32_t)istar << 13);
+}
+
+// =============================================================================
+// EMIT: claim a packet id, emit_packet (dust_transfer.f90:1047-1151), start the first flight
+// =============================================================================
 template <class G, bool SM>
-__global__ void __launch_bounds__(MC_BLOCK, 2)
-mc_photon_loop_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevRun r) {
+__device__ __noinline__ void phase_emit(int slot, bool valid, int np, Stats& st) {
+  const DevModel& m = c_m; const DevRun& r = c_r;
+  const bool POLA = r.lsepar_pola != 0;
+  const Pool P = make_pool<SM>();
+  using CellT = typename G::CellT;
+  const unsigned lane = threadIdx.x & 31;
+  int nextq = Q_NONE;
+  // ---- claim.  Thermal / fixed-count mode: one warp-aggregated atomic on the global counter.  SED mode
+  // (dust_transfer.f90:507-510,529,551): a chunk keeps sending until n_photons2 packets were RECEIVED in
+  // detector bin capt_sup (or n_phot_lim were sent).
+  int nnfot1 = 0, my_chunk = 0;
+  unsigned long long idx_in_chunk = 0;
+  bool got = false;
+  const int first_local = r.nnfot1_start + ((r.rank - ((r.nnfot1_start - 1) % r.n_ranks) + r.n_ranks) % r.n_ranks);
+  if (r.count_sent) {
+    const unsigned need = __ballot_sync(0xffffffffu, valid);
+    if (need) {
+      const int leader = __ffs(need) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == leader) base = atomicAdd(m.work, (unsigned long long)__popc(need));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      const unsigned long long g = base + __popc(need & ((1u << lane) - 1u));
+      if (valid && g < r.n_packets_total) {
+        const unsigned long long lc = g / r.n_per_chunk;
+        idx_in_chunk = g % r.n_per_chunk;
+        nnfot1 = first_local + (int)lc * r.n_ranks;
+        my_chunk = (int)lc;
+        got = true;
+      }
+    }
+  } else if (valid) {
+    const int start = (int)(((unsigned long long)blockIdx.x * NP + slot + st.pk) % (unsigned long long)r.n_local_chunks);
+    for (int tries = 0; tries < r.n_local_chunks && !got; ++tries) {
+      int lc = start + tries; if (lc >= r.n_local_chunks) lc -= r.n_local_chunks;
+      if (__ldcg(m.work + 3 + 2 * lc) >= (unsigned long long)r.n_photons2) continue;
+      const unsigned long long sidx = atomicAdd(m.work + 2 + 2 * lc, 1ull);
+      if (sidx >= r.sent_lim) { atomicAdd(m.work + 2 + 2 * lc, ~0ull); continue; }     // undo (adds -1)
+      idx_in_chunk = sidx; nnfot1 = first_local + lc * r.n_ranks; my_chunk = lc; got = true;
+    }
+  }
+  if (got) {
+    const unsigned long long packet = ((unsigned long long)(nnfot1 - 1) << 40) + idx_in_chunk;
+    const uint32_t pk_lo = (uint32_t)packet, pk_hi = (uint32_t)(packet >> 32);
+    const uint4 b0 = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 0u, pk_lo, pk_hi, r.call_index);
+    const uint4 b1 = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 1u, pk_lo, pk_hi, r.call_index);
+    int di = 0;
+    auto nextf = [&]() -> float {
+      const int i = di++;
+      const uint32_t w = (i == 0) ? b0.x : (i == 1) ? b0.y : (i == 2) ? b0.z : (i == 3) ? b0.w : (i == 4) ? b1.x : (i == 5) ? b1.y : (i == 6) ? b1.z : b1.w;
+      return u01(w);
+    };
+    ++st.pk;
+    // n_phot_envoyes(lambda) is incremented with the PREVIOUS packet's lambda in thermal mode
+    // (dust_transfer.f90:531 precedes :537); on the device packets are unordered, so the count is
+    // attributed to the packet's own emission wavelength (the sum over lambda is identical).
+    int lambda = r.lambda_in;
+    if (!r.lmono) lambda = select_wl_em<SM>(m, nextf());
+    atomicAdd(m.tally + m.lay.n_env + (lambda - 1), 1.0);
+    double x, y, z, u, v, w, S0;
+    CellT cell; null_cell(cell);
+    bool lintersect = true, flag_star, flag_ISM;
+    float rand = nextf();
+    if ((double)rand <= t_frac_star<SM>(m, lambda)) {
+      flag_star = true; flag_ISM = false;
+      const int i_star = select_star(m, lambda, nextf());
+      const float rand1 = nextf(), rand2 = nextf(), rand3 = nextf(), rand4 = nextf();
+      // emit_packet_uniform_sphere (stars.f90:108-169)
+      double zz = 2.0 * rand1 - 1.0;
+      double srw02 = sqrt(1.0 - zz * zz), sa, ca;
+      mcb_sincospi(2.0 * rand2 - 1.0, &sa, &ca);            // argmt = pi*(2 rand2 - 1)
+      double xx = srw02 * ca, yy = srw02 * sa;
+      double cospsi = (double)sqrtf(rand3), sp, cp;
+      mcb_sincospi(2.0 * (double)rand4, &sp, &cp);          // phi = 2 pi rand4
+      cdapres(cospsi, sp, cp, xx, yy, zz, u, v, w);
+      const double r_star = m.star[i_star - 1][3] * (1.0 + 1e-6);
+      x = xx * r_star + m.star[i_star - 1][0]; y = yy * r_star + m.star[i_star - 1][1]; z = zz * r_star + m.star[i_star - 1][2];
+      if (G::is_vor) cell_of_id(m, m.star_icell[i_star - 1], cell);
+      else cell = G::index(m, x, y, z);
+      if (m.star_out[i_star - 1]) lintersect = G::move_to_grid(m, x, y, z, u, v, w, cell);
+      S0 = m.E_paquet;
+    } else if ((double)rand <= t_frac_disk<SM>(m, lambda)) {
+      flag_star = false; flag_ISM = false;
+      const int ic = select_cellule(m, lambda, nextf());
+      cell_of_id(m, ic, cell);
+      const float rand1 = nextf(), rand2 = nextf(), rand3 = nextf();
+      G::pos_em_cell(m, cell, rand1, rand2, rand3, x, y, z);
+      const float rw = nextf(), rp = nextf();
+      random_isotropic_direction(rw, rp, u, v, w);
+      S0 = m.E_paquet;
+    } else {
+      flag_star = false; flag_ISM = true;
+      // emit_packet_ISM (stars.f90:728-787)
+      S0 = 1.0;
+      const float rand1 = nextf(), rand2 = nextf();
+      double zz = 2.0 * rand1 - 1.0;
+      double srw02 = sqrt(1.0 - zz * zz), sa, ca;
+      mcb_sincospi(2.0 * rand2 - 1.0, &sa, &ca);
+      double xx = srw02 * ca, yy = srw02 * sa;
+      const float rand3 = nextf(), rand4 = nextf();
+      double cospsi = (double)(-sqrtf(rand3)), sp, cp;
+      mcb_sincospi(2.0 * (double)rand4, &sp, &cp);
+      cdapres(cospsi, sp, cp, xx, yy, zz, u, v, w);
+      x = m.cISM[0] + xx * m.R_ISM; y = m.cISM[1] + yy * m.R_ISM; z = m.cISM[2] + zz * m.R_ISM;
+      lintersect = G::move_to_grid(m, x, y, z, u, v, w, cell);
+    }
+    if (lintersect) {
+      P.F(F_PX, slot) = x; P.F(F_PY, slot) = y; P.F(F_PZ, slot) = z;
+      P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;
+      P.F(F_S0, slot) = S0;
+      if (POLA) { P.F(F_S1, slot) = 0.0; P.F(F_S2, slot) = 0.0; P.F(F_S3, slot) = 0.0; }
+      uint32_t ca_, cb_; pack_cell(cell, ca_, cb_);
+      P.U(U_C0A, slot) = ca_; P.U(U_C0B, slot) = cb_;
+      P.U(U_PKLO, slot) = pk_lo; P.U(U_PKHI, slot) = pk_hi; P.U(U_EV, slot) = 1u;
+      uint32_t misc = pack_misc(lambda, flag_star, false, flag_ISM, 0, my_chunk);
+      start_flight(m, r, P, slot, x, y, z, u, v, w, pk_lo, pk_hi, 1u, misc);
+      P.U(U_MISC, slot) = misc;
+      nextq = Q_FLY;
+    } else {      // the packet never enters the model: straight to the detector (dust_transfer.f90:545-552)
+      if (!flag_ISM) {
+        const double S[4] = {S0, 0.0, 0.0, 0.0};
+        const int capt = capteur(lambda, u, v, w, S, flag_star, false);
+        if (!r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * my_chunk, 1ull);
+        ++st.esc;
+      }
+      nextq = Q_EMIT;
+    }
+  }
+  push_next(P, np, slot, nextq, lane);
+}
+
+// =============================================================================
+// FLY: up to FLY_STEPS iterations of the physical_length loop (optical_depth.f90:77-178)
+// =============================================================================
+template <class G, bool SM>
+__device__ __noinline__ void phase_fly(int slot, bool valid, int np, Stats& st) {
+  const DevModel& m = c_m; const DevRun& r = c_r;
+  const bool POLA = r.lsepar_pola != 0;
+  const Pool P = make_pool<SM>();
   using CellT = typename G::CellT;
   using Hit = typename G::Hit;
   const unsigned lane = threadIdx.x & 31;
-  const bool thermal = r.letape_th != 0;
-  const bool variable_dust = m.p_n_cells != 1;
-  if (SM) stage_tables(m, r.p_lambda_in);
-
-  // ---- per-lane packet state ----
-  int state = ST_FETCH;
-  Rng rng; rng.seed(0, 0, 0);
-  double x = 0, y = 0, z = 0, u = 0, v = 0, w = 1;       // interaction / emission point and direction
-  double S[4] = {0, 0, 0, 0};
-  int lambda = r.lambda_in;
-  CellT cell; null_cell(cell);
-  bool flag_star = false, flag_scatt = false, flag_ISM = false;
-  // flight state (physical_length locals)
-  double x0 = 0, y0 = 0, z0 = 0, xo = 0, yo = 0, zo = 0, extr = 0;
-  CellT c0, c_old; null_cell(c0); null_cell(c_old);
-  DirInv dinv; dinv.inv_a = 0; dinv.inv_w = 0;
-  int i_star_hit = 0;
-  Rt1Scratch rt1;
-  unsigned long long st_steps = 0, st_int = 0, st_sca = 0, st_abs = 0, st_kill = 0, st_esc = 0, st_bounce = 0, st_pk = 0;
-  int my_chunk = -1;      // SED-mode chunk bookkeeping
-
-  for (;;) {
-    const unsigned need = __ballot_sync(0xffffffffu, state == ST_FETCH);
-    if (need == 0 && __all_sync(0xffffffffu, state == ST_DONE)) break;
-
-    // ------------------------------------------------------------ FETCH + EMIT
-    if (state == ST_FETCH) {
-      // claim the next packet.  Thermal / fixed-count mode: one warp-aggregated atomic on a global
-      // counter.  SED mode (dust_transfer.f90:507-510,529,551): each chunk keeps sending until
-      // n_photons2 packets were RECEIVED in detector bin capt_sup (or n_phot_lim were sent).
-      int nnfot1 = 0;
-      unsigned long long idx_in_chunk = 0;
-      bool got = false;
-      const int first_local = r.nnfot1_start + ((r.rank - ((r.nnfot1_start - 1) % r.n_ranks) + r.n_ranks) % r.n_ranks);
-      if (r.count_sent) {
-        const unsigned leader = __ffs(need) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(m.work, (unsigned long long)__popc(need));
-        base = __shfl_sync(need, base, leader);
-        const unsigned long long g = base + __popc(need & ((1u << lane) - 1u));
-        if (g < r.n_packets_total) {
-          const unsigned long long lc = g / r.n_per_chunk;
-          idx_in_chunk = g % r.n_per_chunk;
-          nnfot1 = first_local + (int)lc * r.n_ranks;
-          my_chunk = (int)lc;
-          got = true;
-        }
-      } else {
-        const int start = (int)((blockIdx.x * blockDim.x + threadIdx.x + st_pk) % (unsigned long long)r.n_local_chunks);
-        for (int tries = 0; tries < r.n_local_chunks && !got; ++tries) {
-          int lc = start + tries; if (lc >= r.n_local_chunks) lc -= r.n_local_chunks;
-          if (__ldcg(m.work + 3 + 2 * lc) >= (unsigned long long)r.n_photons2) continue;
-          const unsigned long long sidx = atomicAdd(m.work + 2 + 2 * lc, 1ull);
-          if (sidx >= r.sent_lim) { atomicAdd(m.work + 2 + 2 * lc, ~0ull); continue; }     // undo (adds -1)
-          idx_in_chunk = sidx; nnfot1 = first_local + lc * r.n_ranks; my_chunk = lc; got = true;
-        }
-      }
-      if (!got) state = ST_DONE;
-      else {
-        rng.seed(r.seed, r.call_index, ((unsigned long long)(nnfot1 - 1) << 40) + idx_in_chunk);
-        ++st_pk;
-        // n_phot_envoyes(lambda) is incremented with the PREVIOUS packet's lambda in thermal mode
-        // (dust_transfer.f90:531 precedes :537); on the device packets are unordered, so the count is
-        // attributed to the packet's own emission wavelength (the sum over lambda is identical).
-        if (!r.lmono) lambda = select_wl_em<SM>(m, rng.nextf());
-        atomicAdd(m.tally + m.lay.n_env + (lambda - 1), 1.0);
-        // ---- emit_packet ----
-        bool lintersect = true;
-        flag_scatt = false;
-        float rand = rng.nextf();
-        if ((double)rand <= t_frac_star<SM>(m, lambda)) {
-          flag_star = true; flag_ISM = false;
-          const int i_star = select_star(m, lambda, rng.nextf());
-          const float rand1 = rng.nextf(), rand2 = rng.nextf(), rand3 = rng.nextf(), rand4 = rng.nextf();
-          // emit_packet_uniform_sphere
-          double zz = 2.0 * rand1 - 1.0;
-          double srw02 = sqrt(1.0 - zz * zz), sa, ca;
-          sincospi(2.0 * rand2 - 1.0, &sa, &ca);            // argmt = pi*(2 rand2 - 1)
-          double xx = srw02 * ca, yy = srw02 * sa;
-          double cospsi = (double)sqrtf(rand3), sp, cp;
-          sincospi(2.0 * (double)rand4, &sp, &cp);          // phi = 2 pi rand4
-          cdapres(cospsi, sp, cp, xx, yy, zz, u, v, w);
-          const double r_star = m.star[i_star - 1][3] * (1.0 + 1e-6);
-          x = xx * r_star + m.star[i_star - 1][0]; y = yy * r_star + m.star[i_star - 1][1]; z = zz * r_star + m.star[i_star - 1][2];
-          if (G::is_vor) cell_of_id(m, m.star_icell[i_star - 1], cell);
-          else cell = G::index(m, x, y, z);
-          if (m.star_out[i_star - 1]) lintersect = G::move_to_grid(m, x, y, z, u, v, w, cell);
-          S[0] = m.E_paquet; S[1] = S[2] = S[3] = 0.0;
-        } else if ((double)rand <= t_frac_disk<SM>(m, lambda)) {
-          flag_star = false; flag_ISM = false;
-          const int ic = select_cellule(m, lambda, rng.nextf());
-          cell_of_id(m, ic, cell);
-          const float rand1 = rng.nextf(), rand2 = rng.nextf(), rand3 = rng.nextf();
-          G::pos_em_cell(m, cell, rand1, rand2, rand3, x, y, z);
-          random_isotropic_direction(rng, u, v, w);
-          S[0] = m.E_paquet; S[1] = S[2] = S[3] = 0.0;
-        } else {
-          flag_star = false; flag_ISM = true;
-          // emit_packet_ISM
-          S[0] = 1.0; S[1] = S[2] = S[3] = 0.0;
-          const float rand1 = rng.nextf(), rand2 = rng.nextf();
-          double zz = 2.0 * rand1 - 1.0;
-          double srw02 = sqrt(1.0 - zz * zz), sa, ca;
-          sincospi(2.0 * rand2 - 1.0, &sa, &ca);
-          double xx = srw02 * ca, yy = srw02 * sa;
-          const float rand3 = rng.nextf(), rand4 = rng.nextf();
-          double cospsi = (double)(-sqrtf(rand3)), sp, cp;
-          sincospi(2.0 * (double)rand4, &sp, &cp);
-          cdapres(cospsi, sp, cp, xx, yy, zz, u, v, w);
-          x = m.cISM[0] + xx * m.R_ISM; y = m.cISM[1] + yy * m.R_ISM; z = m.cISM[2] + zz * m.R_ISM;
-          lintersect = G::move_to_grid(m, x, y, z, u, v, w, cell);
-        }
-        if (lintersect) state = ST_TAU;
-        else {      // packet never enters the model: goes straight to the detector (dust_transfer.f90:545-552)
-          if (!flag_ISM) {
-            const int capt = capteur(m, r, lambda, u, v, w, S, flag_star, false);
-            if (!r.count_sent && capt == r.capt_sup && my_chunk >= 0) atomicAdd(m.work + 3 + 2 * my_chunk, 1ull);
-            ++st_esc;
-          }
-        }
-      }
-    }
-
-    // ------------------------------------------------------------ TAU: start a flight
-    if (state == ST_TAU) {
-      const float rand = rng.nextf();
-      float tau;
-      if (rand == 1.0f) tau = 1.0e30f;
-      else if (rand > 1.0e-6f) tau = -logf(1.0f - rand);       // `real` arithmetic in the reference (dust_transfer.f90:1212)
-      else tau = rand;
-      extr = (double)tau;
-      x0 = x; y0 = y; z0 = z; xo = x; yo = y; zo = z;
-      c0 = cell; null_cell(c_old);
-      dinv = dir_invariants(u, v, w);
-      if (!thermal && r.rt1) angles_scatt_rt1(r, u, v, w, rt1);
-      i_star_hit = intersect_stars(m, x0, y0, z0, u, v, w);
-      state = ST_FLY;
-    }
-
-    // ------------------------------------------------------------ FLY: cell crossings
-    if (state == ST_FLY) {
+  int nextq = Q_NONE;
+  if (valid) {
+    const bool thermal = r.letape_th != 0;
+    const bool variable_dust = m.p_n_cells != 1;
+    double x0 = P.F(F_PX, slot), y0 = P.F(F_PY, slot), z0 = P.F(F_PZ, slot);
+    double u = P.F(F_U, slot), v = P.F(F_V, slot), w = P.F(F_W, slot);
+    double extr = P.F(F_EXTR, slot);
+    const double S0 = P.F(F_S0, slot);
+    const uint32_t misc = P.U(U_MISC, slot);
+    const int lambda = misc_lambda(misc), i_star_hit = misc_istar(misc);
+    CellT c0, c_old;
+    unpack_cell(P.U(U_C0A, slot), P.U(U_C0B, slot), c0);
+    unpack_cell(P.U(U_COA, slot), P.U(U_COB, slot), c_old);
+    double xo = P.F(F_OX, slot), yo = P.F(F_OY, slot), zo = P.F(F_OZ, slot);
+    const DirInv dinv = dir_invariants(u, v, w);
+    Rt1Scratch rt1;
+    const bool rt1_on = (!thermal) && r.rt1;
+    if (rt1_on) angles_scatt_rt1(u, v, w, rt1);       // recomputed per visit (same values as once per flight)
+    nextq = Q_FLY;
+    bool interact = false;
 #pragma unroll 1
-      for (int it = 0; it < 4 && state == ST_FLY; ++it) {
-        if (G::test_exit(m, c0, x0, y0, z0)) {
-          // the packet leaves the model: detector
-          if (!flag_ISM) {
-            const int capt = capteur(m, r, lambda, u, v, w, S, flag_star, flag_scatt);
-            if (!r.count_sent && capt == r.capt_sup && my_chunk >= 0) atomicAdd(m.work + 3 + 2 * my_chunk, 1ull);
-          }
-          ++st_esc;
-          state = ST_FETCH;
+    for (int it = 0; it < FLY_STEPS; ++it) {
+      if (G::test_exit(m, c0, x0, y0, z0)) {
+        if (!misc_ism(misc)) {       // the packet leaves the model: detector (capteur, output.f90:294)
+          double S[4] = {S0, 0.0, 0.0, 0.0};
+          if (POLA) { S[1] = P.F(F_S1, slot); S[2] = P.F(F_S2, slot); S[3] = P.F(F_S3, slot); }
+          const int capt = capteur(lambda, u, v, w, S, misc_star(misc), misc_scatt(misc));
+          if (!r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * misc_chunk(misc), 1ull);
+        }
+        ++st.esc;
+        nextq = Q_EMIT;
+        break;
+      }
+      if (i_star_hit > 0) {
+        CellT cs; cell_of_id(m, m.star_icell[i_star_hit - 1], cs);
+        if (same_cell(c0, cs)) { ++st.kill; nextq = Q_EMIT; break; }     // packet absorbed by the star
+      }
+      const int idx = tally_index(m, c0);
+      double opacity = 0.0;
+      int p_icell = 1;
+      if (idx >= 0) {
+        p_icell = variable_dust ? idx + 1 : 1;
+        opacity = t_kappa<SM>(m, p_icell, lambda) * __ldg(m.kappa_factor + idx);
+        if (__ldg(m.dark + idx)) {
+          // dark-zone bounce (optical_depth.f90:104-112): back to the previous cell's entry point, reversed
+          u = -u; v = -v; w = -w;
+          c0 = c_old; x0 = xo; y0 = yo; z0 = zo;
+          ++st.bounce;
+          interact = true;
           break;
         }
-        if (i_star_hit > 0) {
-          CellT cs; cell_of_id(m, m.star_icell[i_star_hit - 1], cs);
-          if (same_cell(c0, cs)) { ++st_kill; state = ST_FETCH; break; }     // packet absorbed by the star
-        }
-        const int idx = tally_index(m, c0);
-        double opacity = 0.0;
-        int p_icell = 1;
-        if (idx >= 0) {
-          p_icell = variable_dust ? idx + 1 : 1;
-          opacity = t_kappa<SM>(m, p_icell, lambda) * __ldg(m.kappa_factor + idx);
-          if (__ldg(m.dark + idx)) {
-            // dark-zone bounce (optical_depth.f90:104-112): back to the previous cell's entry point, reversed
-            u = -u; v = -v; w = -w;
-            cell = c_old; x = xo; y = yo; z = zo;
-            ++st_bounce;
-            state = ST_INTERACT;
-            break;
-          }
-        }
-        const Hit h = G::distance(m, dinv, x0, y0, z0, u, v, w, c0, c_old);
-        ++st_steps;
-        double l_contrib = hit_l_contrib(h), l = h.l;
-        const double tau_c = l_contrib * opacity;
-        bool lstop = false;
-        if (tau_c > extr) {
-          lstop = true;
-          l_contrib = l_contrib * (extr / tau_c);
-          l = hit_l_void(h) + l_contrib;
-        } else extr = extr - tau_c;
-        if (idx >= 0) {
-          // save_radiation_field
-          if (thermal) {
-            atomicAdd(m.tally + m.lay.xKJ + idx, t_kappa_abs<SM>(m, p_icell, lambda) * l_contrib * S[0]);
-            if (r.lxJ) atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S[0]);
-          } else {
-            if (r.lxJ) atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S[0]);
-            if (r.rt1) {
-              double x1, y1, z1;
-              G::exit_point(h, x0, y0, z0, u, v, w, x1, y1, z1);
-              deposit_rt1(m, r, idx, p_icell, r.p_lambda_in, l_contrib, S, flag_star,
-                          0.5 * (x0 + x1), 0.5 * (y0 + y1), 0.5 * (z0 + z1), rt1);
-            }
-          }
-        }
-        if (lstop) {
-          x = x0 + l * u; y = y0 + l * v; z = z0 + l * w;
-          cell = c0;
-          if (!G::is_vor && m.l3D && m.kind == 1) cell = G::index(m, x, y, z);     // optical_depth.f90:162-165
-          state = ST_INTERACT;
+      }
+      const Hit h = G::distance(m, dinv, x0, y0, z0, u, v, w, c0, c_old);
+      ++st.steps;
+      double l_contrib = hit_l_contrib(h), l = h.l;
+      const double tau_c = l_contrib * opacity;
+      bool lstop = false;
+      if (tau_c > extr) {
+        lstop = true;
+        l_contrib = l_contrib * (extr / tau_c);
+        l = hit_l_void(h) + l_contrib;
+      } else extr = extr - tau_c;
+      if (idx >= 0) {
+        // save_radiation_field (radiation_field.f90:31-135)
+        if (thermal) {
+          atomicAdd(m.tally + m.lay.xKJ + idx, t_kappa_abs<SM>(m, p_icell, lambda) * l_contrib * S0);
+          if (r.lxJ) atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S0);
         } else {
-          double x1, y1, z1;
-          CellT c1;
-          G::advance(m, h, x0, y0, z0, u, v, w, c0, x1, y1, z1, c1);
-          xo = x0; yo = y0; zo = z0; c_old = c0;
-          x0 = x1; y0 = y1; z0 = z1; c0 = c1;
+          if (r.lxJ) atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S0);
+          if (rt1_on) {
+            double x1, y1, z1;
+            G::exit_point(h, x0, y0, z0, u, v, w, x1, y1, z1);
+            double S[4] = {S0, 0.0, 0.0, 0.0};
+            if (POLA) { S[1] = P.F(F_S1, slot); S[2] = P.F(F_S2, slot); S[3] = P.F(F_S3, slot); }
+            deposit_rt1(idx, p_icell, r.p_lambda_in, l_contrib, S, misc_star(misc),
+                        0.5 * (x0 + x1), 0.5 * (y0 + y1), 0.5 * (z0 + z1), rt1);
+          }
         }
       }
+      if (lstop) {
+        x0 = x0 + l * u; y0 = y0 + l * v; z0 = z0 + l * w;                               // interaction point
+        if (!G::is_vor && m.l3D && m.kind == 1) c0 = G::index(m, x0, y0, z0);            // optical_depth.f90:162-165
+        interact = true;
+        break;
+      }
+      double x1, y1, z1;
+      CellT c1;
+      G::advance(m, h, x0, y0, z0, u, v, w, c0, x1, y1, z1, c1);
+      xo = x0; yo = y0; zo = z0; c_old = c0;
+      x0 = x1; y0 = y1; z0 = z1; c0 = c1;
     }
-
-    // ------------------------------------------------------------ INTERACT
-    if (state == ST_INTERACT) {
-      ++st_int;
-      const int idx = tally_index(m, cell);
-      const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
-      const float albedo = t_albedo<SM>(m, p_icell, lambda);
-      float rand;
-      bool dead = false;
-      if (r.lmono) {      // forced scattering (dust_transfer.f90:1263-1278)
-        if (idx >= 0 && __ldg(m.dark + idx)) dead = true;
-        else {
-          S[0] *= albedo; S[1] *= albedo; S[2] *= albedo; S[3] *= albedo;
-          if (S[0] < (double)(FLT_MIN * 1.0e6f)) dead = true;
-        }
-        rand = -1.0f;
-      } else rand = rng.nextf();
-      if (dead) { ++st_kill; state = ST_FETCH; }
-      else if (rand < albedo) {
-        // ---- scattering, method 2 (dust_transfer.f90:1318-1348)
-        ++st_sca;
-        flag_scatt = true;
-        rand = rng.nextf();
-        const float rand2 = rng.nextf();
-        int itheta; double cospsi;
-        if (r.lmethod_aniso1) angle_diff_theta_pos<SM>(m, r.p_lambda_in, p_icell, rand, rand2, itheta, cospsi);
-        else hg(t_gfac<SM>(m, p_icell, lambda), rand, itheta, cospsi);
-        if (r.lisotropic) { itheta = 1; cospsi = (double)__fsub_rn(__fmul_rn(2.0f, rand), 1.0f); }
-        rand = rng.nextf();
-        double sp, cp;
-        sincospi((double)__fsub_rn(__fmul_rn(2.0f, rand), 1.0f), &sp, &cp);     // PHI = PI*(2.0*rand-1.0): fp32 inner
-        double u1, v1, w1;
-        cdapres(cospsi, sp, cp, u, v, w, u1, v1, w1);
-        if (r.lmethod_aniso1 && r.lsepar_pola) scatter_stokes(m, lambda, itheta, rand2, p_icell, S, u, v, w, u1, v1, w1);
-        u = u1; v = v1; w = w1;
-        state = ST_TAU;
-      } else {
-        // ---- absorption + immediate re-emission (LTE) (dust_transfer.f90:1353-1402)
-        ++st_abs;
-        flag_star = false; flag_scatt = false; flag_ISM = false;
-        (void)rng.nextf();                       // rand1 is drawn but unused in the high-memory LTE branch
-        const float rand2 = rng.nextf();
-        lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, rand2);
-        random_isotropic_direction(rng, u, v, w);
-        S[1] = 0.0; S[2] = 0.0; S[3] = 0.0;
-        state = ST_TAU;
+    if (interact) {
+      // the flight ended with an interaction at (x0,y0,z0) in cell c0 (dust_transfer.f90:1260-1284)
+      ++st.inter;
+      if (r.lmono) nextq = Q_SCAT;       // forced scattering; the dark-zone / energy tests are done in the SCATTER phase
+      else {
+        const int idx = tally_index(m, c0);
+        const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
+        nextq = (__uint_as_float(P.U(U_RALB, slot)) < t_albedo<SM>(m, p_icell, lambda)) ? Q_SCAT : Q_ABS;
+      }
+      P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;       // (reversed on a bounce)
+    }
+    if (nextq != Q_EMIT) {
+      P.F(F_PX, slot) = x0; P.F(F_PY, slot) = y0; P.F(F_PZ, slot) = z0;
+      uint32_t ca_, cb_; pack_cell(c0, ca_, cb_);
+      P.U(U_C0A, slot) = ca_; P.U(U_C0B, slot) = cb_;
+      if (nextq == Q_FLY) {
+        P.F(F_OX, slot) = xo; P.F(F_OY, slot) = yo; P.F(F_OZ, slot) = zo;
+        pack_cell(c_old, ca_, cb_);
+        P.U(U_COA, slot) = ca_; P.U(U_COB, slot) = cb_;
+        P.F(F_EXTR, slot) = extr;
       }
     }
   }
+  push_next(P, np, slot, nextq, lane);
+}
+
+// =============================================================================
+// SCATTER: method 2 (dust_transfer.f90:1318-1351) + start of the next flight
+// =============================================================================
+template <class G, bool SM>
+__device__ __noinline__ void phase_scatter(int slot, bool valid, int np, Stats& st) {
+  const DevModel& m = c_m; const DevRun& r = c_r;
+  const bool POLA = r.lsepar_pola != 0;
+  const Pool P = make_pool<SM>();
+  using CellT = typename G::CellT;
+  const unsigned lane = threadIdx.x & 31;
+  int nextq = Q_NONE;
+  if (valid) {
+    const bool variable_dust = m.p_n_cells != 1;
+    uint32_t misc = P.U(U_MISC, slot);
+    const int lambda = misc_lambda(misc);
+    CellT cell; unpack_cell(P.U(U_C0A, slot), P.U(U_C0B, slot), cell);
+    const int idx = tally_index(m, cell);
+    const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
+    bool dead = false;
+    double S[4] = {P.F(F_S0, slot), 0.0, 0.0, 0.0};
+    if (POLA) { S[1] = P.F(F_S1, slot); S[2] = P.F(F_S2, slot); S[3] = P.F(F_S3, slot); }
+    if (r.lmono) {      // forced scattering (dust_transfer.f90:1263-1278)
+      if (idx >= 0 && __ldg(m.dark + idx)) dead = true;
+      else {
+        const float albedo = t_albedo<SM>(m, p_icell, lambda);
+        S[0] *= albedo; S[1] *= albedo; S[2] *= albedo; S[3] *= albedo;
+        if (S[0] < (double)(FLT_MIN * 1.0e6f)) dead = true;
+      }
+    }
+    if (dead) { ++st.kill; nextq = Q_EMIT; }
+    else {
+      ++st.sca;
+      const uint32_t pk_lo = P.U(U_PKLO, slot), pk_hi = P.U(U_PKHI, slot), ev = P.U(U_EV, slot);
+      const uint4 b = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev + 1u, pk_lo, pk_hi, r.call_index);
+      const float rand = u01(b.x), rand2 = u01(b.y), rand3 = u01(b.z);
+      const double u = P.F(F_U, slot), v = P.F(F_V, slot), w = P.F(F_W, slot);
+      int itheta; double cospsi;
+      if (r.lmethod_aniso1) angle_diff_theta_pos<SM>(m, r.p_lambda_in, p_icell, rand, rand2, itheta, cospsi);
+      else hg(t_gfac<SM>(m, p_icell, lambda), rand, itheta, cospsi);
+      if (r.lisotropic) { itheta = 1; cospsi = (double)__fsub_rn(__fmul_rn(2.0f, rand), 1.0f); }
+      double sp, cp;
+      mcb_sincospi((double)__fsub_rn(__fmul_rn(2.0f, rand3), 1.0f), &sp, &cp);     // PHI = PI*(2.0*rand-1.0): fp32 inner
+      double u1, v1, w1;
+      cdapres(cospsi, sp, cp, u, v, w, u1, v1, w1);
+      if (POLA && r.lmethod_aniso1) scatter_stokes(lambda, itheta, rand2, p_icell, S, u, v, w, u1, v1, w1);
+      P.F(F_U, slot) = u1; P.F(F_V, slot) = v1; P.F(F_W, slot) = w1;
+      if (r.lmono || POLA) { P.F(F_S0, slot) = S[0]; if (POLA) { P.F(F_S1, slot) = S[1]; P.F(F_S2, slot) = S[2]; P.F(F_S3, slot) = S[3]; } }
+      misc |= (1u << 11);                                    // flag_scatt
+      P.U(U_EV, slot) = ev + 1u;
+      start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u1, v1, w1, pk_lo, pk_hi, ev + 1u, misc);
+      P.U(U_MISC, slot) = misc;
+      nextq = Q_FLY;
+    }
+  }
+  push_next(P, np, slot, nextq, lane);
+}
+
+// =============================================================================
+// ABSORB: immediate re-emission, LTE (dust_transfer.f90:1353-1402) + start of the next flight
+// =============================================================================
+template <class G, bool SM>
+__device__ __noinline__ void phase_absorb(int slot, bool valid, int np, Stats& st) {
+  const DevModel& m = c_m; const DevRun& r = c_r;
+  const bool POLA = r.lsepar_pola != 0;
+  const Pool P = make_pool<SM>();
+  using CellT = typename G::CellT;
+  const unsigned lane = threadIdx.x & 31;
+  int nextq = Q_NONE;
+  if (valid) {
+    const bool variable_dust = m.p_n_cells != 1;
+    uint32_t misc = P.U(U_MISC, slot);
+    CellT cell; unpack_cell(P.U(U_C0A, slot), P.U(U_C0B, slot), cell);
+    const int idx = tally_index(m, cell);
+    const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
+    ++st.abs_;
+    const uint32_t pk_lo = P.U(U_PKLO, slot), pk_hi = P.U(U_PKHI, slot), ev = P.U(U_EV, slot);
+    const uint4 b = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev + 1u, pk_lo, pk_hi, r.call_index);
+    // b.x is rand1: drawn but unused in the high-memory LTE branch (thermal_emission.f90:739-765)
+    const int lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, u01(b.y));
+    double u, v, w;
+    random_isotropic_direction(u01(b.z), u01(b.w), u, v, w);
+    P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;
+    if (POLA) { P.F(F_S1, slot) = 0.0; P.F(F_S2, slot) = 0.0; P.F(F_S3, slot) = 0.0; }
+    misc = pack_misc(lambda, false, false, false, 0, misc_chunk(misc));      // flag_star = flag_scatt = flag_ISM = .false.
+    P.U(U_EV, slot) = ev + 1u;
+    start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u, v, w, pk_lo, pk_hi, ev + 1u, misc);
+    P.U(U_MISC, slot) = misc;
+    nextq = Q_FLY;
+  }
+  push_next(P, np, slot, nextq, lane);
+}
+
+// =============================================================================
+// The persistent photon-loop kernel: rounds of (claim a single-phase chunk -> run the phase -> regroup)
+// =============================================================================
+template <class G, bool SM>
+__global__ void __launch_bounds__(MC_BLOCK, 1)
+mc_photon_loop_kernel() {
+  const DevModel& m = c_m; const DevRun& r = c_r;
+  const unsigned lane = threadIdx.x & 31;
+  if (SM) stage_tables(m, r.p_lambda_in);
+  const Pool P = make_pool<SM>();
+  // every slot starts in the EMIT queue
+  for (int s = threadIdx.x; s < NP; s += MC_BLOCK) P.Q(0, Q_EMIT)[s] = (unsigned short)s;
+  if (threadIdx.x < 16) P.ctl[threadIdx.x] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) P.QN(0, Q_EMIT) = NP;
+  Stats st = {0, 0, 0, 0, 0, 0, 0, 0};
+  int par = 0;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      for (int qi = 0; qi < NQ; ++qi) { P.ctl[8 + qi] = acc; acc += (P.QN(par, qi) + 31) >> 5; P.QN(par ^ 1, qi) = 0; }
+      P.ctl[8 + NQ] = acc;      // total chunks of this round
+      P.ctl[13] = 0;            // next chunk to claim
+    }
+    __syncthreads();
+    const int total = P.ctl[8 + NQ];
+    if (total == 0) break;
+    for (;;) {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(&P.ctl[13], 1);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if (c >= total) break;
+      int qi = 0;
+      while (qi < NQ - 1 && c >= P.ctl[8 + qi + 1]) ++qi;
+      const int off = ((c - P.ctl[8 + qi]) << 5) + (int)lane;
+      const bool valid = off < P.QN(par, qi);
+      const int slot = valid ? (int)P.Q(par, qi)[off] : 0;
+      switch (qi) {
+        case Q_EMIT: phase_emit<G, SM>(slot, valid, par ^ 1, st); break;
+        case Q_ABS:  phase_absorb<G, SM>(slot, valid, par ^ 1, st); break;
+        case Q_SCAT: phase_scatter<G, SM>(slot, valid, par ^ 1, st); break;
+        default:     phase_fly<G, SM>(slot, valid, par ^ 1, st); break;
+      }
+    }
+    par ^= 1;
+  }
 
   // ---- diagnostics (not part of the reference) ----
-  double* st = m.tally + m.lay.stats;
+  double* stt = m.tally + m.lay.stats;
   auto flush = [&](int k, unsigned long long vv) {
     for (int o = 16; o > 0; o >>= 1) vv += __shfl_down_sync(0xffffffffu, vv, o);
-    if (lane == 0 && vv) atomicAdd(st + k, (double)vv);
+    if (lane == 0 && vv) atomicAdd(stt + k, (double)vv);
   };
-  flush(STAT_PACKETS, st_pk); flush(STAT_STEPS, st_steps); flush(STAT_INTERACT, st_int); flush(STAT_SCATT, st_sca);
-  flush(STAT_ABS, st_abs); flush(STAT_KILLED, st_kill); flush(STAT_ESCAPED, st_esc); flush(STAT_BOUNCE, st_bounce);
+  flush(STAT_PACKETS, st.pk); flush(STAT_STEPS, st.steps); flush(STAT_INTERACT, st.inter); flush(STAT_SCATT, st.sca);
+  flush(STAT_ABS, st.abs_); flush(STAT_KILLED, st.kill); flush(STAT_ESCAPED, st.esc); flush(STAT_BOUNCE, st.bounce);
 }
 
 }  // namespace mcb

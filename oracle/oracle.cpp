@@ -104,6 +104,8 @@ struct Oracle {
   std::vector<ThreadTallies> T;
   int N_type_flux = 1, n_Stokes = 1;
   double* ev_out = nullptr;      // optional per-packet event counts (instrumentation)
+  uint8_t* ev_log = nullptr; int64_t ev_log_cap = 0, ev_log_n = 0;   // optional event trace (single thread): 1 step, 2 scatter, 3 absorb, 0 packet end
+  inline void logev(uint8_t c) { if (ev_log && ev_log_n < ev_log_cap) ev_log[ev_log_n++] = c; }
 
   bool lvariable_dust() const { return o.p_n_cells != 1; }
   bool lVoronoi() const { return g.kind == MCB_GRID_VORONOI; }
@@ -1128,7 +1130,7 @@ struct Oracle {
         }
       } else { lcell_not_empty = false; opacity = 0.0; }
       cross_cell(x0, y0, z0, u, v, w, icell0, previous_cell, x1, y1, z1, next_cell, l, l_contrib, l_void_before);
-      t.stats[1] += 1;
+      t.stats[1] += 1; logev(1);
       tau = l_contrib * opacity;
       if (tau > extr) {
         lstop = true;
@@ -1302,7 +1304,10 @@ struct Oracle {
     bool flag_direct_star, flag_sortie = false;
     p.flag_scatt = false;
     flag_direct_star = p.flag_star;
+    uint32_t n_flight = 0;
     for (;;) {
+      ++n_flight;
+      rng_set_block(&rng, 2 * n_flight);          // flight block: tau, interaction-type draw (see philox.h)
       rand = (float)rng_next(&rng);
       if (rand == 1.0f) tau = 1.0e30f;
       else if (rand > 1.0e-6f) tau = -std::log(1.0f - rand);
@@ -1320,8 +1325,9 @@ struct Oracle {
         rand = -1.0f;
       } else rand = (float)rng_next(&rng);
 
+      rng_set_block(&rng, 2 * n_flight + 1);      // interaction block
       if (rand < tab_albedo_pos(p_icell, lambda)) {
-        t.stats[3] += 1;
+        t.stats[3] += 1; logev(2);
         p.flag_scatt = true; flag_direct_star = false;
         // method 2  :1318-1348
         rand = (float)rng_next(&rng);
@@ -1345,7 +1351,7 @@ struct Oracle {
         }
         p.u = u1; p.v = v1; p.w = w1;
       } else {
-        t.stats[4] += 1;
+        t.stats[4] += 1; logev(3);
         p.flag_star = false; p.flag_scatt = false; flag_direct_star = false; p.flag_ISM = false;
         rand = (float)rng_next(&rng); rand2 = (float)rng_next(&rng);     // lonly_LTE :1373-1375
         im_reemission_LTE(t, p.icell, p_icell, rand, rand2, lambda);
@@ -1462,6 +1468,7 @@ struct Oracle {
             if (capt == r.capt_sup) n_phot_sed2 += 1.0;
             t.stats[6] += 1;
           } else if (!p.alive) t.stats[5] += 1;
+          logev(0);
           if (ev_out && count_sent) ev_out[(size_t)(nnfot1 - 1) * n_photons2_local + (size_t)(nnfot2 - 1.0)] = t.stats[1] + t.stats[2] - ev0;
         }
       }
@@ -1602,6 +1609,8 @@ void oracle_rng_stream(uint64_t seed, uint32_t call_index, uint64_t packet, int 
 }
 // instrumentation: per-packet (cell steps + interactions), thermal mode, length n_photons_loop*n_photons2
 void oracle_set_event_buffer(void* h, double* buf) { ((Oracle*)h)->ev_out = buf; }
+int64_t oracle_set_event_log(void* h, uint8_t* buf, int64_t cap) { Oracle* O = (Oracle*)h; int64_t n = O->ev_log_n; O->ev_log = buf; O->ev_log_cap = cap; O->ev_log_n = 0; return n; }
+int64_t oracle_event_log_size(void* h) { return ((Oracle*)h)->ev_log_n; }
 int oracle_max_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

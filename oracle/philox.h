@@ -15,6 +15,12 @@
  *   packet  = (chunk-1) * 2^40 + index_in_chunk (0-based)
  *   each 128-bit block yields four uniform draws, consumed in order w0..w3:
  *       rand = (w >> 8) * 2^-24          (exactly representable in fp32, in [0,1))
+ *   Blocks are assigned per EVENT so that a packet's RNG state is just (packet,
+ *   event counter) -- what the GPU keeps per packet in shared memory:
+ *       emission (wavelength, source, position, direction)   blocks 0, 1
+ *       flight e = 1, 2, ...   (tau, interaction-type draw)    block  2e
+ *       interaction ending flight e (angles / re-emission)    block  2e + 1
+ *   Unused words of a block are discarded.
  *   Every sprng() call site on this path assigns the result to a Fortran `real`
  *   (fp32), so one 24-bit draw per call carries all the bits the reference keeps
  *   near 1; the one difference is that rand can never round up to exactly 1.0
@@ -57,6 +63,12 @@ static inline void rng_seed_packet(PacketRng *g, uint64_t seed, uint32_t call_in
   g->key[0] = (uint32_t)seed; g->key[1] = (uint32_t)(seed >> 32);
   g->ctr[0] = 0; g->ctr[1] = (uint32_t)packet; g->ctr[2] = (uint32_t)(packet >> 32); g->ctr[3] = call_index;
   g->n_buf = 0; g->n_draws = 0;
+}
+
+/* jump to the first word of a given block (start of an event) */
+static inline void rng_set_block(PacketRng *g, uint32_t block) {
+  if (g->rec) return;
+  g->ctr[0] = block; g->n_buf = 0;
 }
 
 /* the analogue of sprng(stream(id)): a value in [0,1) (24-bit resolution) */

@@ -10,6 +10,7 @@ P.l_dark_zone = S.define_dark_zone(P, P.lambda_seuil, 1500.0, G.dark_zone_walker
 S.repartition_energie(P); G.upload_dark_zone(P.l_dark_zone); G.upload_emission(P)
 G.mc_photon_loop(1, 1, 200)
 for n2 in ns:
+    P.n_photons_eq_th = n2; S.repartition_energie(P); G.upload_emission(P)      # L_packet_th = L_tot / n_packets
     for rep in range(2):
         t = G.mc_photon_loop(1, 1, n2, call_index=rep)
         ms = G.last_kernel_ms()
