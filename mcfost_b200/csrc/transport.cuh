@@ -365,18 +365,21 @@ __host__ __device__ constexpr int pool_nf64(bool pola) { return pola ? 14 : 11; 
 
 // bytes of shared memory after the staged tables
 __host__ __device__ constexpr size_t pool_bytes(bool pola) {
-  return (size_t)pool_nf64(pola) * NP * 8 + (size_t)NU32 * NP * 4 + (size_t)2 * NQ * NP * 2 + 64 * 4;
+  return (size_t)pool_nf64(pola) * NP * 8 + (size_t)NU32 * NP * 4 + (size_t)NQ * NP * 2 + 64 * 4;
 }
 
 struct Pool {
   double* f;            // [NF64][NP]
   uint32_t* u;          // [NU32][NP]
-  unsigned short* q;    // [2][NQ][NP]
-  int* ctl;             // [0..7] qn[parity][queue]; [8..12] chunk prefix; [13] next chunk; [14] total chunks
+  unsigned short* q;    // [NQ][NP] ring buffers of slot ids (0xFFFF = entry not written yet)
+  unsigned* ctl;        // [0..3] head[q]; [4..7] tail[q]; [8] live packets; [9] busy warps
   __device__ __forceinline__ double& F(int field, int slot) const { return f[field * NP + slot]; }
   __device__ __forceinline__ uint32_t& U(int field, int slot) const { return u[field * NP + slot]; }
-  __device__ __forceinline__ unsigned short* Q(int parity, int queue) const { return q + (parity * NQ + queue) * NP; }
-  __device__ __forceinline__ int& QN(int parity, int queue) const { return ctl[parity * NQ + queue]; }
+  __device__ __forceinline__ volatile unsigned short* Q(int queue) const { return q + queue * NP; }
+  __device__ __forceinline__ volatile unsigned& HEAD(int queue) const { return ctl[queue]; }
+  __device__ __forceinline__ volatile unsigned& TAIL(int queue) const { return ctl[NQ + queue]; }
+  __device__ __forceinline__ volatile unsigned& LIVE() const { return ctl[8]; }
+  __device__ __forceinline__ volatile unsigned& BUSY() const { return ctl[9]; }
 };
 
 // misc word: lambda (10 bits) | star 1 | scatt 1 | ISM 1 | i_star_hit 4 | chunk 15
@@ -404,24 +407,29 @@ template <bool SM> __device__ __forceinline__ Pool make_pool() {
   P.f = reinterpret_cast<double*>(base);
   P.u = reinterpret_cast<uint32_t*>(base + nf * NP * 8);
   P.q = reinterpret_cast<unsigned short*>(base + nf * NP * 8 + (size_t)NU32 * NP * 4);
-  P.ctl = reinterpret_cast<int*>(base + nf * NP * 8 + (size_t)NU32 * NP * 4 + (size_t)2 * NQ * NP * 2);
+  P.ctl = reinterpret_cast<unsigned*>(base + nf * NP * 8 + (size_t)NU32 * NP * 4 + (size_t)NQ * NP * 2);
   return P;
 }
 
 struct Stats { unsigned int pk, steps, inter, sca, abs_, kill, esc, bounce; };
 
-// push the packets of this warp to the queues of their next phase (one shared-memory atomic per queue)
-__device__ __forceinline__ void push_next(const Pool& P, int np, int slot, int nextq, unsigned lane) {
+// Regrouping step: push the packets of this warp to the ring queue of their next phase (one shared-
+// memory atomic per destination queue).  Packets that leave the pool (no more work) decrement LIVE.
+// The fence orders the packet-state stores before the queue entry becomes visible to a consumer.
+__device__ __forceinline__ void push_next(const Pool& P, int slot, int nextq, bool valid, unsigned lane) {
+  __threadfence_block();
 #pragma unroll
   for (int qi = 0; qi < NQ; ++qi) {
     const unsigned mask = __ballot_sync(0xffffffffu, nextq == qi);
     if (mask == 0) continue;
     const int leader = __ffs(mask) - 1;
-    int base = 0;
-    if ((int)lane == leader) base = atomicAdd(&P.QN(np, qi), __popc(mask));
+    unsigned base = 0;
+    if ((int)lane == leader) base = atomicAdd((unsigned*)&P.ctl[NQ + qi], (unsigned)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (nextq == qi) P.Q(np, qi)[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)slot;
+    if (nextq == qi) P.Q(qi)[(base + __popc(mask & ((1u << lane) - 1u))) & (NP - 1)] = (unsigned short)slot;
   }
+  const unsigned gone = __ballot_sync(0xffffffffu, valid && nextq == Q_NONE);
+  if (gone && lane == 0) atomicSub((unsigned*)&P.ctl[8], (unsigned)__popc(gone));
 }
 
 // ---- begin flight `ev`: tau and the interaction-type draw from block 2*ev (dust_transfer.f90:1208-1215,1280),
@@ -447,7 +455,7 @@ __device__ __forceinline__ void start_flight(const DevModel& m, const DevRun& r,
 // EMIT: claim a packet id, emit_packet (dust_transfer.f90:1047-1151), start the first flight
 // =============================================================================
 template <class G, bool SM>
-__device__ __noinline__ void phase_emit(int slot, bool valid, int np, Stats& st) {
+__device__ __noinline__ void phase_emit(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
   const Pool P = make_pool<SM>();
@@ -574,14 +582,14 @@ __device__ __noinline__ void phase_emit(int slot, bool valid, int np, Stats& st)
       nextq = Q_EMIT;
     }
   }
-  push_next(P, np, slot, nextq, lane);
+  push_next(P, slot, nextq, valid, lane);
 }
 
 // =============================================================================
 // FLY: up to FLY_STEPS iterations of the physical_length loop (optical_depth.f90:77-178)
 // =============================================================================
 template <class G, bool SM>
-__device__ __noinline__ void phase_fly(int slot, bool valid, int np, Stats& st) {
+__device__ __noinline__ void phase_fly(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
   const Pool P = make_pool<SM>();
@@ -702,14 +710,14 @@ __device__ __noinline__ void phase_fly(int slot, bool valid, int np, Stats& st) 
       }
     }
   }
-  push_next(P, np, slot, nextq, lane);
+  push_next(P, slot, nextq, valid, lane);
 }
 
 // =============================================================================
 // SCATTER: method 2 (dust_transfer.f90:1318-1351) + start of the next flight
 // =============================================================================
 template <class G, bool SM>
-__device__ __noinline__ void phase_scatter(int slot, bool valid, int np, Stats& st) {
+__device__ __noinline__ void phase_scatter(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
   const Pool P = make_pool<SM>();
@@ -759,14 +767,14 @@ __device__ __noinline__ void phase_scatter(int slot, bool valid, int np, Stats& 
       nextq = Q_FLY;
     }
   }
-  push_next(P, np, slot, nextq, lane);
+  push_next(P, slot, nextq, valid, lane);
 }
 
 // =============================================================================
 // ABSORB: immediate re-emission, LTE (dust_transfer.f90:1353-1402) + start of the next flight
 // =============================================================================
 template <class G, bool SM>
-__device__ __noinline__ void phase_absorb(int slot, bool valid, int np, Stats& st) {
+__device__ __noinline__ void phase_absorb(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
   const Pool P = make_pool<SM>();
@@ -794,7 +802,7 @@ __device__ __noinline__ void phase_absorb(int slot, bool valid, int np, Stats& s
     P.U(U_MISC, slot) = misc;
     nextq = Q_FLY;
   }
-  push_next(P, np, slot, nextq, lane);
+  push_next(P, slot, nextq, valid, lane);
 }
 
 // =============================================================================
@@ -808,41 +816,62 @@ mc_photon_loop_kernel() {
   if (SM) stage_tables(m, r.p_lambda_in);
   const Pool P = make_pool<SM>();
   // every slot starts in the EMIT queue
-  for (int s = threadIdx.x; s < NP; s += MC_BLOCK) P.Q(0, Q_EMIT)[s] = (unsigned short)s;
+  for (int i = threadIdx.x; i < NQ * NP; i += MC_BLOCK) P.q[i] = (i < NP) ? (unsigned short)i : (unsigned short)0xFFFFu;   // Q_EMIT == 0
   if (threadIdx.x < 16) P.ctl[threadIdx.x] = 0;
   __syncthreads();
-  if (threadIdx.x == 0) P.QN(0, Q_EMIT) = NP;
+  if (threadIdx.x == 0) { P.ctl[NQ + Q_EMIT] = NP; P.ctl[8] = NP; }
+  __syncthreads();
   Stats st = {0, 0, 0, 0, 0, 0, 0, 0};
-  int par = 0;
+  // ---- asynchronous scheduling: every warp repeatedly claims up to 32 entries of ONE queue (so all its
+  // lanes run the same phase), preferring full chunks; partial chunks are only taken when no other warp
+  // is busy (nothing more will arrive).  No block-wide barriers after this point.
   for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int acc = 0;
-      for (int qi = 0; qi < NQ; ++qi) { P.ctl[8 + qi] = acc; acc += (P.QN(par, qi) + 31) >> 5; P.QN(par ^ 1, qi) = 0; }
-      P.ctl[8 + NQ] = acc;      // total chunks of this round
-      P.ctl[13] = 0;            // next chunk to claim
-    }
-    __syncthreads();
-    const int total = P.ctl[8 + NQ];
-    if (total == 0) break;
-    for (;;) {
-      int c = 0;
-      if (lane == 0) c = atomicAdd(&P.ctl[13], 1);
-      c = __shfl_sync(0xffffffffu, c, 0);
-      if (c >= total) break;
-      int qi = 0;
-      while (qi < NQ - 1 && c >= P.ctl[8 + qi + 1]) ++qi;
-      const int off = ((c - P.ctl[8 + qi]) << 5) + (int)lane;
-      const bool valid = off < P.QN(par, qi);
-      const int slot = valid ? (int)P.Q(par, qi)[off] : 0;
-      switch (qi) {
-        case Q_EMIT: phase_emit<G, SM>(slot, valid, par ^ 1, st); break;
-        case Q_ABS:  phase_absorb<G, SM>(slot, valid, par ^ 1, st); break;
-        case Q_SCAT: phase_scatter<G, SM>(slot, valid, par ^ 1, st); break;
-        default:     phase_fly<G, SM>(slot, valid, par ^ 1, st); break;
+    int qi = -1; unsigned h = 0, n = 0;
+    if (lane == 0) {
+      for (;;) {
+        int best = -1; unsigned best_n = 0;
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+          const unsigned av = P.TAIL(k) - P.HEAD(k);
+          if (av >= 32u) { best = k; best_n = 32u; break; }
+          if (av > best_n) { best = k; best_n = av; }
+        }
+        if (best >= 0 && (best_n == 32u || P.BUSY() == 0u)) {
+          const unsigned hh = P.HEAD(best);
+          const unsigned av = P.TAIL(best) - hh;
+          const unsigned take = av < 32u ? av : 32u;
+          if (take > 0 && (take == 32u || P.BUSY() == 0u) && atomicCAS((unsigned*)&P.ctl[best], hh, hh + take) == hh) {
+            atomicAdd((unsigned*)&P.ctl[9], 1u);
+            qi = best; h = hh; n = take;
+            break;
+          }
+          continue;
+        }
+        if (P.LIVE() == 0u) break;       // every packet of this block is done
+        __nanosleep(64);
       }
     }
-    par ^= 1;
+    qi = __shfl_sync(0xffffffffu, qi, 0);
+    if (qi < 0) break;
+    h = __shfl_sync(0xffffffffu, h, 0);
+    n = __shfl_sync(0xffffffffu, n, 0);
+    const bool valid = lane < n;
+    int slot = 0;
+    if (valid) {
+      volatile unsigned short* e = P.Q(qi) + ((h + lane) & (NP - 1));
+      unsigned short sv;
+      while ((sv = *e) == 0xFFFFu) { }      // the producer reserved this entry and is about to write it
+      *e = 0xFFFFu;
+      slot = sv;
+    }
+    __threadfence_block();                   // acquire: packet state written before the entry
+    switch (qi) {
+      case Q_EMIT: phase_emit<G, SM>(slot, valid, st); break;
+      case Q_ABS:  phase_absorb<G, SM>(slot, valid, st); break;
+      case Q_SCAT: phase_scatter<G, SM>(slot, valid, st); break;
+      default:     phase_fly<G, SM>(slot, valid, st); break;
+    }
+    if (lane == 0) atomicSub((unsigned*)&P.ctl[9], 1u);
   }
 
   // ---- diagnostics (not part of the reference) ----
