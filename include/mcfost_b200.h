@@ -234,6 +234,10 @@ int mcfost_b200_tally_buffers(mcb_handle *h, void **d_f64, int64_t *n_f64,
 int mcfost_b200_download(mcb_handle *h, const mcb_run_params *r, mcb_tallies *out);
 /* device time of the last launch in ms (CUDA events on the handle's stream) */
 int mcfost_b200_last_kernel_ms(mcb_handle *h, float *ms);
+/* scheduling diagnostics of the last launch (not in the reference): out[10] =
+ * {ms until the packet counter ran dry, kernel ms, chunk visits[4], valid lanes[4]}
+ * for the phases EMIT, ABSORB, SCATTER, FLY */
+int mcfost_b200_debug_counters(mcb_handle *h, double *out);
 /* cudaStream_t of the handle, as an integer, so torch can wait on it */
 int mcfost_b200_stream(mcb_handle *h, uint64_t *stream);
 

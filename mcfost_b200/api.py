@@ -18,7 +18,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libmcfost_b200.so")
+LIB_PATH = os.environ.get("MCFOST_B200_LIB") or os.path.join(_HERE, "_lib", "libmcfost_b200.so")   # env override: kernel-tuning builds
 
 # every symbol include/mcfost_b200.h declares
 EXPORTS = (
@@ -26,6 +26,7 @@ EXPORTS = (
     "mcfost_b200_upload_grid", "mcfost_b200_upload_dark_zone", "mcfost_b200_upload_opacity",
     "mcfost_b200_upload_emission", "mcfost_b200_run", "mcfost_b200_launch", "mcfost_b200_sync",
     "mcfost_b200_tally_buffers", "mcfost_b200_download", "mcfost_b200_last_kernel_ms", "mcfost_b200_stream",
+    "mcfost_b200_debug_counters",
     "mcfost_b200_cross_cell", "mcfost_b200_index_cell", "mcfost_b200_move_to_grid",
     "mcfost_b200_optical_length_tot", "mcfost_b200_physical_length",
 )
@@ -172,6 +173,17 @@ class PhotonLoop:
         ms = C.c_float()
         self._check(self.lib.mcfost_b200_last_kernel_ms(self.h, C.byref(ms)))
         return float(ms.value)
+
+    def debug_counters(self):
+        """Scheduling diagnostics of the last launch (see include/mcfost_b200.h)."""
+        out = (C.c_double * 10)()
+        self.lib.mcfost_b200_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        self._check(self.lib.mcfost_b200_debug_counters(self.h, out))
+        v = list(out)
+        names = ("EMIT", "ABSORB", "SCATTER", "FLY")
+        return {"steady_ms": v[0], "kernel_ms": v[1],
+                "chunk_fill": {n: (v[6 + i] / v[2 + i] if v[2 + i] else 0.0) for i, n in enumerate(names)},
+                "visits": {n: v[2 + i] for i, n in enumerate(names)}}
 
     def stream(self):
         s = C.c_uint64()

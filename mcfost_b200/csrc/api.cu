@@ -48,6 +48,26 @@ void mcfost_b200_finalize(mcb_handle* h) {
   delete h;
 }
 
+// Scheduling diagnostics of the last launch (not part of the reference interface):
+// out[0] = ms from kernel start until the global packet counter ran dry (steady-state phase),
+// out[1] = ms of the whole kernel by the device clock, out[2..5] = chunk visits per phase
+// (EMIT, ABSORB, SCATTER, FLY), out[6..9] = valid lanes summed over those visits.
+int mcfost_b200_debug_counters(mcb_handle* h, double* out) {
+  if (!h || !out) return MCB_ERR_BAD_ARG;
+  if (!h->launched || !h->m.work) return fail(h, MCB_ERR_STATE, "no launch yet");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  const int n = 16 + 2 * h->n_photons_loop_alloc;
+  std::vector<unsigned long long> w((size_t)n);
+  CK(cudaMemcpy(w.data(), h->m.work, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  const int b = 2 + 2 * h->n_photons_loop_alloc;
+  const double t0 = (double)w[b], t1 = (double)w[b + 1];
+  out[0] = (w[1] == ~0ull || w[1] == 0ull) ? -1.0 : ((double)w[1] - t0) * 1e-6;
+  out[1] = (t1 - t0) * 1e-6;
+  for (int k = 0; k < 8; ++k) out[2 + k] = (double)w[b + 2 + k];
+  return MCB_OK;
+}
+
 int mcfost_b200_stream(mcb_handle* h, uint64_t* s) { if (!h || !s) return MCB_ERR_BAD_ARG; *s = (uint64_t)(uintptr_t)h->stream; return MCB_OK; }
 
 // ---------------------------------------------------------------------------
@@ -261,14 +281,15 @@ static int setup_tallies(mcb_handle* h, const mcb_run_params* r, bool lxJ, bool 
   const int64_t n_xI = rt1 ? (int64_t)N_AZ_RT * 2 * n_type_flux * n_rt * m.n_cells : 0;
   if (n_xI != h->n_xI) realloc_ = true;
   if ((rc = reserve(h, "xI", (size_t)n_xI, &m.xI))) return rc;
-  if ((rc = reserve(h, "work", (size_t)(4 + 2 * r->n_photons_loop), &m.work))) return rc;
+  if ((rc = reserve(h, "work", (size_t)(16 + 2 * r->n_photons_loop), &m.work))) return rc;
   h->n_tally = L.total; h->n_xI = n_xI; h->lay_xJ = lxJ; h->lay_nsed = n_sed; h->n_type_flux = n_type_flux;
   if (realloc_ || r->reset_tallies) {
     CK(cudaMemsetAsync(m.tally, 0, (size_t)L.total * sizeof(double), h->stream));
     if (n_xI) CK(cudaMemsetAsync(m.xI, 0, (size_t)n_xI * sizeof(float), h->stream));
     fill_int_kernel<<<256, 256, 0, h->stream>>>(m.xT_ech, m.n_cells, 2);      // xT_ech = 2, thermal_emission.f90:119,2164
   }
-  CK(cudaMemsetAsync(m.work, 0, (size_t)(4 + 2 * r->n_photons_loop) * sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(m.work, 0, (size_t)(16 + 2 * r->n_photons_loop) * sizeof(unsigned long long), h->stream));
+  h->n_photons_loop_alloc = r->n_photons_loop;
   return MCB_OK;
 }
 

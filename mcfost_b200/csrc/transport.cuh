@@ -111,6 +111,8 @@ __device__ __forceinline__ void rotation(double xi, double yi, double zi, double
   yf = cost * yi - sint * xi;
   zf = sing * zi - w1 * prod;
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
 // ---- heavy libm entry points, not inlined: one copy each in the instruction stream ----
 __device__ __noinline__ double mcb_log(double x) { return log(x); }
 __device__ __noinline__ void mcb_sincospi(double x, double* s, double* c) { sincospi(x, s, c); }
@@ -355,9 +357,16 @@ __device__ __noinline__ void deposit_rt1(int idx, int p_icell, int p_lambda, dou
 // =============================================================================
 // Packet pool in shared memory
 // =============================================================================
-constexpr int MC_BLOCK = 512;       // threads per block (one block per SM)
+#ifndef MCB_BLOCK_T
+#define MCB_BLOCK_T 512
+#endif
+#ifndef MCB_FLY_STEPS_T
+#define MCB_FLY_STEPS_T 4
+#endif
+constexpr int MC_BLOCK = MCB_BLOCK_T;       // threads per block (one block per SM)
 constexpr int NP = 1024;            // packets in flight per block
-constexpr int FLY_STEPS = 4;        // cell crossings per FLY visit
+constexpr int FLY_STEPS = MCB_FLY_STEPS_T;        // cell crossings per FLY visit
+constexpr unsigned DRAIN_LIVE = 96; // live packets per block below which the pool is considered to be draining out
 
 enum { F_PX = 0, F_PY, F_PZ, F_OX, F_OY, F_OZ, F_U, F_V, F_W, F_S0, F_EXTR, F_S1, F_S2, F_S3 };
 enum { U_C0A = 0, U_C0B, U_COA, U_COB, U_PKLO, U_PKHI, U_EV, U_MISC, U_RALB, NU32 = 9 };
@@ -412,6 +421,8 @@ template <bool SM> __device__ __forceinline__ Pool make_pool() {
 }
 
 struct Stats { unsigned int pk, steps, inter, sca, abs_, kill, esc, bounce; };
+// scheduling diagnostics (per warp, lane 0): chunk visits and valid lanes per phase
+struct SchedStats { unsigned int visits[NQ], lanes[NQ]; };
 
 // Regrouping step: push the packets of this warp to the ring queue of their next phase (one shared-
 // memory atomic per destination queue).  Packets that leave the pool (no more work) decrement LIVE.
@@ -455,7 +466,7 @@ __device__ __forceinline__ void start_flight(const DevModel& m, const DevRun& r,
 // EMIT: claim a packet id, emit_packet (dust_transfer.f90:1047-1151), start the first flight
 // =============================================================================
 template <class G, bool SM>
-__device__ __noinline__ void phase_emit(int slot, bool valid, Stats& st) {
+__device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
   const Pool P = make_pool<SM>();
@@ -477,6 +488,7 @@ __device__ __noinline__ void phase_emit(int slot, bool valid, Stats& st) {
       if ((int)lane == leader) base = atomicAdd(m.work, (unsigned long long)__popc(need));
       base = __shfl_sync(0xffffffffu, base, leader);
       const unsigned long long g = base + __popc(need & ((1u << lane) - 1u));
+      if (valid && g >= r.n_packets_total) atomicMin(m.work + 1, (unsigned long long)globaltimer_ns());     // diagnostics: start of the drain-out
       if (valid && g < r.n_packets_total) {
         const unsigned long long lc = g / r.n_per_chunk;
         idx_in_chunk = g % r.n_per_chunk;
@@ -582,14 +594,14 @@ __device__ __noinline__ void phase_emit(int slot, bool valid, Stats& st) {
       nextq = Q_EMIT;
     }
   }
-  push_next(P, slot, nextq, valid, lane);
+  return nextq;
 }
 
 // =============================================================================
 // FLY: up to FLY_STEPS iterations of the physical_length loop (optical_depth.f90:77-178)
 // =============================================================================
 template <class G, bool SM>
-__device__ __noinline__ void phase_fly(int slot, bool valid, Stats& st) {
+__device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
   const Pool P = make_pool<SM>();
@@ -710,14 +722,14 @@ __device__ __noinline__ void phase_fly(int slot, bool valid, Stats& st) {
       }
     }
   }
-  push_next(P, slot, nextq, valid, lane);
+  return nextq;
 }
 
 // =============================================================================
 // SCATTER: method 2 (dust_transfer.f90:1318-1351) + start of the next flight
 // =============================================================================
 template <class G, bool SM>
-__device__ __noinline__ void phase_scatter(int slot, bool valid, Stats& st) {
+__device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
   const Pool P = make_pool<SM>();
@@ -767,14 +779,14 @@ __device__ __noinline__ void phase_scatter(int slot, bool valid, Stats& st) {
       nextq = Q_FLY;
     }
   }
-  push_next(P, slot, nextq, valid, lane);
+  return nextq;
 }
 
 // =============================================================================
 // ABSORB: immediate re-emission, LTE (dust_transfer.f90:1353-1402) + start of the next flight
 // =============================================================================
 template <class G, bool SM>
-__device__ __noinline__ void phase_absorb(int slot, bool valid, Stats& st) {
+__device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
   const Pool P = make_pool<SM>();
@@ -802,7 +814,7 @@ __device__ __noinline__ void phase_absorb(int slot, bool valid, Stats& st) {
     P.U(U_MISC, slot) = misc;
     nextq = Q_FLY;
   }
-  push_next(P, slot, nextq, valid, lane);
+  return nextq;
 }
 
 // =============================================================================
@@ -822,13 +834,17 @@ mc_photon_loop_kernel() {
   if (threadIdx.x == 0) { P.ctl[NQ + Q_EMIT] = NP; P.ctl[8] = NP; }
   __syncthreads();
   Stats st = {0, 0, 0, 0, 0, 0, 0, 0};
+  SchedStats ss = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  if (blockIdx.x == 0 && threadIdx.x == 0) { m.work[1] = ~0ull; atomicExch(m.work + (2 + 2 * r.n_photons_loop), globaltimer_ns()); }
   // ---- asynchronous scheduling: every warp repeatedly claims up to 32 entries of ONE queue (so all its
   // lanes run the same phase), preferring full chunks; partial chunks are only taken when no other warp
   // is busy (nothing more will arrive).  No block-wide barriers after this point.
   for (;;) {
     int qi = -1; unsigned h = 0, n = 0;
     if (lane == 0) {
-      for (;;) {
+      // prefer a full 32-entry chunk.  Partial chunks are taken at once when the pool is draining out
+      // (few live packets: nothing will fill up), otherwise only after ~2 us without a full chunk.
+      for (int polls = 0;; ++polls) {
         int best = -1; unsigned best_n = 0;
 #pragma unroll
         for (int k = 0; k < NQ; ++k) {
@@ -836,19 +852,16 @@ mc_photon_loop_kernel() {
           if (av >= 32u) { best = k; best_n = 32u; break; }
           if (av > best_n) { best = k; best_n = av; }
         }
-        if (best >= 0 && (best_n == 32u || P.BUSY() == 0u)) {
+        const unsigned live = P.LIVE();
+        if (best >= 0 && (best_n == 32u || live <= DRAIN_LIVE || polls >= 8)) {
           const unsigned hh = P.HEAD(best);
           const unsigned av = P.TAIL(best) - hh;
           const unsigned take = av < 32u ? av : 32u;
-          if (take > 0 && (take == 32u || P.BUSY() == 0u) && atomicCAS((unsigned*)&P.ctl[best], hh, hh + take) == hh) {
-            atomicAdd((unsigned*)&P.ctl[9], 1u);
-            qi = best; h = hh; n = take;
-            break;
-          }
+          if (take > 0 && atomicCAS((unsigned*)&P.ctl[best], hh, hh + take) == hh) { qi = best; h = hh; n = take; break; }
           continue;
         }
-        if (P.LIVE() == 0u) break;       // every packet of this block is done
-        __nanosleep(64);
+        if (best < 0 && live == 0u) break;       // every packet of this block is done
+        __nanosleep(250);
       }
     }
     qi = __shfl_sync(0xffffffffu, qi, 0);
@@ -865,13 +878,38 @@ mc_photon_loop_kernel() {
       slot = sv;
     }
     __threadfence_block();                   // acquire: packet state written before the entry
-    switch (qi) {
-      case Q_EMIT: phase_emit<G, SM>(slot, valid, st); break;
-      case Q_ABS:  phase_absorb<G, SM>(slot, valid, st); break;
-      case Q_SCAT: phase_scatter<G, SM>(slot, valid, st); break;
-      default:     phase_fly<G, SM>(slot, valid, st); break;
+    // Run the phase; then regroup.  If (nearly) all lanes of this warp continue with the same next phase,
+    // or the pool is draining out (small chunk), the warp keeps those packets and runs their next phase
+    // directly; everything else goes back to the shared queues.
+    bool mine = valid;
+    for (;;) {
+      { const unsigned mm = __ballot_sync(0xffffffffu, mine); if (lane == 0) { ss.visits[qi] += 1; ss.lanes[qi] += __popc(mm); } }
+      int nextq;
+      switch (qi) {
+        case Q_EMIT: nextq = phase_emit<G, SM>(slot, mine, st); break;
+        case Q_ABS:  nextq = phase_absorb<G, SM>(slot, mine, st); break;
+        case Q_SCAT: nextq = phase_scatter<G, SM>(slot, mine, st); break;
+        default:     nextq = phase_fly<G, SM>(slot, mine, st); break;
+      }
+      if (!mine) nextq = Q_NONE;
+      int keep = -1, keep_n = 0, total_n = 0;
+#pragma unroll
+      for (int k = 0; k < NQ; ++k) {
+        const int c = __popc(__ballot_sync(0xffffffffu, nextq == k));
+        total_n += c;
+        if (c > keep_n) { keep_n = c; keep = k; }
+      }
+      unsigned live_now = 0;
+      if (lane == 0) live_now = P.LIVE();
+      live_now = __shfl_sync(0xffffffffu, live_now, 0);                      // warp-uniform decision
+      const bool cont = keep_n > 0 && (keep_n >= 28 || live_now <= DRAIN_LIVE);
+      const int pushq = (cont && nextq == keep) ? Q_NONE + 1 : nextq;      // kept lanes are not pushed
+      push_next(P, slot, pushq, mine, lane);
+      if (!cont) break;
+      mine = mine && (nextq == keep);
+      qi = keep;
+      __threadfence_block();
     }
-    if (lane == 0) atomicSub((unsigned*)&P.ctl[9], 1u);
   }
 
   // ---- diagnostics (not part of the reference) ----
@@ -882,6 +920,11 @@ mc_photon_loop_kernel() {
   };
   flush(STAT_PACKETS, st.pk); flush(STAT_STEPS, st.steps); flush(STAT_INTERACT, st.inter); flush(STAT_SCATT, st.sca);
   flush(STAT_ABS, st.abs_); flush(STAT_KILLED, st.kill); flush(STAT_ESCAPED, st.esc); flush(STAT_BOUNCE, st.bounce);
+  if (lane == 0) {
+    unsigned long long* dbg = m.work + (4 + 2 * r.n_photons_loop);
+    for (int k = 0; k < NQ; ++k) { atomicAdd(dbg + k, (unsigned long long)ss.visits[k]); atomicAdd(dbg + NQ + k, (unsigned long long)ss.lanes[k]); }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(m.work + (3 + 2 * r.n_photons_loop), globaltimer_ns());
 }
 
 }  // namespace mcb

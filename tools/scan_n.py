@@ -11,7 +11,9 @@ S.repartition_energie(P); G.upload_dark_zone(P.l_dark_zone); G.upload_emission(P
 G.mc_photon_loop(1, 1, 200)
 for n2 in ns:
     P.n_photons_eq_th = n2; S.repartition_energie(P); G.upload_emission(P)      # L_packet_th = L_tot / n_packets
-    for rep in range(2):
+    for rep in range(int(os.environ.get("REPS", "2"))):
         t = G.mc_photon_loop(1, 1, n2, call_index=rep)
         ms = G.last_kernel_ms()
         print(f"n2={n2} packets={128*n2} kernel {ms:.1f} ms  {128*n2/ms*1e3:.3e} pk/s  steps/s {t.stats[1]/ms*1e3:.3e}  int/s {t.stats[2]/ms*1e3:.3e}  steps/pk {t.stats[1]/t.stats[0]:.1f} int/pk {t.stats[2]/t.stats[0]:.1f}", flush=True)
+        d = G.debug_counters()
+        print(f"    steady {d['steady_ms']:.1f} ms ({128*n2/max(d['steady_ms'],1e-9)*1e3:.3e} pk/s in steady state)  drain {d['kernel_ms']-d['steady_ms']:.1f} ms  fill " + " ".join(f"{k}={v:.1f}" for k, v in d['chunk_fill'].items()), flush=True)
