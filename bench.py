@@ -268,7 +268,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n2", type=int, default=20000, help="packets per chunk per GPU (128 chunks)")
+    ap.add_argument("--n2", type=int, default=1000000, help="packets per chunk per GPU (128 chunks): 1.28e8 packets per step per GPU")
     ap.add_argument("--cpu-n2", type=int, default=8000, help="packets per chunk of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -3,6 +3,7 @@
 // fallback anywhere in this library: without a CUDA device every entry point
 // fails with MCB_ERR_NO_DEVICE.
 #include <cmath>
+#include <cstdlib>
 
 #include "handle.cuh"
 #include "cells.cuh"
@@ -290,6 +291,7 @@ static int setup_tallies(mcb_handle* h, const mcb_run_params* r, bool lxJ, bool 
   }
   CK(cudaMemsetAsync(m.work, 0, (size_t)(16 + 2 * r->n_photons_loop) * sizeof(unsigned long long), h->stream));
   h->n_photons_loop_alloc = r->n_photons_loop;
+  CK(cudaMemsetAsync(m.work + 1, 0xFF, sizeof(unsigned long long), h->stream));      // work[1] = ~0: "counter not dry yet"
   return MCB_OK;
 }
 
@@ -346,6 +348,7 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   dr.n_per_chunk = (unsigned long long)r->n_photons2 < dr.sent_lim ? (unsigned long long)r->n_photons2 : dr.sent_lim;
   dr.n_packets_total = dr.count_sent ? (unsigned long long)n_local * dr.n_per_chunk : 0ull;
   dr.nb_proc_equiv = (double)r->n_ranks;
+  { const char* e = getenv("MCB_DEBUG_ABORT_DRY"); dr.debug_abort_dry = (e && e[0] == '1') ? 1 : 0; }   // profiling aid only: tallies are incomplete
   int rc = setup_tallies(h, r, dr.lxJ != 0, rt1, dr.n_type_flux);
   if (rc) return rc;
   if (n_local == 0 || (dr.count_sent && dr.n_packets_total == 0)) { CK(cudaEventRecord(h->ev0, h->stream)); CK(cudaEventRecord(h->ev1, h->stream)); h->launched = true; return MCB_OK; }

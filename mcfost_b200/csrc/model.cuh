@@ -104,6 +104,7 @@ struct DevRun {
   unsigned long long n_per_chunk;       // count_sent: min(n_photons2, sent_lim)
   unsigned long long n_packets_total;   // count_sent: n_local_chunks * n_per_chunk
   double nb_proc_equiv;                 // n_ranks: scales the local tally in Temp_LTE
+  int debug_abort_dry;                  // profiling aid (env MCB_DEBUG_ABORT_DRY): stop when the packet counter runs dry
 };
 
 }  // namespace mcb

@@ -361,11 +361,11 @@ __device__ __noinline__ void deposit_rt1(int idx, int p_icell, int p_lambda, dou
 #define MCB_BLOCK_T 512
 #endif
 #ifndef MCB_FLY_STEPS_T
-#define MCB_FLY_STEPS_T 4
+#define MCB_FLY_STEPS_T 8
 #endif
 constexpr int MC_BLOCK = MCB_BLOCK_T;       // threads per block (one block per SM)
 constexpr int NP = 1024;            // packets in flight per block
-constexpr int FLY_STEPS = MCB_FLY_STEPS_T;        // cell crossings per FLY visit
+constexpr int FLY_STEPS = MCB_FLY_STEPS_T;        // max cell crossings per FLY visit
 constexpr unsigned DRAIN_LIVE = 96; // live packets per block below which the pool is considered to be draining out
 
 enum { F_PX = 0, F_PY, F_PZ, F_OX, F_OY, F_OZ, F_U, F_V, F_W, F_S0, F_EXTR, F_S1, F_S2, F_S3 };
@@ -607,98 +607,109 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
   const Pool P = make_pool<SM>();
   using CellT = typename G::CellT;
   using Hit = typename G::Hit;
-  const unsigned lane = threadIdx.x & 31;
+  const bool thermal = r.letape_th != 0;
+  const bool variable_dust = m.p_n_cells != 1;
+  const bool rt1_on = (!thermal) && r.rt1;
   int nextq = Q_NONE;
+  double x0 = 0, y0 = 0, z0 = 0, u = 0, v = 0, w = 1, extr = 0, S0 = 0, xo = 0, yo = 0, zo = 0;
+  uint32_t misc = 0;
+  int lambda = 1, i_star_hit = 0;
+  CellT c0, c_old; null_cell(c0); null_cell(c_old);
+  DirInv dinv; dinv.inv_a = 0; dinv.inv_w = 0;
+  Rt1Scratch rt1;
   if (valid) {
-    const bool thermal = r.letape_th != 0;
-    const bool variable_dust = m.p_n_cells != 1;
-    double x0 = P.F(F_PX, slot), y0 = P.F(F_PY, slot), z0 = P.F(F_PZ, slot);
-    double u = P.F(F_U, slot), v = P.F(F_V, slot), w = P.F(F_W, slot);
-    double extr = P.F(F_EXTR, slot);
-    const double S0 = P.F(F_S0, slot);
-    const uint32_t misc = P.U(U_MISC, slot);
-    const int lambda = misc_lambda(misc), i_star_hit = misc_istar(misc);
-    CellT c0, c_old;
+    x0 = P.F(F_PX, slot); y0 = P.F(F_PY, slot); z0 = P.F(F_PZ, slot);
+    u = P.F(F_U, slot); v = P.F(F_V, slot); w = P.F(F_W, slot);
+    extr = P.F(F_EXTR, slot);
+    S0 = P.F(F_S0, slot);
+    misc = P.U(U_MISC, slot);
+    lambda = misc_lambda(misc); i_star_hit = misc_istar(misc);
     unpack_cell(P.U(U_C0A, slot), P.U(U_C0B, slot), c0);
     unpack_cell(P.U(U_COA, slot), P.U(U_COB, slot), c_old);
-    double xo = P.F(F_OX, slot), yo = P.F(F_OY, slot), zo = P.F(F_OZ, slot);
-    const DirInv dinv = dir_invariants(u, v, w);
-    Rt1Scratch rt1;
-    const bool rt1_on = (!thermal) && r.rt1;
+    xo = P.F(F_OX, slot); yo = P.F(F_OY, slot); zo = P.F(F_OZ, slot);
+    dinv = dir_invariants(u, v, w);
     if (rt1_on) angles_scatt_rt1(u, v, w, rt1);       // recomputed per visit (same values as once per flight)
     nextq = Q_FLY;
-    bool interact = false;
+  }
+  const int n_in = __popc(__ballot_sync(0xffffffffu, valid));
+  bool flying = valid, interact = false;
 #pragma unroll 1
-    for (int it = 0; it < FLY_STEPS; ++it) {
-      if (G::test_exit(m, c0, x0, y0, z0)) {
-        if (!misc_ism(misc)) {       // the packet leaves the model: detector (capteur, output.f90:294)
+  for (int it = 0; it < FLY_STEPS; ++it) {
+    // leave the loop once fewer than half of this chunk's packets are still in flight: the rest of the
+    // warp would idle; the packets still flying are re-queued and regrouped into full chunks
+    const int n_fly = __popc(__ballot_sync(0xffffffffu, flying));
+    if (n_fly == 0 || (it > 0 && 2 * n_fly < n_in)) break;
+    if (!flying) continue;
+    if (G::test_exit(m, c0, x0, y0, z0)) {
+      if (!misc_ism(misc)) {       // the packet leaves the model: detector (capteur, output.f90:294)
+        double S[4] = {S0, 0.0, 0.0, 0.0};
+        if (POLA) { S[1] = P.F(F_S1, slot); S[2] = P.F(F_S2, slot); S[3] = P.F(F_S3, slot); }
+        const int capt = capteur(lambda, u, v, w, S, misc_star(misc), misc_scatt(misc));
+        if (!r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * misc_chunk(misc), 1ull);
+      }
+      ++st.esc;
+      nextq = Q_EMIT; flying = false;
+      continue;
+    }
+    if (i_star_hit > 0) {
+      CellT cs; cell_of_id(m, m.star_icell[i_star_hit - 1], cs);
+      if (same_cell(c0, cs)) { ++st.kill; nextq = Q_EMIT; flying = false; continue; }     // packet absorbed by the star
+    }
+    const int idx = tally_index(m, c0);
+    double opacity = 0.0;
+    int p_icell = 1;
+    if (idx >= 0) {
+      p_icell = variable_dust ? idx + 1 : 1;
+      opacity = t_kappa<SM>(m, p_icell, lambda) * __ldg(m.kappa_factor + idx);
+      if (__ldg(m.dark + idx)) {
+        // dark-zone bounce (optical_depth.f90:104-112): back to the previous cell's entry point, reversed
+        u = -u; v = -v; w = -w;
+        c0 = c_old; x0 = xo; y0 = yo; z0 = zo;
+        ++st.bounce;
+        interact = true; flying = false;
+        continue;
+      }
+    }
+    const Hit h = G::distance(m, dinv, x0, y0, z0, u, v, w, c0, c_old);
+    ++st.steps;
+    double l_contrib = hit_l_contrib(h), l = h.l;
+    const double tau_c = l_contrib * opacity;
+    bool lstop = false;
+    if (tau_c > extr) {
+      lstop = true;
+      l_contrib = l_contrib * (extr / tau_c);
+      l = hit_l_void(h) + l_contrib;
+    } else extr = extr - tau_c;
+    if (idx >= 0) {
+      // save_radiation_field (radiation_field.f90:31-135)
+      if (thermal) {
+        atomicAdd(m.tally + m.lay.xKJ + idx, t_kappa_abs<SM>(m, p_icell, lambda) * l_contrib * S0);
+        if (r.lxJ) atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S0);
+      } else {
+        if (r.lxJ) atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S0);
+        if (rt1_on) {
+          double x1, y1, z1;
+          G::exit_point(h, x0, y0, z0, u, v, w, x1, y1, z1);
           double S[4] = {S0, 0.0, 0.0, 0.0};
           if (POLA) { S[1] = P.F(F_S1, slot); S[2] = P.F(F_S2, slot); S[3] = P.F(F_S3, slot); }
-          const int capt = capteur(lambda, u, v, w, S, misc_star(misc), misc_scatt(misc));
-          if (!r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * misc_chunk(misc), 1ull);
-        }
-        ++st.esc;
-        nextq = Q_EMIT;
-        break;
-      }
-      if (i_star_hit > 0) {
-        CellT cs; cell_of_id(m, m.star_icell[i_star_hit - 1], cs);
-        if (same_cell(c0, cs)) { ++st.kill; nextq = Q_EMIT; break; }     // packet absorbed by the star
-      }
-      const int idx = tally_index(m, c0);
-      double opacity = 0.0;
-      int p_icell = 1;
-      if (idx >= 0) {
-        p_icell = variable_dust ? idx + 1 : 1;
-        opacity = t_kappa<SM>(m, p_icell, lambda) * __ldg(m.kappa_factor + idx);
-        if (__ldg(m.dark + idx)) {
-          // dark-zone bounce (optical_depth.f90:104-112): back to the previous cell's entry point, reversed
-          u = -u; v = -v; w = -w;
-          c0 = c_old; x0 = xo; y0 = yo; z0 = zo;
-          ++st.bounce;
-          interact = true;
-          break;
+          deposit_rt1(idx, p_icell, r.p_lambda_in, l_contrib, S, misc_star(misc),
+                      0.5 * (x0 + x1), 0.5 * (y0 + y1), 0.5 * (z0 + z1), rt1);
         }
       }
-      const Hit h = G::distance(m, dinv, x0, y0, z0, u, v, w, c0, c_old);
-      ++st.steps;
-      double l_contrib = hit_l_contrib(h), l = h.l;
-      const double tau_c = l_contrib * opacity;
-      bool lstop = false;
-      if (tau_c > extr) {
-        lstop = true;
-        l_contrib = l_contrib * (extr / tau_c);
-        l = hit_l_void(h) + l_contrib;
-      } else extr = extr - tau_c;
-      if (idx >= 0) {
-        // save_radiation_field (radiation_field.f90:31-135)
-        if (thermal) {
-          atomicAdd(m.tally + m.lay.xKJ + idx, t_kappa_abs<SM>(m, p_icell, lambda) * l_contrib * S0);
-          if (r.lxJ) atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S0);
-        } else {
-          if (r.lxJ) atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S0);
-          if (rt1_on) {
-            double x1, y1, z1;
-            G::exit_point(h, x0, y0, z0, u, v, w, x1, y1, z1);
-            double S[4] = {S0, 0.0, 0.0, 0.0};
-            if (POLA) { S[1] = P.F(F_S1, slot); S[2] = P.F(F_S2, slot); S[3] = P.F(F_S3, slot); }
-            deposit_rt1(idx, p_icell, r.p_lambda_in, l_contrib, S, misc_star(misc),
-                        0.5 * (x0 + x1), 0.5 * (y0 + y1), 0.5 * (z0 + z1), rt1);
-          }
-        }
-      }
-      if (lstop) {
-        x0 = x0 + l * u; y0 = y0 + l * v; z0 = z0 + l * w;                               // interaction point
-        if (!G::is_vor && m.l3D && m.kind == 1) c0 = G::index(m, x0, y0, z0);            // optical_depth.f90:162-165
-        interact = true;
-        break;
-      }
-      double x1, y1, z1;
-      CellT c1;
-      G::advance(m, h, x0, y0, z0, u, v, w, c0, x1, y1, z1, c1);
-      xo = x0; yo = y0; zo = z0; c_old = c0;
-      x0 = x1; y0 = y1; z0 = z1; c0 = c1;
     }
+    if (lstop) {
+      x0 = x0 + l * u; y0 = y0 + l * v; z0 = z0 + l * w;                               // interaction point
+      if (!G::is_vor && m.l3D && m.kind == 1) c0 = G::index(m, x0, y0, z0);            // optical_depth.f90:162-165
+      interact = true; flying = false;
+      continue;
+    }
+    double x1, y1, z1;
+    CellT c1;
+    G::advance(m, h, x0, y0, z0, u, v, w, c0, x1, y1, z1, c1);
+    xo = x0; yo = y0; zo = z0; c_old = c0;
+    x0 = x1; y0 = y1; z0 = z1; c0 = c1;
+  }
+  if (valid) {
     if (interact) {
       // the flight ended with an interaction at (x0,y0,z0) in cell c0 (dust_transfer.f90:1260-1284)
       ++st.inter;
@@ -835,7 +846,7 @@ mc_photon_loop_kernel() {
   __syncthreads();
   Stats st = {0, 0, 0, 0, 0, 0, 0, 0};
   SchedStats ss = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-  if (blockIdx.x == 0 && threadIdx.x == 0) { m.work[1] = ~0ull; atomicExch(m.work + (2 + 2 * r.n_photons_loop), globaltimer_ns()); }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(m.work + (2 + 2 * r.n_photons_loop), globaltimer_ns());
   // ---- asynchronous scheduling: every warp repeatedly claims up to 32 entries of ONE queue (so all its
   // lanes run the same phase), preferring full chunks; partial chunks are only taken when no other warp
   // is busy (nothing more will arrive).  No block-wide barriers after this point.
@@ -861,6 +872,7 @@ mc_photon_loop_kernel() {
           continue;
         }
         if (best < 0 && live == 0u) break;       // every packet of this block is done
+        if (c_r.debug_abort_dry && __ldcg(c_m.work + 1) != ~0ull) break;      // profiling aid: steady-state only
         __nanosleep(250);
       }
     }
