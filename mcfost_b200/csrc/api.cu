@@ -29,6 +29,7 @@ int mcfost_b200_init(int device, mcb_handle** out) {
   mcb_handle* h = new mcb_handle();
   memset(&h->m, 0, sizeof h->m);
   h->device = device;
+  { static int next_bank = 0; h->bank = next_bank++; }      // up to 4 handles per process can have launches in flight together
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return MCB_ERR_CUDA; }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);

@@ -13,6 +13,7 @@
 
 struct mcb_handle {
   int device = 0;
+  int bank = 0;                           // constant-memory bank of this handle's launches (see transport.cuh)
   int n_sm = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

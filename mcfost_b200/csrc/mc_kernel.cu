@@ -13,10 +13,13 @@ static int launch_one(mcb_handle* h, const DevRun& dr) {
   auto kern = mc_photon_loop_kernel<G, SM>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // model + run parameters -> constant memory, ordered on the handle's stream
-  CK(cudaMemcpyToSymbolAsync(c_m, &h->m, sizeof(DevModel), 0, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyToSymbolAsync(c_r, &dr, sizeof(DevRun), 0, cudaMemcpyHostToDevice, h->stream));
+  // the previous launch of this handle must be over before its constant bank is rewritten
+  CK(cudaStreamSynchronize(h->stream));
+  const int bank = h->bank % MCB_BANKS;
+  CK(cudaMemcpyToSymbolAsync(c_mm, &h->m, sizeof(DevModel), (size_t)bank * sizeof(DevModel), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyToSymbolAsync(c_rr, &dr, sizeof(DevRun), (size_t)bank * sizeof(DevRun), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));          // dr / h->m are host stack / heap values
-  const int blocks = h->n_sm;                     // persistent: one 512-thread block (1024 packets in flight) per SM
+  const dim3 blocks(h->n_sm, bank + 1);          // persistent: one 512-thread block (1024 packets in flight) per SM; grid.y = bank + 1
   CK(cudaEventRecord(h->ev0, h->stream));
   kern<<<blocks, MC_BLOCK, smem, h->stream>>>();
   CK(cudaGetLastError());

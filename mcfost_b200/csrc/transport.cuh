@@ -39,9 +39,14 @@ namespace mcb {
 
 // The model and run parameters of the launch in flight live in constant memory (written by
 // mcb_launch_mc on the handle's stream): every phase function reads them through the constant
-// bank without threading pointers through the non-inlined calls.
-__constant__ DevModel c_m;
-__constant__ DevRun c_r;
+// bank without threading pointers through the non-inlined calls.  There are MCB_BANKS copies so
+// that launches of different handles can be in flight together (the drain-out of one call
+// overlaps the next call of another handle); the bank of a launch is gridDim.y - 1.
+constexpr int MCB_BANKS = 4;
+__constant__ DevModel c_mm[MCB_BANKS];
+__constant__ DevRun c_rr[MCB_BANKS];
+#define c_m (c_mm[gridDim.y - 1])
+#define c_r (c_rr[gridDim.y - 1])
 
 enum { Q_EMIT = 0, Q_ABS = 1, Q_SCAT = 2, Q_FLY = 3, NQ = 4, Q_NONE = 7 };     // queue order = claim order (longest phases first)
 enum { STAT_PACKETS = 0, STAT_STEPS, STAT_INTERACT, STAT_SCATT, STAT_ABS, STAT_KILLED, STAT_ESCAPED, STAT_BOUNCE };
@@ -181,31 +186,44 @@ __device__ __forceinline__ void angle_diff_theta_pos(const DevModel& m, int p_la
   cospsi = c0 + rand2 * (c1 - c0);
 }
 
-// ---- scattering.f90:1187-1298 update_Stokes with the per-cell Mueller matrix
-// of get_Mueller_matrix_per_cell (:1328-1350); sparse products written out ------
-__device__ __noinline__ void scatter_stokes(int lambda, int itheta, float frac, int p_icell, double* S,
+// ---- scattering.f90:1187-1298 update_Stokes with the per-cell Mueller matrix of
+// get_Mueller_matrix_per_cell (:1328-1350); sparse products written out.
+// The reference builds the rotation from angles (theta = atan2(v1,u1) in `rotation`, utils.f90:584;
+// theta = acos(costhet), omega = 2(theta + pi/2), cos/sin(omega) in fp32, scattering.f90:1242-1261).
+// Here the same quantities are formed algebraically (cos(atan2(v,u)) = u/hypot(u,v);
+// cos(omega) = 1 - 2 costhet^2, sin(omega) = -+2 costhet sqrt(1 - costhet^2)): identical up to the
+// fp32 rounding the reference itself carries, without atan2 / sincos / acosf / cosf / sinf.
+__device__ __forceinline__ void scatter_stokes(int lambda, int itheta, float frac, int p_icell, double* S,
                                                double u0, double v0, double w0, double u1, double v1, double w1) {
   const DevModel& m = c_m;
   const size_t q1 = (size_t)itheta + (size_t)(NANG + 1) * ((p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)), q0 = q1 - 1;
   const float frac_m1 = 1.0f - frac;
+  const float a22 = __ldg(m.s22 + q1), b22 = __ldg(m.s22 + q0), a12 = __ldg(m.s12 + q1), b12 = __ldg(m.s12 + q0);
+  const float a33 = __ldg(m.s33 + q1), b33 = __ldg(m.s33 + q0), a44 = __ldg(m.s44 + q1), b44 = __ldg(m.s44 + q0);
+  const float a34 = __ldg(m.s34 + q1), b34 = __ldg(m.s34 + q0);
   const double M11 = (double)1.0f;
-  const double M22 = (double)__fadd_rn(__fmul_rn(__ldg(m.s22 + q1), frac), __fmul_rn(__ldg(m.s22 + q0), frac_m1));
-  const double M12 = (double)__fadd_rn(__fmul_rn(__ldg(m.s12 + q1), frac), __fmul_rn(__ldg(m.s12 + q0), frac_m1));
-  const double M33 = (double)__fadd_rn(__fmul_rn(__ldg(m.s33 + q1), frac), __fmul_rn(__ldg(m.s33 + q0), frac_m1));
-  const double M44 = (double)__fadd_rn(__fmul_rn(__ldg(m.s44 + q1), frac), __fmul_rn(__ldg(m.s44 + q0), frac_m1));
-  const double M34 = (double)__fsub_rn(__fmul_rn(-__ldg(m.s34 + q1), frac), __fmul_rn(__ldg(m.s34 + q0), frac_m1));
+  const double M22 = (double)__fadd_rn(__fmul_rn(a22, frac), __fmul_rn(b22, frac_m1));
+  const double M12 = (double)__fadd_rn(__fmul_rn(a12, frac), __fmul_rn(b12, frac_m1));
+  const double M33 = (double)__fadd_rn(__fmul_rn(a33, frac), __fmul_rn(b33, frac_m1));
+  const double M44 = (double)__fadd_rn(__fmul_rn(a44, frac), __fmul_rn(b44, frac_m1));
+  const double M34 = (double)__fsub_rn(__fmul_rn(-a34, frac), __fmul_rn(b34, frac_m1));
   const double M43 = -M34;
-  double v1pi, v1pj, v1pk;
-  rotation(u0, v0, w0, u1, v1, w1, v1pi, v1pj, v1pk);
-  float xnyp = (float)sqrt(v1pk * v1pk + v1pj * v1pj), costhet;
-  if (xnyp < 1e-10f) { xnyp = 0.0f; costhet = 1.0f; }
+  // rotation(u0,v0,w0 ; u1,v1,w1) -> v1p (utils.f90:553-599), algebraic cos/sin of atan2(v1,u1)
+  double cost, sint, sing;
+  if (w1 > 0.999999999) { cost = 1.0; sint = 0.0; sing = 0.0; }
+  else if (fabs(u1) < MCB_TINY_REAL) { cost = 0.0; sint = 1.0; sing = sqrt(1.0 - w1 * w1); }
+  else { const double ih = rsqrt(u1 * u1 + v1 * v1); cost = u1 * ih; sint = v1 * ih; sing = sqrt(1.0 - w1 * w1); }
+  const double prod = cost * u0 + sint * v0;
+  const double v1pj = cost * v0 - sint * u0;
+  const double v1pk = sing * w0 - w1 * prod;
+  const float xnyp = (float)sqrt(v1pk * v1pk + v1pj * v1pj);
+  float costhet;
+  if (xnyp < 1e-10f) costhet = 1.0f;
   else costhet = (float)(-1.0 * v1pj / (double)xnyp);
-  float theta = acosf(costhet);
-  if ((double)theta >= MCB_PI) theta = 0.0f;
-  theta = (float)((double)theta + MCB_HALF_PI);
-  float omega = 2.0f * theta;
-  if (v1pk < 0.0) omega = -1.0f * omega;
-  float cosw = cosf(omega), sinw = sinf(omega);
+  costhet = fminf(1.0f, fmaxf(-1.0f, costhet));
+  float cosw = 1.0f - 2.0f * costhet * costhet;                          // cos(2 theta + pi)
+  float sinw = -2.0f * costhet * sqrtf(fmaxf(0.0f, 1.0f - costhet * costhet));   // sin(2 theta + pi), theta in [0, pi]
+  if (v1pk < 0.0) sinw = -sinw;
   if (fabsf(cosw) < 1e-06f) cosw = 0.0f;
   if (fabsf(sinw) < 1e-06f) sinw = 0.0f;
   const double cw = cosw, sw = sinw;
@@ -217,9 +235,8 @@ __device__ __noinline__ void scatter_stokes(int lambda, int itheta, float frac, 
   // S = RPO.D ; RPO(2,2)=cw RPO(2,3)=sw RPO(3,2)=-sw RPO(3,3)=cw
   S[0] = D0; S[1] = cw * D1 + sw * D2; S[2] = (-sw) * D1 + cw * D2; S[3] = D3;
   if (S[0] > MCB_TINY_REAL) {
-    const double S0 = S[0];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) S[a] = S[a] * M11 * S1_0 / S0;
+    const double f = M11 * S1_0 / S[0];
+    S[0] *= f; S[1] *= f; S[2] *= f; S[3] *= f;
   }
 }
 
@@ -834,6 +851,7 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
 template <class G, bool SM>
 __global__ void __launch_bounds__(MC_BLOCK, 1)
 mc_photon_loop_kernel() {
+  if (blockIdx.y != gridDim.y - 1) return;        // grid.y only encodes the constant bank
   const DevModel& m = c_m; const DevRun& r = c_r;
   const unsigned lane = threadIdx.x & 31;
   if (SM) stage_tables(m, r.p_lambda_in);
