@@ -874,6 +874,7 @@ mc_photon_loop_kernel() {
       // prefer a full 32-entry chunk.  Partial chunks are taken at once when the pool is draining out
       // (few live packets: nothing will fill up), otherwise only after ~2 us without a full chunk.
       for (int polls = 0;; ++polls) {
+        if (c_r.debug_abort_dry && __ldcg(c_m.work + 1) != ~0ull) break;      // profiling aid: steady-state only
         int best = -1; unsigned best_n = 0;
 #pragma unroll
         for (int k = 0; k < NQ; ++k) {
@@ -890,7 +891,6 @@ mc_photon_loop_kernel() {
           continue;
         }
         if (best < 0 && live == 0u) break;       // every packet of this block is done
-        if (c_r.debug_abort_dry && __ldcg(c_m.work + 1) != ~0ull) break;      // profiling aid: steady-state only
         __nanosleep(250);
       }
     }

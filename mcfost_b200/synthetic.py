@@ -665,3 +665,121 @@ def temp_finale(P, xKJ_abs, n_ranks_total_scale=1.0):
         frac = (lq[ic] - col[Ti - 2]) / (col[Ti - 1] - col[Ti - 2])
         T[ic] = np.exp(ltab[Ti - 1] * frac + ltab[Ti - 2] * (1.0 - frac))
     return T
+
+
+# ---------------------------------------------------------------------------
+# Voronoi mesh (stand-in for voro++: the reference's tessellation library is not vendored)
+# ---------------------------------------------------------------------------
+def voronoi_mesh(n_points=1500, half_size=100.0, seed=12345, cut_fraction=0.1):
+    """Seeds drawn from a disk-like density inside a box, tessellated with scipy (qhull).
+
+    The six walls are produced exactly by the mirror trick: every seed is reflected across each wall,
+    so the bisector between a seed and its image IS the wall and every real cell is bounded and inside
+    the box.  Neighbour lists follow the reference's layout (Voronoi.f90:23-66): 1-based cell ids,
+    -wall_id for walls, first/last pointers into `neighbours_list`.  A fraction of elongated cells is
+    flagged `was_cut` (the reference cuts cells whose faces are farther than 3h, voro++_wrapper.cpp:209-225)
+    so that the cut-sphere branch of cross_Voronoi_cell is exercised."""
+    from scipy.spatial import Voronoi, ConvexHull
+    rng = np.random.default_rng(seed)
+    L = half_size
+    # disk-like seeds: gaussian in z with flaring, r^-1 in radius; keep away from the walls
+    r = L * 0.9 * rng.uniform(0.05, 1.0, n_points)
+    phi = rng.uniform(0, 2 * np.pi, n_points)
+    z = rng.normal(0.0, 0.15 * r)
+    pts = np.stack([r * np.cos(phi), r * np.sin(phi), np.clip(z, -0.9 * L, 0.9 * L)], axis=1)
+    pts = np.clip(pts, -0.95 * L, 0.95 * L)
+    n = n_points
+    lim = np.array([-L, L, -L, L, -L, L])
+    ext = [pts]
+    for wdx in range(6):
+        ax, val = wdx // 2, lim[wdx]
+        m = pts.copy()
+        m[:, ax] = 2.0 * val - m[:, ax]
+        ext.append(m)
+    allp = np.concatenate(ext)
+    vor = Voronoi(allp)
+    neigh = [set() for _ in range(n)]
+    for a, b in vor.ridge_points:
+        for i, j in ((a, b), (b, a)):
+            if i < n:
+                neigh[i].add(int(j) + 1 if j < n else -(int(j - n) // n + 1))
+    first = np.zeros(n, np.int32); last = np.zeros(n, np.int32)
+    flat = []
+    for i in range(n):
+        lst = sorted(neigh[i], key=lambda q: (q < 0, abs(q)))
+        first[i] = len(flat) + 1
+        flat.extend(lst)
+        last[i] = len(flat)
+    vol = np.zeros(n); h = np.zeros(n); elong = np.zeros(n)
+    for i in range(n):
+        verts = vor.vertices[vor.regions[vor.point_region[i]]]
+        vol[i] = ConvexHull(verts).volume
+        h[i] = (3.0 * vol[i] / (4.0 * np.pi)) ** (1.0 / 3.0)
+        elong[i] = np.max(np.linalg.norm(verts - pts[i], axis=1)) / h[i]
+    P = Problem()
+    P.kind, P.l3D = MCB_GRID_VORONOI, 1
+    P.n_rad, P.nz, P.n_az = 0, 0, 0
+    P.n_cells = n
+    P.Rmax2, P.zmaxmax = 3.0 * L * L, L
+    P.vor_xyz = np.asfortranarray(pts.T.copy())        # (3, n)
+    P.vor_h = h
+    P.vor_first, P.vor_last = first, last
+    P.neighbours_list = np.array(flat, np.int32)
+    thr = np.quantile(elong, 1.0 - cut_fraction) if cut_fraction > 0 else np.inf
+    P.vor_was_cut = (elong > thr).astype(np.int32)
+    P.vor_is_star = np.zeros(n, np.int32)
+    P.vor_is_star_neighbour = np.zeros(n, np.int32)
+    P.wall_x = [[-1, 0, 0, -L], [1, 0, 0, L], [0, -1, 0, -L], [0, 1, 0, L], [0, 0, -1, -L], [0, 0, 1, L]]
+    P.cutting_distance_o_h = 1.6
+    P.volume = vol
+    P.r_grid = np.hypot(pts[:, 0], pts[:, 1]); P.z_grid = pts[:, 2]; P.phi_grid = np.arctan2(pts[:, 1], pts[:, 0])
+    P.r_lim = P.r_lim_2 = P.r_lim_3 = P.z_lim = P.zmax = P.tan_theta_lim = P.theta_lim = P.tan_phi_lim = None
+    P.cell_map_i = P.cell_map_j = P.cell_map_k = None
+    P.n_cells_tot = 0
+    return P
+
+
+def voronoi_disk(n_points=1500, n_photons_eq_th=200, tau_mid=30.0, n_lambda=50, n_T=100, pola=False, seed=12345):
+    """A small disk on a Voronoi mesh (the phantom / SPH use case, test size)."""
+    P = voronoi_mesh(n_points, seed=seed)
+    rs = np.maximum(P.r_grid, 1.0)
+    rho = rs ** -1.5 * np.exp(-0.5 * (P.z_grid / (0.15 * rs)) ** 2) + 1e-6
+    # _finish needs a radial column to scale kappa: use a pseudo column through the cells sorted by radius
+    order = np.argsort(P.r_grid)
+    P.n_rad = 0
+    P.n_lambda, P.n_T = n_lambda, n_T
+    P.tab_lambda, P.tab_delta_lambda = init_lambda(n_lambda)
+    P.tab_lambda = np.float32(P.tab_lambda).astype(np.float64)
+    P.tab_delta_lambda = np.float32(P.tab_delta_lambda).astype(np.float64)
+    P.T_min, P.T_max = 1.0, 3000.0
+    P.tab_Temp = init_tab_Temp(n_T, P.T_min, P.T_max)
+    P.n_photons_loop, P.n_photons_eq_th = 128, n_photons_eq_th
+    P.n_stars = 1
+    P.star_xyzr = np.asfortranarray(np.array([[0.0], [0.0], [0.0], [2.0 * RSUN_TO_AU]]))
+    P.star_T = np.array([5000.0])
+    P.star_out_model = np.zeros(1, np.int32)
+    d2 = np.sum(P.vor_xyz ** 2, axis=0)
+    P.star_icell = np.array([int(np.argmin(d2)) + 1], np.int32)       # the cell that contains the star
+    P.p_n_cells, P.p_n_lambda_pos = 1, n_lambda
+    P.kappa_factor = rho / rho.max()
+    kext, albedo, g, s11, pol = synthetic_optics(P.tab_lambda, pola=pola)
+    l_seuil = int(np.argmax(P.tab_lambda > 0.81)) + 1
+    P.lambda_seuil = l_seuil
+    rr = P.r_grid[order]
+    col = float(np.sum(P.kappa_factor[order][:-1] * np.diff(rr)))
+    k0 = tau_mid / (col * kext[l_seuil - 1])
+    P.kappa = np.asfortranarray((k0 * kext).reshape(1, n_lambda))
+    P.tab_albedo_pos = np.asfortranarray(np.float32(albedo).reshape(1, n_lambda))
+    P.tab_g_pos = np.asfortranarray(np.float32(g).reshape(1, n_lambda))
+    P.kappa_abs_LTE = np.asfortranarray(P.kappa * (1.0 - P.tab_albedo_pos.astype(np.float64)))
+    for k, v in scattering_tables(P, s11, albedo, P.kappa[0], pol).items():
+        setattr(P, k, v)
+    init_reemission(P)
+    star_energy(P)
+    P.l_dark_zone = np.zeros(P.n_cells, np.int32)
+    P.E_paquet = 1.0
+    P.R_ISM = 0.0
+    P.centre_ISM = (0.0, 0.0, 0.0)
+    repartition_energie(P)
+    P.name = "Voronoi disk"
+    return P

@@ -246,3 +246,65 @@ def test_full_size_properties_ref41():
     assert 100 < T.max() < 3000
     # radiative equilibrium: total re-emitted = absorbed => detected energy equals emitted energy
     assert t.sed.sum() / t.stats[0] > 0.999
+
+
+@pytest.fixture(scope="module")
+def voronoi_pair():
+    P = S.voronoi_disk(n_points=1500, n_photons_eq_th=300)
+    G = api.PhotonLoop(P)
+    yield P, Oracle(P), G
+    G.close()
+
+
+def _voronoi_rays(P, n, seed):
+    rng = np.random.default_rng(seed)
+    ic = rng.integers(1, P.n_cells + 1, n).astype(np.int32)
+    x, y, z = P.vor_xyz[0, ic - 1].copy(), P.vor_xyz[1, ic - 1].copy(), P.vor_xyz[2, ic - 1].copy()
+    # jitter inside the cell: move 30 % of the way towards a random direction's wall
+    w = rng.uniform(-1, 1, n); ph = rng.uniform(0, 2 * np.pi, n)
+    u, v = np.sqrt(1 - w * w) * np.cos(ph), np.sqrt(1 - w * w) * np.sin(ph)
+    return ic, x, y, z, u, v, w
+
+
+def test_voronoi_deterministic_kernels_bit_exact(voronoi_pair):
+    """fp32 plane tests, wall planes and the cut-cell sphere of cross_Voronoi_cell (Voronoi.f90:839-992)."""
+    P, O, G = voronoi_pair
+    ic, x, y, z, u, v, w = _voronoi_rays(P, 100000, 31)
+    o, g = O.cross_cell(x, y, z, u, v, w, ic), G.cross_cell(x, y, z, u, v, w, ic)
+    assert np.array_equal(g["next_cell"], o["next_cell"])
+    for k in ("l", "l_contrib", "l_void_before", "x1", "y1", "z1"):
+        assert np.array_equal(g[k], o[k]), k
+    # continue from the exit points with previous_cell set (the entry face is skipped, :874)
+    ok = o["next_cell"] > 0
+    a = [q[ok] for q in (o["x1"], o["y1"], o["z1"], u, v, w, o["next_cell"], ic)]
+    o2, g2 = O.cross_cell(*a), G.cross_cell(*a)
+    assert np.array_equal(g2["next_cell"], o2["next_cell"]) and np.array_equal(g2["l"], o2["l"])
+    assert np.array_equal(G.index_cell(x[:2000], y[:2000], z[:2000]), O.index_cell(x[:2000], y[:2000], z[:2000]))
+    o = O.optical_length_tot(P.lambda_seuil, x[:20000], y[:20000], z[:20000], u[:20000], v[:20000], w[:20000], ic[:20000])
+    g = G.optical_length_tot(P.lambda_seuil, x[:20000], y[:20000], z[:20000], u[:20000], v[:20000], w[:20000], ic[:20000])
+    assert np.array_equal(g["n_steps"], o["n_steps"])
+    assert np.allclose(g["tau_tot"], o["tau_tot"], rtol=1e-12, atol=0) and np.allclose(g["lmax"], o["lmax"], rtol=1e-12, atol=0)
+    tau = np.random.default_rng(4).exponential(2.0, 20000).astype(np.float32)
+    o = O.physical_length(P.lambda_seuil, x[:20000], y[:20000], z[:20000], u[:20000], v[:20000], w[:20000], ic[:20000], tau)
+    g = G.physical_length(P.lambda_seuil, x[:20000], y[:20000], z[:20000], u[:20000], v[:20000], w[:20000], ic[:20000], tau)
+    for k in ("flag_sortie", "lpacket_alive", "icell"):
+        assert np.array_equal(g[k], o[k]), k
+    assert np.allclose(g["x"], o["x"], rtol=1e-12, atol=0)
+    # entry from outside the box
+    xs, ys, zs, du, dv, dw = rays_from_outside(P, 3000)
+    o, g = O.move_to_grid(xs, ys, zs, du, dv, dw), G.move_to_grid(xs, ys, zs, du, dv, dw)
+    assert np.array_equal(g["lintersect"], o["lintersect"]) and np.array_equal(g["icell"], o["icell"])
+
+
+def test_voronoi_thermal_statistical_parity(voronoi_pair):
+    P, O, G = voronoi_pair
+    tg = G.mc_photon_loop(1, 1, 1500, 1.0e30, 1, False)
+    to = Oracle(P, fast=True).run(n_threads=0, n_photons2=1500)
+    assert tg.stats[0] == to.stats[0] == 128 * 1500
+    assert tg.stats[5] + tg.stats[6] == tg.stats[0]
+    assert tg.sed.sum() == pytest.approx(tg.stats[6])
+    assert abs(tg.xKJ_abs.sum() / to.xKJ_abs.sum() - 1) < 0.03
+    assert abs(tg.stats[1] / to.stats[1] - 1) < 0.02
+    To, Tg = S.temp_finale(P, to.xKJ_abs), S.temp_finale(P, tg.xKJ_abs)
+    lit = (to.xKJ_abs > 0) & (tg.xKJ_abs > 0)
+    assert np.median(np.abs(Tg[lit] - To[lit]) / To[lit]) < 0.02          # 1500 cells, 192k packets: MC noise dominated

@@ -228,3 +228,39 @@ def test_golden_vectors_regression():
     assert np.array_equal(t.stats, G["thermal_stats"])
     assert np.allclose(t.xKJ_abs, G["thermal_xKJ"], rtol=1e-12, atol=0)
     assert np.array_equal(t.sed, G["thermal_sed"])
+
+
+def test_voronoi_mesh_and_walk():
+    """Voronoi mesh stand-in (scipy + mirror trick): cells tile the box exactly; the oracle's
+    fp32 plane walk (Voronoi.f90:839-992) goes from seed to wall through face-sharing cells."""
+    P = S.voronoi_disk(n_points=800, n_photons_eq_th=20)
+    assert abs(P.volume.sum() / 200.0 ** 3 - 1) < 1e-9
+    O = Oracle(P)
+    rng = np.random.default_rng(0)
+    n = 3000
+    ic = rng.integers(1, P.n_cells + 1, n).astype(np.int32)
+    x, y, z = P.vor_xyz[0, ic - 1], P.vor_xyz[1, ic - 1], P.vor_xyz[2, ic - 1]
+    assert np.array_equal(O.index_cell(x, y, z), ic)                       # nearest seed of a seed is itself
+    w = rng.uniform(-1, 1, n); ph = rng.uniform(0, 2 * np.pi, n)
+    u, v = np.sqrt(1 - w * w) * np.cos(ph), np.sqrt(1 - w * w) * np.sin(ph)
+    c = O.cross_cell(x, y, z, u, v, w, ic)
+    assert (c["l"] > 0).all() and (c["next_cell"] != 0).all()
+    # the next cell is a listed neighbour of the current one
+    for k in range(200):
+        nb = P.neighbours_list[P.vor_first[ic[k] - 1] - 1:P.vor_last[ic[k] - 1]]
+        assert c["next_cell"][k] in nb
+    # the exit point is equidistant (to fp32 accuracy) from the two seeds
+    inner = c["next_cell"] > 0
+    p1 = np.stack([c["x1"], c["y1"], c["z1"]])[:, inner]
+    d0 = np.linalg.norm(p1 - P.vor_xyz[:, ic[inner] - 1], axis=0)
+    d1 = np.linalg.norm(p1 - P.vor_xyz[:, c["next_cell"][inner] - 1], axis=0)
+    assert np.median(np.abs(d0 - d1) / d0) < 1e-4
+    # cut cells: contribution + void never exceed the crossing length
+    assert (c["l_contrib"] <= c["l"] * (1 + 1e-12)).all() and (c["l_void_before"] <= c["l"] * (1 + 1e-12)).all()
+    assert (c["l_contrib"][P.vor_was_cut[ic - 1] == 0] == c["l"][P.vor_was_cut[ic - 1] == 0]).all()
+    # whole walks end on a wall: total length <= box diagonal
+    r = O.optical_length_tot(P.lambda_seuil, x, y, z, u, v, w, ic)
+    assert (r["lmax"] > 0).all() and (r["lmax"] < 2 * np.sqrt(3) * 100.0).all()
+    t = O.run(n_threads=2, n_photons2=20)
+    assert t.stats[5] + t.stats[6] == t.stats[0] == 128 * 20
+    assert t.sed.sum() == pytest.approx(t.stats[6])
