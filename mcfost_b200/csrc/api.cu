@@ -160,6 +160,7 @@ int mcfost_b200_upload_grid(mcb_handle* h, const mcb_grid* g) {
   // default: no dark zone
   std::vector<uint8_t> dz((size_t)g->n_cells, 0);
   if ((rc = put(h, "dark", dz.data(), dz.size(), &m.dark))) return rc;
+  h->host_dark = dz; h->kf_dark_stale = true;
   CK(cudaStreamSynchronize(h->stream));
   h->has_grid = true;
   return MCB_OK;
@@ -171,6 +172,8 @@ int mcfost_b200_upload_dark_zone(mcb_handle* h, const int32_t* l_dark_zone) {
   CK(cudaSetDevice(h->device));
   std::vector<uint8_t> dz((size_t)h->m.n_cells, 0);
   if (l_dark_zone) for (int i = 0; i < h->m.n_cells; ++i) dz[i] = l_dark_zone[i] != 0;
+  h->host_dark = dz;
+  h->kf_dark_stale = true;
   int rc;
   if ((rc = put(h, "dark", dz.data(), dz.size(), &h->m.dark))) return rc;
   CK(cudaStreamSynchronize(h->stream));
@@ -193,6 +196,8 @@ int mcfost_b200_upload_opacity(mcb_handle* h, const mcb_opacity* o) {
   if ((rc = put(h, "kappa", o->kappa, npl, &m.kappa))) return rc;
   if ((rc = put(h, "kappa_abs", o->kappa_abs_LTE, npl, &m.kappa_abs))) return rc;
   if ((rc = put(h, "kappa_factor", o->kappa_factor, (size_t)m.n_cells, &m.kappa_factor))) return rc;
+  h->host_kappa_factor.assign(o->kappa_factor, o->kappa_factor + m.n_cells);
+  h->kf_dark_stale = true;
   if ((rc = put(h, "albedo", o->tab_albedo_pos, npl, &m.albedo))) return rc;
   if ((rc = put(h, "gfac", o->tab_g_pos, npl, &m.gfac))) return rc;
   if ((rc = put(h, "prob_s11", o->prob_s11_pos, npos, &m.prob_s11))) return rc;
@@ -353,6 +358,14 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   int rc = setup_tallies(h, r, dr.lxJ != 0, rt1, dr.n_type_flux);
   if (rc) return rc;
   if (n_local == 0 || (dr.count_sent && dr.n_packets_total == 0)) { CK(cudaEventRecord(h->ev0, h->stream)); CK(cudaEventRecord(h->ev1, h->stream)); h->launched = true; return MCB_OK; }
+  if (h->kf_dark_stale) {
+    std::vector<double> kd(h->host_kappa_factor);
+    for (size_t i = 0; i < kd.size(); ++i) if (i < h->host_dark.size() && h->host_dark[i]) kd[i] = -fabs(kd[i]) - 0.0;   // (-0.0 keeps the flag when kappa_factor == 0)
+    for (size_t i = 0; i < kd.size(); ++i) if (i < h->host_dark.size() && h->host_dark[i] && kd[i] == 0.0) kd[i] = -0.0;
+    if ((rc = put(h, "kf_dark", kd.data(), kd.size(), &m.kf_dark))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->kf_dark_stale = false;
+  }
   compute_smem_layout(h, r->p_lambda_in);
   rc = mcb_launch_mc(h, dr);
   if (rc) return rc;

@@ -27,6 +27,9 @@ struct mcb_handle {
   int lay_nsed = -1;
   int n_photons_loop_alloc = 0;
   int n_type_flux = 1;
+  std::vector<double> host_kappa_factor;  // host copies used to build kf_dark (kappa_factor | dark flag)
+  std::vector<uint8_t> host_dark;
+  bool kf_dark_stale = true;
   char err[512] = {0};
 };
 

@@ -7,24 +7,29 @@
 
 using namespace mcb;
 
-template <class G, bool SM>
-static int launch_one(mcb_handle* h, const DevRun& dr) {
+template <class G, bool SM, int BANK>
+static int launch_bank(mcb_handle* h, const DevRun& dr) {
   const size_t smem = (SM ? (size_t)h->m.sm.total_words * 8 : 0) + pool_bytes(dr.lsepar_pola != 0);
-  auto kern = mc_photon_loop_kernel<G, SM>;
+  auto kern = mc_photon_loop_kernel<G, SM, BANK>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // model + run parameters -> constant memory, ordered on the handle's stream
   // the previous launch of this handle must be over before its constant bank is rewritten
   CK(cudaStreamSynchronize(h->stream));
-  const int bank = h->bank % MCB_BANKS;
+  const int bank = BANK;
   CK(cudaMemcpyToSymbolAsync(c_mm, &h->m, sizeof(DevModel), (size_t)bank * sizeof(DevModel), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyToSymbolAsync(c_rr, &dr, sizeof(DevRun), (size_t)bank * sizeof(DevRun), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));          // dr / h->m are host stack / heap values
-  const dim3 blocks(h->n_sm, bank + 1);          // persistent: one 512-thread block (1024 packets in flight) per SM; grid.y = bank + 1
+  const int blocks = h->n_sm;                    // persistent: one 512-thread block (1024 packets in flight) per SM
   CK(cudaEventRecord(h->ev0, h->stream));
   kern<<<blocks, MC_BLOCK, smem, h->stream>>>();
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, h->stream));
   return MCB_OK;
+}
+
+template <class G, bool SM>
+static int launch_one(mcb_handle* h, const DevRun& dr) {
+  return (h->bank % MCB_BANKS) == 0 ? launch_bank<G, SM, 0>(h, dr) : launch_bank<G, SM, 1>(h, dr);
 }
 
 int mcb_launch_mc(mcb_handle* h, const DevRun& dr) {

@@ -52,6 +52,7 @@ struct DevModel {
   double Rmax2, zmaxmax;
   const double *r_lim_2, *r_lim_3, *z_lim, *zmax, *cell_height, *tan_theta_lim, *theta_lim, *tan_phi_lim, *volume;
   const double *kappa_factor;       // (n_cells)
+  const double *kf_dark;            // (n_cells) kappa_factor with the sign bit set where l_dark_zone (photon-loop kernel only)
   const uint8_t *dark;              // (n_cells) l_dark_zone
   // ---- Voronoi (Voronoi.f90:23-66) --------------------------------------
   const double *vor_xyz;            // (3, n_cells) fp64

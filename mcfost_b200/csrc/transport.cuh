@@ -40,13 +40,15 @@ namespace mcb {
 // The model and run parameters of the launch in flight live in constant memory (written by
 // mcb_launch_mc on the handle's stream): every phase function reads them through the constant
 // bank without threading pointers through the non-inlined calls.  There are MCB_BANKS copies so
-// that launches of different handles can be in flight together (the drain-out of one call
-// overlaps the next call of another handle); the bank of a launch is gridDim.y - 1.
-constexpr int MCB_BANKS = 4;
+// that launches of two handles can be in flight together (the drain-out of one call overlaps
+// the next call of the other handle).
+constexpr int MCB_BANKS = 2;
 __constant__ DevModel c_mm[MCB_BANKS];
 __constant__ DevRun c_rr[MCB_BANKS];
-#define c_m (c_mm[gridDim.y - 1])
-#define c_r (c_rr[gridDim.y - 1])
+// BANK is a template parameter of every function below that touches the constants, so that
+// c_m / c_r are compile-time constant-bank addresses (no indexed constant loads in the hot path)
+#define c_m (c_mm[BANK])
+#define c_r (c_rr[BANK])
 
 enum { Q_EMIT = 0, Q_ABS = 1, Q_SCAT = 2, Q_FLY = 3, NQ = 4, Q_NONE = 7 };     // queue order = claim order (longest phases first)
 enum { STAT_PACKETS = 0, STAT_STEPS, STAT_INTERACT, STAT_SCATT, STAT_ABS, STAT_KILLED, STAT_ESCAPED, STAT_BOUNCE };
@@ -193,6 +195,7 @@ __device__ __forceinline__ void angle_diff_theta_pos(const DevModel& m, int p_la
 // Here the same quantities are formed algebraically (cos(atan2(v,u)) = u/hypot(u,v);
 // cos(omega) = 1 - 2 costhet^2, sin(omega) = -+2 costhet sqrt(1 - costhet^2)): identical up to the
 // fp32 rounding the reference itself carries, without atan2 / sincos / acosf / cosf / sinf.
+template <int BANK>
 __device__ __forceinline__ void scatter_stokes(int lambda, int itheta, float frac, int p_icell, double* S,
                                                double u0, double v0, double w0, double u1, double v1, double w1) {
   const DevModel& m = c_m;
@@ -271,6 +274,7 @@ __device__ __forceinline__ int im_reemission_LTE(const DevModel& m, const DevRun
 }
 
 // ---- output.f90:294-595 capteur, SED branch ------------------------------------
+template <int BANK>
 __device__ __noinline__ int capteur(int lambda, double u1, double v1, double w1,
                                        const double* Sin, bool flag_star, bool flag_scatt) {
   const DevModel& m = c_m; const DevRun& r = c_r;
@@ -303,6 +307,7 @@ __device__ __noinline__ int capteur(int lambda, double u1, double v1, double w1,
 // ---- dust_ray_tracing.f90:409-476 angles_scatt_rt1 (per flight) ------------------
 struct Rt1Scratch { unsigned char itheta[MAX_RT]; double cosw[MAX_RT], sinw[MAX_RT]; };
 
+template <int BANK>
 __device__ __noinline__ void angles_scatt_rt1(double u, double v, double w, Rt1Scratch& sc) {
   const DevRun& r = c_r;
   for (int i = 0; i < r.n_rt; ++i) {
@@ -333,6 +338,7 @@ __device__ __noinline__ void angles_scatt_rt1(double u, double v, double w, Rt1S
 
 // ---- radiation_field.f90:63-89 + dust_ray_tracing.f90:480-632: rt1 scattered
 // specific intensity, fp32 atomics ---------------------------------------------------
+template <int BANK>
 __device__ __noinline__ void deposit_rt1(int idx, int p_icell, int p_lambda, double l,
                                             const double* S, bool flag_star, double xm, double ym, double zm, const Rt1Scratch& sc) {
   const DevModel& m = c_m; const DevRun& r = c_r;
@@ -426,7 +432,7 @@ __device__ __forceinline__ void pack_cell(int c, uint32_t& a, uint32_t& b) { a =
 __device__ __forceinline__ void unpack_cell(uint32_t a, uint32_t, int& c) { c = (int)a; }
 
 // the pool of this block: right after the staged tables in dynamic shared memory
-template <bool SM> __device__ __forceinline__ Pool make_pool() {
+template <bool SM, int BANK> __device__ __forceinline__ Pool make_pool() {
   Pool P;
   unsigned char* base = mcb_smem_raw + (SM ? (size_t)c_m.sm.total_words * 8 : 0);
   const size_t nf = (size_t)pool_nf64(c_r.lsepar_pola != 0);
@@ -464,8 +470,7 @@ __device__ __forceinline__ void push_next(const Pool& P, int slot, int nextq, bo
 // physical_length preamble (optical_depth.f90:53-68).  Position / direction / cell are already in the pool. ----
 __device__ __forceinline__ void start_flight(const DevModel& m, const DevRun& r, const Pool& P, int slot,
                                              double x, double y, double z, double u, double v, double w,
-                                             uint32_t pk_lo, uint32_t pk_hi, uint32_t ev, uint32_t& misc) {
-  const uint4 b = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev, pk_lo, pk_hi, r.call_index);
+                                             const uint4 b /* Philox block 2*ev of this packet */, uint32_t& misc) {
   const float rand = u01(b.x);
   float tau;
   if (rand == 1.0f) tau = 1.0e30f;
@@ -482,11 +487,11 @@ __device__ __forceinline__ void start_flight(const DevModel& m, const DevRun& r,
 // =============================================================================
 // EMIT: claim a packet id, emit_packet (dust_transfer.f90:1047-1151), start the first flight
 // =============================================================================
-template <class G, bool SM>
+template <class G, bool SM, int BANK>
 __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
-  const Pool P = make_pool<SM>();
+  const Pool P = make_pool<SM, BANK>();
   using CellT = typename G::CellT;
   const unsigned lane = threadIdx.x & 31;
   int nextq = Q_NONE;
@@ -598,13 +603,13 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
       P.U(U_C0A, slot) = ca_; P.U(U_C0B, slot) = cb_;
       P.U(U_PKLO, slot) = pk_lo; P.U(U_PKHI, slot) = pk_hi; P.U(U_EV, slot) = 1u;
       uint32_t misc = pack_misc(lambda, flag_star, false, flag_ISM, 0, my_chunk);
-      start_flight(m, r, P, slot, x, y, z, u, v, w, pk_lo, pk_hi, 1u, misc);
+      start_flight(m, r, P, slot, x, y, z, u, v, w, philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u, pk_lo, pk_hi, r.call_index), misc);
       P.U(U_MISC, slot) = misc;
       nextq = Q_FLY;
     } else {      // the packet never enters the model: straight to the detector (dust_transfer.f90:545-552)
       if (!flag_ISM) {
         const double S[4] = {S0, 0.0, 0.0, 0.0};
-        const int capt = capteur(lambda, u, v, w, S, flag_star, false);
+        const int capt = capteur<BANK>(lambda, u, v, w, S, flag_star, false);
         if (!r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * my_chunk, 1ull);
         ++st.esc;
       }
@@ -617,11 +622,11 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
 // =============================================================================
 // FLY: up to FLY_STEPS iterations of the physical_length loop (optical_depth.f90:77-178)
 // =============================================================================
-template <class G, bool SM>
+template <class G, bool SM, int BANK>
 __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
-  const Pool P = make_pool<SM>();
+  const Pool P = make_pool<SM, BANK>();
   using CellT = typename G::CellT;
   using Hit = typename G::Hit;
   const bool thermal = r.letape_th != 0;
@@ -645,7 +650,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
     unpack_cell(P.U(U_COA, slot), P.U(U_COB, slot), c_old);
     xo = P.F(F_OX, slot); yo = P.F(F_OY, slot); zo = P.F(F_OZ, slot);
     dinv = dir_invariants(u, v, w);
-    if (rt1_on) angles_scatt_rt1(u, v, w, rt1);       // recomputed per visit (same values as once per flight)
+    if (rt1_on) angles_scatt_rt1<BANK>(u, v, w, rt1);       // recomputed per visit (same values as once per flight)
     nextq = Q_FLY;
   }
   const int n_in = __popc(__ballot_sync(0xffffffffu, valid));
@@ -661,7 +666,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
       if (!misc_ism(misc)) {       // the packet leaves the model: detector (capteur, output.f90:294)
         double S[4] = {S0, 0.0, 0.0, 0.0};
         if (POLA) { S[1] = P.F(F_S1, slot); S[2] = P.F(F_S2, slot); S[3] = P.F(F_S3, slot); }
-        const int capt = capteur(lambda, u, v, w, S, misc_star(misc), misc_scatt(misc));
+        const int capt = capteur<BANK>(lambda, u, v, w, S, misc_star(misc), misc_scatt(misc));
         if (!r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * misc_chunk(misc), 1ull);
       }
       ++st.esc;
@@ -677,8 +682,8 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
     int p_icell = 1;
     if (idx >= 0) {
       p_icell = variable_dust ? idx + 1 : 1;
-      opacity = t_kappa<SM>(m, p_icell, lambda) * __ldg(m.kappa_factor + idx);
-      if (__ldg(m.dark + idx)) {
+      const double kf = __ldg(m.kf_dark + idx);      // kappa_factor, sign bit set <=> l_dark_zone (one load for both)
+      if (signbit(kf)) {
         // dark-zone bounce (optical_depth.f90:104-112): back to the previous cell's entry point, reversed
         u = -u; v = -v; w = -w;
         c0 = c_old; x0 = xo; y0 = yo; z0 = zo;
@@ -686,6 +691,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
         interact = true; flying = false;
         continue;
       }
+      opacity = t_kappa<SM>(m, p_icell, lambda) * kf;
     }
     const Hit h = G::distance(m, dinv, x0, y0, z0, u, v, w, c0, c_old);
     ++st.steps;
@@ -709,7 +715,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
           G::exit_point(h, x0, y0, z0, u, v, w, x1, y1, z1);
           double S[4] = {S0, 0.0, 0.0, 0.0};
           if (POLA) { S[1] = P.F(F_S1, slot); S[2] = P.F(F_S2, slot); S[3] = P.F(F_S3, slot); }
-          deposit_rt1(idx, p_icell, r.p_lambda_in, l_contrib, S, misc_star(misc),
+          deposit_rt1<BANK>(idx, p_icell, r.p_lambda_in, l_contrib, S, misc_star(misc),
                       0.5 * (x0 + x1), 0.5 * (y0 + y1), 0.5 * (z0 + z1), rt1);
         }
       }
@@ -756,11 +762,11 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
 // =============================================================================
 // SCATTER: method 2 (dust_transfer.f90:1318-1351) + start of the next flight
 // =============================================================================
-template <class G, bool SM>
+template <class G, bool SM, int BANK>
 __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
-  const Pool P = make_pool<SM>();
+  const Pool P = make_pool<SM, BANK>();
   using CellT = typename G::CellT;
   const unsigned lane = threadIdx.x & 31;
   int nextq = Q_NONE;
@@ -786,7 +792,13 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
     else {
       ++st.sca;
       const uint32_t pk_lo = P.U(U_PKLO, slot), pk_hi = P.U(U_PKHI, slot), ev = P.U(U_EV, slot);
+#ifdef MCB_PHILOX2
+      uint4 b, bnext;      // interaction block of flight ev, flight block of ev+1
+      philox_block2((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev + 1u, 2u * ev + 2u, pk_lo, pk_hi, r.call_index, b, bnext);
+#else
       const uint4 b = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev + 1u, pk_lo, pk_hi, r.call_index);
+      const uint4 bnext = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev + 2u, pk_lo, pk_hi, r.call_index);
+#endif
       const float rand = u01(b.x), rand2 = u01(b.y), rand3 = u01(b.z);
       const double u = P.F(F_U, slot), v = P.F(F_V, slot), w = P.F(F_W, slot);
       int itheta; double cospsi;
@@ -797,12 +809,12 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
       mcb_sincospi((double)__fsub_rn(__fmul_rn(2.0f, rand3), 1.0f), &sp, &cp);     // PHI = PI*(2.0*rand-1.0): fp32 inner
       double u1, v1, w1;
       cdapres(cospsi, sp, cp, u, v, w, u1, v1, w1);
-      if (POLA && r.lmethod_aniso1) scatter_stokes(lambda, itheta, rand2, p_icell, S, u, v, w, u1, v1, w1);
+      if (POLA && r.lmethod_aniso1) scatter_stokes<BANK>(lambda, itheta, rand2, p_icell, S, u, v, w, u1, v1, w1);
       P.F(F_U, slot) = u1; P.F(F_V, slot) = v1; P.F(F_W, slot) = w1;
       if (r.lmono || POLA) { P.F(F_S0, slot) = S[0]; if (POLA) { P.F(F_S1, slot) = S[1]; P.F(F_S2, slot) = S[2]; P.F(F_S3, slot) = S[3]; } }
       misc |= (1u << 11);                                    // flag_scatt
       P.U(U_EV, slot) = ev + 1u;
-      start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u1, v1, w1, pk_lo, pk_hi, ev + 1u, misc);
+      start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u1, v1, w1, bnext, misc);
       P.U(U_MISC, slot) = misc;
       nextq = Q_FLY;
     }
@@ -813,11 +825,11 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
 // =============================================================================
 // ABSORB: immediate re-emission, LTE (dust_transfer.f90:1353-1402) + start of the next flight
 // =============================================================================
-template <class G, bool SM>
+template <class G, bool SM, int BANK>
 __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
-  const Pool P = make_pool<SM>();
+  const Pool P = make_pool<SM, BANK>();
   using CellT = typename G::CellT;
   const unsigned lane = threadIdx.x & 31;
   int nextq = Q_NONE;
@@ -829,7 +841,13 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
     const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
     ++st.abs_;
     const uint32_t pk_lo = P.U(U_PKLO, slot), pk_hi = P.U(U_PKHI, slot), ev = P.U(U_EV, slot);
+#ifdef MCB_PHILOX2
+    uint4 b, bnext;      // interaction block of flight ev, flight block of ev+1
+    philox_block2((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev + 1u, 2u * ev + 2u, pk_lo, pk_hi, r.call_index, b, bnext);
+#else
     const uint4 b = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev + 1u, pk_lo, pk_hi, r.call_index);
+    const uint4 bnext = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev + 2u, pk_lo, pk_hi, r.call_index);
+#endif
     // b.x is rand1: drawn but unused in the high-memory LTE branch (thermal_emission.f90:739-765)
     const int lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, u01(b.y));
     double u, v, w;
@@ -838,7 +856,7 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
     if (POLA) { P.F(F_S1, slot) = 0.0; P.F(F_S2, slot) = 0.0; P.F(F_S3, slot) = 0.0; }
     misc = pack_misc(lambda, false, false, false, 0, misc_chunk(misc));      // flag_star = flag_scatt = flag_ISM = .false.
     P.U(U_EV, slot) = ev + 1u;
-    start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u, v, w, pk_lo, pk_hi, ev + 1u, misc);
+    start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u, v, w, bnext, misc);
     P.U(U_MISC, slot) = misc;
     nextq = Q_FLY;
   }
@@ -848,14 +866,13 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
 // =============================================================================
 // The persistent photon-loop kernel: rounds of (claim a single-phase chunk -> run the phase -> regroup)
 // =============================================================================
-template <class G, bool SM>
+template <class G, bool SM, int BANK>
 __global__ void __launch_bounds__(MC_BLOCK, 1)
 mc_photon_loop_kernel() {
-  if (blockIdx.y != gridDim.y - 1) return;        // grid.y only encodes the constant bank
   const DevModel& m = c_m; const DevRun& r = c_r;
   const unsigned lane = threadIdx.x & 31;
   if (SM) stage_tables(m, r.p_lambda_in);
-  const Pool P = make_pool<SM>();
+  const Pool P = make_pool<SM, BANK>();
   // every slot starts in the EMIT queue
   for (int i = threadIdx.x; i < NQ * NP; i += MC_BLOCK) P.q[i] = (i < NP) ? (unsigned short)i : (unsigned short)0xFFFFu;   // Q_EMIT == 0
   if (threadIdx.x < 16) P.ctl[threadIdx.x] = 0;
@@ -916,10 +933,10 @@ mc_photon_loop_kernel() {
       { const unsigned mm = __ballot_sync(0xffffffffu, mine); if (lane == 0) { ss.visits[qi] += 1; ss.lanes[qi] += __popc(mm); } }
       int nextq;
       switch (qi) {
-        case Q_EMIT: nextq = phase_emit<G, SM>(slot, mine, st); break;
-        case Q_ABS:  nextq = phase_absorb<G, SM>(slot, mine, st); break;
-        case Q_SCAT: nextq = phase_scatter<G, SM>(slot, mine, st); break;
-        default:     nextq = phase_fly<G, SM>(slot, mine, st); break;
+        case Q_EMIT: nextq = phase_emit<G, SM, BANK>(slot, mine, st); break;
+        case Q_ABS:  nextq = phase_absorb<G, SM, BANK>(slot, mine, st); break;
+        case Q_SCAT: nextq = phase_scatter<G, SM, BANK>(slot, mine, st); break;
+        default:     nextq = phase_fly<G, SM, BANK>(slot, mine, st); break;
       }
       if (!mine) nextq = Q_NONE;
       int keep = -1, keep_n = 0, total_n = 0;
