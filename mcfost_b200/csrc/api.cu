@@ -255,7 +255,10 @@ static void compute_smem_layout(mcb_handle* h, int /*p_lambda_in*/) {
     if (m.l3D) L.tan_phi = take(m.n_az);
     L.kappa = take(m.n_lambda); L.kappa_abs = take(m.n_lambda);
     L.albedo = take((m.n_lambda + 1) / 2); L.gfac = take((m.n_lambda + 1) / 2);
-    L.logQ = take(m.n_T); L.kdB = take(m.n_lambda * m.n_T);
+    L.logQ = take(m.n_T);
+    // kdB_dT_CDF (40 KB for ref4.1) is NOT staged: measured +3.7 % with it in global memory, because the
+    // shared memory it would take is worth more as L1 for kappa_factor / volume / tally lines
+    { const char* e = getenv("MCB_KDB_SMEM"); L.kdB = (e && e[0] == '1') ? take(m.n_lambda * m.n_T) : -1; }
     L.cos_tab = take(NANG + 1); L.prob_s11 = take((NANG + 2) / 2);
     L.spec_cumul = take(m.n_lambda + 1); L.frac_star = take(m.n_lambda); L.frac_disk = take(m.n_lambda);
     L.total_words = off;

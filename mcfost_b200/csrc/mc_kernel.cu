@@ -13,6 +13,13 @@ static int launch_bank(mcb_handle* h, const DevRun& dr) {
   auto kern = mc_photon_loop_kernel<G, SM, BANK>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // model + run parameters -> constant memory, ordered on the handle's stream
+  if (dr.lsepar_pola) {        // Stokes Q,U,V slabs (one per block), L2-resident
+    void*& q = h->bufs["quv"];
+    const size_t bytes = (size_t)h->n_sm * 3 * NP * sizeof(double);
+    if (q && h->buf_bytes["quv"] != bytes) { cudaFree(q); q = nullptr; }
+    if (!q) { CK(cudaMalloc(&q, bytes)); h->buf_bytes["quv"] = bytes; }
+    h->m.quv = (double*)q;
+  }
   // the previous launch of this handle must be over before its constant bank is rewritten
   CK(cudaStreamSynchronize(h->stream));
   const int bank = BANK;

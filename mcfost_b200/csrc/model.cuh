@@ -84,6 +84,7 @@ struct DevModel {
   TallyLayout lay;
   int *xT_ech;              // (n_cells)
   float *xI;                // xI_scatt
+  double *quv;              // Stokes Q,U,V of the packets in flight: (n_blocks, 3, NP), only with lsepar_pola
   unsigned long long *work; // [0] = next work item; [2+2c], [3+2c] = sent / received of local chunk c
   SmemLayout sm;
 };

@@ -66,7 +66,7 @@ template <bool SM> __device__ __forceinline__ float t_gfac(const DevModel& m, in
 template <bool SM> __device__ __forceinline__ double t_logQ(const DevModel& m, int t, int p_icell) {      // t 1-based
   return SM ? smd()[m.sm.logQ + t - 1] : __ldg(m.logQ + (size_t)m.n_T * (p_icell - 1) + t - 1); }
 template <bool SM> __device__ __forceinline__ double t_kdB(const DevModel& m, int l, int t, int p_icell) {  // l, t 1-based
-  return SM ? smd()[m.sm.kdB + (l - 1) + m.n_lambda * (t - 1)]
+  return (SM && m.sm.kdB >= 0) ? smd()[m.sm.kdB + (l - 1) + m.n_lambda * (t - 1)]
             : __ldg(m.kdB + (size_t)m.n_lambda * ((t - 1) + (size_t)m.n_T * (p_icell - 1)) + (l - 1)); }
 template <bool SM> __device__ __forceinline__ double t_cos(const DevModel& m, int k) { return SM ? smd()[m.sm.cos_tab + k] : __ldg(m.cos_tab + k); }
 template <bool SM> __device__ __forceinline__ float t_prob_s11(const DevModel& m, int k, int p_icell, int p_lambda) {
@@ -87,7 +87,7 @@ __device__ __forceinline__ void stage_tables(const DevModel& m, int p_lambda_in)
   if (m.l3D) cp(L.tan_phi, m.tan_phi_lim, m.n_az);
   cp(L.kappa, m.kappa, m.n_lambda); cp(L.kappa_abs, m.kappa_abs, m.n_lambda);
   cpf(L.albedo, m.albedo, m.n_lambda); cpf(L.gfac, m.gfac, m.n_lambda);
-  cp(L.logQ, m.logQ, m.n_T); cp(L.kdB, m.kdB, m.n_lambda * m.n_T);
+  cp(L.logQ, m.logQ, m.n_T); if (L.kdB >= 0) cp(L.kdB, m.kdB, m.n_lambda * m.n_T);
   cp(L.cos_tab, m.cos_tab, NANG + 1);
   if (m.prob_s11) cpf(L.prob_s11, m.prob_s11 + (size_t)(NANG + 1) * (p_lambda_in - 1), NANG + 1);
   cp(L.spec_cumul, m.spec_cumul, m.n_lambda + 1); cp(L.frac_star, m.frac_star, m.n_lambda); cp(L.frac_disk, m.frac_disk, m.n_lambda);
@@ -391,9 +391,14 @@ constexpr int NP = 1024;            // packets in flight per block
 constexpr int FLY_STEPS = MCB_FLY_STEPS_T;        // max cell crossings per FLY visit
 constexpr unsigned DRAIN_LIVE = 96; // live packets per block below which the pool is considered to be draining out
 
-enum { F_PX = 0, F_PY, F_PZ, F_OX, F_OY, F_OZ, F_U, F_V, F_W, F_S0, F_EXTR, F_S1, F_S2, F_S3 };
+enum { F_PX = 0, F_PY, F_PZ, F_OX, F_OY, F_OZ, F_U, F_V, F_W, F_S0, F_EXTR };
+// Stokes Q,U,V of packet `slot` of this block: quv[(blockIdx.x*3 + k)*NP + slot]
+#define QUV(k, slot) (c_m.quv[((size_t)blockIdx.x * 3 + (k)) * NP + (slot)])
 enum { U_C0A = 0, U_C0B, U_COA, U_COB, U_PKLO, U_PKHI, U_EV, U_MISC, U_RALB, NU32 = 9 };
-__host__ __device__ constexpr int pool_nf64(bool pola) { return pola ? 14 : 11; }
+// Stokes Q,U,V live in GLOBAL memory (DevModel.quv, one L2-resident slab per block): they are only touched by
+// scatterings, re-emissions and the detector, and keeping them out of shared memory leaves more of the
+// 227 KB for L1 (kappa_factor / volume / tally lines).
+__host__ __device__ constexpr int pool_nf64(bool) { return 11; }
 
 // bytes of shared memory after the staged tables
 __host__ __device__ constexpr size_t pool_bytes(bool pola) {
@@ -598,7 +603,7 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
       P.F(F_PX, slot) = x; P.F(F_PY, slot) = y; P.F(F_PZ, slot) = z;
       P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;
       P.F(F_S0, slot) = S0;
-      if (POLA) { P.F(F_S1, slot) = 0.0; P.F(F_S2, slot) = 0.0; P.F(F_S3, slot) = 0.0; }
+      if (POLA) { QUV(0, slot) = 0.0; QUV(1, slot) = 0.0; QUV(2, slot) = 0.0; }
       uint32_t ca_, cb_; pack_cell(cell, ca_, cb_);
       P.U(U_C0A, slot) = ca_; P.U(U_C0B, slot) = cb_;
       P.U(U_PKLO, slot) = pk_lo; P.U(U_PKHI, slot) = pk_hi; P.U(U_EV, slot) = 1u;
@@ -665,7 +670,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
     if (G::test_exit(m, c0, x0, y0, z0)) {
       if (!misc_ism(misc)) {       // the packet leaves the model: detector (capteur, output.f90:294)
         double S[4] = {S0, 0.0, 0.0, 0.0};
-        if (POLA) { S[1] = P.F(F_S1, slot); S[2] = P.F(F_S2, slot); S[3] = P.F(F_S3, slot); }
+        if (POLA) { S[1] = QUV(0, slot); S[2] = QUV(1, slot); S[3] = QUV(2, slot); }
         const int capt = capteur<BANK>(lambda, u, v, w, S, misc_star(misc), misc_scatt(misc));
         if (!r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * misc_chunk(misc), 1ull);
       }
@@ -714,7 +719,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
           double x1, y1, z1;
           G::exit_point(h, x0, y0, z0, u, v, w, x1, y1, z1);
           double S[4] = {S0, 0.0, 0.0, 0.0};
-          if (POLA) { S[1] = P.F(F_S1, slot); S[2] = P.F(F_S2, slot); S[3] = P.F(F_S3, slot); }
+          if (POLA) { S[1] = QUV(0, slot); S[2] = QUV(1, slot); S[3] = QUV(2, slot); }
           deposit_rt1<BANK>(idx, p_icell, r.p_lambda_in, l_contrib, S, misc_star(misc),
                       0.5 * (x0 + x1), 0.5 * (y0 + y1), 0.5 * (z0 + z1), rt1);
         }
@@ -779,7 +784,7 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
     const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
     bool dead = false;
     double S[4] = {P.F(F_S0, slot), 0.0, 0.0, 0.0};
-    if (POLA) { S[1] = P.F(F_S1, slot); S[2] = P.F(F_S2, slot); S[3] = P.F(F_S3, slot); }
+    if (POLA) { S[1] = QUV(0, slot); S[2] = QUV(1, slot); S[3] = QUV(2, slot); }
     if (r.lmono) {      // forced scattering (dust_transfer.f90:1263-1278)
       if (idx >= 0 && __ldg(m.dark + idx)) dead = true;
       else {
@@ -811,7 +816,7 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
       cdapres(cospsi, sp, cp, u, v, w, u1, v1, w1);
       if (POLA && r.lmethod_aniso1) scatter_stokes<BANK>(lambda, itheta, rand2, p_icell, S, u, v, w, u1, v1, w1);
       P.F(F_U, slot) = u1; P.F(F_V, slot) = v1; P.F(F_W, slot) = w1;
-      if (r.lmono || POLA) { P.F(F_S0, slot) = S[0]; if (POLA) { P.F(F_S1, slot) = S[1]; P.F(F_S2, slot) = S[2]; P.F(F_S3, slot) = S[3]; } }
+      if (r.lmono || POLA) { P.F(F_S0, slot) = S[0]; if (POLA) { QUV(0, slot) = S[1]; QUV(1, slot) = S[2]; QUV(2, slot) = S[3]; } }
       misc |= (1u << 11);                                    // flag_scatt
       P.U(U_EV, slot) = ev + 1u;
       start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u1, v1, w1, bnext, misc);
@@ -853,7 +858,7 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
     double u, v, w;
     random_isotropic_direction(u01(b.z), u01(b.w), u, v, w);
     P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;
-    if (POLA) { P.F(F_S1, slot) = 0.0; P.F(F_S2, slot) = 0.0; P.F(F_S3, slot) = 0.0; }
+    if (POLA) { QUV(0, slot) = 0.0; QUV(1, slot) = 0.0; QUV(2, slot) = 0.0; }
     misc = pack_misc(lambda, false, false, false, 0, misc_chunk(misc));      // flag_star = flag_scatt = flag_ISM = .false.
     P.U(U_EV, slot) = ev + 1u;
     start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u, v, w, bnext, misc);
