@@ -783,3 +783,68 @@ def voronoi_disk(n_points=1500, n_photons_eq_th=200, tau_mid=30.0, n_lambda=50, 
     repartition_energie(P)
     P.name = "Voronoi disk"
     return P
+
+
+def ref41_multi_like(n_photons_eq_th=200, n_rad=40, nz=20, n_rad_in=5, tau_mid=300.0, n_lambda=50, n_T=100):
+    """G3-like (ref4.1_multi.para, LTE part): two zones (1-5 AU, 10-300 AU) with DIFFERENT dust, so
+    lvariable_dust = .true. and every opacity / scattering / thermal table is per cell
+    (p_n_cells = n_cells, kappa_factor = 1, init_mcfost.f90:1582, dust_prop.f90:951-955).  The
+    scattering tables use the single-wavelength layout p_n_lambda_pos = 1 that the reference falls back
+    to when per-cell x per-wavelength tables would not fit (scattering.f90:39-66)."""
+    zones = [DiskZone(rin=1.0, rout=5.0, dust_mass=1e-5), DiskZone(rin=10.0, rout=300.0, dust_mass=1e-3)]
+    P = cylindrical_grid(n_rad, nz, 1, n_rad_in, zones, l3D=False)
+    P.n_lambda, P.n_T = n_lambda, n_T
+    P.tab_lambda, P.tab_delta_lambda = init_lambda(n_lambda)
+    P.tab_lambda = np.float32(P.tab_lambda).astype(np.float64)
+    P.tab_delta_lambda = np.float32(P.tab_delta_lambda).astype(np.float64)
+    P.T_min, P.T_max = 1.0, 3000.0
+    P.tab_Temp = init_tab_Temp(n_T, P.T_min, P.T_max)
+    P.n_photons_loop, P.n_photons_eq_th = 128, n_photons_eq_th
+    P.n_stars = 1
+    P.star_xyzr = np.asfortranarray(np.array([[0.0], [0.0], [0.0], [2.0 * RSUN_TO_AU]]))
+    P.star_T = np.array([5000.0]); P.star_out_model = np.zeros(1, np.int32)
+    P.star_icell = np.array([star_icell_analytic(P)], np.int32)
+    nc = P.n_cells
+    rho = disk_density(P, zones)
+    inner = P.r_grid < 7.0
+    kext, albedo, g, s11, _ = synthetic_optics(P.tab_lambda, pola=False)
+    # zone A (inner): small grains -> steeper opacity law, higher albedo; zone B: the G1 optics
+    kextA = np.where(P.tab_lambda > 0.3, (0.3 / P.tab_lambda) ** 1.6, 1.0)
+    albA = np.clip(albedo * 1.6, 0.0, 0.9)
+    gA = g * 0.3
+    l_seuil = int(np.argmax(P.tab_lambda > 0.81)) + 1
+    P.lambda_seuil = l_seuil
+    mid = np.arange(n_rad)
+    col = float(np.sum((rho / rho.max())[mid] * (P.r_lim[1:] - P.r_lim[:-1])))
+    k0 = tau_mid / (col * kext[l_seuil - 1])
+    dens = rho / rho.max()
+    P.p_n_cells, P.p_n_lambda_pos = nc, 1
+    P.kappa_factor = np.ones(nc)
+    kap = np.where(inner[:, None], kextA[None, :], kext[None, :]) * dens[:, None] * k0
+    alb = np.where(inner[:, None], albA[None, :], albedo[None, :])
+    gg = np.where(inner[:, None], gA[None, :], g[None, :])
+    P.kappa = np.asfortranarray(kap)
+    P.tab_albedo_pos = np.asfortranarray(np.float32(alb))
+    P.tab_g_pos = np.asfortranarray(np.float32(gg))
+    P.kappa_abs_LTE = np.asfortranarray(kap * (1.0 - alb))
+    # per-cell s11 CDF at the (single) tabulated wavelength index 1
+    theta = np.arange(NANG_SCATT + 1) * PI / NANG_SCATT
+    prob = np.zeros((NANG_SCATT + 1, nc, 1), np.float32, order="F")
+    tab = np.zeros((NANG_SCATT + 1, nc, 1), np.float32, order="F")
+    for zone_mask, gz in ((inner, gA[0]), (~inner, g[0])):
+        s = (1.0 - gz ** 2) * (1.0 + gz ** 2 - 2.0 * gz * np.cos(theta)) ** (-1.5)
+        w = s * np.sin(theta)
+        c = np.concatenate(([0.0], np.cumsum(0.5 * (w[1:] + w[:-1]))))
+        c = c / c[-1]
+        prob[:, zone_mask, 0] = np.float32(c)[:, None]
+        tab[:, zone_mask, 0] = np.float32(s / (np.sum(w) * 2.0 * PI))[:, None]
+    P.prob_s11_pos, P.tab_s11_pos = prob, tab
+    for nm in ("tab_s12_o_s11_pos", "tab_s22_o_s11_pos", "tab_s33_o_s11_pos", "tab_s34_o_s11_pos", "tab_s44_o_s11_pos"):
+        setattr(P, nm, None)
+    init_reemission(P)
+    star_energy(P)
+    P.l_dark_zone = np.zeros(nc, np.int32)
+    P.E_paquet = 1.0; P.R_ISM = 0.0; P.centre_ISM = (0.0, 0.0, 0.0)
+    repartition_energie(P)
+    P.name = "ref4.1_multi-like (G3, LTE part)"
+    return P
