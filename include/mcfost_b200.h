@@ -187,6 +187,9 @@ typedef struct mcb_run_params {
    * the reference's x nb_proc (thermal_emission.f90:670). */
   int32_t rank, n_ranks;
   int32_t reset_tallies;    /* 1: zero all device tallies before the call */
+  /* image step (run_image_mc, dust_transfer.f90:692-824): lmono0 with the rt2 accumulator */
+  int32_t loutput_mc;       /* MC image maps (STOKEI..., output.f90:396-570): must be 0 (not implemented) */
+  int32_t n_theta_I, n_phi_I;   /* angular bins of I_spec (15 x 15, dust_ray_tracing.f90:104-105) */
 } mcb_run_params;
 
 /* ------------------------------------------------------------------------
@@ -203,6 +206,9 @@ typedef struct mcb_tallies {
   double  *sed_star, *sed_star_scat, *sed_disk, *sed_disk_scat;      /* output.f90:573-589 */
   float   *xI_scatt;         /* (45, 2, N_type_flux, RT_n_incl*RT_n_az, n_cells) real, dust_ray_tracing.f90:33 */
   int32_t  N_type_flux;      /* 1, 4 (pola), 5/8 (contrib) as in the reference */
+  /* rt2 accumulators (radiation_field.f90:91-130), `real` like the reference: */
+  float   *I_spec;           /* (N_type_flux, n_theta_I, n_phi_I, n_cells)   dust_ray_tracing.f90:44 */
+  float   *I_spec_star;      /* (n_cells)                                    dust_ray_tracing.f90:45 */
   /* diagnostics (not in the reference): */
   double  *stats;            /* [8]: packets, cell-steps, interactions, scatterings,
                                 absorptions, killed, escaped, dark-zone bounces */

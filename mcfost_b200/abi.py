@@ -93,6 +93,7 @@ class mcb_run_params(C.Structure):
         ("tab_u_rt", c_double_p), ("tab_v_rt", c_double_p), ("tab_w_rt", c_double_p),
         ("seed", C.c_uint64), ("call_index", C.c_uint32),
         ("rank", C.c_int32), ("n_ranks", C.c_int32), ("reset_tallies", C.c_int32),
+        ("loutput_mc", C.c_int32), ("n_theta_I", C.c_int32), ("n_phi_I", C.c_int32),
     ]
 
 
@@ -105,6 +106,7 @@ class mcb_tallies(C.Structure):
         ("sed_star", c_double_p), ("sed_star_scat", c_double_p),
         ("sed_disk", c_double_p), ("sed_disk_scat", c_double_p),
         ("xI_scatt", c_float_p), ("N_type_flux", C.c_int32),
+        ("I_spec", c_float_p), ("I_spec_star", c_float_p),
         ("stats", c_double_p),
     ]
 
@@ -220,7 +222,8 @@ def make_run(**kw) -> Holder:
              l_sym_centrale=1, l_sym_axiale=1, lonly_LTE=1, lxJ_abs_step1=0, lxJ_abs=0,
              N_thet=10, N_phi=1, capt_sup=2, RT_n_incl=0, RT_n_az=0,
              tab_u_rt=None, tab_v_rt=None, tab_w_rt=None,
-             seed=269753, call_index=0, rank=0, n_ranks=1, reset_tallies=1)
+             seed=269753, call_index=0, rank=0, n_ranks=1, reset_tallies=1,
+             loutput_mc=0, n_theta_I=15, n_phi_I=15)
     unknown = set(kw) - set(d)
     if unknown:
         raise TypeError(f"unknown run parameter(s): {sorted(unknown)}")
@@ -240,7 +243,7 @@ def make_run(**kw) -> Holder:
 class Tallies:
     """Caller-allocated tally arrays (shapes of the reference minus the nb_proc dim)."""
 
-    def __init__(self, n_cells, n_lambda, N_thet=10, N_phi=1, xJ=False, n_xI=0):
+    def __init__(self, n_cells, n_lambda, N_thet=10, N_phi=1, xJ=False, n_xI=0, n_Ispec=0):
         self.xKJ_abs = np.zeros(n_cells, np.float64)
         self.xJ_abs = np.zeros((n_cells, n_lambda), np.float64, order="F") if xJ else None
         self.xT_ech = np.zeros(n_cells, np.int32)
@@ -250,6 +253,8 @@ class Tallies:
                      "sed_disk", "sed_disk_scat"):
             setattr(self, name, np.zeros(shp, np.float64, order="F"))
         self.xI_scatt = np.zeros(n_xI, np.float32) if n_xI else None
+        self.I_spec = np.zeros(n_Ispec, np.float32) if n_Ispec else None
+        self.I_spec_star = np.zeros(n_cells, np.float32) if n_Ispec else None
         self.stats = np.zeros(8, np.float64)
         t = mcb_tallies()
         for name in ("xKJ_abs", "xJ_abs", "n_phot_envoyes", "sed", "sed_q", "sed_u", "sed_v", "n_phot_sed",
@@ -257,6 +262,8 @@ class Tallies:
             setattr(t, name, ptr(getattr(self, name), np.float64))
         t.xT_ech = ptr(self.xT_ech, np.int32)
         t.xI_scatt = ptr(self.xI_scatt, np.float32)
+        t.I_spec = ptr(self.I_spec, np.float32)
+        t.I_spec_star = ptr(self.I_spec_star, np.float32)
         t.N_type_flux = 0
         self.struct = t
 

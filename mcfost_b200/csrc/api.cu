@@ -271,7 +271,7 @@ __global__ void fill_int_kernel(int* p, int64_t n, int v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-static int setup_tallies(mcb_handle* h, const mcb_run_params* r, bool lxJ, bool rt1, int n_type_flux) {
+static int setup_tallies(mcb_handle* h, const mcb_run_params* r, bool lxJ, bool rt1, int n_type_flux, bool rt2) {
   DevModel& m = h->m;
   const int n_sed = m.n_lambda * r->N_thet * r->N_phi;
   bool realloc_ = (h->n_tally == 0) || (h->lay_xJ != lxJ) || (h->lay_nsed != n_sed);
@@ -291,11 +291,17 @@ static int setup_tallies(mcb_handle* h, const mcb_run_params* r, bool lxJ, bool 
   const int64_t n_xI = rt1 ? (int64_t)N_AZ_RT * 2 * n_type_flux * n_rt * m.n_cells : 0;
   if (n_xI != h->n_xI) realloc_ = true;
   if ((rc = reserve(h, "xI", (size_t)n_xI, &m.xI))) return rc;
+  const int64_t n_Is = rt2 ? (int64_t)n_type_flux * r->n_theta_I * r->n_phi_I * m.n_cells : 0;
+  if (n_Is != h->n_Ispec) realloc_ = true;
+  if ((rc = reserve(h, "I_spec", (size_t)n_Is, &m.I_spec))) return rc;
+  if ((rc = reserve(h, "I_spec_star", (size_t)(rt2 ? m.n_cells : 0), &m.I_spec_star))) return rc;
+  h->n_Ispec = n_Is;
   if ((rc = reserve(h, "work", (size_t)(16 + 2 * r->n_photons_loop), &m.work))) return rc;
   h->n_tally = L.total; h->n_xI = n_xI; h->lay_xJ = lxJ; h->lay_nsed = n_sed; h->n_type_flux = n_type_flux;
   if (realloc_ || r->reset_tallies) {
     CK(cudaMemsetAsync(m.tally, 0, (size_t)L.total * sizeof(double), h->stream));
     if (n_xI) CK(cudaMemsetAsync(m.xI, 0, (size_t)n_xI * sizeof(float), h->stream));
+    if (n_Is) { CK(cudaMemsetAsync(m.I_spec, 0, (size_t)n_Is * sizeof(float), h->stream)); CK(cudaMemsetAsync(m.I_spec_star, 0, (size_t)m.n_cells * sizeof(float), h->stream)); }
     fill_int_kernel<<<256, 256, 0, h->stream>>>(m.xT_ech, m.n_cells, 2);      // xT_ech = 2, thermal_emission.f90:119,2164
   }
   CK(cudaMemsetAsync(m.work, 0, (size_t)(16 + 2 * r->n_photons_loop) * sizeof(unsigned long long), h->stream));
@@ -314,8 +320,9 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   // ---- modes this library implements; everything else fails loudly ----
   if (r->lscattering_method1) return fail(h, MCB_ERR_UNSUPPORTED, "scattering method 1 (per-grain) not implemented");
   if (!r->lonly_LTE) return fail(h, MCB_ERR_UNSUPPORTED, "nLTE / nRE re-emission not implemented");
-  if (r->lscatt_ray_tracing2) return fail(h, MCB_ERR_UNSUPPORTED, "rt2 (I_spec) accumulator not implemented");
-  if (r->lmono0) return fail(h, MCB_ERR_UNSUPPORTED, "MC image mode (STOKEI maps) not implemented");
+  if (r->loutput_mc) return fail(h, MCB_ERR_UNSUPPORTED, "MC image maps (STOKEI..., loutput_mc) not implemented");
+  if (r->lscatt_ray_tracing2 && (m.l3D || h->gk == GK_VOR)) return fail(h, MCB_ERR_UNSUPPORTED, "rt2 is 2D only (radiation_field.f90:91)");
+  if (r->lscatt_ray_tracing2 && (r->n_theta_I < 1 || r->n_phi_I < 1)) return fail(h, MCB_ERR_BAD_ARG, "n_theta_I / n_phi_I");
   if (r->n_photons_loop < 1 || r->nnfot1_start < 1 || r->n_photons2 < 0) return fail(h, MCB_ERR_BAD_ARG, "bad packet budget");
   if (r->lambda_in < 1 || r->lambda_in > m.n_lambda || r->p_lambda_in < 1 || r->p_lambda_in > m.p_n_lambda_pos) return fail(h, MCB_ERR_BAD_ARG, "lambda index out of range");
   if (r->n_ranks < 1 || r->rank < 0 || r->rank >= r->n_ranks) return fail(h, MCB_ERR_BAD_ARG, "bad rank / n_ranks");
@@ -337,6 +344,8 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   dr.lmethod_aniso1 = r->lmethod_aniso1; dr.lisotropic = r->lisotropic;
   dr.l_sym_centrale = r->l_sym_centrale; dr.l_sym_axiale = r->l_sym_axiale;
   dr.rt1 = rt1;
+  dr.rt2 = ((!r->letape_th) && !rt1 && r->lscatt_ray_tracing2) ? 1 : 0;
+  dr.lmono0 = r->lmono0; dr.n_theta_I = r->n_theta_I; dr.n_phi_I = r->n_phi_I;
   dr.lxJ = r->letape_th ? r->lxJ_abs_step1 : r->lxJ_abs;
   dr.N_thet = r->N_thet; dr.N_phi = r->N_phi; dr.capt_sup = r->capt_sup;
   dr.n_stokes = r->lsepar_pola ? 4 : 1;
@@ -358,7 +367,7 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   dr.n_packets_total = dr.count_sent ? (unsigned long long)n_local * dr.n_per_chunk : 0ull;
   dr.nb_proc_equiv = (double)r->n_ranks;
   { const char* e = getenv("MCB_DEBUG_ABORT_DRY"); dr.debug_abort_dry = (e && e[0] == '1') ? 1 : 0; }   // profiling aid only: tallies are incomplete
-  int rc = setup_tallies(h, r, dr.lxJ != 0, rt1, dr.n_type_flux);
+  int rc = setup_tallies(h, r, dr.lxJ != 0, rt1, dr.n_type_flux, dr.rt2 != 0);
   if (rc) return rc;
   if (n_local == 0 || (dr.count_sent && dr.n_packets_total == 0)) { CK(cudaEventRecord(h->ev0, h->stream)); CK(cudaEventRecord(h->ev1, h->stream)); h->launched = true; return MCB_OK; }
   if (h->kf_dark_stale) {
@@ -419,6 +428,8 @@ int mcfost_b200_download(mcb_handle* h, const mcb_run_params* r, mcb_tallies* ou
   CK(get(out->stats, L.stats, 8));
   if (out->xT_ech) CK(cudaMemcpyAsync(out->xT_ech, m.xT_ech, (size_t)m.n_cells * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (out->xI_scatt && h->n_xI) CK(cudaMemcpyAsync(out->xI_scatt, m.xI, (size_t)h->n_xI * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (out->I_spec && h->n_Ispec) CK(cudaMemcpyAsync(out->I_spec, m.I_spec, (size_t)h->n_Ispec * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (out->I_spec_star && h->n_Ispec) CK(cudaMemcpyAsync(out->I_spec_star, m.I_spec_star, (size_t)m.n_cells * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   out->N_type_flux = h->n_type_flux;
   CK(cudaStreamSynchronize(h->stream));
   (void)r;

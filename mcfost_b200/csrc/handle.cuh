@@ -22,7 +22,7 @@ struct mcb_handle {
   bool has_grid = false, has_op = false, has_em = false, launched = false;
   std::map<std::string, void*> bufs;      // named device allocations
   std::map<std::string, size_t> buf_bytes;
-  int64_t n_tally = 0, n_xI = 0;
+  int64_t n_tally = 0, n_xI = 0, n_Ispec = 0;
   bool lay_xJ = false;
   int lay_nsed = -1;
   int n_photons_loop_alloc = 0;

@@ -84,6 +84,7 @@ struct DevModel {
   TallyLayout lay;
   int *xT_ech;              // (n_cells)
   float *xI;                // xI_scatt
+  float *I_spec, *I_spec_star;   // rt2 accumulators (dust_ray_tracing.f90:44-45)
   double *quv;              // Stokes Q,U,V of the packets in flight: (n_blocks, 3, NP), only with lsepar_pola
   unsigned long long *work; // [0] = next work item; [2+2c], [3+2c] = sent / received of local chunk c
   SmemLayout sm;
@@ -95,6 +96,7 @@ struct DevRun {
   float n_phot_lim;
   int letape_th, lmono, lsepar_pola, lsepar_contrib, lmethod_aniso1, lisotropic;
   int l_sym_centrale, l_sym_axiale, rt1, lxJ;
+  int rt2, lmono0, n_theta_I, n_phi_I;
   int N_thet, N_phi, capt_sup, n_type_flux, n_stokes;
   int n_rt, RT_n_incl, RT_n_az;
   double rt_u[MAX_RT], rt_v[MAX_RT], rt_w[MAX_RT];

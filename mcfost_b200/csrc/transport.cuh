@@ -292,6 +292,7 @@ __device__ __noinline__ int capteur(int lambda, double u1, double v1, double w1,
   } else {
     if (w1 != 1.0) c_phi = (int)(fmodulo(atan2(u1, v1) + MCB_PI / 2, 2 * MCB_PI) / (2 * MCB_PI) * r.N_phi) + 1;
   }
+  if (r.lmono0) return capt;          // lmono0 .and. .not.loutput_mc: no MC map is kept (output.f90:360)
   if (c_phi == r.N_phi + 1) c_phi = r.N_phi; else if (c_phi == 0) c_phi = 1;
   const int64_t ix = (lambda - 1) + (int64_t)m.n_lambda * ((capt - 1) + (int64_t)r.N_thet * (c_phi - 1));
   double* sed = m.tally + m.lay.sed;
@@ -375,6 +376,23 @@ __device__ __noinline__ void deposit_rt1(int idx, int p_icell, int p_lambda, dou
       if (r.lsepar_contrib) atomicAdd(m.xI + base + stride * (size_t)(flag_star ? 5 : 7), (float)(l * R0));
     }
   }
+}
+
+// ---- radiation_field.f90:91-130: rt2 specific intensity I_spec (2D only), fp32 reductions ----
+template <int BANK>
+__device__ __noinline__ void deposit_rt2(int idx, double l, const double* S, bool flag_star, bool flag_direct_star,
+                                         double xm, double ym, double zm, double u, double v, double w) {
+  const DevModel& m = c_m; const DevRun& r = c_r;
+  if (flag_direct_star) { atomicAdd(m.I_spec_star + idx, (float)(l * S[0])); return; }
+  const double phi_pos = atan2(xm, ym);
+  const double phi_vol = atan2(-u, -v) + MCB_TWO_PI;
+  int phi_I = (int)floor(fmodulo(phi_vol - phi_pos, MCB_TWO_PI) / MCB_TWO_PI * r.n_phi_I) + 1;
+  if (phi_I > r.n_phi_I) phi_I = 1;
+  int theta_I = (int)floor(0.5 * ((zm > 0.0 ? w : -w) + 1.0) * r.n_theta_I) + 1;
+  if (theta_I > r.n_theta_I) theta_I = r.n_theta_I;
+  float* base = m.I_spec + (size_t)r.n_type_flux * ((size_t)(theta_I - 1) + (size_t)r.n_theta_I * ((size_t)(phi_I - 1) + (size_t)r.n_phi_I * (size_t)idx));
+  for (int is = 0; is < r.n_stokes; ++is) atomicAdd(base + is, (float)(l * S[is]));
+  if (r.lsepar_contrib) atomicAdd(base + r.n_stokes + (flag_star ? 1 : 3), (float)(l * S[0]));
 }
 
 // =============================================================================
@@ -722,6 +740,14 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
           if (POLA) { S[1] = QUV(0, slot); S[2] = QUV(1, slot); S[3] = QUV(2, slot); }
           deposit_rt1<BANK>(idx, p_icell, r.p_lambda_in, l_contrib, S, misc_star(misc),
                       0.5 * (x0 + x1), 0.5 * (y0 + y1), 0.5 * (z0 + z1), rt1);
+        } else if (r.rt2) {
+          double x1, y1, z1;
+          G::exit_point(h, x0, y0, z0, u, v, w, x1, y1, z1);
+          double S[4] = {S0, 0.0, 0.0, 0.0};
+          if (POLA) { S[1] = QUV(0, slot); S[2] = QUV(1, slot); S[3] = QUV(2, slot); }
+          // flag_direct_star == stellar packet that has not interacted yet (dust_transfer.f90:1189-1193,1262)
+          deposit_rt2<BANK>(idx, l_contrib, S, misc_star(misc), misc_star(misc) && !misc_scatt(misc),
+                            0.5 * (x0 + x1), 0.5 * (y0 + y1), 0.5 * (z0 + z1), u, v, w);
         }
       }
     }

@@ -92,10 +92,10 @@ class Oracle:
         return ci, cj, ck, le
 
     # ---- mc_photon_loop ---------------------------------------------------
-    def run(self, n_threads=0, rec=None, n_xI=0, xJ=False, **params):
+    def run(self, n_threads=0, rec=None, n_xI=0, xJ=False, n_Ispec=0, **params):
         r = abi.make_run(**params)
         P = self.P
-        t = abi.Tallies(P.n_cells, P.n_lambda, r.struct.N_thet, r.struct.N_phi, xJ=xJ, n_xI=n_xI)
+        t = abi.Tallies(P.n_cells, P.n_lambda, r.struct.N_thet, r.struct.N_phi, xJ=xJ, n_xI=n_xI, n_Ispec=n_Ispec)
         rec_a = None if rec is None else np.ascontiguousarray(rec, np.float64)
         self._check(self.lib.oracle_run(self.h, r.ref(), t.ref(), int(n_threads), _p(rec_a),
                                         0 if rec_a is None else len(rec_a)))

@@ -82,6 +82,7 @@ struct ThreadTallies {
   std::vector<double> n_phot_envoyes;
   std::vector<double> sed[9];       // sed, q, u, v, n_phot_sed, star, star_scat, disk, disk_scat
   std::vector<float>  xI_scatt;
+  std::vector<float>  I_spec, I_spec_star;      // rt2, dust_ray_tracing.f90:44-45
   // per-thread scratch of angles_scatt_rt1 (dust_ray_tracing.f90: itheta_rt1 etc.)
   std::vector<int> itheta_rt1;
   std::vector<double> cos_omega_rt1, sin_omega_rt1;
@@ -1065,7 +1066,7 @@ struct Oracle {
   // radiation_field.f90:31-135  save_radiation_field  (rt2 branch: unsupported)
   // =====================================================================
   void save_radiation_field(ThreadTallies& t, int lambda, int p_lambda, int icell, const double* Stokes, double l,
-                            double x0, double y0, double z0, double x1, double y1, double z1, double, double, double, bool flag_star, bool) {
+                            double x0, double y0, double z0, double x1, double y1, double z1, double u, double v, double w, bool flag_star, bool flag_direct_star) {
     int p_icell = lvariable_dust() ? icell : 1;
     if (r.letape_th) {
       t.xKJ_abs[icell - 1] += kappa_abs_LTE(p_icell, lambda) * l * Stokes[0];      // lRE_LTE
@@ -1084,6 +1085,27 @@ struct Oracle {
         }
         if (r.lsepar_pola) calc_xI_scatt_pola(t, p_lambda, icell, phi_k, psup, l, Stokes, flag_star);
         else calc_xI_scatt(t, p_lambda, icell, phi_k, psup, l, Stokes[0], flag_star);
+      } else if (r.lscatt_ray_tracing2) {       // :91-130, only 2D
+        if (flag_direct_star) {
+          float& a = t.I_spec_star[icell - 1];
+          a = (float)((double)a + l * Stokes[0]);
+        } else {
+          const int n_phi_I = r.n_phi_I, n_theta_I = r.n_theta_I;
+          double xm = 0.5 * (x0 + x1), ym = 0.5 * (y0 + y1), zm = 0.5 * (z0 + z1);
+          double phi_pos = std::atan2(xm, ym);
+          double phi_vol = std::atan2(-u, -v) + two_pi;
+          int phi_I = (int)std::floor(fmodulo(phi_vol - phi_pos, two_pi) / two_pi * n_phi_I) + 1;
+          if (phi_I > n_phi_I) phi_I = 1;
+          int theta_I;
+          if (zm > 0.0) theta_I = (int)std::floor(0.5 * (w + 1.0) * n_theta_I) + 1;
+          else theta_I = (int)std::floor(0.5 * (-w + 1.0) * n_theta_I) + 1;
+          if (theta_I > n_theta_I) theta_I = n_theta_I;
+          auto at = [&](int itype) -> float& {
+            return t.I_spec[(size_t)(itype - 1) + (size_t)N_type_flux * ((size_t)(theta_I - 1) + (size_t)n_theta_I * ((size_t)(phi_I - 1) + (size_t)n_phi_I * (size_t)(icell - 1)))];
+          };
+          for (int is = 1; is <= n_Stokes; ++is) { float& a = at(is); a = (float)((double)a + l * Stokes[is - 1]); }
+          if (r.lsepar_contrib) { float& b = at(n_Stokes + (flag_star ? 2 : 4)); b = (float)((double)b + l * Stokes[0]); }
+        }
       }
     }
   }
@@ -1381,6 +1403,7 @@ struct Oracle {
     } else {
       if (w1 == 1.0) c_phi = 1; else c_phi = (int)(fmodulo(std::atan2(u1, v1) + pi / 2, 2 * pi) / (2 * pi) * r.N_phi) + 1;
     }
+    if (r.lmono0) return capt;          // lmono0 .and. .not.loutput_mc: no MC map is kept (output.f90:360)
     if (c_phi == (r.N_phi + 1)) c_phi = r.N_phi; else if (c_phi == 0) c_phi = 1;
     size_t ix = (size_t)(lambda - 1) + (size_t)o.n_lambda * ((size_t)(capt - 1) + (size_t)r.N_thet * (c_phi - 1));
     t.sed[0][ix] += stok[0]; t.sed[1][ix] += stok[1]; t.sed[2][ix] += stok[2]; t.sed[3][ix] += stok[3];
@@ -1402,6 +1425,8 @@ struct Oracle {
     size_t nsed = (size_t)o.n_lambda * r.N_thet * r.N_phi;
     size_t nxI = need_xI ? (size_t)n_az_rt * 2 * N_type_flux * r.RT_n_incl * r.RT_n_az * g.n_cells : 0;
     size_t nrt = (size_t)std::max(1, r.RT_n_incl * r.RT_n_az);
+    const bool need_I = (!r.letape_th) && r.lscatt_ray_tracing2;
+    size_t nI = need_I ? (size_t)N_type_flux * r.n_theta_I * r.n_phi_I * g.n_cells : 0;
     if ((int)T.size() != nthreads) { T.clear(); T.resize(nthreads); reset = true; }
     for (auto& t : T) {
       if (reset || t.xKJ_abs.size() != (size_t)g.n_cells) {
@@ -1411,10 +1436,12 @@ struct Oracle {
         for (auto& s : t.sed) s.assign(nsed, 0.0);
         t.xJ_abs.assign(need_xJ ? (size_t)g.n_cells * o.n_lambda : 0, 0.0);
         t.xI_scatt.assign(nxI, 0.0f);
+        t.I_spec.assign(nI, 0.0f); t.I_spec_star.assign(need_I ? g.n_cells : 0, 0.0f);
         for (double& s : t.stats) s = 0;
       }
       if (t.xJ_abs.size() != (need_xJ ? (size_t)g.n_cells * o.n_lambda : 0)) t.xJ_abs.assign(need_xJ ? (size_t)g.n_cells * o.n_lambda : 0, 0.0);
       if (t.xI_scatt.size() != nxI) t.xI_scatt.assign(nxI, 0.0f);
+      if (t.I_spec.size() != nI) { t.I_spec.assign(nI, 0.0f); t.I_spec_star.assign(need_I ? g.n_cells : 0, 0.0f); }
       if (t.sed[0].size() != nsed) for (auto& s : t.sed) s.assign(nsed, 0.0);
       t.itheta_rt1.assign(nrt, 1); t.cos_omega_rt1.assign(nrt, 0.0); t.sin_omega_rt1.assign(nrt, 0.0);
     }
@@ -1491,6 +1518,11 @@ struct Oracle {
       for (size_t i = 0; i < n; ++i) { float s = 0; for (auto& t : T) s += t.xI_scatt[i]; out->xI_scatt[i] = s; }   // sum(xI_scatt(...,:)) fp32, dust_ray_tracing.f90:689
       out->N_type_flux = N_type_flux;
     }
+    if (out->I_spec && !T[0].I_spec.empty()) {
+      for (size_t i = 0; i < T[0].I_spec.size(); ++i) { float s = 0; for (auto& t : T) s += t.I_spec[i]; out->I_spec[i] = s; }
+      for (size_t i = 0; i < T[0].I_spec_star.size(); ++i) { float s = 0; for (auto& t : T) s += t.I_spec_star[i]; out->I_spec_star[i] = s; }
+      out->N_type_flux = N_type_flux;
+    }
     if (out->stats) for (int a = 0; a < 8; ++a) { double s = 0; for (auto& t : T) s += t.stats[a]; out->stats[a] = s; }
   }
 };
@@ -1539,7 +1571,7 @@ int oracle_set_emission(void* h, const mcb_emission* e) { Oracle* O = (Oracle*)h
 
 static int check_run(Oracle* O, const mcb_run_params* r) {
   if (!O->has_grid || !O->has_op || !O->has_em) { snprintf(O->err, sizeof O->err, "run before uploads"); return MCB_ERR_STATE; }
-  if (r->lscattering_method1 || !r->lonly_LTE || r->lscatt_ray_tracing2 || r->lmono0) { snprintf(O->err, sizeof O->err, "mode not built in the oracle"); return MCB_ERR_UNSUPPORTED; }
+  if (r->lscattering_method1 || !r->lonly_LTE || r->loutput_mc || (r->lscatt_ray_tracing2 && O->g.l3D)) { snprintf(O->err, sizeof O->err, "mode not built in the oracle"); return MCB_ERR_UNSUPPORTED; }
   return MCB_OK;
 }
 

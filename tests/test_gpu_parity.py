@@ -348,3 +348,26 @@ def test_full_size_3d_grid_properties():
     e = t.xKJ_abs.reshape((72, 100, 100))          # (k, j-row, i)
     top, bot = e[:, 50:, :].sum(), e[:, :50, :].sum()
     assert abs(top / bot - 1) < 0.05
+
+
+@pytest.mark.parametrize("pola", [False, True])
+def test_image_step_rt2_matches_oracle(pola):
+    """run_image_mc's call (dust_transfer.f90:758): lmono0, fixed packet count, rt2 accumulators I_spec /
+    I_spec_star (radiation_field.f90:91-130); no feedback, so trajectories match the oracle packet by packet."""
+    P = small_problems()["cyl2D"]()
+    kw = dict(letape_th=0, lmono=1, lmono0=1, lscatt_ray_tracing2=1, lsepar_pola=int(pola), lsepar_contrib=1)
+    ntf = (4 if pola else 1) + 4
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(8, 8, 300, 1.0e30, 1, False, **kw)
+    G.close()
+    to = Oracle(P).run(n_threads=0, n_Ispec=ntf * 15 * 15 * P.n_cells, lambda_in=8, p_lambda_in=8, n_photons2=300, **kw)
+    assert tg.stats[0] == to.stats[0] == 128 * 300
+    assert tg.sed.sum() == 0 and to.sed.sum() == 0                        # image mode keeps no SED (output.f90:360)
+    assert abs(tg.stats[1] - to.stats[1]) <= 1e-4 * to.stats[1]
+    Ig = tg.I_spec.reshape((ntf, 15, 15, P.n_cells), order="F"); Io = to.I_spec.reshape((ntf, 15, 15, P.n_cells), order="F")
+    assert Io[0].sum() > 0 and to.I_spec_star.sum() > 0
+    assert np.allclose(tg.I_spec_star.sum(), to.I_spec_star.sum(), rtol=2e-3)
+    assert np.allclose(Ig.sum(axis=(1, 2, 3)), Io.sum(axis=(1, 2, 3)), rtol=5e-3, atol=1e-6 * np.abs(Io).sum())
+    assert np.allclose(Ig[0].sum(axis=(1, 2)), Io[0].sum(axis=(1, 2)), rtol=0.01, atol=1e-4 * Io[0].sum())   # (theta_I) profile
+    bright = Io[0].sum(axis=(0, 1)) > 0.01 * Io[0].sum(axis=(0, 1)).max()
+    assert np.allclose(Ig[0].sum(axis=(0, 1))[bright], Io[0].sum(axis=(0, 1))[bright], rtol=0.02)
