@@ -130,6 +130,43 @@ typedef struct mcb_opacity {
 } mcb_opacity;
 
 /* ------------------------------------------------------------------------
+ * Per-grain tables: scattering method 1 (dust_transfer.f90:1291-1317) and the
+ * nLTE / qRE re-emission branches (dust_transfer.f90:1353-1395,
+ * thermal_emission.f90:775-866,1441-1514,1953-2040).  Any pointer may be NULL
+ * when the mode that reads it is off.  Grain indices are 1-based and global
+ * (1..n_grains_tot); tables allocated on a sub-range of grains by the reference
+ * (grain_RE_nLTE_start:grain_RE_nLTE_end, grain_nRE_start:grain_nRE_end) cross
+ * with exactly that extent.
+ * --------------------------------------------------------------------- */
+typedef struct mcb_grains {
+  int32_t n_grains_tot;
+  int32_t n_dens;                  /* first extent of dust_density_o_n_grains: n_grains_tot if lvariable_dust else n_zones (mem.f90:35-39) */
+  int32_t grain_RE_LTE_start, grain_RE_LTE_end;     /* grains.f90:36 */
+  int32_t grain_RE_nLTE_start, grain_RE_nLTE_end;
+  int32_t grain_nRE_start, grain_nRE_end;
+  const int32_t *grain_zone;       /* (n_grains_tot) grain(k)%zone */
+  const double  *n_grains;         /* (n_grains_tot) grains.f90:38 */
+  const double  *dust_density_o_n_grains;  /* (n_dens, n_cells) density.f90:32 */
+  const float   *C_abs, *C_abs_norm, *C_sca, *tab_g;   /* (n_grains_tot, n_lambda) grains.f90:54 */
+  /* scattering method 1 */
+  const float   *prob_s11;         /* (n_lambda, n_grains_tot, 0:180) mem.f90:108 */
+  const float   *tab_s11, *tab_s12, *tab_s22, *tab_s33, *tab_s34, *tab_s44;  /* (0:180, n_grains_tot, n_lambda) mem.f90:84-104 */
+  const double  *ksca_CDF;         /* (0:n_grains_tot, p_n_cells, n_lambda) mem.f90:251; NULL if low_mem_scattering */
+  /* RE - nLTE grains */
+  const double  *kappa_abs_nLTE;   /* (p_n_cells, n_lambda) dust_prop.f90:20 */
+  const double  *kabs_nLTE_CDF;    /* (grain_RE_nLTE_start-1:grain_RE_nLTE_end, n_cells, n_lambda) thermal_emission.f90:147 */
+  const double  *log_E_em_1grain;  /* (grain_RE_nLTE_start:grain_RE_nLTE_end, n_T) :159 */
+  const double  *kdB_dT_1grain_nLTE_CDF;   /* (n_lambda, nLTE grains, n_T) :155 */
+  /* nRE grains that reached quasi radiative equilibrium */
+  const double  *kappa_abs_RE;     /* (n_cells, n_lambda) mem.f90:201 */
+  const double  *proba_abs_RE, *Proba_abs_RE_LTE, *Proba_abs_RE_LTE_p_nLTE;   /* (n_cells, n_lambda) dust_prop.f90:21 */
+  const double  *log_E_em_1grain_nRE;      /* (grain_nRE_start:grain_nRE_end, n_T) */
+  const double  *kdB_dT_1grain_nRE_CDF;    /* (n_lambda, nRE grains, n_T) :190 */
+  const int32_t *l_RE;             /* (grain_nRE_start:grain_nRE_end, n_cells) logical, :304 */
+  const double  *J0;               /* (n_cells, n_lambda) radiation_field.f90:154 */
+} mcb_grains;
+
+/* ------------------------------------------------------------------------
  * Emission tables (repartition_energie thermal_emission.f90:1771,
  * repartition_wl_em :315, stars.f90:495-605).  Re-uploaded whenever the
  * Fortran side recomputes them (each temperature iteration / wavelength).
@@ -164,11 +201,11 @@ typedef struct mcb_run_params {
   int32_t letape_th, lmono, lmono0;
   int32_t lscatt_ray_tracing1, lscatt_ray_tracing2;
   int32_t lsepar_pola, lsepar_contrib;
-  int32_t lscattering_method1;   /* must be 0 (method 2) for now */
+  int32_t lscattering_method1;   /* 1: per-grain scattering (needs mcfost_b200_upload_grains) */
   int32_t lmethod_aniso1;        /* 1: tabulated s11 (Mie), 0: HG */
   int32_t lisotropic;
   int32_t l_sym_centrale, l_sym_axiale;
-  int32_t lonly_LTE;             /* must be 1 for now */
+  int32_t lonly_LTE;             /* init_mcfost.f90:1880-1883; 0 needs mcfost_b200_upload_grains */
   int32_t lxJ_abs_step1;         /* xJ_abs tally during the thermal step */
   int32_t lxJ_abs;               /* xJ_abs tally during SED step */
   /* detectors (read_param.f90:180-184) */
@@ -190,6 +227,10 @@ typedef struct mcb_run_params {
   /* image step (run_image_mc, dust_transfer.f90:692-824): lmono0 with the rt2 accumulator */
   int32_t loutput_mc;       /* MC image maps (STOKEI..., output.f90:396-570): must be 0 (not implemented) */
   int32_t n_theta_I, n_phi_I;   /* angular bins of I_spec (15 x 15, dust_ray_tracing.f90:104-105) */
+  /* grain heating regimes (parameters.f90; lonly_* derived in init_mcfost.f90:1880-1883) */
+  int32_t lonly_nLTE, lRE_nLTE, lnRE;
+  int32_t low_mem_th_emission_nLTE;   /* 1: select_absorbing_grain instead of kabs_nLTE_CDF */
+  int32_t low_mem_scattering;         /* method 1: 1 = on-the-fly CDF, 0 = ksca_CDF (dust_prop.f90:1292) */
 } mcb_run_params;
 
 /* ------------------------------------------------------------------------
@@ -212,6 +253,10 @@ typedef struct mcb_tallies {
   /* diagnostics (not in the reference): */
   double  *stats;            /* [8]: packets, cell-steps, interactions, scatterings,
                                 absorptions, killed, escaped, dark-zone bounces */
+  /* nLTE / qRE (thermal_emission.f90:49,60): in/out like xT_ech when reset_tallies = 0 */
+  int32_t *xT_ech_1grain;      /* (grain_RE_nLTE_start:grain_RE_nLTE_end, n_cells) */
+  int32_t *xT_ech_1grain_nRE;  /* (grain_nRE_start:grain_nRE_end, n_cells) */
+  double  *E_abs_nRE;          /* scalar, dust_transfer.f90:1357 */
 } mcb_tallies;
 
 /* ---- life cycle -------------------------------------------------------- */
@@ -225,6 +270,8 @@ int mcfost_b200_upload_grid(mcb_handle *h, const mcb_grid *g);
 int mcfost_b200_upload_dark_zone(mcb_handle *h, const int32_t *l_dark_zone);
 int mcfost_b200_upload_opacity(mcb_handle *h, const mcb_opacity *o);
 int mcfost_b200_upload_emission(mcb_handle *h, const mcb_emission *e);
+/* needs upload_grid and upload_opacity first (extents n_cells, n_lambda, n_T, p_n_cells) */
+int mcfost_b200_upload_grains(mcb_handle *h, const mcb_grains *g);
 
 /* The drop-in for mc_photon_loop: blocking; copies tallies D2H into `out`. */
 int mcfost_b200_run(mcb_handle *h, const mcb_run_params *r, mcb_tallies *out);

@@ -76,6 +76,31 @@ class mcb_emission(C.Structure):
     ]
 
 
+_GR_I32 = ("grain_zone", "l_RE")
+_GR_F32 = ("C_abs", "C_abs_norm", "C_sca", "tab_g", "prob_s11", "tab_s11", "tab_s12", "tab_s22", "tab_s33", "tab_s34", "tab_s44")
+
+
+class mcb_grains(C.Structure):
+    _fields_ = [
+        ("n_grains_tot", C.c_int32), ("n_dens", C.c_int32),
+        ("grain_RE_LTE_start", C.c_int32), ("grain_RE_LTE_end", C.c_int32),
+        ("grain_RE_nLTE_start", C.c_int32), ("grain_RE_nLTE_end", C.c_int32),
+        ("grain_nRE_start", C.c_int32), ("grain_nRE_end", C.c_int32),
+        ("grain_zone", c_int32_p), ("n_grains", c_double_p), ("dust_density_o_n_grains", c_double_p),
+        ("C_abs", c_float_p), ("C_abs_norm", c_float_p), ("C_sca", c_float_p), ("tab_g", c_float_p),
+        ("prob_s11", c_float_p),
+        ("tab_s11", c_float_p), ("tab_s12", c_float_p), ("tab_s22", c_float_p),
+        ("tab_s33", c_float_p), ("tab_s34", c_float_p), ("tab_s44", c_float_p),
+        ("ksca_CDF", c_double_p),
+        ("kappa_abs_nLTE", c_double_p), ("kabs_nLTE_CDF", c_double_p),
+        ("log_E_em_1grain", c_double_p), ("kdB_dT_1grain_nLTE_CDF", c_double_p),
+        ("kappa_abs_RE", c_double_p), ("proba_abs_RE", c_double_p),
+        ("Proba_abs_RE_LTE", c_double_p), ("Proba_abs_RE_LTE_p_nLTE", c_double_p),
+        ("log_E_em_1grain_nRE", c_double_p), ("kdB_dT_1grain_nRE_CDF", c_double_p),
+        ("l_RE", c_int32_p), ("J0", c_double_p),
+    ]
+
+
 class mcb_run_params(C.Structure):
     _fields_ = [
         ("lambda_in", C.c_int32), ("p_lambda_in", C.c_int32), ("n_photons2", C.c_int32),
@@ -94,6 +119,8 @@ class mcb_run_params(C.Structure):
         ("seed", C.c_uint64), ("call_index", C.c_uint32),
         ("rank", C.c_int32), ("n_ranks", C.c_int32), ("reset_tallies", C.c_int32),
         ("loutput_mc", C.c_int32), ("n_theta_I", C.c_int32), ("n_phi_I", C.c_int32),
+        ("lonly_nLTE", C.c_int32), ("lRE_nLTE", C.c_int32), ("lnRE", C.c_int32),
+        ("low_mem_th_emission_nLTE", C.c_int32), ("low_mem_scattering", C.c_int32),
     ]
 
 
@@ -108,6 +135,7 @@ class mcb_tallies(C.Structure):
         ("xI_scatt", c_float_p), ("N_type_flux", C.c_int32),
         ("I_spec", c_float_p), ("I_spec_star", c_float_p),
         ("stats", c_double_p),
+        ("xT_ech_1grain", c_int32_p), ("xT_ech_1grain_nRE", c_int32_p), ("E_abs_nRE", c_double_p),
     ]
 
 
@@ -213,6 +241,23 @@ def make_emission(P) -> Holder:
     return Holder(e, keep)
 
 
+def make_grains(P) -> Holder:
+    """Per-grain tables (scattering method 1, nLTE / qRE re-emission); absent attributes -> NULL."""
+    g = mcb_grains()
+    keep = {}
+    for name, ctype in mcb_grains._fields_:
+        if ctype is C.c_int32:
+            setattr(g, name, int(getattr(P, name, 0) or 0))
+            continue
+        dt = np.int32 if name in _GR_I32 else np.float32 if name in _GR_F32 else np.float64
+        a = getattr(P, name, None)
+        if a is not None:
+            a = farray(a, dt)
+            keep[name] = a
+        setattr(g, name, ptr(a, dt))
+    return Holder(g, keep)
+
+
 def make_run(**kw) -> Holder:
     """Run parameters with the reference's defaults for a thermal step
     (dust_transfer.f90:597-617, read_param.f90:145,180-184)."""
@@ -223,7 +268,8 @@ def make_run(**kw) -> Holder:
              N_thet=10, N_phi=1, capt_sup=2, RT_n_incl=0, RT_n_az=0,
              tab_u_rt=None, tab_v_rt=None, tab_w_rt=None,
              seed=269753, call_index=0, rank=0, n_ranks=1, reset_tallies=1,
-             loutput_mc=0, n_theta_I=15, n_phi_I=15)
+             loutput_mc=0, n_theta_I=15, n_phi_I=15,
+             lonly_nLTE=0, lRE_nLTE=0, lnRE=0, low_mem_th_emission_nLTE=0, low_mem_scattering=1)
     unknown = set(kw) - set(d)
     if unknown:
         raise TypeError(f"unknown run parameter(s): {sorted(unknown)}")
@@ -243,7 +289,7 @@ def make_run(**kw) -> Holder:
 class Tallies:
     """Caller-allocated tally arrays (shapes of the reference minus the nb_proc dim)."""
 
-    def __init__(self, n_cells, n_lambda, N_thet=10, N_phi=1, xJ=False, n_xI=0, n_Ispec=0):
+    def __init__(self, n_cells, n_lambda, N_thet=10, N_phi=1, xJ=False, n_xI=0, n_Ispec=0, n_nLTE=0, n_nRE=0):
         self.xKJ_abs = np.zeros(n_cells, np.float64)
         self.xJ_abs = np.zeros((n_cells, n_lambda), np.float64, order="F") if xJ else None
         self.xT_ech = np.zeros(n_cells, np.int32)
@@ -256,11 +302,17 @@ class Tallies:
         self.I_spec = np.zeros(n_Ispec, np.float32) if n_Ispec else None
         self.I_spec_star = np.zeros(n_cells, np.float32) if n_Ispec else None
         self.stats = np.zeros(8, np.float64)
+        self.xT_ech_1grain = np.zeros((n_nLTE, n_cells), np.int32, order="F") if n_nLTE else None
+        self.xT_ech_1grain_nRE = np.zeros((n_nRE, n_cells), np.int32, order="F") if n_nRE else None
+        self.E_abs_nRE = np.zeros(1, np.float64)
         t = mcb_tallies()
         for name in ("xKJ_abs", "xJ_abs", "n_phot_envoyes", "sed", "sed_q", "sed_u", "sed_v", "n_phot_sed",
                      "sed_star", "sed_star_scat", "sed_disk", "sed_disk_scat", "stats"):
             setattr(t, name, ptr(getattr(self, name), np.float64))
         t.xT_ech = ptr(self.xT_ech, np.int32)
+        t.xT_ech_1grain = ptr(self.xT_ech_1grain, np.int32)
+        t.xT_ech_1grain_nRE = ptr(self.xT_ech_1grain_nRE, np.int32)
+        t.E_abs_nRE = ptr(self.E_abs_nRE, np.float64)
         t.xI_scatt = ptr(self.xI_scatt, np.float32)
         t.I_spec = ptr(self.I_spec, np.float32)
         t.I_spec_star = ptr(self.I_spec_star, np.float32)
@@ -269,3 +321,10 @@ class Tallies:
 
     def ref(self):
         return C.byref(self.struct)
+
+
+def grain_tally_sizes(P, r):
+    """Extents of xT_ech_1grain / xT_ech_1grain_nRE for this run (thermal_emission.f90:163,186)."""
+    n1 = (P.grain_RE_nLTE_end - P.grain_RE_nLTE_start + 1) if (r.lRE_nLTE and hasattr(P, "grain_RE_nLTE_start")) else 0
+    n2 = (P.grain_nRE_end - P.grain_nRE_start + 1) if (r.lnRE and hasattr(P, "grain_nRE_start")) else 0
+    return dict(n_nLTE=int(n1), n_nRE=int(n2))

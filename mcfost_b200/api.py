@@ -24,7 +24,7 @@ LIB_PATH = os.environ.get("MCFOST_B200_LIB") or os.path.join(_HERE, "_lib", "lib
 EXPORTS = (
     "mcfost_b200_init", "mcfost_b200_finalize", "mcfost_b200_last_error",
     "mcfost_b200_upload_grid", "mcfost_b200_upload_dark_zone", "mcfost_b200_upload_opacity",
-    "mcfost_b200_upload_emission", "mcfost_b200_run", "mcfost_b200_launch", "mcfost_b200_sync",
+    "mcfost_b200_upload_emission", "mcfost_b200_upload_grains", "mcfost_b200_run", "mcfost_b200_launch", "mcfost_b200_sync",
     "mcfost_b200_tally_buffers", "mcfost_b200_download", "mcfost_b200_last_kernel_ms", "mcfost_b200_stream",
     "mcfost_b200_debug_counters",
     "mcfost_b200_cross_cell", "mcfost_b200_index_cell", "mcfost_b200_move_to_grid",
@@ -54,7 +54,7 @@ def load_library():
         lib.mcfost_b200_finalize.argtypes = [C.c_void_p]
         lib.mcfost_b200_finalize.restype = None
         for fn in ("mcfost_b200_upload_grid", "mcfost_b200_upload_dark_zone", "mcfost_b200_upload_opacity",
-                   "mcfost_b200_upload_emission", "mcfost_b200_launch"):
+                   "mcfost_b200_upload_emission", "mcfost_b200_upload_grains", "mcfost_b200_launch"):
             getattr(lib, fn).argtypes = [C.c_void_p, C.c_void_p]
         lib.mcfost_b200_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.mcfost_b200_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -99,6 +99,9 @@ class PhotonLoop:
         self._e = None
         if hasattr(P, "prob_E_cell"):
             self.upload_emission(P)
+        self._gr = None
+        if hasattr(P, "n_grains_tot"):
+            self.upload_grains(P)
         self._last_run = None
 
     def close(self):
@@ -125,6 +128,11 @@ class PhotonLoop:
         self._e = abi.make_emission(P)
         self._check(self.lib.mcfost_b200_upload_emission(self.h, self._e.ref()))
 
+    def upload_grains(self, P):
+        """Per-grain tables: scattering method 1 and the nLTE / qRE re-emission branches."""
+        self._gr = abi.make_grains(P)
+        self._check(self.lib.mcfost_b200_upload_grains(self.h, self._gr.ref()))
+
     # ---- the drop-in --------------------------------------------------------
     def _params(self, lambda_in, p_lambda_in, n_photons2, n_phot_lim, nnfot1_start, laffichage, flags):
         flags = dict(flags)
@@ -145,7 +153,8 @@ class PhotonLoop:
         if (not r.struct.letape_th) and r.struct.lscatt_ray_tracing2 and not r.struct.lscatt_ray_tracing1:
             ntf = (4 if r.struct.lsepar_pola else 1) + (4 if r.struct.lsepar_contrib else 0)
             n_Is = ntf * r.struct.n_theta_I * r.struct.n_phi_I * P.n_cells
-        return abi.Tallies(P.n_cells, P.n_lambda, r.struct.N_thet, r.struct.N_phi, xJ=xJ, n_xI=n_xI, n_Ispec=n_Is)
+        return abi.Tallies(P.n_cells, P.n_lambda, r.struct.N_thet, r.struct.N_phi, xJ=xJ, n_xI=n_xI, n_Ispec=n_Is,
+                           **abi.grain_tally_sizes(P, r.struct))
 
     def mc_photon_loop(self, lambda_in=1, p_lambda_in=1, n_photons2=1000, n_phot_lim=1.0e30, nnfot1_start=1,
                        laffichage=False, **flags):

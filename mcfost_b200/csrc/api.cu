@@ -208,6 +208,7 @@ int mcfost_b200_upload_opacity(mcb_handle* h, const mcb_opacity* o) {
   if ((rc = put(h, "s34", o->tab_s34_o_s11_pos, npos, &m.s34))) return rc;
   if ((rc = put(h, "s44", o->tab_s44_o_s11_pos, npos, &m.s44))) return rc;
   if ((rc = put(h, "logQ", o->log_Qcool_minus_extra_heating, (size_t)o->n_T * o->p_n_cells, &m.logQ))) return rc;
+  if ((rc = put(h, "tab_Temp", o->tab_Temp, (size_t)o->n_T, &m.tab_Temp))) return rc;
   if ((rc = put(h, "kdB", o->kdB_dT_CDF, (size_t)o->n_lambda * o->n_T * o->p_n_cells, &m.kdB))) return rc;
   // cos(k*pi/nang_scatt), k = 0..180, with the host libm (scattering.f90:1470-1471 evaluates
   // cos((real(k,dp)-1)*pi/real(nang_scatt,dp)) per event; tabulated once here)
@@ -235,6 +236,57 @@ int mcfost_b200_upload_emission(mcb_handle* h, const mcb_emission* e) {
   for (int a = 0; a < 3; ++a) m.cISM[a] = e->centre_ISM[a];
   CK(cudaStreamSynchronize(h->stream));
   h->has_em = true;
+  return MCB_OK;
+}
+
+int mcfost_b200_upload_grains(mcb_handle* h, const mcb_grains* g) {
+  if (!h || !g) return MCB_ERR_BAD_ARG;
+  if (!h->has_op) return fail(h, MCB_ERR_STATE, "upload_grains before upload_opacity");
+  CK(cudaSetDevice(h->device));
+  DevModel& m = h->m;
+  DevGrains& d = m.gr;
+  memset(&d, 0, sizeof d);
+  if (g->n_grains_tot < 1 || g->n_dens < 1 || !g->n_grains || !g->dust_density_o_n_grains) return fail(h, MCB_ERR_BAD_ARG, "grain tables missing");
+  if (m.p_n_cells != 1 && g->n_dens != g->n_grains_tot) return fail(h, MCB_ERR_BAD_ARG, "lvariable_dust needs dust_density_o_n_grains(n_grains_tot, n_cells)");
+  d.n_grains_tot = g->n_grains_tot; d.n_dens = g->n_dens;
+  d.LTE_s = g->grain_RE_LTE_start; d.LTE_e = g->grain_RE_LTE_end;
+  d.nLTE_s = g->grain_RE_nLTE_start; d.nLTE_e = g->grain_RE_nLTE_end;
+  d.nRE_s = g->grain_nRE_start; d.nRE_e = g->grain_nRE_end;
+  const size_t K = g->n_grains_tot, nl = m.n_lambda, nc = m.n_cells, nT = m.n_T;
+  const size_t k1 = d.nLTE_e >= d.nLTE_s && d.nLTE_s > 0 ? (size_t)(d.nLTE_e - d.nLTE_s + 1) : 0;
+  const size_t k2 = d.nRE_e >= d.nRE_s && d.nRE_s > 0 ? (size_t)(d.nRE_e - d.nRE_s + 1) : 0;
+  int rc;
+  if ((rc = put(h, "g_zone", g->grain_zone, K, &d.zone))) return rc;
+  if ((rc = put(h, "g_n_grains", g->n_grains, K, &d.n_grains))) return rc;
+  if ((rc = put(h, "g_dd", g->dust_density_o_n_grains, (size_t)g->n_dens * nc, &d.dd))) return rc;
+  if ((rc = put(h, "g_C_abs", g->C_abs, K * nl, &d.C_abs))) return rc;
+  if ((rc = put(h, "g_C_abs_norm", g->C_abs_norm, K * nl, &d.C_abs_norm))) return rc;
+  if ((rc = put(h, "g_C_sca", g->C_sca, K * nl, &d.C_sca))) return rc;
+  if ((rc = put(h, "g_tab_g", g->tab_g, K * nl, &d.tab_g))) return rc;
+  const size_t ns = (size_t)(NANG + 1) * K * nl;
+  if ((rc = put(h, "g_prob_s11", g->prob_s11, ns, &d.prob_s11))) return rc;
+  if ((rc = put(h, "g_s11", g->tab_s11, ns, &d.s11))) return rc;
+  if ((rc = put(h, "g_s12", g->tab_s12, ns, &d.s12))) return rc;
+  if ((rc = put(h, "g_s22", g->tab_s22, ns, &d.s22))) return rc;
+  if ((rc = put(h, "g_s33", g->tab_s33, ns, &d.s33))) return rc;
+  if ((rc = put(h, "g_s34", g->tab_s34, ns, &d.s34))) return rc;
+  if ((rc = put(h, "g_s44", g->tab_s44, ns, &d.s44))) return rc;
+  if ((rc = put(h, "g_ksca_CDF", g->ksca_CDF, (K + 1) * (size_t)m.p_n_cells * nl, &d.ksca_CDF))) return rc;
+  if ((rc = put(h, "g_kappa_abs_nLTE", g->kappa_abs_nLTE, (size_t)m.p_n_cells * nl, &d.kappa_abs_nLTE))) return rc;
+  if ((rc = put(h, "g_kabs_nLTE_CDF", g->kabs_nLTE_CDF, (k1 + 1) * nc * nl, &d.kabs_nLTE_CDF))) return rc;
+  if ((rc = put(h, "g_logE", g->log_E_em_1grain, k1 * nT, &d.logE))) return rc;
+  if ((rc = put(h, "g_kdB", g->kdB_dT_1grain_nLTE_CDF, nl * k1 * nT, &d.kdB))) return rc;
+  if ((rc = put(h, "g_kappa_abs_RE", g->kappa_abs_RE, nc * nl, &d.kappa_abs_RE))) return rc;
+  if ((rc = put(h, "g_proba_abs_RE", g->proba_abs_RE, nc * nl, &d.proba_abs_RE))) return rc;
+  if ((rc = put(h, "g_P_LTE", g->Proba_abs_RE_LTE, nc * nl, &d.P_LTE))) return rc;
+  if ((rc = put(h, "g_P_LTE_p_nLTE", g->Proba_abs_RE_LTE_p_nLTE, nc * nl, &d.P_LTE_p_nLTE))) return rc;
+  if ((rc = put(h, "g_logE_nRE", g->log_E_em_1grain_nRE, k2 * nT, &d.logE_nRE))) return rc;
+  if ((rc = put(h, "g_kdB_nRE", g->kdB_dT_1grain_nRE_CDF, nl * k2 * nT, &d.kdB_nRE))) return rc;
+  if ((rc = put(h, "g_l_RE", g->l_RE, k2 * nc, &d.l_RE))) return rc;
+  if ((rc = put(h, "g_J0", g->J0, nc * nl, &d.J0))) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  h->gr_host = *g;
+  h->has_gr = true;
   return MCB_OK;
 }
 
@@ -282,7 +334,8 @@ static int setup_tallies(mcb_handle* h, const mcb_run_params* r, bool lxJ, bool 
   L.sed = L.n_env + m.n_lambda;
   L.n_sed = n_sed;
   L.stats = L.sed + 9 * (int64_t)n_sed;
-  L.total = L.stats + 8;
+  L.E_abs_nRE = L.stats + 8;
+  L.total = L.E_abs_nRE + 1;
   m.lay = L;
   int rc;
   if ((rc = reserve(h, "tally", (size_t)L.total, &m.tally))) return rc;
@@ -296,6 +349,13 @@ static int setup_tallies(mcb_handle* h, const mcb_run_params* r, bool lxJ, bool 
   if ((rc = reserve(h, "I_spec", (size_t)n_Is, &m.I_spec))) return rc;
   if ((rc = reserve(h, "I_spec_star", (size_t)(rt2 ? m.n_cells : 0), &m.I_spec_star))) return rc;
   h->n_Ispec = n_Is;
+  // per-grain temperature indices (thermal_emission.f90:163-165,186-188)
+  const int64_t n_1g = (h->has_gr && r->lRE_nLTE) ? (int64_t)(m.gr.nLTE_e - m.gr.nLTE_s + 1) * m.n_cells : 0;
+  const int64_t n_1g_nRE = (h->has_gr && r->lnRE) ? (int64_t)(m.gr.nRE_e - m.gr.nRE_s + 1) * m.n_cells : 0;
+  if (n_1g != h->n_1g || n_1g_nRE != h->n_1g_nRE) realloc_ = true;
+  if ((rc = reserve(h, "xT_1g", (size_t)n_1g, &m.gr.xT_1g))) return rc;
+  if ((rc = reserve(h, "xT_1g_nRE", (size_t)n_1g_nRE, &m.gr.xT_1g_nRE))) return rc;
+  h->n_1g = n_1g; h->n_1g_nRE = n_1g_nRE;
   if ((rc = reserve(h, "work", (size_t)(16 + 2 * r->n_photons_loop), &m.work))) return rc;
   h->n_tally = L.total; h->n_xI = n_xI; h->lay_xJ = lxJ; h->lay_nsed = n_sed; h->n_type_flux = n_type_flux;
   if (realloc_ || r->reset_tallies) {
@@ -303,7 +363,10 @@ static int setup_tallies(mcb_handle* h, const mcb_run_params* r, bool lxJ, bool 
     if (n_xI) CK(cudaMemsetAsync(m.xI, 0, (size_t)n_xI * sizeof(float), h->stream));
     if (n_Is) { CK(cudaMemsetAsync(m.I_spec, 0, (size_t)n_Is * sizeof(float), h->stream)); CK(cudaMemsetAsync(m.I_spec_star, 0, (size_t)m.n_cells * sizeof(float), h->stream)); }
     fill_int_kernel<<<256, 256, 0, h->stream>>>(m.xT_ech, m.n_cells, 2);      // xT_ech = 2, thermal_emission.f90:119,2164
+    if (n_1g) fill_int_kernel<<<256, 256, 0, h->stream>>>(m.gr.xT_1g, n_1g, 2);
+    if (n_1g_nRE) fill_int_kernel<<<256, 256, 0, h->stream>>>(m.gr.xT_1g_nRE, n_1g_nRE, 2);
   }
+  CK(cudaMemsetAsync(m.tally + L.E_abs_nRE, 0, sizeof(double), h->stream));      // E_abs_nRE = 0.0 at every call (dust_transfer.f90:505)
   CK(cudaMemsetAsync(m.work, 0, (size_t)(16 + 2 * r->n_photons_loop) * sizeof(unsigned long long), h->stream));
   h->n_photons_loop_alloc = r->n_photons_loop;
   CK(cudaMemsetAsync(m.work + 1, 0xFF, sizeof(unsigned long long), h->stream));      // work[1] = ~0: "counter not dry yet"
@@ -318,8 +381,35 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   CK(cudaSetDevice(h->device));
   DevModel& m = h->m;
   // ---- modes this library implements; everything else fails loudly ----
-  if (r->lscattering_method1) return fail(h, MCB_ERR_UNSUPPORTED, "scattering method 1 (per-grain) not implemented");
-  if (!r->lonly_LTE) return fail(h, MCB_ERR_UNSUPPORTED, "nLTE / nRE re-emission not implemented");
+  {
+    const mcb_grains& g = h->gr_host;
+    const bool need_gr = r->lscattering_method1 || (!r->lonly_LTE && !r->lmono);
+    if (need_gr && !h->has_gr) return fail(h, MCB_ERR_STATE, "per-grain mode (method 1 / nLTE / nRE) before upload_grains");
+    if (r->lscattering_method1) {
+      if (!g.C_sca) return fail(h, MCB_ERR_BAD_ARG, "method 1: C_sca missing");
+      if (r->low_mem_scattering ? (m.p_n_cells == 1 && !g.grain_zone) : !g.ksca_CDF) return fail(h, MCB_ERR_BAD_ARG, "method 1: grain_zone / ksca_CDF missing");
+      if (r->lmethod_aniso1 ? !g.prob_s11 : !g.tab_g) return fail(h, MCB_ERR_BAD_ARG, "method 1: prob_s11 / tab_g missing");
+      if (r->lsepar_pola && r->lmethod_aniso1 && (!g.tab_s11 || !g.tab_s12 || !g.tab_s22 || !g.tab_s33 || !g.tab_s34 || !g.tab_s44)) return fail(h, MCB_ERR_BAD_ARG, "method 1: per-grain Mueller tables missing");
+      if ((!r->letape_th) && (r->lscatt_ray_tracing1 || r->lscatt_ray_tracing2)) return fail(h, MCB_ERR_UNSUPPORTED, "ray-tracing accumulators need scattering method 2 (dust_ray_tracing.f90)");
+    }
+    if (!r->lonly_LTE && !r->lmono) {
+      const bool mixed = !r->lonly_nLTE;
+      if (!g.C_abs_norm || !g.J0) return fail(h, MCB_ERR_BAD_ARG, "nLTE / nRE: C_abs_norm / J0 missing");
+      if (!(r->letape_th ? r->lxJ_abs_step1 : r->lxJ_abs)) return fail(h, MCB_ERR_BAD_ARG, "nLTE / nRE re-emission reads xJ_abs: lxJ_abs(_step1) must be on");
+      if (r->lRE_nLTE || r->lonly_nLTE) {
+        if (g.grain_RE_nLTE_start < 1 || g.grain_RE_nLTE_end < g.grain_RE_nLTE_start || !g.log_E_em_1grain || !g.kdB_dT_1grain_nLTE_CDF) return fail(h, MCB_ERR_BAD_ARG, "nLTE tables missing");
+        if (r->low_mem_th_emission_nLTE ? (!g.C_abs || !g.kappa_abs_nLTE) : !g.kabs_nLTE_CDF) return fail(h, MCB_ERR_BAD_ARG, "nLTE grain-selection tables missing");
+        if (!r->lRE_nLTE) return fail(h, MCB_ERR_BAD_ARG, "lonly_nLTE without lRE_nLTE");
+      }
+      if (r->lnRE) {
+        if (g.grain_nRE_start < 1 || g.grain_nRE_end < g.grain_nRE_start || !g.log_E_em_1grain_nRE || !g.kdB_dT_1grain_nRE_CDF || !g.l_RE || !g.kappa_abs_RE || !g.proba_abs_RE || !g.C_abs)
+          return fail(h, MCB_ERR_BAD_ARG, "nRE tables missing");
+        if (r->lRE_nLTE && !g.kappa_abs_nLTE) return fail(h, MCB_ERR_BAD_ARG, "kappa_abs_nLTE missing");
+      }
+      if (mixed && (!g.Proba_abs_RE_LTE || !g.Proba_abs_RE_LTE_p_nLTE)) return fail(h, MCB_ERR_BAD_ARG, "Proba_abs_RE_LTE(_p_nLTE) missing");
+      if (mixed && !r->lnRE && !r->lRE_nLTE) return fail(h, MCB_ERR_BAD_ARG, "lonly_LTE = 0 without lRE_nLTE or lnRE");
+    }
+  }
   if (r->loutput_mc) return fail(h, MCB_ERR_UNSUPPORTED, "MC image maps (STOKEI..., loutput_mc) not implemented");
   if (r->lscatt_ray_tracing2 && (m.l3D || h->gk == GK_VOR)) return fail(h, MCB_ERR_UNSUPPORTED, "rt2 is 2D only (radiation_field.f90:91)");
   if (r->lscatt_ray_tracing2 && (r->n_theta_I < 1 || r->n_phi_I < 1)) return fail(h, MCB_ERR_BAD_ARG, "n_theta_I / n_phi_I");
@@ -346,6 +436,9 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   dr.rt1 = rt1;
   dr.rt2 = ((!r->letape_th) && !rt1 && r->lscatt_ray_tracing2) ? 1 : 0;
   dr.lmono0 = r->lmono0; dr.n_theta_I = r->n_theta_I; dr.n_phi_I = r->n_phi_I;
+  dr.lscattering_method1 = r->lscattering_method1; dr.low_mem_scattering = r->low_mem_scattering;
+  dr.lonly_LTE = (r->lonly_LTE || r->lmono) ? 1 : 0;      // lmono: no absorption event ever happens (forced scattering)
+  dr.lonly_nLTE = r->lonly_nLTE; dr.lRE_nLTE = r->lRE_nLTE; dr.lnRE = r->lnRE; dr.low_mem_nLTE = r->low_mem_th_emission_nLTE;
   dr.lxJ = r->letape_th ? r->lxJ_abs_step1 : r->lxJ_abs;
   dr.N_thet = r->N_thet; dr.N_phi = r->N_phi; dr.capt_sup = r->capt_sup;
   dr.n_stokes = r->lsepar_pola ? 4 : 1;
@@ -426,6 +519,9 @@ int mcfost_b200_download(mcb_handle* h, const mcb_run_params* r, mcb_tallies* ou
   double* sp[9] = {out->sed, out->sed_q, out->sed_u, out->sed_v, out->n_phot_sed, out->sed_star, out->sed_star_scat, out->sed_disk, out->sed_disk_scat};
   for (int a = 0; a < 9; ++a) CK(get(sp[a], L.sed + a * L.n_sed, L.n_sed));
   CK(get(out->stats, L.stats, 8));
+  CK(get(out->E_abs_nRE, L.E_abs_nRE, 1));
+  if (out->xT_ech_1grain && h->n_1g) CK(cudaMemcpyAsync(out->xT_ech_1grain, m.gr.xT_1g, (size_t)h->n_1g * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (out->xT_ech_1grain_nRE && h->n_1g_nRE) CK(cudaMemcpyAsync(out->xT_ech_1grain_nRE, m.gr.xT_1g_nRE, (size_t)h->n_1g_nRE * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (out->xT_ech) CK(cudaMemcpyAsync(out->xT_ech, m.xT_ech, (size_t)m.n_cells * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (out->xI_scatt && h->n_xI) CK(cudaMemcpyAsync(out->xI_scatt, m.xI, (size_t)h->n_xI * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   if (out->I_spec && h->n_Ispec) CK(cudaMemcpyAsync(out->I_spec, m.I_spec, (size_t)h->n_Ispec * sizeof(float), cudaMemcpyDeviceToHost, h->stream));

@@ -27,7 +27,7 @@ enum GridKind { GK_CYL2D = 0, GK_CYL3D = 1, GK_SPH2D = 2, GK_SPH3D = 3, GK_VOR =
 
 // tally block offsets inside the packed fp64 buffer
 struct TallyLayout {
-  int64_t xKJ, xJ, n_env, sed, stats, total;   // offsets in doubles
+  int64_t xKJ, xJ, n_env, sed, stats, E_abs_nRE, total;   // offsets in doubles
   int64_t n_sed;                               // n_lambda*N_thet*N_phi
 };
 
@@ -43,6 +43,27 @@ struct SmemLayout {
   int logQ, kdB, cos_tab, prob_s11;                   // thermal / scattering (prob_s11: float region, one p_lambda slice)
   int spec_cumul, frac_star, frac_disk;
   int total_words;
+};
+
+// per-grain tables (mcb_grains): scattering method 1, nLTE / qRE re-emission
+struct DevGrains {
+  int n_grains_tot, n_dens;
+  int LTE_s, LTE_e, nLTE_s, nLTE_e, nRE_s, nRE_e;     // 1-based inclusive grain ranges (grains.f90:36)
+  const int *zone;                  // (n_grains_tot)
+  const double *n_grains;           // (n_grains_tot)
+  const double *dd;                 // dust_density_o_n_grains (n_dens, n_cells)
+  const float *C_abs, *C_abs_norm, *C_sca, *tab_g;    // (n_grains_tot, n_lambda)
+  const float *prob_s11;            // (n_lambda, n_grains_tot, 0:180)
+  const float *s11, *s12, *s22, *s33, *s34, *s44;     // (0:180, n_grains_tot, n_lambda)
+  const double *ksca_CDF;           // (0:n_grains_tot, p_n_cells, n_lambda)
+  const double *kappa_abs_nLTE;     // (p_n_cells, n_lambda)
+  const double *kabs_nLTE_CDF;      // (nLTE_s-1:nLTE_e, n_cells, n_lambda)
+  const double *logE, *kdB;         // nLTE grains: (k, n_T), (n_lambda, k, n_T)
+  const double *kappa_abs_RE, *proba_abs_RE, *P_LTE, *P_LTE_p_nLTE;   // (n_cells, n_lambda)
+  const double *logE_nRE, *kdB_nRE; // nRE grains
+  const int *l_RE;                  // (nRE grains, n_cells)
+  const double *J0;                 // (n_cells, n_lambda)
+  int *xT_1g, *xT_1g_nRE;           // tallies: xT_ech_1grain (nLTE grains, n_cells), xT_ech_1grain_nRE
 };
 
 struct DevModel {
@@ -75,6 +96,7 @@ struct DevModel {
   const double *kdB;                        // (n_lambda, n_T, p_n_cells)
   const double *cos_tab;                    // cos(k*pi/180), k = 0..180 (host libm)
   float T_min;
+  const float *tab_Temp;                    // (n_T), read by the per-grain re-emission branches only
   // ---- emission ---------------------------------------------------------
   const double *spec_cumul, *frac_star, *frac_disk, *prob_E_cell;
   const float *CDF_E_star;
@@ -88,6 +110,7 @@ struct DevModel {
   double *quv;              // Stokes Q,U,V of the packets in flight: (n_blocks, 3, NP), only with lsepar_pola
   unsigned long long *work; // [0] = next work item; [2+2c], [3+2c] = sent / received of local chunk c
   SmemLayout sm;
+  DevGrains gr;
 };
 
 // run parameters broadcast to the kernel
@@ -97,6 +120,8 @@ struct DevRun {
   int letape_th, lmono, lsepar_pola, lsepar_contrib, lmethod_aniso1, lisotropic;
   int l_sym_centrale, l_sym_axiale, rt1, lxJ;
   int rt2, lmono0, n_theta_I, n_phi_I;
+  int lscattering_method1, low_mem_scattering;          // dust_transfer.f90:1291, dust_prop.f90:1305
+  int lonly_LTE, lonly_nLTE, lRE_nLTE, lnRE, low_mem_nLTE;   // grain heating regimes (dust_transfer.f90:1353-1395)
   int N_thet, N_phi, capt_sup, n_type_flux, n_stokes;
   int n_rt, RT_n_incl, RT_n_az;
   double rt_u[MAX_RT], rt_v[MAX_RT], rt_w[MAX_RT];

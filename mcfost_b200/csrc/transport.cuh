@@ -195,21 +195,8 @@ __device__ __forceinline__ void angle_diff_theta_pos(const DevModel& m, int p_la
 // Here the same quantities are formed algebraically (cos(atan2(v,u)) = u/hypot(u,v);
 // cos(omega) = 1 - 2 costhet^2, sin(omega) = -+2 costhet sqrt(1 - costhet^2)): identical up to the
 // fp32 rounding the reference itself carries, without atan2 / sincos / acosf / cosf / sinf.
-template <int BANK>
-__device__ __forceinline__ void scatter_stokes(int lambda, int itheta, float frac, int p_icell, double* S,
-                                               double u0, double v0, double w0, double u1, double v1, double w1) {
-  const DevModel& m = c_m;
-  const size_t q1 = (size_t)itheta + (size_t)(NANG + 1) * ((p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)), q0 = q1 - 1;
-  const float frac_m1 = 1.0f - frac;
-  const float a22 = __ldg(m.s22 + q1), b22 = __ldg(m.s22 + q0), a12 = __ldg(m.s12 + q1), b12 = __ldg(m.s12 + q0);
-  const float a33 = __ldg(m.s33 + q1), b33 = __ldg(m.s33 + q0), a44 = __ldg(m.s44 + q1), b44 = __ldg(m.s44 + q0);
-  const float a34 = __ldg(m.s34 + q1), b34 = __ldg(m.s34 + q0);
-  const double M11 = (double)1.0f;
-  const double M22 = (double)__fadd_rn(__fmul_rn(a22, frac), __fmul_rn(b22, frac_m1));
-  const double M12 = (double)__fadd_rn(__fmul_rn(a12, frac), __fmul_rn(b12, frac_m1));
-  const double M33 = (double)__fadd_rn(__fmul_rn(a33, frac), __fmul_rn(b33, frac_m1));
-  const double M44 = (double)__fadd_rn(__fmul_rn(a44, frac), __fmul_rn(b44, frac_m1));
-  const double M34 = (double)__fsub_rn(__fmul_rn(-a34, frac), __fmul_rn(b34, frac_m1));
+__device__ __forceinline__ void stokes_update(double M11, double M12, double M22, double M33, double M34, double M44, double* S,
+                                              double u0, double v0, double w0, double u1, double v1, double w1) {
   const double M43 = -M34;
   // rotation(u0,v0,w0 ; u1,v1,w1) -> v1p (utils.f90:553-599), algebraic cos/sin of atan2(v1,u1)
   double cost, sint, sing;
@@ -242,6 +229,24 @@ __device__ __forceinline__ void scatter_stokes(int lambda, int itheta, float fra
     S[0] *= f; S[1] *= f; S[2] *= f; S[3] *= f;
   }
 }
+// per-cell Mueller matrix (get_Mueller_matrix_per_cell, scattering.f90:1328-1350): M11 = 1
+template <int BANK>
+__device__ __forceinline__ void scatter_stokes(int lambda, int itheta, float frac, int p_icell, double* S,
+                                               double u0, double v0, double w0, double u1, double v1, double w1) {
+  const DevModel& m = c_m;
+  const size_t q1 = (size_t)itheta + (size_t)(NANG + 1) * ((p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)), q0 = q1 - 1;
+  const float frac_m1 = 1.0f - frac;
+  const float a22 = __ldg(m.s22 + q1), b22 = __ldg(m.s22 + q0), a12 = __ldg(m.s12 + q1), b12 = __ldg(m.s12 + q0);
+  const float a33 = __ldg(m.s33 + q1), b33 = __ldg(m.s33 + q0), a44 = __ldg(m.s44 + q1), b44 = __ldg(m.s44 + q0);
+  const float a34 = __ldg(m.s34 + q1), b34 = __ldg(m.s34 + q0);
+  const double M11 = (double)1.0f;
+  const double M22 = (double)__fadd_rn(__fmul_rn(a22, frac), __fmul_rn(b22, frac_m1));
+  const double M12 = (double)__fadd_rn(__fmul_rn(a12, frac), __fmul_rn(b12, frac_m1));
+  const double M33 = (double)__fadd_rn(__fmul_rn(a33, frac), __fmul_rn(b33, frac_m1));
+  const double M44 = (double)__fadd_rn(__fmul_rn(a44, frac), __fmul_rn(b44, frac_m1));
+  const double M34 = (double)__fsub_rn(__fmul_rn(-a34, frac), __fmul_rn(b34, frac_m1));
+  stokes_update(M11, M12, M22, M33, M34, M44, S, u0, v0, w0, u1, v1, w1);
+}
 
 // ---- thermal_emission.f90:649-771 Temp_LTE + im_reemission_LTE (high-memory
 // branch): new wavelength index ------------------------------------------------
@@ -271,6 +276,212 @@ __device__ __forceinline__ int im_reemission_LTE(const DevModel& m, const DevRun
     l = (l1 + l2) / 2;
   }
   return l + 1;
+}
+
+
+// =============================================================================
+// Per-grain modes: scattering method 1 (dust_transfer.f90:1291-1317) and the nLTE / qRE
+// re-emission branches (dust_transfer.f90:1353-1395).  Cold code: everything is __noinline__
+// and reads global memory, so the LTE / method-2 instruction footprint is unchanged.
+// =============================================================================
+#define MCB_AU_TO_CM_MUM2 ((149597870700.0 * 100.0) * (1.0e-4 * 1.0e-4))     /* AU_to_cm * mum_to_cm**2 */
+
+// thermal_emission.f90:1953-2040 select_absorbing_grain, heating_method 2 (nLTE) / 3 (qRE); idx 0-based cell
+template <int BANK>
+__device__ __noinline__ int select_absorbing_grain(int lambda, int idx, float rand, int heating_method) {
+  const DevModel& m = c_m; const DevRun& r = c_r; const DevGrains& g = m.gr;
+  const bool variable = m.p_n_cells != 1;
+  const size_t pl = (size_t)(variable ? idx : 0) + (size_t)m.p_n_cells * (lambda - 1);
+  const double kf = __ldg(m.kappa_factor + idx);
+  double norm; int kstart, kend;
+  if (heating_method == 2) {
+    norm = __ldg(g.kappa_abs_nLTE + pl) * kf / MCB_AU_TO_CM_MUM2;
+    kstart = g.nLTE_s; kend = g.nLTE_e;
+  } else {
+    const double kRE = __ldg(g.kappa_abs_RE + idx + (size_t)m.n_cells * (lambda - 1));
+    if (r.lRE_nLTE) norm = (kRE - (__ldg(m.kappa_abs + pl) + __ldg(g.kappa_abs_nLTE + pl)) * kf) / MCB_AU_TO_CM_MUM2;
+    else            norm = (kRE - __ldg(m.kappa_abs + pl) * kf) / MCB_AU_TO_CM_MUM2;
+    kstart = g.nRE_s; kend = g.nRE_e;
+  }
+  const bool masked = heating_method > 2;
+  const int nkR = g.nRE_e - g.nRE_s + 1;
+  const bool up = rand < 0.5f;
+  const double prob = up ? rand * norm : (double)(1.0f - rand) * norm;
+  double CDF = 0.0;
+  int k = up ? kstart : kend;
+  const int step = up ? 1 : -1;
+  for (; up ? (k <= kend) : (k >= kstart); k += step) {
+    if (!masked || __ldg(g.l_RE + (k - g.nRE_s) + (size_t)nkR * idx))
+      CDF = CDF + (double)__ldg(g.C_abs + (k - 1) + (size_t)g.n_grains_tot * (lambda - 1)) * __ldg(g.dd + (variable ? k - 1 : 0) + (size_t)g.n_dens * idx) * __ldg(g.n_grains + k - 1);
+    if (CDF > prob) break;
+  }
+  // the reference returns the run-out do-variable (kend+1 / kstart-1) and then indexes out of bounds
+  // (:2033-2034 are commented out); only reachable with inconsistent tables: clamp for memory safety
+  return min(max(k, kstart), kend);
+}
+
+// shared tail of im_reemission_NLTE / im_reemission_qRE (thermal_emission.f90:812-863, 1469-1511):
+// temperature index of grain kk (0-based inside its regime) from log_E_abs, then the wavelength bisection
+template <int BANK>
+__device__ __noinline__ int reemit_1grain(int* xT, const double* logE, const double* kdB, int nk, int kk, int idx,
+                                          double log_E_abs, float rand2) {
+  const DevModel& m = c_m;
+  int* px = xT + kk + (size_t)nk * idx;
+  auto LE = [&](int t) { return __ldg(logE + kk + (size_t)nk * (t - 1)); };
+  int Ti = __ldcg(px);
+  while ((LE(Ti) < log_E_abs) && (Ti < m.n_T)) ++Ti;
+  while (Ti > 2 && !(LE(Ti - 1) < log_E_abs)) --Ti;      // index cached by another warp from a later, larger tally
+  atomicMax(px, Ti);
+  const int T2 = Ti, T1 = Ti - 1;
+  const double Temp2 = __ldg(m.tab_Temp + T2 - 1), Temp1 = __ldg(m.tab_Temp + T1 - 1);
+  const double frac = (log_E_abs - LE(T1)) / (LE(T2) - LE(T1));
+  const double Temp = exp(mcb_log(Temp2) * frac + mcb_log(Temp1) * (1.0 - frac));
+  const double frac_T2 = (Temp - Temp1) / (Temp2 - Temp1), frac_T1 = 1.0 - frac_T2;
+  auto CDF = [&](int l, int t) { return __ldg(kdB + (l - 1) + (size_t)m.n_lambda * (kk + (size_t)nk * (t - 1))); };
+  int l1 = 0, l2 = m.n_lambda, l = (l1 + l2) / 2;
+  while ((l2 - l1) > 1) {
+    const double proba = frac_T1 * CDF(l, T1) + frac_T2 * CDF(l, T2);
+    if ((double)rand2 > proba) l1 = l; else l2 = l;
+    l = (l1 + l2) / 2;
+  }
+  return l + 1;
+}
+
+// Sum_lambda C_abs_norm(k,l) * (xJ_abs(icell,l) [running, all ranks] + J0(icell, l or lambda0))
+template <int BANK>
+__device__ __forceinline__ double log_E_abs_1grain(int k, int idx, int j0_fixed_lambda) {
+  const DevModel& m = c_m; const DevRun& r = c_r; const DevGrains& g = m.gr;
+  double J_abs = 0.0;
+  for (int il = 1; il <= m.n_lambda; ++il) {
+    const size_t cl = (size_t)idx + (size_t)m.n_cells * (il - 1);
+    const double j0 = __ldg(g.J0 + (j0_fixed_lambda ? (size_t)idx + (size_t)m.n_cells * (j0_fixed_lambda - 1) : cl));
+    J_abs = J_abs + (double)__ldg(g.C_abs_norm + (k - 1) + (size_t)g.n_grains_tot * (il - 1)) * (__ldcg(m.tally + m.lay.xJ + cl) * r.nb_proc_equiv + j0);
+  }
+  return mcb_log(J_abs * m.L_packet_th / __ldg(m.volume + idx));
+}
+
+// thermal_emission.f90:775-866 im_reemission_NLTE
+template <int BANK>
+__device__ __noinline__ int im_reemission_NLTE(int idx, int lambda0, float rand1, float rand2) {
+  const DevModel& m = c_m; const DevRun& r = c_r; const DevGrains& g = m.gr;
+  int k;
+  if (r.low_mem_nLTE) k = select_absorbing_grain<BANK>(lambda0, idx, rand1, 2);
+  else {
+    const int nk1 = g.nLTE_e - g.nLTE_s + 2;
+    const double* cdf = g.kabs_nLTE_CDF + (size_t)nk1 * ((size_t)idx + (size_t)m.n_cells * (lambda0 - 1)) - (g.nLTE_s - 1);
+    int kmin = g.nLTE_s, kmax = g.nLTE_e;
+    k = (kmin + kmax) / 2;
+    while ((kmax - kmin) > 1) {
+      if (__ldg(cdf + k) < (double)rand1) kmin = k; else kmax = k;
+      k = (kmin + kmax) / 2;
+    }
+    k = kmax;
+  }
+  const double log_E_abs = log_E_abs_1grain<BANK>(k, idx, 0);
+  return reemit_1grain<BANK>(g.xT_1g, g.logE, g.kdB, g.nLTE_e - g.nLTE_s + 1, k - g.nLTE_s, idx, log_E_abs, rand2);
+}
+// thermal_emission.f90:1441-1514 im_reemission_qRE (J0(icell,lambda) with the ABSORBED wavelength, :1466)
+template <int BANK>
+__device__ __noinline__ int im_reemission_qRE(int idx, int lambda0, float rand1, float rand2) {
+  const DevModel& m = c_m; const DevGrains& g = m.gr;
+  const int k = select_absorbing_grain<BANK>(lambda0, idx, rand1, 3);
+  const double log_E_abs = log_E_abs_1grain<BANK>(k, idx, lambda0);
+  return reemit_1grain<BANK>(g.xT_1g_nRE, g.logE_nRE, g.kdB_nRE, g.nRE_e - g.nRE_s + 1, k - g.nRE_s, idx, log_E_abs, rand2);
+}
+
+// dust_prop.f90:1292-1380 select_scattering_grain (the reference passes p_icell as its `icell`)
+template <int BANK>
+__device__ __noinline__ int select_scattering_grain(int lambda, int p_icell, float rand) {
+  const DevModel& m = c_m; const DevRun& r = c_r; const DevGrains& g = m.gr;
+  const bool variable = m.p_n_cells != 1;
+  const size_t pl = (size_t)(p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1);
+  if (r.low_mem_scattering) {
+    const double norm = __ldg(m.kappa + pl) * __ldg(m.albedo + pl) / MCB_AU_TO_CM_MUM2;
+    const bool up = rand < 0.5f;
+    const double prob = up ? rand * norm : (double)(1.0f - rand) * norm;
+    double CDF = 0.0;
+    int k = up ? 1 : g.n_grains_tot;
+    const int step = up ? 1 : -1;
+    for (; up ? (k <= g.n_grains_tot) : (k >= 1); k += step) {
+      const int pk = variable ? k : __ldg(g.zone + k - 1);
+      const double density = __ldg(g.dd + (pk - 1) + (size_t)g.n_dens * (p_icell - 1)) * __ldg(g.n_grains + k - 1);
+      CDF = CDF + __ldg(g.C_sca + (k - 1) + (size_t)g.n_grains_tot * (lambda - 1)) * density;
+      if (CDF > prob) break;
+    }
+    return min(max(k, 1), g.n_grains_tot);
+  }
+  const double* cdf = g.ksca_CDF + (size_t)(g.n_grains_tot + 1) * pl;
+  const double prob = (double)rand;
+  int kmin = 0, kmax = g.n_grains_tot, k = (kmin + kmax) / 2;
+  while (__ldg(cdf + k) != prob) {
+    if (__ldg(cdf + k) < prob) kmin = k; else kmax = k;
+    k = (kmin + kmax) / 2;
+    if ((kmax - kmin) <= 1) break;
+  }
+  return kmax;
+}
+// scattering.f90:1387-1429 angle_diff_theta (per grain)
+template <int BANK>
+__device__ __noinline__ void angle_diff_theta_grain(int lambda, int igrain, float rand, float rand2, int& itheta, double& cospsi) {
+  const DevModel& m = c_m; const DevGrains& g = m.gr;
+  const float* p = g.prob_s11 + (lambda - 1) + (size_t)m.n_lambda * (igrain - 1);
+  const size_t stride = (size_t)m.n_lambda * g.n_grains_tot;
+  int kmin = 0, kmax = NANG, k = (kmin + kmax) / 2;
+  while ((kmax - kmin) > 1) {
+    if (__ldg(p + stride * k) < rand) kmin = k; else kmax = k;
+    k = (kmin + kmax) / 2;
+  }
+  k = kmax;
+  itheta = k;
+  const double c0 = __ldg(m.cos_tab + k - 1), c1 = __ldg(m.cos_tab + k);
+  cospsi = c0 + rand2 * (c1 - c0);
+}
+
+
+// dust_transfer.f90:1291-1317: scattering method 1.  Philox words of the interaction block:
+// x = grain draw, y = rand, z = rand2, w = phi draw.
+template <int BANK>
+__device__ __noinline__ void scatter_method1(int lambda, int p_icell, uint4 b, bool pola, double* S,
+                                             double u, double v, double w, double& u1, double& v1, double& w1) {
+  const DevModel& m = c_m; const DevRun& r = c_r; const DevGrains& g = m.gr;
+  const int igrain = select_scattering_grain<BANK>(lambda, p_icell, u01(b.x));
+  const float rand = u01(b.y), rand2 = u01(b.z), rand3 = u01(b.w);
+  int itheta; double cospsi;
+  if (r.lmethod_aniso1) angle_diff_theta_grain<BANK>(lambda, igrain, rand, rand2, itheta, cospsi);
+  else {
+    hg(__ldg(g.tab_g + (igrain - 1) + (size_t)g.n_grains_tot * (lambda - 1)), rand, itheta, cospsi);
+    if (r.lisotropic) { itheta = 1; cospsi = (double)__fsub_rn(__fmul_rn(2.0f, rand), 1.0f); }
+  }
+  double sp, cp;
+  mcb_sincospi((double)__fsub_rn(__fmul_rn(2.0f, rand3), 1.0f), &sp, &cp);
+  cdapres(cospsi, sp, cp, u, v, w, u1, v1, w1);
+  if (pola && r.lmethod_aniso1) {     // get_Mueller_matrix_per_grain, scattering.f90:1302-1324 (fp32 interpolation)
+    const size_t q1 = (size_t)itheta + (size_t)(NANG + 1) * ((igrain - 1) + (size_t)g.n_grains_tot * (lambda - 1)), q0 = q1 - 1;
+    const float frac = rand2, frac_m1 = 1.0f - frac;
+    auto mix = [&](const float* t) { return (double)__fadd_rn(__fmul_rn(__ldg(t + q1), frac), __fmul_rn(__ldg(t + q0), frac_m1)); };
+    const double M34 = (double)__fsub_rn(__fmul_rn(-__ldg(g.s34 + q1), frac), __fmul_rn(__ldg(g.s34 + q0), frac_m1));
+    stokes_update(mix(g.s11), mix(g.s12), mix(g.s22), mix(g.s33), M34, mix(g.s44), S, u, v, w, u1, v1, w1);
+  }
+}
+
+// dust_transfer.f90:1353-1395 when .not.lonly_LTE: energy kept by grains out of equilibrium, choice of
+// the grain regime, re-emission wavelength.  Returns the new wavelength, or 0 if the packet is dropped.
+// S0 is scaled in place; e_nRE returns this packet's contribution to E_abs_nRE.
+template <bool SM, int BANK>
+__device__ __noinline__ int absorb_grain_regimes(int idx, int p_icell, int lambda0, uint4 b, float sel, double& S0, double& e_nRE) {
+  const DevModel& m = c_m; const DevRun& r = c_r; const DevGrains& g = m.gr;
+  const size_t cl = (size_t)idx + (size_t)m.n_cells * (lambda0 - 1);
+  if (r.lnRE) {
+    const double pRE = __ldg(g.proba_abs_RE + cl);
+    e_nRE = S0 * (1.0 - pRE);
+    S0 = S0 * pRE;
+    if (S0 < MCB_TINY_REAL) return 0;
+  }
+  const float rand1 = u01(b.x), rand2 = u01(b.y);
+  if (r.lonly_nLTE) return im_reemission_NLTE<BANK>(idx, lambda0, rand1, rand2);
+  if ((double)sel <= __ldg(g.P_LTE + cl)) return im_reemission_LTE<SM>(m, r, idx, p_icell, rand2);
+  if ((double)sel <= __ldg(g.P_LTE_p_nLTE + cl)) return im_reemission_NLTE<BANK>(idx, lambda0, rand1, rand2);
+  return im_reemission_qRE<BANK>(idx, lambda0, rand1, rand2);
 }
 
 // ---- output.f90:294-595 capteur, SED branch ------------------------------------
@@ -830,17 +1041,20 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
       const uint4 b = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev + 1u, pk_lo, pk_hi, r.call_index);
       const uint4 bnext = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev + 2u, pk_lo, pk_hi, r.call_index);
 #endif
-      const float rand = u01(b.x), rand2 = u01(b.y), rand3 = u01(b.z);
       const double u = P.F(F_U, slot), v = P.F(F_V, slot), w = P.F(F_W, slot);
-      int itheta; double cospsi;
-      if (r.lmethod_aniso1) angle_diff_theta_pos<SM>(m, r.p_lambda_in, p_icell, rand, rand2, itheta, cospsi);
-      else hg(t_gfac<SM>(m, p_icell, lambda), rand, itheta, cospsi);
-      if (r.lisotropic) { itheta = 1; cospsi = (double)__fsub_rn(__fmul_rn(2.0f, rand), 1.0f); }
-      double sp, cp;
-      mcb_sincospi((double)__fsub_rn(__fmul_rn(2.0f, rand3), 1.0f), &sp, &cp);     // PHI = PI*(2.0*rand-1.0): fp32 inner
       double u1, v1, w1;
-      cdapres(cospsi, sp, cp, u, v, w, u1, v1, w1);
-      if (POLA && r.lmethod_aniso1) scatter_stokes<BANK>(lambda, itheta, rand2, p_icell, S, u, v, w, u1, v1, w1);
+      if (r.lscattering_method1) scatter_method1<BANK>(lambda, p_icell, b, POLA, S, u, v, w, u1, v1, w1);
+      else {
+        const float rand = u01(b.x), rand2 = u01(b.y), rand3 = u01(b.z);
+        int itheta; double cospsi;
+        if (r.lmethod_aniso1) angle_diff_theta_pos<SM>(m, r.p_lambda_in, p_icell, rand, rand2, itheta, cospsi);
+        else hg(t_gfac<SM>(m, p_icell, lambda), rand, itheta, cospsi);
+        if (r.lisotropic) { itheta = 1; cospsi = (double)__fsub_rn(__fmul_rn(2.0f, rand), 1.0f); }
+        double sp, cp;
+        mcb_sincospi((double)__fsub_rn(__fmul_rn(2.0f, rand3), 1.0f), &sp, &cp);     // PHI = PI*(2.0*rand-1.0): fp32 inner
+        cdapres(cospsi, sp, cp, u, v, w, u1, v1, w1);
+        if (POLA && r.lmethod_aniso1) scatter_stokes<BANK>(lambda, itheta, rand2, p_icell, S, u, v, w, u1, v1, w1);
+      }
       P.F(F_U, slot) = u1; P.F(F_V, slot) = v1; P.F(F_W, slot) = w1;
       if (r.lmono || POLA) { P.F(F_S0, slot) = S[0]; if (POLA) { QUV(0, slot) = S[1]; QUV(1, slot) = S[2]; QUV(2, slot) = S[3]; } }
       misc |= (1u << 11);                                    // flag_scatt
@@ -864,6 +1078,7 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
   using CellT = typename G::CellT;
   const unsigned lane = threadIdx.x & 31;
   int nextq = Q_NONE;
+  double e_nRE = 0.0;
   if (valid) {
     const bool variable_dust = m.p_n_cells != 1;
     uint32_t misc = P.U(U_MISC, slot);
@@ -879,17 +1094,35 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
     const uint4 b = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev + 1u, pk_lo, pk_hi, r.call_index);
     const uint4 bnext = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev + 2u, pk_lo, pk_hi, r.call_index);
 #endif
-    // b.x is rand1: drawn but unused in the high-memory LTE branch (thermal_emission.f90:739-765)
-    const int lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, u01(b.y));
-    double u, v, w;
-    random_isotropic_direction(u01(b.z), u01(b.w), u, v, w);
-    P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;
-    if (POLA) { QUV(0, slot) = 0.0; QUV(1, slot) = 0.0; QUV(2, slot) = 0.0; }
-    misc = pack_misc(lambda, false, false, false, 0, misc_chunk(misc));      // flag_star = flag_scatt = flag_ISM = .false.
-    P.U(U_EV, slot) = ev + 1u;
-    start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u, v, w, bnext, misc);
-    P.U(U_MISC, slot) = misc;
-    nextq = Q_FLY;
+    int lambda;
+    if (r.lonly_LTE) {
+      // b.x is rand1: drawn but unused in the high-memory LTE branch (thermal_emission.f90:739-765)
+      lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, u01(b.y));
+    } else {
+      // the grain-regime draw (dust_transfer.f90:1379) has its own Philox block, so rand / rand2 / the
+      // direction draws keep the words they have in the lonly_LTE case
+      float sel = 0.0f;
+      if (!r.lonly_nLTE) sel = u01(philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), (2u * ev + 1u) | 0x80000000u, pk_lo, pk_hi, r.call_index).x);
+      double S0 = P.F(F_S0, slot);
+      lambda = absorb_grain_regimes<SM, BANK>(idx, p_icell, misc_lambda(misc), b, sel, S0, e_nRE);
+      if (r.lnRE) P.F(F_S0, slot) = S0;
+    }
+    if (lambda == 0) { ++st.kill; nextq = Q_EMIT; }      // Stokes(1) < tiny_real: packet dropped (dust_transfer.f90:1361-1364)
+    else {
+      double u, v, w;
+      random_isotropic_direction(u01(b.z), u01(b.w), u, v, w);
+      P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;
+      if (POLA) { QUV(0, slot) = 0.0; QUV(1, slot) = 0.0; QUV(2, slot) = 0.0; }
+      misc = pack_misc(lambda, false, false, false, 0, misc_chunk(misc));      // flag_star = flag_scatt = flag_ISM = .false.
+      P.U(U_EV, slot) = ev + 1u;
+      start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u, v, w, bnext, misc);
+      P.U(U_MISC, slot) = misc;
+      nextq = Q_FLY;
+    }
+  }
+  if (r.lnRE) {      // E_abs_nRE (omp reduction in the reference, dust_transfer.f90:489): one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) e_nRE += __shfl_down_sync(0xffffffffu, e_nRE, o);
+    if (lane == 0 && e_nRE != 0.0) atomicAdd(m.tally + m.lay.E_abs_nRE, e_nRE);
   }
   return nextq;
 }

@@ -848,3 +848,183 @@ def ref41_multi_like(n_photons_eq_th=200, n_rad=40, nz=20, n_rad_in=5, tau_mid=3
     repartition_energie(P)
     P.name = "ref4.1_multi-like (G3, LTE part)"
     return P
+
+
+AU_TO_CM = 149597870700.0 * 100.0
+MUM_TO_CM = 1.0e-4
+AU_TO_CM_MUM2 = AU_TO_CM * (MUM_TO_CM * MUM_TO_CM)      # AU_to_cm * mum_to_cm**2
+
+
+def multi_grain_like(n_photons_eq_th=100, n_rad=24, nz=12, n_rad_in=4, tau_mid=30.0, n_lambda=30, n_T=60,
+                     n_LTE=5, n_nLTE=3, n_nRE=3, variable=False, pola=True, qre_fraction=0.5, seed=11):
+    """A disk whose dust is a SIZE DISTRIBUTION of n_LTE + n_nLTE + n_nRE grains in the three heating
+    regimes of ref4.1_multi.para (methode_chauffage 1, 2, 3): per-grain cross sections, phase functions
+    and emissivities, and every table the per-grain branches read, built the way the reference builds
+    them (opacite dust_prop.f90:787-1000, init_reemission thermal_emission.f90:404-644,
+    update_proba_abs_nRE :1518-1600).  Optics are an analytic stand-in for Mie theory:
+    Q_abs = x/(1+x), Q_sca = x^4/(1+x^4), g = 0.7 x^2/(1+x^2) with x = 2 pi a / lambda.
+    variable=True: lvariable_dust (size-dependent settling, p_n_cells = n_cells, p_n_lambda_pos = 1)."""
+    zones = [DiskZone(rin=1.0, rout=100.0, edge=0.0)]
+    P = cylindrical_grid(n_rad, nz, 1, n_rad_in, zones, l3D=False)
+    nc = P.n_cells
+    P.n_lambda, P.n_T = n_lambda, n_T
+    P.tab_lambda, P.tab_delta_lambda = init_lambda(n_lambda)
+    P.tab_lambda = np.float32(P.tab_lambda).astype(np.float64)
+    P.tab_delta_lambda = np.float32(P.tab_delta_lambda).astype(np.float64)
+    P.T_min, P.T_max = 1.0, 3000.0
+    P.tab_Temp = init_tab_Temp(n_T, P.T_min, P.T_max)
+    P.n_photons_loop, P.n_photons_eq_th = 128, n_photons_eq_th
+    P.n_stars = 1
+    P.star_xyzr = np.asfortranarray(np.array([[0.0], [0.0], [0.0], [2.0 * RSUN_TO_AU]]))
+    P.star_T = np.array([6000.0]); P.star_out_model = np.zeros(1, np.int32)
+    P.star_icell = np.array([star_icell_analytic(P)], np.int32)
+    lam = P.tab_lambda
+    # ---- grains: big (LTE) first, then nLTE, then the smallest (nRE), like the reference's sorted populations
+    K = n_LTE + n_nLTE + n_nRE
+    a = np.logspace(1.0, -2.3, K)                       # um
+    ng = a ** -3.5 * a                                   # dn/dlog a
+    ng = ng / ng.sum()
+    P.n_grains_tot, P.n_grains = K, ng
+    P.grain_RE_LTE_start, P.grain_RE_LTE_end = 1, n_LTE
+    P.grain_RE_nLTE_start, P.grain_RE_nLTE_end = n_LTE + 1, n_LTE + n_nLTE
+    P.grain_nRE_start, P.grain_nRE_end = n_LTE + n_nLTE + 1, K
+    P.grain_zone = np.ones(K, np.int32)
+    x = 2.0 * PI * a[:, None] / lam[None, :]
+    geo = PI * a[:, None] ** 2
+    C_abs = np.float32(geo * x / (1.0 + x))
+    C_sca = np.float32(geo * x ** 4 / (1.0 + x ** 4))
+    C_ext = np.float32(C_abs.astype(np.float64) + C_sca)
+    tab_g = np.float32(0.7 * x ** 2 / (1.0 + x ** 2))
+    P.C_abs, P.C_sca, P.tab_g = (np.asfortranarray(t) for t in (C_abs, C_sca, tab_g))
+    P.C_abs_norm = np.asfortranarray(np.float32(C_abs.astype(np.float64) * AU_TO_CM * MUM_TO_CM ** 2))
+    # ---- number densities: dust_density_o_n_grains(n_dens, n_cells)
+    rho = disk_density(P, zones)
+    rho = rho / rho[0]
+    if variable:
+        # settling: scale height shrinks with grain size
+        h_fac = np.clip((a / a.min()) ** -0.15, 0.3, 1.0)
+        z_o_h = np.abs(P.z_grid) / np.maximum(zones[0].sclht * (P.r_grid / zones[0].rref) ** zones[0].exp_beta, 1e-30)
+        dd = rho[None, :] * np.exp(-0.5 * z_o_h[None, :] ** 2 * (1.0 / h_fac[:, None] ** 2 - 1.0)) / h_fac[:, None]
+        P.n_dens = K
+    else:
+        dd = rho[None, :].copy()
+        P.n_dens = 1
+    pk = (np.arange(K) if variable else np.zeros(K, int))
+    dens = dd[pk, :] * ng[:, None]                       # (K, n_cells): density of grain k in each cell
+    # ---- opacities (dust_prop.f90:850-890, x fact at :965-970), scaled to tau_mid at 0.81 um
+    l_seuil = int(np.argmax(lam > 0.81)) + 1
+    P.lambda_seuil = l_seuil
+    kext_cell = np.einsum("kl,kc->cl", C_ext.astype(np.float64), dens)          # (n_cells, n_lambda), um^2 cm^-3
+    mid = np.arange(n_rad)
+    col = float(np.sum(kext_cell[mid, l_seuil - 1] * (P.r_lim[1:] - P.r_lim[:-1])))
+    scale = tau_mid / (col * AU_TO_CM_MUM2)
+    dd = dd * scale; dens = dens * scale
+    P.dust_density_o_n_grains = np.asfortranarray(dd)
+
+    def ksum(C, ks, cells):
+        return np.einsum("kl,kc->cl", C[ks].astype(np.float64), dens[ks][:, cells])
+    cells = np.arange(nc) if variable else np.array([0])
+    allk = np.arange(K); kL = np.arange(0, n_LTE); kN = np.arange(n_LTE, n_LTE + n_nLTE); kR = np.arange(n_LTE + n_nLTE, K)
+    P.p_n_cells = nc if variable else 1
+    P.kappa_factor = np.ones(nc) if variable else rho.copy()
+    kap = ksum(C_ext, allk, cells); ksca = ksum(C_sca, allk, cells)
+    P.kappa = np.asfortranarray(kap * AU_TO_CM_MUM2)
+    alb = np.where(kap > 0, ksca / np.maximum(kap, 1e-300), 0.0)
+    P.tab_albedo_pos = np.asfortranarray(np.float32(alb))
+    gpos = np.einsum("kl,kc->cl", (C_sca * tab_g).astype(np.float64), dens[:, cells]) / np.maximum(ksca, 1e-300)
+    P.tab_g_pos = np.asfortranarray(np.float32(gpos))
+    P.kappa_abs_LTE = np.asfortranarray(ksum(C_abs, kL, cells) * AU_TO_CM_MUM2)
+    P.kappa_abs_nLTE = np.asfortranarray(ksum(C_abs, kN, cells) * AU_TO_CM_MUM2)
+    # ---- per-grain phase functions (HG per grain; tab_s11 = 1 after mueller's normalisation)
+    theta = np.arange(NANG_SCATT + 1) * PI / NANG_SCATT
+    mu = np.cos(theta)
+    gk = tab_g.astype(np.float64)
+    s11 = (1.0 - gk[None] ** 2) * (1.0 + gk[None] ** 2 - 2.0 * gk[None] * mu[:, None, None]) ** (-1.5)      # (181, K, nl)
+    wgt = s11 * np.sin(theta)[:, None, None]
+    cdf = np.concatenate((np.zeros((1, K, n_lambda)), np.cumsum(0.5 * (wgt[1:] + wgt[:-1]), axis=0)))
+    cdf = cdf / cdf[-1:]
+    P.prob_s11 = np.asfortranarray(np.float32(np.transpose(cdf, (2, 1, 0))))    # (n_lambda, K, 0:180)
+    ones = np.ones((NANG_SCATT + 1, K, n_lambda), np.float32)
+    P.tab_s11 = np.asfortranarray(ones)
+    if pola:
+        pmax = 0.2 + 0.3 / (1.0 + x)                      # small grains polarise more
+        P.tab_s12 = np.asfortranarray(np.float32(-pmax[None] * ((1.0 - mu * mu) / (1.0 + mu * mu))[:, None, None]))
+        P.tab_s22 = np.asfortranarray(ones.copy())
+        s33 = (2.0 * mu / (1.0 + mu * mu))[:, None, None] * np.ones((1, K, n_lambda))
+        P.tab_s33 = np.asfortranarray(np.float32(s33)); P.tab_s44 = np.asfortranarray(np.float32(s33))
+        P.tab_s34 = np.asfortranarray(np.float32((0.1 * np.sin(theta) ** 2 * mu)[:, None, None] * np.ones((1, K, n_lambda))))
+    # ksca_CDF(0:K, p_n_cells, n_lambda) (dust_prop.f90:1180-1200): normalised cumulative of C_sca * density
+    c = np.cumsum(np.einsum("kl,kc->kcl", C_sca.astype(np.float64), dens[:, cells]), axis=0)
+    c = np.concatenate((np.zeros((1,) + c.shape[1:]), c)) / np.maximum(c[-1:], 1e-300)
+    P.ksca_CDF = np.asfortranarray(c)
+    # ---- method-2 tables of the population (calc_local_scattering_matrices)
+    if variable:
+        P.p_n_lambda_pos = 1
+        w = (C_sca.astype(np.float64)[:, None, 0] * dens)                        # (K, n_cells) at lambda index 1
+        s_cell = np.einsum("akl,kc->ac", s11[:, :, :1], w) / np.maximum(w.sum(0), 1e-300)
+        wg = s_cell * np.sin(theta)[:, None]
+        cc = np.concatenate((np.zeros((1, nc)), np.cumsum(0.5 * (wg[1:] + wg[:-1]), axis=0)))
+        P.prob_s11_pos = np.asfortranarray(np.float32(cc / cc[-1:]).reshape(NANG_SCATT + 1, nc, 1))
+        P.tab_s11_pos = np.asfortranarray(np.float32(s_cell / (wg.sum(0) * 2.0 * PI)).reshape(NANG_SCATT + 1, nc, 1))
+        for nm in ("tab_s12_o_s11_pos", "tab_s22_o_s11_pos", "tab_s33_o_s11_pos", "tab_s34_o_s11_pos", "tab_s44_o_s11_pos"):
+            setattr(P, nm, None)
+    else:
+        P.p_n_lambda_pos = n_lambda
+        w = C_sca.astype(np.float64) * dens[:, :1]                               # (K, nl)
+        s_pop = np.einsum("akl,kl->al", s11, w) / np.maximum(w.sum(0), 1e-300)
+        pol = None
+        if pola:
+            pol = ((-0.3 * (1.0 - mu * mu) / (1.0 + mu * mu)), np.ones_like(mu), 2.0 * mu / (1.0 + mu * mu),
+                   0.1 * np.sin(theta) ** 2 * mu, 2.0 * mu / (1.0 + mu * mu))
+        for k_, v_ in scattering_tables(P, s_pop, alb[0], P.kappa[0], pol).items():
+            setattr(P, k_, v_)
+    # ---- LTE thermal tables of the LTE grains, emission tables
+    init_reemission(P)
+    star_energy(P)
+    P.l_dark_zone = np.zeros(nc, np.int32)
+    P.E_paquet = 1.0; P.R_ISM = 0.0; P.centre_ISM = (0.0, 0.0, 0.0)
+    repartition_energie(P)
+    # ---- per-grain thermal tables (init_reemission :554-640)
+    cst_E = 2.0 * HP * C_LIGHT ** 2 * 4.0 * PI
+    wl = lam * 1.0e-6; dwl = P.tab_delta_lambda * 1.0e-6
+    B = np.zeros((n_lambda, n_T)); dB = np.zeros((n_lambda, n_T))
+    for t in range(n_T):
+        cw = THERMAL_CONST / float(P.tab_Temp[t]) / wl
+        ok = cw < 500.0
+        ce = np.exp(np.where(ok, cw, 1.0))
+        B[:, t] = np.where(ok, 1.0 / ((wl ** 5) * (ce - 1.0)) * dwl, 0.0)
+        dB[:, t] = np.where(ok, B[:, t] * cw * ce / (ce - 1.0), 0.0)
+    Cn = P.C_abs_norm.astype(np.float64)
+
+    def one_grain(ks):
+        integ = Cn[ks] @ B                                                       # (nk, n_T)
+        logE = np.where(integ > np.finfo(np.float64).tiny, np.log(np.maximum(integ, 1e-300) * cst_E), -1000.0)
+        i3 = np.cumsum(Cn[ks][:, 1:, None] * dB[None, 1:, :], axis=1)            # (nk, nl-1, n_T): integ3(2:n_lambda)
+        i3 = np.concatenate((np.zeros((len(ks), 1, n_T)), i3), axis=1)
+        cdf_ = i3 / np.maximum(i3[:, -1:, :], 1e-300)
+        return np.asfortranarray(logE), np.asfortranarray(np.transpose(cdf_, (1, 0, 2)))     # (nk, n_T), (nl, nk, n_T)
+    P.log_E_em_1grain, P.kdB_dT_1grain_nLTE_CDF = one_grain(kN)
+    P.log_E_em_1grain_nRE, P.kdB_dT_1grain_nRE_CDF = one_grain(kR)
+    # kabs_nLTE_CDF(grain_RE_nLTE_start-1:grain_RE_nLTE_end, n_cells, n_lambda) (dust_prop.f90:930-945)
+    pkN = kN if variable else np.zeros(len(kN), int)
+    cab = np.cumsum(np.einsum("kl,kc->kcl", C_abs[kN].astype(np.float64), dd[pkN, :] * ng[kN, None]), axis=0)
+    cab = np.concatenate((np.zeros((1, nc, n_lambda)), cab))
+    last = cab[-1:]
+    P.kabs_nLTE_CDF = np.asfortranarray(np.where(last > np.finfo(np.float32).tiny, cab / np.maximum(last, 1e-300), cab))
+    # ---- nRE grains: which are at quasi equilibrium in which cell, and the probabilities that follow
+    rng = np.random.default_rng(seed)
+    l_RE = (rng.random((n_nRE, nc)) < qre_fraction)
+    P.l_RE = np.asfortranarray(l_RE.astype(np.int32))
+    full = dd[(np.arange(K) if variable else np.zeros(K, int)), :] * ng[:, None]                     # (K, n_cells)
+    k_tot = np.einsum("kl,kc->cl", C_abs.astype(np.float64), full)
+    k_LTE = np.einsum("kl,kc->cl", C_abs[kL].astype(np.float64), full[kL])
+    k_nLTE = np.einsum("kl,kc->cl", C_abs[kN].astype(np.float64), full[kN])
+    k_qRE = np.einsum("kl,kc->cl", C_abs[kR].astype(np.float64), full[kR] * l_RE)
+    k_RE = k_LTE + k_nLTE + k_qRE
+    P.kappa_abs_RE = np.asfortranarray(k_RE * AU_TO_CM_MUM2)
+    P.proba_abs_RE = np.asfortranarray(np.where(l_RE.all(0)[:, None], 1.0, k_RE / k_tot))
+    P.Proba_abs_RE_LTE = np.asfortranarray(k_LTE / k_RE)
+    P.Proba_abs_RE_LTE_p_nLTE = np.asfortranarray((k_LTE + k_nLTE) / k_RE)
+    P.J0 = np.asfortranarray(1.0e-10 * P.volume[:, None] * np.ones((1, n_lambda)))
+    P.name = "multi-grain disk (LTE + nLTE + nRE/qRE grains%s)" % (", lvariable_dust" if variable else "")
+    return P

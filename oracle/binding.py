@@ -37,7 +37,7 @@ def _load(name):
     lib.oracle_last_error.restype = C.c_char_p
     lib.oracle_last_error.argtypes = [C.c_void_p]
     for fn in ("oracle_destroy", "oracle_set_grid", "oracle_set_dark_zone", "oracle_set_opacity",
-               "oracle_set_emission", "oracle_n_cells_tot"):
+               "oracle_set_emission", "oracle_set_grains", "oracle_n_cells_tot"):
         getattr(lib, fn).argtypes = [C.c_void_p] + ([C.c_void_p] if fn not in ("oracle_destroy", "oracle_n_cells_tot") else [])
     lib.oracle_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
     return lib
@@ -61,6 +61,10 @@ class Oracle:
         self._check(self.lib.oracle_set_opacity(self.h, self._o.ref()))
         if self._e is not None:
             self._check(self.lib.oracle_set_emission(self.h, self._e.ref()))
+        self._gr = None
+        if hasattr(P, "n_grains_tot"):
+            self._gr = abi.make_grains(P)
+            self._check(self.lib.oracle_set_grains(self.h, self._gr.ref()))
         self.set_dark_zone(getattr(P, "l_dark_zone", None))
 
     def __del__(self):
@@ -95,7 +99,8 @@ class Oracle:
     def run(self, n_threads=0, rec=None, n_xI=0, xJ=False, n_Ispec=0, **params):
         r = abi.make_run(**params)
         P = self.P
-        t = abi.Tallies(P.n_cells, P.n_lambda, r.struct.N_thet, r.struct.N_phi, xJ=xJ, n_xI=n_xI, n_Ispec=n_Ispec)
+        t = abi.Tallies(P.n_cells, P.n_lambda, r.struct.N_thet, r.struct.N_phi, xJ=xJ, n_xI=n_xI, n_Ispec=n_Ispec,
+                        **abi.grain_tally_sizes(P, r.struct))
         rec_a = None if rec is None else np.ascontiguousarray(rec, np.float64)
         self._check(self.lib.oracle_run(self.h, r.ref(), t.ref(), int(n_threads), _p(rec_a),
                                         0 if rec_a is None else len(rec_a)))

@@ -56,6 +56,9 @@ const float  tiny_real_x1e6 = tiny_real * 1.0e6f;
 const float  max_int = (float)2147483647 * (1.0f - 1.0e-5f);
 const double grid_prec = 1.0e-14;
 const double prec_grille_sph = 1.0e-7;
+const double AU_to_cm = 149597870700.0 * 100.0;     // constants.f90:62-65
+const double mum_to_cm = 1.0e-4;                    // constants.f90:73
+const double AU_to_cm_mum2 = AU_to_cm * (mum_to_cm * mum_to_cm);   // AU_to_cm * mum_to_cm**2
 const int nang_scatt = MCB_NANG_SCATT;
 const int n_az_rt = MCB_N_AZ_RT;
 
@@ -79,6 +82,8 @@ struct ThreadTallies {
   std::vector<double> xKJ_abs;      // (n_cells)
   std::vector<double> xJ_abs;       // (n_cells, n_lambda)
   std::vector<int>    xT_ech;       // (n_cells)
+  std::vector<int>    xT_ech_1grain, xT_ech_1grain_nRE;   // (grains of the regime, n_cells) thermal_emission.f90:50
+  double E_abs_nRE = 0.0;           // omp reduction variable, dust_transfer.f90:489
   std::vector<double> n_phot_envoyes;
   std::vector<double> sed[9];       // sed, q, u, v, n_phot_sed, star, star_scat, disk, disk_scat
   std::vector<float>  xI_scatt;
@@ -94,7 +99,8 @@ struct Oracle {
   mcb_opacity o{};
   mcb_emission e{};
   mcb_run_params r{};
-  bool has_grid = false, has_op = false, has_em = false;
+  mcb_grains gr{};
+  bool has_grid = false, has_op = false, has_em = false, has_gr = false;
   char err[256] = {0};
 
   // ---- build_cylindrical_cell_mapping, cylindrical_grid.f90:45-179
@@ -131,6 +137,22 @@ struct Oracle {
   inline double log_Qcool(int t, int pc) const { return o.log_Qcool_minus_extra_heating[(size_t)(t - 1) + (size_t)o.n_T * (pc - 1)]; }
   inline double kdB_dT_CDF(int l, int t, int pc) const { return o.kdB_dT_CDF[(size_t)(l - 1) + (size_t)o.n_lambda * ((size_t)(t - 1) + (size_t)o.n_T * (pc - 1))]; }
   inline float tab_Temp(int t) const { return o.tab_Temp[t - 1]; }
+  // per-grain tables (mcb_grains)
+  inline size_t gl_idx(int k, int l) const { return (size_t)(k - 1) + (size_t)gr.n_grains_tot * (l - 1); }
+  inline size_t cl_idx(int ic, int l) const { return (size_t)(ic - 1) + (size_t)g.n_cells * (l - 1); }
+  inline double dust_density_o_n_grains(int pk, int ic) const { return gr.dust_density_o_n_grains[(size_t)(pk - 1) + (size_t)gr.n_dens * (ic - 1)]; }
+  inline int nk_nLTE() const { return gr.grain_RE_nLTE_end - gr.grain_RE_nLTE_start + 1; }
+  inline int nk_nRE() const { return gr.grain_nRE_end - gr.grain_nRE_start + 1; }
+  inline double kabs_nLTE_CDF(int k, int ic, int l) const { return gr.kabs_nLTE_CDF[(size_t)(k - gr.grain_RE_nLTE_start + 1) + (size_t)(nk_nLTE() + 1) * cl_idx(ic, l)]; }
+  inline double log_E_em_1grain(int k, int t) const { return gr.log_E_em_1grain[(size_t)(k - gr.grain_RE_nLTE_start) + (size_t)nk_nLTE() * (t - 1)]; }
+  inline double kdB_dT_1grain_nLTE_CDF(int l, int k, int t) const { return gr.kdB_dT_1grain_nLTE_CDF[(size_t)(l - 1) + (size_t)o.n_lambda * ((size_t)(k - gr.grain_RE_nLTE_start) + (size_t)nk_nLTE() * (t - 1))]; }
+  inline double log_E_em_1grain_nRE(int k, int t) const { return gr.log_E_em_1grain_nRE[(size_t)(k - gr.grain_nRE_start) + (size_t)nk_nRE() * (t - 1)]; }
+  inline double kdB_dT_1grain_nRE_CDF(int l, int k, int t) const { return gr.kdB_dT_1grain_nRE_CDF[(size_t)(l - 1) + (size_t)o.n_lambda * ((size_t)(k - gr.grain_nRE_start) + (size_t)nk_nRE() * (t - 1))]; }
+  inline bool l_RE(int k, int ic) const { return gr.l_RE[(size_t)(k - gr.grain_nRE_start) + (size_t)nk_nRE() * (ic - 1)] != 0; }
+  inline double kappa_abs_nLTE(int pc, int l) const { return gr.kappa_abs_nLTE[(size_t)(pc - 1) + (size_t)o.p_n_cells * (l - 1)]; }
+  inline float prob_s11(int l, int k, int a) const { return gr.prob_s11[(size_t)(l - 1) + (size_t)o.n_lambda * ((size_t)(k - 1) + (size_t)gr.n_grains_tot * a)]; }
+  inline size_t s_idx(int a, int k, int l) const { return (size_t)a + (size_t)(nang_scatt + 1) * gl_idx(k, l); }
+  inline double ksca_CDF(int k, int pc, int l) const { return gr.ksca_CDF[(size_t)k + (size_t)(gr.n_grains_tot + 1) * ((size_t)(pc - 1) + (size_t)o.p_n_cells * (l - 1))]; }
   inline double prob_E_cell(int k, int l) const { return e.prob_E_cell[(size_t)k + (size_t)(g.n_cells + 1) * (l - 1)]; }
   inline float CDF_E_star(int l, int k) const { return e.CDF_E_star[(size_t)(l - 1) + (size_t)o.n_lambda * k]; }
   inline double star_x(int i) const { return g.star_xyzr[4 * (i - 1) + 0]; }
@@ -1316,8 +1338,168 @@ struct Oracle {
     lambda = l + 1;
   }
 
+
   // =====================================================================
-  // dust_transfer.f90:1155-1409  propagate_packet  (method 2, lonly_LTE)
+  // thermal_emission.f90:1953-2040  select_absorbing_grain  (heating_method 2, 3)
+  // =====================================================================
+  int select_absorbing_grain(int lambda, int icell, float rand, int heating_method) const {
+    const double AU3 = AU_to_cm_mum2;
+    int p_icell = lvariable_dust() ? icell : 1;          // icell1
+    double norm; int kstart, kend, k;
+    if (heating_method == 1) {
+      norm = kappa_abs_LTE(p_icell, lambda) * kappa_factor(icell) / AU3;
+      kstart = gr.grain_RE_LTE_start; kend = gr.grain_RE_LTE_end;
+    } else if (heating_method == 2) {
+      norm = kappa_abs_nLTE(p_icell, lambda) * kappa_factor(icell) / AU3;
+      kstart = gr.grain_RE_nLTE_start; kend = gr.grain_RE_nLTE_end;
+    } else {
+      if (r.lRE_nLTE) norm = (gr.kappa_abs_RE[cl_idx(icell, lambda)] - (kappa_abs_LTE(p_icell, lambda) + kappa_abs_nLTE(p_icell, lambda)) * kappa_factor(icell)) / AU3;
+      else            norm = (gr.kappa_abs_RE[cl_idx(icell, lambda)] - kappa_abs_LTE(p_icell, lambda) * kappa_factor(icell)) / AU3;
+      kstart = gr.grain_nRE_start; kend = gr.grain_nRE_end;
+    }
+    // p_k => k if lvariable_dust else => k1 = 1  (:1970-1977: zone 1 whatever the grain)
+    // C_abs(k,lambda) * dust_density_o_n_grains(p_k,icell) * n_grains(k), left to right
+    auto term = [&](int kk) { return (double)gr.C_abs[gl_idx(kk, lambda)] * dust_density_o_n_grains(lvariable_dust() ? kk : 1, icell) * gr.n_grains[kk - 1]; };
+    const bool masked = heating_method > 2;
+    double prob, CDF = 0.0;
+    if (rand < 0.5f) {
+      prob = rand * norm;
+      for (k = kstart; k <= kend; ++k) {
+        if (!masked || l_RE(k, icell)) CDF = CDF + term(k);
+        if (CDF > prob) break;
+      }
+    } else {
+      prob = (1.0f - rand) * norm;                      // (1.0-rand) evaluated in fp32
+      for (k = kend; k >= kstart; --k) {
+        if (!masked || l_RE(k, icell)) CDF = CDF + term(k);
+        if (CDF > prob) break;
+      }
+    }
+    return k;       // kend+1 / kstart-1 when the loop runs out, exactly like the Fortran do-variable
+  }
+
+  // shared tail of im_reemission_NLTE / im_reemission_qRE: temperature of grain k from
+  // log_E_abs, then the wavelength bisection  (thermal_emission.f90:812-863, 1469-1511)
+  template <class FE, class FC>
+  void reemit_1grain(std::vector<int> ThreadTallies::*xT, ThreadTallies& t, size_t ix, double log_E_abs, float rand2, FE logE, FC cdf, int& lambda) {
+    int T_int = (T[0].*xT)[ix];
+    for (auto& tt : T) T_int = std::max(T_int, (tt.*xT)[ix]);            // maxval(xT_ech_1grain(k,icell,:))
+    while ((logE(T_int) < log_E_abs) && (T_int < o.n_T)) T_int = T_int + 1;
+    (t.*xT)[ix] = T_int;
+    int T2 = T_int, T1 = T_int - 1;
+    double Temp2 = tab_Temp(T2), Temp1 = tab_Temp(T1);
+    double frac = (log_E_abs - logE(T1)) / (logE(T2) - logE(T1));
+    double Temp = std::exp(std::log(Temp2) * frac + std::log(Temp1) * (1.0 - frac));
+    double frac_T2 = (Temp - Temp1) / (Temp2 - Temp1), frac_T1 = 1.0 - frac_T2;
+    int l1 = 0, l2 = o.n_lambda, l = (l1 + l2) / 2;
+    while ((l2 - l1) > 1) {
+      double proba = frac_T1 * cdf(l, T1) + frac_T2 * cdf(l, T2);
+      if ((double)rand2 > proba) l1 = l; else l2 = l;
+      l = (l1 + l2) / 2;
+    }
+    lambda = l + 1;
+  }
+  // sum(xJ_abs(icell,ilambda,:)) over the id slices
+  double xJ_abs_sum(int icell, int ilambda) const { double s = 0.0; size_t ix = cl_idx(icell, ilambda); for (auto& tt : T) s += tt.xJ_abs[ix]; return s; }
+
+  // =====================================================================
+  // thermal_emission.f90:775-866  im_reemission_NLTE
+  // =====================================================================
+  void im_reemission_NLTE(ThreadTallies& t, int icell, int /*p_icell*/, float rand1, float rand2, int& lambda) {
+    const int lambda0 = lambda;
+    int k;
+    if (r.low_mem_th_emission_nLTE) k = select_absorbing_grain(lambda0, icell, rand1, 2);
+    else {
+      int kmin = gr.grain_RE_nLTE_start, kmax = gr.grain_RE_nLTE_end;
+      k = (kmin + kmax) / 2;
+      while ((kmax - kmin) > 1) {
+        if (kabs_nLTE_CDF(k, icell, lambda0) < (double)rand1) kmin = k; else kmax = k;
+        k = (kmin + kmax) / 2;
+      }
+      k = kmax;
+    }
+    double J_abs = 0.0;
+    for (int il = 1; il <= o.n_lambda; ++il) J_abs = J_abs + gr.C_abs_norm[gl_idx(k, il)] * (xJ_abs_sum(icell, il) + gr.J0[cl_idx(icell, il)]);
+    double log_E_abs = std::log(J_abs * e.L_packet_th / volume(icell));
+    size_t ix = (size_t)(k - gr.grain_RE_nLTE_start) + (size_t)nk_nLTE() * (icell - 1);
+    reemit_1grain(&ThreadTallies::xT_ech_1grain, t, ix, log_E_abs, rand2,
+                  [&](int Ti) { return log_E_em_1grain(k, Ti); }, [&](int l, int Ti) { return kdB_dT_1grain_nLTE_CDF(l, k, Ti); }, lambda);
+  }
+  // =====================================================================
+  // thermal_emission.f90:1441-1514  im_reemission_qRE
+  // (J0(icell,lambda) is indexed with the absorbed wavelength, not ilambda: :1466)
+  // =====================================================================
+  void im_reemission_qRE(ThreadTallies& t, int icell, int /*p_icell*/, float rand1, float rand2, int& lambda) {
+    const int lambda0 = lambda;
+    int k = select_absorbing_grain(lambda0, icell, rand1, 3);
+    double J_abs = 0.0;
+    for (int il = 1; il <= o.n_lambda; ++il) J_abs = J_abs + gr.C_abs_norm[gl_idx(k, il)] * (xJ_abs_sum(icell, il) + gr.J0[cl_idx(icell, lambda)]);
+    double log_E_abs = std::log(J_abs * e.L_packet_th / volume(icell));
+    size_t ix = (size_t)(k - gr.grain_nRE_start) + (size_t)nk_nRE() * (icell - 1);
+    reemit_1grain(&ThreadTallies::xT_ech_1grain_nRE, t, ix, log_E_abs, rand2,
+                  [&](int Ti) { return log_E_em_1grain_nRE(k, Ti); }, [&](int l, int Ti) { return kdB_dT_1grain_nRE_CDF(l, k, Ti); }, lambda);
+  }
+
+  // =====================================================================
+  // dust_prop.f90:1292-1336 select_scattering_grain, :1340-1380 select_grainsize_high_mem
+  // =====================================================================
+  int select_scattering_grain(int lambda, int icell, float rand) const {
+    if (r.low_mem_scattering) {
+      double norm = kappa(icell, lambda) * tab_albedo_pos(icell, lambda) / AU_to_cm_mum2;
+      double prob, CDF = 0.0; int k;
+      auto dens = [&](int kk) { return dust_density_o_n_grains(lvariable_dust() ? kk : gr.grain_zone[kk - 1], icell) * gr.n_grains[kk - 1]; };
+      if (rand < 0.5f) {
+        prob = rand * norm;
+        for (k = 1; k <= gr.n_grains_tot; ++k) { CDF = CDF + gr.C_sca[gl_idx(k, lambda)] * dens(k); if (CDF > prob) break; }
+      } else {
+        prob = (1.0f - rand) * norm;
+        for (k = gr.n_grains_tot; k >= 1; --k) { CDF = CDF + gr.C_sca[gl_idx(k, lambda)] * dens(k); if (CDF > prob) break; }
+      }
+      return k;
+    }
+    float prob = rand;
+    int kmin = 0, kmax = gr.n_grains_tot, k = (kmin + kmax) / 2;
+    while (ksca_CDF(k, icell, lambda) != (double)prob) {
+      if (ksca_CDF(k, icell, lambda) < (double)prob) kmin = k; else kmax = k;
+      k = (kmin + kmax) / 2;
+      if ((kmax - kmin) <= 1) break;
+    }
+    return kmax;
+  }
+  // =====================================================================
+  // scattering.f90:1387-1429  angle_diff_theta  (per grain)
+  // =====================================================================
+  void angle_diff_theta(int lambda, int igrain, float rand, float rand2, int& itheta, double& cospsi) const {
+    int kmin = 0, kmax = nang_scatt, k = (kmin + kmax) / 2;
+    while ((kmax - kmin) > 1) {
+      if (prob_s11(lambda, igrain, k) < rand) kmin = k; else kmax = k;
+      k = (kmin + kmax) / 2;
+    }
+    k = kmax;
+    itheta = k;
+    // real(k), real(nang_scatt) are fp32 but promoted: (real(k)-1.0)*pi/real(nang_scatt) is dp because pi is dp
+    cospsi = std::cos(((double)((float)k - 1.0f)) * pi / (double)nang_scatt) +
+             rand2 * (std::cos(((double)(float)k) * pi / (double)nang_scatt) - std::cos(((double)((float)k - 1.0f)) * pi / (double)nang_scatt));
+  }
+  // =====================================================================
+  // scattering.f90:1302-1324  get_Mueller_matrix_per_grain
+  // =====================================================================
+  void get_Mueller_matrix_per_grain(int lambda, int itheta, float frac, int igrain, double M[4][4]) const {
+    float frac_m1 = 1.0f - frac;
+    for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) M[a][b] = 0.0;
+    size_t q1 = s_idx(itheta, igrain, lambda), q0 = s_idx(itheta - 1, igrain, lambda);
+    M[0][0] = gr.tab_s11[q1] * frac + gr.tab_s11[q0] * frac_m1;          // fp32 expressions
+    M[1][1] = gr.tab_s22[q1] * frac + gr.tab_s22[q0] * frac_m1;
+    M[0][1] = gr.tab_s12[q1] * frac + gr.tab_s12[q0] * frac_m1;
+    M[1][0] = M[0][1];
+    M[2][2] = gr.tab_s33[q1] * frac + gr.tab_s33[q0] * frac_m1;
+    M[3][3] = gr.tab_s44[q1] * frac + gr.tab_s44[q0] * frac_m1;
+    M[2][3] = -gr.tab_s34[q1] * frac - gr.tab_s34[q0] * frac_m1;
+    M[3][2] = -M[2][3];
+  }
+
+  // =====================================================================
+  // dust_transfer.f90:1155-1409  propagate_packet  
   // =====================================================================
   void propagate_packet(PacketRng& rng, ThreadTallies& t, int& lambda, int p_lambda, Packet& p) {
     double M[4][4], u1, v1, w1, phi, cospsi;
@@ -1351,6 +1533,30 @@ struct Oracle {
       if (rand < tab_albedo_pos(p_icell, lambda)) {
         t.stats[3] += 1; logev(2);
         p.flag_scatt = true; flag_direct_star = false;
+        if (r.lscattering_method1) {                 // :1291-1317
+          rand = (float)rng_next(&rng);
+          int igrain = select_scattering_grain(lambda, p_icell, rand);
+          rand = (float)rng_next(&rng);
+          rand2 = (float)rng_next(&rng);
+          if (r.lmethod_aniso1) {
+            angle_diff_theta(lambda, igrain, rand, rand2, itheta, cospsi);
+            rand = (float)rng_next(&rng);
+            phi = pi * (double)(2.0f * rand - 1.0f);
+            cdapres(cospsi, phi, p.u, p.v, p.w, u1, v1, w1);
+            if (r.lsepar_pola) {
+              get_Mueller_matrix_per_grain(lambda, itheta, rand2, igrain, M);
+              update_Stokes(p.S, p.u, p.v, p.w, u1, v1, w1, M);
+            }
+          } else {
+            hg(gr.tab_g[gl_idx(igrain, lambda)], rand, itheta, cospsi);
+            if (r.lisotropic) { itheta = 1; cospsi = (double)(2.0f * rand - 1.0f); }
+            rand = (float)rng_next(&rng);
+            phi = pi * (double)(2.0f * rand - 1.0f);
+            cdapres(cospsi, phi, p.u, p.v, p.w, u1, v1, w1);
+          }
+          p.u = u1; p.v = v1; p.w = w1;
+          continue;
+        }
         // method 2  :1318-1348
         rand = (float)rng_next(&rng);
         rand2 = (float)rng_next(&rng);
@@ -1374,9 +1580,30 @@ struct Oracle {
         p.u = u1; p.v = v1; p.w = w1;
       } else {
         t.stats[4] += 1; logev(3);
+        if ((!r.lmono) && r.lnRE) {                                     // :1355-1366
+          const double pRE = gr.proba_abs_RE[cl_idx(p.icell, lambda)];
+          t.E_abs_nRE = t.E_abs_nRE + p.S[0] * (1.0 - pRE);
+          for (int a = 0; a < 4; ++a) p.S[a] = p.S[a] * pRE;
+          if (p.S[0] < tiny_real) { p.alive = false; return; }
+        }
         p.flag_star = false; p.flag_scatt = false; flag_direct_star = false; p.flag_ISM = false;
-        rand = (float)rng_next(&rng); rand2 = (float)rng_next(&rng);     // lonly_LTE :1373-1375
-        im_reemission_LTE(t, p.icell, p_icell, rand, rand2, lambda);
+        if (r.lonly_LTE) {
+          rand = (float)rng_next(&rng); rand2 = (float)rng_next(&rng);   // :1373-1375
+          im_reemission_LTE(t, p.icell, p_icell, rand, rand2, lambda);
+        } else if (r.lonly_nLTE) {
+          rand = (float)rng_next(&rng); rand2 = (float)rng_next(&rng);
+          im_reemission_NLTE(t, p.icell, p_icell, rand, rand2, lambda);
+        } else {
+          // grain-regime draw: its own Philox block so that rand/rand2/direction keep their words
+          rng_set_block(&rng, (2 * n_flight + 1) | 0x80000000u);
+          rand = (float)rng_next(&rng);
+          rng_set_block(&rng, 2 * n_flight + 1);
+          const float sel = rand;
+          rand = (float)rng_next(&rng); rand2 = (float)rng_next(&rng);
+          if ((double)sel <= gr.Proba_abs_RE_LTE[cl_idx(p.icell, lambda)]) im_reemission_LTE(t, p.icell, p_icell, rand, rand2, lambda);
+          else if ((double)sel <= gr.Proba_abs_RE_LTE_p_nLTE[cl_idx(p.icell, lambda)]) im_reemission_NLTE(t, p.icell, p_icell, rand, rand2, lambda);
+          else im_reemission_qRE(t, p.icell, p_icell, rand, rand2, lambda);
+        }
         random_isotropic_direction(rng, p.u, p.v, p.w);
         p.S[1] = 0.0; p.S[2] = 0.0; p.S[3] = 0.0;
       }
@@ -1432,6 +1659,9 @@ struct Oracle {
       if (reset || t.xKJ_abs.size() != (size_t)g.n_cells) {
         t.xKJ_abs.assign(g.n_cells, 0.0);
         t.xT_ech.assign(g.n_cells, 2);                 // thermal_emission.f90:119, 2164
+        t.xT_ech_1grain.assign(has_gr && r.lRE_nLTE ? (size_t)nk_nLTE() * g.n_cells : 0, 2);      // :165
+        t.xT_ech_1grain_nRE.assign(has_gr && r.lnRE ? (size_t)nk_nRE() * g.n_cells : 0, 2);       // :188
+        t.E_abs_nRE = 0.0;
         t.n_phot_envoyes.assign(o.n_lambda, 0.0);
         for (auto& s : t.sed) s.assign(nsed, 0.0);
         t.xJ_abs.assign(need_xJ ? (size_t)g.n_cells * o.n_lambda : 0, 0.0);
@@ -1458,6 +1688,7 @@ struct Oracle {
     nthreads = 1;
 #endif
     alloc_tallies(nthreads, r.reset_tallies != 0);
+    for (auto& t : T) t.E_abs_nRE = 0.0;                              // :505
 #pragma omp parallel num_threads(nthreads)
     {
       int id = 0;
@@ -1510,6 +1741,9 @@ struct Oracle {
     if (out->xKJ_abs) { for (size_t i = 0; i < nc; ++i) { double s = 0; for (auto& t : T) s += t.xKJ_abs[i]; out->xKJ_abs[i] = s; } }
     if (out->xJ_abs && !T.empty() && !T[0].xJ_abs.empty()) { for (size_t i = 0; i < nc * nl; ++i) { double s = 0; for (auto& t : T) s += t.xJ_abs[i]; out->xJ_abs[i] = s; } }
     if (out->xT_ech) { for (size_t i = 0; i < nc; ++i) { int m = T[0].xT_ech[i]; for (auto& t : T) m = std::max(m, t.xT_ech[i]); out->xT_ech[i] = m; } }
+    if (out->xT_ech_1grain) for (size_t i = 0; i < T[0].xT_ech_1grain.size(); ++i) { int m = 0; for (auto& t : T) m = std::max(m, t.xT_ech_1grain[i]); out->xT_ech_1grain[i] = m; }
+    if (out->xT_ech_1grain_nRE) for (size_t i = 0; i < T[0].xT_ech_1grain_nRE.size(); ++i) { int m = 0; for (auto& t : T) m = std::max(m, t.xT_ech_1grain_nRE[i]); out->xT_ech_1grain_nRE[i] = m; }
+    if (out->E_abs_nRE) { double s = 0; for (auto& t : T) s += t.E_abs_nRE; *out->E_abs_nRE = s; }
     if (out->n_phot_envoyes) { for (size_t i = 0; i < nl; ++i) { double s = 0; for (auto& t : T) s += t.n_phot_envoyes[i]; out->n_phot_envoyes[i] = s; } }
     double* sp[9] = {out->sed, out->sed_q, out->sed_u, out->sed_v, out->n_phot_sed, out->sed_star, out->sed_star_scat, out->sed_disk, out->sed_disk_scat};
     for (int a = 0; a < 9; ++a) if (sp[a]) { size_t n = T[0].sed[a].size(); for (size_t i = 0; i < n; ++i) { double s = 0; for (auto& t : T) s += t.sed[a][i]; sp[a][i] = s; } }
@@ -1569,9 +1803,12 @@ int oracle_set_dark_zone(void* h, const int32_t* dz) {
 int oracle_set_opacity(void* h, const mcb_opacity* o) { Oracle* O = (Oracle*)h; O->o = *o; O->has_op = true; return MCB_OK; }
 int oracle_set_emission(void* h, const mcb_emission* e) { Oracle* O = (Oracle*)h; O->e = *e; O->has_em = true; return MCB_OK; }
 
+int oracle_set_grains(void* h, const mcb_grains* g) { Oracle* O = (Oracle*)h; O->gr = *g; O->has_gr = true; return MCB_OK; }
+
 static int check_run(Oracle* O, const mcb_run_params* r) {
   if (!O->has_grid || !O->has_op || !O->has_em) { snprintf(O->err, sizeof O->err, "run before uploads"); return MCB_ERR_STATE; }
-  if (r->lscattering_method1 || !r->lonly_LTE || r->loutput_mc || (r->lscatt_ray_tracing2 && O->g.l3D)) { snprintf(O->err, sizeof O->err, "mode not built in the oracle"); return MCB_ERR_UNSUPPORTED; }
+  if ((r->lscattering_method1 || !r->lonly_LTE) && !O->has_gr) { snprintf(O->err, sizeof O->err, "per-grain mode without grain tables"); return MCB_ERR_STATE; }
+  if (r->loutput_mc || (r->lscatt_ray_tracing2 && O->g.l3D)) { snprintf(O->err, sizeof O->err, "mode not built in the oracle"); return MCB_ERR_UNSUPPORTED; }
   return MCB_OK;
 }
 

@@ -34,7 +34,8 @@ def test_library_exports_every_declared_symbol(lib):
 def test_struct_layout_matches_ctypes_mirror():
     """sizeof/offsetof from the real header (compiled with gcc) vs the ctypes Structures."""
     structs = {"mcb_grid": abi.mcb_grid, "mcb_opacity": abi.mcb_opacity, "mcb_emission": abi.mcb_emission,
-               "mcb_run_params": abi.mcb_run_params, "mcb_tallies": abi.mcb_tallies}
+               "mcb_run_params": abi.mcb_run_params, "mcb_tallies": abi.mcb_tallies,
+               "mcb_grains": abi.mcb_grains}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for sname, st in structs.items():
         lines.append(f'printf("{sname} %zu\\n", sizeof({sname}));')
