@@ -55,7 +55,8 @@ def load_library():
         lib.mcfost_b200_finalize.restype = None
         for fn in ("mcfost_b200_upload_grid", "mcfost_b200_upload_dark_zone", "mcfost_b200_upload_opacity",
                    "mcfost_b200_upload_emission", "mcfost_b200_upload_grains", "mcfost_b200_launch"):
-            getattr(lib, fn).argtypes = [C.c_void_p, C.c_void_p]
+            if hasattr(lib, fn):       # an older build given through MCFOST_B200_LIB (A/B timing) may lack the newest entry points
+                getattr(lib, fn).argtypes = [C.c_void_p, C.c_void_p]
         lib.mcfost_b200_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.mcfost_b200_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.mcfost_b200_sync.argtypes = [C.c_void_p]

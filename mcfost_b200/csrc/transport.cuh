@@ -281,8 +281,8 @@ __device__ __forceinline__ int im_reemission_LTE(const DevModel& m, const DevRun
 
 // =============================================================================
 // Per-grain modes: scattering method 1 (dust_transfer.f90:1291-1317) and the nLTE / qRE
-// re-emission branches (dust_transfer.f90:1353-1395).  Cold code: everything is __noinline__
-// and reads global memory, so the LTE / method-2 instruction footprint is unchanged.
+// re-emission branches (dust_transfer.f90:1353-1395).  Cold code: __noinline__, global-memory tables, and
+// compiled only into the GR = true instantiation of the kernel, so the LTE / method-2 kernels are unchanged.
 // =============================================================================
 #define MCB_AU_TO_CM_MUM2 ((149597870700.0 * 100.0) * (1.0e-4 * 1.0e-4))     /* AU_to_cm * mum_to_cm**2 */
 
@@ -440,10 +440,14 @@ __device__ __noinline__ void angle_diff_theta_grain(int lambda, int igrain, floa
 
 // dust_transfer.f90:1291-1317: scattering method 1.  Philox words of the interaction block:
 // x = grain draw, y = rand, z = rand2, w = phi draw.
+// (results come back by value: no local of the hot SCATTER / ABSORB phases has its address taken)
+struct Scat1Out { double u1, v1, w1, S0, S1, S2, S3; };
 template <int BANK>
-__device__ __noinline__ void scatter_method1(int lambda, int p_icell, uint4 b, bool pola, double* S,
-                                             double u, double v, double w, double& u1, double& v1, double& w1) {
+__device__ __noinline__ Scat1Out scatter_method1(int lambda, int p_icell, uint4 b, bool pola, double S0, double S1, double S2, double S3,
+                                                 double u, double v, double w) {
   const DevModel& m = c_m; const DevRun& r = c_r; const DevGrains& g = m.gr;
+  double S[4] = {S0, S1, S2, S3};
+  double u1, v1, w1;
   const int igrain = select_scattering_grain<BANK>(lambda, p_icell, u01(b.x));
   const float rand = u01(b.y), rand2 = u01(b.z), rand3 = u01(b.w);
   int itheta; double cospsi;
@@ -462,26 +466,30 @@ __device__ __noinline__ void scatter_method1(int lambda, int p_icell, uint4 b, b
     const double M34 = (double)__fsub_rn(__fmul_rn(-__ldg(g.s34 + q1), frac), __fmul_rn(__ldg(g.s34 + q0), frac_m1));
     stokes_update(mix(g.s11), mix(g.s12), mix(g.s22), mix(g.s33), M34, mix(g.s44), S, u, v, w, u1, v1, w1);
   }
+  return Scat1Out{u1, v1, w1, S[0], S[1], S[2], S[3]};
 }
 
 // dust_transfer.f90:1353-1395 when .not.lonly_LTE: energy kept by grains out of equilibrium, choice of
 // the grain regime, re-emission wavelength.  Returns the new wavelength, or 0 if the packet is dropped.
 // S0 is scaled in place; e_nRE returns this packet's contribution to E_abs_nRE.
+struct AbsOut { int lambda; double S0, e_nRE; };
 template <bool SM, int BANK>
-__device__ __noinline__ int absorb_grain_regimes(int idx, int p_icell, int lambda0, uint4 b, float sel, double& S0, double& e_nRE) {
+__device__ __noinline__ AbsOut absorb_grain_regimes(int idx, int p_icell, int lambda0, uint4 b, float sel, double S0) {
   const DevModel& m = c_m; const DevRun& r = c_r; const DevGrains& g = m.gr;
   const size_t cl = (size_t)idx + (size_t)m.n_cells * (lambda0 - 1);
+  AbsOut o = {0, S0, 0.0};
   if (r.lnRE) {
     const double pRE = __ldg(g.proba_abs_RE + cl);
-    e_nRE = S0 * (1.0 - pRE);
-    S0 = S0 * pRE;
-    if (S0 < MCB_TINY_REAL) return 0;
+    o.e_nRE = S0 * (1.0 - pRE);
+    o.S0 = S0 * pRE;
+    if (o.S0 < MCB_TINY_REAL) return o;
   }
   const float rand1 = u01(b.x), rand2 = u01(b.y);
-  if (r.lonly_nLTE) return im_reemission_NLTE<BANK>(idx, lambda0, rand1, rand2);
-  if ((double)sel <= __ldg(g.P_LTE + cl)) return im_reemission_LTE<SM>(m, r, idx, p_icell, rand2);
-  if ((double)sel <= __ldg(g.P_LTE_p_nLTE + cl)) return im_reemission_NLTE<BANK>(idx, lambda0, rand1, rand2);
-  return im_reemission_qRE<BANK>(idx, lambda0, rand1, rand2);
+  if (r.lonly_nLTE) o.lambda = im_reemission_NLTE<BANK>(idx, lambda0, rand1, rand2);
+  else if ((double)sel <= __ldg(g.P_LTE + cl)) o.lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, rand2);
+  else if ((double)sel <= __ldg(g.P_LTE_p_nLTE + cl)) o.lambda = im_reemission_NLTE<BANK>(idx, lambda0, rand1, rand2);
+  else o.lambda = im_reemission_qRE<BANK>(idx, lambda0, rand1, rand2);
+  return o;
 }
 
 // ---- output.f90:294-595 capteur, SED branch ------------------------------------
@@ -1004,7 +1012,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
 // =============================================================================
 // SCATTER: method 2 (dust_transfer.f90:1318-1351) + start of the next flight
 // =============================================================================
-template <class G, bool SM, int BANK>
+template <class G, bool SM, int BANK, bool GR>
 __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
@@ -1043,8 +1051,10 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
 #endif
       const double u = P.F(F_U, slot), v = P.F(F_V, slot), w = P.F(F_W, slot);
       double u1, v1, w1;
-      if (r.lscattering_method1) scatter_method1<BANK>(lambda, p_icell, b, POLA, S, u, v, w, u1, v1, w1);
-      else {
+      if (GR && r.lscattering_method1) {
+        const Scat1Out o = scatter_method1<BANK>(lambda, p_icell, b, POLA, S[0], S[1], S[2], S[3], u, v, w);
+        u1 = o.u1; v1 = o.v1; w1 = o.w1; S[0] = o.S0; S[1] = o.S1; S[2] = o.S2; S[3] = o.S3;
+      } else {
         const float rand = u01(b.x), rand2 = u01(b.y), rand3 = u01(b.z);
         int itheta; double cospsi;
         if (r.lmethod_aniso1) angle_diff_theta_pos<SM>(m, r.p_lambda_in, p_icell, rand, rand2, itheta, cospsi);
@@ -1070,7 +1080,7 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
 // =============================================================================
 // ABSORB: immediate re-emission, LTE (dust_transfer.f90:1353-1402) + start of the next flight
 // =============================================================================
-template <class G, bool SM, int BANK>
+template <class G, bool SM, int BANK, bool GR>
 __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
@@ -1095,7 +1105,7 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
     const uint4 bnext = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev + 2u, pk_lo, pk_hi, r.call_index);
 #endif
     int lambda;
-    if (r.lonly_LTE) {
+    if (!GR || r.lonly_LTE) {
       // b.x is rand1: drawn but unused in the high-memory LTE branch (thermal_emission.f90:739-765)
       lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, u01(b.y));
     } else {
@@ -1103,9 +1113,9 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
       // direction draws keep the words they have in the lonly_LTE case
       float sel = 0.0f;
       if (!r.lonly_nLTE) sel = u01(philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), (2u * ev + 1u) | 0x80000000u, pk_lo, pk_hi, r.call_index).x);
-      double S0 = P.F(F_S0, slot);
-      lambda = absorb_grain_regimes<SM, BANK>(idx, p_icell, misc_lambda(misc), b, sel, S0, e_nRE);
-      if (r.lnRE) P.F(F_S0, slot) = S0;
+      const AbsOut o = absorb_grain_regimes<SM, BANK>(idx, p_icell, misc_lambda(misc), b, sel, P.F(F_S0, slot));
+      lambda = o.lambda; e_nRE = o.e_nRE;
+      if (r.lnRE) P.F(F_S0, slot) = o.S0;
     }
     if (lambda == 0) { ++st.kill; nextq = Q_EMIT; }      // Stokes(1) < tiny_real: packet dropped (dust_transfer.f90:1361-1364)
     else {
@@ -1120,7 +1130,7 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
       nextq = Q_FLY;
     }
   }
-  if (r.lnRE) {      // E_abs_nRE (omp reduction in the reference, dust_transfer.f90:489): one atomic per warp
+  if (GR && r.lnRE) {      // E_abs_nRE (omp reduction in the reference, dust_transfer.f90:489): one atomic per warp
     for (int o = 16; o > 0; o >>= 1) e_nRE += __shfl_down_sync(0xffffffffu, e_nRE, o);
     if (lane == 0 && e_nRE != 0.0) atomicAdd(m.tally + m.lay.E_abs_nRE, e_nRE);
   }
@@ -1130,7 +1140,7 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
 // =============================================================================
 // The persistent photon-loop kernel: rounds of (claim a single-phase chunk -> run the phase -> regroup)
 // =============================================================================
-template <class G, bool SM, int BANK>
+template <class G, bool SM, int BANK, bool GR>
 __global__ void __launch_bounds__(MC_BLOCK, 1)
 mc_photon_loop_kernel() {
   const DevModel& m = c_m; const DevRun& r = c_r;
@@ -1198,8 +1208,8 @@ mc_photon_loop_kernel() {
       int nextq;
       switch (qi) {
         case Q_EMIT: nextq = phase_emit<G, SM, BANK>(slot, mine, st); break;
-        case Q_ABS:  nextq = phase_absorb<G, SM, BANK>(slot, mine, st); break;
-        case Q_SCAT: nextq = phase_scatter<G, SM, BANK>(slot, mine, st); break;
+        case Q_ABS:  nextq = phase_absorb<G, SM, BANK, GR>(slot, mine, st); break;
+        case Q_SCAT: nextq = phase_scatter<G, SM, BANK, GR>(slot, mine, st); break;
         default:     nextq = phase_fly<G, SM, BANK>(slot, mine, st); break;
       }
       if (!mine) nextq = Q_NONE;

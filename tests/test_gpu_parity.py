@@ -98,6 +98,9 @@ def test_empty_and_error_paths():
     assert len(G.cross_cell(e, e, e, e, e, e, np.zeros(0, np.int32))["l"]) == 0
     with pytest.raises(api.McfostB200Error) as err:
         G.mc_photon_loop(1, 1, 10, lonly_LTE=0)
+    assert err.value.code == 6         # MCB_ERR_STATE: nLTE / nRE re-emission needs upload_grains first
+    with pytest.raises(api.McfostB200Error) as err:
+        G.mc_photon_loop(1, 1, 10, loutput_mc=1, letape_th=0, lmono=1, lmono0=1)
     assert err.value.code == 5         # MCB_ERR_UNSUPPORTED: fails loudly, no silent fallback
     with pytest.raises(api.McfostB200Error):
         G.mc_photon_loop(P.n_lambda + 1, 1, 10)
