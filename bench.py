@@ -35,6 +35,20 @@ def b_packet(n_cells):
     return np.ceil(np.log2(n_cells)) * 8.0 + 96.0
 
 
+def measured_traffic(packets_per_launch):
+    """DRAM bytes per launch of the photon-loop kernel from the committed ncu launch list of this same
+    command (profiles/r01_traffic.json); None when it was taken at another packet budget."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        if int(t["packets_per_launch"]) == int(packets_per_launch):
+            return float(t["dram_bytes_per_launch_mean"])
+    except Exception:
+        pass
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -255,7 +269,8 @@ def gpu_arm(args):
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(args.steps * 2),          # mc_photon_loop_kernel + fill_int_kernel (xT_ech reset) per step
                 "clocks": sampler.summary(),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(packets_per_step / world),
+                             "algorithmic_bytes_per_launch": nb_per_gpu,
                              "peak_source": peak_src, "kernel": "mc_photon_loop_kernel<GeomCyl<false,true>,true>", "kernel_ms": last_ms,
                              "note": "algorithmic bytes (SURVEY 8d) / kernel time; tables are L2-resident so the path is latency/atomic-bound, not HBM-bound",
                              "steps_per_s": stats[1] / world / (last_ms * 1e-3), "interactions_per_s": stats[2] / world / (last_ms * 1e-3),
