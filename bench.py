@@ -173,6 +173,9 @@ def gpu_arm(args):
     # drain-out of step i (a few very long-lived packets, most SMs already free) overlaps the start of
     # step i+1.  Every step is a complete, separately reduced mc_photon_loop call.
     loops = [loop] + [api.PhotonLoop(P, device=local, rank=rank, n_ranks=world) for _ in range(max(1, args.pipeline) - 1)]
+    if len(loops) > 1 and args.overlap_sms > 0:
+        for l in loops:
+            l.set_overlap(args.overlap_sms, max(1, args.overlap_sms // (len(loops) - 1)))   # main launches leave these SMs to the straggler launches of the other handles
     dev = torch.device("cuda", local)
     n2 = args.n2 * world                      # weak scaling: 128/world chunks x (n2*world) packets per rank
     streams = [torch.cuda.ExternalStream(l.stream(), device=dev) for l in loops]
@@ -226,6 +229,7 @@ def gpu_arm(args):
     # ---- e2e: the reference-facing blocking call with HOST buffers (emission tables H2D, tallies D2H) ----
     e2e_steps = max(1, min(args.steps, 3))
     barrier()
+    loop.set_overlap(0)                       # a blocking call has nothing to overlap with: all SMs to the main launch
     t0 = time.perf_counter()
     h2d = d2h = 0
     for i in range(e2e_steps):
@@ -264,10 +268,10 @@ def gpu_arm(args):
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "G1 ref4.1-like: cylindrical 100x70x1, 50 lambda, n_T=100, thermal step, tau_mid(0.81um)=1e5, dark zone tau>1500",
-                           "packets_per_step": int(packets_per_step), "parallelism": f"packets x{world} (replicated grid, 1 all-reduce/step)", "pipeline": f"{len(loops)} handles alternate so that the drain-out of one step overlaps the next",
+                           "packets_per_step": int(packets_per_step), "parallelism": f"packets x{world} (replicated grid, 1 all-reduce/step)", "pipeline": f"{len(loops)} handles alternate so that the drain-out of one step overlaps the next" + (f"; {args.overlap_sms} SMs reserved for the straggler launches" if len(loops) > 1 and args.overlap_sms > 0 else ""),
                            "l2_policy": "tallies are re-zeroed (memset) every step; working set is L2-resident by design (0.5 MB tables)"},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-                "gpu_launches": int(args.steps * 2),          # mc_photon_loop_kernel + fill_int_kernel (xT_ech reset) per step
+                "gpu_launches": int(args.steps * (3 if (len(loops) > 1 and args.overlap_sms > 0) else 2)),   # per step: mc_photon_loop_kernel (+ its straggler launch) + fill_int_kernel (xT_ech reset)
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(packets_per_step / world),
                              "algorithmic_bytes_per_launch": nb_per_gpu,
@@ -293,6 +297,7 @@ def main():
     ap.add_argument("--cpu-n2", type=int, default=8000, help="packets per chunk of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--pipeline", type=int, default=2, help="handles used alternately (1 = strictly serial steps)")
+    ap.add_argument("--overlap-sms", type=int, default=16, help="SMs reserved for straggler launches when pipelining (0 = off)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -282,14 +282,26 @@ int mcfost_b200_run(mcb_handle *h, const mcb_run_params *r, mcb_tallies *out);
  * it in place (one NCCL call), then download. */
 int mcfost_b200_launch(mcb_handle *h, const mcb_run_params *r);
 int mcfost_b200_sync(mcb_handle *h);
+/* Overlap of successive calls (no reference counterpart).  When the packet counter of a thermal call runs
+ * dry, ~15 % of the packets in flight belong to the longest-lived 0.1 % (length-biased sampling): ~2 % of the
+ * call's events, but up to 3e5 sequential events per packet, i.e. ~1 s during which most SMs idle.  With
+ * n_sms_reserved > 0 the main launch of every following call uses all but n_sms_reserved SMs and, once its
+ * counter is dry, hands its last packets (<= 256 per SM) to a second launch of n_sms_straggler blocks, so that
+ * calls issued on OTHER handles (own streams) can start on the rest of the GPU while this one finishes.
+ * With k handles used in turn, n_sms_straggler = n_sms_reserved / (k - 1) keeps every launch resident.
+ * Results are unchanged; (0, 0) (default) turns it off.  n_sms_straggler <= n_sms_reserved <= half the SMs;
+ * only calls that count packets SENT (thermal, image) hand over. */
+int mcfost_b200_set_overlap(mcb_handle *h, int n_sms_reserved, int n_sms_straggler);
 int mcfost_b200_tally_buffers(mcb_handle *h, void **d_f64, int64_t *n_f64,
                               void **d_f32, int64_t *n_f32);
 int mcfost_b200_download(mcb_handle *h, const mcb_run_params *r, mcb_tallies *out);
 /* device time of the last launch in ms (CUDA events on the handle's stream) */
 int mcfost_b200_last_kernel_ms(mcb_handle *h, float *ms);
-/* scheduling diagnostics of the last launch (not in the reference): out[10] =
- * {ms until the packet counter ran dry, kernel ms, chunk visits[4], valid lanes[4]}
- * for the phases EMIT, ABSORB, SCATTER, FLY */
+/* scheduling diagnostics of the last launch (not in the reference): out[14] =
+ * {ms until the packet counter ran dry, kernel ms, chunk visits[4], valid lanes[4]
+ * for the phases EMIT, ABSORB, SCATTER, FLY, packets handed to the straggler launch,
+ * ms until the main launch ended, ms until the straggler launch ended,
+ * device timer at the start of the main launch in ms}; out must hold 16 doubles */
 int mcfost_b200_debug_counters(mcb_handle *h, double *out);
 /* cudaStream_t of the handle, as an integer, so torch can wait on it */
 int mcfost_b200_stream(mcb_handle *h, uint64_t *stream);

@@ -26,7 +26,7 @@ EXPORTS = (
     "mcfost_b200_upload_grid", "mcfost_b200_upload_dark_zone", "mcfost_b200_upload_opacity",
     "mcfost_b200_upload_emission", "mcfost_b200_upload_grains", "mcfost_b200_run", "mcfost_b200_launch", "mcfost_b200_sync",
     "mcfost_b200_tally_buffers", "mcfost_b200_download", "mcfost_b200_last_kernel_ms", "mcfost_b200_stream",
-    "mcfost_b200_debug_counters",
+    "mcfost_b200_debug_counters", "mcfost_b200_set_overlap",
     "mcfost_b200_cross_cell", "mcfost_b200_index_cell", "mcfost_b200_move_to_grid",
     "mcfost_b200_optical_length_tot", "mcfost_b200_physical_length",
 )
@@ -60,6 +60,8 @@ def load_library():
         lib.mcfost_b200_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.mcfost_b200_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.mcfost_b200_sync.argtypes = [C.c_void_p]
+        if hasattr(lib, "mcfost_b200_set_overlap"):
+            lib.mcfost_b200_set_overlap.argtypes = [C.c_void_p, C.c_int, C.c_int]
         lib.mcfost_b200_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         lib.mcfost_b200_stream.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         lib.mcfost_b200_tally_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
@@ -177,6 +179,10 @@ class PhotonLoop:
     def sync(self):
         self._check(self.lib.mcfost_b200_sync(self.h))
 
+    def set_overlap(self, n_sms_reserved, n_sms_straggler=0):
+        """Reserve SMs for the straggler launches so that calls on several handles overlap (0 = off)."""
+        self._check(self.lib.mcfost_b200_set_overlap(self.h, int(n_sms_reserved), int(n_sms_straggler)))
+
     def download(self, r=None, want_xI=True):
         r = r or self._last_run
         t = self._tallies(r, want_xI)
@@ -190,14 +196,15 @@ class PhotonLoop:
 
     def debug_counters(self):
         """Scheduling diagnostics of the last launch (see include/mcfost_b200.h)."""
-        out = (C.c_double * 10)()
+        out = (C.c_double * 16)()
         self.lib.mcfost_b200_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         self._check(self.lib.mcfost_b200_debug_counters(self.h, out))
         v = list(out)
         names = ("EMIT", "ABSORB", "SCATTER", "FLY")
         return {"steady_ms": v[0], "kernel_ms": v[1],
                 "chunk_fill": {n: (v[6 + i] / v[2 + i] if v[2 + i] else 0.0) for i, n in enumerate(names)},
-                "visits": {n: v[2 + i] for i, n in enumerate(names)}}
+                "visits": {n: v[2 + i] for i, n in enumerate(names)}, "parked": v[10],
+                "main_end_ms": v[11], "straggler_end_ms": v[12], "t0_ms": v[13], "straggler_start_ms": v[14]}
 
     def stream(self):
         s = C.c_uint64()

@@ -29,13 +29,19 @@ int mcfost_b200_init(int device, mcb_handle** out) {
   mcb_handle* h = new mcb_handle();
   memset(&h->m, 0, sizeof h->m);
   h->device = device;
-  { static int next_bank = 0; h->bank = next_bank++; }      // up to 4 handles per process can have launches in flight together
+  { static int next_bank = 0; h->bank = next_bank++; }      // handles share MCB_BANKS constant banks round-robin (guarded in mc_kernel.cu)
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return MCB_ERR_CUDA; }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   h->n_sm = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MCB_ERR_CUDA; }
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&h->stream_hi, cudaStreamNonBlocking, hi) != cudaSuccess) { delete h; return MCB_ERR_CUDA; }
+    cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_strag, cudaEventDisableTiming);
+  }
   *out = h;
   return MCB_OK;
 }
@@ -46,6 +52,10 @@ void mcfost_b200_finalize(mcb_handle* h) {
   cudaStreamSynchronize(h->stream);
   for (auto& kv : h->bufs) if (kv.second) cudaFree(kv.second);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  cudaStreamSynchronize(h->stream_hi);
+  mcb_forget_handle(h);
+  cudaEventDestroy(h->ev_main); cudaEventDestroy(h->ev_strag);
+  cudaStreamDestroy(h->stream_hi);
   cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -53,13 +63,15 @@ void mcfost_b200_finalize(mcb_handle* h) {
 // Scheduling diagnostics of the last launch (not part of the reference interface):
 // out[0] = ms from kernel start until the global packet counter ran dry (steady-state phase),
 // out[1] = ms of the whole kernel by the device clock, out[2..5] = chunk visits per phase
-// (EMIT, ABSORB, SCATTER, FLY), out[6..9] = valid lanes summed over those visits.
+// (EMIT, ABSORB, SCATTER, FLY), out[6..9] = valid lanes summed over those visits,
+// out[10] = packets handed over to the straggler launch (mcfost_b200_set_overlap), out[11] / out[12] = ms until the
+// last block of the main launch / of the straggler launch left.
 int mcfost_b200_debug_counters(mcb_handle* h, double* out) {
   if (!h || !out) return MCB_ERR_BAD_ARG;
   if (!h->launched || !h->m.work) return fail(h, MCB_ERR_STATE, "no launch yet");
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
-  const int n = 16 + 2 * h->n_photons_loop_alloc;
+  const int n = 48 + 2 * h->n_photons_loop_alloc;
   std::vector<unsigned long long> w((size_t)n);
   CK(cudaMemcpy(w.data(), h->m.work, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   const int b = 2 + 2 * h->n_photons_loop_alloc;
@@ -67,6 +79,14 @@ int mcfost_b200_debug_counters(mcb_handle* h, double* out) {
   out[0] = (w[1] == ~0ull || w[1] == 0ull) ? -1.0 : ((double)w[1] - t0) * 1e-6;
   out[1] = (t1 - t0) * 1e-6;
   for (int k = 0; k < 8; ++k) out[2 + k] = (double)w[b + 2 + k];
+  out[10] = (double)w[b + 10];
+  out[11] = w[b + 11] ? ((double)w[b + 11] - t0) * 1e-6 : -1.0;      // ms until the last block of the main launch left
+  out[12] = w[b + 13] ? ((double)w[b + 13] - t0) * 1e-6 : -1.0;      // ms until the straggler launch ended
+  out[14] = w[b + 14] ? ((double)w[b + 14] - t0) * 1e-6 : -1.0;      // ms until the straggler launch started
+  out[13] = t0 * 1e-6;      // device globaltimer at the start of the main launch, ms (to line up calls on two handles)
+  if (getenv("MCB_DRAIN_PROBE_PRINT")) {      // development builds (-DMCB_DRAIN_PROBE) only
+    for (int k = 0; k < 11; ++k) fprintf(stderr, "drain probe: live <= %4d  max %8.2f ms  mean %8.2f ms after dry\n", k < 10 ? (512 >> k) : 0, (double)w[b + 16 + k] * 1e-6, (double)w[b + 27 + k] * 1e-6 / (double)h->n_sm);
+  }
   return MCB_OK;
 }
 
@@ -356,7 +376,7 @@ static int setup_tallies(mcb_handle* h, const mcb_run_params* r, bool lxJ, bool 
   if ((rc = reserve(h, "xT_1g", (size_t)n_1g, &m.gr.xT_1g))) return rc;
   if ((rc = reserve(h, "xT_1g_nRE", (size_t)n_1g_nRE, &m.gr.xT_1g_nRE))) return rc;
   h->n_1g = n_1g; h->n_1g_nRE = n_1g_nRE;
-  if ((rc = reserve(h, "work", (size_t)(16 + 2 * r->n_photons_loop), &m.work))) return rc;
+  if ((rc = reserve(h, "work", (size_t)(48 + 2 * r->n_photons_loop), &m.work))) return rc;
   h->n_tally = L.total; h->n_xI = n_xI; h->lay_xJ = lxJ; h->lay_nsed = n_sed; h->n_type_flux = n_type_flux;
   if (realloc_ || r->reset_tallies) {
     CK(cudaMemsetAsync(m.tally, 0, (size_t)L.total * sizeof(double), h->stream));
@@ -367,7 +387,7 @@ static int setup_tallies(mcb_handle* h, const mcb_run_params* r, bool lxJ, bool 
     if (n_1g_nRE) fill_int_kernel<<<256, 256, 0, h->stream>>>(m.gr.xT_1g_nRE, n_1g_nRE, 2);
   }
   CK(cudaMemsetAsync(m.tally + L.E_abs_nRE, 0, sizeof(double), h->stream));      // E_abs_nRE = 0.0 at every call (dust_transfer.f90:505)
-  CK(cudaMemsetAsync(m.work, 0, (size_t)(16 + 2 * r->n_photons_loop) * sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(m.work, 0, (size_t)(48 + 2 * r->n_photons_loop) * sizeof(unsigned long long), h->stream));
   h->n_photons_loop_alloc = r->n_photons_loop;
   CK(cudaMemsetAsync(m.work + 1, 0xFF, sizeof(unsigned long long), h->stream));      // work[1] = ~0: "counter not dry yet"
   return MCB_OK;
@@ -459,6 +479,9 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   dr.n_per_chunk = (unsigned long long)r->n_photons2 < dr.sent_lim ? (unsigned long long)r->n_photons2 : dr.sent_lim;
   dr.n_packets_total = dr.count_sent ? (unsigned long long)n_local * dr.n_per_chunk : 0ull;
   dr.nb_proc_equiv = (double)r->n_ranks;
+  dr.park_enable = (h->overlap_sms > 0 && dr.count_sent) ? 1 : 0;
+  dr.park_live = 256;
+  { const char* e = getenv("MCB_PARK_LIVE"); if (e && atoi(e) > 0 && atoi(e) <= 256) dr.park_live = atoi(e); }      // tuning knob
   { const char* e = getenv("MCB_DEBUG_ABORT_DRY"); dr.debug_abort_dry = (e && e[0] == '1') ? 1 : 0; }   // profiling aid only: tallies are incomplete
   int rc = setup_tallies(h, r, dr.lxJ != 0, rt1, dr.n_type_flux, dr.rt2 != 0);
   if (rc) return rc;
@@ -475,6 +498,15 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   rc = mcb_launch_mc(h, dr);
   if (rc) return rc;
   h->launched = true;
+  return MCB_OK;
+}
+
+int mcfost_b200_set_overlap(mcb_handle* h, int n_sms_reserved, int n_sms_straggler) {
+  if (!h) return MCB_ERR_BAD_ARG;
+  if (n_sms_reserved == 0) { h->overlap_sms = 0; h->straggler_sms = 0; return MCB_OK; }
+  if (n_sms_straggler <= 0) n_sms_straggler = n_sms_reserved;
+  if (n_sms_reserved < 0 || n_sms_reserved > h->n_sm / 2 || n_sms_straggler > n_sms_reserved) return fail(h, MCB_ERR_BAD_ARG, "set_overlap: 0 <= straggler SMs <= reserved SMs <= half the SMs");
+  h->overlap_sms = n_sms_reserved; h->straggler_sms = n_sms_straggler;
   return MCB_OK;
 }
 

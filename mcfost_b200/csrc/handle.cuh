@@ -16,6 +16,8 @@ struct mcb_handle {
   int bank = 0;                           // constant-memory bank of this handle's launches (see transport.cuh)
   int n_sm = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_hi = nullptr;       // highest priority: straggler launches are dispatched before pending main blocks of other handles
+  cudaEvent_t ev_main = nullptr, ev_strag = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   mcb::DevModel m;
   mcb::GridKind gk = mcb::GK_CYL2D;
@@ -29,6 +31,8 @@ struct mcb_handle {
   int lay_nsed = -1;
   int n_photons_loop_alloc = 0;
   int n_type_flux = 1;
+  int straggler_sms = 0;                  // blocks of this handle's straggler launch
+  int overlap_sms = 0;                    // mcfost_b200_set_overlap: SMs reserved for straggler launches (0 = off)
   std::vector<double> host_kappa_factor;  // host copies used to build kf_dark (kappa_factor | dark flag)
   std::vector<uint8_t> host_dark;
   bool kf_dark_stale = true;
@@ -75,3 +79,4 @@ static int reserve(mcb_handle* h, const char* name, size_t n, T** dst) {
 
 // defined in mc_kernel.cu
 int mcb_launch_mc(mcb_handle* h, const mcb::DevRun& dr);
+void mcb_forget_handle(const mcb_handle* h);

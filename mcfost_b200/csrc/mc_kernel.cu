@@ -8,6 +8,18 @@
 
 using namespace mcb;
 
+// End-of-main-launch events of the last two calls that hand stragglers over (any handle).  A new main launch waits
+// for the one before the previous: at most ONE main launch is pending while another runs, so the SMs the
+// running one leaves free go to straggler launches (high-priority stream), not to a third call's blocks.
+static cudaEvent_t g_main_hist[2] = {nullptr, nullptr};
+void mcb_forget_handle(const mcb_handle* h) {
+  for (auto& e : g_main_hist) if (e == h->ev_main) e = nullptr;
+}
+
+// last user of each constant bank (GR kernels have their own copies of the symbols' users, same banks)
+struct BankGuard { const mcb_handle* owner = nullptr; cudaEvent_t done = nullptr; };
+static BankGuard bank_guard[2 * MCB_BANKS];
+
 template <class G, bool SM, int BANK, bool GR>
 static int launch_bank(mcb_handle* h, const DevRun& dr) {
   const size_t smem = (SM ? (size_t)h->m.sm.total_words * 8 : 0) + pool_bytes(dr.lsepar_pola != 0);
@@ -21,31 +33,62 @@ static int launch_bank(mcb_handle* h, const DevRun& dr) {
     if (!q) { CK(cudaMalloc(&q, bytes)); h->buf_bytes["quv"] = bytes; }
     h->m.quv = (double*)q;
   }
-  // the previous launch of this handle must be over before its constant bank is rewritten
+  if (dr.park_enable) {
+    void*& pk = h->bufs["park"];
+    const size_t bytes = (size_t)h->n_sm * PARK_LIVE * PARK_REC * sizeof(double);
+    if (pk && h->buf_bytes["park"] != bytes) { cudaFree(pk); pk = nullptr; }
+    if (!pk) { CK(cudaMalloc(&pk, bytes)); h->buf_bytes["park"] = bytes; }
+    h->m.park = (double*)pk;
+  }
+  // the previous launch of this handle must be over before its constant bank is rewritten; so must the last
+  // launch of any OTHER handle that maps to the same bank (more handles than banks)
   CK(cudaStreamSynchronize(h->stream));
+  {
+    BankGuard& g = bank_guard[BANK + (GR ? MCB_BANKS : 0)];
+    if (g.owner && g.owner != h && g.done) CK(cudaEventSynchronize(g.done));
+    if (!g.done) CK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+  }
   const int bank = BANK;
   CK(cudaMemcpyToSymbolAsync(c_mm, &h->m, sizeof(DevModel), (size_t)bank * sizeof(DevModel), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyToSymbolAsync(c_rr, &dr, sizeof(DevRun), (size_t)bank * sizeof(DevRun), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));          // dr / h->m are host stack / heap values
   int blocks = h->n_sm;                          // persistent: one 512-thread block (1024 packets in flight) per SM
+  const int n2 = dr.park_enable ? h->straggler_sms : 0;    // blocks of the straggler launch (mcfost_b200_set_overlap)
+  if (dr.park_enable) blocks -= h->overlap_sms;            // SMs the main launch leaves to straggler launches
   // test knob: fewer blocks = fewer packets in flight.  Immediate re-emission reads RUNNING tallies, so a
   // run whose packet budget is not >> 1024 x blocks sees them at a different stage than a 16-thread CPU run.
   { const char* e = getenv("MCB_BLOCKS"); if (e && atoi(e) > 0 && atoi(e) < blocks) blocks = atoi(e); }
+  if (n2 > 0 && g_main_hist[0] && g_main_hist[0] != h->ev_main) CK(cudaStreamWaitEvent(h->stream, g_main_hist[0], 0));
   CK(cudaEventRecord(h->ev0, h->stream));
-  kern<<<blocks, MC_BLOCK, smem, h->stream>>>();
+  kern<<<blocks, MC_BLOCK, smem, h->stream>>>(0);
   CK(cudaGetLastError());
+  if (n2 > 0) {      // the stragglers the main launch parked, on the SMs the main launches leave free.  Highest
+    // stream priority: when SMs free up, these few blocks go before the pending main blocks of other handles.
+    CK(cudaEventRecord(h->ev_main, h->stream));
+    g_main_hist[0] = g_main_hist[1]; g_main_hist[1] = h->ev_main;
+    CK(cudaStreamWaitEvent(h->stream_hi, h->ev_main, 0));
+    kern<<<n2, MC_BLOCK, smem, h->stream_hi>>>(1);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev_strag, h->stream_hi));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_strag, 0));      // everything later on the handle's stream is ordered after it
+  }
   CK(cudaEventRecord(h->ev1, h->stream));
+  { BankGuard& g = bank_guard[BANK + (GR ? MCB_BANKS : 0)]; g.owner = h; CK(cudaEventRecord(g.done, h->stream)); }
   return MCB_OK;
 }
 
 template <class G, bool SM>
 static int launch_one(mcb_handle* h, const DevRun& dr) {
-  return (h->bank % MCB_BANKS) == 0 ? launch_bank<G, SM, 0, false>(h, dr) : launch_bank<G, SM, 1, false>(h, dr);
+  switch (h->bank % MCB_BANKS) {
+    case 0:  return launch_bank<G, SM, 0, false>(h, dr);
+    case 1:  return launch_bank<G, SM, 1, false>(h, dr);
+    default: return launch_bank<G, SM, 2, false>(h, dr);
+  }
 }
 // per-grain modes (scattering method 1, nLTE / qRE re-emission): tables in global memory, GR = true kernels
 template <class G>
 static int launch_grains(mcb_handle* h, const DevRun& dr) {
-  return (h->bank % MCB_BANKS) == 0 ? launch_bank<G, false, 0, true>(h, dr) : launch_bank<G, false, 1, true>(h, dr);
+  return (h->bank % 2) == 0 ? launch_bank<G, false, 0, true>(h, dr) : launch_bank<G, false, 1, true>(h, dr);      // two banks are enough here (guarded)
 }
 
 int mcb_launch_mc(mcb_handle* h, const DevRun& dr) {

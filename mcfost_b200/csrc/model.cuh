@@ -109,6 +109,7 @@ struct DevModel {
   float *I_spec, *I_spec_star;   // rt2 accumulators (dust_ray_tracing.f90:44-45)
   double *quv;              // Stokes Q,U,V of the packets in flight: (n_blocks, 3, NP), only with lsepar_pola
   unsigned long long *work; // [0] = next work item; [2+2c], [3+2c] = sent / received of local chunk c
+  double *park;             // parked stragglers: (PARK_REC doubles) x capacity, see transport.cuh
   SmemLayout sm;
   DevGrains gr;
 };
@@ -133,6 +134,8 @@ struct DevRun {
   unsigned long long n_per_chunk;       // count_sent: min(n_photons2, sent_lim)
   unsigned long long n_packets_total;   // count_sent: n_local_chunks * n_per_chunk
   double nb_proc_equiv;                 // n_ranks: scales the local tally in Temp_LTE
+  int park_live;                        // hand over when at most this many packets of a block are in flight (<= PARK_LIVE)
+  int park_enable;                      // hand stragglers over to a second small launch (count_sent modes only)
   int debug_abort_dry;                  // profiling aid (env MCB_DEBUG_ABORT_DRY): stop when the packet counter runs dry
 };
 

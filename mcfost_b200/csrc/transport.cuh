@@ -40,9 +40,9 @@ namespace mcb {
 // The model and run parameters of the launch in flight live in constant memory (written by
 // mcb_launch_mc on the handle's stream): every phase function reads them through the constant
 // bank without threading pointers through the non-inlined calls.  There are MCB_BANKS copies so
-// that launches of two handles can be in flight together (the drain-out of one call overlaps
-// the next call of the other handle).
-constexpr int MCB_BANKS = 2;
+// that launches of up to three handles can be in flight together (the drain-out of one call overlaps
+// the next calls of the other handles); mc_kernel.cu guards a bank against a second concurrent user.
+constexpr int MCB_BANKS = 3;
 __constant__ DevModel c_mm[MCB_BANKS];
 __constant__ DevRun c_rr[MCB_BANKS];
 // BANK is a template parameter of every function below that touches the constants, so that
@@ -250,16 +250,26 @@ __device__ __forceinline__ void scatter_stokes(int lambda, int itheta, float fra
 
 // ---- thermal_emission.f90:649-771 Temp_LTE + im_reemission_LTE (high-memory
 // branch): new wavelength index ------------------------------------------------
+// The three global loads it starts from (running tally, cached temperature index, cell volume) are passed in
+// so that the caller can issue them BEFORE the Philox blocks of the event: one L2 round trip of the dependent
+// chain instead of three (matters for the last, latency-bound packets of a call).
+struct LtePre { double xkj, vol; int Ti; };
+__device__ __forceinline__ LtePre lte_prefetch(const DevModel& m, int idx) {
+  LtePre p;
+  p.xkj = __ldcg(m.tally + m.lay.xKJ + idx);      // running tally: L2-coherent load (the adds are L2 atomics)
+  p.Ti = __ldcg(m.xT_ech + idx);
+  p.vol = __ldg(m.volume + idx);
+  return p;
+}
 template <bool SM>
-__device__ __forceinline__ int im_reemission_LTE(const DevModel& m, const DevRun& r, int idx, int p_icell, float rand2) {
-  // running tally: L2-coherent load (the adds are L2 atomics)
-  double Qheat = __ldcg(m.tally + m.lay.xKJ + idx) * r.nb_proc_equiv * m.L_packet_th / __ldg(m.volume + idx);
+__device__ __forceinline__ int im_reemission_LTE(const DevModel& m, const DevRun& r, int idx, int p_icell, float rand2, const LtePre pre) {
+  double Qheat = pre.xkj * r.nb_proc_equiv * m.L_packet_th / pre.vol;
   int Ti = 2;
   double frac_T2 = 0.0;       // `frac` is left undefined by the reference at T_min; 0 chosen (same as the oracle)
   if (!(Qheat < MCB_TINY_DP)) {
     double log_Qheat = mcb_log(Qheat);
     if (!(log_Qheat < t_logQ<SM>(m, 1, p_icell))) {
-      Ti = __ldcg(m.xT_ech + idx);
+      Ti = pre.Ti;
       while ((t_logQ<SM>(m, Ti, p_icell) < log_Qheat) && (Ti < m.n_T)) ++Ti;
       // another warp may have cached an index computed from a larger running tally: step back down
       while (Ti > 2 && !(t_logQ<SM>(m, Ti - 1, p_icell) < log_Qheat)) --Ti;
@@ -486,7 +496,7 @@ __device__ __noinline__ AbsOut absorb_grain_regimes(int idx, int p_icell, int la
   }
   const float rand1 = u01(b.x), rand2 = u01(b.y);
   if (r.lonly_nLTE) o.lambda = im_reemission_NLTE<BANK>(idx, lambda0, rand1, rand2);
-  else if ((double)sel <= __ldg(g.P_LTE + cl)) o.lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, rand2);
+  else if ((double)sel <= __ldg(g.P_LTE + cl)) o.lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, rand2, lte_prefetch(m, idx));
   else if ((double)sel <= __ldg(g.P_LTE_p_nLTE + cl)) o.lambda = im_reemission_NLTE<BANK>(idx, lambda0, rand1, rand2);
   else o.lambda = im_reemission_qRE<BANK>(idx, lambda0, rand1, rand2);
   return o;
@@ -627,6 +637,14 @@ constexpr int MC_BLOCK = MCB_BLOCK_T;       // threads per block (one block per 
 constexpr int NP = 1024;            // packets in flight per block
 constexpr int FLY_STEPS = MCB_FLY_STEPS_T;        // max cell crossings per FLY visit
 constexpr unsigned DRAIN_LIVE = 96; // live packets per block below which the pool is considered to be draining out
+// Straggler hand-over (DevRun.park_enable): once the packet counter is dry and at most DevRun.park_live (<= PARK_LIVE)
+// packets of a block are still in flight, the block writes them to a global buffer and exits; a second, small launch
+// of the same kernel (adopt = 1) takes them from that buffer instead of emitting new packets and finishes them on a
+// few SMs, while the next call's main launch (another handle, another stream) already owns the rest of the GPU.
+// Why: when the counter runs dry, ~15 % of the slots hold packets of the longest-lived 0.1 % (an in-flight packet is
+// a length-biased sample); their remaining events are ~30 ms worth of throughput but ~1 s of dependent latency.
+constexpr unsigned PARK_LIVE = 256;
+constexpr int PARK_REC = 20;        // doubles per parked packet: 11 F fields | 10 u32 (9 U fields, queue) | Q,U,V | pad
 
 enum { F_PX = 0, F_PY, F_PZ, F_OX, F_OY, F_OZ, F_U, F_V, F_W, F_S0, F_EXTR };
 // Stokes Q,U,V of packet `slot` of this block: quv[(blockIdx.x*3 + k)*NP + slot]
@@ -654,6 +672,8 @@ struct Pool {
   __device__ __forceinline__ volatile unsigned& TAIL(int queue) const { return ctl[NQ + queue]; }
   __device__ __forceinline__ volatile unsigned& LIVE() const { return ctl[8]; }
   __device__ __forceinline__ volatile unsigned& BUSY() const { return ctl[9]; }
+  __device__ __forceinline__ volatile unsigned& PARK() const { return ctl[10]; }   // this block is handing its packets over
+  __device__ __forceinline__ volatile unsigned& DRYF() const { return ctl[11]; }   // the global packet counter ran dry
 };
 
 // misc word: lambda (10 bits) | star 1 | scatt 1 | ISM 1 | i_star_hit 4 | chunk 15
@@ -752,7 +772,7 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
       if ((int)lane == leader) base = atomicAdd(m.work, (unsigned long long)__popc(need));
       base = __shfl_sync(0xffffffffu, base, leader);
       const unsigned long long g = base + __popc(need & ((1u << lane) - 1u));
-      if (valid && g >= r.n_packets_total) atomicMin(m.work + 1, (unsigned long long)globaltimer_ns());     // diagnostics: start of the drain-out
+      if (valid && g >= r.n_packets_total) { atomicMin(m.work + 1, (unsigned long long)globaltimer_ns()); P.DRYF() = 1u; }     // start of the drain-out
       if (valid && g < r.n_packets_total) {
         const unsigned long long lc = g / r.n_per_chunk;
         idx_in_chunk = g % r.n_per_chunk;
@@ -1096,6 +1116,7 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
     const int idx = tally_index(m, cell);
     const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
     ++st.abs_;
+    const LtePre pre = lte_prefetch(m, idx);      // in flight while the Philox blocks are computed
     const uint32_t pk_lo = P.U(U_PKLO, slot), pk_hi = P.U(U_PKHI, slot), ev = P.U(U_EV, slot);
 #ifdef MCB_PHILOX2
     uint4 b, bnext;      // interaction block of flight ev, flight block of ev+1
@@ -1107,7 +1128,7 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
     int lambda;
     if (!GR || r.lonly_LTE) {
       // b.x is rand1: drawn but unused in the high-memory LTE branch (thermal_emission.f90:739-765)
-      lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, u01(b.y));
+      lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, u01(b.y), pre);
     } else {
       // the grain-regime draw (dust_transfer.f90:1379) has its own Philox block, so rand / rand2 / the
       // direction draws keep the words they have in the lonly_LTE case
@@ -1138,24 +1159,73 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
 }
 
 // =============================================================================
+// ADOPT (straggler launch): a free slot takes the next packet the main launch parked
+// =============================================================================
+template <bool SM, int BANK>
+__device__ __noinline__ int phase_adopt(int slot, bool valid) {
+  const DevModel& m = c_m; const DevRun& r = c_r;
+  const Pool P = make_pool<SM, BANK>();
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned need = __ballot_sync(0xffffffffu, valid);
+  if (!need) return Q_NONE;
+  unsigned long long* park_count = m.work + (12 + 2 * r.n_photons_loop);
+  unsigned long long* park_head = m.work + (14 + 2 * r.n_photons_loop);
+  const int leader = __ffs(need) - 1;
+  unsigned long long base = 0;
+  if ((int)lane == leader) base = atomicAdd(park_head, (unsigned long long)__popc(need));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  const unsigned long long j = base + __popc(need & ((1u << lane) - 1u));
+  if (!valid || j >= __ldcg(park_count)) return Q_NONE;
+  const double* rec = m.park + j * PARK_REC;
+#pragma unroll
+  for (int f = 0; f < 11; ++f) P.F(f, slot) = __ldcg(rec + f);
+  const uint32_t* ru = reinterpret_cast<const uint32_t*>(rec + 11);
+#pragma unroll
+  for (int f = 0; f < NU32; ++f) P.U(f, slot) = __ldcg(ru + f);
+  if (r.lsepar_pola) { QUV(0, slot) = __ldcg(rec + 16); QUV(1, slot) = __ldcg(rec + 17); QUV(2, slot) = __ldcg(rec + 18); }
+  return (int)__ldcg(ru + NU32);
+}
+
+#ifdef MCB_DRAIN_PROBE
+// development probe: when does the number of live packets of a block fall below 512, 256, ... 1, 0 after the
+// packet counter ran dry?  max and sum over blocks of (t - t_dry) land in work[18+2n ..] (ns)
+__device__ __forceinline__ void drain_probe(unsigned long long* work, int npl, unsigned live, int& k) {
+  while (k < 11 && live <= (k < 10 ? (512u >> k) : 0u)) {
+    const unsigned long long dry = __ldcg(work + 1);
+    const unsigned long long now = globaltimer_ns();
+    const unsigned long long dt = (dry != ~0ull && now > dry) ? now - dry : 0ull;
+    atomicMax(work + (18 + 2 * npl + k), dt);
+    atomicAdd(work + (29 + 2 * npl + k), dt);
+    ++k;
+  }
+}
+#endif
+
+// =============================================================================
 // The persistent photon-loop kernel: rounds of (claim a single-phase chunk -> run the phase -> regroup)
 // =============================================================================
 template <class G, bool SM, int BANK, bool GR>
 __global__ void __launch_bounds__(MC_BLOCK, 1)
-mc_photon_loop_kernel() {
+mc_photon_loop_kernel(const int adopt) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const unsigned lane = threadIdx.x & 31;
   if (SM) stage_tables(m, r.p_lambda_in);
   const Pool P = make_pool<SM, BANK>();
-  // every slot starts in the EMIT queue
-  for (int i = threadIdx.x; i < NQ * NP; i += MC_BLOCK) P.q[i] = (i < NP) ? (unsigned short)i : (unsigned short)0xFFFFu;   // Q_EMIT == 0
+  const bool POLA_ = r.lsepar_pola != 0;
+  unsigned long long* park_count = m.work + (12 + 2 * r.n_photons_loop);
   if (threadIdx.x < 16) P.ctl[threadIdx.x] = 0;
+  // every slot starts in the EMIT queue (main launch: emits new packets; straggler launch: adopts parked ones)
+  for (int i = threadIdx.x; i < NQ * NP; i += MC_BLOCK) P.q[i] = (i < NP) ? (unsigned short)i : (unsigned short)0xFFFFu;   // Q_EMIT == 0
   __syncthreads();
   if (threadIdx.x == 0) { P.ctl[NQ + Q_EMIT] = NP; P.ctl[8] = NP; }
   __syncthreads();
+  const bool park_ok = r.park_enable && !adopt;
   Stats st = {0, 0, 0, 0, 0, 0, 0, 0};
   SchedStats ss = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(m.work + (2 + 2 * r.n_photons_loop), globaltimer_ns());
+#ifdef MCB_DRAIN_PROBE
+  int probe_k = 0;
+#endif
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(m.work + ((adopt ? 16 : 2) + 2 * r.n_photons_loop), globaltimer_ns());
   // ---- asynchronous scheduling: every warp repeatedly claims up to 32 entries of ONE queue (so all its
   // lanes run the same phase), preferring full chunks; partial chunks are only taken when no other warp
   // is busy (nothing more will arrive).  No block-wide barriers after this point.
@@ -1166,6 +1236,7 @@ mc_photon_loop_kernel() {
       // (few live packets: nothing will fill up), otherwise only after ~2 us without a full chunk.
       for (int polls = 0;; ++polls) {
         if (c_r.debug_abort_dry && __ldcg(c_m.work + 1) != ~0ull) break;      // profiling aid: steady-state only
+        if (park_ok && P.PARK()) break;                                       // the block is handing its packets over
         int best = -1; unsigned best_n = 0;
 #pragma unroll
         for (int k = 0; k < NQ; ++k) {
@@ -1174,6 +1245,10 @@ mc_photon_loop_kernel() {
           if (av > best_n) { best = k; best_n = av; }
         }
         const unsigned live = P.LIVE();
+#ifdef MCB_DRAIN_PROBE
+        if (threadIdx.x == 0 && P.DRYF()) drain_probe(c_m.work, c_r.n_photons_loop, live, probe_k);
+#endif
+        if (park_ok && live <= (unsigned)r.park_live && live > 0u && P.DRYF()) { P.PARK() = 1u; break; }
         if (best >= 0 && (best_n == 32u || live <= DRAIN_LIVE || polls >= 8)) {
           const unsigned hh = P.HEAD(best);
           const unsigned av = P.TAIL(best) - hh;
@@ -1207,7 +1282,7 @@ mc_photon_loop_kernel() {
       { const unsigned mm = __ballot_sync(0xffffffffu, mine); if (lane == 0) { ss.visits[qi] += 1; ss.lanes[qi] += __popc(mm); } }
       int nextq;
       switch (qi) {
-        case Q_EMIT: nextq = phase_emit<G, SM, BANK>(slot, mine, st); break;
+        case Q_EMIT: nextq = adopt ? phase_adopt<SM, BANK>(slot, mine) : phase_emit<G, SM, BANK>(slot, mine, st); break;
         case Q_ABS:  nextq = phase_absorb<G, SM, BANK, GR>(slot, mine, st); break;
         case Q_SCAT: nextq = phase_scatter<G, SM, BANK, GR>(slot, mine, st); break;
         default:     nextq = phase_fly<G, SM, BANK>(slot, mine, st); break;
@@ -1221,15 +1296,40 @@ mc_photon_loop_kernel() {
         if (c > keep_n) { keep_n = c; keep = k; }
       }
       unsigned live_now = 0;
-      if (lane == 0) live_now = P.LIVE();
+      if (lane == 0) live_now = (park_ok && P.PARK()) ? 0xFFFFFFFFu : P.LIVE();      // parking: everything goes back to the queues
+#ifdef MCB_DRAIN_PROBE
+      if (threadIdx.x == 0 && P.DRYF() && live_now != 0xFFFFFFFFu) drain_probe(c_m.work, c_r.n_photons_loop, live_now, probe_k);
+#endif
       live_now = __shfl_sync(0xffffffffu, live_now, 0);                      // warp-uniform decision
-      const bool cont = keep_n > 0 && (keep_n >= 28 || live_now <= DRAIN_LIVE);
+      const bool cont = keep_n > 0 && live_now != 0xFFFFFFFFu && (keep_n >= 28 || live_now <= DRAIN_LIVE);
       const int pushq = (cont && nextq == keep) ? Q_NONE + 1 : nextq;      // kept lanes are not pushed
       push_next(P, slot, pushq, mine, lane);
       if (!cont) break;
       mine = mine && (nextq == keep);
       qi = keep;
       __threadfence_block();
+    }
+  }
+
+  // ---- straggler hand-over: every warp has left the loop, so every live packet sits in a queue ----
+  if (park_ok) {
+    __syncthreads();
+    if (P.PARK()) {
+      for (int k = Q_ABS; k < NQ; ++k) {          // EMIT entries are free slots (the counter is dry)
+        const unsigned hq = P.HEAD(k), nq = P.TAIL(k) - hq;
+        for (unsigned t = threadIdx.x; t < nq; t += MC_BLOCK) {
+          const int slot = P.Q(k)[(hq + t) & (NP - 1)];
+          const unsigned long long j = atomicAdd(park_count, 1ull);
+          double* rec = m.park + j * PARK_REC;
+#pragma unroll
+          for (int f = 0; f < 11; ++f) rec[f] = P.F(f, slot);
+          uint32_t* ru = reinterpret_cast<uint32_t*>(rec + 11);
+#pragma unroll
+          for (int f = 0; f < NU32; ++f) ru[f] = P.U(f, slot);
+          ru[NU32] = (uint32_t)k;
+          if (POLA_) { rec[16] = QUV(0, slot); rec[17] = QUV(1, slot); rec[18] = QUV(2, slot); }
+        }
+      }
     }
   }
 
@@ -1246,6 +1346,8 @@ mc_photon_loop_kernel() {
     for (int k = 0; k < NQ; ++k) { atomicAdd(dbg + k, (unsigned long long)ss.visits[k]); atomicAdd(dbg + NQ + k, (unsigned long long)ss.lanes[k]); }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(m.work + (3 + 2 * r.n_photons_loop), globaltimer_ns());
+  // last block to leave: end of the main launch / of the straggler launch (diagnostics)
+  if (threadIdx.x == 0) atomicMax(m.work + ((adopt ? 15 : 13) + 2 * r.n_photons_loop), (unsigned long long)globaltimer_ns());
 }
 
 }  // namespace mcb

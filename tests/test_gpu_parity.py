@@ -374,3 +374,27 @@ def test_image_step_rt2_matches_oracle(pola):
     assert np.allclose(Ig[0].sum(axis=(1, 2)), Io[0].sum(axis=(1, 2)), rtol=0.01, atol=1e-4 * Io[0].sum())   # (theta_I) profile
     bright = Io[0].sum(axis=(0, 1)) > 0.01 * Io[0].sum(axis=(0, 1)).max()
     assert np.allclose(Ig[0].sum(axis=(0, 1))[bright], Io[0].sum(axis=(0, 1))[bright], rtol=0.02)
+
+
+def test_straggler_handover_keeps_every_packet():
+    """mcfost_b200_set_overlap: the main launch parks its last packets, a second small launch finishes them.
+    Nothing is lost or duplicated, and the tallies are those of an ordinary call within Monte Carlo noise."""
+    P = small_problems()["cyl2D"]()
+    G = api.PhotonLoop(P)
+    ref = G.mc_photon_loop(1, 1, 4000, 1.0e30, 1, False, lsepar_pola=1)
+    G.set_overlap(8)
+    t = G.mc_photon_loop(1, 1, 4000, 1.0e30, 1, False, lsepar_pola=1)
+    d = G.debug_counters()
+    assert t.stats[0] == ref.stats[0] == 128 * 4000 == t.n_phot_envoyes.sum()
+    assert t.stats[5] + t.stats[6] == t.stats[0]
+    assert t.sed.sum() == pytest.approx(t.stats[6])
+    assert abs(t.xKJ_abs.sum() / ref.xKJ_abs.sum() - 1) < 0.01
+    assert abs(t.stats[1] / ref.stats[1] - 1) < 0.01 and abs(t.stats[2] / ref.stats[2] - 1) < 0.01
+    assert np.abs(t.sed_q).sum() > 0 and abs(np.abs(t.sed_q).sum() / np.abs(ref.sed_q).sum() - 1) < 0.1
+    assert d["parked"] > 0                        # the hand-over did happen
+    # SED mode counts received packets: no hand-over there, the call is unchanged
+    s = G.mc_photon_loop(8, 8, 10 ** 9, 64.0, 1, False, letape_th=0, lmono=1)
+    assert s.stats[0] == 128 * 64
+    with pytest.raises(api.McfostB200Error):
+        G.set_overlap(-1)
+    G.close()
