@@ -398,3 +398,25 @@ def test_straggler_handover_keeps_every_packet():
     with pytest.raises(api.McfostB200Error):
         G.set_overlap(-1)
     G.close()
+
+
+def test_more_handles_than_constant_banks_run_concurrently():
+    """Four handles launch back to back (the library has three constant banks): the bank guard serialises the
+    two that share a bank, every call keeps its own tallies and conserves its packets."""
+    P = small_problems()["cyl2D"]()
+    Gs = [api.PhotonLoop(P) for _ in range(4)]
+    for g in Gs:
+        g.set_overlap(16, 8)
+    runs = [g.launch(1, 1, 3000 + 500 * i, 1.0e30, 1, call_index=i) for i, g in enumerate(Gs)]
+    for i, (g, r) in enumerate(zip(Gs, runs)):
+        g.sync()
+        t = g.download(r)
+        assert t.stats[0] == 128 * (3000 + 500 * i) == t.n_phot_envoyes.sum()
+        assert t.stats[5] + t.stats[6] == t.stats[0]
+        assert t.sed.sum() == pytest.approx(t.stats[6])
+    # same seed, same call_index on two different handles: identical packets, tallies equal up to summation order
+    a = Gs[0].mc_photon_loop(8, 8, 10 ** 9, 32.0, 1, False, letape_th=0, lmono=1, call_index=7)
+    b = Gs[3].mc_photon_loop(8, 8, 10 ** 9, 32.0, 1, False, letape_th=0, lmono=1, call_index=7)
+    assert np.array_equal(a.n_phot_sed, b.n_phot_sed) and np.allclose(a.sed, b.sed, rtol=1e-9, atol=1e-12)
+    for g in Gs:
+        g.close()
