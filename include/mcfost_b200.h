@@ -225,12 +225,21 @@ typedef struct mcb_run_params {
   int32_t rank, n_ranks;
   int32_t reset_tallies;    /* 1: zero all device tallies before the call */
   /* image step (run_image_mc, dust_transfer.f90:692-824): lmono0 with the rt2 accumulator */
-  int32_t loutput_mc;       /* MC image maps (STOKEI..., output.f90:396-570): must be 0 (not implemented) */
+  int32_t loutput_mc;       /* keep the MC photon maps (STOKEI..., output.f90:396-570) in the image step */
   int32_t n_theta_I, n_phi_I;   /* angular bins of I_spec (15 x 15, dust_ray_tracing.f90:104-105) */
   /* grain heating regimes (parameters.f90; lonly_* derived in init_mcfost.f90:1880-1883) */
   int32_t lonly_nLTE, lRE_nLTE, lnRE;
   int32_t low_mem_th_emission_nLTE;   /* 1: select_absorbing_grain instead of kabs_nLTE_CDF */
   int32_t low_mem_scattering;         /* method 1: 1 = on-the-fly CDF, 0 = ksca_CDF (dust_prop.f90:1292) */
+  /* capteur, Monte Carlo photon maps and packet origin (output.f90:303-357,396-570): used when lmono0 and
+   * loutput_mc (maps), lonly_capt_interet (all modes) and lorigine */
+  int32_t npix_x, npix_y;             /* read_param.f90:176 */
+  float   zoom;                       /* parameters.f90:109 */
+  double  map_size;                   /* parameters.f90:169, AU */
+  double  cos_disk, sin_disk;         /* output.f90:94-95: cos / sin(ang_disque) */
+  int32_t l_sym_ima;                  /* left-right symmetry: half a photon in each mirror pixel */
+  int32_t lonly_capt_interet, capt_inf;   /* keep only detector bins capt_inf..capt_sup (read_param.f90:182-190) */
+  int32_t lorigine, capt_interet;     /* star_origin / disk_origin tallies for bin capt_interet */
 } mcb_run_params;
 
 /* ------------------------------------------------------------------------
@@ -257,6 +266,12 @@ typedef struct mcb_tallies {
   int32_t *xT_ech_1grain;      /* (grain_RE_nLTE_start:grain_RE_nLTE_end, n_cells) */
   int32_t *xT_ech_1grain_nRE;  /* (grain_nRE_start:grain_nRE_end, n_cells) */
   double  *E_abs_nRE;          /* scalar, dust_transfer.f90:1357 */
+  /* Monte Carlo photon maps of ONE wavelength (the call's lambda_in): (npix_x, npix_y, N_thet, N_phi, n_maps)
+   * with n_maps = N_type_flux and the planes ordered I [, Q, U, V] [, I_star, I_star_scat, I_disk, I_disk_scat]
+   * = STOKEI, STOKEQ, STOKEU, STOKEV, STOKEI_star, ..._disk_scat (lambda,:,:,:,:) of output.f90:26-34 */
+  double  *stokes_map;
+  double  *star_origin;        /* (n_lambda)           output.f90:37 */
+  double  *disk_origin;        /* (n_lambda, n_cells)  output.f90:36 */
 } mcb_tallies;
 
 /* ---- life cycle -------------------------------------------------------- */

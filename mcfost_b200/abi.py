@@ -121,6 +121,9 @@ class mcb_run_params(C.Structure):
         ("loutput_mc", C.c_int32), ("n_theta_I", C.c_int32), ("n_phi_I", C.c_int32),
         ("lonly_nLTE", C.c_int32), ("lRE_nLTE", C.c_int32), ("lnRE", C.c_int32),
         ("low_mem_th_emission_nLTE", C.c_int32), ("low_mem_scattering", C.c_int32),
+        ("npix_x", C.c_int32), ("npix_y", C.c_int32), ("zoom", C.c_float), ("map_size", C.c_double),
+        ("cos_disk", C.c_double), ("sin_disk", C.c_double), ("l_sym_ima", C.c_int32),
+        ("lonly_capt_interet", C.c_int32), ("capt_inf", C.c_int32), ("lorigine", C.c_int32), ("capt_interet", C.c_int32),
     ]
 
 
@@ -136,6 +139,7 @@ class mcb_tallies(C.Structure):
         ("I_spec", c_float_p), ("I_spec_star", c_float_p),
         ("stats", c_double_p),
         ("xT_ech_1grain", c_int32_p), ("xT_ech_1grain_nRE", c_int32_p), ("E_abs_nRE", c_double_p),
+        ("stokes_map", c_double_p), ("star_origin", c_double_p), ("disk_origin", c_double_p),
     ]
 
 
@@ -269,7 +273,9 @@ def make_run(**kw) -> Holder:
              tab_u_rt=None, tab_v_rt=None, tab_w_rt=None,
              seed=269753, call_index=0, rank=0, n_ranks=1, reset_tallies=1,
              loutput_mc=0, n_theta_I=15, n_phi_I=15,
-             lonly_nLTE=0, lRE_nLTE=0, lnRE=0, low_mem_th_emission_nLTE=0, low_mem_scattering=1)
+             lonly_nLTE=0, lRE_nLTE=0, lnRE=0, low_mem_th_emission_nLTE=0, low_mem_scattering=1,
+             npix_x=0, npix_y=0, zoom=1.0, map_size=0.0, cos_disk=1.0, sin_disk=0.0, l_sym_ima=0,
+             lonly_capt_interet=0, capt_inf=1, lorigine=0, capt_interet=1)
     unknown = set(kw) - set(d)
     if unknown:
         raise TypeError(f"unknown run parameter(s): {sorted(unknown)}")
@@ -289,7 +295,8 @@ def make_run(**kw) -> Holder:
 class Tallies:
     """Caller-allocated tally arrays (shapes of the reference minus the nb_proc dim)."""
 
-    def __init__(self, n_cells, n_lambda, N_thet=10, N_phi=1, xJ=False, n_xI=0, n_Ispec=0, n_nLTE=0, n_nRE=0):
+    def __init__(self, n_cells, n_lambda, N_thet=10, N_phi=1, xJ=False, n_xI=0, n_Ispec=0, n_nLTE=0, n_nRE=0,
+                 map_shape=None, origin=False):
         self.xKJ_abs = np.zeros(n_cells, np.float64)
         self.xJ_abs = np.zeros((n_cells, n_lambda), np.float64, order="F") if xJ else None
         self.xT_ech = np.zeros(n_cells, np.int32)
@@ -305,6 +312,9 @@ class Tallies:
         self.xT_ech_1grain = np.zeros((n_nLTE, n_cells), np.int32, order="F") if n_nLTE else None
         self.xT_ech_1grain_nRE = np.zeros((n_nRE, n_cells), np.int32, order="F") if n_nRE else None
         self.E_abs_nRE = np.zeros(1, np.float64)
+        self.stokes_map = np.zeros(map_shape, np.float64, order="F") if map_shape else None
+        self.star_origin = np.zeros(n_lambda, np.float64) if origin else None
+        self.disk_origin = np.zeros((n_lambda, n_cells), np.float64, order="F") if origin else None
         t = mcb_tallies()
         for name in ("xKJ_abs", "xJ_abs", "n_phot_envoyes", "sed", "sed_q", "sed_u", "sed_v", "n_phot_sed",
                      "sed_star", "sed_star_scat", "sed_disk", "sed_disk_scat", "stats"):
@@ -313,6 +323,9 @@ class Tallies:
         t.xT_ech_1grain = ptr(self.xT_ech_1grain, np.int32)
         t.xT_ech_1grain_nRE = ptr(self.xT_ech_1grain_nRE, np.int32)
         t.E_abs_nRE = ptr(self.E_abs_nRE, np.float64)
+        t.stokes_map = ptr(self.stokes_map, np.float64)
+        t.star_origin = ptr(self.star_origin, np.float64)
+        t.disk_origin = ptr(self.disk_origin, np.float64)
         t.xI_scatt = ptr(self.xI_scatt, np.float32)
         t.I_spec = ptr(self.I_spec, np.float32)
         t.I_spec_star = ptr(self.I_spec_star, np.float32)
@@ -328,3 +341,14 @@ def grain_tally_sizes(P, r):
     n1 = (P.grain_RE_nLTE_end - P.grain_RE_nLTE_start + 1) if (r.lRE_nLTE and hasattr(P, "grain_RE_nLTE_start")) else 0
     n2 = (P.grain_nRE_end - P.grain_nRE_start + 1) if (r.lnRE and hasattr(P, "grain_nRE_start")) else 0
     return dict(n_nLTE=int(n1), n_nRE=int(n2))
+
+
+def map_tally_args(r):
+    """Tallies(...) keyword arguments for the Monte Carlo photon maps / origin tallies of this run."""
+    kw = {}
+    if r.lmono0 and r.loutput_mc and r.npix_x > 0 and r.npix_y > 0:
+        ntf = (4 if r.lsepar_pola else 1) + (4 if r.lsepar_contrib else 0)
+        kw["map_shape"] = (r.npix_x, r.npix_y, r.N_thet, r.N_phi, ntf)
+    if r.lorigine:
+        kw["origin"] = True
+    return kw

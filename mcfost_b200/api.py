@@ -157,7 +157,7 @@ class PhotonLoop:
             ntf = (4 if r.struct.lsepar_pola else 1) + (4 if r.struct.lsepar_contrib else 0)
             n_Is = ntf * r.struct.n_theta_I * r.struct.n_phi_I * P.n_cells
         return abi.Tallies(P.n_cells, P.n_lambda, r.struct.N_thet, r.struct.N_phi, xJ=xJ, n_xI=n_xI, n_Ispec=n_Is,
-                           **abi.grain_tally_sizes(P, r.struct))
+                           **abi.grain_tally_sizes(P, r.struct), **abi.map_tally_args(r.struct))
 
     def mc_photon_loop(self, lambda_in=1, p_lambda_in=1, n_photons2=1000, n_phot_lim=1.0e30, nnfot1_start=1,
                        laffichage=False, **flags):

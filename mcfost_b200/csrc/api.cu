@@ -430,7 +430,9 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
       if (mixed && !r->lnRE && !r->lRE_nLTE) return fail(h, MCB_ERR_BAD_ARG, "lonly_LTE = 0 without lRE_nLTE or lnRE");
     }
   }
-  if (r->loutput_mc) return fail(h, MCB_ERR_UNSUPPORTED, "MC image maps (STOKEI..., loutput_mc) not implemented");
+  const bool mc_maps = r->lmono0 && r->loutput_mc;
+  if (mc_maps && (r->npix_x < 1 || r->npix_y < 1 || !(r->map_size > 0.0))) return fail(h, MCB_ERR_BAD_ARG, "loutput_mc needs npix_x, npix_y, map_size");
+  if (r->lorigine && (r->capt_interet < 1 || r->capt_interet > r->N_thet)) return fail(h, MCB_ERR_BAD_ARG, "capt_interet out of range");
   if (r->lscatt_ray_tracing2 && (m.l3D || h->gk == GK_VOR)) return fail(h, MCB_ERR_UNSUPPORTED, "rt2 is 2D only (radiation_field.f90:91)");
   if (r->lscatt_ray_tracing2 && (r->n_theta_I < 1 || r->n_phi_I < 1)) return fail(h, MCB_ERR_BAD_ARG, "n_theta_I / n_phi_I");
   if (r->n_photons_loop < 1 || r->nnfot1_start < 1 || r->n_photons2 < 0) return fail(h, MCB_ERR_BAD_ARG, "bad packet budget");
@@ -479,12 +481,30 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   dr.n_per_chunk = (unsigned long long)r->n_photons2 < dr.sent_lim ? (unsigned long long)r->n_photons2 : dr.sent_lim;
   dr.n_packets_total = dr.count_sent ? (unsigned long long)n_local * dr.n_per_chunk : 0ull;
   dr.nb_proc_equiv = (double)r->n_ranks;
-  dr.park_enable = (h->overlap_sms > 0 && dr.count_sent) ? 1 : 0;
+  dr.mc_maps = mc_maps ? 1 : 0; dr.lorigine = r->lorigine; dr.capt_interet = r->capt_interet;
+  dr.lonly_capt_interet = r->lonly_capt_interet; dr.capt_inf = r->capt_inf;
+  dr.npix_x = r->npix_x; dr.npix_y = r->npix_y; dr.l_sym_ima = r->l_sym_ima;
+  dr.zoom = (double)r->zoom; dr.map_size = r->map_size; dr.cos_disk = r->cos_disk; dr.sin_disk = r->sin_disk;
+  dr.capt_full = (mc_maps || r->lorigine || r->lonly_capt_interet) ? 1 : 0;
+  // (the flight-start slab of capteur_full is not part of a parked packet: no hand-over in those modes)
+  dr.park_enable = (h->overlap_sms > 0 && dr.count_sent && !dr.capt_full) ? 1 : 0;
   dr.park_live = 256;
   { const char* e = getenv("MCB_PARK_LIVE"); if (e && atoi(e) > 0 && atoi(e) <= 256) dr.park_live = atoi(e); }      // tuning knob
   { const char* e = getenv("MCB_DEBUG_ABORT_DRY"); dr.debug_abort_dry = (e && e[0] == '1') ? 1 : 0; }   // profiling aid only: tallies are incomplete
   int rc = setup_tallies(h, r, dr.lxJ != 0, rt1, dr.n_type_flux, dr.rt2 != 0);
   if (rc) return rc;
+  {   // capteur extras: photon maps of this wavelength, origin tallies, flight-start slab
+    const int64_t n_map = mc_maps ? (int64_t)r->npix_x * r->npix_y * r->N_thet * r->N_phi * dr.n_type_flux : 0;
+    const int64_t n_org = r->lorigine ? (int64_t)m.n_lambda * (m.n_cells + 1) : 0;
+    const bool fresh = (n_map != h->n_map) || (n_org != h->n_org) || r->reset_tallies;
+    if ((rc = reserve(h, "smap", (size_t)n_map, &m.smap))) return rc;
+    if ((rc = reserve(h, "origin", (size_t)n_org, &m.star_origin))) return rc;
+    m.disk_origin = m.star_origin + m.n_lambda;
+    if ((rc = reserve(h, "pos0", dr.capt_full ? (size_t)h->n_sm * 4 * 1024 : 0, &m.pos0))) return rc;
+    h->n_map = n_map; h->n_org = n_org;
+    if (fresh && n_map) CK(cudaMemsetAsync(m.smap, 0, (size_t)n_map * sizeof(double), h->stream));
+    if (fresh && n_org) CK(cudaMemsetAsync(m.star_origin, 0, (size_t)n_org * sizeof(double), h->stream));
+  }
   if (n_local == 0 || (dr.count_sent && dr.n_packets_total == 0)) { CK(cudaEventRecord(h->ev0, h->stream)); CK(cudaEventRecord(h->ev1, h->stream)); h->launched = true; return MCB_OK; }
   if (h->kf_dark_stale) {
     std::vector<double> kd(h->host_kappa_factor);
@@ -552,6 +572,9 @@ int mcfost_b200_download(mcb_handle* h, const mcb_run_params* r, mcb_tallies* ou
   for (int a = 0; a < 9; ++a) CK(get(sp[a], L.sed + a * L.n_sed, L.n_sed));
   CK(get(out->stats, L.stats, 8));
   CK(get(out->E_abs_nRE, L.E_abs_nRE, 1));
+  if (out->stokes_map && h->n_map) CK(cudaMemcpyAsync(out->stokes_map, m.smap, (size_t)h->n_map * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (out->star_origin && h->n_org) CK(cudaMemcpyAsync(out->star_origin, m.star_origin, (size_t)m.n_lambda * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (out->disk_origin && h->n_org) CK(cudaMemcpyAsync(out->disk_origin, m.disk_origin, (size_t)m.n_lambda * m.n_cells * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (out->xT_ech_1grain && h->n_1g) CK(cudaMemcpyAsync(out->xT_ech_1grain, m.gr.xT_1g, (size_t)h->n_1g * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (out->xT_ech_1grain_nRE && h->n_1g_nRE) CK(cudaMemcpyAsync(out->xT_ech_1grain_nRE, m.gr.xT_1g_nRE, (size_t)h->n_1g_nRE * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (out->xT_ech) CK(cudaMemcpyAsync(out->xT_ech, m.xT_ech, (size_t)m.n_cells * sizeof(int), cudaMemcpyDeviceToHost, h->stream));

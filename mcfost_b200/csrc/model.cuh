@@ -109,6 +109,8 @@ struct DevModel {
   float *I_spec, *I_spec_star;   // rt2 accumulators (dust_ray_tracing.f90:44-45)
   double *quv;              // Stokes Q,U,V of the packets in flight: (n_blocks, 3, NP), only with lsepar_pola
   unsigned long long *work; // [0] = next work item; [2+2c], [3+2c] = sent / received of local chunk c
+  double *pos0;             // (n_blocks, 4, NP): start point x,y,z and cell index of the flight in progress (photon maps / lorigine only)
+  double *smap, *star_origin, *disk_origin;   // Monte Carlo photon maps of the call's wavelength, packet-origin tallies (output.f90:26-37)
   double *park;             // parked stragglers: (PARK_REC doubles) x capacity, see transport.cuh
   SmemLayout sm;
   DevGrains gr;
@@ -134,6 +136,10 @@ struct DevRun {
   unsigned long long n_per_chunk;       // count_sent: min(n_photons2, sent_lim)
   unsigned long long n_packets_total;   // count_sent: n_local_chunks * n_per_chunk
   double nb_proc_equiv;                 // n_ranks: scales the local tally in Temp_LTE
+  // capteur extras (output.f90:303-357,396-570)
+  int capt_full;                        // 1: lorigine / lonly_capt_interet / photon maps are on -> capteur_full
+  int mc_maps, lorigine, capt_interet, lonly_capt_interet, capt_inf, npix_x, npix_y, l_sym_ima;
+  double zoom, map_size, cos_disk, sin_disk;
   int park_live;                        // hand over when at most this many packets of a block are in flight (<= PARK_LIVE)
   int park_enable;                      // hand stragglers over to a second small launch (count_sent modes only)
   int debug_abort_dry;                  // profiling aid (env MCB_DEBUG_ABORT_DRY): stop when the packet counter runs dry

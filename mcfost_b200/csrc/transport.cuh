@@ -534,6 +534,85 @@ __device__ __noinline__ int capteur(int lambda, double u1, double v1, double w1,
   return capt;
 }
 
+// ---- output.f90:294-595 capteur, complete: packet origin (lorigine), lonly_capt_interet, and the Monte
+// Carlo photon maps of the image step (rotation to the observer's frame, disk position angle, pixel,
+// left-right half-photon symmetry).  x,y,z is the START of the last flight (physical_length leaves its inout
+// position untouched when the packet exits, optical_depth.f90:86-90), idx0 the 0-based cell it started in.
+#define POS0(k, slot) (c_m.pos0[((size_t)blockIdx.x * 4 + (k)) * NP + (slot)])
+template <int BANK>
+__device__ __noinline__ int capteur_full(int lambda, double x1, double y1, double z1, double u1, double v1, double w1,
+                                         const double* Sin, bool flag_star, bool flag_scatt, int idx0) {
+  const DevModel& m = c_m; const DevRun& r = c_r;
+  double s0 = Sin[0], s1 = Sin[1], s2 = Sin[2], s3 = Sin[3];
+  if (w1 < 0.0) {
+    if (r.l_sym_centrale) { x1 = -x1; y1 = -y1; z1 = -z1; u1 = -u1; v1 = -v1; w1 = -w1; s2 = -s2; }
+    else return 0;
+  }
+  int capt = (int)((-1.0 * w1 + 1.0) * r.N_thet) + 1;
+  if (capt == r.N_thet + 1) capt = r.N_thet;
+  if (r.lorigine && capt == r.capt_interet) {
+    if (flag_star) atomicAdd(m.star_origin + (lambda - 1), s0);
+    else if (idx0 >= 0) atomicAdd(m.disk_origin + (lambda - 1) + (size_t)m.n_lambda * idx0, s0);
+  }
+  if (r.lmono0 && !r.mc_maps) return capt;
+  if (r.lonly_capt_interet && ((capt > r.capt_sup) || (capt < r.capt_inf))) return capt;
+  int c_phi = 1;
+  if (r.l_sym_axiale) {
+    if (v1 < 0.0) { v1 = -v1; y1 = -y1; s2 = -s2; }
+    if (w1 != 1.0) c_phi = (int)(atan2(v1, u1) / MCB_PI * r.N_phi) + 1;
+  } else {
+    if (w1 != 1.0) c_phi = (int)(fmodulo(atan2(u1, v1) + MCB_PI / 2, 2 * MCB_PI) / (2 * MCB_PI) * r.N_phi) + 1;
+  }
+  if (c_phi == r.N_phi + 1) c_phi = r.N_phi; else if (c_phi == 0) c_phi = 1;
+  if (r.lmono0) {
+    const int maxigrid = max(r.npix_x, r.npix_y);
+    int deltapix_x = 1, deltapix_y = 1;
+    if (r.npix_x > r.npix_y) deltapix_y = 1 - (r.npix_x / 2) + (r.npix_y / 2);
+    else if (r.npix_x < r.npix_y) deltapix_x = 1 - (r.npix_y / 2) + (r.npix_x / 2);
+    const double size_pix = maxigrid / r.map_size;
+    double xprim, yprim, zprim;
+    rotation(x1, y1, z1, u1, v1, w1, xprim, yprim, zprim);
+    double ytmp = yprim; const double ztmp = zprim;
+    yprim = ytmp * r.cos_disk + ztmp * r.sin_disk;
+    zprim = ztmp * r.cos_disk - ytmp * r.sin_disk;
+    const int imap1 = (int)((yprim * r.zoom + 0.5 * r.map_size) * size_pix) + deltapix_x;
+    if (imap1 <= 0 || imap1 > r.npix_x) return capt;
+    const int jmap1 = (int)((zprim * r.zoom + 0.5 * r.map_size) * size_pix) + deltapix_y;
+    if (jmap1 <= 0 || jmap1 > r.npix_y) return capt;
+    const size_t plane = (size_t)r.npix_x * r.npix_y * r.N_thet * r.N_phi;
+    const int i_contrib = r.n_stokes + (flag_star ? (flag_scatt ? 1 : 0) : (flag_scatt ? 3 : 2));
+    auto add = [&](int im, int jm, double f, double sign_u) {
+      const size_t q = (size_t)(im - 1) + (size_t)r.npix_x * ((size_t)(jm - 1) + (size_t)r.npix_y * ((size_t)(capt - 1) + (size_t)r.N_thet * (c_phi - 1)));
+      atomicAdd(m.smap + q, f * s0);
+      if (r.lsepar_pola) { atomicAdd(m.smap + plane + q, f * s1); atomicAdd(m.smap + 2 * plane + q, sign_u * f * s2); atomicAdd(m.smap + 3 * plane + q, f * s3); }
+      if (r.lsepar_contrib) atomicAdd(m.smap + (size_t)i_contrib * plane + q, f * s0);
+    };
+    if (r.l_sym_ima) {
+      add(imap1, jmap1, 0.5, 1.0);
+      ytmp = -ytmp;
+      yprim = ytmp * r.cos_disk - ztmp * r.sin_disk;
+      zprim = ztmp * r.cos_disk + ytmp * r.sin_disk;
+      const int imap2 = (int)((yprim * r.zoom + 0.5 * r.map_size) * size_pix) + deltapix_x;
+      if (imap2 <= 0 || imap2 > r.npix_x) return capt;
+      const int jmap2 = (int)((zprim * r.zoom + 0.5 * r.map_size) * size_pix) + deltapix_y;
+      if (jmap2 <= 0 || jmap2 > r.npix_y) return capt;
+      if (imap1 == imap2 && jmap1 == jmap2) add(imap1, jmap1, 0.5, 1.0);
+      else add(imap2, jmap2, 0.5, -1.0);
+    } else add(imap1, jmap1, 1.0, 1.0);
+    return capt;
+  }
+  const int64_t ix = (lambda - 1) + (int64_t)m.n_lambda * ((capt - 1) + (int64_t)r.N_thet * (c_phi - 1));
+  double* sed = m.tally + m.lay.sed;
+  const int64_t n = m.lay.n_sed;
+  atomicAdd(sed + 0 * n + ix, s0);
+  if (r.lsepar_pola) { atomicAdd(sed + 1 * n + ix, s1); atomicAdd(sed + 2 * n + ix, s2); atomicAdd(sed + 3 * n + ix, s3); }
+  atomicAdd(sed + 4 * n + ix, 1.0);
+  const int which = flag_star ? (flag_scatt ? 6 : 5) : (flag_scatt ? 8 : 7);
+  atomicAdd(sed + which * n + ix, s0);
+  return capt;
+}
+
+
 // ---- dust_ray_tracing.f90:409-476 angles_scatt_rt1 (per flight) ------------------
 struct Rt1Scratch { unsigned char itheta[MAX_RT]; double cosw[MAX_RT], sinw[MAX_RT]; };
 
@@ -866,12 +945,14 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
       P.U(U_PKLO, slot) = pk_lo; P.U(U_PKHI, slot) = pk_hi; P.U(U_EV, slot) = 1u;
       uint32_t misc = pack_misc(lambda, flag_star, false, flag_ISM, 0, my_chunk);
       start_flight(m, r, P, slot, x, y, z, u, v, w, philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u, pk_lo, pk_hi, r.call_index), misc);
+      if (r.capt_full) { POS0(0, slot) = x; POS0(1, slot) = y; POS0(2, slot) = z; POS0(3, slot) = (double)tally_index(m, cell); }
       P.U(U_MISC, slot) = misc;
       nextq = Q_FLY;
     } else {      // the packet never enters the model: straight to the detector (dust_transfer.f90:545-552)
       if (!flag_ISM) {
         const double S[4] = {S0, 0.0, 0.0, 0.0};
-        const int capt = capteur<BANK>(lambda, u, v, w, S, flag_star, false);
+        const int capt = r.capt_full ? capteur_full<BANK>(lambda, x, y, z, u, v, w, S, flag_star, false, tally_index(m, cell))
+                                     : capteur<BANK>(lambda, u, v, w, S, flag_star, false);
         if (!r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * my_chunk, 1ull);
         ++st.esc;
       }
@@ -928,7 +1009,8 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
       if (!misc_ism(misc)) {       // the packet leaves the model: detector (capteur, output.f90:294)
         double S[4] = {S0, 0.0, 0.0, 0.0};
         if (POLA) { S[1] = QUV(0, slot); S[2] = QUV(1, slot); S[3] = QUV(2, slot); }
-        const int capt = capteur<BANK>(lambda, u, v, w, S, misc_star(misc), misc_scatt(misc));
+        const int capt = r.capt_full ? capteur_full<BANK>(lambda, POS0(0, slot), POS0(1, slot), POS0(2, slot), u, v, w, S, misc_star(misc), misc_scatt(misc), (int)POS0(3, slot))
+                                     : capteur<BANK>(lambda, u, v, w, S, misc_star(misc), misc_scatt(misc));
         if (!r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * misc_chunk(misc), 1ull);
       }
       ++st.esc;
@@ -1090,6 +1172,7 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
       misc |= (1u << 11);                                    // flag_scatt
       P.U(U_EV, slot) = ev + 1u;
       start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u1, v1, w1, bnext, misc);
+      if (r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
       P.U(U_MISC, slot) = misc;
       nextq = Q_FLY;
     }
@@ -1147,6 +1230,7 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
       misc = pack_misc(lambda, false, false, false, 0, misc_chunk(misc));      // flag_star = flag_scatt = flag_ISM = .false.
       P.U(U_EV, slot) = ev + 1u;
       start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u, v, w, bnext, misc);
+      if (r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
       P.U(U_MISC, slot) = misc;
       nextq = Q_FLY;
     }

@@ -100,7 +100,7 @@ class Oracle:
         r = abi.make_run(**params)
         P = self.P
         t = abi.Tallies(P.n_cells, P.n_lambda, r.struct.N_thet, r.struct.N_phi, xJ=xJ, n_xI=n_xI, n_Ispec=n_Ispec,
-                        **abi.grain_tally_sizes(P, r.struct))
+                        **abi.grain_tally_sizes(P, r.struct), **abi.map_tally_args(r.struct))
         rec_a = None if rec is None else np.ascontiguousarray(rec, np.float64)
         self._check(self.lib.oracle_run(self.h, r.ref(), t.ref(), int(n_threads), _p(rec_a),
                                         0 if rec_a is None else len(rec_a)))

@@ -84,6 +84,7 @@ struct ThreadTallies {
   std::vector<int>    xT_ech;       // (n_cells)
   std::vector<int>    xT_ech_1grain, xT_ech_1grain_nRE;   // (grains of the regime, n_cells) thermal_emission.f90:50
   double E_abs_nRE = 0.0;           // omp reduction variable, dust_transfer.f90:489
+  std::vector<double> stokes_map, star_origin, disk_origin;   // output.f90:26-37
   std::vector<double> n_phot_envoyes;
   std::vector<double> sed[9];       // sed, q, u, v, n_phot_sed, star, star_scat, disk, disk_scat
   std::vector<float>  xI_scatt;
@@ -1615,23 +1616,68 @@ struct Oracle {
   // returns capt (0 if the packet is dropped by the symmetry test)
   // =====================================================================
   int capteur(ThreadTallies& t, int lambda, const Packet& p) {
+    // output.f90:308-319
+    const int maxigrid = std::max(r.npix_x, r.npix_y);
+    int deltapix_x = 1, deltapix_y = 1;
+    if (r.npix_x > r.npix_y) deltapix_y = 1 - (r.npix_x / 2) + (r.npix_y / 2);
+    else if (r.npix_x < r.npix_y) deltapix_x = 1 - (r.npix_y / 2) + (r.npix_x / 2);
+    const double size_pix = r.map_size > 0.0 ? maxigrid / r.map_size : 0.0;
+    double x1 = p.x, y1 = p.y, z1 = p.z;
     double u1 = p.u, v1 = p.v, w1 = p.w;
     double stok[4] = {p.S[0], p.S[1], p.S[2], p.S[3]};
     if (w1 < 0.0) {
-      if (r.l_sym_centrale) { u1 = -u1; v1 = -v1; w1 = -w1; stok[2] = -stok[2]; }
+      if (r.l_sym_centrale) { x1 = -x1; y1 = -y1; z1 = -z1; u1 = -u1; v1 = -v1; w1 = -w1; stok[2] = -stok[2]; }
       else return 0;
     }
     int capt = (int)((-1.0 * w1 + 1.0) * r.N_thet) + 1;
     if (capt == (r.N_thet + 1)) capt = r.N_thet;
+    if (r.lorigine && capt == r.capt_interet) {                        // :348-357
+      if (p.flag_star) t.star_origin[lambda - 1] += stok[0];
+      else t.disk_origin[(size_t)(lambda - 1) + (size_t)o.n_lambda * (p.icell - 1)] += stok[0];
+    }
+    if (r.lmono0 && !r.loutput_mc) return capt;                        // :360
+    if (r.lonly_capt_interet) { if ((capt > r.capt_sup) || (capt < r.capt_inf)) return capt; }
     int c_phi;
     if (r.l_sym_axiale) {
-      if (v1 < 0.0) { v1 = -v1; stok[2] = -stok[2]; }
+      if (v1 < 0.0) { v1 = -v1; y1 = -y1; stok[2] = -stok[2]; }
       if (w1 == 1.0) c_phi = 1; else c_phi = (int)(std::atan2(v1, u1) / pi * r.N_phi) + 1;
     } else {
       if (w1 == 1.0) c_phi = 1; else c_phi = (int)(fmodulo(std::atan2(u1, v1) + pi / 2, 2 * pi) / (2 * pi) * r.N_phi) + 1;
     }
-    if (r.lmono0) return capt;          // lmono0 .and. .not.loutput_mc: no MC map is kept (output.f90:360)
     if (c_phi == (r.N_phi + 1)) c_phi = r.N_phi; else if (c_phi == 0) c_phi = 1;
+    if (r.lmono0) {                                                     // map creation :396-570
+      double xprim, yprim, zprim;
+      rotation(x1, y1, z1, u1, v1, w1, xprim, yprim, zprim);
+      double ytmp = yprim, ztmp = zprim;
+      yprim = ytmp * r.cos_disk + ztmp * r.sin_disk;
+      zprim = ztmp * r.cos_disk - ytmp * r.sin_disk;
+      const double zoom = (double)r.zoom;
+      const int imap1 = (int)((yprim * zoom + 0.5 * r.map_size) * size_pix) + deltapix_x;
+      if (imap1 <= 0 || imap1 > r.npix_x) return capt;
+      const int jmap1 = (int)((zprim * zoom + 0.5 * r.map_size) * size_pix) + deltapix_y;
+      if (jmap1 <= 0 || jmap1 > r.npix_y) return capt;
+      const size_t plane = (size_t)r.npix_x * r.npix_y * r.N_thet * r.N_phi;
+      auto pix = [&](int im, int jm) { return (size_t)(im - 1) + (size_t)r.npix_x * ((size_t)(jm - 1) + (size_t)r.npix_y * ((size_t)(capt - 1) + (size_t)r.N_thet * (c_phi - 1))); };
+      const int i_contrib = n_Stokes + (p.flag_star ? (p.flag_scatt ? 1 : 0) : (p.flag_scatt ? 3 : 2));
+      auto add = [&](size_t q, double f, double sign_u) {
+        t.stokes_map[q] += f * stok[0];
+        if (r.lsepar_pola) { t.stokes_map[plane + q] += f * stok[1]; t.stokes_map[2 * plane + q] += sign_u * f * stok[2]; t.stokes_map[3 * plane + q] += f * stok[3]; }
+        if (r.lsepar_contrib) t.stokes_map[(size_t)i_contrib * plane + q] += f * stok[0];
+      };
+      if (r.l_sym_ima) {
+        add(pix(imap1, jmap1), 0.5, 1.0);
+        ytmp = -ytmp;                                                   // mirror photon :468-471
+        yprim = ytmp * r.cos_disk - ztmp * r.sin_disk;
+        zprim = ztmp * r.cos_disk + ytmp * r.sin_disk;
+        const int imap2 = (int)((yprim * zoom + 0.5 * r.map_size) * size_pix) + deltapix_x;
+        if (imap2 <= 0 || imap2 > r.npix_x) return capt;
+        const int jmap2 = (int)((zprim * zoom + 0.5 * r.map_size) * size_pix) + deltapix_y;
+        if (jmap2 <= 0 || jmap2 > r.npix_y) return capt;
+        if ((imap1 == imap2) && (jmap1 == jmap2)) add(pix(imap1, jmap1), 0.5, 1.0);
+        else add(pix(imap2, jmap2), 0.5, -1.0);                         // U changes sign in the mirror pixel :520
+      } else add(pix(imap1, jmap1), 1.0, 1.0);
+      return capt;
+    }
     size_t ix = (size_t)(lambda - 1) + (size_t)o.n_lambda * ((size_t)(capt - 1) + (size_t)r.N_thet * (c_phi - 1));
     t.sed[0][ix] += stok[0]; t.sed[1][ix] += stok[1]; t.sed[2][ix] += stok[2]; t.sed[3][ix] += stok[3];
     t.sed[4][ix] += 1.0;
@@ -1662,6 +1708,9 @@ struct Oracle {
         t.xT_ech_1grain.assign(has_gr && r.lRE_nLTE ? (size_t)nk_nLTE() * g.n_cells : 0, 2);      // :165
         t.xT_ech_1grain_nRE.assign(has_gr && r.lnRE ? (size_t)nk_nRE() * g.n_cells : 0, 2);       // :188
         t.E_abs_nRE = 0.0;
+        t.stokes_map.assign((r.lmono0 && r.loutput_mc) ? (size_t)r.npix_x * r.npix_y * r.N_thet * r.N_phi * N_type_flux : 0, 0.0);
+        t.star_origin.assign(r.lorigine ? o.n_lambda : 0, 0.0);
+        t.disk_origin.assign(r.lorigine ? (size_t)o.n_lambda * g.n_cells : 0, 0.0);
         t.n_phot_envoyes.assign(o.n_lambda, 0.0);
         for (auto& s : t.sed) s.assign(nsed, 0.0);
         t.xJ_abs.assign(need_xJ ? (size_t)g.n_cells * o.n_lambda : 0, 0.0);
@@ -1744,6 +1793,9 @@ struct Oracle {
     if (out->xT_ech_1grain) for (size_t i = 0; i < T[0].xT_ech_1grain.size(); ++i) { int m = 0; for (auto& t : T) m = std::max(m, t.xT_ech_1grain[i]); out->xT_ech_1grain[i] = m; }
     if (out->xT_ech_1grain_nRE) for (size_t i = 0; i < T[0].xT_ech_1grain_nRE.size(); ++i) { int m = 0; for (auto& t : T) m = std::max(m, t.xT_ech_1grain_nRE[i]); out->xT_ech_1grain_nRE[i] = m; }
     if (out->E_abs_nRE) { double s = 0; for (auto& t : T) s += t.E_abs_nRE; *out->E_abs_nRE = s; }
+    if (out->stokes_map) for (size_t i = 0; i < T[0].stokes_map.size(); ++i) { double s = 0; for (auto& t : T) s += t.stokes_map[i]; out->stokes_map[i] = s; }
+    if (out->star_origin) for (size_t i = 0; i < T[0].star_origin.size(); ++i) { double s = 0; for (auto& t : T) s += t.star_origin[i]; out->star_origin[i] = s; }
+    if (out->disk_origin) for (size_t i = 0; i < T[0].disk_origin.size(); ++i) { double s = 0; for (auto& t : T) s += t.disk_origin[i]; out->disk_origin[i] = s; }
     if (out->n_phot_envoyes) { for (size_t i = 0; i < nl; ++i) { double s = 0; for (auto& t : T) s += t.n_phot_envoyes[i]; out->n_phot_envoyes[i] = s; } }
     double* sp[9] = {out->sed, out->sed_q, out->sed_u, out->sed_v, out->n_phot_sed, out->sed_star, out->sed_star_scat, out->sed_disk, out->sed_disk_scat};
     for (int a = 0; a < 9; ++a) if (sp[a]) { size_t n = T[0].sed[a].size(); for (size_t i = 0; i < n; ++i) { double s = 0; for (auto& t : T) s += t.sed[a][i]; sp[a][i] = s; } }
@@ -1808,7 +1860,8 @@ int oracle_set_grains(void* h, const mcb_grains* g) { Oracle* O = (Oracle*)h; O-
 static int check_run(Oracle* O, const mcb_run_params* r) {
   if (!O->has_grid || !O->has_op || !O->has_em) { snprintf(O->err, sizeof O->err, "run before uploads"); return MCB_ERR_STATE; }
   if ((r->lscattering_method1 || !r->lonly_LTE) && !O->has_gr) { snprintf(O->err, sizeof O->err, "per-grain mode without grain tables"); return MCB_ERR_STATE; }
-  if (r->loutput_mc || (r->lscatt_ray_tracing2 && O->g.l3D)) { snprintf(O->err, sizeof O->err, "mode not built in the oracle"); return MCB_ERR_UNSUPPORTED; }
+  if (r->lmono0 && r->loutput_mc && (r->npix_x < 1 || r->npix_y < 1 || !(r->map_size > 0.0))) { snprintf(O->err, sizeof O->err, "loutput_mc needs npix_x, npix_y, map_size"); return MCB_ERR_BAD_ARG; }
+  if ( (r->lscatt_ray_tracing2 && O->g.l3D)) { snprintf(O->err, sizeof O->err, "mode not built in the oracle"); return MCB_ERR_UNSUPPORTED; }
   return MCB_OK;
 }
 

@@ -420,3 +420,46 @@ def test_more_handles_than_constant_banks_run_concurrently():
     assert np.array_equal(a.n_phot_sed, b.n_phot_sed) and np.allclose(a.sed, b.sed, rtol=1e-9, atol=1e-12)
     for g in Gs:
         g.close()
+
+
+@pytest.mark.parametrize("sym", [0, 1])
+def test_photon_maps_match_oracle(sym):
+    """Image step with loutput_mc: forced scattering has no feedback, so with the shared Philox streams every packet
+    lands in the same pixel as in the oracle (up to libm-ulp flips at pixel edges)."""
+    P = small_problems()["cyl2D"]()
+    kw = dict(letape_th=0, lmono=1, lmono0=1, loutput_mc=1, lsepar_pola=1, lsepar_contrib=1, l_sym_ima=sym,
+              npix_x=24, npix_y=16, map_size=700.0, N_thet=4, N_phi=2)
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(8, 8, 400, 1.0e30, 1, False, **kw)
+    G.close()
+    to = Oracle(P).run(n_threads=0, lambda_in=8, p_lambda_in=8, n_photons2=400, **kw)
+    assert tg.stats[0] == to.stats[0] == 128 * 400
+    mg, mo = tg.stokes_map, to.stokes_map
+    assert mg.shape == mo.shape == (24, 16, 4, 2, 8)
+    assert mo[..., 0].sum() > 0 and np.isclose(mg[..., 0].sum(), mo[..., 0].sum(), rtol=1e-3)
+    # per detector bin and per plane
+    assert np.allclose(mg.sum(axis=(0, 1)), mo.sum(axis=(0, 1)), rtol=5e-3, atol=2e-3 * np.abs(mo).sum(axis=(0, 1)).max())
+    # pixel by pixel for the bright pixels of the intensity map
+    Ig, Io = mg[..., 0], mo[..., 0]
+    bright = Io > 0.01 * Io.max()
+    assert bright.sum() > 20
+    assert np.allclose(Ig[bright], Io[bright], rtol=0.02)
+    # the four contributions still add up to I on the device
+    assert np.allclose(mg[..., 4:8].sum(axis=-1), mg[..., 0], rtol=1e-9, atol=1e-12)
+
+
+def test_capt_interet_and_origin_match_oracle():
+    P = small_problems()["cyl2D"]()
+    kw = dict(letape_th=0, lmono=1, N_thet=5, lorigine=1, capt_interet=2, lonly_capt_interet=1, capt_inf=2, capt_sup=3)
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(8, 8, 10 ** 9, 150.0, 1, False, **kw)
+    G.close()
+    to = Oracle(P).run(n_threads=0, lambda_in=8, p_lambda_in=8, n_photons2=10 ** 9, n_phot_lim=150.0, **kw)
+    assert tg.stats[0] == to.stats[0] == 128 * 150
+    assert tg.sed[:, 0].sum() == 0 and tg.sed[:, 3:].sum() == 0
+    assert np.allclose(tg.n_phot_sed, to.n_phot_sed, atol=3)
+    assert np.isclose(tg.star_origin[7], to.star_origin[7], rtol=1e-3) and to.star_origin[7] > 0
+    assert np.isclose(tg.disk_origin[7].sum(), to.disk_origin[7].sum(), rtol=5e-3)
+    assert np.isclose(tg.star_origin[7] + tg.disk_origin[7].sum(), tg.sed[7, 1].sum(), rtol=1e-9)
+    big = to.disk_origin[7] > 0.01 * to.disk_origin[7].max()
+    assert np.allclose(tg.disk_origin[7][big], to.disk_origin[7][big], rtol=0.05)
