@@ -164,6 +164,8 @@ typedef struct mcb_grains {
   const double  *kdB_dT_1grain_nRE_CDF;    /* (n_lambda, nRE grains, n_T) :190 */
   const int32_t *l_RE;             /* (grain_nRE_start:grain_nRE_end, n_cells) logical, :304 */
   const double  *J0;               /* (n_cells, n_lambda) radiation_field.f90:154 */
+  /* LTE grains, low-memory emission (low_mem_th_emission, thermal_emission.f90:127-140,739-751) */
+  const double  *kdB_dT_1grain_LTE_CDF;    /* (n_lambda, grain_RE_LTE_start:grain_RE_LTE_end, n_T) :137 */
 } mcb_grains;
 
 /* ------------------------------------------------------------------------
@@ -181,6 +183,7 @@ typedef struct mcb_emission {
   double  E_paquet;                      /* Stokes(1) at emission  */
   double  R_ISM;                         /* stars.f90:728-787      */
   double  centre_ISM[3];
+  const double *correct_E_emission;      /* (n_cells) with lweight_emission (dust_transfer.f90:1140), else NULL */
 } mcb_emission;
 
 /* ------------------------------------------------------------------------
@@ -240,6 +243,13 @@ typedef struct mcb_run_params {
   int32_t l_sym_ima;                  /* left-right symmetry: half a photon in each mirror pixel */
   int32_t lonly_capt_interet, capt_inf;   /* keep only detector bins capt_inf..capt_sup (read_param.f90:182-190) */
   int32_t lorigine, capt_interet;     /* star_origin / disk_origin tallies for bin capt_interet */
+  /* emission extras (dust_transfer.f90:1090-1142) and the low-memory LTE emission branch */
+  int32_t low_mem_th_emission;        /* 1: per-grain kdB_dT_1grain_LTE_CDF + select_absorbing_grain (needs upload_grains) */
+  int32_t lweight_emission;           /* disk packets carry correct_E_emission(icell) */
+  int32_t lspot;                      /* hot spot on star 1 */
+  float   T_spot, surf_fraction_spot, theta_spot, phi_spot;   /* parameters.f90:247 (degrees) */
+  double  star1_T;                    /* star(1)%T */
+  const double *tab_lambda;           /* (n_lambda) micron, wavelengths.f90:15; read with lspot only */
 } mcb_run_params;
 
 /* ------------------------------------------------------------------------

@@ -73,6 +73,7 @@ class mcb_emission(C.Structure):
         ("prob_E_cell", c_double_p), ("CDF_E_star", c_float_p),
         ("L_packet_th", C.c_double), ("E_paquet", C.c_double),
         ("R_ISM", C.c_double), ("centre_ISM", C.c_double * 3),
+        ("correct_E_emission", c_double_p),
     ]
 
 
@@ -97,7 +98,7 @@ class mcb_grains(C.Structure):
         ("kappa_abs_RE", c_double_p), ("proba_abs_RE", c_double_p),
         ("Proba_abs_RE_LTE", c_double_p), ("Proba_abs_RE_LTE_p_nLTE", c_double_p),
         ("log_E_em_1grain_nRE", c_double_p), ("kdB_dT_1grain_nRE_CDF", c_double_p),
-        ("l_RE", c_int32_p), ("J0", c_double_p),
+        ("l_RE", c_int32_p), ("J0", c_double_p), ("kdB_dT_1grain_LTE_CDF", c_double_p),
     ]
 
 
@@ -124,6 +125,9 @@ class mcb_run_params(C.Structure):
         ("npix_x", C.c_int32), ("npix_y", C.c_int32), ("zoom", C.c_float), ("map_size", C.c_double),
         ("cos_disk", C.c_double), ("sin_disk", C.c_double), ("l_sym_ima", C.c_int32),
         ("lonly_capt_interet", C.c_int32), ("capt_inf", C.c_int32), ("lorigine", C.c_int32), ("capt_interet", C.c_int32),
+        ("low_mem_th_emission", C.c_int32), ("lweight_emission", C.c_int32), ("lspot", C.c_int32),
+        ("T_spot", C.c_float), ("surf_fraction_spot", C.c_float), ("theta_spot", C.c_float), ("phi_spot", C.c_float),
+        ("star1_T", C.c_double), ("tab_lambda", c_double_p),
     ]
 
 
@@ -242,6 +246,11 @@ def make_emission(P) -> Holder:
     c = getattr(P, "centre_ISM", (0.0, 0.0, 0.0))
     for i in range(3):
         e.centre_ISM[i] = float(c[i])
+    a = getattr(P, "correct_E_emission", None)
+    if a is not None:
+        a = farray(a, np.float64)
+        keep["correct_E_emission"] = a
+    e.correct_E_emission = ptr(a, np.float64)
     return Holder(e, keep)
 
 
@@ -275,7 +284,9 @@ def make_run(**kw) -> Holder:
              loutput_mc=0, n_theta_I=15, n_phi_I=15,
              lonly_nLTE=0, lRE_nLTE=0, lnRE=0, low_mem_th_emission_nLTE=0, low_mem_scattering=1,
              npix_x=0, npix_y=0, zoom=1.0, map_size=0.0, cos_disk=1.0, sin_disk=0.0, l_sym_ima=0,
-             lonly_capt_interet=0, capt_inf=1, lorigine=0, capt_interet=1)
+             lonly_capt_interet=0, capt_inf=1, lorigine=0, capt_interet=1,
+             low_mem_th_emission=0, lweight_emission=0, lspot=0, T_spot=0.0, surf_fraction_spot=0.0, theta_spot=0.0,
+             phi_spot=0.0, star1_T=0.0, tab_lambda=None)
     unknown = set(kw) - set(d)
     if unknown:
         raise TypeError(f"unknown run parameter(s): {sorted(unknown)}")
@@ -283,7 +294,7 @@ def make_run(**kw) -> Holder:
     r = mcb_run_params()
     keep = {}
     for k, v in d.items():
-        if k in ("tab_u_rt", "tab_v_rt", "tab_w_rt"):
+        if k in ("tab_u_rt", "tab_v_rt", "tab_w_rt", "tab_lambda"):
             a = None if v is None else farray(v, np.float64)
             keep[k] = a
             setattr(r, k, ptr(a, np.float64))

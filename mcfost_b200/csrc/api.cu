@@ -252,6 +252,7 @@ int mcfost_b200_upload_emission(mcb_handle* h, const mcb_emission* e) {
   if ((rc = put(h, "frac_disk", e->frac_E_disk, (size_t)m.n_lambda, &m.frac_disk))) return rc;
   if ((rc = put(h, "prob_E_cell", e->prob_E_cell, (size_t)(m.n_cells + 1) * m.n_lambda, &m.prob_E_cell))) return rc;
   if ((rc = put(h, "CDF_E_star", e->CDF_E_star, (size_t)m.n_lambda * (m.n_stars + 1), &m.CDF_E_star))) return rc;
+  if ((rc = put(h, "correct_E", e->correct_E_emission, (size_t)m.n_cells, &m.correct_E))) return rc;
   m.L_packet_th = e->L_packet_th; m.E_paquet = e->E_paquet; m.R_ISM = e->R_ISM;
   for (int a = 0; a < 3; ++a) m.cISM[a] = e->centre_ISM[a];
   CK(cudaStreamSynchronize(h->stream));
@@ -304,6 +305,10 @@ int mcfost_b200_upload_grains(mcb_handle* h, const mcb_grains* g) {
   if ((rc = put(h, "g_kdB_nRE", g->kdB_dT_1grain_nRE_CDF, nl * k2 * nT, &d.kdB_nRE))) return rc;
   if ((rc = put(h, "g_l_RE", g->l_RE, k2 * nc, &d.l_RE))) return rc;
   if ((rc = put(h, "g_J0", g->J0, nc * nl, &d.J0))) return rc;
+  {
+    const size_t k0 = d.LTE_e >= d.LTE_s && d.LTE_s > 0 ? (size_t)(d.LTE_e - d.LTE_s + 1) : 0;
+    if ((rc = put(h, "g_kdB_LTE", g->kdB_dT_1grain_LTE_CDF, nl * k0 * nT, &d.kdB_LTE))) return rc;
+  }
   CK(cudaStreamSynchronize(h->stream));
   h->gr_host = *g;
   h->has_gr = true;
@@ -403,7 +408,7 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   // ---- modes this library implements; everything else fails loudly ----
   {
     const mcb_grains& g = h->gr_host;
-    const bool need_gr = r->lscattering_method1 || (!r->lonly_LTE && !r->lmono);
+    const bool need_gr = r->lscattering_method1 || (!r->lonly_LTE && !r->lmono) || (r->low_mem_th_emission && !r->lmono);
     if (need_gr && !h->has_gr) return fail(h, MCB_ERR_STATE, "per-grain mode (method 1 / nLTE / nRE) before upload_grains");
     if (r->lscattering_method1) {
       if (!g.C_sca) return fail(h, MCB_ERR_BAD_ARG, "method 1: C_sca missing");
@@ -412,6 +417,10 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
       if (r->lsepar_pola && r->lmethod_aniso1 && (!g.tab_s11 || !g.tab_s12 || !g.tab_s22 || !g.tab_s33 || !g.tab_s34 || !g.tab_s44)) return fail(h, MCB_ERR_BAD_ARG, "method 1: per-grain Mueller tables missing");
       if ((!r->letape_th) && (r->lscatt_ray_tracing1 || r->lscatt_ray_tracing2)) return fail(h, MCB_ERR_UNSUPPORTED, "ray-tracing accumulators need scattering method 2 (dust_ray_tracing.f90)");
     }
+    if (r->low_mem_th_emission && !r->lmono && (!g.kdB_dT_1grain_LTE_CDF || !g.C_abs || g.grain_RE_LTE_start < 1 || g.grain_RE_LTE_end < g.grain_RE_LTE_start))
+      return fail(h, MCB_ERR_BAD_ARG, "low_mem_th_emission: kdB_dT_1grain_LTE_CDF / C_abs / LTE grain range missing");
+    if (r->lweight_emission && !m.correct_E) return fail(h, MCB_ERR_BAD_ARG, "lweight_emission: correct_E_emission missing (upload_emission)");
+    if (r->lspot && (!r->tab_lambda || !(r->star1_T > 0.0) || !(r->T_spot > 0.0f))) return fail(h, MCB_ERR_BAD_ARG, "lspot: tab_lambda / star1_T / T_spot missing");
     if (!r->lonly_LTE && !r->lmono) {
       const bool mixed = !r->lonly_nLTE;
       if (!g.C_abs_norm || !g.J0) return fail(h, MCB_ERR_BAD_ARG, "nLTE / nRE: C_abs_norm / J0 missing");
@@ -481,6 +490,18 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   dr.n_per_chunk = (unsigned long long)r->n_photons2 < dr.sent_lim ? (unsigned long long)r->n_photons2 : dr.sent_lim;
   dr.n_packets_total = dr.count_sent ? (unsigned long long)n_local * dr.n_per_chunk : 0ull;
   dr.nb_proc_equiv = (double)r->n_ranks;
+  dr.low_mem_th = (r->low_mem_th_emission && !r->lmono) ? 1 : 0;
+  dr.lweight_emission = r->lweight_emission; dr.lspot = r->lspot;
+  if (r->lspot) {      // dust_transfer.f90:1101-1107, evaluated once (the reference recomputes it per packet)
+    const double PI_ = MCB_PI;
+    dr.z_spot = (float)cos((double)(r->theta_spot / 180.0f) * PI_);
+    dr.x_spot = (float)(sin((double)(r->theta_spot / 180.0f) * PI_) * cos((double)(r->phi_spot / 180.0f) * PI_));
+    dr.y_spot = (float)(sin((double)(r->theta_spot / 180.0f) * PI_) * sin((double)(r->phi_spot / 180.0f) * PI_));
+    dr.cos_thet_spot = sqrtf(1.0f - r->surf_fraction_spot);
+    dr.T_spot = r->T_spot; dr.star1_T = r->star1_T;
+    int rc2;
+    if ((rc2 = put(h, "tab_lambda", r->tab_lambda, (size_t)m.n_lambda, &m.tab_lambda))) return rc2;
+  }
   dr.mc_maps = mc_maps ? 1 : 0; dr.lorigine = r->lorigine; dr.capt_interet = r->capt_interet;
   dr.lonly_capt_interet = r->lonly_capt_interet; dr.capt_inf = r->capt_inf;
   dr.npix_x = r->npix_x; dr.npix_y = r->npix_y; dr.l_sym_ima = r->l_sym_ima;

@@ -63,6 +63,7 @@ struct DevGrains {
   const double *logE_nRE, *kdB_nRE; // nRE grains
   const int *l_RE;                  // (nRE grains, n_cells)
   const double *J0;                 // (n_cells, n_lambda)
+  const double *kdB_LTE;            // LTE grains, low-memory emission: (n_lambda, k, n_T)
   int *xT_1g, *xT_1g_nRE;           // tallies: xT_ech_1grain (nLTE grains, n_cells), xT_ech_1grain_nRE
 };
 
@@ -101,6 +102,8 @@ struct DevModel {
   const double *spec_cumul, *frac_star, *frac_disk, *prob_E_cell;
   const float *CDF_E_star;
   double L_packet_th, E_paquet, R_ISM, cISM[3];
+  const double *correct_E;          // (n_cells) correct_E_emission (lweight_emission) or null
+  const double *tab_lambda;         // (n_lambda) micron (hot spot only)
   // ---- tallies ----------------------------------------------------------
   double *tally;            // packed fp64 block
   TallyLayout lay;
@@ -136,6 +139,10 @@ struct DevRun {
   unsigned long long n_per_chunk;       // count_sent: min(n_photons2, sent_lim)
   unsigned long long n_packets_total;   // count_sent: n_local_chunks * n_per_chunk
   double nb_proc_equiv;                 // n_ranks: scales the local tally in Temp_LTE
+  // emission extras (dust_transfer.f90:1090-1142); spot direction and opening precomputed on the host
+  int low_mem_th, lweight_emission, lspot;
+  float x_spot, y_spot, z_spot, cos_thet_spot, T_spot;
+  double star1_T;
   // capteur extras (output.f90:303-357,396-570)
   int capt_full;                        // 1: lorigine / lonly_capt_interet / photon maps are on -> capteur_full
   int mc_maps, lorigine, capt_interet, lonly_capt_interet, capt_inf, npix_x, npix_y, l_sym_ima;

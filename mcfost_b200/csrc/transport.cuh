@@ -261,8 +261,9 @@ __device__ __forceinline__ LtePre lte_prefetch(const DevModel& m, int idx) {
   p.vol = __ldg(m.volume + idx);
   return p;
 }
+// Temp_LTE (thermal_emission.f90:649-706): temperature index and interpolation fraction of the cell
 template <bool SM>
-__device__ __forceinline__ int im_reemission_LTE(const DevModel& m, const DevRun& r, int idx, int p_icell, float rand2, const LtePre pre) {
+__device__ __forceinline__ void temp_lte(const DevModel& m, const DevRun& r, int idx, int p_icell, const LtePre pre, int& Ti_out, double& frac_out) {
   double Qheat = pre.xkj * r.nb_proc_equiv * m.L_packet_th / pre.vol;
   int Ti = 2;
   double frac_T2 = 0.0;       // `frac` is left undefined by the reference at T_min; 0 chosen (same as the oracle)
@@ -278,6 +279,12 @@ __device__ __forceinline__ int im_reemission_LTE(const DevModel& m, const DevRun
     }
   }
   atomicMax(m.xT_ech + idx, Ti);
+  Ti_out = Ti; frac_out = frac_T2;
+}
+template <bool SM>
+__device__ __forceinline__ int im_reemission_LTE(const DevModel& m, const DevRun& r, int idx, int p_icell, float rand2, const LtePre pre) {
+  int Ti; double frac_T2;
+  temp_lte<SM>(m, r, idx, p_icell, pre, Ti, frac_T2);
   const double frac_T1 = 1.0 - frac_T2;
   int l1 = 0, l2 = m.n_lambda, l = (l1 + l2) / 2;
   while ((l2 - l1) > 1) {
@@ -296,7 +303,7 @@ __device__ __forceinline__ int im_reemission_LTE(const DevModel& m, const DevRun
 // =============================================================================
 #define MCB_AU_TO_CM_MUM2 ((149597870700.0 * 100.0) * (1.0e-4 * 1.0e-4))     /* AU_to_cm * mum_to_cm**2 */
 
-// thermal_emission.f90:1953-2040 select_absorbing_grain, heating_method 2 (nLTE) / 3 (qRE); idx 0-based cell
+// thermal_emission.f90:1953-2040 select_absorbing_grain, heating_method 1 (LTE) / 2 (nLTE) / 3 (qRE); idx 0-based cell
 template <int BANK>
 __device__ __noinline__ int select_absorbing_grain(int lambda, int idx, float rand, int heating_method) {
   const DevModel& m = c_m; const DevRun& r = c_r; const DevGrains& g = m.gr;
@@ -304,7 +311,10 @@ __device__ __noinline__ int select_absorbing_grain(int lambda, int idx, float ra
   const size_t pl = (size_t)(variable ? idx : 0) + (size_t)m.p_n_cells * (lambda - 1);
   const double kf = __ldg(m.kappa_factor + idx);
   double norm; int kstart, kend;
-  if (heating_method == 2) {
+  if (heating_method == 1) {
+    norm = __ldg(m.kappa_abs + pl) * kf / MCB_AU_TO_CM_MUM2;
+    kstart = g.LTE_s; kend = g.LTE_e;
+  } else if (heating_method == 2) {
     norm = __ldg(g.kappa_abs_nLTE + pl) * kf / MCB_AU_TO_CM_MUM2;
     kstart = g.nLTE_s; kend = g.nLTE_e;
   } else {
@@ -479,6 +489,26 @@ __device__ __noinline__ Scat1Out scatter_method1(int lambda, int p_icell, uint4 
   return Scat1Out{u1, v1, w1, S[0], S[1], S[2], S[3]};
 }
 
+// im_reemission_LTE, low-memory branch (thermal_emission.f90:739-751): the absorbing LTE grain is drawn and its own
+// kdB_dT_1grain_LTE_CDF is bisected instead of the cell's kdB_dT_CDF
+template <bool SM, int BANK>
+__device__ __noinline__ int im_reemission_LTE_lowmem(int idx, int p_icell, int lambda0, float rand1, float rand2, const LtePre pre) {
+  const DevModel& m = c_m; const DevRun& r = c_r; const DevGrains& g = m.gr;
+  int Ti; double frac_T2;
+  temp_lte<SM>(m, r, idx, p_icell, pre, Ti, frac_T2);
+  const double frac_T1 = 1.0 - frac_T2;
+  const int k = select_absorbing_grain<BANK>(lambda0, idx, rand1, 1);
+  const int nk = g.LTE_e - g.LTE_s + 1, kk = k - g.LTE_s;
+  auto CDF = [&](int l, int t) { return __ldg(g.kdB_LTE + (l - 1) + (size_t)m.n_lambda * (kk + (size_t)nk * (t - 1))); };
+  int l1 = 0, l2 = m.n_lambda, l = (l1 + l2) / 2;
+  while ((l2 - l1) > 1) {
+    const double proba = frac_T1 * CDF(l, Ti - 1) + frac_T2 * CDF(l, Ti);
+    if ((double)rand2 > proba) l1 = l; else l2 = l;
+    l = (l1 + l2) / 2;
+  }
+  return l + 1;
+}
+
 // dust_transfer.f90:1353-1395 when .not.lonly_LTE: energy kept by grains out of equilibrium, choice of
 // the grain regime, re-emission wavelength.  Returns the new wavelength, or 0 if the packet is dropped.
 // S0 is scaled in place; e_nRE returns this packet's contribution to E_abs_nRE.
@@ -496,7 +526,8 @@ __device__ __noinline__ AbsOut absorb_grain_regimes(int idx, int p_icell, int la
   }
   const float rand1 = u01(b.x), rand2 = u01(b.y);
   if (r.lonly_nLTE) o.lambda = im_reemission_NLTE<BANK>(idx, lambda0, rand1, rand2);
-  else if ((double)sel <= __ldg(g.P_LTE + cl)) o.lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, rand2, lte_prefetch(m, idx));
+  else if ((double)sel <= __ldg(g.P_LTE + cl)) o.lambda = r.low_mem_th ? im_reemission_LTE_lowmem<SM, BANK>(idx, p_icell, lambda0, rand1, rand2, lte_prefetch(m, idx))
+                                                                     : im_reemission_LTE<SM>(m, r, idx, p_icell, rand2, lte_prefetch(m, idx));
   else if ((double)sel <= __ldg(g.P_LTE_p_nLTE + cl)) o.lambda = im_reemission_NLTE<BANK>(idx, lambda0, rand1, rand2);
   else o.lambda = im_reemission_qRE<BANK>(idx, lambda0, rand1, rand2);
   return o;
@@ -910,6 +941,13 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
       else cell = G::index(m, x, y, z);
       if (m.star_out[i_star - 1]) lintersect = G::move_to_grid(m, x, y, z, u, v, w, cell);
       S0 = m.E_paquet;
+      if (r.lspot) {      // hot spot on star 1 (dust_transfer.f90:1094-1119), tested on the position emit_packet_uniform_sphere returns
+        if ((double)r.x_spot * x + (double)r.y_spot * y + (double)r.z_spot * z > (double)r.cos_thet_spot * m.star[0][3]) {
+          const float hc_lk = (float)(6.626070040e-34 * 299792458.0 / (__ldg(m.tab_lambda + lambda - 1) * 1e-6 * 1.38064852e-23));
+          const float correct_spot = (float)((exp((double)hc_lk / r.star1_T) - 1) / (double)(expf(hc_lk / r.T_spot) - 1));
+          S0 = S0 * correct_spot;
+        }
+      }
     } else if ((double)rand <= t_frac_disk<SM>(m, lambda)) {
       flag_star = false; flag_ISM = false;
       const int ic = select_cellule(m, lambda, nextf());
@@ -919,6 +957,7 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
       const float rw = nextf(), rp = nextf();
       random_isotropic_direction(rw, rp, u, v, w);
       S0 = m.E_paquet;
+      if (r.lweight_emission) S0 = S0 * __ldg(m.correct_E + ic - 1);      // dust_transfer.f90:1140-1142
     } else {
       flag_star = false; flag_ISM = true;
       // emit_packet_ISM (stars.f90:728-787)
@@ -1209,9 +1248,11 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
     const uint4 bnext = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev + 2u, pk_lo, pk_hi, r.call_index);
 #endif
     int lambda;
-    if (!GR || r.lonly_LTE) {
+    if (!GR || (r.lonly_LTE && !r.low_mem_th)) {
       // b.x is rand1: drawn but unused in the high-memory LTE branch (thermal_emission.f90:739-765)
       lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, u01(b.y), pre);
+    } else if (r.lonly_LTE) {
+      lambda = im_reemission_LTE_lowmem<SM, BANK>(idx, p_icell, misc_lambda(misc), u01(b.x), u01(b.y), pre);
     } else {
       // the grain-regime draw (dust_transfer.f90:1379) has its own Philox block, so rand / rand2 / the
       // direction draws keep the words they have in the lonly_LTE case

@@ -1003,6 +1003,7 @@ def multi_grain_like(n_photons_eq_th=100, n_rad=24, nz=12, n_rad_in=4, tau_mid=3
         i3 = np.concatenate((np.zeros((len(ks), 1, n_T)), i3), axis=1)
         cdf_ = i3 / np.maximum(i3[:, -1:, :], 1e-300)
         return np.asfortranarray(logE), np.asfortranarray(np.transpose(cdf_, (1, 0, 2)))     # (nk, n_T), (nl, nk, n_T)
+    _, P.kdB_dT_1grain_LTE_CDF = one_grain(kL)
     P.log_E_em_1grain, P.kdB_dT_1grain_nLTE_CDF = one_grain(kN)
     P.log_E_em_1grain_nRE, P.kdB_dT_1grain_nRE_CDF = one_grain(kR)
     # kabs_nLTE_CDF(grain_RE_nLTE_start-1:grain_RE_nLTE_end, n_cells, n_lambda) (dust_prop.f90:930-945)

@@ -56,6 +56,7 @@ const float  tiny_real_x1e6 = tiny_real * 1.0e6f;
 const float  max_int = (float)2147483647 * (1.0f - 1.0e-5f);
 const double grid_prec = 1.0e-14;
 const double prec_grille_sph = 1.0e-7;
+const double hp = 6.626070040e-34, kb = 1.38064852e-23, c_light = 299792458.0;      // constants.f90:21-23
 const double AU_to_cm = 149597870700.0 * 100.0;     // constants.f90:62-65
 const double mum_to_cm = 1.0e-4;                    // constants.f90:73
 const double AU_to_cm_mum2 = AU_to_cm * (mum_to_cm * mum_to_cm);   // AU_to_cm * mum_to_cm**2
@@ -964,7 +965,7 @@ struct Oracle {
   }
 
   // =====================================================================
-  // dust_transfer.f90:1047-1151  emit_packet   (lspot, lweight_emission off)
+  // dust_transfer.f90:1047-1151  emit_packet
   // =====================================================================
   void emit_packet(PacketRng& rng, Packet& p) {
     p.lintersect = true;
@@ -977,6 +978,17 @@ struct Oracle {
       float rand2 = (float)rng_next(&rng), rand3 = (float)rng_next(&rng), rand4 = (float)rng_next(&rng);
       emit_packet_uniform_sphere(i_star, rand, rand2, rand3, rand4, p.icell, p.x, p.y, p.z, p.u, p.v, p.w, p.lintersect);
       p.S[0] = e.E_paquet; p.S[1] = p.S[2] = p.S[3] = 0.0;
+      if (r.lspot) {                                                   // :1094-1119 (`real` locals)
+        const float z_spot = (float)std::cos((double)(r.theta_spot / 180.0f) * pi);
+        const float x_spot = (float)(std::sin((double)(r.theta_spot / 180.0f) * pi) * std::cos((double)(r.phi_spot / 180.0f) * pi));
+        const float y_spot = (float)(std::sin((double)(r.theta_spot / 180.0f) * pi) * std::sin((double)(r.phi_spot / 180.0f) * pi));
+        const float cos_thet_spot = std::sqrt(1.0f - r.surf_fraction_spot);
+        if ((double)x_spot * p.x + (double)y_spot * p.y + (double)z_spot * p.z > (double)cos_thet_spot * star_r(1)) {
+          const float hc_lk = (float)(hp * c_light / (r.tab_lambda[p.lambda - 1] * 1e-6 * kb));
+          const float correct_spot = (float)((std::exp((double)hc_lk / r.star1_T) - 1) / (double)(std::exp(hc_lk / r.T_spot) - 1));
+          for (int a = 0; a < 4; ++a) p.S[a] = p.S[a] * correct_spot;
+        }
+      }
     } else if ((double)rand <= e.frac_E_disk[p.lambda - 1]) {
       p.flag_star = false; p.flag_ISM = false;
       rand = (float)rng_next(&rng);
@@ -986,6 +998,7 @@ struct Oracle {
       pos_em_cell(p.icell, rand, rand2, rand3, p.x, p.y, p.z);
       random_isotropic_direction(rng, p.u, p.v, p.w);
       p.S[0] = e.E_paquet; p.S[1] = p.S[2] = p.S[3] = 0.0;
+      if (r.lweight_emission) p.S[0] = p.S[0] * e.correct_E_emission[p.icell - 1];      // :1140-1142
     } else {
       p.flag_star = false; p.flag_ISM = true;
       emit_packet_ISM(rng, p.icell, p.x, p.y, p.z, p.u, p.v, p.w, p.S, p.lintersect);
@@ -1325,12 +1338,24 @@ struct Oracle {
   // =====================================================================
   // thermal_emission.f90:710-771  im_reemission_LTE  (high-memory branch)
   // =====================================================================
-  void im_reemission_LTE(ThreadTallies& t, int icell, int p_icell, float /*rand1*/, float rand2, int& lambda) {
+  void im_reemission_LTE(ThreadTallies& t, int icell, int p_icell, float rand1, float rand2, int& lambda) {
     int Ti; float Temp; double frac_T2;
     Temp_LTE(t, icell, Ti, Temp, frac_T2);
     int T2 = Ti, T1 = Ti - 1;
     double frac_T1 = 1.0 - frac_T2;
     int l1 = 0, l2 = o.n_lambda, l = (l1 + l2) / 2;
+    if (r.low_mem_th_emission) {                                       // :739-751
+      const int k = select_absorbing_grain(lambda, icell, rand1, 1);
+      const int nk = gr.grain_RE_LTE_end - gr.grain_RE_LTE_start + 1;
+      auto cdf = [&](int ll, int Tt) { return gr.kdB_dT_1grain_LTE_CDF[(size_t)(ll - 1) + (size_t)o.n_lambda * ((size_t)(k - gr.grain_RE_LTE_start) + (size_t)nk * (Tt - 1))]; };
+      while ((l2 - l1) > 1) {
+        double proba = frac_T1 * cdf(l, T1) + frac_T2 * cdf(l, T2);
+        if ((double)rand2 > proba) l1 = l; else l2 = l;
+        l = (l1 + l2) / 2;
+      }
+      lambda = l + 1;
+      return;
+    }
     while ((l2 - l1) > 1) {
       double proba = frac_T1 * kdB_dT_CDF(l, T1, p_icell) + frac_T2 * kdB_dT_CDF(l, T2, p_icell);
       if ((double)rand2 > proba) l1 = l; else l2 = l;
@@ -1859,7 +1884,7 @@ int oracle_set_grains(void* h, const mcb_grains* g) { Oracle* O = (Oracle*)h; O-
 
 static int check_run(Oracle* O, const mcb_run_params* r) {
   if (!O->has_grid || !O->has_op || !O->has_em) { snprintf(O->err, sizeof O->err, "run before uploads"); return MCB_ERR_STATE; }
-  if ((r->lscattering_method1 || !r->lonly_LTE) && !O->has_gr) { snprintf(O->err, sizeof O->err, "per-grain mode without grain tables"); return MCB_ERR_STATE; }
+  if ((r->lscattering_method1 || !r->lonly_LTE || r->low_mem_th_emission) && !O->has_gr) { snprintf(O->err, sizeof O->err, "per-grain mode without grain tables"); return MCB_ERR_STATE; }
   if (r->lmono0 && r->loutput_mc && (r->npix_x < 1 || r->npix_y < 1 || !(r->map_size > 0.0))) { snprintf(O->err, sizeof O->err, "loutput_mc needs npix_x, npix_y, map_size"); return MCB_ERR_BAD_ARG; }
   if ( (r->lscatt_ray_tracing2 && O->g.l3D)) { snprintf(O->err, sizeof O->err, "mode not built in the oracle"); return MCB_ERR_UNSUPPORTED; }
   return MCB_OK;

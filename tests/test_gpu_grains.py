@@ -156,3 +156,42 @@ def test_only_nlte_and_state_errors(monkeypatch):
         G2.mc_photon_loop(1, 1, 10, 1.0e30, 1, False, lscattering_method1=1)
     assert ei.value.code == 6
     G2.close()
+
+
+def test_hot_spot_and_weighted_emission_match_oracle_packet_by_packet():
+    P = S.multi_grain_like(n_photons_eq_th=50, tau_mid=5.0, pola=False)
+    S.repartition_energie(P, Tdust=np.full(P.n_cells, 150.0))        # warm disk: some packets come from the dust
+    P.correct_E_emission = 0.25 + 0.5 * np.random.default_rng(3).random(P.n_cells)
+    lam = int(np.argmax(P.tab_lambda > 30.0)) + 1
+    kw = dict(letape_th=0, lmono=1, lspot=1, T_spot=12000.0, surf_fraction_spot=0.75, theta_spot=30.0, phi_spot=40.0,
+              star1_T=float(P.star_T[0]), tab_lambda=P.tab_lambda, lweight_emission=1, l_sym_axiale=0, N_phi=4)
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(lam, lam, 10 ** 9, 300.0, 1, False, **kw)
+    G.close()
+    to = Oracle(P).run(n_threads=0, lambda_in=lam, p_lambda_in=lam, n_photons2=10 ** 9, n_phot_lim=300.0, **kw)
+    assert tg.stats[0] == to.stats[0] == 128 * 300
+    assert np.allclose(tg.n_phot_sed, to.n_phot_sed, atol=3)
+    assert to.sed_disk.sum() > 0 and to.sed_star.sum() > 0
+    assert np.isclose(tg.sed_star.sum(), to.sed_star.sum(), rtol=2e-3)
+    assert np.isclose(tg.sed_disk.sum(), to.sed_disk.sum(), rtol=2e-3)
+    assert np.allclose(tg.sed.sum(axis=0), to.sed.sum(axis=0), rtol=5e-3, atol=1e-3 * to.sed.sum())
+
+
+def test_low_memory_lte_emission_statistical_parity(monkeypatch):
+    monkeypatch.setenv("MCB_BLOCKS", "8")
+    P = S.multi_grain_like(n_photons_eq_th=1500, tau_mid=30.0, pola=False)
+    kw = dict(lonly_LTE=1, low_mem_th_emission=1)
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(1, 1, 1500, 1.0e30, 1, False, **kw)
+    G.close()
+    to = Oracle(P).run(n_threads=0, n_photons2=1500, **kw)
+    assert tg.stats[0] == to.stats[0] and tg.stats[5] + tg.stats[6] == tg.stats[0]
+    assert _close(tg.stats[4], to.stats[4]) and _close(tg.stats[3], to.stats[3])
+    To, Tg = S.temp_finale(P, to.xKJ_abs), S.temp_finale(P, tg.xKJ_abs)
+    lit = (to.xKJ_abs > 0) & (tg.xKJ_abs > 0)
+    rel = np.abs(Tg[lit] - To[lit]) / To[lit]
+    assert np.median(rel) < 0.01 and np.percentile(rel, 75) < 0.05
+    no, ng = to.n_phot_sed.sum(axis=(1, 2)), tg.n_phot_sed.sum(axis=(1, 2))
+    m = (no + ng) > 100
+    z = (ng[m] - no[m]) / np.sqrt(no[m] + ng[m])
+    assert np.mean(np.abs(z) < 3.5) > 0.95 and abs(z.mean()) < 0.5

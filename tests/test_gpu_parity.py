@@ -101,6 +101,10 @@ def test_empty_and_error_paths():
     assert err.value.code == 6         # MCB_ERR_STATE: nLTE / nRE re-emission needs upload_grains first
     with pytest.raises(api.McfostB200Error) as err:
         G.mc_photon_loop(1, 1, 10, loutput_mc=1, letape_th=0, lmono=1, lmono0=1)
+    assert err.value.code == 2         # MCB_ERR_BAD_ARG: photon maps without npix / map_size
+    with pytest.raises(api.McfostB200Error) as err:
+        G.mc_photon_loop(1, 1, 10, letape_th=0, lmono=1, lscatt_ray_tracing1=1, RT_n_incl=9, RT_n_az=1,
+                         tab_u_rt=np.zeros((9, 1)), tab_v_rt=np.zeros((9, 1)), tab_w_rt=np.ones(9))
     assert err.value.code == 5         # MCB_ERR_UNSUPPORTED: fails loudly, no silent fallback
     with pytest.raises(api.McfostB200Error):
         G.mc_photon_loop(P.n_lambda + 1, 1, 10)

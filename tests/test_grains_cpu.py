@@ -136,3 +136,43 @@ def test_variable_dust_mixed_regimes():
     assert (t.xT_ech_1grain > 2).any()
     t1 = O.run(n_threads=1, n_photons2=30, lscattering_method1=1, lmethod_aniso1=0, low_mem_scattering=1)
     assert t1.stats[5] + t1.stats[6] == t1.stats[0]
+
+
+def test_low_memory_lte_emission_matches_the_cell_cdf_statistically():
+    """low_mem_th_emission draws the absorbing LTE grain and bisects its own CDF; summed over grains with the
+    absorption weights this is the cell's kdB_dT_CDF, so the temperature structure and the emergent spectrum agree
+    with the high-memory branch within noise."""
+    P = S.multi_grain_like(n_photons_eq_th=300, tau_mid=20.0, n_rad=12, nz=8, n_rad_in=3, pola=False)
+    O = Oracle(P)
+    a = O.run(n_threads=0, n_photons2=300, lonly_LTE=1, low_mem_th_emission=1)
+    b = O.run(n_threads=0, n_photons2=300, lonly_LTE=1, low_mem_th_emission=0)
+    assert a.stats[5] + a.stats[6] == a.stats[0]
+    assert abs(a.stats[4] / b.stats[4] - 1.0) < 0.05
+    big = b.xKJ_abs > np.percentile(b.xKJ_abs, 50)
+    assert np.median(np.abs(a.xKJ_abs[big] / b.xKJ_abs[big] - 1.0)) < 0.1
+    na, nb = a.n_phot_sed.sum(axis=(1, 2)), b.n_phot_sed.sum(axis=(1, 2))
+    m = (na + nb) > 200
+    z = (na[m] - nb[m]) / np.sqrt(na[m] + nb[m])
+    assert np.mean(np.abs(z) < 4) > 0.9
+
+
+def test_hot_spot_and_weighted_emission_scale_the_packet_energy():
+    P = S.multi_grain_like(n_photons_eq_th=50, tau_mid=5.0, pola=False)
+    S.repartition_energie(P, Tdust=np.full(P.n_cells, 150.0))        # warm disk: some packets are emitted by the dust
+    lam = int(np.argmax(P.tab_lambda > 30.0)) + 1
+    assert 0.0 < P.frac_E_stars[lam - 1] < 1.0
+    O = Oracle(P)
+    kw = dict(letape_th=0, lmono=1, lambda_in=lam, p_lambda_in=lam, n_photons2=10 ** 9, n_phot_lim=200.0)
+    base = O.run(n_threads=1, **kw)
+    # hot spot covering half the star, 2x hotter: the star-light energy goes up, packet counts do not change
+    spot = O.run(n_threads=1, lspot=1, T_spot=12000.0, surf_fraction_spot=0.75, theta_spot=0.0, phi_spot=0.0,
+                 star1_T=float(P.star_T[0]), tab_lambda=P.tab_lambda, **kw)
+    assert np.array_equal(spot.n_phot_sed, base.n_phot_sed)
+    assert spot.sed_star.sum() > 1.2 * base.sed_star.sum() and np.isclose(spot.sed_disk.sum(), base.sed_disk.sum())
+    # weighted emission: every disk packet carries correct_E_emission of its cell
+    P.correct_E_emission = np.full(P.n_cells, 0.25)
+    O.set_emission(P)
+    w = O.run(n_threads=1, lweight_emission=1, **kw)
+    assert np.array_equal(w.n_phot_sed, base.n_phot_sed)
+    assert np.isclose(w.sed_disk.sum(), 0.25 * base.sed_disk.sum(), rtol=1e-12) and base.sed_disk.sum() > 0
+    assert np.isclose(w.sed_star.sum(), base.sed_star.sum(), rtol=1e-12)
