@@ -250,6 +250,9 @@ typedef struct mcb_run_params {
   float   T_spot, surf_fraction_spot, theta_spot, phi_spot;   /* parameters.f90:247 (degrees) */
   double  star1_T;                    /* star(1)%T */
   const double *tab_lambda;           /* (n_lambda) micron, wavelengths.f90:15; read with lspot only */
+  /* packet counts per cell (radiation_field.f90:53,60): thermal step with lmcfost_lib (one column), SED / image
+   * step with lProDiMo (inside lxJ_abs; one column per wavelength) */
+  int32_t lxN_abs;
 } mcb_run_params;
 
 /* ------------------------------------------------------------------------
@@ -282,6 +285,7 @@ typedef struct mcb_tallies {
   double  *stokes_map;
   double  *star_origin;        /* (n_lambda)           output.f90:37 */
   double  *disk_origin;        /* (n_lambda, n_cells)  output.f90:36 */
+  double  *xN_abs;             /* (n_cells) in the thermal step, (n_cells, n_lambda) otherwise; radiation_field.f90:23 */
 } mcb_tallies;
 
 /* ---- life cycle -------------------------------------------------------- */

@@ -127,7 +127,7 @@ class mcb_run_params(C.Structure):
         ("lonly_capt_interet", C.c_int32), ("capt_inf", C.c_int32), ("lorigine", C.c_int32), ("capt_interet", C.c_int32),
         ("low_mem_th_emission", C.c_int32), ("lweight_emission", C.c_int32), ("lspot", C.c_int32),
         ("T_spot", C.c_float), ("surf_fraction_spot", C.c_float), ("theta_spot", C.c_float), ("phi_spot", C.c_float),
-        ("star1_T", C.c_double), ("tab_lambda", c_double_p),
+        ("star1_T", C.c_double), ("tab_lambda", c_double_p), ("lxN_abs", C.c_int32),
     ]
 
 
@@ -143,7 +143,7 @@ class mcb_tallies(C.Structure):
         ("I_spec", c_float_p), ("I_spec_star", c_float_p),
         ("stats", c_double_p),
         ("xT_ech_1grain", c_int32_p), ("xT_ech_1grain_nRE", c_int32_p), ("E_abs_nRE", c_double_p),
-        ("stokes_map", c_double_p), ("star_origin", c_double_p), ("disk_origin", c_double_p),
+        ("stokes_map", c_double_p), ("star_origin", c_double_p), ("disk_origin", c_double_p), ("xN_abs", c_double_p),
     ]
 
 
@@ -286,7 +286,7 @@ def make_run(**kw) -> Holder:
              npix_x=0, npix_y=0, zoom=1.0, map_size=0.0, cos_disk=1.0, sin_disk=0.0, l_sym_ima=0,
              lonly_capt_interet=0, capt_inf=1, lorigine=0, capt_interet=1,
              low_mem_th_emission=0, lweight_emission=0, lspot=0, T_spot=0.0, surf_fraction_spot=0.0, theta_spot=0.0,
-             phi_spot=0.0, star1_T=0.0, tab_lambda=None)
+             phi_spot=0.0, star1_T=0.0, tab_lambda=None, lxN_abs=0)
     unknown = set(kw) - set(d)
     if unknown:
         raise TypeError(f"unknown run parameter(s): {sorted(unknown)}")
@@ -307,7 +307,7 @@ class Tallies:
     """Caller-allocated tally arrays (shapes of the reference minus the nb_proc dim)."""
 
     def __init__(self, n_cells, n_lambda, N_thet=10, N_phi=1, xJ=False, n_xI=0, n_Ispec=0, n_nLTE=0, n_nRE=0,
-                 map_shape=None, origin=False):
+                 map_shape=None, origin=False, n_xN=0):
         self.xKJ_abs = np.zeros(n_cells, np.float64)
         self.xJ_abs = np.zeros((n_cells, n_lambda), np.float64, order="F") if xJ else None
         self.xT_ech = np.zeros(n_cells, np.int32)
@@ -326,6 +326,7 @@ class Tallies:
         self.stokes_map = np.zeros(map_shape, np.float64, order="F") if map_shape else None
         self.star_origin = np.zeros(n_lambda, np.float64) if origin else None
         self.disk_origin = np.zeros((n_lambda, n_cells), np.float64, order="F") if origin else None
+        self.xN_abs = np.zeros((n_cells, n_xN), np.float64, order="F") if n_xN else None
         t = mcb_tallies()
         for name in ("xKJ_abs", "xJ_abs", "n_phot_envoyes", "sed", "sed_q", "sed_u", "sed_v", "n_phot_sed",
                      "sed_star", "sed_star_scat", "sed_disk", "sed_disk_scat", "stats"):
@@ -337,6 +338,7 @@ class Tallies:
         t.stokes_map = ptr(self.stokes_map, np.float64)
         t.star_origin = ptr(self.star_origin, np.float64)
         t.disk_origin = ptr(self.disk_origin, np.float64)
+        t.xN_abs = ptr(self.xN_abs, np.float64)
         t.xI_scatt = ptr(self.xI_scatt, np.float32)
         t.I_spec = ptr(self.I_spec, np.float32)
         t.I_spec_star = ptr(self.I_spec_star, np.float32)
@@ -362,4 +364,6 @@ def map_tally_args(r):
         kw["map_shape"] = (r.npix_x, r.npix_y, r.N_thet, r.N_phi, ntf)
     if r.lorigine:
         kw["origin"] = True
+    if r.lxN_abs and (r.letape_th or r.lxJ_abs):
+        kw["n_xN"] = 1 if r.letape_th else None      # None -> n_lambda, filled in by the caller
     return kw

@@ -32,6 +32,13 @@ EXPORTS = (
 )
 
 
+def _map_args(P, r):
+    kw = abi.map_tally_args(r)
+    if "n_xN" in kw and kw["n_xN"] is None:
+        kw["n_xN"] = P.n_lambda
+    return kw
+
+
 class McfostB200Error(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"mcfost_b200 error {code}: {msg}")
@@ -157,7 +164,7 @@ class PhotonLoop:
             ntf = (4 if r.struct.lsepar_pola else 1) + (4 if r.struct.lsepar_contrib else 0)
             n_Is = ntf * r.struct.n_theta_I * r.struct.n_phi_I * P.n_cells
         return abi.Tallies(P.n_cells, P.n_lambda, r.struct.N_thet, r.struct.N_phi, xJ=xJ, n_xI=n_xI, n_Ispec=n_Is,
-                           **abi.grain_tally_sizes(P, r.struct), **abi.map_tally_args(r.struct))
+                           **abi.grain_tally_sizes(P, r.struct), **_map_args(P, r.struct))
 
     def mc_photon_loop(self, lambda_in=1, p_lambda_in=1, n_photons2=1000, n_phot_lim=1.0e30, nnfot1_start=1,
                        laffichage=False, **flags):

@@ -491,7 +491,7 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   dr.n_packets_total = dr.count_sent ? (unsigned long long)n_local * dr.n_per_chunk : 0ull;
   dr.nb_proc_equiv = (double)r->n_ranks;
   dr.low_mem_th = (r->low_mem_th_emission && !r->lmono) ? 1 : 0;
-  dr.lweight_emission = r->lweight_emission; dr.lspot = r->lspot;
+  dr.lweight_emission = r->lweight_emission; dr.lspot = r->lspot; dr.lxN = r->lxN_abs ? 1 : 0;
   if (r->lspot) {      // dust_transfer.f90:1101-1107, evaluated once (the reference recomputes it per packet)
     const double PI_ = MCB_PI;
     dr.z_spot = (float)cos((double)(r->theta_spot / 180.0f) * PI_);
@@ -521,6 +521,11 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
     if ((rc = reserve(h, "smap", (size_t)n_map, &m.smap))) return rc;
     if ((rc = reserve(h, "origin", (size_t)n_org, &m.star_origin))) return rc;
     m.disk_origin = m.star_origin + m.n_lambda;
+    const int64_t n_xN = r->lxN_abs ? (int64_t)m.n_cells * (r->letape_th ? 1 : m.n_lambda) : 0;
+    const bool fresh_xN = (n_xN != h->n_xN) || r->reset_tallies;
+    if ((rc = reserve(h, "xN", (size_t)n_xN, &m.xN))) return rc;
+    h->n_xN = n_xN;
+    if (fresh_xN && n_xN) CK(cudaMemsetAsync(m.xN, 0, (size_t)n_xN * sizeof(double), h->stream));
     if ((rc = reserve(h, "pos0", dr.capt_full ? (size_t)h->n_sm * 4 * 1024 : 0, &m.pos0))) return rc;
     h->n_map = n_map; h->n_org = n_org;
     if (fresh && n_map) CK(cudaMemsetAsync(m.smap, 0, (size_t)n_map * sizeof(double), h->stream));
@@ -593,6 +598,7 @@ int mcfost_b200_download(mcb_handle* h, const mcb_run_params* r, mcb_tallies* ou
   for (int a = 0; a < 9; ++a) CK(get(sp[a], L.sed + a * L.n_sed, L.n_sed));
   CK(get(out->stats, L.stats, 8));
   CK(get(out->E_abs_nRE, L.E_abs_nRE, 1));
+  if (out->xN_abs && h->n_xN) CK(cudaMemcpyAsync(out->xN_abs, m.xN, (size_t)h->n_xN * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (out->stokes_map && h->n_map) CK(cudaMemcpyAsync(out->stokes_map, m.smap, (size_t)h->n_map * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (out->star_origin && h->n_org) CK(cudaMemcpyAsync(out->star_origin, m.star_origin, (size_t)m.n_lambda * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (out->disk_origin && h->n_org) CK(cudaMemcpyAsync(out->disk_origin, m.disk_origin, (size_t)m.n_lambda * m.n_cells * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

@@ -23,6 +23,7 @@ struct mcb_handle {
   mcb::GridKind gk = mcb::GK_CYL2D;
   bool has_grid = false, has_op = false, has_em = false, has_gr = false, launched = false;
   mcb_grains gr_host{};                   // which optional grain tables were supplied (pointers are not dereferenced after upload)
+  int64_t n_xN = 0;                       // xN_abs size of the last launch
   int64_t n_map = 0, n_org = 0;           // photon-map / origin tally sizes of the last launch
   int64_t n_1g = 0, n_1g_nRE = 0;         // extents of xT_ech_1grain / xT_ech_1grain_nRE of the last launch
   std::map<std::string, void*> bufs;      // named device allocations

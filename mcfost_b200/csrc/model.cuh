@@ -113,6 +113,7 @@ struct DevModel {
   double *quv;              // Stokes Q,U,V of the packets in flight: (n_blocks, 3, NP), only with lsepar_pola
   unsigned long long *work; // [0] = next work item; [2+2c], [3+2c] = sent / received of local chunk c
   double *pos0;             // (n_blocks, 4, NP): start point x,y,z and cell index of the flight in progress (photon maps / lorigine only)
+  double *xN;               // xN_abs: (n_cells) thermal / (n_cells, n_lambda) otherwise, or null
   double *smap, *star_origin, *disk_origin;   // Monte Carlo photon maps of the call's wavelength, packet-origin tallies (output.f90:26-37)
   double *park;             // parked stragglers: (PARK_REC doubles) x capacity, see transport.cuh
   SmemLayout sm;
@@ -140,7 +141,7 @@ struct DevRun {
   unsigned long long n_packets_total;   // count_sent: n_local_chunks * n_per_chunk
   double nb_proc_equiv;                 // n_ranks: scales the local tally in Temp_LTE
   // emission extras (dust_transfer.f90:1090-1142); spot direction and opening precomputed on the host
-  int low_mem_th, lweight_emission, lspot;
+  int low_mem_th, lweight_emission, lspot, lxN;
   float x_spot, y_spot, z_spot, cos_thet_spot, T_spot;
   double star1_T;
   // capteur extras (output.f90:303-357,396-570)

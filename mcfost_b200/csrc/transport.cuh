@@ -1091,8 +1091,12 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
       if (thermal) {
         atomicAdd(m.tally + m.lay.xKJ + idx, t_kappa_abs<SM>(m, p_icell, lambda) * l_contrib * S0);
         if (r.lxJ) atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S0);
+        if (r.lxN) atomicAdd(m.xN + idx, 1.0);
       } else {
-        if (r.lxJ) atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S0);
+        if (r.lxJ) {
+          atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S0);
+          if (r.lxN) atomicAdd(m.xN + idx + (size_t)m.n_cells * (lambda - 1), 1.0);
+        }
         if (rt1_on) {
           double x1, y1, z1;
           G::exit_point(h, x0, y0, z0, u, v, w, x1, y1, z1);

@@ -47,6 +47,13 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def _map_args(P, r):
+    kw = abi.map_tally_args(r)
+    if "n_xN" in kw and kw["n_xN"] is None:
+        kw["n_xN"] = P.n_lambda
+    return kw
+
+
 class Oracle:
     """Reference-order CPU implementation of mc_photon_loop and its callees."""
 
@@ -100,7 +107,7 @@ class Oracle:
         r = abi.make_run(**params)
         P = self.P
         t = abi.Tallies(P.n_cells, P.n_lambda, r.struct.N_thet, r.struct.N_phi, xJ=xJ, n_xI=n_xI, n_Ispec=n_Ispec,
-                        **abi.grain_tally_sizes(P, r.struct), **abi.map_tally_args(r.struct))
+                        **abi.grain_tally_sizes(P, r.struct), **_map_args(P, r.struct))
         rec_a = None if rec is None else np.ascontiguousarray(rec, np.float64)
         self._check(self.lib.oracle_run(self.h, r.ref(), t.ref(), int(n_threads), _p(rec_a),
                                         0 if rec_a is None else len(rec_a)))

@@ -86,6 +86,7 @@ struct ThreadTallies {
   std::vector<int>    xT_ech_1grain, xT_ech_1grain_nRE;   // (grains of the regime, n_cells) thermal_emission.f90:50
   double E_abs_nRE = 0.0;           // omp reduction variable, dust_transfer.f90:489
   std::vector<double> stokes_map, star_origin, disk_origin;   // output.f90:26-37
+  std::vector<double> xN_abs;       // radiation_field.f90:23
   std::vector<double> n_phot_envoyes;
   std::vector<double> sed[9];       // sed, q, u, v, n_phot_sed, star, star_scat, disk, disk_scat
   std::vector<float>  xI_scatt;
@@ -1107,8 +1108,12 @@ struct Oracle {
     if (r.letape_th) {
       t.xKJ_abs[icell - 1] += kappa_abs_LTE(p_icell, lambda) * l * Stokes[0];      // lRE_LTE
       if (r.lxJ_abs_step1) t.xJ_abs[(size_t)(icell - 1) + (size_t)g.n_cells * (lambda - 1)] += l * Stokes[0];
+      if (r.lxN_abs) t.xN_abs[icell - 1] += 1.0;                                    // lmcfost_lib :53 (no wavelength dependence)
     } else {
-      if (r.lxJ_abs) t.xJ_abs[(size_t)(icell - 1) + (size_t)g.n_cells * (lambda - 1)] += l * Stokes[0];
+      if (r.lxJ_abs) {
+        t.xJ_abs[(size_t)(icell - 1) + (size_t)g.n_cells * (lambda - 1)] += l * Stokes[0];
+        if (r.lxN_abs) t.xN_abs[(size_t)(icell - 1) + (size_t)g.n_cells * (lambda - 1)] += 1.0;      // lProDiMo :60
+      }
       if (r.lscatt_ray_tracing1) {
         double xm = 0.5 * (x0 + x1), ym = 0.5 * (y0 + y1), zm = 0.5 * (z0 + z1);
         int phi_k, psup;
@@ -1734,6 +1739,7 @@ struct Oracle {
         t.xT_ech_1grain_nRE.assign(has_gr && r.lnRE ? (size_t)nk_nRE() * g.n_cells : 0, 2);       // :188
         t.E_abs_nRE = 0.0;
         t.stokes_map.assign((r.lmono0 && r.loutput_mc) ? (size_t)r.npix_x * r.npix_y * r.N_thet * r.N_phi * N_type_flux : 0, 0.0);
+        t.xN_abs.assign(r.lxN_abs ? (size_t)g.n_cells * (r.letape_th ? 1 : o.n_lambda) : 0, 0.0);
         t.star_origin.assign(r.lorigine ? o.n_lambda : 0, 0.0);
         t.disk_origin.assign(r.lorigine ? (size_t)o.n_lambda * g.n_cells : 0, 0.0);
         t.n_phot_envoyes.assign(o.n_lambda, 0.0);
@@ -1819,6 +1825,7 @@ struct Oracle {
     if (out->xT_ech_1grain_nRE) for (size_t i = 0; i < T[0].xT_ech_1grain_nRE.size(); ++i) { int m = 0; for (auto& t : T) m = std::max(m, t.xT_ech_1grain_nRE[i]); out->xT_ech_1grain_nRE[i] = m; }
     if (out->E_abs_nRE) { double s = 0; for (auto& t : T) s += t.E_abs_nRE; *out->E_abs_nRE = s; }
     if (out->stokes_map) for (size_t i = 0; i < T[0].stokes_map.size(); ++i) { double s = 0; for (auto& t : T) s += t.stokes_map[i]; out->stokes_map[i] = s; }
+    if (out->xN_abs) for (size_t i = 0; i < T[0].xN_abs.size(); ++i) { double s = 0; for (auto& t : T) s += t.xN_abs[i]; out->xN_abs[i] = s; }
     if (out->star_origin) for (size_t i = 0; i < T[0].star_origin.size(); ++i) { double s = 0; for (auto& t : T) s += t.star_origin[i]; out->star_origin[i] = s; }
     if (out->disk_origin) for (size_t i = 0; i < T[0].disk_origin.size(); ++i) { double s = 0; for (auto& t : T) s += t.disk_origin[i]; out->disk_origin[i] = s; }
     if (out->n_phot_envoyes) { for (size_t i = 0; i < nl; ++i) { double s = 0; for (auto& t : T) s += t.n_phot_envoyes[i]; out->n_phot_envoyes[i] = s; } }

@@ -67,3 +67,18 @@ def test_only_capt_interet_and_origin_tallies():
     got = full.star_origin[7] + full.disk_origin[7].sum()
     assert np.isclose(got, full.sed[7, 1].sum(), rtol=1e-12)
     assert full.star_origin[7] > 0
+
+
+def test_packet_counts_per_cell():
+    """xN_abs (radiation_field.f90:53,60): one count per crossing of a non-empty cell."""
+    P = _P()
+    O = Oracle(P)
+    t = O.run(n_threads=1, n_photons2=50, lxN_abs=1)                      # thermal, library mode: one column
+    assert t.xN_abs.shape == (P.n_cells, 1)
+    assert 0 < t.xN_abs.sum() <= t.stats[1]
+    assert np.array_equal(t.xN_abs[:, 0] > 0, t.xKJ_abs > 0)
+    s = O.run(n_threads=1, xJ=True, letape_th=0, lmono=1, lambda_in=8, p_lambda_in=8, n_photons2=10 ** 9, n_phot_lim=50.0,
+              lxJ_abs=1, lxN_abs=1)
+    assert s.xN_abs.shape == (P.n_cells, P.n_lambda)
+    assert s.xN_abs[:, 7].sum() > 0 and s.xN_abs.sum() == s.xN_abs[:, 7].sum()
+    assert np.array_equal(s.xN_abs[:, 7] > 0, s.xJ_abs[:, 7] > 0)

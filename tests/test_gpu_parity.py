@@ -467,3 +467,18 @@ def test_capt_interet_and_origin_match_oracle():
     assert np.isclose(tg.star_origin[7] + tg.disk_origin[7].sum(), tg.sed[7, 1].sum(), rtol=1e-9)
     big = to.disk_origin[7] > 0.01 * to.disk_origin[7].max()
     assert np.allclose(tg.disk_origin[7][big], to.disk_origin[7][big], rtol=0.05)
+
+
+def test_packet_counts_per_cell_match_oracle():
+    P = small_problems()["cyl2D"]()
+    kw = dict(letape_th=0, lmono=1, lxJ_abs=1, lxN_abs=1)
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(8, 8, 10 ** 9, 200.0, 1, False, **kw)
+    th = G.mc_photon_loop(1, 1, 200, 1.0e30, 1, False, lxN_abs=1)
+    G.close()
+    to = Oracle(P).run(n_threads=0, xJ=True, lambda_in=8, p_lambda_in=8, n_photons2=10 ** 9, n_phot_lim=200.0, **kw)
+    assert tg.xN_abs.shape == to.xN_abs.shape == (P.n_cells, P.n_lambda)
+    assert to.xN_abs.sum() > 0 and abs(tg.xN_abs.sum() - to.xN_abs.sum()) <= 1e-4 * to.xN_abs.sum()
+    assert np.allclose(tg.xN_abs[:, 7], to.xN_abs[:, 7], atol=3, rtol=1e-3)
+    assert th.xN_abs.shape == (P.n_cells, 1) and 0 < th.xN_abs.sum() <= th.stats[1]
+    assert np.array_equal(th.xN_abs[:, 0] > 0, th.xKJ_abs > 0)
