@@ -95,7 +95,7 @@ int mcb_launch_mc(mcb_handle* h, const DevRun& dr) {
   bool sm = h->m.sm.enabled != 0;
   // the pool (~127-151 KB) and the staged tables must fit the 227 KB of one SM
   if (sm && (size_t)h->m.sm.total_words * 8 + pool_bytes(dr.lsepar_pola != 0) > 227 * 1024) sm = false;
-  if (dr.lscattering_method1 || !dr.lonly_LTE || dr.low_mem_th) {
+  if (dr.lscattering_method1 || !dr.lonly_LTE || dr.low_mem_th || dr.capt_full || dr.lspot || dr.lweight_emission || dr.lxN) {
     switch (h->gk) {
       case GK_CYL2D: return launch_grains<GeomCyl<false, false>>(h, dr);
       case GK_CYL3D: return launch_grains<GeomCyl<true, false>>(h, dr);

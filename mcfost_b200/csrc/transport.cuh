@@ -300,6 +300,9 @@ __device__ __forceinline__ int im_reemission_LTE(const DevModel& m, const DevRun
 // Per-grain modes: scattering method 1 (dust_transfer.f90:1291-1317) and the nLTE / qRE
 // re-emission branches (dust_transfer.f90:1353-1395).  Cold code: __noinline__, global-memory tables, and
 // compiled only into the GR = true instantiation of the kernel, so the LTE / method-2 kernels are unchanged.
+// GR = true also carries the other rarely used options (complete capteur with photon maps / origin tallies, hot
+// spot, weighted emission, low-memory LTE emission, xN_abs): each of them cost steady-state throughput of the
+// default kernel when it merely sat behind a run-time flag (measured -10 % for all of them together).
 // =============================================================================
 #define MCB_AU_TO_CM_MUM2 ((149597870700.0 * 100.0) * (1.0e-4 * 1.0e-4))     /* AU_to_cm * mum_to_cm**2 */
 
@@ -859,7 +862,7 @@ __device__ __forceinline__ void start_flight(const DevModel& m, const DevRun& r,
 // =============================================================================
 // EMIT: claim a packet id, emit_packet (dust_transfer.f90:1047-1151), start the first flight
 // =============================================================================
-template <class G, bool SM, int BANK>
+template <class G, bool SM, int BANK, bool GR>
 __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
@@ -941,7 +944,7 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
       else cell = G::index(m, x, y, z);
       if (m.star_out[i_star - 1]) lintersect = G::move_to_grid(m, x, y, z, u, v, w, cell);
       S0 = m.E_paquet;
-      if (r.lspot) {      // hot spot on star 1 (dust_transfer.f90:1094-1119), tested on the position emit_packet_uniform_sphere returns
+      if (GR && r.lspot) {      // hot spot on star 1 (dust_transfer.f90:1094-1119), tested on the position emit_packet_uniform_sphere returns
         if ((double)r.x_spot * x + (double)r.y_spot * y + (double)r.z_spot * z > (double)r.cos_thet_spot * m.star[0][3]) {
           const float hc_lk = (float)(6.626070040e-34 * 299792458.0 / (__ldg(m.tab_lambda + lambda - 1) * 1e-6 * 1.38064852e-23));
           const float correct_spot = (float)((exp((double)hc_lk / r.star1_T) - 1) / (double)(expf(hc_lk / r.T_spot) - 1));
@@ -957,7 +960,7 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
       const float rw = nextf(), rp = nextf();
       random_isotropic_direction(rw, rp, u, v, w);
       S0 = m.E_paquet;
-      if (r.lweight_emission) S0 = S0 * __ldg(m.correct_E + ic - 1);      // dust_transfer.f90:1140-1142
+      if (GR && r.lweight_emission) S0 = S0 * __ldg(m.correct_E + ic - 1);      // dust_transfer.f90:1140-1142
     } else {
       flag_star = false; flag_ISM = true;
       // emit_packet_ISM (stars.f90:728-787)
@@ -984,13 +987,13 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
       P.U(U_PKLO, slot) = pk_lo; P.U(U_PKHI, slot) = pk_hi; P.U(U_EV, slot) = 1u;
       uint32_t misc = pack_misc(lambda, flag_star, false, flag_ISM, 0, my_chunk);
       start_flight(m, r, P, slot, x, y, z, u, v, w, philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u, pk_lo, pk_hi, r.call_index), misc);
-      if (r.capt_full) { POS0(0, slot) = x; POS0(1, slot) = y; POS0(2, slot) = z; POS0(3, slot) = (double)tally_index(m, cell); }
+      if (GR && r.capt_full) { POS0(0, slot) = x; POS0(1, slot) = y; POS0(2, slot) = z; POS0(3, slot) = (double)tally_index(m, cell); }
       P.U(U_MISC, slot) = misc;
       nextq = Q_FLY;
     } else {      // the packet never enters the model: straight to the detector (dust_transfer.f90:545-552)
       if (!flag_ISM) {
         const double S[4] = {S0, 0.0, 0.0, 0.0};
-        const int capt = r.capt_full ? capteur_full<BANK>(lambda, x, y, z, u, v, w, S, flag_star, false, tally_index(m, cell))
+        const int capt = (GR && r.capt_full) ? capteur_full<BANK>(lambda, x, y, z, u, v, w, S, flag_star, false, tally_index(m, cell))
                                      : capteur<BANK>(lambda, u, v, w, S, flag_star, false);
         if (!r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * my_chunk, 1ull);
         ++st.esc;
@@ -1004,7 +1007,7 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
 // =============================================================================
 // FLY: up to FLY_STEPS iterations of the physical_length loop (optical_depth.f90:77-178)
 // =============================================================================
-template <class G, bool SM, int BANK>
+template <class G, bool SM, int BANK, bool GR>
 __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
@@ -1048,7 +1051,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
       if (!misc_ism(misc)) {       // the packet leaves the model: detector (capteur, output.f90:294)
         double S[4] = {S0, 0.0, 0.0, 0.0};
         if (POLA) { S[1] = QUV(0, slot); S[2] = QUV(1, slot); S[3] = QUV(2, slot); }
-        const int capt = r.capt_full ? capteur_full<BANK>(lambda, POS0(0, slot), POS0(1, slot), POS0(2, slot), u, v, w, S, misc_star(misc), misc_scatt(misc), (int)POS0(3, slot))
+        const int capt = (GR && r.capt_full) ? capteur_full<BANK>(lambda, POS0(0, slot), POS0(1, slot), POS0(2, slot), u, v, w, S, misc_star(misc), misc_scatt(misc), (int)POS0(3, slot))
                                      : capteur<BANK>(lambda, u, v, w, S, misc_star(misc), misc_scatt(misc));
         if (!r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * misc_chunk(misc), 1ull);
       }
@@ -1091,11 +1094,11 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
       if (thermal) {
         atomicAdd(m.tally + m.lay.xKJ + idx, t_kappa_abs<SM>(m, p_icell, lambda) * l_contrib * S0);
         if (r.lxJ) atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S0);
-        if (r.lxN) atomicAdd(m.xN + idx, 1.0);
+        if (GR && r.lxN) atomicAdd(m.xN + idx, 1.0);
       } else {
         if (r.lxJ) {
           atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S0);
-          if (r.lxN) atomicAdd(m.xN + idx + (size_t)m.n_cells * (lambda - 1), 1.0);
+          if (GR && r.lxN) atomicAdd(m.xN + idx + (size_t)m.n_cells * (lambda - 1), 1.0);
         }
         if (rt1_on) {
           double x1, y1, z1;
@@ -1215,7 +1218,7 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
       misc |= (1u << 11);                                    // flag_scatt
       P.U(U_EV, slot) = ev + 1u;
       start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u1, v1, w1, bnext, misc);
-      if (r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
+      if (GR && r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
       P.U(U_MISC, slot) = misc;
       nextq = Q_FLY;
     }
@@ -1275,7 +1278,7 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
       misc = pack_misc(lambda, false, false, false, 0, misc_chunk(misc));      // flag_star = flag_scatt = flag_ISM = .false.
       P.U(U_EV, slot) = ev + 1u;
       start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u, v, w, bnext, misc);
-      if (r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
+      if (GR && r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
       P.U(U_MISC, slot) = misc;
       nextq = Q_FLY;
     }
@@ -1411,10 +1414,10 @@ mc_photon_loop_kernel(const int adopt) {
       { const unsigned mm = __ballot_sync(0xffffffffu, mine); if (lane == 0) { ss.visits[qi] += 1; ss.lanes[qi] += __popc(mm); } }
       int nextq;
       switch (qi) {
-        case Q_EMIT: nextq = adopt ? phase_adopt<SM, BANK>(slot, mine) : phase_emit<G, SM, BANK>(slot, mine, st); break;
+        case Q_EMIT: nextq = adopt ? phase_adopt<SM, BANK>(slot, mine) : phase_emit<G, SM, BANK, GR>(slot, mine, st); break;
         case Q_ABS:  nextq = phase_absorb<G, SM, BANK, GR>(slot, mine, st); break;
         case Q_SCAT: nextq = phase_scatter<G, SM, BANK, GR>(slot, mine, st); break;
-        default:     nextq = phase_fly<G, SM, BANK>(slot, mine, st); break;
+        default:     nextq = phase_fly<G, SM, BANK, GR>(slot, mine, st); break;
       }
       if (!mine) nextq = Q_NONE;
       int keep = -1, keep_n = 0, total_n = 0;
