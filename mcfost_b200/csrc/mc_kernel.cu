@@ -16,14 +16,14 @@ void mcb_forget_handle(const mcb_handle* h) {
   for (auto& e : g_main_hist) if (e == h->ev_main) e = nullptr;
 }
 
-// last user of each constant bank (GR kernels have their own copies of the symbols' users, same banks)
+// last user of each constant bank (every kernel variant of a bank reads the same __constant__ copy)
 struct BankGuard { const mcb_handle* owner = nullptr; cudaEvent_t done = nullptr; };
-static BankGuard bank_guard[2 * MCB_BANKS];
+static BankGuard bank_guard[MCB_BANKS];
 
-template <class G, bool SM, int BANK, bool GR>
+template <class G, bool SM, int BANK, int VAR>
 static int launch_bank(mcb_handle* h, const DevRun& dr) {
   const size_t smem = (SM ? (size_t)h->m.sm.total_words * 8 : 0) + pool_bytes(dr.lsepar_pola != 0);
-  auto kern = mc_photon_loop_kernel<G, SM, BANK, GR>;
+  auto kern = mc_photon_loop_kernel<G, SM, BANK, VAR>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // model + run parameters -> constant memory, ordered on the handle's stream
   if (dr.lsepar_pola) {        // Stokes Q,U,V slabs (one per block), L2-resident
@@ -44,7 +44,7 @@ static int launch_bank(mcb_handle* h, const DevRun& dr) {
   // launch of any OTHER handle that maps to the same bank (more handles than banks)
   CK(cudaStreamSynchronize(h->stream));
   {
-    BankGuard& g = bank_guard[BANK + (GR ? MCB_BANKS : 0)];
+    BankGuard& g = bank_guard[BANK];
     if (g.owner && g.owner != h && g.done) CK(cudaEventSynchronize(g.done));
     if (!g.done) CK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
   }
@@ -73,22 +73,24 @@ static int launch_bank(mcb_handle* h, const DevRun& dr) {
     CK(cudaStreamWaitEvent(h->stream, h->ev_strag, 0));      // everything later on the handle's stream is ordered after it
   }
   CK(cudaEventRecord(h->ev1, h->stream));
-  { BankGuard& g = bank_guard[BANK + (GR ? MCB_BANKS : 0)]; g.owner = h; CK(cudaEventRecord(g.done, h->stream)); }
+  { BankGuard& g = bank_guard[BANK]; g.owner = h; CK(cudaEventRecord(g.done, h->stream)); }
   return MCB_OK;
 }
 
 template <class G, bool SM>
 static int launch_one(mcb_handle* h, const DevRun& dr) {
+  // the thermal step (wavelength drawn per packet, chunks end on packets sent, no ray-tracing tallies) has its own variant
+  const bool th = dr.letape_th && !dr.lmono && dr.count_sent && !dr.rt1 && !dr.rt2;
   switch (h->bank % MCB_BANKS) {
-    case 0:  return launch_bank<G, SM, 0, false>(h, dr);
-    case 1:  return launch_bank<G, SM, 1, false>(h, dr);
-    default: return launch_bank<G, SM, 2, false>(h, dr);
+    case 0:  return th ? launch_bank<G, SM, 0, VAR_THERMAL>(h, dr) : launch_bank<G, SM, 0, VAR_GENERIC>(h, dr);
+    case 1:  return th ? launch_bank<G, SM, 1, VAR_THERMAL>(h, dr) : launch_bank<G, SM, 1, VAR_GENERIC>(h, dr);
+    default: return th ? launch_bank<G, SM, 2, VAR_THERMAL>(h, dr) : launch_bank<G, SM, 2, VAR_GENERIC>(h, dr);
   }
 }
 // per-grain modes (scattering method 1, nLTE / qRE re-emission): tables in global memory, GR = true kernels
 template <class G>
 static int launch_grains(mcb_handle* h, const DevRun& dr) {
-  return (h->bank % 2) == 0 ? launch_bank<G, false, 0, true>(h, dr) : launch_bank<G, false, 1, true>(h, dr);      // two banks are enough here (guarded)
+  return (h->bank % 2) == 0 ? launch_bank<G, false, 0, VAR_EXTRAS>(h, dr) : launch_bank<G, false, 1, VAR_EXTRAS>(h, dr);      // two banks are enough here (guarded)
 }
 
 int mcb_launch_mc(mcb_handle* h, const DevRun& dr) {

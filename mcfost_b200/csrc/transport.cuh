@@ -50,6 +50,11 @@ __constant__ DevRun c_rr[MCB_BANKS];
 #define c_m (c_mm[BANK])
 #define c_r (c_rr[BANK])
 
+// kernel variants (template parameter VAR): the default thermal step gets its own instantiation without the SED /
+// image-step code (forced scattering, received-packet chunk accounting, ray-tracing accumulators) and without the
+// rarely used options; every such branch that merely sat behind a run-time flag cost instruction-cache footprint
+// and registers of the hot loop.
+enum { VAR_THERMAL = 0, VAR_GENERIC = 1, VAR_EXTRAS = 2 };
 enum { Q_EMIT = 0, Q_ABS = 1, Q_SCAT = 2, Q_FLY = 3, NQ = 4, Q_NONE = 7 };     // queue order = claim order (longest phases first)
 enum { STAT_PACKETS = 0, STAT_STEPS, STAT_INTERACT, STAT_SCATT, STAT_ABS, STAT_KILLED, STAT_ESCAPED, STAT_BOUNCE };
 
@@ -862,8 +867,9 @@ __device__ __forceinline__ void start_flight(const DevModel& m, const DevRun& r,
 // =============================================================================
 // EMIT: claim a packet id, emit_packet (dust_transfer.f90:1047-1151), start the first flight
 // =============================================================================
-template <class G, bool SM, int BANK, bool GR>
+template <class G, bool SM, int BANK, int VAR>
 __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
+  constexpr bool GR = VAR == VAR_EXTRAS; constexpr bool TH = VAR == VAR_THERMAL; (void)GR; (void)TH;
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
   const Pool P = make_pool<SM, BANK>();
@@ -877,7 +883,7 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
   unsigned long long idx_in_chunk = 0;
   bool got = false;
   const int first_local = r.nnfot1_start + ((r.rank - ((r.nnfot1_start - 1) % r.n_ranks) + r.n_ranks) % r.n_ranks);
-  if (r.count_sent) {
+  if (TH || r.count_sent) {
     const unsigned need = __ballot_sync(0xffffffffu, valid);
     if (need) {
       const int leader = __ffs(need) - 1;
@@ -920,7 +926,7 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
     // (dust_transfer.f90:531 precedes :537); on the device packets are unordered, so the count is
     // attributed to the packet's own emission wavelength (the sum over lambda is identical).
     int lambda = r.lambda_in;
-    if (!r.lmono) lambda = select_wl_em<SM>(m, nextf());
+    if (TH || !r.lmono) lambda = select_wl_em<SM>(m, nextf());
     atomicAdd(m.tally + m.lay.n_env + (lambda - 1), 1.0);
     double x, y, z, u, v, w, S0;
     CellT cell; null_cell(cell);
@@ -995,7 +1001,7 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
         const double S[4] = {S0, 0.0, 0.0, 0.0};
         const int capt = (GR && r.capt_full) ? capteur_full<BANK>(lambda, x, y, z, u, v, w, S, flag_star, false, tally_index(m, cell))
                                      : capteur<BANK>(lambda, u, v, w, S, flag_star, false);
-        if (!r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * my_chunk, 1ull);
+        if (!TH && !r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * my_chunk, 1ull);
         ++st.esc;
       }
       nextq = Q_EMIT;
@@ -1007,16 +1013,17 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
 // =============================================================================
 // FLY: up to FLY_STEPS iterations of the physical_length loop (optical_depth.f90:77-178)
 // =============================================================================
-template <class G, bool SM, int BANK, bool GR>
+template <class G, bool SM, int BANK, int VAR>
 __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
+  constexpr bool GR = VAR == VAR_EXTRAS; constexpr bool TH = VAR == VAR_THERMAL; (void)GR; (void)TH;
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
   const Pool P = make_pool<SM, BANK>();
   using CellT = typename G::CellT;
   using Hit = typename G::Hit;
-  const bool thermal = r.letape_th != 0;
+  const bool thermal = TH || r.letape_th != 0;
   const bool variable_dust = m.p_n_cells != 1;
-  const bool rt1_on = (!thermal) && r.rt1;
+  const bool rt1_on = !TH && (!thermal) && r.rt1;
   int nextq = Q_NONE;
   double x0 = 0, y0 = 0, z0 = 0, u = 0, v = 0, w = 1, extr = 0, S0 = 0, xo = 0, yo = 0, zo = 0;
   uint32_t misc = 0;
@@ -1053,7 +1060,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
         if (POLA) { S[1] = QUV(0, slot); S[2] = QUV(1, slot); S[3] = QUV(2, slot); }
         const int capt = (GR && r.capt_full) ? capteur_full<BANK>(lambda, POS0(0, slot), POS0(1, slot), POS0(2, slot), u, v, w, S, misc_star(misc), misc_scatt(misc), (int)POS0(3, slot))
                                      : capteur<BANK>(lambda, u, v, w, S, misc_star(misc), misc_scatt(misc));
-        if (!r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * misc_chunk(misc), 1ull);
+        if (!TH && !r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * misc_chunk(misc), 1ull);
       }
       ++st.esc;
       nextq = Q_EMIT; flying = false;
@@ -1107,7 +1114,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
           if (POLA) { S[1] = QUV(0, slot); S[2] = QUV(1, slot); S[3] = QUV(2, slot); }
           deposit_rt1<BANK>(idx, p_icell, r.p_lambda_in, l_contrib, S, misc_star(misc),
                       0.5 * (x0 + x1), 0.5 * (y0 + y1), 0.5 * (z0 + z1), rt1);
-        } else if (r.rt2) {
+        } else if (!TH && r.rt2) {
           double x1, y1, z1;
           G::exit_point(h, x0, y0, z0, u, v, w, x1, y1, z1);
           double S[4] = {S0, 0.0, 0.0, 0.0};
@@ -1134,7 +1141,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
     if (interact) {
       // the flight ended with an interaction at (x0,y0,z0) in cell c0 (dust_transfer.f90:1260-1284)
       ++st.inter;
-      if (r.lmono) nextq = Q_SCAT;       // forced scattering; the dark-zone / energy tests are done in the SCATTER phase
+      if (!TH && r.lmono) nextq = Q_SCAT;       // forced scattering; the dark-zone / energy tests are done in the SCATTER phase
       else {
         const int idx = tally_index(m, c0);
         const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
@@ -1160,8 +1167,9 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
 // =============================================================================
 // SCATTER: method 2 (dust_transfer.f90:1318-1351) + start of the next flight
 // =============================================================================
-template <class G, bool SM, int BANK, bool GR>
+template <class G, bool SM, int BANK, int VAR>
 __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
+  constexpr bool GR = VAR == VAR_EXTRAS; constexpr bool TH = VAR == VAR_THERMAL; (void)GR; (void)TH;
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
   const Pool P = make_pool<SM, BANK>();
@@ -1178,7 +1186,7 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
     bool dead = false;
     double S[4] = {P.F(F_S0, slot), 0.0, 0.0, 0.0};
     if (POLA) { S[1] = QUV(0, slot); S[2] = QUV(1, slot); S[3] = QUV(2, slot); }
-    if (r.lmono) {      // forced scattering (dust_transfer.f90:1263-1278)
+    if (!TH && r.lmono) {      // forced scattering (dust_transfer.f90:1263-1278)
       if (idx >= 0 && __ldg(m.dark + idx)) dead = true;
       else {
         const float albedo = t_albedo<SM>(m, p_icell, lambda);
@@ -1214,7 +1222,7 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
         if (POLA && r.lmethod_aniso1) scatter_stokes<BANK>(lambda, itheta, rand2, p_icell, S, u, v, w, u1, v1, w1);
       }
       P.F(F_U, slot) = u1; P.F(F_V, slot) = v1; P.F(F_W, slot) = w1;
-      if (r.lmono || POLA) { P.F(F_S0, slot) = S[0]; if (POLA) { QUV(0, slot) = S[1]; QUV(1, slot) = S[2]; QUV(2, slot) = S[3]; } }
+      if ((!TH && r.lmono) || POLA) { P.F(F_S0, slot) = S[0]; if (POLA) { QUV(0, slot) = S[1]; QUV(1, slot) = S[2]; QUV(2, slot) = S[3]; } }
       misc |= (1u << 11);                                    // flag_scatt
       P.U(U_EV, slot) = ev + 1u;
       start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u1, v1, w1, bnext, misc);
@@ -1229,8 +1237,9 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
 // =============================================================================
 // ABSORB: immediate re-emission, LTE (dust_transfer.f90:1353-1402) + start of the next flight
 // =============================================================================
-template <class G, bool SM, int BANK, bool GR>
+template <class G, bool SM, int BANK, int VAR>
 __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
+  constexpr bool GR = VAR == VAR_EXTRAS; constexpr bool TH = VAR == VAR_THERMAL; (void)GR; (void)TH;
   const DevModel& m = c_m; const DevRun& r = c_r;
   const bool POLA = r.lsepar_pola != 0;
   const Pool P = make_pool<SM, BANK>();
@@ -1336,7 +1345,7 @@ __device__ __forceinline__ void drain_probe(unsigned long long* work, int npl, u
 // =============================================================================
 // The persistent photon-loop kernel: rounds of (claim a single-phase chunk -> run the phase -> regroup)
 // =============================================================================
-template <class G, bool SM, int BANK, bool GR>
+template <class G, bool SM, int BANK, int VAR>
 __global__ void __launch_bounds__(MC_BLOCK, 1)
 mc_photon_loop_kernel(const int adopt) {
   const DevModel& m = c_m; const DevRun& r = c_r;
@@ -1414,10 +1423,10 @@ mc_photon_loop_kernel(const int adopt) {
       { const unsigned mm = __ballot_sync(0xffffffffu, mine); if (lane == 0) { ss.visits[qi] += 1; ss.lanes[qi] += __popc(mm); } }
       int nextq;
       switch (qi) {
-        case Q_EMIT: nextq = adopt ? phase_adopt<SM, BANK>(slot, mine) : phase_emit<G, SM, BANK, GR>(slot, mine, st); break;
-        case Q_ABS:  nextq = phase_absorb<G, SM, BANK, GR>(slot, mine, st); break;
-        case Q_SCAT: nextq = phase_scatter<G, SM, BANK, GR>(slot, mine, st); break;
-        default:     nextq = phase_fly<G, SM, BANK, GR>(slot, mine, st); break;
+        case Q_EMIT: nextq = adopt ? phase_adopt<SM, BANK>(slot, mine) : phase_emit<G, SM, BANK, VAR>(slot, mine, st); break;
+        case Q_ABS:  nextq = phase_absorb<G, SM, BANK, VAR>(slot, mine, st); break;
+        case Q_SCAT: nextq = phase_scatter<G, SM, BANK, VAR>(slot, mine, st); break;
+        default:     nextq = phase_fly<G, SM, BANK, VAR>(slot, mine, st); break;
       }
       if (!mine) nextq = Q_NONE;
       int keep = -1, keep_n = 0, total_n = 0;
