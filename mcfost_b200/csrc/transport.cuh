@@ -1022,7 +1022,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
   using CellT = typename G::CellT;
   using Hit = typename G::Hit;
   const bool thermal = TH || r.letape_th != 0;
-  const bool variable_dust = m.p_n_cells != 1;
+  const bool variable_dust = !SM && m.p_n_cells != 1;      // staged tables imply p_n_cells == 1
   const bool rt1_on = !TH && (!thermal) && r.rt1;
   int nextq = Q_NONE;
   double x0 = 0, y0 = 0, z0 = 0, u = 0, v = 0, w = 1, extr = 0, S0 = 0, xo = 0, yo = 0, zo = 0;
@@ -1177,7 +1177,7 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
   const unsigned lane = threadIdx.x & 31;
   int nextq = Q_NONE;
   if (valid) {
-    const bool variable_dust = m.p_n_cells != 1;
+    const bool variable_dust = !SM && m.p_n_cells != 1;      // staged tables imply p_n_cells == 1
     uint32_t misc = P.U(U_MISC, slot);
     const int lambda = misc_lambda(misc);
     CellT cell; unpack_cell(P.U(U_C0A, slot), P.U(U_C0B, slot), cell);
@@ -1248,7 +1248,7 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
   int nextq = Q_NONE;
   double e_nRE = 0.0;
   if (valid) {
-    const bool variable_dust = m.p_n_cells != 1;
+    const bool variable_dust = !SM && m.p_n_cells != 1;      // staged tables imply p_n_cells == 1
     uint32_t misc = P.U(U_MISC, slot);
     CellT cell; unpack_cell(P.U(U_C0A, slot), P.U(U_C0B, slot), cell);
     const int idx = tally_index(m, cell);
