@@ -335,6 +335,14 @@ int mcfost_b200_debug_counters(mcb_handle *h, double *out);
 /* cudaStream_t of the handle, as an integer, so torch can wait on it */
 int mcfost_b200_stream(mcb_handle *h, uint64_t *stream);
 
+/* ---- post-MC temperature solves on the device-resident tallies of the last call:
+ * Temp_finale (thermal_emission.f90:870-906, Temp_LTE with id = 0) -> Tdust(n_cells), `real`;
+ * Temp_finale_nLTE (:1010-1075) -> Tdust_1grain(grain_RE_nLTE_start:grain_RE_nLTE_end, n_cells), `real`.
+ * They read xKJ_abs / xJ_abs / xT_ech* where the photon loop (and the multi-GPU all-reduce) left them, so only
+ * the temperatures cross the bus.  Host output pointers. */
+int mcfost_b200_temp_finale(mcb_handle *h, float *Tdust);
+int mcfost_b200_temp_finale_nlte(mcb_handle *h, float *Tdust_1grain);
+
 /* ---- deterministic sub-kernels (parity tests; also the building blocks of
  * define_dark_zone / integ_tau).  One ray per thread.
  * All arrays are HOST pointers of length n. ------------------------------ */

@@ -26,7 +26,7 @@ EXPORTS = (
     "mcfost_b200_upload_grid", "mcfost_b200_upload_dark_zone", "mcfost_b200_upload_opacity",
     "mcfost_b200_upload_emission", "mcfost_b200_upload_grains", "mcfost_b200_run", "mcfost_b200_launch", "mcfost_b200_sync",
     "mcfost_b200_tally_buffers", "mcfost_b200_download", "mcfost_b200_last_kernel_ms", "mcfost_b200_stream",
-    "mcfost_b200_debug_counters", "mcfost_b200_set_overlap",
+    "mcfost_b200_debug_counters", "mcfost_b200_set_overlap", "mcfost_b200_temp_finale", "mcfost_b200_temp_finale_nlte",
     "mcfost_b200_cross_cell", "mcfost_b200_index_cell", "mcfost_b200_move_to_grid",
     "mcfost_b200_optical_length_tot", "mcfost_b200_physical_length",
 )
@@ -195,6 +195,21 @@ class PhotonLoop:
         t = self._tallies(r, want_xI)
         self._check(self.lib.mcfost_b200_download(self.h, r.ref(), t.ref()))
         return t
+
+    def temp_finale(self):
+        """Tdust(n_cells) from the device-resident tallies of the last call (Temp_finale)."""
+        T = np.zeros(self.P.n_cells, np.float32)
+        self.lib.mcfost_b200_temp_finale.argtypes = [C.c_void_p, C.c_void_p]
+        self._check(self.lib.mcfost_b200_temp_finale(self.h, _p(T)))
+        return T
+
+    def temp_finale_nlte(self):
+        """Tdust_1grain(nLTE grains, n_cells) from the device-resident xJ_abs of the last call (Temp_finale_nLTE)."""
+        P = self.P
+        T = np.zeros((P.grain_RE_nLTE_end - P.grain_RE_nLTE_start + 1, P.n_cells), np.float32, order="F")
+        self.lib.mcfost_b200_temp_finale_nlte.argtypes = [C.c_void_p, C.c_void_p]
+        self._check(self.lib.mcfost_b200_temp_finale_nlte(self.h, _p(T)))
+        return T
 
     def last_kernel_ms(self):
         ms = C.c_float()

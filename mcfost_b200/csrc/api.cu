@@ -626,6 +626,95 @@ int mcfost_b200_run(mcb_handle* h, const mcb_run_params* r, mcb_tallies* out) {
 }  // extern "C"
 
 // ===========================================================================
+// post-MC temperature solves (one cell / one (grain, cell) pair per thread), reference arithmetic order
+// ===========================================================================
+__global__ void temp_finale_kernel(const __grid_constant__ DevModel m, float* Tdust) {
+  const int ic = blockIdx.x * blockDim.x + threadIdx.x;       // 0-based cell
+  if (ic >= m.n_cells) return;
+  const int pc = (m.p_n_cells != 1) ? ic : 0;
+  const double* logQ = m.logQ + (size_t)m.n_T * pc;            // log_Qcool_minus_extra_heating(:, p_icell)
+  const double Qheat = m.tally[m.lay.xKJ + ic] * m.L_packet_th / m.volume[ic];      // sum over id = the merged tally
+  float Temp = m.T_min;
+  if (!(Qheat < MCB_TINY_DP)) {
+    const double log_Qheat = log(Qheat);
+    if (!(log_Qheat < logQ[0])) {
+      int Ti = m.xT_ech[ic];
+      while ((logQ[Ti - 1] < log_Qheat) && (Ti < m.n_T)) ++Ti;
+      // the photon loop's cached index can sit above the final one (it is an atomicMax of racing warps): step back
+      while (Ti > 2 && !(logQ[Ti - 2] < log_Qheat)) --Ti;
+      const double frac = (log_Qheat - logQ[Ti - 2]) / (logQ[Ti - 1] - logQ[Ti - 2]);
+      Temp = (float)exp((double)logf(m.tab_Temp[Ti - 1]) * frac + (double)logf(m.tab_Temp[Ti - 2]) * (1.0 - frac));
+    }
+  }
+  Tdust[ic] = Temp;
+}
+
+__global__ void temp_finale_nlte_kernel(const __grid_constant__ DevModel m, float* T1g) {
+  const DevGrains& g = m.gr;
+  const int nk = g.nLTE_e - g.nLTE_s + 1;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= (int64_t)nk * m.n_cells) return;
+  const int kk = (int)(t % nk), ic = (int)(t / nk);
+  const int k = g.nLTE_s + kk;
+  const int pk = (m.p_n_cells != 1) ? k : g.zone[k - 1];
+  if (!(g.dd[(pk - 1) + (size_t)g.n_dens * ic] > MCB_TINY_DP)) { T1g[t] = 0.0f; return; }
+  double J = 0.0;
+  for (int l = 0; l < m.n_lambda; ++l) {
+    const size_t cl = (size_t)ic + (size_t)m.n_cells * l;
+    J = J + (double)g.C_abs_norm[(k - 1) + (size_t)g.n_grains_tot * l] * (m.tally[m.lay.xJ + cl] + g.J0[cl]);
+  }
+  J = J * m.L_packet_th / m.volume[ic];
+  float Temp = m.T_min;
+  if (!(J < MCB_TINY_DP)) {
+    const double log_E = log(J);
+    auto LE = [&](int Tt) { return g.logE[kk + (size_t)nk * (Tt - 1)]; };
+    if (!(log_E < LE(1))) {
+      int Ti = g.xT_1g[kk + (size_t)nk * ic];
+      while ((LE(Ti) < log_E) && (Ti < m.n_T)) ++Ti;
+      while (Ti > 2 && !(LE(Ti - 1) < log_E)) --Ti;
+      const double T2 = m.tab_Temp[Ti - 1], T1 = m.tab_Temp[Ti - 2];
+      const double frac = (log_E - LE(Ti - 1)) / (LE(Ti) - LE(Ti - 1));
+      Temp = (float)exp(log(T2) * frac + log(T1) * (1.0 - frac));
+    }
+  }
+  T1g[t] = Temp;
+}
+
+extern "C" {
+
+int mcfost_b200_temp_finale(mcb_handle* h, float* Tdust) {
+  if (!h || !Tdust) return MCB_ERR_BAD_ARG;
+  if (!h->n_tally || !h->launched) return fail(h, MCB_ERR_STATE, "temp_finale before a photon-loop call");
+  if (!h->m.logQ || !h->m.tab_Temp) return fail(h, MCB_ERR_BAD_ARG, "thermal tables missing");
+  CK(cudaSetDevice(h->device));
+  float* d = nullptr; int rc;
+  if ((rc = reserve(h, "Tdust", (size_t)h->m.n_cells, &d))) return rc;
+  temp_finale_kernel<<<(h->m.n_cells + 127) / 128, 128, 0, h->stream>>>(h->m, d);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(Tdust, d, (size_t)h->m.n_cells * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
+}
+
+int mcfost_b200_temp_finale_nlte(mcb_handle* h, float* T1g) {
+  if (!h || !T1g) return MCB_ERR_BAD_ARG;
+  if (!h->n_tally || !h->launched) return fail(h, MCB_ERR_STATE, "temp_finale_nlte before a photon-loop call");
+  if (!h->has_gr || !h->n_1g || !h->lay_xJ) return fail(h, MCB_ERR_STATE, "temp_finale_nlte needs a call with lRE_nLTE and xJ_abs");
+  const mcb_grains& gh = h->gr_host;
+  if (!gh.C_abs_norm || !gh.J0 || !gh.log_E_em_1grain || (h->m.p_n_cells == 1 && !gh.grain_zone)) return fail(h, MCB_ERR_BAD_ARG, "nLTE tables missing");
+  CK(cudaSetDevice(h->device));
+  float* d = nullptr; int rc;
+  if ((rc = reserve(h, "T1g", (size_t)h->n_1g, &d))) return rc;
+  temp_finale_nlte_kernel<<<(unsigned)((h->n_1g + 127) / 128), 128, 0, h->stream>>>(h->m, d);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(T1g, d, (size_t)h->n_1g * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
+}
+
+}  // extern "C"
+
+// ===========================================================================
 // deterministic sub-kernels: one ray per thread
 // ===========================================================================
 template <class G>

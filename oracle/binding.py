@@ -113,6 +113,19 @@ class Oracle:
                                         0 if rec_a is None else len(rec_a)))
         return t
 
+    def temp_finale(self):
+        T = np.zeros(self.P.n_cells, np.float32)
+        self.lib.oracle_temp_finale.argtypes = [C.c_void_p, C.c_void_p]
+        self._check(self.lib.oracle_temp_finale(self.h, _p(T)))
+        return T
+
+    def temp_finale_nlte(self):
+        P = self.P
+        T = np.zeros((P.grain_RE_nLTE_end - P.grain_RE_nLTE_start + 1, P.n_cells), np.float32, order="F")
+        self.lib.oracle_temp_finale_nlte.argtypes = [C.c_void_p, C.c_void_p]
+        self._check(self.lib.oracle_temp_finale_nlte(self.h, _p(T)))
+        return T
+
     # ---- deterministic sub-kernels ----------------------------------------
     @staticmethod
     def _f64(*arrs):

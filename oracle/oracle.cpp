@@ -1814,6 +1814,55 @@ struct Oracle {
     return MCB_OK;
   }
 
+  // =====================================================================
+  // thermal_emission.f90:870-906 Temp_finale (Temp_LTE with id = 0: sum / minval over the id slices)
+  // =====================================================================
+  void Temp_finale(float* Tdust) {
+    for (int icell = 1; icell <= g.n_cells; ++icell) {
+      const int p_icell = lvariable_dust() ? icell : 1;
+      double sum = 0.0; for (auto& t : T) sum += t.xKJ_abs[icell - 1];
+      const double Qheat = sum * e.L_packet_th / volume(icell);
+      float Temp;
+      if (Qheat < tiny_dp) Temp = o.T_min;
+      else {
+        const double log_Qheat = std::log(Qheat);
+        if (log_Qheat < log_Qcool(1, p_icell)) Temp = o.T_min;
+        else {
+          int Ti = T[0].xT_ech[icell - 1]; for (auto& t : T) Ti = std::min(Ti, t.xT_ech[icell - 1]);
+          while ((log_Qcool(Ti, p_icell) < log_Qheat) && (Ti < o.n_T)) Ti = Ti + 1;
+          const double frac = (log_Qheat - log_Qcool(Ti - 1, p_icell)) / (log_Qcool(Ti, p_icell) - log_Qcool(Ti - 1, p_icell));
+          Temp = (float)std::exp((double)std::log(tab_Temp(Ti)) * frac + (double)std::log(tab_Temp(Ti - 1)) * (1.0 - frac));
+        }
+      }
+      Tdust[icell - 1] = Temp;
+    }
+  }
+  // =====================================================================
+  // thermal_emission.f90:1010-1075 Temp_finale_nLTE
+  // =====================================================================
+  void Temp_finale_nLTE(float* T1g) {
+    const int nk = nk_nLTE();
+    for (int icell = 1; icell <= g.n_cells; ++icell)
+      for (int k = gr.grain_RE_nLTE_start; k <= gr.grain_RE_nLTE_end; ++k) {
+        const int p_k = lvariable_dust() ? k : gr.grain_zone[k - 1];
+        float& out = T1g[(size_t)(k - gr.grain_RE_nLTE_start) + (size_t)nk * (icell - 1)];
+        if (!(dust_density_o_n_grains(p_k, icell) > tiny_dp)) { out = 0.0f; continue; }
+        double J = 0.0;
+        for (int l = 1; l <= o.n_lambda; ++l) J = J + gr.C_abs_norm[gl_idx(k, l)] * (xJ_abs_sum(icell, l) + gr.J0[cl_idx(icell, l)]);
+        J = J * e.L_packet_th / volume(icell);
+        if (J < tiny_dp) { out = o.T_min; continue; }
+        const double log_E_abs = std::log(J);
+        if (log_E_abs < log_E_em_1grain(k, 1)) { out = o.T_min; continue; }
+        const size_t ix = (size_t)(k - gr.grain_RE_nLTE_start) + (size_t)nk * (icell - 1);
+        int T_int = T[0].xT_ech_1grain[ix]; for (auto& t : T) T_int = std::max(T_int, t.xT_ech_1grain[ix]);
+        while ((log_E_em_1grain(k, T_int) < log_E_abs) && (T_int < o.n_T)) T_int = T_int + 1;
+        const int T2 = T_int, T1 = T_int - 1;
+        const double Temp2 = tab_Temp(T2), Temp1 = tab_Temp(T1);
+        const double frac = (log_E_abs - log_E_em_1grain(k, T1)) / (log_E_em_1grain(k, T2) - log_E_em_1grain(k, T1));
+        out = (float)std::exp(std::log(Temp2) * frac + std::log(Temp1) * (1.0 - frac));
+      }
+  }
+
   // merge the id slices (the reference's readers do sum(..., dim=id))
   void collect(mcb_tallies* out) {
     if (!out) return;
@@ -1907,6 +1956,9 @@ int oracle_run(void* h, const mcb_run_params* r, mcb_tallies* out, int n_threads
   O->collect(out);
   return MCB_OK;
 }
+
+int oracle_temp_finale(void* h, float* Tdust) { Oracle* O = (Oracle*)h; if (O->T.empty()) return MCB_ERR_STATE; O->Temp_finale(Tdust); return MCB_OK; }
+int oracle_temp_finale_nlte(void* h, float* T1g) { Oracle* O = (Oracle*)h; if (O->T.empty() || O->T[0].xT_ech_1grain.empty() || O->T[0].xJ_abs.empty()) return MCB_ERR_STATE; O->Temp_finale_nLTE(T1g); return MCB_OK; }
 
 int oracle_cross_cell(void* h, int64_t n, const double* x0, const double* y0, const double* z0, const double* u, const double* v, const double* w,
                       const int32_t* icell, const int32_t* previous_cell, double* x1, double* y1, double* z1, int32_t* next_cell,

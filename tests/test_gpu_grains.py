@@ -195,3 +195,32 @@ def test_low_memory_lte_emission_statistical_parity(monkeypatch):
     m = (no + ng) > 100
     z = (ng[m] - no[m]) / np.sqrt(no[m] + ng[m])
     assert np.mean(np.abs(z) < 3.5) > 0.95 and abs(z.mean()) < 0.5
+
+
+def test_temp_finale_on_device_matches_the_tallies(monkeypatch):
+    """mcfost_b200_temp_finale / _temp_finale_nlte read the device-resident tallies of the last call: they must be
+    the reference formulas applied to exactly the tallies the call returns."""
+    monkeypatch.setenv("MCB_BLOCKS", "8")
+    P = S.multi_grain_like(n_photons_eq_th=500, tau_mid=20.0, pola=False)
+    G = api.PhotonLoop(P)
+    t = G.mc_photon_loop(1, 1, 500, 1.0e30, 1, False, **MIXED)
+    T = G.temp_finale()
+    T1 = G.temp_finale_nlte()
+    G.close()
+    assert np.allclose(T, S.temp_finale(P, t.xKJ_abs), rtol=5e-6)
+    assert T.max() > 10 * P.T_min
+    ref = _grain_temperatures(P, t, "nLTE")
+    ks = np.arange(P.grain_RE_nLTE_start, P.grain_RE_nLTE_end + 1)
+    C = P.C_abs_norm[ks - 1].astype(np.float64)
+    E = (C @ (t.xJ_abs + P.J0).T) * P.L_packet_th / P.volume[None, :]
+    ref = np.where(np.log(E) < P.log_E_em_1grain[:, :1], P.T_min, ref)
+    assert T1.shape == ref.shape and np.allclose(T1, ref, rtol=5e-6)
+    # an LTE-only handle has no per-grain state: loud error
+    P2 = S.ref41_like(n_photons_eq_th=50, dark_zone=False, n_rad=20, nz=10, n_rad_in=3, tau_mid=10.0)
+    G2 = api.PhotonLoop(P2)
+    G2.mc_photon_loop(1, 1, 50)
+    assert np.allclose(G2.temp_finale(), S.temp_finale(P2, G2.download().xKJ_abs), rtol=5e-6)
+    with pytest.raises(api.McfostB200Error):
+        G2.lib.mcfost_b200_temp_finale_nlte.argtypes = None
+        G2._check(G2.lib.mcfost_b200_temp_finale_nlte(G2.h, np.zeros(4, np.float32).ctypes.data_as(__import__("ctypes").c_void_p)))
+    G2.close()

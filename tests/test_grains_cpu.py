@@ -176,3 +176,22 @@ def test_hot_spot_and_weighted_emission_scale_the_packet_energy():
     assert np.array_equal(w.n_phot_sed, base.n_phot_sed)
     assert np.isclose(w.sed_disk.sum(), 0.25 * base.sed_disk.sum(), rtol=1e-12) and base.sed_disk.sum() > 0
     assert np.isclose(w.sed_star.sum(), base.sed_star.sum(), rtol=1e-12)
+
+
+def test_temp_finale_and_temp_finale_nlte_of_the_oracle():
+    """Temp_finale / Temp_finale_nLTE restated in the oracle against their numpy restatements on the same tallies."""
+    P = S.multi_grain_like(n_photons_eq_th=200, tau_mid=20.0, pola=False)
+    O = Oracle(P)
+    t = O.run(n_threads=0, xJ=True, n_photons2=200, **MIXED)
+    T = O.temp_finale()
+    ref = S.temp_finale(P, t.xKJ_abs)
+    assert T.shape == (P.n_cells,) and np.allclose(T, ref, rtol=2e-6)
+    T1 = O.temp_finale_nlte()
+    ks = np.arange(P.grain_RE_nLTE_start, P.grain_RE_nLTE_end + 1)
+    C = P.C_abs_norm[ks - 1].astype(np.float64)
+    E = (C @ (t.xJ_abs + P.J0).T) * P.L_packet_th / P.volume[None, :]
+    lt = np.log(P.tab_Temp.astype(np.float64))
+    for j in range(len(ks)):
+        ref1 = np.exp(np.interp(np.log(E[j]), P.log_E_em_1grain[j], lt))
+        ref1 = np.where(np.log(E[j]) < P.log_E_em_1grain[j, 0], P.T_min, ref1)
+        assert np.allclose(T1[j], ref1, rtol=2e-6), j
