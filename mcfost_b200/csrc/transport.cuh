@@ -1176,7 +1176,6 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
   const bool POLA = r.lsepar_pola != 0;
   const Pool P = make_pool<SM, BANK>();
   using CellT = typename G::CellT;
-  const unsigned lane = threadIdx.x & 31;
   int nextq = Q_NONE;
   if (valid) {
     const bool variable_dust = !SM && m.p_n_cells != 1;      // staged tables imply p_n_cells == 1
