@@ -509,6 +509,8 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   dr.capt_full = (mc_maps || r->lorigine || r->lonly_capt_interet) ? 1 : 0;
   // (the flight-start slab of capteur_full is not part of a parked packet: no hand-over in those modes)
   dr.park_enable = (h->overlap_sms > 0 && dr.count_sent && !dr.capt_full) ? 1 : 0;
+  dr.patience = 8;
+  { const char* e = getenv("MCB_PATIENCE"); if (e && atoi(e) > 0 && atoi(e) <= 4096) dr.patience = atoi(e); }      // tuning knob
   dr.park_live = 256;
   { const char* e = getenv("MCB_PARK_LIVE"); if (e && atoi(e) > 0 && atoi(e) <= 256) dr.park_live = atoi(e); }      // tuning knob
   { const char* e = getenv("MCB_DEBUG_ABORT_DRY"); dr.debug_abort_dry = (e && e[0] == '1') ? 1 : 0; }   // profiling aid only: tallies are incomplete

@@ -148,6 +148,7 @@ struct DevRun {
   int capt_full;                        // 1: lorigine / lonly_capt_interet / photon maps are on -> capteur_full
   int mc_maps, lorigine, capt_interet, lonly_capt_interet, capt_inf, npix_x, npix_y, l_sym_ima;
   double zoom, map_size, cos_disk, sin_disk;
+  int patience;                         // polls (250 ns each) a warp waits for a full 32-packet chunk before it takes a partial one
   int park_live;                        // hand over when at most this many packets of a block are in flight (<= PARK_LIVE)
   int park_enable;                      // hand stragglers over to a second small launch (count_sent modes only)
   int debug_abort_dry;                  // profiling aid (env MCB_DEBUG_ABORT_DRY): stop when the packet counter runs dry

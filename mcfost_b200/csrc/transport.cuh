@@ -1391,7 +1391,7 @@ mc_photon_loop_kernel(const int adopt) {
         if (threadIdx.x == 0 && P.DRYF()) drain_probe(c_m.work, c_r.n_photons_loop, live, probe_k);
 #endif
         if (park_ok && live <= (unsigned)r.park_live && live > 0u && P.DRYF()) { P.PARK() = 1u; break; }
-        if (best >= 0 && (best_n == 32u || live <= DRAIN_LIVE || polls >= 8)) {
+        if (best >= 0 && (best_n == 32u || live <= DRAIN_LIVE || polls >= c_r.patience)) {
           const unsigned hh = P.HEAD(best);
           const unsigned av = P.TAIL(best) - hh;
           const unsigned take = av < 32u ? av : 32u;
