@@ -106,7 +106,13 @@ def cpu_run(P, n2, threads=0, rank=0, n_ranks=1):
     from oracle import binding
     from oracle.binding import Oracle
     O = Oracle(P, fast=True)
-    nthr = threads or O.lib.oracle_max_threads()
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # turn the OpenMP baseline into a single-thread run, so the affinity mask decides, not the environment
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    nthr = threads or max(O.lib.oracle_max_threads(), avail)
     O.run(n_threads=nthr, n_photons2=max(1, n2 // 50), **FLAGS)           # warm-up (thread pool, page faults)
     t0 = time.perf_counter()
     t = O.run(n_threads=nthr, n_photons2=n2, **FLAGS)
