@@ -162,7 +162,10 @@ def test_thermal_ref41_like_statistical_parity():
 
 
 @pytest.mark.parametrize("name", ["cyl3D", "sph2D", "sph3D"])
-def test_thermal_other_grids_statistical_parity(name):
+def test_thermal_other_grids_statistical_parity(name, monkeypatch):
+    # 192k packets against 148 x 1024 in flight would put most of the run inside the concurrency window of the
+    # immediate re-emission: 8 blocks keep 4 % of the packets in flight, like a CPU run
+    monkeypatch.setenv("MCB_BLOCKS", "8")
     P = small_problems()[name]()
     to, tg = _thermal_pair(P, 1500)
     assert tg.stats[0] == to.stats[0]
@@ -303,7 +306,8 @@ def test_voronoi_deterministic_kernels_bit_exact(voronoi_pair):
     assert np.array_equal(g["lintersect"], o["lintersect"]) and np.array_equal(g["icell"], o["icell"])
 
 
-def test_voronoi_thermal_statistical_parity(voronoi_pair):
+def test_voronoi_thermal_statistical_parity(voronoi_pair, monkeypatch):
+    monkeypatch.setenv("MCB_BLOCKS", "8")        # small packet budget: see test_thermal_other_grids_statistical_parity
     P, O, G = voronoi_pair
     tg = G.mc_photon_loop(1, 1, 1500, 1.0e30, 1, False)
     to = Oracle(P, fast=True).run(n_threads=0, n_photons2=1500)
@@ -317,10 +321,11 @@ def test_voronoi_thermal_statistical_parity(voronoi_pair):
     assert np.median(np.abs(Tg[lit] - To[lit]) / To[lit]) < 0.02          # 1500 cells, 192k packets: MC noise dominated
 
 
-def test_variable_dust_per_cell_tables():
+def test_variable_dust_per_cell_tables(monkeypatch):
     """lvariable_dust = .true. (ref4.1_multi-like, LTE part): every opacity / scattering / thermal table is
     indexed by cell (p_n_cells = n_cells, kappa_factor = 1), single-wavelength scattering tables
     (p_n_lambda_pos = 1); the kernel reads them from global memory instead of the shared-memory staging."""
+    monkeypatch.setenv("MCB_BLOCKS", "8")        # small packet budget: see test_thermal_other_grids_statistical_parity
     P = S.ref41_multi_like(n_photons_eq_th=1500)
     O, G = Oracle(P), api.PhotonLoop(P)
     ic, x, y, z, u, v, w = rays_in_cells(P, 20000, seed=41)
