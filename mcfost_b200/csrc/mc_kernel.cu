@@ -11,14 +11,17 @@ using namespace mcb;
 // End-of-main-launch events of the last two calls that hand stragglers over (any handle).  A new main launch waits
 // for the one before the previous: at most ONE main launch is pending while another runs, so the SMs the
 // running one leaves free go to straggler launches (high-priority stream), not to a third call's blocks.
-static cudaEvent_t g_main_hist[2] = {nullptr, nullptr};
-void mcb_forget_handle(const mcb_handle* h) {
-  for (auto& e : g_main_hist) if (e == h->ev_main) e = nullptr;
-}
-
+// (__constant__ banks and SMs are per device, so both pieces of bookkeeping are kept per device)
+constexpr int MCB_MAX_DEV = 16;
+static cudaEvent_t g_main_hist_dev[MCB_MAX_DEV][2] = {};
 // last user of each constant bank (every kernel variant of a bank reads the same __constant__ copy)
 struct BankGuard { const mcb_handle* owner = nullptr; cudaEvent_t done = nullptr; };
-static BankGuard bank_guard[MCB_BANKS];
+static BankGuard bank_guard_dev[MCB_MAX_DEV][MCB_BANKS];
+void mcb_forget_handle(const mcb_handle* h) {      // called by finalize after the handle's streams were synchronised
+  for (auto& e : g_main_hist_dev[h->device % MCB_MAX_DEV]) if (e == h->ev_main) e = nullptr;
+  for (auto& g : bank_guard_dev[h->device % MCB_MAX_DEV]) if (g.owner == h) g.owner = nullptr;
+}
+
 
 template <class G, bool SM, int BANK, int VAR>
 static int launch_bank(mcb_handle* h, const DevRun& dr) {
@@ -44,7 +47,7 @@ static int launch_bank(mcb_handle* h, const DevRun& dr) {
   // launch of any OTHER handle that maps to the same bank (more handles than banks)
   CK(cudaStreamSynchronize(h->stream));
   {
-    BankGuard& g = bank_guard[BANK];
+    BankGuard& g = bank_guard_dev[h->device % MCB_MAX_DEV][BANK];
     if (g.owner && g.owner != h && g.done) CK(cudaEventSynchronize(g.done));
     if (!g.done) CK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
   }
@@ -58,6 +61,7 @@ static int launch_bank(mcb_handle* h, const DevRun& dr) {
   // test knob: fewer blocks = fewer packets in flight.  Immediate re-emission reads RUNNING tallies, so a
   // run whose packet budget is not >> 1024 x blocks sees them at a different stage than a 16-thread CPU run.
   { const char* e = getenv("MCB_BLOCKS"); if (e && atoi(e) > 0 && atoi(e) < blocks) blocks = atoi(e); }
+  cudaEvent_t* g_main_hist = g_main_hist_dev[h->device % MCB_MAX_DEV];
   if (n2 > 0 && g_main_hist[0] && g_main_hist[0] != h->ev_main) CK(cudaStreamWaitEvent(h->stream, g_main_hist[0], 0));
   CK(cudaEventRecord(h->ev0, h->stream));
   kern<<<blocks, MC_BLOCK, smem, h->stream>>>(0);
@@ -73,7 +77,7 @@ static int launch_bank(mcb_handle* h, const DevRun& dr) {
     CK(cudaStreamWaitEvent(h->stream, h->ev_strag, 0));      // everything later on the handle's stream is ordered after it
   }
   CK(cudaEventRecord(h->ev1, h->stream));
-  { BankGuard& g = bank_guard[BANK]; g.owner = h; CK(cudaEventRecord(g.done, h->stream)); }
+  { BankGuard& g = bank_guard_dev[h->device % MCB_MAX_DEV][BANK]; g.owner = h; CK(cudaEventRecord(g.done, h->stream)); }
   return MCB_OK;
 }
 
