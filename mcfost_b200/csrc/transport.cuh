@@ -1065,8 +1065,8 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
         const int capt = (GR && r.capt_full) ? capteur_full<BANK>(lambda, POS0(0, slot), POS0(1, slot), POS0(2, slot), u, v, w, S, misc_star(misc), misc_scatt(misc), (int)POS0(3, slot))
                                      : capteur<BANK>(lambda, u, v, w, S, misc_star(misc), misc_scatt(misc));
         if (!TH && !r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * misc_chunk(misc), 1ull);
+        ++st.esc;      // (interstellar packets leave without being detected, dust_transfer.f90:548)
       }
-      ++st.esc;
       nextq = Q_EMIT; flying = false;
       continue;
     }

@@ -439,7 +439,7 @@ def repartition_energie(P, Tdust=None):
         E_disk[l] = E.sum()
         c = np.concatenate(([0.0], np.cumsum(E)))
         prob[:, l] = c / c[nc] if c[nc] > np.finfo(np.float64).tiny else 0.0
-    E_ISM = np.zeros(nl)
+    E_ISM = np.asarray(getattr(P, "E_ISM", np.zeros(nl)), np.float64)      # interstellar radiation field (stars.f90:607-640), optional
     tot = P.E_stars + E_disk + E_ISM
     P.E_disk = E_disk
     P.frac_E_stars = P.E_stars / tot

@@ -487,3 +487,25 @@ def test_packet_counts_per_cell_match_oracle():
     assert np.allclose(tg.xN_abs[:, 7], to.xN_abs[:, 7], atol=3, rtol=1e-3)
     assert th.xN_abs.shape == (P.n_cells, 1) and 0 < th.xN_abs.sum() <= th.stats[1]
     assert np.array_equal(th.xN_abs[:, 0] > 0, th.xKJ_abs > 0)
+
+
+def test_interstellar_radiation_field_matches_oracle():
+    """emit_packet_ISM + move_to_grid from outside, packet by packet in the forced-scattering step; ISM packets are
+    never detected (flag_ISM) but feed xJ_abs."""
+    P = small_problems()["cyl2D"]()
+    P.E_ISM = 0.5 * P.E_stars
+    P.R_ISM = 1.5 * float(np.sqrt(P.Rmax2)); P.centre_ISM = (0.0, 0.0, 0.0)
+    S.repartition_energie(P)
+    kw = dict(letape_th=0, lmono=1, lxJ_abs=1)
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(8, 8, 10 ** 9, 200.0, 1, False, **kw)
+    G.close()
+    to = Oracle(P).run(n_threads=0, xJ=True, lambda_in=8, p_lambda_in=8, n_photons2=10 ** 9, n_phot_lim=200.0, **kw)
+    assert tg.stats[0] == to.stats[0] == 128 * 200
+    n_ism = to.stats[0] - to.stats[5] - to.stats[6]
+    assert n_ism > 0.2 * to.stats[0]                                        # a third of the packets come from outside
+    assert abs(tg.stats[6] - to.stats[6]) <= 3 and abs(tg.stats[5] - to.stats[5]) <= 3
+    assert abs(tg.stats[1] - to.stats[1]) <= 2e-4 * to.stats[1]
+    assert np.allclose(tg.n_phot_sed, to.n_phot_sed, atol=3)
+    assert np.allclose(tg.sed.sum(axis=0), to.sed.sum(axis=0), rtol=2e-3)
+    assert np.isclose(tg.xJ_abs.sum(), to.xJ_abs.sum(), rtol=1e-3)

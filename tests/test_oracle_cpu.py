@@ -279,3 +279,24 @@ def test_voronoi_mesh_and_walk():
     t = O.run(n_threads=2, n_photons2=20)
     assert t.stats[5] + t.stats[6] == t.stats[0] == 128 * 20
     assert t.sed.sum() == pytest.approx(t.stats[6])
+
+
+def test_interstellar_radiation_field_packets():
+    """emit_packet_ISM (stars.f90:728-787): packets start on a sphere of radius R_ISM around the model, fly inwards
+    with a cosine law, enter through move_to_grid, heat the dust, and are never detected (flag_ISM)."""
+    P = small_problems()["cyl2D"]()
+    P.E_ISM = 0.5 * P.E_stars                      # a third of the energy comes from outside
+    P.R_ISM = 1.5 * float(np.sqrt(P.Rmax2)); P.centre_ISM = (0.0, 0.0, 0.0)
+    S.repartition_energie(P)
+    assert np.allclose(P.frac_E_disk[7] - 0.0, P.frac_E_stars[7]) and P.frac_E_stars[7] == pytest.approx(2.0 / 3.0)
+    O = Oracle(P)
+    t = O.run(n_threads=1, n_photons2=200)
+    n = t.stats[0]
+    n_ism = n - t.stats[5] - t.stats[6]            # alive at exit but not detected
+    assert 0.15 * n < n_ism < 0.34 * n             # 1/3 of the packets start as ISM; those absorbed on the way are re-emitted as disk packets
+    assert t.sed.sum() == pytest.approx(t.stats[6])
+    base = small_problems()["cyl2D"]()
+    t0 = Oracle(base).run(n_threads=1, n_photons2=200)
+    # the outer disk is heated from outside: more absorbed energy per stellar packet than without the ISM field
+    outer = base.r_grid > 0.5 * base.r_grid.max()
+    assert t.xKJ_abs[outer].sum() / t.stats[6] > 1.2 * t0.xKJ_abs[outer].sum() / t0.stats[6]
