@@ -98,6 +98,11 @@ typedef struct mcb_grid {
   const double  *star_xyzr;        /* (4, n_stars): x,y,z,r  [AU] */
   const int32_t *star_icell;       /* (n_stars) star(:)%icell */
   const int32_t *star_out_model;   /* (n_stars) star(:)%out_model */
+
+  /* wall tables read only by distance_to_closest_wall_* (modified random walk); may be NULL when lMRW is
+   * never requested.  cylindrical_grid.f90:30-31,498-598 */
+  const double *w_lim;             /* (0:nz)  sin(theta_lim)   (sph) */
+  const double *sin_phi_lim, *cos_phi_lim;   /* (n_az)        (3D)  */
 } mcb_grid;
 
 /* ------------------------------------------------------------------------
@@ -253,6 +258,22 @@ typedef struct mcb_run_params {
   /* packet counts per cell (radiation_field.f90:53,60): thermal step with lmcfost_lib (one column), SED / image
    * step with lProDiMo (inside lxJ_abs; one column per wavelength) */
   int32_t lxN_abs;
+  /* Modified random walk (MRW.f90, call site dust_transfer.f90:1222-1239 -- disabled and unfinished in the
+   * reference; built here to Min et al. 2009 / Robitaille 2010).  Thermal step with lonly_LTE
+   * only.  A packet whose last n_iteractions_in_cell > 5 flights all ended in the cell they started in
+   * (dust_transfer.f90:1242-1249) takes diffusion steps of radius d = distance_to_closest_wall while
+   * d > gamma_MRW * (local Rosseland-type mean free path). */
+  int32_t lMRW;
+  float   gamma_MRW;                  /* MRW.f90:11 (2.0); <= 0 selects 2.0 */
+  /* lProDiMo / lML form of the SED loop (dust_transfer.f90:512-516): chunks end on packets SENT even though the
+   * call is not the thermal step, and wavelengths below 0.5 micron send 10x the packets.  The caller passes the
+   * resulting per-chunk count in n_photons2 exactly as the Fortran computes it; this flag only selects the
+   * termination rule. */
+  int32_t lcount_sent;
+  /* Packets in flight are capped at max(one warp per SM, max_inflight_fraction * packets sent so far) so that
+   * immediate re-emission sees running tallies the way a host run with a few threads does.  <= 0 selects the
+   * default (1/32). */
+  float   max_inflight_fraction;
 } mcb_run_params;
 
 /* ------------------------------------------------------------------------
@@ -273,8 +294,9 @@ typedef struct mcb_tallies {
   float   *I_spec;           /* (N_type_flux, n_theta_I, n_phi_I, n_cells)   dust_ray_tracing.f90:44 */
   float   *I_spec_star;      /* (n_cells)                                    dust_ray_tracing.f90:45 */
   /* diagnostics (not in the reference): */
-  double  *stats;            /* [8]: packets, cell-steps, interactions, scatterings,
-                                absorptions, killed, escaped, dark-zone bounces */
+  double  *stats;            /* [12]: packets, cell-steps, interactions, scatterings,
+                                absorptions, killed, escaped, dark-zone bounces,
+                                MRW walks, MRW steps, 2 spare */
   /* nLTE / qRE (thermal_emission.f90:49,60): in/out like xT_ech when reset_tallies = 0 */
   int32_t *xT_ech_1grain;      /* (grain_RE_nLTE_start:grain_RE_nLTE_end, n_cells) */
   int32_t *xT_ech_1grain_nRE;  /* (grain_nRE_start:grain_nRE_end, n_cells) */
@@ -375,6 +397,16 @@ int mcfost_b200_physical_length(mcb_handle *h, int64_t n, int32_t lambda,
         double *x, double *y, double *z, double *u, double *v, double *w,
         int32_t *icell, const float *tau, float *ltot,
         int32_t *flag_sortie, int32_t *lpacket_alive);
+
+/* distance_to_closest_wall (grid.f90 procedure pointer -> cylindrical_grid.f90:1179-1226,
+ * spherical_grid.f90:451-499, Voronoi.f90:996-1061): radius of the largest sphere around (x,y,z)
+ * that stays inside cell icell; the modified random walk steps by it. */
+int mcfost_b200_distance_to_closest_wall(mcb_handle *h, int64_t n, const int32_t *icell,
+        const double *x, const double *y, const double *z, double *s);
+/* Mean opacities of the modified random walk per temperature index (compute_Planck_opacities,
+ * diffusion.f90:631-693, restated for the running re-emission spectrum kdB_dT_CDF):
+ * A, B, C are host arrays (n_T, p_n_cells).  Built on the device at the first lMRW call or here. */
+int mcfost_b200_mrw_tables(mcb_handle *h, double *A, double *B, double *C);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,7 @@ class mcb_grid(C.Structure):
         ("cutting_distance_o_h", C.c_double),
         ("n_stars", C.c_int32),
         ("star_xyzr", c_double_p), ("star_icell", c_int32_p), ("star_out_model", c_int32_p),
+        ("w_lim", c_double_p), ("sin_phi_lim", c_double_p), ("cos_phi_lim", c_double_p),
     ]
 
 
@@ -128,6 +129,7 @@ class mcb_run_params(C.Structure):
         ("low_mem_th_emission", C.c_int32), ("lweight_emission", C.c_int32), ("lspot", C.c_int32),
         ("T_spot", C.c_float), ("surf_fraction_spot", C.c_float), ("theta_spot", C.c_float), ("phi_spot", C.c_float),
         ("star1_T", C.c_double), ("tab_lambda", c_double_p), ("lxN_abs", C.c_int32),
+        ("lMRW", C.c_int32), ("gamma_MRW", C.c_float), ("lcount_sent", C.c_int32), ("max_inflight_fraction", C.c_float),
     ]
 
 
@@ -193,7 +195,7 @@ def make_grid(P) -> Holder:
     g.n_rad, g.nz, g.n_az, g.n_cells = int(P.n_rad), int(P.nz), int(P.n_az), int(P.n_cells)
     g.Rmax2, g.zmaxmax = float(P.Rmax2), float(P.zmaxmax)
     for name in ("r_lim", "r_lim_2", "r_lim_3", "z_lim", "zmax", "tan_theta_lim", "theta_lim",
-                 "tan_phi_lim", "volume", "vor_xyz", "vor_h", "star_xyzr"):
+                 "tan_phi_lim", "volume", "vor_xyz", "vor_h", "star_xyzr", "w_lim", "sin_phi_lim", "cos_phi_lim"):
         put(name, np.float64)
     for name in ("cell_map_i", "cell_map_j", "cell_map_k", "vor_first", "vor_last", "vor_was_cut",
                  "vor_is_star", "vor_is_star_neighbour", "neighbours_list", "star_icell", "star_out_model"):
@@ -286,7 +288,8 @@ def make_run(**kw) -> Holder:
              npix_x=0, npix_y=0, zoom=1.0, map_size=0.0, cos_disk=1.0, sin_disk=0.0, l_sym_ima=0,
              lonly_capt_interet=0, capt_inf=1, lorigine=0, capt_interet=1,
              low_mem_th_emission=0, lweight_emission=0, lspot=0, T_spot=0.0, surf_fraction_spot=0.0, theta_spot=0.0,
-             phi_spot=0.0, star1_T=0.0, tab_lambda=None, lxN_abs=0)
+             phi_spot=0.0, star1_T=0.0, tab_lambda=None, lxN_abs=0,
+             lMRW=0, gamma_MRW=2.0, lcount_sent=0, max_inflight_fraction=0.0)
     unknown = set(kw) - set(d)
     if unknown:
         raise TypeError(f"unknown run parameter(s): {sorted(unknown)}")
@@ -319,7 +322,7 @@ class Tallies:
         self.xI_scatt = np.zeros(n_xI, np.float32) if n_xI else None
         self.I_spec = np.zeros(n_Ispec, np.float32) if n_Ispec else None
         self.I_spec_star = np.zeros(n_cells, np.float32) if n_Ispec else None
-        self.stats = np.zeros(8, np.float64)
+        self.stats = np.zeros(12, np.float64)
         self.xT_ech_1grain = np.zeros((n_nLTE, n_cells), np.int32, order="F") if n_nLTE else None
         self.xT_ech_1grain_nRE = np.zeros((n_nRE, n_cells), np.int32, order="F") if n_nRE else None
         self.E_abs_nRE = np.zeros(1, np.float64)

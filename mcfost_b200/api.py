@@ -29,6 +29,7 @@ EXPORTS = (
     "mcfost_b200_debug_counters", "mcfost_b200_set_overlap", "mcfost_b200_temp_finale", "mcfost_b200_temp_finale_nlte",
     "mcfost_b200_cross_cell", "mcfost_b200_index_cell", "mcfost_b200_move_to_grid",
     "mcfost_b200_optical_length_tot", "mcfost_b200_physical_length",
+    "mcfost_b200_distance_to_closest_wall", "mcfost_b200_mrw_tables",
 )
 
 
@@ -291,6 +292,21 @@ class PhotonLoop:
         self._check(self.lib.mcfost_b200_physical_length(self.h, C.c_int64(n), C.c_int32(lam), _p(x), _p(y), _p(z), _p(u), _p(v), _p(w),
                                                          _p(icell), _p(tau), _p(ltot), _p(fs), _p(alive)))
         return dict(x=x, y=y, z=z, u=u, v=v, w=w, icell=icell, ltot=ltot, flag_sortie=fs, lpacket_alive=alive)
+
+    def distance_to_closest_wall(self, icell, x, y, z):
+        """distance_to_closest_wall (grid.f90 procedure pointer) for points inside real cells."""
+        x, y, z = self._f64(x, y, z)
+        icell = np.ascontiguousarray(icell, np.int32)
+        s = np.zeros(len(x))
+        self._check(self.lib.mcfost_b200_distance_to_closest_wall(self.h, C.c_int64(len(x)), _p(icell), _p(x), _p(y), _p(z), _p(s)))
+        return s
+
+    def mrw_tables(self):
+        """Mean opacities of the modified random walk, (n_T, p_n_cells) each: A, B, C (see include/mcfost_b200.h)."""
+        shp = (self.P.n_T, self.P.p_n_cells)
+        A, B, Cc = (np.zeros(shp, np.float64, order="F") for _ in range(3))
+        self._check(self.lib.mcfost_b200_mrw_tables(self.h, _p(A), _p(B), _p(Cc)))
+        return A, B, Cc
 
     def dark_zone_walker(self):
         """Step-4 ray walk of define_dark_zone (optical_depth.f90:1519-1550) on the GPU."""

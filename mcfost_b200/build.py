@@ -30,24 +30,31 @@ def stale():
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force=False, verbose=False):
-    if not (force or stale()):
+def build(force=False, verbose=False, defs=(), out=None):
+    """defs / out: development builds (e.g. defs=("MCB_DEV", "MCB_DEV_CYL2D_ONLY"), out="libdev.so": only the kernels of
+    the headline configuration, with the profiling knobs; select it with MCFOST_B200_LIB)."""
+    lib = os.path.join(LIBDIR, out) if out else LIB
+    if not (force or out or stale()):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     objs = []
     procs = []
+    tag = ("." + os.path.splitext(out)[0]) if out else ""
     for src, extra in UNITS:
-        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        obj = os.path.join(LIBDIR, src.replace(".cu", tag + ".o"))
+        cmd = ["nvcc"] + NVCC_FLAGS + extra + ["-D" + d for d in defs] + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
         procs.append((cmd, subprocess.Popen(cmd, cwd=CSRC)))
         objs.append(obj)
     for cmd, pr in procs:
         if pr.wait() != 0:
             raise subprocess.CalledProcessError(pr.returncode, cmd)
-    subprocess.run(["nvcc", "-shared", "-o", LIB] + objs, check=True, cwd=CSRC)
-    return LIB
+    subprocess.run(["nvcc", "-shared", "-o", lib] + objs, check=True, cwd=CSRC)
+    return lib
 
 
 if __name__ == "__main__":
-    build(force=True, verbose=True)
-    print(LIB)
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "dev":
+        print(build(force=True, verbose=True, defs=("MCB_DEV", "MCB_DEV_CYL2D_ONLY") + tuple(sys.argv[2:]), out="libmcfost_b200_dev.so"))
+    else:
+        print(build(force=True, verbose=True))

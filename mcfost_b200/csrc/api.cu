@@ -99,6 +99,8 @@ int mcfost_b200_upload_grid(mcb_handle* h, const mcb_grid* g) {
   DevModel& m = h->m;
   if (g->kind < MCB_GRID_CYL || g->kind > MCB_GRID_VORONOI) return fail(h, MCB_ERR_BAD_ARG, "unknown grid kind");
   if (g->n_stars > MAX_STARS) return fail(h, MCB_ERR_UNSUPPORTED, "more than 8 stars");
+  // limits of the packed packet state (transport.cuh pack_cell: zj in 16 signed bits, k in 16 bits)
+  if (g->kind != MCB_GRID_VORONOI && (g->nz > 32766 || g->n_az > 65535)) return fail(h, MCB_ERR_UNSUPPORTED, "nz > 32766 or n_az > 65535");
   m.kind = g->kind; m.l3D = g->l3D; m.n_rad = g->n_rad; m.nz = g->nz; m.n_az = g->n_az; m.n_cells = g->n_cells;
   m.nj = g->l3D ? 2 * g->nz : g->nz;
   m.Rmax2 = g->Rmax2; m.zmaxmax = g->zmaxmax;
@@ -110,6 +112,7 @@ int mcfost_b200_upload_grid(mcb_handle* h, const mcb_grid* g) {
     if (!g->r_lim_2) return fail(h, MCB_ERR_BAD_ARG, "r_lim_2 missing");
     if ((rc = put(h, "r_lim_2", g->r_lim_2, (size_t)g->n_rad + 1, &m.r_lim_2))) return rc;
     if ((rc = put(h, "r_lim_3", g->r_lim_3, (size_t)g->n_rad + 1, &m.r_lim_3))) return rc;
+    if ((rc = put(h, "r_lim", g->r_lim, (size_t)g->n_rad + 1, &m.r_lim))) return rc;      // distance_to_closest_wall_* only
     if (g->kind == MCB_GRID_CYL) {
       if (!g->z_lim || !g->zmax) return fail(h, MCB_ERR_BAD_ARG, "z_lim / zmax missing");
       if ((rc = put(h, "z_lim", g->z_lim, (size_t)g->n_rad * (g->nz + 2), &m.z_lim))) return rc;
@@ -133,10 +136,17 @@ int mcfost_b200_upload_grid(mcb_handle* h, const mcb_grid* g) {
       if (!g->tan_theta_lim || !g->theta_lim) return fail(h, MCB_ERR_BAD_ARG, "tan_theta_lim / theta_lim missing");
       if ((rc = put(h, "tan_theta_lim", g->tan_theta_lim, (size_t)g->nz + 1, &m.tan_theta_lim))) return rc;
       if ((rc = put(h, "theta_lim", g->theta_lim, (size_t)g->nz + 1, &m.theta_lim))) return rc;
+      if ((rc = put(h, "w_lim", g->w_lim, (size_t)g->nz + 1, &m.w_lim))) return rc;
+      std::vector<double> cth((size_t)g->nz + 1);
+      for (int j = 0; j <= g->nz; ++j) cth[j] = cos(g->theta_lim[j]);       // host libm, like cos_tab
+      if ((rc = put(h, "cos_theta_lim", cth.data(), cth.size(), &m.cos_theta_lim))) return rc;
+      CK(cudaStreamSynchronize(h->stream));
     }
     if (g->l3D) {
       if (!g->tan_phi_lim) return fail(h, MCB_ERR_BAD_ARG, "tan_phi_lim missing");
       if ((rc = put(h, "tan_phi_lim", g->tan_phi_lim, (size_t)g->n_az, &m.tan_phi_lim))) return rc;
+      if ((rc = put(h, "sin_phi_lim", g->sin_phi_lim, (size_t)g->n_az, &m.sin_phi_lim))) return rc;
+      if ((rc = put(h, "cos_phi_lim", g->cos_phi_lim, (size_t)g->n_az, &m.cos_phi_lim))) return rc;
     }
     // verify the closed-form numbering against the caller's cell maps
     if (g->cell_map_i && g->cell_map_j && g->cell_map_k && g->n_cells_tot > 0) {
@@ -207,6 +217,9 @@ int mcfost_b200_upload_opacity(mcb_handle* h, const mcb_opacity* o) {
   DevModel& m = h->m;
   if (o->p_n_cells != 1 && o->p_n_cells != m.n_cells) return fail(h, MCB_ERR_BAD_ARG, "p_n_cells must be 1 or n_cells");
   if (o->p_n_lambda_pos != 1 && o->p_n_lambda_pos != o->n_lambda) return fail(h, MCB_ERR_BAD_ARG, "p_n_lambda_pos must be 1 or n_lambda");
+  if (o->n_lambda < 1 || o->n_lambda > 8191) return fail(h, MCB_ERR_UNSUPPORTED, "n_lambda must be 1..8191 (13 bits of the packed packet state)");
+  if (o->n_T < 2) return fail(h, MCB_ERR_BAD_ARG, "n_T < 2");
+  h->mrw_ready = false;
   m.n_lambda = o->n_lambda; m.p_n_cells = o->p_n_cells; m.p_n_lambda_pos = o->p_n_lambda_pos; m.n_T = o->n_T;
   m.T_min = o->T_min;
   const size_t npl = (size_t)o->p_n_cells * o->n_lambda;
@@ -335,13 +348,92 @@ static void compute_smem_layout(mcb_handle* h, int /*p_lambda_in*/) {
     L.logQ = take(m.n_T);
     // kdB_dT_CDF (40 KB for ref4.1) is NOT staged: measured +3.7 % with it in global memory, because the
     // shared memory it would take is worth more as L1 for kappa_factor / volume / tally lines
-    { const char* e = getenv("MCB_KDB_SMEM"); L.kdB = (e && e[0] == '1') ? take(m.n_lambda * m.n_T) : -1; }
+    L.kdB = -1;
     L.cos_tab = take(NANG + 1); L.prob_s11 = take((NANG + 2) / 2);
     L.spec_cumul = take(m.n_lambda + 1); L.frac_star = take(m.n_lambda); L.frac_disk = take(m.n_lambda);
     L.total_words = off;
     L.enabled = (off * 8 <= 96 * 1024) && m.logQ && m.kdB && m.spec_cumul;
   }
   m.sm = L;
+}
+
+
+// ===========================================================================
+// Modified random walk: tables (MRW.f90:16-54 zeta; mean opacities, the job of compute_Planck_opacities
+// diffusion.f90:631-693, see DESIGN.md "MRW")
+// ===========================================================================
+// One thread per (temperature index, p_icell): A = Sum p/(kappa(1-a)), B = Sum p/(kappa(1-a) kappa(1-a g)),
+// C = Sum p kappa_abs_LTE/(kappa(1-a)) with p = increments of kdB_dT_CDF(:, T, p_icell).
+__global__ void mrw_means_kernel(const __grid_constant__ DevModel m, double* A, double* B, double* Cc) {
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= (int64_t)m.n_T * m.p_n_cells) return;
+  const int t = (int)(q % m.n_T), pc = (int)(q / m.n_T);
+  const double* cdf = m.kdB + (size_t)m.n_lambda * ((size_t)t + (size_t)m.n_T * pc);
+  double a_ = 0.0, b_ = 0.0, c_ = 0.0, prev = 0.0;
+  for (int l = 0; l < m.n_lambda; ++l) {
+    const double cur = cdf[l];
+    const double pl = cur - prev;
+    prev = cur;
+    const size_t pl_i = (size_t)pc + (size_t)m.p_n_cells * l;
+    const double kap = m.kappa[pl_i], alb = (double)m.albedo[pl_i];
+    const double gg = m.gfac ? (double)m.gfac[pl_i] : 0.0;
+    const double k_abs = kap * (1.0 - alb), k_tr = kap * (1.0 - alb * gg);
+    if (!(pl > 0.0) || !(k_abs > 0.0)) continue;
+    a_ = a_ + pl / k_abs;
+    b_ = b_ + pl / (k_abs * k_tr);
+    c_ = c_ + pl * m.kappa_abs[pl_i] / k_abs;
+  }
+  A[q] = a_; B[q] = b_; Cc[q] = c_;
+}
+
+static int ensure_mrw_tables(mcb_handle* h) {
+  if (h->mrw_ready) return MCB_OK;
+  DevModel& m = h->m;
+  if (!m.kdB || !m.kappa || !m.kappa_abs || !m.albedo) return fail(h, MCB_ERR_BAD_ARG, "lMRW: thermal / opacity tables missing");
+  // zeta(y) = 2 Sum_{n>=1} (-1)^(n+1) y^(n^2), y = (i-1)/(n-1) (MRW.f90:16-54), made monotone by a running maximum
+  // (beyond y ~ 0.95 the series is 1 to rounding)
+  std::vector<double> zeta((size_t)N_ZETA, 0.0);
+  for (int i = 1; i <= N_ZETA; ++i) {
+    const double y = (double)(i - 1) / (double)(N_ZETA - 1);
+    double z = 0.0;
+    if (i == N_ZETA) z = 0.5;
+    else {
+      int j = 0;
+      for (;;) {
+        j = j + 1;
+        const double term = pow(y, (double)j * (double)j);
+        if (term == 0.0) break;
+        if (j % 2 == 0) z = z - term; else z = z + term;
+      }
+    }
+    zeta[i - 1] = z * 2.0;
+  }
+  for (int i = 1; i < N_ZETA; ++i) if (zeta[i] < zeta[i - 1]) zeta[i] = zeta[i - 1];
+  int rc;
+  if ((rc = put(h, "zeta", zeta.data(), zeta.size(), &m.zeta))) return rc;
+  const size_t n = (size_t)m.n_T * m.p_n_cells;
+  double *A = nullptr, *B = nullptr, *Cc = nullptr;
+  if ((rc = reserve(h, "mrw_A", n, &A)) || (rc = reserve(h, "mrw_B", n, &B)) || (rc = reserve(h, "mrw_C", n, &Cc))) return rc;
+  mrw_means_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(m, A, B, Cc);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));          // zeta is a host vector
+  m.mrw_A = A; m.mrw_B = B; m.mrw_C = Cc;
+  h->mrw_ready = true;
+  return MCB_OK;
+}
+
+extern "C" int mcfost_b200_mrw_tables(mcb_handle* h, double* A, double* B, double* Cc) {
+  if (!h) return MCB_ERR_BAD_ARG;
+  if (!h->has_op) return fail(h, MCB_ERR_STATE, "mrw_tables before upload_opacity");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_mrw_tables(h);
+  if (rc) return rc;
+  const size_t bytes = (size_t)h->m.n_T * h->m.p_n_cells * sizeof(double);
+  if (A) CK(cudaMemcpyAsync(A, h->m.mrw_A, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (B) CK(cudaMemcpyAsync(B, h->m.mrw_B, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (Cc) CK(cudaMemcpyAsync(Cc, h->m.mrw_C, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
 }
 
 __global__ void fill_int_kernel(int* p, int64_t n, int v) {
@@ -359,7 +451,7 @@ static int setup_tallies(mcb_handle* h, const mcb_run_params* r, bool lxJ, bool 
   L.sed = L.n_env + m.n_lambda;
   L.n_sed = n_sed;
   L.stats = L.sed + 9 * (int64_t)n_sed;
-  L.E_abs_nRE = L.stats + 8;
+  L.E_abs_nRE = L.stats + 12;
   L.total = L.E_abs_nRE + 1;
   m.lay = L;
   int rc;
@@ -451,10 +543,24 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   if (!r->lmethod_aniso1 && !m.gfac) return fail(h, MCB_ERR_BAD_ARG, "tab_g_pos missing for HG scattering");
   if (r->lsepar_pola && r->lmethod_aniso1 && (!m.s12 || !m.s22 || !m.s33 || !m.s34 || !m.s44)) return fail(h, MCB_ERR_BAD_ARG, "Mueller tables missing for lsepar_pola");
   if (r->letape_th && (!m.logQ || !m.kdB || !m.spec_cumul)) return fail(h, MCB_ERR_BAD_ARG, "thermal tables missing");
+  if (r->N_thet < 1 || r->N_phi < 1 || r->capt_sup < 1 || r->capt_sup > r->N_thet) return fail(h, MCB_ERR_BAD_ARG, "N_thet, N_phi >= 1 and 1 <= capt_sup <= N_thet");
+  // the per-cell Mueller tables are read with the packet's own wavelength (scattering.f90:1333-1341): with the
+  // single-wavelength layout (p_n_lambda_pos = 1) that index only exists for lambda = 1
+  if (r->lsepar_pola && r->lmethod_aniso1 && !r->lscattering_method1 && m.p_n_lambda_pos == 1 && m.n_lambda > 1 && !r->lmono)
+    return fail(h, MCB_ERR_UNSUPPORTED, "lsepar_pola with p_n_lambda_pos = 1 needs a monochromatic call (Mueller tables hold one wavelength)");
+  if (r->lMRW) {
+    if (!r->letape_th || r->lmono || !r->lonly_LTE || r->low_mem_th_emission || r->lxJ_abs_step1 || r->lscattering_method1)
+      return fail(h, MCB_ERR_UNSUPPORTED, "lMRW: thermal step with lonly_LTE, scattering method 2 and no xJ_abs only");
+    if (h->gk != GK_VOR && !m.r_lim) return fail(h, MCB_ERR_BAD_ARG, "lMRW: r_lim missing");
+    if ((h->gk == GK_SPH2D || h->gk == GK_SPH3D) && !m.w_lim) return fail(h, MCB_ERR_BAD_ARG, "lMRW: w_lim missing");
+    if ((h->gk == GK_CYL3D || h->gk == GK_SPH3D) && (!m.sin_phi_lim || !m.cos_phi_lim)) return fail(h, MCB_ERR_BAD_ARG, "lMRW: sin_phi_lim / cos_phi_lim missing");
+    const int rcm = ensure_mrw_tables(h);
+    if (rcm) return rcm;
+  }
   const bool rt1 = (!r->letape_th) && r->lscatt_ray_tracing1;
   const int n_rt = r->RT_n_incl * r->RT_n_az;
   if (rt1) {
-    if (n_rt < 1 || n_rt > MAX_RT) return fail(h, MCB_ERR_UNSUPPORTED, "rt1 needs 1..8 observer directions");
+    if (n_rt < 1 || n_rt > MAX_RT) return fail(h, MCB_ERR_UNSUPPORTED, "rt1 needs 1..16 observer directions");
     if (!r->tab_u_rt || !r->tab_v_rt || !r->tab_w_rt || !m.s11) return fail(h, MCB_ERR_BAD_ARG, "rt1 direction / s11 tables missing");
   }
   DevRun dr;
@@ -484,7 +590,8 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   int n_local = 0;
   for (int c = r->nnfot1_start; c <= r->n_photons_loop; ++c) if (((c - 1) % r->n_ranks) == r->rank) ++n_local;
   dr.n_local_chunks = n_local;
-  dr.count_sent = (r->letape_th || r->lmono0) ? 1 : 0;
+  if (n_local > 32767 * 65536) return fail(h, MCB_ERR_UNSUPPORTED, "too many chunks");
+  dr.count_sent = (r->letape_th || r->lmono0 || r->lcount_sent) ? 1 : 0;      // dust_transfer.f90:503-518
   const double lim = ceil((double)r->n_phot_lim);
   dr.sent_lim = (lim >= 1.8e19) ? ~0ull : (lim <= 0 ? 0ull : (unsigned long long)lim);
   dr.n_per_chunk = (unsigned long long)r->n_photons2 < dr.sent_lim ? (unsigned long long)r->n_photons2 : dr.sent_lim;
@@ -508,12 +615,21 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   dr.zoom = (double)r->zoom; dr.map_size = r->map_size; dr.cos_disk = r->cos_disk; dr.sin_disk = r->sin_disk;
   dr.capt_full = (mc_maps || r->lorigine || r->lonly_capt_interet) ? 1 : 0;
   // (the flight-start slab of capteur_full is not part of a parked packet: no hand-over in those modes)
-  dr.park_enable = (h->overlap_sms > 0 && dr.count_sent && !dr.capt_full) ? 1 : 0;
+  dr.park_enable = 0;      // set by mcb_launch_mc for the kernels that hand their last packets over
   dr.patience = 8;
-  { const char* e = getenv("MCB_PATIENCE"); if (e && atoi(e) > 0 && atoi(e) <= 4096) dr.patience = atoi(e); }      // tuning knob
   dr.park_live = 256;
-  { const char* e = getenv("MCB_PARK_LIVE"); if (e && atoi(e) > 0 && atoi(e) <= 256) dr.park_live = atoi(e); }      // tuning knob
-  { const char* e = getenv("MCB_DEBUG_ABORT_DRY"); dr.debug_abort_dry = (e && e[0] == '1') ? 1 : 0; }   // profiling aid only: tallies are incomplete
+  dr.debug_abort_dry = 0;
+#ifdef MCB_DEV      // development builds only: a science library does not change its results on an environment variable
+  { const char* e = getenv("MCB_PATIENCE"); if (e && atoi(e) > 0 && atoi(e) <= 4096) dr.patience = atoi(e); }
+  { const char* e = getenv("MCB_PARK_LIVE"); if (e && atoi(e) > 0 && atoi(e) <= 256) dr.park_live = atoi(e); }
+  { const char* e = getenv("MCB_DEBUG_ABORT_DRY"); dr.debug_abort_dry = (e && e[0] == '1') ? 1 : 0; }   // profiling aid: tallies are incomplete
+#endif
+  dr.lMRW = r->lMRW ? 1 : 0;
+  dr.gamma_MRW = (r->gamma_MRW > 0.0f) ? (double)r->gamma_MRW : 2.0;
+  // concurrency window: immediate re-emission reads RUNNING tallies, so the packets in flight are kept a small
+  // fraction of the packets already sent (a host run keeps nb_proc in flight); floor = one warp per block
+  dr.inflight_floor = 32u;
+  dr.inflight_frac_per_block = ((r->max_inflight_fraction > 0.0f) ? fminf(r->max_inflight_fraction, 1.0f) : 1.0f / 16.0f);      // the fraction itself; mc_kernel.cu divides it by its block count
   int rc = setup_tallies(h, r, dr.lxJ != 0, rt1, dr.n_type_flux, dr.rt2 != 0);
   if (rc) return rc;
   {   // capteur extras: photon maps of this wavelength, origin tallies, flight-start slab
@@ -598,7 +714,7 @@ int mcfost_b200_download(mcb_handle* h, const mcb_run_params* r, mcb_tallies* ou
   CK(get(out->n_phot_envoyes, L.n_env, m.n_lambda));
   double* sp[9] = {out->sed, out->sed_q, out->sed_u, out->sed_v, out->n_phot_sed, out->sed_star, out->sed_star_scat, out->sed_disk, out->sed_disk_scat};
   for (int a = 0; a < 9; ++a) CK(get(sp[a], L.sed + a * L.n_sed, L.n_sed));
-  CK(get(out->stats, L.stats, 8));
+  CK(get(out->stats, L.stats, 12));
   CK(get(out->E_abs_nRE, L.E_abs_nRE, 1));
   if (out->xN_abs && h->n_xN) CK(cudaMemcpyAsync(out->xN_abs, m.xN, (size_t)h->n_xN * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (out->stokes_map && h->n_map) CK(cudaMemcpyAsync(out->stokes_map, m.smap, (size_t)h->n_map * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -752,6 +868,15 @@ __global__ void move_to_grid_kernel(const __grid_constant__ DevModel m, int64_t 
   lintersect[i] = ok;
   icell[i] = ok ? id_of_cell(m, c) : 0;
   if (ok) { x[i] = a; y[i] = b; z[i] = cc; }
+}
+
+// distance_to_closest_wall (grid.f90 procedure pointer)
+template <class G>
+__global__ void closest_wall_kernel(const __grid_constant__ DevModel m, int64_t n, const int* icell, const double* x, const double* y, const double* z, double* s) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  typename G::CellT c; cell_of_id(m, icell[i], c);
+  s[i] = G::closest_wall(m, c, x[i], y[i], z[i]);
 }
 
 // optical_depth.f90:248-324
@@ -918,6 +1043,29 @@ int mcfost_b200_index_cell(mcb_handle* h, int64_t n, const double* x, const doub
   DISPATCH(index_cell_kernel, h->m, n, dx, dy, dz, dic);
   CK(cudaGetLastError());
   s.out(icell, dic, n);
+  CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
+}
+
+int mcfost_b200_distance_to_closest_wall(mcb_handle* h, int64_t n, const int32_t* icell, const double* x, const double* y, const double* z, double* s_out) {
+  if (!h || n < 0) return MCB_ERR_BAD_ARG;
+  if (!h->has_grid) return fail(h, MCB_ERR_STATE, "distance_to_closest_wall before upload_grid");
+  if (n == 0) return MCB_OK;
+  const DevModel& m = h->m;
+  if (h->gk != GK_VOR && !m.r_lim) return fail(h, MCB_ERR_BAD_ARG, "r_lim missing");
+  if ((h->gk == GK_SPH2D || h->gk == GK_SPH3D) && !m.w_lim) return fail(h, MCB_ERR_BAD_ARG, "w_lim missing");
+  if ((h->gk == GK_CYL3D || h->gk == GK_SPH3D) && (!m.sin_phi_lim || !m.cos_phi_lim)) return fail(h, MCB_ERR_BAD_ARG, "sin_phi_lim / cos_phi_lim missing");
+  for (int64_t i = 0; i < n; ++i) if (icell[i] < 1 || icell[i] > m.n_cells) return fail(h, MCB_ERR_BAD_ARG, "distance_to_closest_wall: icell is not a real cell");
+  CK(cudaSetDevice(h->device));
+  Scratch s{h};
+  const int* dic = s.in(icell, n);
+  const double *dx = s.in(x, n), *dy = s.in(y, n), *dz = s.in(z, n);
+  double* ds = s.in<double>(nullptr, n);
+  if (!ds) return fail(h, MCB_ERR_CUDA, "scratch allocation failed");
+  const unsigned nb = (unsigned)((n + 127) / 128);
+  DISPATCH(closest_wall_kernel, h->m, n, dic, dx, dy, dz, ds);
+  CK(cudaGetLastError());
+  s.out(s_out, ds, n);
   CK(cudaStreamSynchronize(h->stream));
   return MCB_OK;
 }

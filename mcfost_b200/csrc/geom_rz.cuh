@@ -125,6 +125,11 @@ __device__ __forceinline__ int phi_index(const DevModel& m, double x, double y) 
   return k;
 }
 
+// sin_phi_lim(k) as a wall normal: the grid set-up stores 1.0d300 next to tan_phi_lim = 1.0d300 for the walls at
+// phi = pi/2 (mod pi) (cylindrical_grid.f90:591-594), which would take them out of distance_to_closest_wall's minimum;
+// they are the planes x = 0 (sin = 1, cos = 0)
+__device__ __forceinline__ double sin_phi_wall(const DevModel& m, int k) { const double sp = __ldg(m.sin_phi_lim + k - 1); return sp > 1.0e299 ? 1.0 : sp; }
+
 // =========================================================================
 // cylindrical
 // =========================================================================
@@ -171,6 +176,10 @@ struct GeomCyl {
   }
 
   // ---- wall-distance half of cross_cylindrical_cell (:941-1094): which wall, how far ----
+  // Written with selects instead of the reference's nested ifs: a warp's 32 packets sit in different cells and fly in
+  // different directions, so every two-sided test of the Fortran (inward / outward, up / down, above / below the
+  // midplane) diverges.  Each candidate is formed with the reference's own operations in the reference's order and the
+  // result is chosen afterwards, so the values are bit-identical to the branched form (checked against the oracle).
   static __device__ __forceinline__ HitRZ distance(const DevModel& m, DirInv d, double x0, double y0, double z0,
                                                    double u, double v, double w, Cell c, Cell /*prev*/) {
     const double correct_moins = 1.0 - MCB_GRID_PREC, correct_plus = 1.0 + MCB_GRID_PREC;
@@ -186,69 +195,60 @@ struct GeomCyl {
       s = (-b + rac) * correct_plus;
       t = MCB_HUGE_REAL; t_phi = MCB_HUGE_REAL;
     } else {
-      // 1) radial wall
-      double dotprod = u * x0 + v * y0, delta;
-      if (dotprod < 0.0) {
-        double cc = (r_2 - r_lim_2<SM>(m, ri0 - 1) * correct_moins) * d.inv_a;
-        delta = b * b - cc;
-        if (delta < 0.0) {
-          cc = (r_2 - r_lim_2<SM>(m, ri0) * correct_plus) * d.inv_a;
-          delta = fmax(b * b - cc, 0.0);
-        } else h.d_rad = -1;
-      } else {
-        double cc = (r_2 - r_lim_2<SM>(m, ri0) * correct_plus) * d.inv_a;
-        delta = fmax(b * b - cc, 0.0);
+      // 1) radial wall: inner wall if the packet moves inwards and its line reaches it, else the outer wall
+      {
+        const double dotprod = u * x0 + v * y0;
+        const double bb = b * b;
+        const double delta_in = bb - (r_2 - r_lim_2<SM>(m, ri0 - 1) * correct_moins) * d.inv_a;
+        const double delta_out = fmax(bb - (r_2 - r_lim_2<SM>(m, ri0) * correct_plus) * d.inv_a, 0.0);
+        const bool inner = (dotprod < 0.0) && !(delta_in < 0.0);
+        h.d_rad = inner ? -1 : 1;
+        const double rac = sqrt(inner ? delta_in : delta_out);
+        const double sm = (-b - rac) * correct_plus, sp = (-b + rac) * correct_plus;
+        s = (sm < 0.0) ? sp : ((sm == 0.0) ? MCB_GRID_PREC : sm);
       }
-      double rac = sqrt(delta);
-      s = (-b - rac) * correct_plus;
-      if (s < 0.0) s = (-b + rac) * correct_plus;
-      else if (s == 0.0) s = MCB_GRID_PREC;
-
       // 2) horizontal wall
-      dotprod = w * z0;
-      if (dotprod == 0.0) t = (double)1.0e10f;
-      else {
+      {
+        const double dotprod = w * z0;
         const int aj = zj0 < 0 ? -zj0 : zj0;
-        double zlim;
-        if (dotprod > 0.0) {
-          if (aj == m.nz + 1) { h.d_j = 0; zlim = copysign(1.0e10, z0); }
-          else {
-            zlim = copysign(z_lim<SM>(m, ri0, aj + 1) * correct_plus, z0);
-            h.d_j = (L3D && z0 < 0.0) ? -1 : 1;
-          }
+        const bool up = dotprod > 0.0;                     // away from the midplane
+        const bool top = aj == m.nz + 1;
+        const bool zpos = z0 > 0.0;
+        // wall row and the side of the midplane it is taken on
+        int jw, dj; bool neg;
+        if (L3D) {
+          jw = up ? aj + 1 : aj;
+          neg = up ? signbit(z0) : !zpos;
+          dj = up ? ((z0 < 0.0) ? -1 : 1) : (zpos ? ((zj0 == 1) ? -2 : -1) : ((zj0 == -1) ? 2 : 1));
         } else {
-          if (L3D) {
-            if (z0 > 0.0) { zlim = z_lim<SM>(m, ri0, aj) * correct_moins; h.d_j = (zj0 == 1) ? -2 : -1; }
-            else { zlim = -z_lim<SM>(m, ri0, aj) * correct_moins; h.d_j = (zj0 == -1) ? 2 : 1; }
-          } else {
-            if (zj0 == 1) {          // midplane mirror in 2D
-              h.d_j = 1;
-              zlim = (z0 > 0.0) ? -z_lim<SM>(m, ri0, 2) * correct_moins : z_lim<SM>(m, ri0, 2) * correct_moins;
-            } else {
-              zlim = (z0 > 0.0) ? z_lim<SM>(m, ri0, zj0) * correct_moins : -z_lim<SM>(m, ri0, zj0) * correct_moins;
-              h.d_j = -1;
-            }
-          }
+          const bool mirror = zj0 == 1;                    // 2D: the midplane reflects (:1031-1050)
+          jw = up ? aj + 1 : (mirror ? 2 : zj0);
+          neg = up ? signbit(z0) : (mirror ? zpos : !zpos);
+          dj = up ? 1 : (mirror ? 1 : -1);
         }
+        if (up && top) { dj = 0; jw = aj; }
+        const double zl = z_lim<SM>(m, ri0, jw) * (up ? correct_plus : correct_moins);
+        double zlim = neg ? -zl : zl;
+        if (up && top) zlim = copysign(1.0e10, z0);
         t = (zlim - z0) * d.inv_w;
         if (t < 0.0) t = MCB_GRID_PREC;
+        if (dotprod == 0.0) { t = (double)1.0e10f; dj = 0; }
+        h.d_j = dj;
       }
-
       // 3) azimuthal wall
       if (L3D) {
-        dotprod = x0 * v - y0 * u;
-        if (fabs(dotprod) < (double)1.0e-10f) t_phi = (double)1.0e30f;
-        else {
-          double tan_angle_lim;
-          if (dotprod > 0.0) { tan_angle_lim = tan_phi_lim<SM>(m, k0); h.d_phi = 1; }
-          else { int km = k0 - 1; if (km == 0) km = m.n_az; tan_angle_lim = tan_phi_lim<SM>(m, km); h.d_phi = -1; }
-          if (tan_angle_lim > 1.0e299) t_phi = (fabs(u) > (double)1e-6f) ? -x0 / u : (double)1.0e30f;
-          else {
-            double den = v - u * tan_angle_lim;
-            t_phi = (fabs(den) > (double)1.0e-6f) ? -(y0 - x0 * tan_angle_lim) / den : (double)1.0e30f;
-          }
-          if (t_phi < 0.0) t_phi = (double)1.0e30f;
-        }
+        const double dotprod = x0 * v - y0 * u;
+        const bool fwd = dotprod > 0.0;
+        int kw = fwd ? k0 : k0 - 1; if (kw == 0) kw = m.n_az;
+        const bool par = fabs(dotprod) < (double)1.0e-10f;
+        h.d_phi = par ? 0 : (fwd ? 1 : -1);
+        const double tan_angle_lim = tan_phi_lim<SM>(m, kw);
+        const double den = v - u * tan_angle_lim;
+        const double t_a = (fabs(u) > (double)1e-6f) ? -x0 / u : (double)1.0e30f;
+        const double t_b = (fabs(den) > (double)1.0e-6f) ? -(y0 - x0 * tan_angle_lim) / den : (double)1.0e30f;
+        t_phi = (tan_angle_lim > 1.0e299) ? t_a : t_b;
+        if (t_phi < 0.0) t_phi = (double)1.0e30f;
+        if (par) t_phi = (double)1.0e30f;
       } else t_phi = MCB_HUGE_REAL;
     }
     if ((s < t) && (s < t_phi)) { h.l = s; h.which = 0; }
@@ -303,6 +303,26 @@ struct GeomCyl {
       nxt.k = k1;
     }
     if (z1 == 0.0) z1 = L3D ? copysign(MCB_GRID_PREC, w) : MCB_GRID_PREC;
+  }
+
+  // distance_to_closest_wall_cyl (cylindrical_grid.f90:1179-1226).  The wall below azimuthal sector 1 is the upper
+  // wall of sector n_az (the reference indexes sin_phi_lim(0) there, out of bounds).
+  static __device__ double closest_wall(const DevModel& m, Cell c, double x, double y, double z) {
+    const int ri0 = c.ri, aj = c.zj < 0 ? -c.zj : c.zj, k0 = c.k;
+    const double r = sqrt(x * x + y * y);
+    const double s1 = __ldg(m.r_lim + ri0) - r;
+    const double s2 = r - __ldg(m.r_lim + ri0 - 1);
+    const double z0 = fabs(z);
+    const double s3 = z_lim<SM>(m, ri0, aj + 1) - z0;
+    const double s4 = z0 - z_lim<SM>(m, ri0, aj);
+    double s = fmin(fmin(s1, s2), fmin(s3, s4));
+    if (L3D) {
+      const int km = (k0 - 1 >= 1) ? k0 - 1 : m.n_az;
+      const double s5 = fabs(x * sin_phi_wall(m, k0) - y * __ldg(m.cos_phi_lim + k0 - 1));
+      const double s6 = fabs(x * sin_phi_wall(m, km) - y * __ldg(m.cos_phi_lim + km - 1));
+      s = fmin(s, fmin(s5, s6));
+    }
+    return s;
   }
 
   // the full cross_cylindrical_cell (deterministic kernels)
@@ -514,6 +534,30 @@ struct GeomSph {
       nxt.k = k1;
     }
     if (z1 == 0.0) z1 = MCB_GRID_PREC;
+  }
+
+  // distance_to_closest_wall_sph (spherical_grid.f90:451-499).  The reference forms the theta-wall distances with
+  // cos_phi_lim(thetaj0) (:471-472): the azimuthal table (size n_az, zero in 2D) indexed with the theta index, an
+  // out-of-bounds read in dead code.  The distance from (rcyl, |z|) to the cone of theta_lim(j) is
+  // |rcyl sin(theta_lim(j)) - |z| cos(theta_lim(j))|: cos(theta_lim) (tabulated on the host) replaces the mis-indexed table.
+  static __device__ double closest_wall(const DevModel& m, Cell c, double x, double y, double z) {
+    const int ri0 = c.ri, tj = c.zj < 0 ? -c.zj : c.zj, k0 = c.k;
+    const double r2_cyl = x * x + y * y;
+    const double rcyl = sqrt(r2_cyl);
+    const double r = sqrt(r2_cyl + z * z);
+    const double s1 = __ldg(m.r_lim + ri0) - r;
+    const double s2 = r - __ldg(m.r_lim + ri0 - 1);
+    const double z0 = fabs(z);
+    const double s3 = fabs(rcyl * __ldg(m.w_lim + tj) - z0 * __ldg(m.cos_theta_lim + tj));
+    const double s4 = fabs(rcyl * __ldg(m.w_lim + tj - 1) - z0 * __ldg(m.cos_theta_lim + tj - 1));
+    double s = fmin(fmin(s1, s2), fmin(s3, s4));
+    if (L3D) {
+      const int km = (k0 - 1 >= 1) ? k0 - 1 : m.n_az;
+      const double s5 = fabs(x * sin_phi_wall(m, k0) - y * __ldg(m.cos_phi_lim + k0 - 1));
+      const double s6 = fabs(x * sin_phi_wall(m, km) - y * __ldg(m.cos_phi_lim + km - 1));
+      s = fmin(s, fmin(s5, s6));
+    }
+    return s;
   }
 
   static __device__ __forceinline__ double cross(const DevModel& m, DirInv d, double x0, double y0, double z0,

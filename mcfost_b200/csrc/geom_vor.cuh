@@ -129,6 +129,35 @@ struct GeomVor {
     return h;
   }
 
+  // distance_to_closest_wall_Voronoi (Voronoi.f90:996-1061): fp32 plane geometry as in the crossing.  The reference
+  // divides dot(n, p - r) by dot(n, n) with the un-normalised n = r_neighbour - r_cell, i.e. returns the distance in
+  // units of |n| (dead code there); the length dot(n, p - r) / |n| is returned here.  0 for cut cells and for cells
+  // that touch a wall of the box (:1009, :1051).
+  static __device__ double closest_wall(const DevModel& m, int icell, double x, double y, double z) {
+    const unsigned flags = __ldg(m.vor_flags + icell - 1);
+    if (flags & 1u) return 0.0;
+    const float rx = (float)x, ry = (float)y, rz = (float)z;
+    double s = (double)1e30f;
+    const float4 rc = __ldg(m.vor_xyz32 + (icell - 1));
+    const int ifirst = __ldg(m.vor_first + icell - 1), ilast = __ldg(m.vor_last + icell - 1);
+    for (int i = ifirst; i <= ilast; ++i) {
+      const int id_n = __ldg(m.neigh + i - 1);
+      double s_tmp;
+      if (id_n > 0) {
+        const float4 rn = __ldg(m.vor_xyz32 + (id_n - 1));
+        const float nx = __fsub_rn(rn.x, rc.x), ny = __fsub_rn(rn.y, rc.y), nz = __fsub_rn(rn.z, rc.z);
+        const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz));
+        const double den = (double)__fsqrt_rn(n2);
+        const float px = __fmul_rn(0.5f, __fadd_rn(rn.x, rc.x)), py = __fmul_rn(0.5f, __fadd_rn(rn.y, rc.y)), pz = __fmul_rn(0.5f, __fadd_rn(rn.z, rc.z));
+        const float dot = __fadd_rn(__fadd_rn(__fmul_rn(nx, __fsub_rn(px, rx)), __fmul_rn(ny, __fsub_rn(py, ry))), __fmul_rn(nz, __fsub_rn(pz, rz)));
+        s_tmp = (double)dot / den;
+        if (s_tmp < 0.) s_tmp = MCB_HUGE_REAL;
+      } else s_tmp = 0.0;
+      if (s_tmp < s) s = s_tmp;
+    }
+    return s;
+  }
+
   static __device__ __forceinline__ void exit_point(const HitVor& h, double x, double y, double z, double u, double v, double w,
                                                     double& x1, double& y1, double& z1) {
     x1 = x + u * h.l; y1 = y + v * h.l; z1 = z + w * h.l;      // (h.l = 0 on the rounding fallback: the packet does not move)

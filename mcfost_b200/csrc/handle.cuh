@@ -33,11 +33,13 @@ struct mcb_handle {
   int lay_nsed = -1;
   int n_photons_loop_alloc = 0;
   int n_type_flux = 1;
-  int straggler_sms = 0;                  // blocks of this handle's straggler launch
+  int straggler_sms = 0;                  // (kept for the set_overlap signature)
+  int launches_last_call = 0;             // kernels of this library launched by the last mcfost_b200_launch
   int overlap_sms = 0;                    // mcfost_b200_set_overlap: SMs reserved for straggler launches (0 = off)
   std::vector<double> host_kappa_factor;  // host copies used to build kf_dark (kappa_factor | dark flag)
   std::vector<uint8_t> host_dark;
   bool kf_dark_stale = true;
+  bool mrw_ready = false;                 // zeta table + mean opacities of the modified random walk are on the device
   char err[512] = {0};
 };
 

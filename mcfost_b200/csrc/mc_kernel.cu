@@ -2,33 +2,76 @@
 // the packet loop is statistical (atomics make the summation order non-deterministic anyway),
 // so FMA contraction is allowed here, while the deterministic sub-kernels in api.cu keep
 // the reference's non-contracted arithmetic and stay bit-exact against the oracle.
+#include <cmath>
 #include <cstdlib>
+#include <mutex>
 #include "handle.cuh"
 #include "transport.cuh"
+#include "warp_engine.cuh"
 
 using namespace mcb;
 
 // End-of-main-launch events of the last two calls that hand stragglers over (any handle).  A new main launch waits
 // for the one before the previous: at most ONE main launch is pending while another runs, so the SMs the
 // running one leaves free go to straggler launches (high-priority stream), not to a third call's blocks.
-// (__constant__ banks and SMs are per device, so both pieces of bookkeeping are kept per device)
-constexpr int MCB_MAX_DEV = 16;
+// (__constant__ banks and SMs are per device, so both pieces of bookkeeping are kept per device; a mutex guards them,
+// several host threads may launch on their own handles)
+constexpr int MCB_MAX_DEV = 64;
+static std::mutex g_launch_mutex;
 static cudaEvent_t g_main_hist_dev[MCB_MAX_DEV][2] = {};
 // last user of each constant bank (every kernel variant of a bank reads the same __constant__ copy)
 struct BankGuard { const mcb_handle* owner = nullptr; cudaEvent_t done = nullptr; };
 static BankGuard bank_guard_dev[MCB_MAX_DEV][MCB_BANKS];
 void mcb_forget_handle(const mcb_handle* h) {      // called by finalize after the handle's streams were synchronised
+  std::lock_guard<std::mutex> lock(g_launch_mutex);
   for (auto& e : g_main_hist_dev[h->device % MCB_MAX_DEV]) if (e == h->ev_main) e = nullptr;
   for (auto& g : bank_guard_dev[h->device % MCB_MAX_DEV]) if (g.owner == h) g.owner = nullptr;
 }
 
+__global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
+
+// Packets the packet-per-warp kernel sends before the packet-per-lane kernel takes over (thermal step).
+// The packet-per-lane kernel keeps up to 1024 packets per SM in flight; immediate re-emission reads RUNNING tallies, so
+// it is only started once `frac` x (packets sent) covers a useful number of packets in flight per block (its own
+// scheduler then caps the packets in flight at frac x sent, see DevRun::inflight_frac_per_block), and calls whose
+// whole budget is small are run by the low-latency kernel alone.
+static unsigned long long engine_first_packets(unsigned long long n_total, int blocks, double frac) {
+  const double start_per_block = 128.0;                       // packets in flight per block at which the per-lane kernel starts
+  const unsigned long long s_a = (unsigned long long)std::ceil(start_per_block * blocks / frac);
+  if (n_total <= 4ull * s_a) return n_total;                  // small budget: latency-bound from start to end
+  return s_a;
+}
 
 template <class G, bool SM, int BANK, int VAR>
-static int launch_bank(mcb_handle* h, const DevRun& dr) {
-  const size_t smem = (SM ? (size_t)h->m.sm.total_words * 8 : 0) + pool_bytes(dr.lsepar_pola != 0);
+static int launch_bank(mcb_handle* h, DevRun dr) {
+  if (h->device < 0 || h->device >= MCB_MAX_DEV) return fail(h, MCB_ERR_UNSUPPORTED, "device index >= 64");
+  std::lock_guard<std::mutex> lock(g_launch_mutex);
+  const size_t smem_tables = SM ? (size_t)h->m.sm.total_words * 8 : 0;
+  const size_t smem = smem_tables + pool_bytes(dr.lsepar_pola != 0);
   auto kern = mc_photon_loop_kernel<G, SM, BANK, VAR>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // model + run parameters -> constant memory, ordered on the handle's stream
+  const int blocks_full = h->n_sm - h->overlap_sms;            // persistent: one block (1024 packets in flight) per SM; set_overlap leaves SMs to the tail kernels of other handles
+  // ---- which kernels run this call
+  constexpr bool TH = VAR == VAR_THERMAL;
+  const double frac = dr.inflight_frac_per_block;            // (api.cu stores the caller's fraction here; divided by the block count below)
+  unsigned long long n_engine_first = 0;                     // thermal step: packets sent by the packet-per-warp kernel
+  bool lane_kernel = true;
+  int blocks = blocks_full;
+  if (TH) {
+    n_engine_first = engine_first_packets(dr.n_packets_total, blocks_full, frac);
+    lane_kernel = n_engine_first < dr.n_packets_total;
+    dr.park_enable = 1;                                      // the last packets of the per-lane kernel are finished by the packet-per-warp kernel
+    dr.inflight_floor = 32u;
+    dr.inflight_frac_per_block = (float)(frac / blocks);
+  } else {
+    dr.inflight_frac_per_block = 0.0f;                       // no cap inside the kernel
+    if (dr.letape_th && dr.count_sent) {
+      // other thermal modes (per-grain branches): keep the packets in flight a small fraction of the budget by using fewer blocks
+      const unsigned long long want = (unsigned long long)(frac * (double)dr.n_packets_total / NP);
+      blocks = (int)std::min<unsigned long long>((unsigned long long)blocks_full, std::max<unsigned long long>(1ull, want));
+    }
+    dr.park_enable = 0;
+  }
   if (dr.lsepar_pola) {        // Stokes Q,U,V slabs (one per block), L2-resident
     void*& q = h->bufs["quv"];
     const size_t bytes = (size_t)h->n_sm * 3 * NP * sizeof(double);
@@ -43,11 +86,18 @@ static int launch_bank(mcb_handle* h, const DevRun& dr) {
     if (!pk) { CK(cudaMalloc(&pk, bytes)); h->buf_bytes["park"] = bytes; }
     h->m.park = (double*)pk;
   }
+  if (dr.lMRW) {
+    void*& c0 = h->bufs["mrw_c0"];
+    const size_t bytes = (size_t)h->n_sm * NP * sizeof(int);
+    if (c0 && h->buf_bytes["mrw_c0"] != bytes) { cudaFree(c0); c0 = nullptr; }
+    if (!c0) { CK(cudaMalloc(&c0, bytes)); h->buf_bytes["mrw_c0"] = bytes; }
+    h->m.mrw_c0 = (int*)c0;
+  }
   // the previous launch of this handle must be over before its constant bank is rewritten; so must the last
   // launch of any OTHER handle that maps to the same bank (more handles than banks)
   CK(cudaStreamSynchronize(h->stream));
   {
-    BankGuard& g = bank_guard_dev[h->device % MCB_MAX_DEV][BANK];
+    BankGuard& g = bank_guard_dev[h->device][BANK];
     if (g.owner && g.owner != h && g.done) CK(cudaEventSynchronize(g.done));
     if (!g.done) CK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
   }
@@ -55,29 +105,48 @@ static int launch_bank(mcb_handle* h, const DevRun& dr) {
   CK(cudaMemcpyToSymbolAsync(c_mm, &h->m, sizeof(DevModel), (size_t)bank * sizeof(DevModel), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyToSymbolAsync(c_rr, &dr, sizeof(DevRun), (size_t)bank * sizeof(DevRun), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));          // dr / h->m are host stack / heap values
-  int blocks = h->n_sm;                          // persistent: one 512-thread block (1024 packets in flight) per SM
-  const int n2 = dr.park_enable ? h->straggler_sms : 0;    // blocks of the straggler launch (mcfost_b200_set_overlap)
-  if (dr.park_enable) blocks -= h->overlap_sms;            // SMs the main launch leaves to straggler launches
-  // test knob: fewer blocks = fewer packets in flight.  Immediate re-emission reads RUNNING tallies, so a
-  // run whose packet budget is not >> 1024 x blocks sees them at a different stage than a 16-thread CPU run.
-  { const char* e = getenv("MCB_BLOCKS"); if (e && atoi(e) > 0 && atoi(e) < blocks) blocks = atoi(e); }
-  cudaEvent_t* g_main_hist = g_main_hist_dev[h->device % MCB_MAX_DEV];
-  if (n2 > 0 && g_main_hist[0] && g_main_hist[0] != h->ev_main) CK(cudaStreamWaitEvent(h->stream, g_main_hist[0], 0));
+  cudaEvent_t* g_main_hist = g_main_hist_dev[h->device];
+  const bool overlap = h->overlap_sms > 0 && dr.park_enable;
+  if (overlap && g_main_hist[0] && g_main_hist[0] != h->ev_main) CK(cudaStreamWaitEvent(h->stream, g_main_hist[0], 0));
   CK(cudaEventRecord(h->ev0, h->stream));
-  kern<<<blocks, MC_BLOCK, smem, h->stream>>>(0);
-  CK(cudaGetLastError());
-  if (n2 > 0) {      // the stragglers the main launch parked, on the SMs the main launches leave free.  Highest
-    // stream priority: when SMs free up, these few blocks go before the pending main blocks of other handles.
-    CK(cudaEventRecord(h->ev_main, h->stream));
-    g_main_hist[0] = g_main_hist[1]; g_main_hist[1] = h->ev_main;
-    CK(cudaStreamWaitEvent(h->stream_hi, h->ev_main, 0));
-    kern<<<n2, MC_BLOCK, smem, h->stream_hi>>>(1);
+  h->launches_last_call = 0;
+  if constexpr (TH) {
+    auto eng = mc_warp_engine_kernel<G, SM, BANK>;
+    if (smem_tables > 48 * 1024) CK(cudaFuncSetAttribute(eng, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
+    if (n_engine_first > 0) {
+      eng<<<h->n_sm, ENG_BLOCK, smem_tables, h->stream>>>(n_engine_first, 0);
+      CK(cudaGetLastError());
+      ++h->launches_last_call;
+    }
+    if (lane_kernel) {
+      set_u64_kernel<<<1, 1, 0, h->stream>>>(h->m.work, n_engine_first);      // the per-lane kernel continues the packet counter
+      kern<<<blocks, MC_BLOCK, smem, h->stream>>>(0);
+      CK(cudaGetLastError());
+      h->launches_last_call += 2;
+      // its stragglers, on the packet-per-warp kernel.  With set_overlap: highest stream priority, so that when SMs free
+      // up these blocks go before the pending main blocks of other handles.
+      cudaStream_t st2 = h->stream;
+      if (overlap) {
+        CK(cudaEventRecord(h->ev_main, h->stream));
+        g_main_hist[0] = g_main_hist[1]; g_main_hist[1] = h->ev_main;
+        CK(cudaStreamWaitEvent(h->stream_hi, h->ev_main, 0));
+        st2 = h->stream_hi;
+      }
+      eng<<<h->n_sm, ENG_BLOCK, smem_tables, st2>>>(0ull, 1);
+      CK(cudaGetLastError());
+      ++h->launches_last_call;
+      if (overlap) {
+        CK(cudaEventRecord(h->ev_strag, h->stream_hi));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_strag, 0));      // everything later on the handle's stream is ordered after it
+      }
+    }
+  } else {
+    kern<<<blocks, MC_BLOCK, smem, h->stream>>>(0);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev_strag, h->stream_hi));
-    CK(cudaStreamWaitEvent(h->stream, h->ev_strag, 0));      // everything later on the handle's stream is ordered after it
+    ++h->launches_last_call;
   }
   CK(cudaEventRecord(h->ev1, h->stream));
-  { BankGuard& g = bank_guard_dev[h->device % MCB_MAX_DEV][BANK]; g.owner = h; CK(cudaEventRecord(g.done, h->stream)); }
+  { BankGuard& g = bank_guard_dev[h->device][BANK]; g.owner = h; CK(cudaEventRecord(g.done, h->stream)); }
   return MCB_OK;
 }
 
@@ -104,18 +173,24 @@ int mcb_launch_mc(mcb_handle* h, const DevRun& dr) {
   if (dr.lscattering_method1 || !dr.lonly_LTE || dr.low_mem_th || dr.capt_full || dr.lspot || dr.lweight_emission || dr.lxN) {
     switch (h->gk) {
       case GK_CYL2D: return launch_grains<GeomCyl<false, false>>(h, dr);
+#ifndef MCB_DEV_CYL2D_ONLY
       case GK_CYL3D: return launch_grains<GeomCyl<true, false>>(h, dr);
       case GK_SPH2D: return launch_grains<GeomSph<false, false>>(h, dr);
       case GK_SPH3D: return launch_grains<GeomSph<true, false>>(h, dr);
       case GK_VOR:   return launch_grains<GeomVor>(h, dr);
+#endif
+      default: return MCB_ERR_BAD_ARG;
     }
   }
   switch (h->gk) {
-    case GK_CYL2D: return sm ? launch_one<GeomCyl<false, true>, true>(h, dr) : launch_one<GeomCyl<false, false>, false>(h, dr);
+#ifndef MCB_DEV_CYL2D_ONLY      // development builds: only the kernels of the headline configuration (fast compile)
     case GK_CYL3D: return sm ? launch_one<GeomCyl<true, true>, true>(h, dr) : launch_one<GeomCyl<true, false>, false>(h, dr);
     case GK_SPH2D: return sm ? launch_one<GeomSph<false, true>, true>(h, dr) : launch_one<GeomSph<false, false>, false>(h, dr);
     case GK_SPH3D: return sm ? launch_one<GeomSph<true, true>, true>(h, dr) : launch_one<GeomSph<true, false>, false>(h, dr);
     case GK_VOR:   return launch_one<GeomVor, false>(h, dr);
+#endif
+    case GK_CYL2D: return sm ? launch_one<GeomCyl<false, true>, true>(h, dr) : launch_one<GeomCyl<false, false>, false>(h, dr);
+    default: break;
   }
   return MCB_ERR_BAD_ARG;
 }

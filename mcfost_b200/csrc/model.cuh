@@ -10,7 +10,8 @@ namespace mcb {
 constexpr int MAX_STARS = 8;
 constexpr int NANG = 180;      // nang_scatt
 constexpr int N_AZ_RT = 45;    // n_az_rt
-constexpr int MAX_RT = 8;      // max RT_n_incl * RT_n_az observer directions
+constexpr int MAX_RT = 16;     // max RT_n_incl * RT_n_az observer directions
+constexpr int N_ZETA = 10000;  // MRW.f90:8
 
 // numerical constants of the reference (constants.f90:8-14,151-159)
 #define MCB_PI       3.141592653589793238462643383279502884197
@@ -73,6 +74,9 @@ struct DevModel {
   int z_regular;                                 // z_lim(i,j) == (j-1)*z_lim(i,2) bit-for-bit (default grid, :459-465)
   double Rmax2, zmaxmax;
   const double *r_lim_2, *r_lim_3, *z_lim, *zmax, *cell_height, *tan_theta_lim, *theta_lim, *tan_phi_lim, *volume;
+  // walls as read by distance_to_closest_wall_* (modified random walk): r_lim(0:n_rad), w_lim(0:nz) = sin(theta_lim),
+  // cos(theta_lim(0:nz)) (host libm), sin / cos_phi_lim(n_az)
+  const double *r_lim, *w_lim, *cos_theta_lim, *sin_phi_lim, *cos_phi_lim;
   const double *kappa_factor;       // (n_cells)
   const double *kf_dark;            // (n_cells) kappa_factor with the sign bit set where l_dark_zone (photon-loop kernel only)
   const uint8_t *dark;              // (n_cells) l_dark_zone
@@ -116,6 +120,9 @@ struct DevModel {
   double *xN;               // xN_abs: (n_cells) thermal / (n_cells, n_lambda) otherwise, or null
   double *smap, *star_origin, *disk_origin;   // Monte Carlo photon maps of the call's wavelength, packet-origin tallies (output.f90:26-37)
   double *park;             // parked stragglers: (PARK_REC doubles) x capacity, see transport.cuh
+  // modified random walk (MRW.f90): zeta(1:n_zeta), mean opacities A, B, C (n_T, p_n_cells), flight-start cell ids
+  const double *zeta, *mrw_A, *mrw_B, *mrw_C;
+  int *mrw_c0;              // (n_blocks, NP): cell id the flight in progress started in (dust_transfer.f90:1242)
   SmemLayout sm;
   DevGrains gr;
 };
@@ -151,7 +158,11 @@ struct DevRun {
   int patience;                         // polls (250 ns each) a warp waits for a full 32-packet chunk before it takes a partial one
   int park_live;                        // hand over when at most this many packets of a block are in flight (<= PARK_LIVE)
   int park_enable;                      // hand stragglers over to a second small launch (count_sent modes only)
-  int debug_abort_dry;                  // profiling aid (env MCB_DEBUG_ABORT_DRY): stop when the packet counter runs dry
+  int debug_abort_dry;                  // profiling aid, development builds (-DMCB_DEV) only: stop when the packet counter runs dry
+  int lMRW;                             // modified random walk in the thermal step
+  double gamma_MRW;
+  unsigned inflight_floor;              // packets in flight per block: never capped below this,
+  float inflight_frac_per_block;        // else max_inflight_fraction * packets sent so far / blocks
 };
 
 }  // namespace mcb

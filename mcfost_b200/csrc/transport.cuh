@@ -56,7 +56,7 @@ __constant__ DevRun c_rr[MCB_BANKS];
 // and registers of the hot loop.
 enum { VAR_THERMAL = 0, VAR_GENERIC = 1, VAR_EXTRAS = 2 };
 enum { Q_EMIT = 0, Q_ABS = 1, Q_SCAT = 2, Q_FLY = 3, NQ = 4, Q_NONE = 7 };     // queue order = claim order (longest phases first)
-enum { STAT_PACKETS = 0, STAT_STEPS, STAT_INTERACT, STAT_SCATT, STAT_ABS, STAT_KILLED, STAT_ESCAPED, STAT_BOUNCE };
+enum { STAT_PACKETS = 0, STAT_STEPS, STAT_INTERACT, STAT_SCATT, STAT_ABS, STAT_KILLED, STAT_ESCAPED, STAT_BOUNCE, STAT_MRW_WALKS, STAT_MRW_STEPS };
 
 // ---- opacity / thermal table accessors (SM: shared-memory staging, p_n_cells == 1) ----
 __device__ __forceinline__ const float* smf(int word_off) { return reinterpret_cast<const float*>(smd() + word_off); }
@@ -796,18 +796,30 @@ struct Pool {
   __device__ __forceinline__ volatile unsigned& BUSY() const { return ctl[9]; }
   __device__ __forceinline__ volatile unsigned& PARK() const { return ctl[10]; }   // this block is handing its packets over
   __device__ __forceinline__ volatile unsigned& DRYF() const { return ctl[11]; }   // the global packet counter ran dry
+  __device__ __forceinline__ volatile unsigned& SENT() const { return ctl[12]; }   // latest value of the global packet counter seen by this block (saturated)
 };
 
-// misc word: lambda (10 bits) | star 1 | scatt 1 | ISM 1 | i_star_hit 4 | chunk 15
-__device__ __forceinline__ uint32_t pack_misc(int lambda, bool star, bool scatt, bool ism, int istar, int chunk) {
-  return (uint32_t)lambda | ((uint32_t)star << 10) | ((uint32_t)scatt << 11) | ((uint32_t)ism << 12) | ((uint32_t)istar << 13) | ((uint32_t)chunk << 17);
+// misc word: lambda (13 bits) | star 1 | scatt 1 | ISM 1 | i_star_hit 4 | n_iteractions_in_cell 8 (saturating) | 4 spare.
+// (the chunk of a packet is recovered from its id: packet = (nnfot1 - 1) << 40 | index, see misc_chunk)
+__device__ __forceinline__ uint32_t pack_misc(int lambda, bool star, bool scatt, bool ism, int istar, int n_in_cell) {
+  return (uint32_t)lambda | ((uint32_t)star << 13) | ((uint32_t)scatt << 14) | ((uint32_t)ism << 15) | ((uint32_t)istar << 16) | ((uint32_t)n_in_cell << 20);
 }
-__device__ __forceinline__ int misc_lambda(uint32_t m) { return m & 1023; }
-__device__ __forceinline__ bool misc_star(uint32_t m) { return (m >> 10) & 1; }
-__device__ __forceinline__ bool misc_scatt(uint32_t m) { return (m >> 11) & 1; }
-__device__ __forceinline__ bool misc_ism(uint32_t m) { return (m >> 12) & 1; }
-__device__ __forceinline__ int misc_istar(uint32_t m) { return (m >> 13) & 15; }
-__device__ __forceinline__ int misc_chunk(uint32_t m) { return (int)(m >> 17); }
+constexpr uint32_t MISC_SCATT = 1u << 14;
+__device__ __forceinline__ int misc_lambda(uint32_t m) { return m & 8191; }
+__device__ __forceinline__ bool misc_star(uint32_t m) { return (m >> 13) & 1; }
+__device__ __forceinline__ bool misc_scatt(uint32_t m) { return (m >> 14) & 1; }
+__device__ __forceinline__ bool misc_ism(uint32_t m) { return (m >> 15) & 1; }
+__device__ __forceinline__ int misc_istar(uint32_t m) { return (m >> 16) & 15; }
+__device__ __forceinline__ int misc_n_in_cell(uint32_t m) { return (m >> 20) & 255; }
+__device__ __forceinline__ uint32_t misc_set_istar(uint32_t m, int istar) { return (m & ~(15u << 16)) | ((uint32_t)istar << 16); }
+__device__ __forceinline__ uint32_t misc_set_n_in_cell(uint32_t m, int n) { return (m & ~(255u << 20)) | ((uint32_t)(n > 255 ? 255 : n) << 20); }
+// local chunk index of a packet from the high word of its id (nnfot1 - 1 = pk_hi >> 8)
+template <int BANK> __device__ __forceinline__ int chunk_of(uint32_t pk_hi) {
+  const DevRun& r = c_r;
+  const int nnfot1 = (int)(pk_hi >> 8) + 1;
+  const int first_local = r.nnfot1_start + ((r.rank - ((r.nnfot1_start - 1) % r.n_ranks) + r.n_ranks) % r.n_ranks);
+  return (nnfot1 - first_local) / r.n_ranks;
+}
 
 // cells <-> two 32-bit words
 __device__ __forceinline__ void pack_cell(Cell c, uint32_t& a, uint32_t& b) { a = (uint32_t)c.ri; b = ((uint32_t)c.zj & 0xFFFFu) | ((uint32_t)c.k << 16); }
@@ -827,7 +839,7 @@ template <bool SM, int BANK> __device__ __forceinline__ Pool make_pool() {
   return P;
 }
 
-struct Stats { unsigned int pk, steps, inter, sca, abs_, kill, esc, bounce; };
+struct Stats { unsigned int pk, steps, inter, sca, abs_, kill, esc, bounce, mrw_w, mrw_s; };
 // scheduling diagnostics (per warp, lane 0): chunk visits and valid lanes per phase
 struct SchedStats { unsigned int visits[NQ], lanes[NQ]; };
 
@@ -852,20 +864,175 @@ __device__ __forceinline__ void push_next(const Pool& P, int slot, int nextq, bo
 
 // ---- begin flight `ev`: tau and the interaction-type draw from block 2*ev (dust_transfer.f90:1208-1215,1280),
 // physical_length preamble (optical_depth.f90:53-68).  Position / direction / cell are already in the pool. ----
-__device__ __forceinline__ void start_flight(const DevModel& m, const DevRun& r, const Pool& P, int slot,
-                                             double x, double y, double z, double u, double v, double w,
-                                             const uint4 b /* Philox block 2*ev of this packet */, uint32_t& misc) {
-  const float rand = u01(b.x);
-  float tau;
-  if (rand == 1.0f) tau = 1.0e30f;
-  else if (rand > 1.0e-6f) tau = -logf(1.0f - rand);       // `real` arithmetic in the reference (dust_transfer.f90:1212)
-  else tau = rand;
-  P.F(F_EXTR, slot) = (double)tau;
+__device__ __forceinline__ float tau_of_rand(float rand) {
+  if (rand == 1.0f) return 1.0e30f;
+  if (rand > 1.0e-6f) return -logf(1.0f - rand);       // `real` arithmetic in the reference (dust_transfer.f90:1212)
+  return rand;
+}
+#define MRW_C0(slot) (c_m.mrw_c0[(size_t)blockIdx.x * NP + (slot)])
+template <int BANK, class CellT>
+__device__ __forceinline__ void start_flight(const Pool& P, int slot, double x, double y, double z, double u, double v, double w,
+                                             const uint4 b /* Philox block 2*ev of this packet */, uint32_t& misc, CellT cell) {
+  const DevModel& m = c_m; const DevRun& r = c_r;
+  P.F(F_EXTR, slot) = (double)tau_of_rand(u01(b.x));
   P.U(U_RALB, slot) = __float_as_uint(u01(b.y));
   P.F(F_OX, slot) = x; P.F(F_OY, slot) = y; P.F(F_OZ, slot) = z;
   P.U(U_COA, slot) = 0xFFFFFFF9u; P.U(U_COB, slot) = 0;          // null previous cell
   const int istar = intersect_stars(m, x, y, z, u, v, w);
-  misc = (misc & ~(15u << 13)) | ((uint32_t)istar << 13);
+  misc = misc_set_istar(misc, istar);
+  if (r.lMRW) MRW_C0(slot) = id_of_cell(m, cell);               // icell_old of dust_transfer.f90:1242
+}
+
+// =============================================================================
+// Modified random walk (MRW.f90, call site dust_transfer.f90:1222-1239; Min et al. 2009, Robitaille 2010).
+// WARP = false: one packet per lane (phase_absorb / phase_scatter).  WARP = true: the packet-per-warp kernel, where all
+// 32 lanes run this for the SAME packet: mutable global memory is read by lane 0 and broadcast (so that the lanes stay
+// bit-identical) and only lane 0 deposits.
+// `ev` is the number of the flight about to start; every step and the closing re-emission take one event number each,
+// Philox block (2 ev + 1) | 0x40000000.
+// =============================================================================
+template <bool WARP> __device__ __forceinline__ double bcast0(double v) { return WARP ? __shfl_sync(0xffffffffu, v, 0) : v; }
+template <bool WARP> __device__ __forceinline__ int bcast0(int v) { return WARP ? __shfl_sync(0xffffffffu, v, 0) : v; }
+template <bool WARP> __device__ __forceinline__ LtePre lte_prefetch_w(const DevModel& m, int idx) {
+  LtePre p = lte_prefetch(m, idx);
+  p.xkj = bcast0<WARP>(p.xkj); p.Ti = bcast0<WARP>(p.Ti);
+  return p;
+}
+// MRW.f90:58-70 sample_zeta = interp(y_MRW, zeta, zeta_random) (utils.f90:190-247): first j in 2..n-1 with zeta(j) > xp, else n
+__device__ __forceinline__ double sample_zeta(const DevModel& m, double zr) {
+  int a = 1, b = N_ZETA - 1;
+  while (a < b) { const int mid = (a + b) >> 1; if (__ldg(m.zeta + mid) > zr) b = mid; else a = mid + 1; }
+  const double x0 = __ldg(m.zeta + a - 1), x1 = __ldg(m.zeta + a);
+  const double y0 = (double)(a - 1) / (double)(N_ZETA - 1), y1 = (double)a / (double)(N_ZETA - 1);
+  const double frac = (zr - x0) / (x1 - x0);
+  return y0 * (1. - frac) + y1 * frac;
+}
+struct MrwOut { double x, y, z, u, v, w; int lambda; uint32_t ev; unsigned steps; };
+template <class G, bool SM, int BANK, bool WARP>
+__device__ __noinline__ MrwOut mrw_walk(typename G::CellT cell, int idx, int p_icell, double x, double y, double z, double S0,
+                                        uint32_t pk_lo, uint32_t pk_hi, uint32_t ev) {
+  const DevModel& m = c_m; const DevRun& r = c_r;
+  const bool leader = !WARP || (threadIdx.x & 31) == 0;
+  MrwOut o; o.x = x; o.y = y; o.z = z; o.u = 0; o.v = 0; o.w = 1; o.lambda = 0; o.ev = ev; o.steps = 0;
+  const double kf = __ldg(m.kappa_factor + idx);
+  if (!(kf > 0.0)) return o;
+  double d = G::closest_wall(m, cell, x, y, z);
+  int Ti; double frac_T2;
+  temp_lte<SM>(m, r, idx, p_icell, lte_prefetch_w<WARP>(m, idx), Ti, frac_T2);
+  const double frac_T1 = 1.0 - frac_T2;
+  const size_t q1 = (size_t)(Ti - 2) + (size_t)m.n_T * (p_icell - 1), q2 = q1 + 1;
+  const double A = frac_T1 * __ldg(m.mrw_A + q1) + frac_T2 * __ldg(m.mrw_A + q2);
+  const double B = frac_T1 * __ldg(m.mrw_B + q1) + frac_T2 * __ldg(m.mrw_B + q2);
+  const double Cc = frac_T1 * __ldg(m.mrw_C + q1) + frac_T2 * __ldg(m.mrw_C + q2);
+  if (!(A > 0.0) || !(B > 0.0)) return o;
+  const double l_R = B / (A * kf);                  // Rosseland-type mean free path 1 / (rho chi_R)
+  while (d > r.gamma_MRW * l_R && o.steps < 100000u) {
+    const uint4 b = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), (2u * o.ev + 1u) | 0x40000000u, pk_lo, pk_hi, r.call_index);
+    double u, v, w;
+    random_isotropic_direction(u01(b.x), u01(b.y), u, v, w);      // MRW.f90:84-88: random point on the sphere of radius d
+    o.x = o.x + u * d; o.y = o.y + v * d; o.z = o.z + w * d;
+    double zr = (double)u01(b.z);
+    if (zr <= 0.0) zr = 1.0 / 33554432.0;
+    const double ym = sample_zeta(m, zr);                          // MRW.f90:92
+    const double ct = -mcb_log(ym) * (d / MCB_PI) * (d / MCB_PI) * 3.0 / l_R;     // Min et al. 2009 eq. 8 with D = l_R / 3
+    if (leader) atomicAdd(m.tally + m.lay.xKJ + idx, S0 * ct * Cc / A);            // energy left along the walk
+    ++o.steps; ++o.ev;
+    d = G::closest_wall(m, cell, o.x, o.y, o.z);
+  }
+  if (o.steps == 0u) return o;
+  // end of the walk: thermal re-emission at the cell's running temperature, isotropic, unpolarised
+  const uint4 b = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), (2u * o.ev + 1u) | 0x40000000u, pk_lo, pk_hi, r.call_index);
+  if (WARP) __syncwarp();
+  o.lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, u01(b.y), lte_prefetch_w<WARP>(m, idx));
+  random_isotropic_direction(u01(b.z), u01(b.w), o.u, o.v, o.w);
+  ++o.ev;
+  return o;
+}
+
+// =============================================================================
+// emit_packet (dust_transfer.f90:1047-1151) of packet (pk_lo, pk_hi): wavelength (thermal / polychromatic calls), source,
+// position, direction, first cell.  Pure function of the packet id (Philox blocks 0 and 1), shared by the packet-per-lane
+// kernel (phase_emit) and the packet-per-warp kernel (warp_engine.cuh).
+// =============================================================================
+template <class CellT> struct Emitted { double x, y, z, u, v, w, S0; CellT cell; int lambda; bool flag_star, flag_ISM, lintersect; };
+
+template <class G, bool SM, int BANK, int VAR>
+__device__ __forceinline__ Emitted<typename G::CellT> emit_packet_core(uint32_t pk_lo, uint32_t pk_hi) {
+  constexpr bool GR = VAR == VAR_EXTRAS; constexpr bool TH = VAR == VAR_THERMAL; (void)GR; (void)TH;
+  const DevModel& m = c_m; const DevRun& r = c_r;
+  using CellT = typename G::CellT;
+  Emitted<CellT> e;
+  const uint4 b0 = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 0u, pk_lo, pk_hi, r.call_index);
+  const uint4 b1 = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 1u, pk_lo, pk_hi, r.call_index);
+  int di = 0;
+  auto nextf = [&]() -> float {
+    const int i = di++;
+    const uint32_t w = (i == 0) ? b0.x : (i == 1) ? b0.y : (i == 2) ? b0.z : (i == 3) ? b0.w : (i == 4) ? b1.x : (i == 5) ? b1.y : (i == 6) ? b1.z : b1.w;
+    return u01(w);
+  };
+  // n_phot_envoyes(lambda) is incremented with the PREVIOUS packet's lambda in thermal mode
+  // (dust_transfer.f90:531 precedes :537); on the device packets are unordered, so the count is
+  // attributed to the packet's own emission wavelength (the sum over lambda is identical).
+  int lambda = r.lambda_in;
+  if (TH || !r.lmono) lambda = select_wl_em<SM>(m, nextf());
+  e.lambda = lambda;
+  double x, y, z, u, v, w, S0;
+  CellT cell; null_cell(cell);
+  bool lintersect = true;
+  float rand = nextf();
+  if ((double)rand <= t_frac_star<SM>(m, lambda)) {
+    e.flag_star = true; e.flag_ISM = false;
+    const int i_star = select_star(m, lambda, nextf());
+    const float rand1 = nextf(), rand2 = nextf(), rand3 = nextf(), rand4 = nextf();
+    // emit_packet_uniform_sphere (stars.f90:108-169)
+    double zz = 2.0 * rand1 - 1.0;
+    double srw02 = sqrt(1.0 - zz * zz), sa, ca;
+    mcb_sincospi(2.0 * rand2 - 1.0, &sa, &ca);            // argmt = pi*(2 rand2 - 1)
+    double xx = srw02 * ca, yy = srw02 * sa;
+    double cospsi = (double)sqrtf(rand3), sp, cp;
+    mcb_sincospi(2.0 * (double)rand4, &sp, &cp);          // phi = 2 pi rand4
+    cdapres(cospsi, sp, cp, xx, yy, zz, u, v, w);
+    const double r_star = m.star[i_star - 1][3] * (1.0 + 1e-6);
+    x = xx * r_star + m.star[i_star - 1][0]; y = yy * r_star + m.star[i_star - 1][1]; z = zz * r_star + m.star[i_star - 1][2];
+    if (G::is_vor) cell_of_id(m, m.star_icell[i_star - 1], cell);
+    else cell = G::index(m, x, y, z);
+    if (m.star_out[i_star - 1]) lintersect = G::move_to_grid(m, x, y, z, u, v, w, cell);
+    S0 = m.E_paquet;
+    if (GR && r.lspot) {      // hot spot on star 1 (dust_transfer.f90:1094-1119), tested on the position emit_packet_uniform_sphere returns
+      if ((double)r.x_spot * x + (double)r.y_spot * y + (double)r.z_spot * z > (double)r.cos_thet_spot * m.star[0][3]) {
+        const float hc_lk = (float)(6.626070040e-34 * 299792458.0 / (__ldg(m.tab_lambda + lambda - 1) * 1e-6 * 1.38064852e-23));
+        const float correct_spot = (float)((exp((double)hc_lk / r.star1_T) - 1) / (double)(expf(hc_lk / r.T_spot) - 1));
+        S0 = S0 * correct_spot;
+      }
+    }
+  } else if ((double)rand <= t_frac_disk<SM>(m, lambda)) {
+    e.flag_star = false; e.flag_ISM = false;
+    const int ic = select_cellule(m, lambda, nextf());
+    cell_of_id(m, ic, cell);
+    const float rand1 = nextf(), rand2 = nextf(), rand3 = nextf();
+    G::pos_em_cell(m, cell, rand1, rand2, rand3, x, y, z);
+    const float rw = nextf(), rp = nextf();
+    random_isotropic_direction(rw, rp, u, v, w);
+    S0 = m.E_paquet;
+    if (GR && r.lweight_emission) S0 = S0 * __ldg(m.correct_E + ic - 1);      // dust_transfer.f90:1140-1142
+  } else {
+    e.flag_star = false; e.flag_ISM = true;
+    // emit_packet_ISM (stars.f90:728-787)
+    S0 = 1.0;
+    const float rand1 = nextf(), rand2 = nextf();
+    double zz = 2.0 * rand1 - 1.0;
+    double srw02 = sqrt(1.0 - zz * zz), sa, ca;
+    mcb_sincospi(2.0 * rand2 - 1.0, &sa, &ca);
+    double xx = srw02 * ca, yy = srw02 * sa;
+    const float rand3 = nextf(), rand4 = nextf();
+    double cospsi = (double)(-sqrtf(rand3)), sp, cp;
+    mcb_sincospi(2.0 * (double)rand4, &sp, &cp);
+    cdapres(cospsi, sp, cp, xx, yy, zz, u, v, w);
+    x = m.cISM[0] + xx * m.R_ISM; y = m.cISM[1] + yy * m.R_ISM; z = m.cISM[2] + zz * m.R_ISM;
+    lintersect = G::move_to_grid(m, x, y, z, u, v, w, cell);
+  }
+  e.x = x; e.y = y; e.z = z; e.u = u; e.v = v; e.w = w; e.S0 = S0; e.cell = cell; e.lintersect = lintersect;
+  return e;
 }
 
 // =============================================================================
@@ -895,6 +1062,7 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
       if ((int)lane == leader) base = atomicAdd(m.work, (unsigned long long)__popc(need));
       base = __shfl_sync(0xffffffffu, base, leader);
       const unsigned long long g = base + __popc(need & ((1u << lane) - 1u));
+      if ((int)lane == leader) P.SENT() = (unsigned)(base > 0xffffffffull ? 0xffffffffull : base);
       if (valid && g >= r.n_packets_total) { atomicMin(m.work + 1, (unsigned long long)globaltimer_ns()); P.DRYF() = 1u; }     // start of the drain-out
       if (valid && g < r.n_packets_total) {
         const unsigned long long lc = g / r.n_per_chunk;
@@ -917,94 +1085,28 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
   if (got) {
     const unsigned long long packet = ((unsigned long long)(nnfot1 - 1) << 40) + idx_in_chunk;
     const uint32_t pk_lo = (uint32_t)packet, pk_hi = (uint32_t)(packet >> 32);
-    const uint4 b0 = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 0u, pk_lo, pk_hi, r.call_index);
-    const uint4 b1 = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 1u, pk_lo, pk_hi, r.call_index);
-    int di = 0;
-    auto nextf = [&]() -> float {
-      const int i = di++;
-      const uint32_t w = (i == 0) ? b0.x : (i == 1) ? b0.y : (i == 2) ? b0.z : (i == 3) ? b0.w : (i == 4) ? b1.x : (i == 5) ? b1.y : (i == 6) ? b1.z : b1.w;
-      return u01(w);
-    };
     ++st.pk;
-    // n_phot_envoyes(lambda) is incremented with the PREVIOUS packet's lambda in thermal mode
-    // (dust_transfer.f90:531 precedes :537); on the device packets are unordered, so the count is
-    // attributed to the packet's own emission wavelength (the sum over lambda is identical).
-    int lambda = r.lambda_in;
-    if (TH || !r.lmono) lambda = select_wl_em<SM>(m, nextf());
+    const Emitted<CellT> e = emit_packet_core<G, SM, BANK, VAR>(pk_lo, pk_hi);
+    const int lambda = e.lambda;
     atomicAdd(m.tally + m.lay.n_env + (lambda - 1), 1.0);
-    double x, y, z, u, v, w, S0;
-    CellT cell; null_cell(cell);
-    bool lintersect = true, flag_star, flag_ISM;
-    float rand = nextf();
-    if ((double)rand <= t_frac_star<SM>(m, lambda)) {
-      flag_star = true; flag_ISM = false;
-      const int i_star = select_star(m, lambda, nextf());
-      const float rand1 = nextf(), rand2 = nextf(), rand3 = nextf(), rand4 = nextf();
-      // emit_packet_uniform_sphere (stars.f90:108-169)
-      double zz = 2.0 * rand1 - 1.0;
-      double srw02 = sqrt(1.0 - zz * zz), sa, ca;
-      mcb_sincospi(2.0 * rand2 - 1.0, &sa, &ca);            // argmt = pi*(2 rand2 - 1)
-      double xx = srw02 * ca, yy = srw02 * sa;
-      double cospsi = (double)sqrtf(rand3), sp, cp;
-      mcb_sincospi(2.0 * (double)rand4, &sp, &cp);          // phi = 2 pi rand4
-      cdapres(cospsi, sp, cp, xx, yy, zz, u, v, w);
-      const double r_star = m.star[i_star - 1][3] * (1.0 + 1e-6);
-      x = xx * r_star + m.star[i_star - 1][0]; y = yy * r_star + m.star[i_star - 1][1]; z = zz * r_star + m.star[i_star - 1][2];
-      if (G::is_vor) cell_of_id(m, m.star_icell[i_star - 1], cell);
-      else cell = G::index(m, x, y, z);
-      if (m.star_out[i_star - 1]) lintersect = G::move_to_grid(m, x, y, z, u, v, w, cell);
-      S0 = m.E_paquet;
-      if (GR && r.lspot) {      // hot spot on star 1 (dust_transfer.f90:1094-1119), tested on the position emit_packet_uniform_sphere returns
-        if ((double)r.x_spot * x + (double)r.y_spot * y + (double)r.z_spot * z > (double)r.cos_thet_spot * m.star[0][3]) {
-          const float hc_lk = (float)(6.626070040e-34 * 299792458.0 / (__ldg(m.tab_lambda + lambda - 1) * 1e-6 * 1.38064852e-23));
-          const float correct_spot = (float)((exp((double)hc_lk / r.star1_T) - 1) / (double)(expf(hc_lk / r.T_spot) - 1));
-          S0 = S0 * correct_spot;
-        }
-      }
-    } else if ((double)rand <= t_frac_disk<SM>(m, lambda)) {
-      flag_star = false; flag_ISM = false;
-      const int ic = select_cellule(m, lambda, nextf());
-      cell_of_id(m, ic, cell);
-      const float rand1 = nextf(), rand2 = nextf(), rand3 = nextf();
-      G::pos_em_cell(m, cell, rand1, rand2, rand3, x, y, z);
-      const float rw = nextf(), rp = nextf();
-      random_isotropic_direction(rw, rp, u, v, w);
-      S0 = m.E_paquet;
-      if (GR && r.lweight_emission) S0 = S0 * __ldg(m.correct_E + ic - 1);      // dust_transfer.f90:1140-1142
-    } else {
-      flag_star = false; flag_ISM = true;
-      // emit_packet_ISM (stars.f90:728-787)
-      S0 = 1.0;
-      const float rand1 = nextf(), rand2 = nextf();
-      double zz = 2.0 * rand1 - 1.0;
-      double srw02 = sqrt(1.0 - zz * zz), sa, ca;
-      mcb_sincospi(2.0 * rand2 - 1.0, &sa, &ca);
-      double xx = srw02 * ca, yy = srw02 * sa;
-      const float rand3 = nextf(), rand4 = nextf();
-      double cospsi = (double)(-sqrtf(rand3)), sp, cp;
-      mcb_sincospi(2.0 * (double)rand4, &sp, &cp);
-      cdapres(cospsi, sp, cp, xx, yy, zz, u, v, w);
-      x = m.cISM[0] + xx * m.R_ISM; y = m.cISM[1] + yy * m.R_ISM; z = m.cISM[2] + zz * m.R_ISM;
-      lintersect = G::move_to_grid(m, x, y, z, u, v, w, cell);
-    }
-    if (lintersect) {
-      P.F(F_PX, slot) = x; P.F(F_PY, slot) = y; P.F(F_PZ, slot) = z;
-      P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;
-      P.F(F_S0, slot) = S0;
+    if (e.lintersect) {
+      P.F(F_PX, slot) = e.x; P.F(F_PY, slot) = e.y; P.F(F_PZ, slot) = e.z;
+      P.F(F_U, slot) = e.u; P.F(F_V, slot) = e.v; P.F(F_W, slot) = e.w;
+      P.F(F_S0, slot) = e.S0;
       if (POLA) { QUV(0, slot) = 0.0; QUV(1, slot) = 0.0; QUV(2, slot) = 0.0; }
-      uint32_t ca_, cb_; pack_cell(cell, ca_, cb_);
+      uint32_t ca_, cb_; pack_cell(e.cell, ca_, cb_);
       P.U(U_C0A, slot) = ca_; P.U(U_C0B, slot) = cb_;
       P.U(U_PKLO, slot) = pk_lo; P.U(U_PKHI, slot) = pk_hi; P.U(U_EV, slot) = 1u;
-      uint32_t misc = pack_misc(lambda, flag_star, false, flag_ISM, 0, my_chunk);
-      start_flight(m, r, P, slot, x, y, z, u, v, w, philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u, pk_lo, pk_hi, r.call_index), misc);
-      if (GR && r.capt_full) { POS0(0, slot) = x; POS0(1, slot) = y; POS0(2, slot) = z; POS0(3, slot) = (double)tally_index(m, cell); }
+      uint32_t misc = pack_misc(lambda, e.flag_star, false, e.flag_ISM, 0, 0);
+      start_flight<BANK>(P, slot, e.x, e.y, e.z, e.u, e.v, e.w, philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u, pk_lo, pk_hi, r.call_index), misc, e.cell);
+      if (GR && r.capt_full) { POS0(0, slot) = e.x; POS0(1, slot) = e.y; POS0(2, slot) = e.z; POS0(3, slot) = (double)tally_index(m, e.cell); }
       P.U(U_MISC, slot) = misc;
       nextq = Q_FLY;
     } else {      // the packet never enters the model: straight to the detector (dust_transfer.f90:545-552)
-      if (!flag_ISM) {
-        const double S[4] = {S0, 0.0, 0.0, 0.0};
-        const int capt = (GR && r.capt_full) ? capteur_full<BANK>(lambda, x, y, z, u, v, w, S, flag_star, false, tally_index(m, cell))
-                                     : capteur<BANK>(lambda, u, v, w, S, flag_star, false);
+      if (!e.flag_ISM) {
+        const double S[4] = {e.S0, 0.0, 0.0, 0.0};
+        const int capt = (GR && r.capt_full) ? capteur_full<BANK>(lambda, e.x, e.y, e.z, e.u, e.v, e.w, S, e.flag_star, false, tally_index(m, e.cell))
+                                     : capteur<BANK>(lambda, e.u, e.v, e.w, S, e.flag_star, false);
         if (!TH && !r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * my_chunk, 1ull);
         ++st.esc;
       }
@@ -1064,7 +1166,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
         if (POLA) { S[1] = QUV(0, slot); S[2] = QUV(1, slot); S[3] = QUV(2, slot); }
         const int capt = (GR && r.capt_full) ? capteur_full<BANK>(lambda, POS0(0, slot), POS0(1, slot), POS0(2, slot), u, v, w, S, misc_star(misc), misc_scatt(misc), (int)POS0(3, slot))
                                      : capteur<BANK>(lambda, u, v, w, S, misc_star(misc), misc_scatt(misc));
-        if (!TH && !r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * misc_chunk(misc), 1ull);
+        if (!TH && !r.count_sent && capt == r.capt_sup) atomicAdd(m.work + 3 + 2 * chunk_of<BANK>(P.U(U_PKHI, slot)), 1ull);
         ++st.esc;      // (interstellar packets leave without being detected, dust_transfer.f90:548)
       }
       nextq = Q_EMIT; flying = false;
@@ -1152,6 +1254,10 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
         nextq = (__uint_as_float(P.U(U_RALB, slot)) < t_albedo<SM>(m, p_icell, lambda)) ? Q_SCAT : Q_ABS;
       }
       P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;       // (reversed on a bounce)
+      if (TH && r.lMRW) {      // n_iteractions_in_cell (dust_transfer.f90:1242-1249): flights in a row that ended in the cell they started in
+        const bool same = id_of_cell(m, c0) == MRW_C0(slot);
+        P.U(U_MISC, slot) = misc_set_n_in_cell(misc, same ? misc_n_in_cell(misc) + 1 : 0);
+      }
     }
     if (nextq != Q_EMIT) {
       P.F(F_PX, slot) = x0; P.F(F_PY, slot) = y0; P.F(F_PZ, slot) = z0;
@@ -1186,11 +1292,11 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
     CellT cell; unpack_cell(P.U(U_C0A, slot), P.U(U_C0B, slot), cell);
     const int idx = tally_index(m, cell);
     const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
-    bool dead = false;
+    bool dead = idx < 0;      // interaction in a virtual cell (only with an inconsistent dark-zone mask): drop the packet
     double S[4] = {P.F(F_S0, slot), 0.0, 0.0, 0.0};
     if (POLA) { S[1] = QUV(0, slot); S[2] = QUV(1, slot); S[3] = QUV(2, slot); }
     if (!TH && r.lmono) {      // forced scattering (dust_transfer.f90:1263-1278)
-      if (idx >= 0 && __ldg(m.dark + idx)) dead = true;
+      if (dead || __ldg(m.dark + idx)) dead = true;
       else {
         const float albedo = t_albedo<SM>(m, p_icell, lambda);
         S[0] *= albedo; S[1] *= albedo; S[2] *= albedo; S[3] *= albedo;
@@ -1224,11 +1330,24 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
         cdapres(cospsi, sp, cp, u, v, w, u1, v1, w1);
         if (POLA && r.lmethod_aniso1) scatter_stokes<BANK>(lambda, itheta, rand2, p_icell, S, u, v, w, u1, v1, w1);
       }
+      misc |= MISC_SCATT;                                    // flag_scatt
+      uint32_t evn = ev + 1u;
+      uint4 bn = bnext;
+      double px = P.F(F_PX, slot), py = P.F(F_PY, slot), pz = P.F(F_PZ, slot);
+      if (TH && r.lMRW && misc_n_in_cell(misc) > 5 && idx >= 0) {      // dust_transfer.f90:1222-1239
+        const MrwOut o = mrw_walk<G, SM, BANK, false>(cell, idx, p_icell, px, py, pz, S[0], pk_lo, pk_hi, evn);
+        if (o.steps) {
+          px = o.x; py = o.y; pz = o.z; u1 = o.u; v1 = o.v; w1 = o.w; S[1] = 0.0; S[2] = 0.0; S[3] = 0.0;
+          P.F(F_PX, slot) = px; P.F(F_PY, slot) = py; P.F(F_PZ, slot) = pz;
+          misc = pack_misc(o.lambda, false, false, false, 0, misc_n_in_cell(misc));
+          evn = o.ev; bn = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * evn, pk_lo, pk_hi, r.call_index);
+          ++st.mrw_w; st.mrw_s += o.steps;
+        }
+      }
       P.F(F_U, slot) = u1; P.F(F_V, slot) = v1; P.F(F_W, slot) = w1;
       if ((!TH && r.lmono) || POLA) { P.F(F_S0, slot) = S[0]; if (POLA) { QUV(0, slot) = S[1]; QUV(1, slot) = S[2]; QUV(2, slot) = S[3]; } }
-      misc |= (1u << 11);                                    // flag_scatt
-      P.U(U_EV, slot) = ev + 1u;
-      start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u1, v1, w1, bnext, misc);
+      P.U(U_EV, slot) = evn;
+      start_flight<BANK>(P, slot, px, py, pz, u1, v1, w1, bn, misc, cell);
       if (GR && r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
       P.U(U_MISC, slot) = misc;
       nextq = Q_FLY;
@@ -1257,7 +1376,8 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
     const int idx = tally_index(m, cell);
     const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
     ++st.abs_;
-    const LtePre pre = lte_prefetch(m, idx);      // in flight while the Philox blocks are computed
+    // idx < 0: interaction in a virtual cell (only with an inconsistent dark-zone mask): the packet is dropped below
+    const LtePre pre = lte_prefetch(m, idx < 0 ? 0 : idx);      // in flight while the Philox blocks are computed
     const uint32_t pk_lo = P.U(U_PKLO, slot), pk_hi = P.U(U_PKHI, slot), ev = P.U(U_EV, slot);
 #ifdef MCB_PHILOX2
     uint4 b, bnext;      // interaction block of flight ev, flight block of ev+1
@@ -1267,7 +1387,8 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
     const uint4 bnext = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev + 2u, pk_lo, pk_hi, r.call_index);
 #endif
     int lambda;
-    if (!GR || (r.lonly_LTE && !r.low_mem_th)) {
+    if (idx < 0) lambda = 0;
+    else if (!GR || (r.lonly_LTE && !r.low_mem_th)) {
       // b.x is rand1: drawn but unused in the high-memory LTE branch (thermal_emission.f90:739-765)
       lambda = im_reemission_LTE<SM>(m, r, idx, p_icell, u01(b.y), pre);
     } else if (r.lonly_LTE) {
@@ -1285,11 +1406,24 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
     else {
       double u, v, w;
       random_isotropic_direction(u01(b.z), u01(b.w), u, v, w);
-      P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;
       if (POLA) { QUV(0, slot) = 0.0; QUV(1, slot) = 0.0; QUV(2, slot) = 0.0; }
-      misc = pack_misc(lambda, false, false, false, 0, misc_chunk(misc));      // flag_star = flag_scatt = flag_ISM = .false.
-      P.U(U_EV, slot) = ev + 1u;
-      start_flight(m, r, P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u, v, w, bnext, misc);
+      misc = pack_misc(lambda, false, false, false, 0, misc_n_in_cell(misc));      // flag_star = flag_scatt = flag_ISM = .false.
+      uint32_t evn = ev + 1u;
+      uint4 bn = bnext;
+      double px = P.F(F_PX, slot), py = P.F(F_PY, slot), pz = P.F(F_PZ, slot);
+      if (TH && r.lMRW && misc_n_in_cell(misc) > 5 && idx >= 0) {      // dust_transfer.f90:1222-1239
+        const MrwOut o = mrw_walk<G, SM, BANK, false>(cell, idx, p_icell, px, py, pz, P.F(F_S0, slot), pk_lo, pk_hi, evn);
+        if (o.steps) {
+          px = o.x; py = o.y; pz = o.z; u = o.u; v = o.v; w = o.w;
+          P.F(F_PX, slot) = px; P.F(F_PY, slot) = py; P.F(F_PZ, slot) = pz;
+          misc = pack_misc(o.lambda, false, false, false, 0, misc_n_in_cell(misc));
+          evn = o.ev; bn = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * evn, pk_lo, pk_hi, r.call_index);
+          ++st.mrw_w; st.mrw_s += o.steps;
+        }
+      }
+      P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;
+      P.U(U_EV, slot) = evn;
+      start_flight<BANK>(P, slot, px, py, pz, u, v, w, bn, misc, cell);
       if (GR && r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
       P.U(U_MISC, slot) = misc;
       nextq = Q_FLY;
@@ -1364,7 +1498,7 @@ mc_photon_loop_kernel(const int adopt) {
   if (threadIdx.x == 0) { P.ctl[NQ + Q_EMIT] = NP; P.ctl[8] = NP; }
   __syncthreads();
   const bool park_ok = r.park_enable && !adopt;
-  Stats st = {0, 0, 0, 0, 0, 0, 0, 0};
+  Stats st = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   SchedStats ss = {{0, 0, 0, 0}, {0, 0, 0, 0}};
 #ifdef MCB_DRAIN_PROBE
   int probe_k = 0;
@@ -1379,28 +1513,39 @@ mc_photon_loop_kernel(const int adopt) {
       // prefer a full 32-entry chunk.  Partial chunks are taken at once when the pool is draining out
       // (few live packets: nothing will fill up), otherwise only after ~2 us without a full chunk.
       for (int polls = 0;; ++polls) {
+#ifdef MCB_DEV
         if (c_r.debug_abort_dry && __ldcg(c_m.work + 1) != ~0ull) break;      // profiling aid: steady-state only
+#endif
         if (park_ok && P.PARK()) break;                                       // the block is handing its packets over
         int best = -1; unsigned best_n = 0;
+        const unsigned live = P.LIVE();
+        unsigned emit_allow = 0xffffffffu;
+        if (!adopt && c_r.inflight_frac_per_block > 0.0f) {
+          // concurrency window: packets in flight <= max(floor, fraction of the packets sent so far) (see DevRun)
+          const unsigned cap = max(c_r.inflight_floor, (unsigned)fminf(c_r.inflight_frac_per_block * (float)P.SENT(), (float)NP));
+          const unsigned in_flight = live - (P.TAIL(Q_EMIT) - P.HEAD(Q_EMIT));
+          emit_allow = cap > in_flight ? cap - in_flight : 0u;
+        }
 #pragma unroll
         for (int k = 0; k < NQ; ++k) {
-          const unsigned av = P.TAIL(k) - P.HEAD(k);
+          unsigned av = P.TAIL(k) - P.HEAD(k);
+          if (k == Q_EMIT && av > emit_allow) av = emit_allow;
           if (av >= 32u) { best = k; best_n = 32u; break; }
           if (av > best_n) { best = k; best_n = av; }
         }
-        const unsigned live = P.LIVE();
 #ifdef MCB_DRAIN_PROBE
         if (threadIdx.x == 0 && P.DRYF()) drain_probe(c_m.work, c_r.n_photons_loop, live, probe_k);
 #endif
         if (park_ok && live <= (unsigned)r.park_live && live > 0u && P.DRYF()) { P.PARK() = 1u; break; }
         if (best >= 0 && (best_n == 32u || live <= DRAIN_LIVE || polls >= c_r.patience)) {
           const unsigned hh = P.HEAD(best);
-          const unsigned av = P.TAIL(best) - hh;
+          unsigned av = P.TAIL(best) - hh;
+          if (best == Q_EMIT && av > emit_allow) av = emit_allow;
           const unsigned take = av < 32u ? av : 32u;
           if (take > 0 && atomicCAS((unsigned*)&P.ctl[best], hh, hh + take) == hh) { qi = best; h = hh; n = take; break; }
           continue;
         }
-        if (best < 0 && live == 0u) break;       // every packet of this block is done
+        if (best_n == 0u && live == 0u) break;       // every packet of this block is done
         __nanosleep(250);
       }
     }
@@ -1472,6 +1617,7 @@ mc_photon_loop_kernel(const int adopt) {
           for (int f = 0; f < NU32; ++f) ru[f] = P.U(f, slot);
           ru[NU32] = (uint32_t)k;
           if (POLA_) { rec[16] = QUV(0, slot); rec[17] = QUV(1, slot); rec[18] = QUV(2, slot); }
+          *reinterpret_cast<uint32_t*>(rec + 19) = r.lMRW ? (uint32_t)MRW_C0(slot) : 0u;      // cell the flight in progress started in
         }
       }
     }
@@ -1485,6 +1631,7 @@ mc_photon_loop_kernel(const int adopt) {
   };
   flush(STAT_PACKETS, st.pk); flush(STAT_STEPS, st.steps); flush(STAT_INTERACT, st.inter); flush(STAT_SCATT, st.sca);
   flush(STAT_ABS, st.abs_); flush(STAT_KILLED, st.kill); flush(STAT_ESCAPED, st.esc); flush(STAT_BOUNCE, st.bounce);
+  flush(STAT_MRW_WALKS, st.mrw_w); flush(STAT_MRW_STEPS, st.mrw_s);
   if (lane == 0) {
     unsigned long long* dbg = m.work + (4 + 2 * r.n_photons_loop);
     for (int k = 0; k < NQ; ++k) { atomicAdd(dbg + k, (unsigned long long)ss.visits[k]); atomicAdd(dbg + NQ + k, (unsigned long long)ss.lanes[k]); }

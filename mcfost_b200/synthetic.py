@@ -173,14 +173,19 @@ def cylindrical_grid(n_rad=100, nz=70, n_az=1, n_rad_in=20, zones=None, l3D=Fals
         V = V * 0.5 / float(np.float32(n_az))
         # tan_phi_lim (:586-600) in fp32 like the reference
         d_phi = np.float32(2.0) * np.float32(3.1415926535) / np.float32(n_az)
-        tan_phi = np.zeros(n_az)
+        tan_phi = np.zeros(n_az); cos_phi = np.zeros(n_az); sin_phi = np.zeros(n_az)
         for k in range(1, n_az + 1):
             phi = np.float32(d_phi * np.float32(k))
             m = np.float32(np.mod(np.float32(phi - np.float32(0.5) * np.float32(3.1415926535)), np.float32(3.1415926535)))
             tan_phi[k - 1] = 1.0e300 if abs(m) < 1.0e-6 else float(np.tan(np.float32(phi)))
+            # cos_phi_lim / sin_phi_lim (:592-598), read by distance_to_closest_wall_* only
+            cos_phi[k - 1] = 0.0 if abs(m) < 1.0e-6 else float(np.cos(np.float32(phi)))
+            sin_phi[k - 1] = 1.0e300 if abs(m) < 1.0e-6 else float(np.sin(np.float32(phi)))
         P.tan_phi_lim = tan_phi
+        P.cos_phi_lim, P.sin_phi_lim = cos_phi, sin_phi
     else:
         P.tan_phi_lim = np.zeros(max(n_az, 1))
+        P.cos_phi_lim = np.zeros(max(n_az, 1)); P.sin_phi_lim = np.zeros(max(n_az, 1))
     ci, cj, ck = cell_numbering(n_rad, nz, n_az, l3D)
     P.cell_map_i, P.cell_map_j, P.cell_map_k = ci, cj, ck
     P.n_cells_tot = len(ci)
@@ -237,14 +242,19 @@ def spherical_grid(n_rad=60, nz=30, n_az=1, n_rad_in=5, rin=10.0, rout=200.0, l3
     if l3D:
         V = V * 0.5 / float(np.float32(n_az))
         d_phi = np.float32(2.0) * np.float32(3.1415926535) / np.float32(n_az)
-        tan_phi = np.zeros(n_az)
+        tan_phi = np.zeros(n_az); cos_phi = np.zeros(n_az); sin_phi = np.zeros(n_az)
         for k in range(1, n_az + 1):
             phi = np.float32(d_phi * np.float32(k))
             m = np.float32(np.mod(np.float32(phi - np.float32(0.5) * np.float32(3.1415926535)), np.float32(3.1415926535)))
             tan_phi[k - 1] = 1.0e300 if abs(m) < 1.0e-6 else float(np.tan(np.float32(phi)))
+            # cos_phi_lim / sin_phi_lim (:592-598), read by distance_to_closest_wall_* only
+            cos_phi[k - 1] = 0.0 if abs(m) < 1.0e-6 else float(np.cos(np.float32(phi)))
+            sin_phi[k - 1] = 1.0e300 if abs(m) < 1.0e-6 else float(np.sin(np.float32(phi)))
         P.tan_phi_lim = tan_phi
+        P.cos_phi_lim, P.sin_phi_lim = cos_phi, sin_phi
     else:
         P.tan_phi_lim = np.zeros(max(n_az, 1))
+        P.cos_phi_lim = np.zeros(max(n_az, 1)); P.sin_phi_lim = np.zeros(max(n_az, 1))
     ci, cj, ck = cell_numbering(n_rad, nz, n_az, l3D)
     P.cell_map_i, P.cell_map_j, P.cell_map_k = ci, cj, ck
     P.n_cells_tot = len(ci)

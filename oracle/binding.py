@@ -40,6 +40,8 @@ def _load(name):
                "oracle_set_emission", "oracle_set_grains", "oracle_n_cells_tot"):
         getattr(lib, fn).argtypes = [C.c_void_p] + ([C.c_void_p] if fn not in ("oracle_destroy", "oracle_n_cells_tot") else [])
     lib.oracle_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
+    lib.oracle_distance_to_closest_wall.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5
+    lib.oracle_mrw_tables.argtypes = [C.c_void_p] * 4
     return lib
 
 
@@ -176,6 +178,30 @@ class Oracle:
         self._check(self.lib.oracle_physical_length(self.h, C.c_int64(n), C.c_int32(lam), _p(x), _p(y), _p(z), _p(u), _p(v), _p(w),
                                                     _p(icell), _p(tau), _p(ltot), _p(fs), _p(alive)))
         return dict(x=x, y=y, z=z, u=u, v=v, w=w, icell=icell, ltot=ltot, flag_sortie=fs, lpacket_alive=alive)
+
+    def distance_to_closest_wall(self, icell, x, y, z):
+        x, y, z = self._f64(x, y, z)
+        icell = np.ascontiguousarray(icell, np.int32)
+        s = np.zeros(len(x))
+        self._check(self.lib.oracle_distance_to_closest_wall(self.h, C.c_int64(len(x)), _p(icell), _p(x), _p(y), _p(z), _p(s)))
+        return s
+
+    def mrw_tables(self):
+        shp = (self.P.n_T, self.P.p_n_cells)
+        A, B, Cc = (np.zeros(shp, np.float64, order="F") for _ in range(3))
+        self._check(self.lib.oracle_mrw_tables(self.h, _p(A), _p(B), _p(Cc)))
+        return A, B, Cc
+
+    def zeta_table(self):
+        z = np.zeros(10000)
+        self.lib.oracle_zeta_table.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self.lib.oracle_zeta_table(self.h, _p(z), 10000)
+        return z
+
+    def sample_zeta(self, zr):
+        self.lib.oracle_sample_zeta.argtypes = [C.c_void_p, C.c_double]
+        self.lib.oracle_sample_zeta.restype = C.c_double
+        return float(self.lib.oracle_sample_zeta(self.h, float(zr)))
 
     def dark_zone_walker(self):
         """Callable for synthetic.define_dark_zone (step 4 ray walk)."""

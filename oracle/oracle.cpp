@@ -94,7 +94,7 @@ struct ThreadTallies {
   // per-thread scratch of angles_scatt_rt1 (dust_ray_tracing.f90: itheta_rt1 etc.)
   std::vector<int> itheta_rt1;
   std::vector<double> cos_omega_rt1, sin_omega_rt1;
-  double stats[8];
+  double stats[12];
 };
 
 struct Oracle {
@@ -1540,14 +1540,21 @@ struct Oracle {
     p.flag_scatt = false;
     flag_direct_star = p.flag_star;
     uint32_t n_flight = 0;
+    int n_iteractions_in_cell = 0;                // :1204
     for (;;) {
       ++n_flight;
+      if (r.lMRW && n_iteractions_in_cell > 5) {  // :1222-1239
+        if (modified_random_walk(rng, t, n_flight, lambda, p)) flag_direct_star = false;
+      }
       rng_set_block(&rng, 2 * n_flight);          // flight block: tau, interaction-type draw (see philox.h)
       rand = (float)rng_next(&rng);
       if (rand == 1.0f) tau = 1.0e30f;
       else if (rand > 1.0e-6f) tau = -std::log(1.0f - rand);
       else tau = rand;
+      const int icell_old = p.icell;                                    // :1242-1249
       physical_length(t, lambda, p_lambda, p.S, p.icell, p.x, p.y, p.z, p.u, p.v, p.w, p.flag_star, flag_direct_star, tau, dvol, flag_sortie, p.alive);
+      if (p.icell == icell_old) n_iteractions_in_cell = n_iteractions_in_cell + 1;
+      else n_iteractions_in_cell = 0;
       if (flag_sortie) return;
       int p_icell = lvariable_dust() ? p.icell : 1;
       t.stats[2] += 1;
@@ -1639,6 +1646,227 @@ struct Oracle {
         p.S[1] = 0.0; p.S[2] = 0.0; p.S[3] = 0.0;
       }
     }
+  }
+
+
+  // =====================================================================
+  // Modified random walk.  MRW.f90:16-115 (zeta table, sample_zeta, make_MRW_step -- unfinished in the
+  // reference), call site dust_transfer.f90:1222-1239 (commented out), distance_to_closest_wall_*
+  // (cylindrical_grid.f90:1179-1226, spherical_grid.f90:451-499, Voronoi.f90:996-1061), mean opacities
+  // compute_Planck_opacities diffusion.f90:631-693 (T hard-wired to 20 K there).  The step itself follows
+  // Min et al. 2009 (A&A 497, 155) sect. 3-4 and Robitaille 2010 (A&A 520, A70), with the mean opacities
+  // taken over the spectrum this code's own immediate re-emission samples (kdB_dT_CDF at the cell's running
+  // temperature), so that the walk it replaces is exactly the one propagate_packet would have done.
+  // =====================================================================
+  static constexpr int n_zeta = 10000;            // MRW.f90:8
+  std::vector<double> zeta_tab;                    // zeta(1:n), y_MRW(i) = (i-1)/(n-1)
+  std::vector<double> mrw_A, mrw_B, mrw_C;         // (n_T, p_n_cells)
+  const void* mrw_for = nullptr;                   // opacity tables the means were built from
+
+  // MRW.f90:16-54 initialize_cumulative_zeta: zeta(y) = 2 Sum_{n>=1} (-1)^(n+1) y^(n^2)  (Min et al. 2009 eq. 7).
+  // A running maximum is applied afterwards: beyond y ~ 0.95 the series equals 1 to rounding and its noise would
+  // make the table non-monotonic (no 24-bit draw can land there; it keeps the lookup well defined).
+  void initialize_cumulative_zeta() {
+    zeta_tab.assign(n_zeta, 0.0);
+    for (int i = 1; i <= n_zeta; ++i) {
+      const double y = (double)(i - 1) / (double)(n_zeta - 1);
+      double z = 0.0;
+      if (i == n_zeta) z = 0.5;
+      else {
+        int j = 0;
+        for (;;) {
+          j = j + 1;
+          const double term = std::pow(y, (double)j * (double)j);
+          if (term == 0.0) break;
+          if (j % 2 == 0) z = z - term; else z = z + term;
+        }
+      }
+      zeta_tab[i - 1] = z * 2.0;
+    }
+    for (int i = 1; i < n_zeta; ++i) zeta_tab[i] = std::max(zeta_tab[i], zeta_tab[i - 1]);
+  }
+  // MRW.f90:58-70 sample_zeta = interp(y_MRW, zeta, zeta_random)  (utils.f90:190-247: first j in 2..n-1 with
+  // x(j) > xp, else n; linear interpolation, no extrapolation)
+  double sample_zeta(double zeta_random) const {
+    const int n = n_zeta;
+    if (zeta_random < zeta_tab[0]) return 0.0;
+    if (zeta_random > zeta_tab[n - 1]) return 1.0;
+    int j = 2;
+    for (; j <= n - 1; ++j) if (zeta_tab[j - 1] > zeta_random) break;
+    const double x0 = zeta_tab[j - 2], x1 = zeta_tab[j - 1];
+    const double y0 = (double)(j - 2) / (double)(n - 1), y1 = (double)(j - 1) / (double)(n - 1);
+    const double frac = (zeta_random - x0) / (x1 - x0);
+    return y0 * (1. - frac) + y1 * frac;
+  }
+
+  // sin_phi_lim(k) as a wall normal: the grid set-up stores 1.0d300 next to tan_phi_lim = 1.0d300 for the walls at
+  // phi = pi/2 (mod pi) (cylindrical_grid.f90:591-594), which would take those walls out of the minimum; they are the
+  // planes x = 0, i.e. sin = 1, cos = 0.
+  inline double sin_phi_wall(int k) const { const double sp = g.sin_phi_lim[k - 1]; return sp > 1.0e299 ? 1.0 : sp; }
+  // cylindrical_grid.f90:1179-1226 distance_to_closest_wall_cyl.  (k0-1 = 0 indexes sin_phi_lim(0) in the
+  // reference, out of bounds; the wall below sector 1 is the upper wall of sector n_az.)
+  double distance_to_closest_wall_cyl(int icell, double x, double y, double z) const {
+    const int ri0 = cmap_i[icell]; int zj0 = cmap_j[icell]; const int k0 = cmap_k[icell];
+    const double rr = std::sqrt(x * x + y * y);
+    const double s1 = r_lim(ri0) - rr;
+    const double s2 = rr - r_lim(ri0 - 1);
+    const double z0 = std::fabs(z);
+    zj0 = std::abs(zj0);
+    const double s3 = z_lim(ri0, std::abs(zj0) + 1) - z0;
+    const double s4 = z0 - z_lim(ri0, std::abs(zj0));
+    double s_ = std::min(std::min(s1, s2), std::min(s3, s4));
+    if (g.l3D) {
+      const int km = (k0 - 1 >= 1) ? k0 - 1 : g.n_az;
+      const double s5 = std::fabs(x * sin_phi_wall(k0) - y * g.cos_phi_lim[k0 - 1]);
+      const double s6 = std::fabs(x * sin_phi_wall(km) - y * g.cos_phi_lim[km - 1]);
+      s_ = std::min(s_, std::min(s5, s6));
+    }
+    return s_;
+  }
+  // spherical_grid.f90:451-499 distance_to_closest_wall_sph.  The reference writes the theta walls as
+  // abs(rcyl*w_lim(thetaj0) - z0*cos_phi_lim(thetaj0)) (:471-472): cos_phi_lim is the AZIMUTHAL table (size n_az,
+  // zero in 2D) indexed with the theta index -- an out-of-bounds read of dead code.  The distance from (rcyl, z0)
+  // to the cone z = rcyl tan(theta_lim(j)) is |rcyl sin(theta_lim) - z0 cos(theta_lim)|; that is what is computed,
+  // with cos(theta_lim(j)) in place of the mis-indexed table.
+  double distance_to_closest_wall_sph(int icell, double x, double y, double z) const {
+    const int ri0 = cmap_i[icell]; const int thetaj0 = std::abs(cmap_j[icell]); const int k0 = cmap_k[icell];
+    const double r2_cyl = x * x + y * y;
+    const double rcyl = std::sqrt(r2_cyl);
+    const double rr = std::sqrt(r2_cyl + z * z);
+    const double s1 = r_lim(ri0) - rr;
+    const double s2 = rr - r_lim(ri0 - 1);
+    const double z0 = std::fabs(z);
+    const double s3 = std::fabs(rcyl * g.w_lim[thetaj0] - z0 * std::cos(theta_lim(thetaj0)));
+    const double s4 = std::fabs(rcyl * g.w_lim[thetaj0 - 1] - z0 * std::cos(theta_lim(thetaj0 - 1)));
+    double s_ = std::min(std::min(s1, s2), std::min(s3, s4));
+    if (g.l3D) {
+      const int km = (k0 - 1 >= 1) ? k0 - 1 : g.n_az;
+      const double s5 = std::fabs(x * sin_phi_wall(k0) - y * g.cos_phi_lim[k0 - 1]);
+      const double s6 = std::fabs(x * sin_phi_wall(km) - y * g.cos_phi_lim[km - 1]);
+      s_ = std::min(s_, std::min(s5, s6));
+    }
+    return s_;
+  }
+  // Voronoi.f90:996-1061 distance_to_closest_wall_Voronoi (fp32 plane geometry like cross_Voronoi_cell).
+  // The reference divides dot(n, p - r) by den = dot(n, n) with the UN-normalised normal n = r_neighbour - r_cell,
+  // which yields the distance in units of |n|, not a length; the length is dot(n, p - r) / |n| and that is
+  // what is returned here (den = sqrt(dot(n, n))).  Cut cells and cells touching a wall return 0 (:1009, :1051).
+  double distance_to_closest_wall_Voronoi(int icell, double x, double y, double z) const {
+    if (g.vor_was_cut[icell - 1] != 0) return 0.0;
+    float n[3], p[3], r[3], r_cell[3], r_neighbour[3];
+    r[0] = (float)x; r[1] = (float)y; r[2] = (float)z;
+    double s_ = (double)1e30f;
+    const double* cxyz = g.vor_xyz + 3 * (size_t)(icell - 1);
+    for (int a = 0; a < 3; ++a) r_cell[a] = (float)cxyz[a];
+    const int ifirst = g.vor_first[icell - 1], ilast = g.vor_last[icell - 1];
+    for (int i = ifirst; i <= ilast; ++i) {
+      const int id_n = g.neighbours_list[i - 1];
+      double s_tmp;
+      if (id_n > 0) {
+        const double* nxyz = g.vor_xyz + 3 * (size_t)(id_n - 1);
+        for (int a = 0; a < 3; ++a) r_neighbour[a] = (float)nxyz[a];
+        for (int a = 0; a < 3; ++a) n[a] = r_neighbour[a] - r_cell[a];
+        const double den = (double)std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        for (int a = 0; a < 3; ++a) p[a] = 0.5f * (r_neighbour[a] + r_cell[a]);
+        const float dot = n[0] * (p[0] - r[0]) + n[1] * (p[1] - r[1]) + n[2] * (p[2] - r[2]);
+        s_tmp = (double)dot / den;
+        if (s_tmp < 0.) s_tmp = (double)huge_real;
+      } else s_tmp = 0.0;
+      if (s_tmp < s_) s_ = s_tmp;
+    }
+    return s_;
+  }
+  double distance_to_closest_wall(int icell, double x, double y, double z) const {
+    if (g.kind == MCB_GRID_CYL) return distance_to_closest_wall_cyl(icell, x, y, z);
+    if (g.kind == MCB_GRID_SPH) return distance_to_closest_wall_sph(icell, x, y, z);
+    return distance_to_closest_wall_Voronoi(icell, x, y, z);
+  }
+
+  // Mean opacities per temperature index (the job of compute_Planck_opacities, diffusion.f90:631-693).
+  // One absorb / re-emit cycle of propagate_packet: a wavelength from p_T(lambda) = increments of
+  // kdB_dT_CDF(:,T), then flights of mean length 1/(kf kappa) with albedo a and asymmetry g until the
+  // absorption.  Per cycle, in units of kappa_factor:
+  //   A(T) = Sum p / (kappa (1-a))                      mean path
+  //   B(T) = Sum p / (kappa (1-a) kappa (1-a g))        mean squared displacement / 2
+  //   C(T) = Sum p kappa_abs_LTE / (kappa (1-a))        mean xKJ_abs deposit / Stokes(1)
+  // so that the diffusion coefficient per unit path is B / (3 A kf) (a Rosseland-type mean of the transport
+  // opacity) and the energy left per unit path is C / A (a Planck-type mean of the absorption opacity).
+  void compute_MRW_means() {
+    if (mrw_for == (const void*)o.kdB_dT_CDF && !mrw_A.empty()) return;
+    const int nT = o.n_T, npc = o.p_n_cells, nl = o.n_lambda;
+    mrw_A.assign((size_t)nT * npc, 0.0); mrw_B.assign((size_t)nT * npc, 0.0); mrw_C.assign((size_t)nT * npc, 0.0);
+    for (int pc = 1; pc <= npc; ++pc)
+      for (int t = 1; t <= nT; ++t) {
+        double A = 0.0, B = 0.0, Cc = 0.0;
+        for (int l = 1; l <= nl; ++l) {
+          const double pl = kdB_dT_CDF(l, t, pc) - (l > 1 ? kdB_dT_CDF(l - 1, t, pc) : 0.0);
+          const double kap = kappa(pc, l), a = (double)tab_albedo_pos(pc, l);
+          const double gg = o.tab_g_pos ? (double)tab_g_pos(pc, l) : 0.0;
+          const double k_abs = kap * (1.0 - a), k_tr = kap * (1.0 - a * gg);
+          if (!(pl > 0.0) || !(k_abs > 0.0)) continue;
+          A = A + pl / k_abs;
+          B = B + pl / (k_abs * k_tr);
+          Cc = Cc + pl * kappa_abs_LTE(pc, l) / k_abs;
+        }
+        const size_t q = (size_t)(t - 1) + (size_t)nT * (pc - 1);
+        mrw_A[q] = A; mrw_B[q] = B; mrw_C[q] = Cc;
+      }
+    mrw_for = (const void*)o.kdB_dT_CDF;
+  }
+
+  // dust_transfer.f90:1222-1239 (restated; see the header of this section).  Returns true if at least one
+  // step was made; the packet then leaves with a new wavelength, an isotropic direction and no polarisation.
+  // RNG: every step and the final re-emission take one event number each, block (2 n_flight + 1) | 0x40000000.
+  bool modified_random_walk(PacketRng& rng, ThreadTallies& t, uint32_t& n_flight, int& lambda, Packet& p) {
+    const int icell = p.icell;
+    if (icell < 1 || icell > g.n_cells) return false;
+    const double kf = kappa_factor(icell);
+    if (!(kf > 0.0)) return false;
+    const int p_icell = lvariable_dust() ? icell : 1;
+    const double gamma = (r.gamma_MRW > 0.0f) ? (double)r.gamma_MRW : 2.0;
+    double d = distance_to_closest_wall(icell, p.x, p.y, p.z);
+    // running temperature of the cell -> mean opacities (interpolated like the re-emission CDF)
+    int Ti; float Temp; double frac_T2;
+    Temp_LTE(t, icell, Ti, Temp, frac_T2);
+    const double frac_T1 = 1.0 - frac_T2;
+    const size_t q1 = (size_t)(Ti - 2) + (size_t)o.n_T * (p_icell - 1), q2 = q1 + 1;
+    const double A = frac_T1 * mrw_A[q1] + frac_T2 * mrw_A[q2];
+    const double B = frac_T1 * mrw_B[q1] + frac_T2 * mrw_B[q2];
+    const double Cc = frac_T1 * mrw_C[q1] + frac_T2 * mrw_C[q2];
+    if (!(A > 0.0) || !(B > 0.0)) return false;
+    const double l_R = B / (A * kf);                 // 1 / (rho chi_R): Rosseland-type mean free path
+    bool did = false;
+    int n_steps = 0;
+    t.stats[10] += 1;                                // diagnostics: walks attempted / refused (d <= gamma l_R)
+    if (!(d > gamma * l_R)) { t.stats[11] += 1; if (getenv("ORACLE_MRW_DEBUG") && ((int)t.stats[11] % 20000) == 1) fprintf(stderr, "refused: cell %d (ri %d zj %d) d %.4g l_R %.4g Ti %d frac %.3f lambda %d kf %.4g 1/(kf kappa(lambda)) %.4g A %.4g B %.4g\n", icell, cmap_i[icell], cmap_j[icell], d, l_R, Ti, frac_T2, lambda, kf, 1.0 / (kf * kappa(p_icell, lambda)), A, B); }
+    while (d > gamma * l_R && n_steps < 100000) {
+      rng_set_block(&rng, (2 * n_flight + 1) | 0x40000000u);
+      // MRW.f90:84-88: random point on the sphere of radius d around the packet
+      double u, v, w;
+      random_isotropic_direction(rng, u, v, w);
+      p.x = p.x + u * d; p.y = p.y + v * d; p.z = p.z + w * d;
+      // MRW.f90:92-98: y from zeta(y) = random; Min et al. 2009 eq. 8: c t = -ln(y) (d/pi)^2 / D, D = l_R / 3
+      double zr = rng_next(&rng);
+      if (zr <= 0.0) zr = 1.0 / 33554432.0;
+      const double ym = sample_zeta(zr);
+      const double ct = -std::log(ym) * (d / pi) * (d / pi) * 3.0 / l_R;
+      // energy left in the cell along the walk (Lucy path-length estimator, radiation_field.f90:53)
+      t.xKJ_abs[icell - 1] = t.xKJ_abs[icell - 1] + p.S[0] * ct * Cc / A;
+      t.stats[9] += 1;
+      did = true; ++n_steps; ++n_flight;
+      d = distance_to_closest_wall(icell, p.x, p.y, p.z);
+    }
+    if (!did) return false;
+    t.stats[8] += 1;
+    // end of the walk: thermal re-emission at the cell's running temperature
+    rng_set_block(&rng, (2 * n_flight + 1) | 0x40000000u);
+    const float rand1 = (float)rng_next(&rng), rand2 = (float)rng_next(&rng);
+    im_reemission_LTE(t, icell, p_icell, rand1, rand2, lambda);
+    random_isotropic_direction(rng, p.u, p.v, p.w);
+    p.S[1] = 0.0; p.S[2] = 0.0; p.S[3] = 0.0;
+    p.flag_star = false; p.flag_scatt = false; p.flag_ISM = false;
+    ++n_flight;
+    return true;
   }
 
   // =====================================================================
@@ -1890,7 +2118,7 @@ struct Oracle {
       for (size_t i = 0; i < T[0].I_spec_star.size(); ++i) { float s = 0; for (auto& t : T) s += t.I_spec_star[i]; out->I_spec_star[i] = s; }
       out->N_type_flux = N_type_flux;
     }
-    if (out->stats) for (int a = 0; a < 8; ++a) { double s = 0; for (auto& t : T) s += t.stats[a]; out->stats[a] = s; }
+    if (out->stats) for (int a = 0; a < 12; ++a) { double s = 0; for (auto& t : T) s += t.stats[a]; out->stats[a] = s; }
   }
 };
 
@@ -1952,6 +2180,11 @@ int oracle_run(void* h, const mcb_run_params* r, mcb_tallies* out, int n_threads
   O->r = *r;
   int rc = check_run(O, r); if (rc) return rc;
   if (rec) n_threads = 1;
+  if (r->lMRW) {
+    if (!r->letape_th || !r->lonly_LTE || r->low_mem_th_emission || r->lxJ_abs_step1) { snprintf(O->err, sizeof O->err, "lMRW: thermal step with lonly_LTE only"); return MCB_ERR_UNSUPPORTED; }
+    if (O->zeta_tab.empty()) O->initialize_cumulative_zeta();
+    O->compute_MRW_means();
+  }
   rc = O->mc_photon_loop(n_threads, rec, n_rec); if (rc) return rc;
   O->collect(out);
   return MCB_OK;
@@ -1970,6 +2203,29 @@ int oracle_cross_cell(void* h, int64_t n, const double* x0, const double* y0, co
     next_cell[i] = nc;
   }
   return MCB_OK;
+}
+int oracle_distance_to_closest_wall(void* h, int64_t n, const int32_t* icell, const double* x, const double* y, const double* z, double* s) {
+  Oracle* O = (Oracle*)h;
+  for (int64_t i = 0; i < n; ++i) s[i] = O->distance_to_closest_wall(icell[i], x[i], y[i], z[i]);
+  return MCB_OK;
+}
+int oracle_mrw_tables(void* h, double* A, double* B, double* Cc) {
+  Oracle* O = (Oracle*)h;
+  O->mrw_for = nullptr; O->compute_MRW_means();
+  const size_t n = O->mrw_A.size();
+  for (size_t i = 0; i < n; ++i) { A[i] = O->mrw_A[i]; B[i] = O->mrw_B[i]; Cc[i] = O->mrw_C[i]; }
+  return MCB_OK;
+}
+int oracle_zeta_table(void* h, double* zeta, int n) {
+  Oracle* O = (Oracle*)h;
+  if (O->zeta_tab.empty()) O->initialize_cumulative_zeta();
+  for (int i = 0; i < n && i < Oracle::n_zeta; ++i) zeta[i] = O->zeta_tab[i];
+  return Oracle::n_zeta;
+}
+double oracle_sample_zeta(void* h, double zr) {
+  Oracle* O = (Oracle*)h;
+  if (O->zeta_tab.empty()) O->initialize_cumulative_zeta();
+  return O->sample_zeta(zr);
 }
 int oracle_index_cell(void* h, int64_t n, const double* x, const double* y, const double* z, int32_t* icell) {
   Oracle* O = (Oracle*)h;

@@ -1,0 +1,181 @@
+"""GPU tests (-m gpu) of the round-2 pieces of the thermal step, all through the C ABI, at the PRODUCTION launch
+configuration (no tuning knobs): the packet-per-warp kernel that runs small budgets and the last packets of large
+ones, the three-launch hand-over, distance_to_closest_wall, the modified random walk and its tables."""
+import numpy as np
+import pytest
+
+from mcfost_b200 import api, synthetic as S
+from oracle.binding import Oracle
+
+from helpers import rays_in_cells, small_problems
+
+pytestmark = pytest.mark.gpu
+
+GRIDS = ["cyl2D", "cyl3D", "sph2D", "sph3D"]
+
+
+def _spectrum_z(ta, tb, min_count=100):
+    """z-scores of the emergent packet counts per wavelength (all inclinations) of two independent runs."""
+    na, nb = ta.n_phot_sed.sum(axis=(1, 2)), tb.n_phot_sed.sum(axis=(1, 2))
+    m = (na + nb) > min_count
+    return (na[m] - nb[m]) / np.sqrt(na[m] + nb[m])
+
+
+def _energy_spectrum_close(ta, tb):
+    """energy-weighted emergent spectrum: sed per wavelength within 3 sigma of its own packet statistics"""
+    ea, eb = ta.sed.sum(axis=(1, 2)), tb.sed.sum(axis=(1, 2))
+    na, nb = ta.n_phot_sed.sum(axis=(1, 2)), tb.n_phot_sed.sum(axis=(1, 2))
+    m = (na + nb) > 100
+    sig = np.sqrt(ea[m] ** 2 / np.maximum(na[m], 1) + eb[m] ** 2 / np.maximum(nb[m], 1))
+    return np.abs(ea[m] - eb[m]) / sig
+
+
+@pytest.mark.parametrize("name", GRIDS)
+def test_distance_to_closest_wall_bit_exact(name):
+    P = small_problems()[name]()
+    O, G = Oracle(P), api.PhotonLoop(P)
+    ic, x, y, z, *_ = rays_in_cells(P, 100000, seed=31)
+    assert np.array_equal(G.distance_to_closest_wall(ic, x, y, z), O.distance_to_closest_wall(ic, x, y, z))
+    with pytest.raises(api.McfostB200Error):
+        G.distance_to_closest_wall(np.array([P.n_cells + 1], np.int32), x[:1], y[:1], z[:1])
+    G.close()
+
+
+def test_distance_to_closest_wall_voronoi_bit_exact():
+    P = S.voronoi_disk(n_points=1500, n_photons_eq_th=300)
+    O, G = Oracle(P), api.PhotonLoop(P)
+    rng = np.random.default_rng(4)
+    ic = rng.integers(1, P.n_cells + 1, 20000).astype(np.int32)
+    jit = 1e-3 * rng.normal(size=(3, len(ic))) * np.asarray(P.vor_h)[ic - 1]
+    x, y, z = (P.vor_xyz[a, ic - 1] + jit[a] for a in range(3))
+    assert np.array_equal(G.distance_to_closest_wall(ic, x, y, z), O.distance_to_closest_wall(ic, x, y, z))
+    G.close()
+
+
+def test_mrw_mean_opacity_tables_match_oracle():
+    for P in (small_problems()["cyl2D"](), S.ref41_multi_like(n_photons_eq_th=10)):
+        O, G = Oracle(P), api.PhotonLoop(P)
+        for a, b in zip(G.mrw_tables(), O.mrw_tables()):
+            assert np.array_equal(a, b)
+        G.close()
+
+
+@pytest.mark.parametrize("name", GRIDS)
+def test_para_budget_spectrum_every_grid(name):
+    """128 x 1000 packets (the budget of the reference's own .para files): the packet-per-warp kernel runs the whole
+    call.  Emergent spectrum per wavelength (counts AND energy) against the oracle within 3 sigma, temperatures within the
+    north_star bars."""
+    P = small_problems()[name]()
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(1, 1, 1000, 1.0e30, 1, False)
+    Tg = G.temp_finale()
+    assert G.debug_counters()["parked"] == 0
+    G.close()
+    O = Oracle(P, fast=True)
+    to = O.run(n_threads=0, n_photons2=1000)
+    To = O.temp_finale()
+    assert tg.stats[0] == to.stats[0] == 128000 == tg.n_phot_envoyes.sum()
+    assert tg.stats[5] + tg.stats[6] == tg.stats[0]
+    assert tg.sed.sum() == pytest.approx(tg.stats[6] * P.E_paquet)
+    z = _spectrum_z(tg, to)
+    assert np.mean(np.abs(z) < 3) >= 0.95 and abs(z.mean()) < 0.5, z
+    assert np.mean(_energy_spectrum_close(tg, to) < 3) >= 0.95
+    lit = (to.xKJ_abs > 0) & (tg.xKJ_abs > 0) & (To > 1.5)
+    rel = np.abs(Tg[lit] - To[lit]) / To[lit]
+    assert np.median(rel) < 0.02 and np.percentile(rel, 75) < 0.05, (np.median(rel), np.percentile(rel, 75))
+    assert abs(tg.xKJ_abs.sum() / to.xKJ_abs.sum() - 1) < 0.03
+    assert abs(tg.stats[1] / to.stats[1] - 1) < 0.02 and abs(tg.stats[2] / to.stats[2] - 1) < 0.03
+
+
+def test_para_budget_with_stokes_and_variable_dust():
+    """the same for the polarised call of ref4.1 (lsepar_pola) and for cell-dependent tables (global-memory kernels)"""
+    P = small_problems()["cyl2D"]()
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(1, 1, 1000, 1.0e30, 1, False, lsepar_pola=1, lsepar_contrib=1)
+    G.close()
+    to = Oracle(P, fast=True).run(n_threads=0, n_photons2=1000, lsepar_pola=1, lsepar_contrib=1)
+    z = _spectrum_z(tg, to)
+    assert np.mean(np.abs(z) < 3) >= 0.95 and abs(z.mean()) < 0.5
+    qg, qo = np.abs(tg.sed_q).sum(), np.abs(to.sed_q).sum()
+    assert qg > 0 and abs(qg / qo - 1) < 0.1
+    assert abs(tg.sed_star_scat.sum() / to.sed_star_scat.sum() - 1) < 0.05
+    P = S.ref41_multi_like(n_photons_eq_th=1000)
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(1, 1, 1000, 1.0e30, 1, False)
+    G.close()
+    to = Oracle(P, fast=True).run(n_threads=0, n_photons2=1000)
+    z = _spectrum_z(tg, to)
+    assert np.mean(np.abs(z) < 3) >= 0.95 and abs(z.mean()) < 0.5
+    assert abs(tg.xKJ_abs.sum() / to.xKJ_abs.sum() - 1) < 0.03
+
+
+def test_three_launch_call_matches_oracle():
+    """2.56e6 packets on the G1 geometry at test size: packet-per-warp kernel first, packet-per-lane kernel for the bulk
+    with the packets in flight capped at a fraction of those sent, stragglers back on the packet-per-warp kernel."""
+    P = S.ref41_like(n_photons_eq_th=20000, dark_zone=False, n_rad=40, nz=20, n_rad_in=5, tau_mid=1.0e3)
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(1, 1, 20000, 1.0e30, 1, False, lsepar_pola=1)
+    Tg = G.temp_finale()
+    d = G.debug_counters()
+    G.close()
+    O = Oracle(P, fast=True)
+    to = O.run(n_threads=0, n_photons2=20000, lsepar_pola=1)
+    To = O.temp_finale()
+    assert d["parked"] > 0
+    assert tg.stats[0] == to.stats[0] == 128 * 20000 == tg.n_phot_envoyes.sum()
+    assert tg.stats[5] + tg.stats[6] == tg.stats[0]
+    assert tg.sed.sum() == pytest.approx(tg.stats[6])
+    lit = (to.xKJ_abs > 0) & (tg.xKJ_abs > 0) & (To > 1.5)
+    rel = np.abs(Tg[lit] - To[lit]) / To[lit]
+    assert np.median(rel) < 0.01 and np.percentile(rel, 75) < 0.05, (np.median(rel), np.percentile(rel, 75))
+    z = _spectrum_z(tg, to)
+    assert np.mean(np.abs(z) < 3) >= 0.95 and abs(z.mean()) < 0.5, z
+    assert abs(tg.stats[1] / to.stats[1] - 1) < 0.01 and abs(tg.stats[2] / to.stats[2] - 1) < 0.01
+    assert abs(np.abs(tg.sed_q).sum() / np.abs(to.sed_q).sum() - 1) < 0.05
+
+
+@pytest.mark.parametrize("n2", [1500, 12000])
+def test_modified_random_walk_matches_oracle_and_plain_run(n2):
+    """lMRW on an optically thick disk, small budget (packet-per-warp kernel) and three-launch budget: same physics as
+    the oracle's MRW and as the run without it."""
+    P = S.ref41_like(n_photons_eq_th=n2, dark_zone=False, n_rad=40, nz=20, n_rad_in=5, tau_mid=1.0e4)
+    O = Oracle(P, fast=True)
+    P.l_dark_zone = S.define_dark_zone(P, P.lambda_seuil, 1500.0, O.dark_zone_walker())
+    S.repartition_energie(P)
+    O.set_dark_zone(P.l_dark_zone); O.set_emission(P)
+    G = api.PhotonLoop(P)
+    t0 = G.mc_photon_loop(1, 1, n2, 1.0e30, 1, False); T0 = G.temp_finale()
+    t1 = G.mc_photon_loop(1, 1, n2, 1.0e30, 1, False, lMRW=1); T1 = G.temp_finale()
+    with pytest.raises(api.McfostB200Error):
+        G.mc_photon_loop(8, 8, 10, 64.0, 1, False, letape_th=0, lmono=1, lMRW=1)
+    G.close()
+    to = O.run(n_threads=0, n_photons2=n2, lMRW=1); To = O.temp_finale()
+    assert t0.stats[8] == 0 and t1.stats[8] > 0 and t1.stats[9] >= t1.stats[8]
+    for t in (t0, t1):
+        assert t.stats[0] == 128 * n2 and t.stats[5] + t.stats[6] == t.stats[0]
+    assert t1.stats[2] < 0.97 * t0.stats[2]
+    # walks and steps per packet like the oracle's
+    assert abs(t1.stats[8] / to.stats[8] - 1) < 0.1 and abs(t1.stats[9] / to.stats[9] - 1) < 0.1
+    assert abs(t1.stats[2] / to.stats[2] - 1) < 0.05
+    lit = (np.asarray(P.l_dark_zone) == 0) & (t0.xKJ_abs > 0) & (t1.xKJ_abs > 0) & (to.xKJ_abs > 0) & (To > 1.5)
+    for Ta, Tb in ((T1, To), (T1, T0)):
+        rel = np.abs(Ta[lit] - Tb[lit]) / Tb[lit]
+        assert np.median(rel) < 0.01 and np.percentile(rel, 75) < 0.05, (np.median(rel), np.percentile(rel, 75))
+        assert abs(np.mean((Ta[lit] - Tb[lit]) / Tb[lit])) < 0.01
+    z = _spectrum_z(t1, to)
+    assert np.mean(np.abs(z) < 3) >= 0.95 and abs(z.mean()) < 0.5
+    z = _spectrum_z(t1, t0)
+    assert np.mean(np.abs(z) < 3) >= 0.95 and abs(z.mean()) < 0.5
+
+
+def test_modified_random_walk_other_grids():
+    for name in ("cyl3D", "sph2D"):
+        P = small_problems()[name]()
+        G = api.PhotonLoop(P)
+        t0 = G.mc_photon_loop(1, 1, 1000, 1.0e30, 1, False); T0 = G.temp_finale()
+        t1 = G.mc_photon_loop(1, 1, 1000, 1.0e30, 1, False, lMRW=1); T1 = G.temp_finale()
+        G.close()
+        assert t1.stats[5] + t1.stats[6] == t1.stats[0] == 128000
+        lit = (t0.xKJ_abs > 0) & (t1.xKJ_abs > 0) & (T0 > 1.5)
+        rel = np.abs(T1[lit] - T0[lit]) / T0[lit]
+        assert np.median(rel) < 0.02 and np.percentile(rel, 75) < 0.05

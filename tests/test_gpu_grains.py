@@ -51,7 +51,6 @@ def test_method1_nontrivial_s11_scales_the_packet_energy():
 
 
 def test_method1_thermal_statistical_parity(monkeypatch):
-    monkeypatch.setenv("MCB_BLOCKS", "8")
     P = S.multi_grain_like(n_photons_eq_th=1500, tau_mid=30.0)
     kw = dict(n_photons2=1500, lscattering_method1=1, lmethod_aniso1=1, lsepar_pola=1, lonly_LTE=1)
     G = api.PhotonLoop(P)
@@ -91,8 +90,7 @@ def test_mixed_heating_regimes_statistical_parity(variable, low_mem, monkeypatch
     Immediate re-emission reads the RUNNING tallies (Bjorkman & Wood): its spectrum is only independent of
     the order of the packets when few of them are in flight at once compared with the packet budget.  The
     full grid keeps 148 x 1024 packets in flight -- nothing against the 1e7-1e9 packets of a production
-    run, but most of this test's 192 000.  MCB_BLOCKS=8 brings the test to the same regime (4 % in flight)."""
-    monkeypatch.setenv("MCB_BLOCKS", "8")
+    run, but most of this test's 192 000: the library picks the number of blocks from the budget."""
     P = S.multi_grain_like(n_photons_eq_th=1500, tau_mid=30.0, variable=variable, pola=False)
     kw = dict(low_mem_th_emission_nLTE=low_mem, **MIXED)
     G = api.PhotonLoop(P)
@@ -133,7 +131,6 @@ def test_mixed_heating_regimes_statistical_parity(variable, low_mem, monkeypatch
 
 
 def test_only_nlte_and_state_errors(monkeypatch):
-    monkeypatch.setenv("MCB_BLOCKS", "8")
     P = S.multi_grain_like(n_photons_eq_th=400, tau_mid=5.0, pola=False)
     G = api.PhotonLoop(P)
     kw = dict(lonly_LTE=0, lonly_nLTE=1, lRE_nLTE=1, lxJ_abs_step1=1)
@@ -178,7 +175,6 @@ def test_hot_spot_and_weighted_emission_match_oracle_packet_by_packet():
 
 
 def test_low_memory_lte_emission_statistical_parity(monkeypatch):
-    monkeypatch.setenv("MCB_BLOCKS", "8")
     P = S.multi_grain_like(n_photons_eq_th=1500, tau_mid=30.0, pola=False)
     kw = dict(lonly_LTE=1, low_mem_th_emission=1)
     G = api.PhotonLoop(P)
@@ -200,7 +196,6 @@ def test_low_memory_lte_emission_statistical_parity(monkeypatch):
 def test_temp_finale_on_device_matches_the_tallies(monkeypatch):
     """mcfost_b200_temp_finale / _temp_finale_nlte read the device-resident tallies of the last call: they must be
     the reference formulas applied to exactly the tallies the call returns."""
-    monkeypatch.setenv("MCB_BLOCKS", "8")
     P = S.multi_grain_like(n_photons_eq_th=500, tau_mid=20.0, pola=False)
     G = api.PhotonLoop(P)
     t = G.mc_photon_loop(1, 1, 500, 1.0e30, 1, False, **MIXED)

@@ -163,9 +163,8 @@ def test_thermal_ref41_like_statistical_parity():
 
 @pytest.mark.parametrize("name", ["cyl3D", "sph2D", "sph3D"])
 def test_thermal_other_grids_statistical_parity(name, monkeypatch):
-    # 192k packets against 148 x 1024 in flight would put most of the run inside the concurrency window of the
-    # immediate re-emission: 8 blocks keep 4 % of the packets in flight, like a CPU run
-    monkeypatch.setenv("MCB_BLOCKS", "8")
+    # (production launch configuration: the library itself keeps the packets in flight a small fraction of the packets
+    # sent)
     P = small_problems()[name]()
     to, tg = _thermal_pair(P, 1500)
     assert tg.stats[0] == to.stats[0]
@@ -307,7 +306,6 @@ def test_voronoi_deterministic_kernels_bit_exact(voronoi_pair):
 
 
 def test_voronoi_thermal_statistical_parity(voronoi_pair, monkeypatch):
-    monkeypatch.setenv("MCB_BLOCKS", "8")        # small packet budget: see test_thermal_other_grids_statistical_parity
     P, O, G = voronoi_pair
     tg = G.mc_photon_loop(1, 1, 1500, 1.0e30, 1, False)
     to = Oracle(P, fast=True).run(n_threads=0, n_photons2=1500)
@@ -325,7 +323,6 @@ def test_variable_dust_per_cell_tables(monkeypatch):
     """lvariable_dust = .true. (ref4.1_multi-like, LTE part): every opacity / scattering / thermal table is
     indexed by cell (p_n_cells = n_cells, kappa_factor = 1), single-wavelength scattering tables
     (p_n_lambda_pos = 1); the kernel reads them from global memory instead of the shared-memory staging."""
-    monkeypatch.setenv("MCB_BLOCKS", "8")        # small packet budget: see test_thermal_other_grids_statistical_parity
     P = S.ref41_multi_like(n_photons_eq_th=1500)
     O, G = Oracle(P), api.PhotonLoop(P)
     ic, x, y, z, u, v, w = rays_in_cells(P, 20000, seed=41)
@@ -386,21 +383,31 @@ def test_image_step_rt2_matches_oracle(pola):
 
 
 def test_straggler_handover_keeps_every_packet():
-    """mcfost_b200_set_overlap: the main launch parks its last packets, a second small launch finishes them.
-    Nothing is lost or duplicated, and the tallies are those of an ordinary call within Monte Carlo noise."""
+    """A thermal call above the small-budget threshold runs on three launches: the packet-per-warp kernel sends the first
+    packets, the packet-per-lane kernel the bulk, and it parks its last packets for the packet-per-warp kernel.  Nothing
+    is lost or duplicated, with and without mcfost_b200_set_overlap, and the tallies are those of a small-budget call
+    (packet-per-warp kernel alone) within Monte Carlo noise."""
     P = small_problems()["cyl2D"]()
     G = api.PhotonLoop(P)
-    ref = G.mc_photon_loop(1, 1, 4000, 1.0e30, 1, False, lsepar_pola=1)
+    n2 = 12000
+    small = G.mc_photon_loop(1, 1, 1500, 1.0e30, 1, False, lsepar_pola=1)
+    assert G.debug_counters()["parked"] == 0      # 192 000 packets: the low-latency kernel alone
+    ref = G.mc_photon_loop(1, 1, n2, 1.0e30, 1, False, lsepar_pola=1)
+    d0 = G.debug_counters()
     G.set_overlap(8)
-    t = G.mc_photon_loop(1, 1, 4000, 1.0e30, 1, False, lsepar_pola=1)
+    t = G.mc_photon_loop(1, 1, n2, 1.0e30, 1, False, lsepar_pola=1, call_index=1)
     d = G.debug_counters()
-    assert t.stats[0] == ref.stats[0] == 128 * 4000 == t.n_phot_envoyes.sum()
-    assert t.stats[5] + t.stats[6] == t.stats[0]
-    assert t.sed.sum() == pytest.approx(t.stats[6])
+    for q in (ref, t):
+        assert q.stats[0] == 128 * n2 == q.n_phot_envoyes.sum()
+        assert q.stats[5] + q.stats[6] == q.stats[0]
+        assert q.sed.sum() == pytest.approx(q.stats[6])
     assert abs(t.xKJ_abs.sum() / ref.xKJ_abs.sum() - 1) < 0.01
     assert abs(t.stats[1] / ref.stats[1] - 1) < 0.01 and abs(t.stats[2] / ref.stats[2] - 1) < 0.01
     assert np.abs(t.sed_q).sum() > 0 and abs(np.abs(t.sed_q).sum() / np.abs(ref.sed_q).sum() - 1) < 0.1
-    assert d["parked"] > 0                        # the hand-over did happen
+    assert d["parked"] > 0 and d0["parked"] > 0   # the hand-over did happen
+    # per packet the three-launch call and the one-launch call are the same physics
+    assert abs(ref.stats[1] / ref.stats[0] / (small.stats[1] / small.stats[0]) - 1) < 0.02
+    assert abs(ref.xKJ_abs.sum() / ref.stats[0] / (small.xKJ_abs.sum() / small.stats[0]) - 1) < 0.02
     # SED mode counts received packets: no hand-over there, the call is unchanged
     s = G.mc_photon_loop(8, 8, 10 ** 9, 64.0, 1, False, letape_th=0, lmono=1)
     assert s.stats[0] == 128 * 64

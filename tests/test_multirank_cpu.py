@@ -44,5 +44,5 @@ def test_two_ranks_sum_to_one_rank(tmp_path):
     P = small_problems()["cyl2D"]()
     t = Oracle(P).run(n_threads=1, **KW)
     ref = np.concatenate([t.sed.ravel(order="F"), t.n_phot_sed.ravel(order="F"), t.n_phot_envoyes, t.stats])
-    assert got[-8] == ref[-8] == 128 * 20          # packets
+    assert got[-12] == ref[-12] == 128 * 20         # packets (stats[0] of 12)
     assert np.allclose(got, ref, rtol=1e-12, atol=0)

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from mcfost_b200 import synthetic as S, api
 
-os.environ.setdefault("MCB_BLOCKS", "4")
+
 P = S.multi_grain_like(n_photons_eq_th=20, n_rad=12, nz=8, n_rad_in=3, tau_mid=20.0)
 G = api.PhotonLoop(P)
 t = G.mc_photon_loop(1, 1, 20)                                                     # thermal variant
