@@ -5,9 +5,12 @@ ref4.1 disk at 1/2/4/8 B200 vs host OpenMP).
     python bench.py --gpus N --steps K --warmup W            # CUDA arm
     python bench.py --impl reference --gpus N --steps K ...   # host-core OpenMP arm
 
-One "step" = one thermal-mode pass of mc_photon_loop (dust_transfer.f90:439) over one batch of
-packets on the synthetic ref4.1-like model G1: 128 chunks x --n2 packets per GPU
-(weak scaling: chunks are dealt round-robin to ranks, n2 is scaled by the number of ranks).
+One "step" = one BLOCKING thermal-mode pass of mc_photon_loop (dust_transfer.f90:439) over one batch of
+packets on the synthetic ref4.1-like model G1: 128 chunks x --n2 packets per GPU (weak scaling:
+chunks are dealt round-robin to ranks, n2 is scaled by the number of ranks).  What a drop-in caller gets:
+one call at a time, nothing overlapped.  Besides the headline the line carries
+  sweep[]   the same call at 1.28e5 .. 1.28e8 packets (the reference arm runs the SAME budgets),
+  strong    (N > 1) the fixed 1.28e8-packet job split over the N ranks.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -27,26 +30,22 @@ import numpy as np  # noqa: E402
 
 METRIC = "photon packets/sec (ref4.1 disk, thermal mc_photon_loop)"
 UNIT = "packets/s"
+WORKLOAD = "G1 ref4.1-like: cylindrical 100x70x1, 50 lambda, n_T=100, thermal step, tau_mid(0.81um)=1e5, dark zone tau>1500"
 # SURVEY 8d algorithmic bytes: per cell-crossing step (2D cyl), per scattering, per absorption, per packet
 B_STEP, B_SCA, B_ABS = 112.0, 72.0, 112.0
+SWEEP_N2 = (1000, 10000, 100000, 1000000)          # x 128 chunks: 1.28e5 (the .para budget) .. 1.28e8 packets
 
 
 def b_packet(n_cells):
     return np.ceil(np.log2(n_cells)) * 8.0 + 96.0
 
 
-def measured_traffic(packets_per_launch):
-    """DRAM bytes per launch of the photon-loop kernel from the committed ncu launch list of this same
-    command (profiles/r01_traffic.json); None when it was taken at another packet budget."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+def _json(name):
     try:
-        with open(path) as f:
-            t = json.load(f)
-        if int(t["packets_per_launch"]) == int(packets_per_launch):
-            return float(t["dram_bytes_per_launch_mean"])
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return json.load(f)
     except Exception:
-        pass
-    return None
+        return None
 
 
 def peaks():
@@ -92,32 +91,36 @@ class ClockSampler(threading.Thread):
 FLAGS = dict(lsepar_pola=1, lsepar_contrib=1)
 
 
-def make_problem(args, walker_factory=None, world=1):
+def make_problem(n2_total, walker_factory=None):
     from mcfost_b200 import synthetic as S
-    P = S.ref41_like(n_photons_eq_th=args.n2 * world, dark_zone=False)      # L_packet_th = L_tot / (128 * n2 * world)
+    P = S.ref41_like(n_photons_eq_th=n2_total, dark_zone=False)      # L_packet_th = L_tot / (128 * n2_total)
     if walker_factory is not None:
         P.l_dark_zone = S.define_dark_zone(P, P.lambda_seuil, 1500.0, walker_factory(P))
         S.repartition_energie(P)
     return P
 
 
-def cpu_run(P, n2, threads=0, rank=0, n_ranks=1):
-    """oracle-OpenMP (reference restatement), timing flavour; returns (packets, seconds, stats, threads)."""
-    from oracle import binding
-    from oracle.binding import Oracle
-    O = Oracle(P, fast=True)
+def set_budget(P, n2_total):
+    from mcfost_b200 import synthetic as S
+    P.n_photons_eq_th = n2_total
+    S.repartition_energie(P)                   # same model, L_packet_th for this packet count
+
+
+def host_threads(O):
     # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
     # turn the OpenMP baseline into a single-thread run, so the affinity mask decides, not the environment
     try:
         avail = len(os.sched_getaffinity(0))
     except AttributeError:
         avail = os.cpu_count() or 1
-    nthr = threads or max(O.lib.oracle_max_threads(), avail)
-    O.run(n_threads=nthr, n_photons2=max(1, n2 // 50), **FLAGS)           # warm-up (thread pool, page faults)
+    return max(O.lib.oracle_max_threads(), avail)
+
+
+def cpu_run(O, n2, nthr, mrw):
+    """oracle-OpenMP (reference restatement), timing flavour; returns (packets, seconds)."""
     t0 = time.perf_counter()
-    t = O.run(n_threads=nthr, n_photons2=n2, **FLAGS)
-    dt = time.perf_counter() - t0
-    return float(t.stats[0]), dt, t.stats.copy(), nthr
+    t = O.run(n_threads=nthr, n_photons2=n2, lMRW=mrw, **FLAGS)
+    return float(t.stats[0]), time.perf_counter() - t0
 
 
 def reference_arm(args):
@@ -130,21 +133,32 @@ def reference_arm(args):
     except Exception:
         binding.build()
     from oracle.binding import Oracle
-    args.n2 = args.cpu_n2                      # the sample's own packet count sets L_packet_th
-    P = make_problem(args, lambda P: Oracle(P).dark_zone_walker())
     n2 = args.cpu_n2
+    P = make_problem(n2, lambda P: Oracle(P).dark_zone_walker())
+    O = Oracle(P, fast=True)
+    nthr = args.cpu_threads or host_threads(O)
+    cpu_run(O, max(1, n2 // 50), nthr, args.mrw)           # warm-up (thread pool, page faults)
     times, packets = [], 0.0
     for i in range(args.warmup + args.steps):
-        pk, dt, st, nthr = cpu_run(P, n2)
+        pk, dt = cpu_run(O, n2, nthr, args.mrw)
         if i >= args.warmup:
             times.append(dt); packets += pk
     total = sum(times)
     val = packets / total
+    # the budgets of the GPU arm's sweep, same packet counts (the largest is bounded by --cpu-sweep-max)
+    sweep = []
+    for s2 in SWEEP_N2:
+        if 128 * s2 > args.cpu_sweep_max:
+            sweep.append({"packets": 128 * s2, "value": None, "note": "skipped: above --cpu-sweep-max (host time)"})
+            continue
+        set_budget(P, s2); O.set_emission(P)
+        pk, dt = cpu_run(O, s2, nthr, args.mrw)
+        sweep.append({"packets": int(pk), "value": pk / dt, "ms": 1e3 * dt})
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "G1 ref4.1-like: cylindrical 100x70x1, 50 lambda, n_T=100, thermal step, tau_mid(0.81um)=1e5, dark zone tau>1500",
-                       "packets_per_step": int(128 * n2)},
+            "config": {"workload": WORKLOAD, "packets_per_step": int(128 * n2), "lMRW": int(args.mrw)},
+            "sweep": sweep,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthr, "kind": "port",
                              "sample": f"oracle-OpenMP (reference restatement, the Fortran cannot be built here), {128 * n2} packets per step, schedule(dynamic,1) over 128 chunks"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -168,78 +182,71 @@ def gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    P = make_problem(args, world=world)
+    P = make_problem(args.n2 * world)
     loop = api.PhotonLoop(P, device=local, rank=rank, n_ranks=world)
     # dark zone via the library's own deterministic ray-walk kernel (define_dark_zone step 4)
     P.l_dark_zone = S.define_dark_zone(P, P.lambda_seuil, 1500.0, loop.dark_zone_walker())
     S.repartition_energie(P)
     loop.upload_dark_zone(P.l_dark_zone)
     loop.upload_emission(P)
-    # Two handles (own stream, own tallies, own constant bank) are used alternately so that the
-    # drain-out of step i (a few very long-lived packets, most SMs already free) overlaps the start of
-    # step i+1.  Every step is a complete, separately reduced mc_photon_loop call.
-    loops = [loop] + [api.PhotonLoop(P, device=local, rank=rank, n_ranks=world) for _ in range(max(1, args.pipeline) - 1)]
-    if len(loops) > 1 and args.overlap_sms > 0:
-        for l in loops:
-            l.set_overlap(args.overlap_sms, max(1, args.overlap_sms // (len(loops) - 1)))   # main launches leave these SMs to the straggler launches of the other handles
     dev = torch.device("cuda", local)
-    n2 = args.n2 * world                      # weak scaling: 128/world chunks x (n2*world) packets per rank
-    streams = [torch.cuda.ExternalStream(l.stream(), device=dev) for l in loops]
-    views = [None] * len(loops)
+    stream = torch.cuda.ExternalStream(loop.stream(), device=dev)
+    flags = dict(FLAGS, lMRW=int(args.mrw))
+    view = [None]
 
-    def step(i, call_index):
-        k = i % len(loops)
-        loops[k].launch(1, 1, n2, 1.0e30, 1, call_index=call_index, reset_tallies=1, **FLAGS)
+    def reduce_tallies():
         if world > 1:
-            if views[k] is None:
-                v64, _ = loops[k].tally_buffers()
-                views[k] = torch.as_tensor(v64, device=dev)
-            with torch.cuda.stream(streams[k]):
-                dist.all_reduce(views[k], op=dist.ReduceOp.SUM)     # one NCCL all-reduce per call
+            if view[0] is None:
+                v64, _ = loop.tally_buffers()
+                view[0] = torch.as_tensor(v64, device=dev)
+            with torch.cuda.stream(stream):
+                dist.all_reduce(view[0], op=dist.ReduceOp.SUM)     # one NCCL all-reduce per call
+
+    def step(n2, call_index):
+        """one blocking call: launch, (all-reduce,) wait"""
+        loop.launch(1, 1, n2, 1.0e30, 1, call_index=call_index, reset_tallies=1, **flags)
+        reduce_tallies()
+        loop.sync()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        for l in loops:
-            l.sync()
+        loop.sync()
 
+    def timed(n2, k, first_index):
+        """k blocking calls back to back: device time (CUDA events on the library's stream), max over ranks"""
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for i in range(k):
+            step(n2, first_index + i)
+        ev1.record(stream)
+        barrier()
+        tm = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        return float(tm[0])
+
+    n2 = args.n2 * world                      # weak scaling: 128/world chunks x (n2*world) packets per rank
     for i in range(args.warmup):
-        step(i, i)
-    barrier()
+        step(n2, i)
     sampler = ClockSampler(local)
     sampler.start()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ends = [torch.cuda.Event(enable_timing=True) for _ in loops]
-    ev0.record(streams[0])
-    for s_ in streams[1:]:
-        s_.wait_event(ev0)
-    for i in range(args.steps):
-        step(i, args.warmup + i)
-    for e_, s_ in zip(ends, streams):
-        e_.record(s_)
-    barrier()
+    dev_ms = timed(n2, args.steps, args.warmup)
     sampler.stop_flag = True
-    dev_ms = max(ev0.elapsed_time(e_) for e_ in ends)
-    # stats of the last step (whole-job counts after the all-reduce), for the roofline
-    t_last = loops[(args.steps - 1) % len(loops)].download(want_xI=False)
-    stats = t_last.stats.copy()
-    tm = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    dev_ms = float(tm[0])
-    last_ms = dev_ms / args.steps             # average device time per launch over the timed region
-    packets_per_step = 128 * args.n2 * world          # whole job
+    d_last = loop.debug_counters()
+    launches_per_step = 4 if 128 * n2 // world > 2000000 else 1       # packet-per-warp + counter hand-over + packet-per-lane + packet-per-warp (stragglers); small budgets: packet-per-warp alone
+    t_last = loop.download(want_xI=False)
+    stats = t_last.stats.copy()                # whole-job counts after the all-reduce
+    packets_per_step = 128 * args.n2 * world
     value = packets_per_step * args.steps / (dev_ms * 1e-3)
+    last_ms = dev_ms / args.steps
 
-    # ---- e2e: the same calls through the C ABI with HOST buffers inside the timed region.  Every step uploads its
-    # emission tables from host memory (repartition_energie output changes every temperature iteration / wavelength:
-    # mcfost_b200_upload_emission), launches (mcfost_b200_launch), and its tallies are brought back to host arrays
-    # (mcfost_b200_sync + mcfost_b200_download).  The handles are used in turn exactly as in the device-timed loop, so
-    # the download of step i overlaps the run of step i+1; nothing is created on the device.
-    e2e_steps = args.steps
-    # the host copies of the emission tables live in PINNED memory for the e2e loop (the ctypes layer passes the
-    # arrays through untouched when dtype and Fortran layout already match)
+    # ---- e2e: the same blocking calls through the C ABI with HOST buffers inside the timed region.  Every step uploads
+    # its emission tables from pinned host memory (repartition_energie output changes every temperature iteration:
+    # mcfost_b200_upload_emission), runs (mcfost_b200_launch + all-reduce + mcfost_b200_sync) and brings its tallies back
+    # to host arrays (mcfost_b200_download).  Nothing is created on the device, nothing overlaps.
     pinned_keep = []
 
     def pin(a, dtype):
@@ -253,35 +260,64 @@ def gpu_arm(args):
     for nm in ("spectre_emission_cumul", "frac_E_stars", "frac_E_disk", "prob_E_cell"):
         setattr(P, nm, pin(getattr(P, nm), np.float64))
     P.CDF_E_star = pin(P.CDF_E_star, np.float32)
+    tally_names = ("xKJ_abs", "xT_ech", "n_phot_envoyes", "sed", "sed_q", "sed_u", "sed_v", "n_phot_sed",
+                   "sed_star", "sed_star_scat", "sed_disk", "sed_disk_scat", "stats")
+
+    def e2e_call(n2_, call_index):
+        loop.upload_emission(P)
+        h2d_ = sum(a.nbytes for a in loop._e.keep.values())
+        step(n2_, call_index)
+        t = loop.download(want_xI=False)
+        d2h_ = sum(getattr(t, nm).nbytes for nm in tally_names)
+        return h2d_, d2h_
+
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
-    pending = [None] * len(loops)
-    for i in range(e2e_steps + len(loops)):
-        k = i % len(loops)
-        if pending[k] is not None:
-            loops[k].sync()
-            t = loops[k].download(pending[k], want_xI=False)
-            d2h = sum(getattr(t, nm).nbytes for nm in ("xKJ_abs", "xT_ech", "n_phot_envoyes", "sed", "sed_q", "sed_u", "sed_v", "n_phot_sed",
-                                                       "sed_star", "sed_star_scat", "sed_disk", "sed_disk_scat", "stats"))
-            pending[k] = None
-        if i < e2e_steps:
-            loops[k].upload_emission(P)
-            h2d = sum(a.nbytes for a in loops[k]._e.keep.values())
-            step(i, 1000 + i)
-            pending[k] = loops[k]._last_run
+    for i in range(args.steps):
+        h2d, d2h = e2e_call(n2, 1000 + i)
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = packets_per_step * e2e_steps / float(te[0])
+    e2e_val = packets_per_step * args.steps / float(te[0])
+
+    # ---- strong scaling (N > 1): the fixed 1.28e8-packet job over the N ranks (128/N chunks x n2 packets per rank)
+    strong = None
+    if world > 1:
+        set_budget(P, args.n2); loop.upload_emission(P)
+        step(args.n2, 3000)
+        s_ms = timed(args.n2, args.strong_steps, 3001)
+        strong = {"scaling": "strong", "packets_per_step": int(128 * args.n2), "steps": args.strong_steps,
+                  "ms_per_step": s_ms / args.strong_steps, "value": 128 * args.n2 * args.strong_steps / (s_ms * 1e-3), "unit": UNIT}
+        set_budget(P, args.n2 * world)
+
+    # ---- budget sweep (N = 1): one blocking e2e call per budget, host buffers, best of 2 after one warm-up call
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        sweep = []
+        for s2 in SWEEP_N2:
+            set_budget(P, s2)
+            e2e_call(s2, 4000)
+            best, best_dev = 1e30, 0.0
+            for rep in range(2):
+                t1 = time.perf_counter()
+                e2e_call(s2, 4001 + rep)
+                dt = time.perf_counter() - t1
+                if dt < best:
+                    best, best_dev = dt, loop.last_kernel_ms()
+            sweep.append({"packets": 128 * s2, "value": 128 * s2 / best, "ms": 1e3 * best, "device_ms": best_dev})
+        set_budget(P, args.n2); loop.upload_emission(P)
 
     if rank == 0:
         peak, peak_src = peaks()
         nb = stats[1] * B_STEP + stats[3] * B_SCA + stats[4] * B_ABS + stats[0] * b_packet(P.n_cells)
         nb_per_gpu = nb / world
-        achieved = nb_per_gpu / (last_ms * 1e-3) / 1e9
+        hbm_achieved = nb_per_gpu / (last_ms * 1e-3) / 1e9
+        atomics_per_s = stats[1] / world / (last_ms * 1e-3)            # one fp64 reduction per crossed cell
+        l2 = _json("r02_l2_atomic.json")
+        traffic = _json("r02_traffic.json")
         cpu = None
         if world == 1 and not args.no_cpu:
             from oracle import binding
@@ -289,34 +325,48 @@ def gpu_arm(args):
                 binding.build(fast_native=True)
             except Exception:
                 binding.build()
+            from oracle.binding import Oracle
             import copy
             Pc = copy.copy(P)
-            Pc.n_photons_eq_th = args.cpu_n2
-            S.repartition_energie(Pc)                 # same model, L_packet_th for the sample's packet count
-            pk, dt, st, nthr = cpu_run(Pc, args.cpu_n2)
+            set_budget(Pc, args.cpu_n2)
+            O = Oracle(Pc, fast=True)
+            nthr = host_threads(O)
+            cpu_run(O, max(1, args.cpu_n2 // 50), nthr, args.mrw)
+            pk, dt = cpu_run(O, args.cpu_n2, nthr, args.mrw)
             cpu = {"value": pk / dt, "unit": UNIT, "cores": nthr, "kind": "port",
                    "sample": f"oracle-OpenMP (reference restatement), same model, {int(pk)} packets in {dt:.2f} s wall on {nthr} threads"}
+        if l2 and "g1_hits" in l2:
+            l2_peak = float(l2["g1_hits"]["red_f64_per_s"])
+            roof = {"bound": "l2_atomic", "achieved": atomics_per_s * 8e-9, "peak": l2_peak * 8e-9, "unit": "GB/s", "frac": atomics_per_s / l2_peak,
+                    "peak_source": "measured: red.global.add.f64 into 7000 L2-resident doubles with G1's per-cell crossing distribution (tools/l2_atomic_peak.cu, profiles/r02_l2_atomic.json); payload bytes of the reductions"}
+        else:
+            roof = {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak, "peak_source": peak_src}
+        roof.update({"traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                     "algorithmic_bytes_per_launch": nb_per_gpu, "hbm_algorithmic_GBps": hbm_achieved, "hbm_frac": hbm_achieved / peak,
+                     "kernel": "mc_photon_loop_kernel<GeomCyl<0,1>,1,BANK,0> (packet per lane) between two launches of mc_warp_engine_kernel (packet per warp)",
+                     "kernel_ms": last_ms,
+                     "phases_ms_last_call": {"packet_per_lane_dry": d_last["steady_ms"], "packet_per_lane_end": d_last["main_end_ms"],
+                                             "stragglers_start": d_last["straggler_start_ms"], "stragglers_end": d_last["straggler_end_ms"], "parked": d_last["parked"]},
+                     "note": "tables and tallies are L2 / shared-memory resident (DRAM traffic ~ 1e-4 of the algorithmic bytes): the ceiling is the L2 reduction rate and the issue rate of a divergent fp64 code, not HBM; hbm_frac is the formal algorithmic-bytes figure",
+                     "fp64_reductions_per_s": atomics_per_s, "steps_per_s": stats[1] / world / (last_ms * 1e-3), "interactions_per_s": stats[2] / world / (last_ms * 1e-3),
+                     "steps_per_packet": stats[1] / stats[0], "interactions_per_packet": stats[2] / stats[0], "mrw_steps_per_packet": stats[9] / stats[0]})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "G1 ref4.1-like: cylindrical 100x70x1, 50 lambda, n_T=100, thermal step, tau_mid(0.81um)=1e5, dark zone tau>1500",
-                           "packets_per_step": int(packets_per_step), "parallelism": f"packets x{world} (replicated grid, 1 all-reduce/step)", "pipeline": f"{len(loops)} handles alternate so that the drain-out of one step overlaps the next" + (f"; {args.overlap_sms} SMs reserved for the straggler launches" if len(loops) > 1 and args.overlap_sms > 0 else ""),
+                "config": {"workload": WORKLOAD, "packets_per_step": int(packets_per_step), "lMRW": int(args.mrw),
+                           "parallelism": f"packets x{world} (replicated grid, 1 all-reduce/step)",
+                           "calls": "one blocking call per step (launch + all-reduce + sync), nothing overlapped",
                            "l2_policy": "tallies are re-zeroed (memset) every step; working set is L2-resident by design (0.5 MB tables)"},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "host_buffers": "emission tables in pinned host memory (%d pinned arrays), tallies into host numpy arrays" % len(pinned_keep)},
-                "gpu_launches": int(args.steps * (3 if (len(loops) > 1 and args.overlap_sms > 0) else 2)),   # per step: mc_photon_loop_kernel (+ its straggler launch) + fill_int_kernel (xT_ech reset)
-                "clocks": sampler.summary(),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(packets_per_step / world),
-                             "algorithmic_bytes_per_launch": nb_per_gpu,
-                             "peak_source": peak_src, "kernel": "mc_photon_loop_kernel<GeomCyl<0,1>,1,BANK,0> (main + straggler launch)", "kernel_ms": last_ms,
-                             "launch_ms_last_call": loops[(args.steps - 1) % len(loops)].last_kernel_ms(),
-                             "note": "algorithmic bytes (SURVEY 8d) of one call / device time per call over the timed region (calls on the handles overlap, so one call's own launches last longer: launch_ms_last_call); tables are L2-resident so the path is latency/issue-bound, not HBM-bound",
-                             "steps_per_s": stats[1] / world / (last_ms * 1e-3), "interactions_per_s": stats[2] / world / (last_ms * 1e-3),
-                             "steps_per_packet": stats[1] / stats[0], "interactions_per_packet": stats[2] / stats[0]},
-                "cpu_baseline": cpu}
+                "gpu_launches": int(args.steps * (launches_per_step + 1)),   # + fill_int_kernel (xT_ech reset)
+                "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
+        if sweep is not None:
+            line["sweep"] = sweep
+        if strong is not None:
+            line["strong"] = strong
         print(json.dumps(line))
-    for l in loops:
-        l.close()
+    loop.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -329,9 +379,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n2", type=int, default=1000000, help="packets per chunk per GPU (128 chunks): 1.28e8 packets per step per GPU")
     ap.add_argument("--cpu-n2", type=int, default=8000, help="packets per chunk of the bounded CPU sample")
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--cpu-sweep-max", type=float, default=1.28e7, help="largest sweep budget the reference arm runs (1.28e8 takes minutes of host time)")
+    ap.add_argument("--mrw", type=int, default=0, help="1: modified random walk on (both arms); the reference's own behaviour is off")
+    ap.add_argument("--strong-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=2, help="handles used alternately (1 = strictly serial steps)")
-    ap.add_argument("--overlap-sms", type=int, default=16, help="SMs reserved for straggler launches when pipelining (0 = off)")
+    ap.add_argument("--no-sweep", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -408,6 +408,28 @@ int mcfost_b200_distance_to_closest_wall(mcb_handle *h, int64_t n, const int32_t
  * A, B, C are host arrays (n_T, p_n_cells).  Built on the device at the first lMRW call or here. */
 int mcfost_b200_mrw_tables(mcb_handle *h, double *A, double *B, double *C);
 
+/* ---- multi-GPU behind the boundary: ONE host process, the n GPUs of a node.  Grid and tables are
+ * replicated (the multi_upload_* calls upload to every GPU), GPU g runs the chunks c with (c-1) mod n == g, and
+ * mcfost_b200_multi_run merges EVERY tally of the call with one group of NCCL all-reduces over NVLink before it
+ * returns the merged tallies of GPU 0: sum for the packed fp64 block, xI_scatt, I_spec, I_spec_star, the photon maps,
+ * the origin tallies and xN_abs (sum(...,dim=id) in the reference: thermal_emission.f90:668, output.f90:3084-3102,
+ * dust_ray_tracing.f90:661,689); min for xT_ech (Temp_LTE with id = 0 starts from minval(xT_ech(icell,:)),
+ * thermal_emission.f90:683); max for xT_ech_1grain / xT_ech_1grain_nRE (maxval, :823, :977).  r->rank / r->n_ranks are
+ * set by the library.  NCCL (libnccl.so.2) is loaded at run time when n_gpus > 1. */
+typedef struct mcb_multi mcb_multi;
+int  mcfost_b200_multi_init(int n_gpus, const int *devices /* NULL: 0..n_gpus-1 */, mcb_multi **m);
+void mcfost_b200_multi_finalize(mcb_multi *m);
+const char *mcfost_b200_multi_last_error(const mcb_multi *m);
+int  mcfost_b200_multi_n_gpus(const mcb_multi *m);
+mcb_handle *mcfost_b200_multi_handle(mcb_multi *m, int i);      /* the per-GPU handle (deterministic kernels, diagnostics) */
+int mcfost_b200_multi_upload_grid(mcb_multi *m, const mcb_grid *g);
+int mcfost_b200_multi_upload_dark_zone(mcb_multi *m, const int32_t *l_dark_zone);
+int mcfost_b200_multi_upload_opacity(mcb_multi *m, const mcb_opacity *o);
+int mcfost_b200_multi_upload_emission(mcb_multi *m, const mcb_emission *e);
+int mcfost_b200_multi_upload_grains(mcb_multi *m, const mcb_grains *g);
+int mcfost_b200_multi_run(mcb_multi *m, const mcb_run_params *r, mcb_tallies *out);
+int mcfost_b200_multi_temp_finale(mcb_multi *m, float *Tdust);
+
 #ifdef __cplusplus
 }
 #endif

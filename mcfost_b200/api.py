@@ -30,6 +30,10 @@ EXPORTS = (
     "mcfost_b200_cross_cell", "mcfost_b200_index_cell", "mcfost_b200_move_to_grid",
     "mcfost_b200_optical_length_tot", "mcfost_b200_physical_length",
     "mcfost_b200_distance_to_closest_wall", "mcfost_b200_mrw_tables",
+    "mcfost_b200_multi_init", "mcfost_b200_multi_finalize", "mcfost_b200_multi_last_error", "mcfost_b200_multi_n_gpus",
+    "mcfost_b200_multi_handle", "mcfost_b200_multi_upload_grid", "mcfost_b200_multi_upload_dark_zone",
+    "mcfost_b200_multi_upload_opacity", "mcfost_b200_multi_upload_emission", "mcfost_b200_multi_upload_grains",
+    "mcfost_b200_multi_run", "mcfost_b200_multi_temp_finale",
 )
 
 
@@ -313,3 +317,71 @@ class PhotonLoop:
         def walk(lam, x, y, z, u, v, w, icell, tau, dark):
             return self.physical_length(lam, x, y, z, u, v, w, icell, tau, dark)["flag_sortie"].astype(bool)
         return walk
+
+
+class MultiPhotonLoop:
+    """The n GPUs of one node behind ONE object and one call (mcfost_b200_multi_*): grid and tables replicated,
+    chunks dealt round-robin, every tally merged by NCCL inside the library before the call returns."""
+
+    def __init__(self, P, n_gpus, devices=None):
+        self.lib = load_library()
+        L = self.lib
+        L.mcfost_b200_multi_init.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.mcfost_b200_multi_finalize.argtypes = [C.c_void_p]; L.mcfost_b200_multi_finalize.restype = None
+        L.mcfost_b200_multi_last_error.argtypes = [C.c_void_p]; L.mcfost_b200_multi_last_error.restype = C.c_char_p
+        L.mcfost_b200_multi_handle.argtypes = [C.c_void_p, C.c_int]; L.mcfost_b200_multi_handle.restype = C.c_void_p
+        for fn in ("upload_grid", "upload_dark_zone", "upload_opacity", "upload_emission", "upload_grains", "temp_finale"):
+            getattr(L, "mcfost_b200_multi_" + fn).argtypes = [C.c_void_p, C.c_void_p]
+        L.mcfost_b200_multi_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self.P, self.n_gpus = P, int(n_gpus)
+        self.m = C.c_void_p()
+        dev = None if devices is None else np.ascontiguousarray(devices, np.int32)
+        rc = L.mcfost_b200_multi_init(self.n_gpus, _p(dev), C.byref(self.m))
+        if rc != 0:
+            raise McfostB200Error(rc, "multi_init failed (no such devices, or libnccl.so.2 not found): " + L.mcfost_b200_last_error(None).decode())
+        self._g = abi.make_grid(P); self._check(L.mcfost_b200_multi_upload_grid(self.m, self._g.ref()))
+        self._o = abi.make_opacity(P); self._check(L.mcfost_b200_multi_upload_opacity(self.m, self._o.ref()))
+        self.upload_dark_zone(getattr(P, "l_dark_zone", None))
+        self._e = None
+        if hasattr(P, "prob_E_cell"):
+            self.upload_emission(P)
+        self._gr = None
+        if hasattr(P, "n_grains_tot"):
+            self._gr = abi.make_grains(P); self._check(L.mcfost_b200_multi_upload_grains(self.m, self._gr.ref()))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise McfostB200Error(rc, self.lib.mcfost_b200_multi_last_error(self.m).decode())
+
+    def upload_dark_zone(self, dz):
+        a = None if dz is None else np.ascontiguousarray(dz, np.int32)
+        self._check(self.lib.mcfost_b200_multi_upload_dark_zone(self.m, _p(a)))
+
+    def upload_emission(self, P):
+        self._e = abi.make_emission(P)
+        self._check(self.lib.mcfost_b200_multi_upload_emission(self.m, self._e.ref()))
+
+    def mc_photon_loop(self, lambda_in=1, p_lambda_in=1, n_photons2=1000, n_phot_lim=1.0e30, nnfot1_start=1, laffichage=False, **flags):
+        flags = dict(flags)
+        flags.setdefault("n_photons_loop", getattr(self.P, "n_photons_loop", 128))
+        r = abi.make_run(lambda_in=lambda_in, p_lambda_in=p_lambda_in, n_photons2=n_photons2, n_phot_lim=n_phot_lim,
+                         nnfot1_start=nnfot1_start, laffichage=int(laffichage), **flags)
+        t = PhotonLoop._tallies(self, r)
+        self._check(self.lib.mcfost_b200_multi_run(self.m, r.ref(), t.ref()))
+        return t
+
+    def temp_finale(self):
+        T = np.zeros(self.P.n_cells, np.float32)
+        self._check(self.lib.mcfost_b200_multi_temp_finale(self.m, _p(T)))
+        return T
+
+    def close(self):
+        if getattr(self, "m", None) is not None and self.m:
+            self.lib.mcfost_b200_multi_finalize(self.m)
+            self.m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

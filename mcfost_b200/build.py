@@ -15,7 +15,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 #   api.cu       host API + deterministic sub-kernels: --fmad=false so that geometry is bit-exact
 #                against the reference's non-contracted arithmetic (DESIGN.md "precision")
 #   mc_kernel.cu the Monte Carlo photon-loop kernel: FMA contraction allowed (statistical path)
-UNITS = [("api.cu", ["--fmad=false"]), ("mc_kernel.cu", [])]
+#   multi.cu     multi-GPU driver (host code only; NCCL is dlopened at run time)
+UNITS = [("api.cu", ["--fmad=false"]), ("mc_kernel.cu", []), ("multi.cu", [])]
 
 
 def sources():
@@ -48,13 +49,14 @@ def build(force=False, verbose=False, defs=(), out=None):
     for cmd, pr in procs:
         if pr.wait() != 0:
             raise subprocess.CalledProcessError(pr.returncode, cmd)
-    subprocess.run(["nvcc", "-shared", "-o", lib] + objs, check=True, cwd=CSRC)
+    subprocess.run(["nvcc", "-shared", "-o", lib] + objs + ["-ldl"], check=True, cwd=CSRC)
     return lib
 
 
 if __name__ == "__main__":
     import sys
     if len(sys.argv) > 1 and sys.argv[1] == "dev":
-        print(build(force=True, verbose=True, defs=("MCB_DEV", "MCB_DEV_CYL2D_ONLY") + tuple(sys.argv[2:]), out="libmcfost_b200_dev.so"))
+        print(build(force=True, verbose=True, defs=("MCB_DEV", "MCB_DEV_CYL2D_ONLY") + tuple(sys.argv[2:]),
+                    out=os.environ.get("MCB_DEV_OUT", "libmcfost_b200_dev.so")))
     else:
         print(build(force=True, verbose=True))

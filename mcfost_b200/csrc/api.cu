@@ -2,6 +2,7 @@
 // ownership, uploads, kernel launches, tally download.  There is NO CPU
 // fallback anywhere in this library: without a CUDA device every entry point
 // fails with MCB_ERR_NO_DEVICE.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -176,6 +177,39 @@ int mcfost_b200_upload_grid(mcb_handle* h, const mcb_grid* g) {
     }
     if ((rc = put(h, "vor_xyz32", x32.data(), x32.size(), &m.vor_xyz32))) return rc;
     if ((rc = put(h, "vor_flags", fl.data(), fl.size(), &m.vor_flags))) return rc;
+    // uniform grid over the seeds for point location (GeomVor::index; the reference's kd-tree, Voronoi.f90:1625-1645):
+    // ~4 seeds per grid cell, ids ascending inside a cell (counting sort keeps the order of the ids)
+    m.vg_start = nullptr; m.vg_items = nullptr;
+    std::vector<int> vg_start, vg_items;
+    if (g->n_cells >= 64) {
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      for (int i = 0; i < g->n_cells; ++i) for (int a = 0; a < 3; ++a) { const double q = g->vor_xyz[3 * (size_t)i + a]; lo[a] = std::min(lo[a], q); hi[a] = std::max(hi[a], q); }
+      const double per_axis = std::cbrt((double)g->n_cells / 4.0);
+      size_t ng = 1;
+      for (int a = 0; a < 3; ++a) {
+        const double ext = std::max(hi[a] - lo[a], 1e-300);
+        m.vg_n[a] = std::max(1, std::min(1024, (int)per_axis));
+        m.vg_lo[a] = lo[a]; m.vg_step[a] = ext / m.vg_n[a] * (1.0 + 1e-12); m.vg_inv[a] = 1.0 / m.vg_step[a];
+        ng *= (size_t)m.vg_n[a];
+      }
+      auto cell_of = [&](int i) {
+        size_t gidx = 0, mul = 1;
+        for (int a = 0; a < 3; ++a) {
+          const double q = std::floor((g->vor_xyz[3 * (size_t)i + a] - m.vg_lo[a]) * m.vg_inv[a]);
+          const int c = q < 0.0 ? 0 : (q >= (double)m.vg_n[a] ? m.vg_n[a] - 1 : (int)q);
+          gidx += mul * (size_t)c; mul *= (size_t)m.vg_n[a];
+        }
+        return gidx;
+      };
+      vg_start.assign(ng + 1, 0);
+      for (int i = 0; i < g->n_cells; ++i) ++vg_start[cell_of(i) + 1];
+      for (size_t c = 0; c < ng; ++c) vg_start[c + 1] += vg_start[c];
+      vg_items.resize((size_t)g->n_cells);
+      std::vector<int> fill(vg_start.begin(), vg_start.end() - 1);
+      for (int i = 0; i < g->n_cells; ++i) vg_items[(size_t)fill[cell_of(i)]++] = i + 1;
+      if ((rc = put(h, "vg_start", vg_start.data(), vg_start.size(), &m.vg_start))) return rc;
+      if ((rc = put(h, "vg_items", vg_items.data(), vg_items.size(), &m.vg_items))) return rc;
+    }
     CK(cudaStreamSynchronize(h->stream));       // x32 / fl are stack-owned
     memcpy(m.wall, g->wall_x, sizeof m.wall);
     m.cut_o_h = g->cutting_distance_o_h;
@@ -617,7 +651,7 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   // (the flight-start slab of capteur_full is not part of a parked packet: no hand-over in those modes)
   dr.park_enable = 0;      // set by mcb_launch_mc for the kernels that hand their last packets over
   dr.patience = 8;
-  dr.park_live = 256;
+  dr.park_live = 48;      // measured (profiles/r02_tail.md): the packet-per-lane kernel drains faster than the packet-per-warp kernel down to ~50 packets per SM
   dr.debug_abort_dry = 0;
 #ifdef MCB_DEV      // development builds only: a science library does not change its results on an environment variable
   { const char* e = getenv("MCB_PATIENCE"); if (e && atoi(e) > 0 && atoi(e) <= 4096) dr.patience = atoi(e); }

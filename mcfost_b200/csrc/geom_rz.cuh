@@ -175,6 +175,95 @@ struct GeomCyl {
     return c;
   }
 
+#ifdef MCB_BRANCHY_DISTANCE      // round-1 form, kept for A/B timing
+  // ---- wall-distance half of cross_cylindrical_cell (:941-1094): which wall, how far ----
+  static __device__ __forceinline__ HitRZ distance(const DevModel& m, DirInv d, double x0, double y0, double z0,
+                                                   double u, double v, double w, Cell c, Cell /*prev*/) {
+    const double correct_moins = 1.0 - MCB_GRID_PREC, correct_plus = 1.0 + MCB_GRID_PREC;
+    const int ri0 = c.ri, zj0 = c.zj, k0 = c.k;
+    double s, t, t_phi;
+    HitRZ h; h.d_rad = 1; h.d_j = 0; h.d_phi = 0;
+    const double r_2 = x0 * x0 + y0 * y0;
+    const double b = (x0 * u + y0 * v) * d.inv_a;
+
+    if (ri0 == 0) {
+      double cc = (r_2 - r_lim_2<SM>(m, 0)) * d.inv_a;
+      double rac = sqrt(b * b - cc);
+      s = (-b + rac) * correct_plus;
+      t = MCB_HUGE_REAL; t_phi = MCB_HUGE_REAL;
+    } else {
+      // 1) radial wall
+      double dotprod = u * x0 + v * y0, delta;
+      if (dotprod < 0.0) {
+        double cc = (r_2 - r_lim_2<SM>(m, ri0 - 1) * correct_moins) * d.inv_a;
+        delta = b * b - cc;
+        if (delta < 0.0) {
+          cc = (r_2 - r_lim_2<SM>(m, ri0) * correct_plus) * d.inv_a;
+          delta = fmax(b * b - cc, 0.0);
+        } else h.d_rad = -1;
+      } else {
+        double cc = (r_2 - r_lim_2<SM>(m, ri0) * correct_plus) * d.inv_a;
+        delta = fmax(b * b - cc, 0.0);
+      }
+      double rac = sqrt(delta);
+      s = (-b - rac) * correct_plus;
+      if (s < 0.0) s = (-b + rac) * correct_plus;
+      else if (s == 0.0) s = MCB_GRID_PREC;
+
+      // 2) horizontal wall
+      dotprod = w * z0;
+      if (dotprod == 0.0) t = (double)1.0e10f;
+      else {
+        const int aj = zj0 < 0 ? -zj0 : zj0;
+        double zlim;
+        if (dotprod > 0.0) {
+          if (aj == m.nz + 1) { h.d_j = 0; zlim = copysign(1.0e10, z0); }
+          else {
+            zlim = copysign(z_lim<SM>(m, ri0, aj + 1) * correct_plus, z0);
+            h.d_j = (L3D && z0 < 0.0) ? -1 : 1;
+          }
+        } else {
+          if (L3D) {
+            if (z0 > 0.0) { zlim = z_lim<SM>(m, ri0, aj) * correct_moins; h.d_j = (zj0 == 1) ? -2 : -1; }
+            else { zlim = -z_lim<SM>(m, ri0, aj) * correct_moins; h.d_j = (zj0 == -1) ? 2 : 1; }
+          } else {
+            if (zj0 == 1) {          // midplane mirror in 2D
+              h.d_j = 1;
+              zlim = (z0 > 0.0) ? -z_lim<SM>(m, ri0, 2) * correct_moins : z_lim<SM>(m, ri0, 2) * correct_moins;
+            } else {
+              zlim = (z0 > 0.0) ? z_lim<SM>(m, ri0, zj0) * correct_moins : -z_lim<SM>(m, ri0, zj0) * correct_moins;
+              h.d_j = -1;
+            }
+          }
+        }
+        t = (zlim - z0) * d.inv_w;
+        if (t < 0.0) t = MCB_GRID_PREC;
+      }
+
+      // 3) azimuthal wall
+      if (L3D) {
+        dotprod = x0 * v - y0 * u;
+        if (fabs(dotprod) < (double)1.0e-10f) t_phi = (double)1.0e30f;
+        else {
+          double tan_angle_lim;
+          if (dotprod > 0.0) { tan_angle_lim = tan_phi_lim<SM>(m, k0); h.d_phi = 1; }
+          else { int km = k0 - 1; if (km == 0) km = m.n_az; tan_angle_lim = tan_phi_lim<SM>(m, km); h.d_phi = -1; }
+          if (tan_angle_lim > 1.0e299) t_phi = (fabs(u) > (double)1e-6f) ? -x0 / u : (double)1.0e30f;
+          else {
+            double den = v - u * tan_angle_lim;
+            t_phi = (fabs(den) > (double)1.0e-6f) ? -(y0 - x0 * tan_angle_lim) / den : (double)1.0e30f;
+          }
+          if (t_phi < 0.0) t_phi = (double)1.0e30f;
+        }
+      } else t_phi = MCB_HUGE_REAL;
+    }
+    if ((s < t) && (s < t_phi)) { h.l = s; h.which = 0; }
+    else if (t < t_phi) { h.l = t; h.which = 1; }
+    else { h.l = t_phi; h.which = 2; }
+    return h;
+  }
+
+#else
   // ---- wall-distance half of cross_cylindrical_cell (:941-1094): which wall, how far ----
   // Written with selects instead of the reference's nested ifs: a warp's 32 packets sit in different cells and fly in
   // different directions, so every two-sided test of the Fortran (inward / outward, up / down, above / below the
@@ -257,6 +346,7 @@ struct GeomCyl {
     return h;
   }
 
+#endif
   // exit point on the wall (:1100-1165)
   static __device__ __forceinline__ void exit_point(const HitRZ& h, double x0, double y0, double z0, double u, double v, double w,
                                                     double& x1, double& y1, double& z1) {

@@ -36,14 +36,54 @@ struct GeomVor {
   static __device__ __forceinline__ bool is_in_volume(const DevModel& m, double x, double y, double z) {
     return (x > m.wall[0][3]) && (x < m.wall[1][3]) && (y > m.wall[2][3]) && (y < m.wall[3][3]) && (z > m.wall[4][3]) && (z < m.wall[5][3]);
   }
-  // O(n_cells) nearest seed with fp32 distances (reference behaviour; only reached on
-  // the rounding fallback of cross and on entry from outside)
+  // index_cell_voronoi (Voronoi.f90:1548-1572): nearest seed, distances rounded to fp32, strict `<` in a loop over
+  // ascending ids (ties go to the lowest id).  The reference scans all n_cells seeds (and finds entry cells with a
+  // kd-tree, :1625-1645); here the seeds are binned in a uniform grid at upload and the search visits the shells of grid
+  // cells around the point until no unvisited cell can hold a closer seed.  Same result as the O(n) scan (checked
+  // against the oracle's brute force); a shell is only skipped when its nearest face is farther than the best
+  // distance plus the fp32 rounding margin.
+  static __device__ __forceinline__ void index_try(const DevModel& m, int id, double x, double y, double z, float& best, int& ic) {
+    const double dx = __ldg(m.vor_xyz + 3 * (size_t)(id - 1)) - x, dy = __ldg(m.vor_xyz + 3 * (size_t)(id - 1) + 1) - y, dz = __ldg(m.vor_xyz + 3 * (size_t)(id - 1) + 2) - z;
+    const float d2 = (float)(dx * dx + dy * dy + dz * dz);
+    if (d2 < best || (d2 == best && id < ic)) { best = d2; ic = id; }
+  }
   static __device__ int index(const DevModel& m, double x, double y, double z) {
     float best = FLT_MAX; int ic = 0;
-    for (int i = 0; i < m.n_cells; ++i) {
-      const double dx = __ldg(m.vor_xyz + 3 * (size_t)i) - x, dy = __ldg(m.vor_xyz + 3 * (size_t)i + 1) - y, dz = __ldg(m.vor_xyz + 3 * (size_t)i + 2) - z;
-      const float d2 = (float)(dx * dx + dy * dy + dz * dz);
-      if (d2 < best) { best = d2; ic = i + 1; }
+    if (!m.vg_start) {      // no grid (tiny meshes): plain scan
+      for (int i = 1; i <= m.n_cells; ++i) index_try(m, i, x, y, z, best, ic);
+      return ic;
+    }
+    const double p[3] = {x, y, z};
+    int c[3];
+    for (int a = 0; a < 3; ++a) {
+      const double q = floor((p[a] - m.vg_lo[a]) * m.vg_inv[a]);
+      c[a] = q < 0.0 ? 0 : (q >= (double)m.vg_n[a] ? m.vg_n[a] - 1 : (int)q);
+    }
+    const int rmax = max(max(m.vg_n[0], m.vg_n[1]), m.vg_n[2]);
+    for (int r = 0; r < rmax; ++r) {
+      // shell r: grid cells with max(|di|, |dj|, |dk|) == r
+      const int i0 = max(c[0] - r, 0), i1 = min(c[0] + r, m.vg_n[0] - 1);
+      const int j0 = max(c[1] - r, 0), j1 = min(c[1] + r, m.vg_n[1] - 1);
+      const int k0 = max(c[2] - r, 0), k1 = min(c[2] + r, m.vg_n[2] - 1);
+      for (int k = k0; k <= k1; ++k)
+        for (int j = j0; j <= j1; ++j) {
+          const bool edge_jk = (abs(k - c[2]) == r) || (abs(j - c[1]) == r);
+          const int step = edge_jk ? 1 : max(i1 - i0, 1);      // interior rows: only the two end cells belong to the shell
+          for (int i = i0; i <= i1; i += step) {
+            if (!edge_jk && abs(i - c[0]) != r) continue;
+            const int g = i + m.vg_n[0] * (j + m.vg_n[1] * k);
+            const int e1 = __ldg(m.vg_start + g + 1);
+            for (int e = __ldg(m.vg_start + g); e < e1; ++e) index_try(m, __ldg(m.vg_items + e), x, y, z, best, ic);
+          }
+        }
+      // can a cell outside the visited block [c - r, c + r] hold a closer seed?  distance from the point to the block's faces
+      double dmin = 1.0e300; bool open = false;
+      for (int a = 0; a < 3; ++a) {
+        if (c[a] - r > 0) { open = true; dmin = fmin(dmin, p[a] - (m.vg_lo[a] + (c[a] - r) * m.vg_step[a])); }
+        if (c[a] + r < m.vg_n[a] - 1) { open = true; dmin = fmin(dmin, (m.vg_lo[a] + (c[a] + r + 1) * m.vg_step[a]) - p[a]); }
+      }
+      if (!open) break;
+      if (ic > 0 && dmin > 0.0 && dmin * dmin > (double)best * (1.0 + 1.0e-5)) break;
     }
     return ic;
   }

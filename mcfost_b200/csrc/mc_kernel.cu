@@ -30,16 +30,15 @@ void mcb_forget_handle(const mcb_handle* h) {      // called by finalize after t
 
 __global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
 
-// Packets the packet-per-warp kernel sends before the packet-per-lane kernel takes over (thermal step).
-// The packet-per-lane kernel keeps up to 1024 packets per SM in flight; immediate re-emission reads RUNNING tallies, so
-// it is only started once `frac` x (packets sent) covers a useful number of packets in flight per block (its own
-// scheduler then caps the packets in flight at frac x sent, see DevRun::inflight_frac_per_block), and calls whose
-// whole budget is small are run by the low-latency kernel alone.
+// Thermal step: which kernel sends the packets.
+// The packet-per-lane kernel keeps up to 1024 packets per SM in flight and is throughput-oriented: ~5 us per event of
+// one packet.  A call whose whole budget is small is latency-bound from start to end (the longest packet chain decides)
+// and runs on the packet-per-warp kernel alone (~0.5 us per event, 16 packets in flight per SM); larger calls run on the
+// packet-per-lane kernel, whose scheduler ramps the packets in flight up with the packets sent (DevRun::inflight_*),
+// and only their last packets go to the packet-per-warp kernel.
 static unsigned long long engine_first_packets(unsigned long long n_total, int blocks, double frac) {
-  const double start_per_block = 128.0;                       // packets in flight per block at which the per-lane kernel starts
-  const unsigned long long s_a = (unsigned long long)std::ceil(start_per_block * blocks / frac);
-  if (n_total <= 4ull * s_a) return n_total;                  // small budget: latency-bound from start to end
-  return s_a;
+  const unsigned long long small = (unsigned long long)std::ceil(4.0 * 128.0 * blocks / frac);      // 1.2e6 packets on 148 SMs at 1/16
+  return n_total <= small ? n_total : 0ull;
 }
 
 template <class G, bool SM, int BANK, int VAR>
@@ -92,6 +91,12 @@ static int launch_bank(mcb_handle* h, DevRun dr) {
     if (c0 && h->buf_bytes["mrw_c0"] != bytes) { cudaFree(c0); c0 = nullptr; }
     if (!c0) { CK(cudaMalloc(&c0, bytes)); h->buf_bytes["mrw_c0"] = bytes; }
     h->m.mrw_c0 = (int*)c0;
+    void*& lr = h->bufs["mrw_lR"];
+    const size_t bytes_lr = (size_t)h->m.n_cells * 2 * sizeof(float);
+    if (lr && h->buf_bytes["mrw_lR"] != bytes_lr) { cudaFree(lr); lr = nullptr; }
+    if (!lr) { CK(cudaMalloc(&lr, bytes_lr)); h->buf_bytes["mrw_lR"] = bytes_lr; }
+    CK(cudaMemsetAsync(lr, 0, bytes_lr, h->stream));      // (a hint only; reset per call so that a call does not depend on the previous one)
+    h->m.mrw_lR = (float*)lr;
   }
   // the previous launch of this handle must be over before its constant bank is rewritten; so must the last
   // launch of any OTHER handle that maps to the same bank (more handles than banks)
@@ -112,9 +117,15 @@ static int launch_bank(mcb_handle* h, DevRun dr) {
   h->launches_last_call = 0;
   if constexpr (TH) {
     auto eng = mc_warp_engine_kernel<G, SM, BANK>;
-    if (smem_tables > 48 * 1024) CK(cudaFuncSetAttribute(eng, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
+    // the packet-per-warp kernel has no packet pool: kf_dark(n_cells) and, with constant dust, kdB_dT_CDF(n_lambda, n_T)
+    // are staged in the shared memory that frees, when they fit
+    int sm_kf = -1, sm_kdB = -1;
+    size_t smem_eng = smem_tables;
+    if (smem_eng + (size_t)h->m.n_cells * 8 <= 160 * 1024) { sm_kf = (int)(smem_eng / 8); smem_eng += (size_t)h->m.n_cells * 8; }
+    if (h->m.p_n_cells == 1 && smem_eng + (size_t)h->m.n_lambda * h->m.n_T * 8 <= 200 * 1024) { sm_kdB = (int)(smem_eng / 8); smem_eng += (size_t)h->m.n_lambda * h->m.n_T * 8; }
+    if (smem_eng > 48 * 1024) CK(cudaFuncSetAttribute(eng, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_eng));
     if (n_engine_first > 0) {
-      eng<<<h->n_sm, ENG_BLOCK, smem_tables, h->stream>>>(n_engine_first, 0);
+      eng<<<h->n_sm, ENG_BLOCK, smem_eng, h->stream>>>(n_engine_first, 0, sm_kf, sm_kdB);
       CK(cudaGetLastError());
       ++h->launches_last_call;
     }
@@ -132,7 +143,7 @@ static int launch_bank(mcb_handle* h, DevRun dr) {
         CK(cudaStreamWaitEvent(h->stream_hi, h->ev_main, 0));
         st2 = h->stream_hi;
       }
-      eng<<<h->n_sm, ENG_BLOCK, smem_tables, st2>>>(0ull, 1);
+      eng<<<h->n_sm, ENG_BLOCK, smem_eng, st2>>>(0ull, 1, sm_kf, sm_kdB);
       CK(cudaGetLastError());
       ++h->launches_last_call;
       if (overlap) {

@@ -88,6 +88,11 @@ struct DevModel {
   const uint8_t *vor_flags;         // bit0 was_cut, bit1 is_star, bit2 is_star_neighbour
   float wall[6][4];
   double cut_o_h;
+  // uniform grid over the seeds' bounding box for point location (the reference uses a kd-tree, Voronoi.f90:1625-1645):
+  // vg_start(0:nx*ny*nz), vg_items = seed ids (1-based, ascending inside a grid cell)
+  const int *vg_start, *vg_items;
+  int vg_n[3];
+  double vg_lo[3], vg_inv[3], vg_step[3];
   // ---- stars ------------------------------------------------------------
   int n_stars;
   double star[MAX_STARS][4];
@@ -123,6 +128,7 @@ struct DevModel {
   // modified random walk (MRW.f90): zeta(1:n_zeta), mean opacities A, B, C (n_T, p_n_cells), flight-start cell ids
   const double *zeta, *mrw_A, *mrw_B, *mrw_C;
   int *mrw_c0;              // (n_blocks, NP): cell id the flight in progress started in (dust_transfer.f90:1242)
+  float *mrw_lR;            // (2, n_cells): mean free path of the last walk evaluated in the cell (0 = none yet) and the temperature index it was evaluated at, see mrw_worth_trying
   SmemLayout sm;
   DevGrains gr;
 };

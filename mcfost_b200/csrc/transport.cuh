@@ -55,7 +55,8 @@ __constant__ DevRun c_rr[MCB_BANKS];
 // rarely used options; every such branch that merely sat behind a run-time flag cost instruction-cache footprint
 // and registers of the hot loop.
 enum { VAR_THERMAL = 0, VAR_GENERIC = 1, VAR_EXTRAS = 2 };
-enum { Q_EMIT = 0, Q_ABS = 1, Q_SCAT = 2, Q_FLY = 3, NQ = 4, Q_NONE = 7 };     // queue order = claim order (longest phases first)
+enum { Q_EMIT = 0, Q_ABS = 1, Q_SCAT = 2, Q_FLY = 3, Q_MRW = 4, NQ = 5, Q_NONE = 7 };
+enum { CTL_LIVE = 2 * NQ, CTL_BUSY, CTL_PARK, CTL_DRY, CTL_SENT };      // Pool::ctl: [0, NQ) heads, [NQ, 2 NQ) tails, then these
 enum { STAT_PACKETS = 0, STAT_STEPS, STAT_INTERACT, STAT_SCATT, STAT_ABS, STAT_KILLED, STAT_ESCAPED, STAT_BOUNCE, STAT_MRW_WALKS, STAT_MRW_STEPS };
 
 // ---- opacity / thermal table accessors (SM: shared-memory staging, p_n_cells == 1) ----
@@ -786,17 +787,17 @@ struct Pool {
   double* f;            // [NF64][NP]
   uint32_t* u;          // [NU32][NP]
   unsigned short* q;    // [NQ][NP] ring buffers of slot ids (0xFFFF = entry not written yet)
-  unsigned* ctl;        // [0..3] head[q]; [4..7] tail[q]; [8] live packets; [9] busy warps
+  unsigned* ctl;        // heads, tails, live packets, ... (CTL_* above)
   __device__ __forceinline__ double& F(int field, int slot) const { return f[field * NP + slot]; }
   __device__ __forceinline__ uint32_t& U(int field, int slot) const { return u[field * NP + slot]; }
   __device__ __forceinline__ volatile unsigned short* Q(int queue) const { return q + queue * NP; }
   __device__ __forceinline__ volatile unsigned& HEAD(int queue) const { return ctl[queue]; }
   __device__ __forceinline__ volatile unsigned& TAIL(int queue) const { return ctl[NQ + queue]; }
-  __device__ __forceinline__ volatile unsigned& LIVE() const { return ctl[8]; }
-  __device__ __forceinline__ volatile unsigned& BUSY() const { return ctl[9]; }
-  __device__ __forceinline__ volatile unsigned& PARK() const { return ctl[10]; }   // this block is handing its packets over
-  __device__ __forceinline__ volatile unsigned& DRYF() const { return ctl[11]; }   // the global packet counter ran dry
-  __device__ __forceinline__ volatile unsigned& SENT() const { return ctl[12]; }   // latest value of the global packet counter seen by this block (saturated)
+  __device__ __forceinline__ volatile unsigned& LIVE() const { return ctl[CTL_LIVE]; }
+  __device__ __forceinline__ volatile unsigned& BUSY() const { return ctl[CTL_BUSY]; }
+  __device__ __forceinline__ volatile unsigned& PARK() const { return ctl[CTL_PARK]; }   // this block is handing its packets over
+  __device__ __forceinline__ volatile unsigned& DRYF() const { return ctl[CTL_DRY]; }   // the global packet counter ran dry
+  __device__ __forceinline__ volatile unsigned& SENT() const { return ctl[CTL_SENT]; }   // latest value of the global packet counter seen by this block (saturated)
 };
 
 // misc word: lambda (13 bits) | star 1 | scatt 1 | ISM 1 | i_star_hit 4 | n_iteractions_in_cell 8 (saturating) | 4 spare.
@@ -841,7 +842,7 @@ template <bool SM, int BANK> __device__ __forceinline__ Pool make_pool() {
 
 struct Stats { unsigned int pk, steps, inter, sca, abs_, kill, esc, bounce, mrw_w, mrw_s; };
 // scheduling diagnostics (per warp, lane 0): chunk visits and valid lanes per phase
-struct SchedStats { unsigned int visits[NQ], lanes[NQ]; };
+struct SchedStats { unsigned int visits[NQ], lanes[NQ]; };      // (the first four are reported: EMIT, ABSORB, SCATTER, FLY)
 
 // Regrouping step: push the packets of this warp to the ring queue of their next phase (one shared-
 // memory atomic per destination queue).  Packets that leave the pool (no more work) decrement LIVE.
@@ -859,7 +860,7 @@ __device__ __forceinline__ void push_next(const Pool& P, int slot, int nextq, bo
     if (nextq == qi) P.Q(qi)[(base + __popc(mask & ((1u << lane) - 1u))) & (NP - 1)] = (unsigned short)slot;
   }
   const unsigned gone = __ballot_sync(0xffffffffu, valid && nextq == Q_NONE);
-  if (gone && lane == 0) atomicSub((unsigned*)&P.ctl[8], (unsigned)__popc(gone));
+  if (gone && lane == 0) atomicSub((unsigned*)&P.ctl[CTL_LIVE], (unsigned)__popc(gone));
 }
 
 // ---- begin flight `ev`: tau and the interaction-type draw from block 2*ev (dust_transfer.f90:1208-1215,1280),
@@ -908,6 +909,17 @@ __device__ __forceinline__ double sample_zeta(const DevModel& m, double zr) {
   return y0 * (1. - frac) + y1 * frac;
 }
 struct MrwOut { double x, y, z, u, v, w; int lambda; uint32_t ev; unsigned steps; };
+// Cheap pre-test of a walk: distance to the closest wall against the mean free path this cell had the last time a walk
+// was evaluated in it (0 = never: try).  Skipping an attempt is harmless -- the packet just makes ordinary flights, which
+// is what the walk stands for -- so a stale value only costs or saves time.  Most attempts fail (a packet that keeps
+// interacting in one cell usually sits near a wall of a moderately thick cell), and this keeps them at a few instructions.
+template <class G, int BANK>
+__device__ __forceinline__ bool mrw_worth_trying(typename G::CellT cell, int idx, double x, double y, double z) {
+  const DevModel& m = c_m; const DevRun& r = c_r;
+  const float2 c = __ldcg(reinterpret_cast<const float2*>(m.mrw_lR) + idx);      // (mean free path, temperature index it was evaluated at)
+  if (c.x == 0.0f || (int)c.y != __ldcg(m.xT_ech + idx)) return true;           // never evaluated, or the cell has warmed up since
+  return G::closest_wall(m, cell, x, y, z) > 0.8 * r.gamma_MRW * (double)c.x;
+}
 template <class G, bool SM, int BANK, bool WARP>
 __device__ __noinline__ MrwOut mrw_walk(typename G::CellT cell, int idx, int p_icell, double x, double y, double z, double S0,
                                         uint32_t pk_lo, uint32_t pk_hi, uint32_t ev) {
@@ -926,6 +938,7 @@ __device__ __noinline__ MrwOut mrw_walk(typename G::CellT cell, int idx, int p_i
   const double Cc = frac_T1 * __ldg(m.mrw_C + q1) + frac_T2 * __ldg(m.mrw_C + q2);
   if (!(A > 0.0) || !(B > 0.0)) return o;
   const double l_R = B / (A * kf);                  // Rosseland-type mean free path 1 / (rho chi_R)
+  if (leader) reinterpret_cast<float2*>(m.mrw_lR)[idx] = make_float2((float)l_R, (float)Ti);      // remembered per cell: the cheap pre-test of the next attempts (mrw_worth_trying)
   while (d > r.gamma_MRW * l_R && o.steps < 100000u) {
     const uint4 b = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), (2u * o.ev + 1u) | 0x40000000u, pk_lo, pk_hi, r.call_index);
     double u, v, w;
@@ -1331,26 +1344,18 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
         if (POLA && r.lmethod_aniso1) scatter_stokes<BANK>(lambda, itheta, rand2, p_icell, S, u, v, w, u1, v1, w1);
       }
       misc |= MISC_SCATT;                                    // flag_scatt
-      uint32_t evn = ev + 1u;
-      uint4 bn = bnext;
-      double px = P.F(F_PX, slot), py = P.F(F_PY, slot), pz = P.F(F_PZ, slot);
-      if (TH && r.lMRW && misc_n_in_cell(misc) > 5 && idx >= 0) {      // dust_transfer.f90:1222-1239
-        const MrwOut o = mrw_walk<G, SM, BANK, false>(cell, idx, p_icell, px, py, pz, S[0], pk_lo, pk_hi, evn);
-        if (o.steps) {
-          px = o.x; py = o.y; pz = o.z; u1 = o.u; v1 = o.v; w1 = o.w; S[1] = 0.0; S[2] = 0.0; S[3] = 0.0;
-          P.F(F_PX, slot) = px; P.F(F_PY, slot) = py; P.F(F_PZ, slot) = pz;
-          misc = pack_misc(o.lambda, false, false, false, 0, misc_n_in_cell(misc));
-          evn = o.ev; bn = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * evn, pk_lo, pk_hi, r.call_index);
-          ++st.mrw_w; st.mrw_s += o.steps;
-        }
-      }
       P.F(F_U, slot) = u1; P.F(F_V, slot) = v1; P.F(F_W, slot) = w1;
       if ((!TH && r.lmono) || POLA) { P.F(F_S0, slot) = S[0]; if (POLA) { QUV(0, slot) = S[1]; QUV(1, slot) = S[2]; QUV(2, slot) = S[3]; } }
-      P.U(U_EV, slot) = evn;
-      start_flight<BANK>(P, slot, px, py, pz, u1, v1, w1, bn, misc, cell);
-      if (GR && r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
+      P.U(U_EV, slot) = ev + 1u;
+      if (TH && r.lMRW && misc_n_in_cell(misc) > 5 && idx >= 0 &&
+          mrw_worth_trying<G, BANK>(cell, idx, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot))) {
+        nextq = Q_MRW;      // dust_transfer.f90:1222-1239: the walk has its own phase (MRW queue), which also starts the flight
+      } else {
+        start_flight<BANK>(P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u1, v1, w1, bnext, misc, cell);
+        if (GR && r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
+        nextq = Q_FLY;
+      }
       P.U(U_MISC, slot) = misc;
-      nextq = Q_FLY;
     }
   }
   return nextq;
@@ -1408,30 +1413,63 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
       random_isotropic_direction(u01(b.z), u01(b.w), u, v, w);
       if (POLA) { QUV(0, slot) = 0.0; QUV(1, slot) = 0.0; QUV(2, slot) = 0.0; }
       misc = pack_misc(lambda, false, false, false, 0, misc_n_in_cell(misc));      // flag_star = flag_scatt = flag_ISM = .false.
-      uint32_t evn = ev + 1u;
-      uint4 bn = bnext;
-      double px = P.F(F_PX, slot), py = P.F(F_PY, slot), pz = P.F(F_PZ, slot);
-      if (TH && r.lMRW && misc_n_in_cell(misc) > 5 && idx >= 0) {      // dust_transfer.f90:1222-1239
-        const MrwOut o = mrw_walk<G, SM, BANK, false>(cell, idx, p_icell, px, py, pz, P.F(F_S0, slot), pk_lo, pk_hi, evn);
-        if (o.steps) {
-          px = o.x; py = o.y; pz = o.z; u = o.u; v = o.v; w = o.w;
-          P.F(F_PX, slot) = px; P.F(F_PY, slot) = py; P.F(F_PZ, slot) = pz;
-          misc = pack_misc(o.lambda, false, false, false, 0, misc_n_in_cell(misc));
-          evn = o.ev; bn = philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * evn, pk_lo, pk_hi, r.call_index);
-          ++st.mrw_w; st.mrw_s += o.steps;
-        }
-      }
       P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;
-      P.U(U_EV, slot) = evn;
-      start_flight<BANK>(P, slot, px, py, pz, u, v, w, bn, misc, cell);
-      if (GR && r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
+      P.U(U_EV, slot) = ev + 1u;
+      if (TH && r.lMRW && misc_n_in_cell(misc) > 5 &&
+          mrw_worth_trying<G, BANK>(cell, idx, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot))) {
+        nextq = Q_MRW;      // dust_transfer.f90:1222-1239: the walk has its own phase (MRW queue), which also starts the flight
+      } else {
+        start_flight<BANK>(P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u, v, w, bnext, misc, cell);
+        if (GR && r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
+        nextq = Q_FLY;
+      }
       P.U(U_MISC, slot) = misc;
-      nextq = Q_FLY;
     }
   }
   if (GR && r.lnRE) {      // E_abs_nRE (omp reduction in the reference, dust_transfer.f90:489): one atomic per warp
     for (int o = 16; o > 0; o >>= 1) e_nRE += __shfl_down_sync(0xffffffffu, e_nRE, o);
     if (lane == 0 && e_nRE != 0.0) atomicAdd(m.tally + m.lay.E_abs_nRE, e_nRE);
+  }
+  return nextq;
+}
+
+// =============================================================================
+// MRW: the modified random walk of packets phase_absorb / phase_scatter found worth trying (dust_transfer.f90:1222-1239),
+// then the start of the next flight.  A phase of its own so that the 32 lanes of a warp all walk: inside ABSORB it
+// stalled the 31 other packets of the warp for the ~10 us of a walk.
+// =============================================================================
+template <class G, bool SM, int BANK, int VAR>
+__device__ __noinline__ int phase_mrw(int slot, bool valid, Stats& st) {
+  const DevModel& m = c_m; const DevRun& r = c_r;
+  const bool POLA = r.lsepar_pola != 0;
+  const Pool P = make_pool<SM, BANK>();
+  using CellT = typename G::CellT;
+  int nextq = Q_NONE;
+  if (valid) {
+    uint32_t misc = P.U(U_MISC, slot);
+    CellT cell; unpack_cell(P.U(U_C0A, slot), P.U(U_C0B, slot), cell);
+    const int idx = tally_index(m, cell);
+    const bool variable_dust = !SM && m.p_n_cells != 1;
+    const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
+    const uint32_t pk_lo = P.U(U_PKLO, slot), pk_hi = P.U(U_PKHI, slot);
+    uint32_t ev = P.U(U_EV, slot);                    // number of the flight about to start
+    double px = P.F(F_PX, slot), py = P.F(F_PY, slot), pz = P.F(F_PZ, slot);
+    double u = P.F(F_U, slot), v = P.F(F_V, slot), w = P.F(F_W, slot);
+    if (idx >= 0) {
+      const MrwOut o = mrw_walk<G, SM, BANK, false>(cell, idx, p_icell, px, py, pz, P.F(F_S0, slot), pk_lo, pk_hi, ev);
+      if (o.steps) {
+        px = o.x; py = o.y; pz = o.z; u = o.u; v = o.v; w = o.w; ev = o.ev;
+        P.F(F_PX, slot) = px; P.F(F_PY, slot) = py; P.F(F_PZ, slot) = pz;
+        P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;
+        if (POLA) { QUV(0, slot) = 0.0; QUV(1, slot) = 0.0; QUV(2, slot) = 0.0; }
+        misc = pack_misc(o.lambda, false, false, false, 0, misc_n_in_cell(misc));
+        P.U(U_EV, slot) = ev;
+        ++st.mrw_w; st.mrw_s += o.steps;
+      }
+    }
+    start_flight<BANK>(P, slot, px, py, pz, u, v, w, philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev, pk_lo, pk_hi, r.call_index), misc, cell);
+    P.U(U_MISC, slot) = misc;
+    nextq = Q_FLY;
   }
   return nextq;
 }
@@ -1495,11 +1533,16 @@ mc_photon_loop_kernel(const int adopt) {
   // every slot starts in the EMIT queue (main launch: emits new packets; straggler launch: adopts parked ones)
   for (int i = threadIdx.x; i < NQ * NP; i += MC_BLOCK) P.q[i] = (i < NP) ? (unsigned short)i : (unsigned short)0xFFFFu;   // Q_EMIT == 0
   __syncthreads();
-  if (threadIdx.x == 0) { P.ctl[NQ + Q_EMIT] = NP; P.ctl[8] = NP; }
+  if (threadIdx.x == 0) { P.ctl[NQ + Q_EMIT] = NP; P.ctl[CTL_LIVE] = NP; }
   __syncthreads();
   const bool park_ok = r.park_enable && !adopt;
+  // preferred queue order of this warp, one nibble per rank (see the scheduling loop); EMIT stays first everywhere:
+  // free slots are refilled at once
+  const unsigned q_order = ((threadIdx.x >> 5) & 3u) == 0u ? (unsigned)(Q_EMIT | (Q_MRW << 4) | (Q_ABS << 8) | (Q_SCAT << 12) | (Q_FLY << 16))
+                         : ((threadIdx.x >> 5) & 3u) == 1u ? (unsigned)(Q_EMIT | (Q_MRW << 4) | (Q_SCAT << 8) | (Q_ABS << 12) | (Q_FLY << 16))
+                                                           : (unsigned)(Q_EMIT | (Q_FLY << 4) | (Q_ABS << 8) | (Q_SCAT << 12) | (Q_MRW << 16));
   Stats st = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  SchedStats ss = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  SchedStats ss = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
 #ifdef MCB_DRAIN_PROBE
   int probe_k = 0;
 #endif
@@ -1526,8 +1569,18 @@ mc_photon_loop_kernel(const int adopt) {
           const unsigned in_flight = live - (P.TAIL(Q_EMIT) - P.HEAD(Q_EMIT));
           emit_allow = cap > in_flight ? cap - in_flight : 0u;
         }
+        // Queue order by SM sub-partition (warp id mod 4): two sub-partitions look at FLY first, one at ABSORB, one at
+        // SCATTER, and each falls back to the other phases only when its own has no full chunk.  The phases are ~10-30 KB
+        // of code each; warps that stay in one phase keep hitting the instruction cache of their sub-partition
+        // (`no_instruction` was the top stall with every warp hopping between all phases).
+#ifndef MCB_NO_PHASE_AFFINITY
+        const unsigned order = q_order;
+#else
+        const unsigned order = 0x43210u;
+#endif
 #pragma unroll
-        for (int k = 0; k < NQ; ++k) {
+        for (int kk = 0; kk < NQ; ++kk) {
+          const int k = (int)((order >> (4 * kk)) & 15u);
           unsigned av = P.TAIL(k) - P.HEAD(k);
           if (k == Q_EMIT && av > emit_allow) av = emit_allow;
           if (av >= 32u) { best = k; best_n = 32u; break; }
@@ -1574,6 +1627,7 @@ mc_photon_loop_kernel(const int adopt) {
         case Q_EMIT: nextq = adopt ? phase_adopt<SM, BANK>(slot, mine) : phase_emit<G, SM, BANK, VAR>(slot, mine, st); break;
         case Q_ABS:  nextq = phase_absorb<G, SM, BANK, VAR>(slot, mine, st); break;
         case Q_SCAT: nextq = phase_scatter<G, SM, BANK, VAR>(slot, mine, st); break;
+        case Q_MRW:  if constexpr (VAR == VAR_THERMAL) nextq = phase_mrw<G, SM, BANK, VAR>(slot, mine, st); else nextq = Q_NONE; break;
         default:     nextq = phase_fly<G, SM, BANK, VAR>(slot, mine, st); break;
       }
       if (!mine) nextq = Q_NONE;
@@ -1634,7 +1688,7 @@ mc_photon_loop_kernel(const int adopt) {
   flush(STAT_MRW_WALKS, st.mrw_w); flush(STAT_MRW_STEPS, st.mrw_s);
   if (lane == 0) {
     unsigned long long* dbg = m.work + (4 + 2 * r.n_photons_loop);
-    for (int k = 0; k < NQ; ++k) { atomicAdd(dbg + k, (unsigned long long)ss.visits[k]); atomicAdd(dbg + NQ + k, (unsigned long long)ss.lanes[k]); }
+    for (int k = 0; k < 4; ++k) { atomicAdd(dbg + k, (unsigned long long)ss.visits[k]); atomicAdd(dbg + 4 + k, (unsigned long long)ss.lanes[k]); }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(m.work + (3 + 2 * r.n_photons_loop), globaltimer_ns());
   // last block to leave: end of the main launch / of the straggler launch (diagnostics)

@@ -68,7 +68,9 @@ __device__ __forceinline__ Look look_ahead(uint32_t pk_lo, uint32_t pk_hi, uint3
 
 template <class G, bool SM, int BANK>
 __global__ void __launch_bounds__(ENG_BLOCK, 1)
-mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt) {
+mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt, const int sm_kf, const int sm_kdB) {
+  // sm_kf / sm_kdB: word offsets of kf_dark(n_cells) / kdB_dT_CDF(n_lambda, n_T) staged in shared memory by this kernel
+  // (it has no packet pool, so the space is free), or -1: a lone warp cannot hide an L2 round trip per cell crossing
   constexpr int VAR = VAR_THERMAL;
   const DevModel& m = c_m; const DevRun& r = c_r;
   using CellT = typename G::CellT;
@@ -77,6 +79,15 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt) {
   const bool POLA = r.lsepar_pola != 0;
   const bool variable_dust = !SM && m.p_n_cells != 1;
   if (SM) stage_tables(m, r.p_lambda_in);
+  {
+    double* sd = reinterpret_cast<double*>(mcb_smem_raw);
+    if (sm_kf >= 0) for (int i = threadIdx.x; i < m.n_cells; i += blockDim.x) sd[sm_kf + i] = m.kf_dark[i];
+    if (sm_kdB >= 0) for (int i = threadIdx.x; i < m.n_lambda * m.n_T; i += blockDim.x) sd[sm_kdB + i] = m.kdB[i];
+    __syncthreads();
+  }
+  auto kf_of = [&](int idx) -> double { return sm_kf >= 0 ? smd()[sm_kf + idx] : __ldg(m.kf_dark + idx); };
+  auto kdB_of = [&](int l, int t, int p_icell) -> double {      // l, t 1-based
+    return sm_kdB >= 0 ? smd()[sm_kdB + (l - 1) + m.n_lambda * (t - 1)] : t_kdB<SM>(m, l, t, p_icell); };
   const int b0 = 2 + 2 * r.n_photons_loop;
   unsigned long long* park_count = m.work + (b0 + 10);
   unsigned long long* park_head = m.work + (b0 + 12);
@@ -140,6 +151,7 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt) {
     int lambda = misc_lambda(misc);
     int n_in_cell = misc_n_in_cell(misc);
     uint32_t la_base = 0u; bool la_have = false;
+    int pre_idx = -1; LtePre pre_raw; pre_raw.xkj = 0.0; pre_raw.vol = 1.0; pre_raw.Ti = 2; double dep_own = 0.0;
     Look L; L.tau = 0; L.ralb = 0; L.rand2 = 0; L.iu = 0; L.iv = 0; L.iw = 1; L.cpsi = 1; L.sphi = 0; L.cphi = 1; L.itheta = 1;
 
     // ------------------------------------------------------------------ the packet's life
@@ -149,6 +161,11 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt) {
       if (entry == Q_FLY) {
         const DirInv dinv = dir_invariants(u, v, w);
         const int i_star_hit = misc_istar(misc);
+        // running tally / temperature index / volume of the cell the flight starts in, requested now and used by the
+        // absorption if the flight ends in the same cell (the rule for a trapped packet): the L2 round trip overlaps the flight
+        pre_idx = tally_index(m, c0);
+        if (pre_idx >= 0) pre_raw = lte_prefetch(m, pre_idx);
+        dep_own = 0.0;
         for (;;) {
           if (G::test_exit(m, c0, x0, y0, z0)) {
             if (!misc_ism(misc)) {
@@ -163,11 +180,14 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt) {
             if (same_cell(c0, cs)) { ++n_kill; finished = true; break; }
           }
           const int idx = tally_index(m, c0);
-          double opacity = 0.0;
+          double opacity = 0.0, kf = 0.0;
           int p_icell = 1;
           if (idx >= 0) {
             p_icell = variable_dust ? idx + 1 : 1;
-            const double kf = __ldg(m.kf_dark + idx);
+            kf = kf_of(idx);
+          }
+          const Hit h = G::distance(m, dinv, x0, y0, z0, u, v, w, c0, c_old);      // (does not depend on kf: overlaps its load)
+          if (idx >= 0) {
             if (signbit(kf)) {      // dark-zone bounce (optical_depth.f90:104-112)
               u = -u; v = -v; w = -w;
               c0 = c_old; x0 = xo; y0 = yo; z0 = zo;
@@ -176,16 +196,19 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt) {
             }
             opacity = t_kappa<SM>(m, p_icell, lambda) * kf;
           }
-          const Hit h = G::distance(m, dinv, x0, y0, z0, u, v, w, c0, c_old);
           ++n_steps;
           double l_contrib = hit_l_contrib(h), l = h.l;
           const double tau_c = l_contrib * opacity;
           bool lstop = false;
           if (tau_c > extr) { lstop = true; l_contrib = l_contrib * (extr / tau_c); l = hit_l_void(h) + l_contrib; }
           else extr = extr - tau_c;
-          if (idx >= 0 && lane == 0) {      // save_radiation_field (radiation_field.f90:53-54)
-            atomicAdd(m.tally + m.lay.xKJ + idx, t_kappa_abs<SM>(m, p_icell, lambda) * l_contrib * S0);
-            if (r.lxJ) atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S0);
+          if (idx >= 0) {      // save_radiation_field (radiation_field.f90:53-54)
+            const double dep = t_kappa_abs<SM>(m, p_icell, lambda) * l_contrib * S0;
+            if (idx == pre_idx) dep_own += dep;
+            if (lane == 0) {
+              atomicAdd(m.tally + m.lay.xKJ + idx, dep);
+              if (r.lxJ) atomicAdd(m.tally + m.lay.xJ + idx + (size_t)m.n_cells * (lambda - 1), l_contrib * S0);
+            }
           }
           if (lstop) {
             x0 = x0 + l * u; y0 = y0 + l * v; z0 = z0 + l * w;
@@ -205,6 +228,10 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt) {
       const int idx = tally_index(m, c0);
       const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
       if (idx < 0) { ++n_kill; break; }      // interaction in a virtual cell (inconsistent dark-zone mask): drop the packet
+      if (entry == Q_MRW) {      // parked after its interaction, waiting for the walk: straight to the MRW test below
+        entry = Q_FLY;
+        la_base = ev; la_have = true; L = look_ahead<SM, BANK>(pk_lo, pk_hi, la_base, lane);
+      } else {
       if (!la_have || ev - la_base >= (uint32_t)ENG_LOOK) { la_base = ev; la_have = true; L = look_ahead<SM, BANK>(pk_lo, pk_hi, la_base, lane); }
       const int k = (int)(ev - la_base);
       const bool scatter = (entry == Q_FLY) ? (ralb < t_albedo<SM>(m, p_icell, lambda)) : (entry == Q_SCAT);
@@ -236,7 +263,11 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt) {
       } else {
         ++n_abs;
         // Temp_LTE + im_reemission_LTE (thermal_emission.f90:649-771): running tally read by lane 0
-        LtePre pre = lte_prefetch_w<true>(m, idx);
+        LtePre pre;
+        if (idx == pre_idx) {      // requested at the start of the flight; this flight's own deposits in the cell are added
+          pre.xkj = __shfl_sync(0xffffffffu, pre_raw.xkj, 0) + dep_own; pre.Ti = __shfl_sync(0xffffffffu, pre_raw.Ti, 0); pre.vol = pre_raw.vol;
+        } else pre = lte_prefetch_w<true>(m, idx);
+        pre_idx = -1;
         int Ti; double frac_T2;
         temp_lte<SM>(m, r, idx, p_icell, pre, Ti, frac_T2);
         const double frac_T1 = 1.0 - frac_T2;
@@ -247,7 +278,7 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt) {
           const int l = base + (int)lane + 1;
           bool ok = false;
           if (l <= m.n_lambda - 1) {
-            const double proba = frac_T1 * t_kdB<SM>(m, l, Ti - 1, p_icell) + frac_T2 * t_kdB<SM>(m, l, Ti, p_icell);
+            const double proba = frac_T1 * kdB_of(l, Ti - 1, p_icell) + frac_T2 * kdB_of(l, Ti, p_icell);
             ok = !((double)rand2 > proba);
           }
           const unsigned bal = __ballot_sync(0xffffffffu, ok);
@@ -261,8 +292,11 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt) {
         misc = pack_misc(lambda, false, false, false, 0, 0);
       }
       ++ev;
+      }
       // ---- modified random walk (dust_transfer.f90:1222-1239)
-      if (r.lMRW && n_in_cell > 5) {
+      bool try_mrw = false;
+      if (r.lMRW && n_in_cell > 5) try_mrw = __shfl_sync(0xffffffffu, (int)mrw_worth_trying<G, BANK>(c0, idx, x0, y0, z0), 0) != 0;
+      if (try_mrw) {
         const MrwOut o = mrw_walk<G, SM, BANK, true>(c0, idx, p_icell, x0, y0, z0, S0, pk_lo, pk_hi, ev);
         if (o.steps) {
           x0 = o.x; y0 = o.y; z0 = o.z; u = o.u; v = o.v; w = o.w; lambda = o.lambda; ev = o.ev;

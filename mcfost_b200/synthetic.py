@@ -546,9 +546,10 @@ def envelope_density(P, azimuthal=0.0):
     return rho
 
 
-def _finish(P, rho, n_lambda, n_T, tau_mid, pola, isotropic, n_photons_eq_th, star_T, star_R):
+def _finish(P, rho, n_lambda, n_T, tau_mid, pola, isotropic, n_photons_eq_th, star_T, star_R,
+            lam_range=(0.1, 3000.0), lam_tau=0.81, optics=None):
     P.n_lambda, P.n_T = n_lambda, n_T
-    P.tab_lambda, P.tab_delta_lambda = init_lambda(n_lambda)
+    P.tab_lambda, P.tab_delta_lambda = init_lambda(n_lambda, lam_range[0], lam_range[1])
     P.tab_lambda = np.float32(P.tab_lambda).astype(np.float64)          # `real` tables in the reference
     P.tab_delta_lambda = np.float32(P.tab_delta_lambda).astype(np.float64)
     P.T_min, P.T_max = 1.0, 3000.0
@@ -563,9 +564,9 @@ def _finish(P, rho, n_lambda, n_T, tau_mid, pola, isotropic, n_photons_eq_th, st
     P.p_n_cells, P.p_n_lambda_pos = 1, n_lambda
     rho0 = rho[int(np.argmax(rho))]          # icell_not_empty stand-in: the densest cell
     P.kappa_factor = rho / rho0
-    kext, albedo, g, s11, pol = synthetic_optics(P.tab_lambda, pola=pola, isotropic=isotropic)
-    # scale so that the radial midplane optical depth at 0.81 um is tau_mid
-    l_seuil = int(np.argmax(P.tab_lambda > 0.81)) + 1
+    kext, albedo, g, s11, pol = (optics or synthetic_optics)(P.tab_lambda, pola=pola, isotropic=isotropic)
+    # scale so that the radial midplane optical depth at lam_tau (0.81 um) is tau_mid
+    l_seuil = int(np.argmax(P.tab_lambda > lam_tau)) + 1
     P.lambda_seuil = l_seuil
     if P.kind == MCB_GRID_CYL:
         mid = np.array([(i - 1) + P.n_rad * (0 if not P.l3D else P.nz) for i in range(1, P.n_rad + 1)])
@@ -622,6 +623,43 @@ def ref41_like(n_photons_eq_th=1000, tau_mid=1.0e5, pola=True, n_rad=100, nz=70,
         P.l_dark_zone = define_dark_zone(P, P.lambda_seuil, 1500.0, physical_length)
     repartition_energie(P)
     P.name = "ref4.1-like (G1)"
+    return P
+
+
+def pascucci_optics(lam, pola=True, isotropic=True):
+    """Stand-in for the single 0.12 um astronomical-silicate grain of the Pascucci et al. (2004) benchmark (the
+    reference computes it with Mie theory on Draine_Si.dat, which is not available offline): geometric cross sections
+    below 2 pi a = 0.754 um, absorption ~ 1/lambda beyond with the 9.7 and 18 um silicate bands and ~ 1/lambda^2 in
+    the far infrared, Rayleigh scattering ~ 1/lambda^4, isotropic phase function (benchmarks.f90:30-31 forces
+    lisotropic).  Same return convention as synthetic_optics (unit extinction at the shortest wavelengths)."""
+    n = len(lam)
+    xs = 0.754 / np.maximum(lam, 1e-30)
+    q_abs = np.minimum(1.0, xs) * (1.0 + 2.5 * np.exp(-(((lam - 9.7) / 1.5) ** 2)) + 1.0 * np.exp(-(((lam - 18.0) / 4.0) ** 2)))
+    q_abs = q_abs * np.where(lam > 30.0, 30.0 / lam, 1.0)
+    q_sca = np.minimum(1.0, xs ** 4)
+    kext = (q_abs + q_sca) / 2.0
+    albedo = q_sca / (q_abs + q_sca)
+    g = 0.0 * lam
+    s11 = np.ones((NANG_SCATT + 1, n))
+    theta = np.arange(NANG_SCATT + 1) * PI / NANG_SCATT
+    mu = np.cos(theta)
+    pol = (-(1.0 - mu * mu) / (1.0 + mu * mu), np.ones_like(mu), 2.0 * mu / (1.0 + mu * mu), 0.0 * mu, 2.0 * mu / (1.0 + mu * mu)) if pola else None
+    return kext, albedo, g, s11, pol
+
+
+def pascucci_like(tau_V=1.0, n_photons_eq_th=10000, n_rad=100, nz=70, n_rad_in=20, n_T=100, pola=True):
+    """G2: Pascucci_3.0.para -- the 2D disk benchmark of Pascucci et al. 2004: cylindrical 100x70x1, disk 1-1000 AU,
+    scale height 99.74 AU at 500 AU, flaring 1.125, surface-density exponent +0.125 (rho ~ 1/r), one 0.12 um
+    silicate grain with isotropic scattering, 61 wavelengths 0.1107-2168.8 um, star 5800 K / 1 Rsun, 1.28e6 thermal
+    packets (Pascucci_3.0.para:4-8,49-56,68; benchmarks.f90:30-31).  tau_V is the midplane optical depth at
+    0.55 um from the star to the outer edge (0.1, 1, 10, 100 in the benchmark)."""
+    zones = [DiskZone(rin=1.0, rout=1000.0, sclht=99.73557010035817, rref=500.0, exp_beta=1.125, surf=0.125, dust_mass=1.1e-6)]
+    P = cylindrical_grid(n_rad, nz, 1, n_rad_in, zones, l3D=False)
+    _finish(P, disk_density(P, zones), 61, n_T, tau_V, pola, True, n_photons_eq_th, 5800.0, 1.0,
+            lam_range=(0.110662, 2168.76), lam_tau=0.55, optics=pascucci_optics)
+    P.star_icell = np.array([star_icell_analytic(P)], np.int32)
+    repartition_energie(P)
+    P.name = "Pascucci-like (G2), tau_V = %g" % tau_V
     return P
 
 
@@ -754,6 +792,11 @@ def voronoi_disk(n_points=1500, n_photons_eq_th=200, tau_mid=30.0, n_lambda=50, 
     P = voronoi_mesh(n_points, seed=seed)
     rs = np.maximum(P.r_grid, 1.0)
     rho = rs ** -1.5 * np.exp(-0.5 * (P.z_grid / (0.15 * rs)) ** 2) + 1e-6
+    return _finish_voronoi(P, rho, n_photons_eq_th, tau_mid, n_lambda, n_T, pola, "Voronoi disk")
+
+
+def _finish_voronoi(P, rho, n_photons_eq_th, tau_mid, n_lambda, n_T, pola, name):
+    """star, constant-dust opacities (p_n_cells = 1) and emission tables of a Voronoi model with cell densities rho"""
     # _finish needs a radial column to scale kappa: use a pseudo column through the cells sorted by radius
     order = np.argsort(P.r_grid)
     P.n_rad = 0
@@ -791,8 +834,118 @@ def voronoi_disk(n_points=1500, n_photons_eq_th=200, tau_mid=30.0, n_lambda=50, 
     P.R_ISM = 0.0
     P.centre_ISM = (0.0, 0.0, 0.0)
     repartition_energie(P)
-    P.name = "Voronoi disk"
+    P.name = name
     return P
+
+
+_MESH_KEYS = ("vor_xyz", "vor_h", "vor_first", "vor_last", "neighbours_list", "vor_was_cut", "volume", "wall_x", "rho", "Rmax2", "zmaxmax")
+
+
+def voronoi_sph_disk(n_points=1000000, n_photons_eq_th=1000, tau_mid=1.0e3, n_lambda=50, n_T=100, pola=False, seed=12345,
+                     keep=0.999, zone=None, cache=None):
+    """G5: a Voronoi mesh on the particles of a synthetic SPH disk (phantom-like), SURVEY 8d.
+
+    Particles: n_points drawn from the G1 density (ref4.1 geometry: Sigma ~ r^-0.5 between 1 and 300 AU, Gaussian in z
+    with H = 10 AU (r / 100 AU)^1.125), numpy seed 12345 (inverse-transform sampling of the same distribution the
+    survey's rejection sampling would give).  Box: the reference's percentile rule, SPH_keep_particles = 0.999, i.e. the
+    0.05 % outermost particles are dropped on each side of each axis (SPH2mcfost.f90:246,261-273).  Mesh: scipy Delaunay
+    (qhull) gives the neighbour lists voro++ gives the reference (Voronoi.f90:472-475); cells on the hull get the walls
+    they face as negative neighbours.  Stand-ins, documented: the cell volume is the expectation 1 / (N pdf(x_i)) of the
+    Voronoi volume under the sampling density instead of the polyhedron's (a million convex hulls in Python), h =
+    (3 V / 4 pi)^(1/3), and a cell is `was_cut` when its farthest neighbour is more than 6 h away (the reference cuts
+    faces farther than 3 h, voro++_wrapper.cpp:209-225)."""
+    import os
+    if cache and os.path.exists(cache):      # a mesh generated earlier with the same arguments (tools/make_g5_mesh.py)
+        d = np.load(cache)
+        P = Problem()
+        P.kind, P.l3D = MCB_GRID_VORONOI, 1
+        P.n_rad, P.nz, P.n_az = 0, 0, 0
+        P.vor_xyz = np.asfortranarray(d["vor_xyz"]); P.n_cells = P.vor_xyz.shape[1]
+        for k in ("vor_h", "vor_first", "vor_last", "neighbours_list", "vor_was_cut", "volume"):
+            setattr(P, k, d[k])
+        P.wall_x = [list(map(float, w)) for w in d["wall_x"]]
+        P.Rmax2, P.zmaxmax = float(d["Rmax2"]), float(d["zmaxmax"])
+        P.vor_is_star = np.zeros(P.n_cells, np.int32); P.vor_is_star_neighbour = np.zeros(P.n_cells, np.int32)
+        P.cutting_distance_o_h = 3.0
+        P.r_grid = np.hypot(P.vor_xyz[0], P.vor_xyz[1]); P.z_grid = P.vor_xyz[2].copy(); P.phi_grid = np.arctan2(P.vor_xyz[1], P.vor_xyz[0])
+        P.r_lim = P.r_lim_2 = P.r_lim_3 = P.z_lim = P.zmax = P.tan_theta_lim = P.theta_lim = P.tan_phi_lim = None
+        P.cell_map_i = P.cell_map_j = P.cell_map_k = None
+        P.n_cells_tot = 0
+        return _finish_voronoi(P, d["rho"], n_photons_eq_th, tau_mid, n_lambda, n_T, pola, "Voronoi SPH disk (G5), %d cells" % P.n_cells)
+    from scipy.spatial import Delaunay
+    z_ = zone or DiskZone()
+    rng = np.random.default_rng(seed)
+    # r from p(r) ~ r Sigma(r) = r^(1+surf) on [rin, rout]; z Gaussian with H(r); phi uniform
+    a = 2.0 + z_.surf
+    uu = rng.uniform(size=n_points)
+    r = (z_.rin ** a + uu * (z_.rout ** a - z_.rin ** a)) ** (1.0 / a)
+    H = z_.sclht * (r / z_.rref) ** z_.exp_beta
+    zz = rng.normal(size=n_points) * H
+    phi = rng.uniform(0.0, 2.0 * np.pi, n_points)
+    pts = np.stack([r * np.cos(phi), r * np.sin(phi), zz], axis=1)
+    # percentile box (SPH2mcfost.f90:261-273)
+    lo = np.quantile(pts, 0.5 * (1.0 - keep), axis=0)
+    hi = np.quantile(pts, 1.0 - 0.5 * (1.0 - keep), axis=0)
+    ok = np.all((pts > lo) & (pts < hi), axis=1)
+    pts, r, H, zz = pts[ok], r[ok], H[ok], zz[ok]
+    n = len(pts)
+    tri = Delaunay(pts)
+    indptr, indices = tri.vertex_neighbor_vertices
+    deg = np.diff(indptr).astype(np.int64)
+    # walls faced by the hull cells: a hull vertex gets every wall it is closer to than to its farthest neighbour
+    hull = np.unique(tri.convex_hull)
+    dmax = np.zeros(n)
+    src = np.repeat(np.arange(n), deg)
+    dist = np.sqrt(np.sum((pts[src] - pts[indices]) ** 2, axis=1))
+    np.maximum.at(dmax, src, dist)
+    wall_lists = [[] for _ in range(6)]
+    dw = np.stack([pts[hull, 0] - lo[0], hi[0] - pts[hull, 0], pts[hull, 1] - lo[1], hi[1] - pts[hull, 1], pts[hull, 2] - lo[2], hi[2] - pts[hull, 2]], axis=1)
+    near = dw <= np.maximum(dmax[hull][:, None], dw.min(axis=1, keepdims=True))
+    n_wall = np.zeros(n, np.int64)
+    n_wall[hull] = near.sum(axis=1)
+    first = np.zeros(n, np.int64)
+    tot = deg + n_wall
+    first[1:] = np.cumsum(tot)[:-1]
+    flat = np.zeros(int(tot.sum()), np.int32)
+    # cell neighbours first (1-based ids), then the walls (negative ids)
+    pos = first[src] + (np.arange(len(src)) - indptr[src])
+    flat[pos] = indices.astype(np.int32) + 1
+    hrow, hwall = np.nonzero(near)
+    order = np.lexsort((hwall, hrow))
+    hrow, hwall = hrow[order], hwall[order]
+    rank = np.arange(len(hrow)) - np.searchsorted(hrow, hrow, side="left")
+    flat[first[hull[hrow]] + deg[hull[hrow]] + rank] = -(hwall.astype(np.int32) + 1)
+    # expected Voronoi volume under the sampling density
+    norm_r = (z_.rout ** a - z_.rin ** a) / a
+    pdf = (r ** (a - 1.0) / norm_r) / (2.0 * np.pi * r) * np.exp(-0.5 * (zz / H) ** 2) / (np.sqrt(2.0 * np.pi) * H)
+    vol = 1.0 / (n_points * pdf)
+    h = (3.0 * vol / (4.0 * np.pi)) ** (1.0 / 3.0)
+    P = Problem()
+    P.kind, P.l3D = MCB_GRID_VORONOI, 1
+    P.n_rad, P.nz, P.n_az = 0, 0, 0
+    P.n_cells = n
+    L = float(np.max(np.abs(np.concatenate([lo, hi]))))
+    P.Rmax2, P.zmaxmax = 3.0 * L * L, float(max(abs(lo[2]), abs(hi[2])))
+    P.vor_xyz = np.asfortranarray(pts.T.copy())
+    P.vor_h = h
+    P.vor_first = (first + 1).astype(np.int32); P.vor_last = (first + tot).astype(np.int32)
+    P.neighbours_list = flat
+    P.vor_was_cut = (dmax > 6.0 * h).astype(np.int32)
+    P.vor_is_star = np.zeros(n, np.int32)
+    P.vor_is_star_neighbour = np.zeros(n, np.int32)
+    P.wall_x = [[-1, 0, 0, lo[0]], [1, 0, 0, hi[0]], [0, -1, 0, lo[1]], [0, 1, 0, hi[1]], [0, 0, -1, lo[2]], [0, 0, 1, hi[2]]]
+    P.cutting_distance_o_h = 3.0
+    P.volume = vol
+    P.r_grid = np.hypot(pts[:, 0], pts[:, 1]); P.z_grid = pts[:, 2]; P.phi_grid = np.arctan2(pts[:, 1], pts[:, 0])
+    P.r_lim = P.r_lim_2 = P.r_lim_3 = P.z_lim = P.zmax = P.tan_theta_lim = P.theta_lim = P.tan_phi_lim = None
+    P.cell_map_i = P.cell_map_j = P.cell_map_k = None
+    P.n_cells_tot = 0
+    rho = pdf / pdf.max()          # the particles ARE the density: equal-mass particles, rho_i = m / V_i
+    if cache:
+        os.makedirs(os.path.dirname(os.path.abspath(cache)), exist_ok=True)
+        np.savez(cache, vor_xyz=P.vor_xyz, vor_h=np.float64(h), vor_first=P.vor_first, vor_last=P.vor_last, neighbours_list=flat,
+                 vor_was_cut=P.vor_was_cut, volume=vol, wall_x=np.array(P.wall_x, np.float64), rho=rho, Rmax2=P.Rmax2, zmaxmax=P.zmaxmax)
+    return _finish_voronoi(P, rho, n_photons_eq_th, tau_mid, n_lambda, n_T, pola, "Voronoi SPH disk (G5), %d cells" % n)
 
 
 def ref41_multi_like(n_photons_eq_th=200, n_rad=40, nz=20, n_rad_in=5, tau_mid=300.0, n_lambda=50, n_T=100):

@@ -179,3 +179,85 @@ def test_modified_random_walk_other_grids():
         lit = (t0.xKJ_abs > 0) & (t1.xKJ_abs > 0) & (T0 > 1.5)
         rel = np.abs(T1[lit] - T0[lit]) / T0[lit]
         assert np.median(rel) < 0.02 and np.percentile(rel, 75) < 0.05
+
+
+@pytest.mark.parametrize("tau_V", [0.1, 1.0, 10.0, 100.0])
+def test_pascucci_benchmark_matches_oracle(tau_V):
+    """G2: Pascucci_3.0.para (2D disk benchmark, single 0.12 um grain, isotropic scattering, 61 wavelengths) at the
+    file's own budget of 1.28e6 thermal packets, for the four optical depths of the benchmark."""
+    n2 = 10000
+    P = S.pascucci_like(tau_V=tau_V, n_photons_eq_th=n2)
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(1, 1, n2, 1.0e30, 1, False, lisotropic=1)
+    Tg = G.temp_finale()
+    G.close()
+    O = Oracle(P, fast=True)
+    to = O.run(n_threads=0, n_photons2=n2, lisotropic=1)
+    To = O.temp_finale()
+    assert tg.stats[0] == to.stats[0] == 128 * n2 == tg.n_phot_envoyes.sum()
+    assert tg.stats[5] + tg.stats[6] == tg.stats[0]
+    lit = (to.xKJ_abs > 0) & (tg.xKJ_abs > 0) & (To > 1.5)
+    rel = np.abs(Tg[lit] - To[lit]) / To[lit]
+    assert lit.sum() > 0.8 * P.n_cells
+    assert np.median(rel) < 0.01 and np.percentile(rel, 75) < 0.05, (np.median(rel), np.percentile(rel, 75))
+    z = _spectrum_z(tg, to)
+    assert np.mean(np.abs(z) < 3) >= 0.95 and abs(z.mean()) < 0.5, z
+    assert np.mean(_energy_spectrum_close(tg, to) < 3) >= 0.95
+    assert abs(tg.stats[1] / to.stats[1] - 1) < 0.01
+    assert abs(tg.stats[2] - to.stats[2]) < 5 * np.sqrt(to.stats[2]) + 0.01 * to.stats[2]
+
+
+def test_voronoi_point_location_grid_equals_brute_force():
+    """GeomVor::index walks a uniform grid of seeds instead of the reference's O(n_cells) scan (index_cell_voronoi,
+    Voronoi.f90:1548-1572): same nearest seed (fp32 distances, ties to the lowest id) for 1e5 points, including points
+    on seeds, midway between seeds and outside the seeds' bounding box."""
+    P = S.voronoi_disk(n_points=1500, n_photons_eq_th=10)
+    O, G = Oracle(P), api.PhotonLoop(P)
+    rng = np.random.default_rng(11)
+    n = 100000
+    L = 100.0
+    x, y, z = (rng.uniform(-L, L, n) for _ in range(3))
+    # on seeds, midpoints of random seed pairs, far outside
+    s = rng.integers(0, P.n_cells, 3000)
+    x[:1000], y[:1000], z[:1000] = P.vor_xyz[0, s[:1000]], P.vor_xyz[1, s[:1000]], P.vor_xyz[2, s[:1000]]
+    a, b = s[1000:2000], s[2000:3000]
+    x[1000:2000], y[1000:2000], z[1000:2000] = (0.5 * (P.vor_xyz[k, a] + P.vor_xyz[k, b]) for k in range(3))
+    x[2000:2500] *= 5.0; y[2000:2500] *= 5.0; z[2500:3000] *= 7.0
+    assert np.array_equal(G.index_cell(x, y, z), O.index_cell(x, y, z))
+    G.close()
+
+
+def _n_cuda_devices():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("n_gpus", [1, 2])
+def test_multi_gpu_behind_the_abi_equals_one_gpu(n_gpus):
+    """mcfost_b200_multi_*: n GPUs, one call, every tally merged inside the library.  The SED step has no feedback, so
+    the union of the ranks' packets is exactly the single-GPU set: counts identical, sums to rounding; xI_scatt too.
+    The thermal step (feedback: local tally x n) agrees statistically, and Temp_finale runs on the merged tallies."""
+    if _n_cuda_devices() < n_gpus:
+        pytest.skip("needs %d GPUs" % n_gpus)
+    P = small_problems()["cyl2D"]()
+    kw = dict(letape_th=0, lmono=1, lscatt_ray_tracing1=1, lsepar_pola=1, lsepar_contrib=1, RT_n_incl=3, RT_n_az=1,
+              tab_u_rt=np.array([[0.0], [0.5], [0.9]]), tab_v_rt=np.zeros((3, 1)), tab_w_rt=np.array([1.0, np.sqrt(0.75), np.sqrt(0.19)]))
+    G1 = api.PhotonLoop(P)
+    a = G1.mc_photon_loop(8, 8, 10 ** 9, 200.0, 1, False, **kw)
+    th1 = G1.mc_photon_loop(1, 1, 1500, 1.0e30, 1, False); T1 = G1.temp_finale()
+    G1.close()
+    M = api.MultiPhotonLoop(P, n_gpus)
+    b = M.mc_photon_loop(8, 8, 10 ** 9, 200.0, 1, False, **kw)
+    thn = M.mc_photon_loop(1, 1, 1500, 1.0e30, 1, False); Tn = M.temp_finale()
+    M.close()
+    assert b.stats[0] == a.stats[0] == 128 * 200
+    assert np.array_equal(b.n_phot_sed, a.n_phot_sed) and np.array_equal(b.n_phot_envoyes, a.n_phot_envoyes)
+    assert np.array_equal(b.stats[:8], a.stats[:8])
+    for k in ("sed", "sed_q", "sed_u", "sed_star_scat", "sed_disk_scat"):
+        assert np.allclose(getattr(b, k), getattr(a, k), rtol=1e-9, atol=1e-12), k
+    assert np.allclose(b.xI_scatt, a.xI_scatt, rtol=2e-4, atol=1e-6 * np.abs(a.xI_scatt).max())      # fp32 sums, different order
+    assert thn.stats[0] == th1.stats[0] == 128 * 1500 and thn.stats[5] + thn.stats[6] == thn.stats[0]
+    assert abs(thn.xKJ_abs.sum() / th1.xKJ_abs.sum() - 1) < 0.02
+    lit = (th1.xKJ_abs > 0) & (thn.xKJ_abs > 0) & (T1 > 1.5)
+    assert np.median(np.abs(Tn[lit] - T1[lit]) / T1[lit]) < 0.02
+    assert (thn.xT_ech >= 2).all()

