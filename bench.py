@@ -91,8 +91,27 @@ class ClockSampler(threading.Thread):
 FLAGS = dict(lsepar_pola=1, lsepar_contrib=1)
 
 
-def make_problem(n2_total, walker_factory=None):
+# the other BASELINE configs (bench lines on request: --workload g2|g4|g5; the driver's default line is G1)
+WORKLOADS = {
+    "g1": dict(name=WORKLOAD, b_step=112.0, flags={}),
+    "g2": dict(name="G2 Pascucci-like (Pascucci_3.0.para): cylindrical 100x70x1, 61 lambda, one 0.12 um grain, isotropic scattering, tau_V = 100, thermal step",
+               b_step=112.0, flags=dict(lisotropic=1)),
+    "g4": dict(name="G4 ref4.1_3D-like: cylindrical 100x50x72 two-sided = 720 000 cells, 50 lambda, thermal step, tau_mid(0.81um)=1e3",
+               b_step=120.0, flags={}),
+    "g5": dict(name="G5 Voronoi mesh of a synthetic 1M-particle SPH disk (997 016 cells, 15.5 neighbours per cell), 50 lambda, thermal step, tau_mid=1e3",
+               b_step=332.0, flags=dict(lsepar_pola=0, lsepar_contrib=0)),
+}
+
+
+def make_problem(n2_total, walker_factory=None, workload="g1"):
     from mcfost_b200 import synthetic as S
+    if workload == "g2":
+        return S.pascucci_like(tau_V=100.0, n_photons_eq_th=n2_total)
+    if workload == "g4":
+        return S.ref41_3d_like(n_photons_eq_th=n2_total, tau_mid=1.0e3, n_rad=100, nz=50, n_az=72)
+    if workload == "g5":
+        return S.voronoi_sph_disk(n_points=1000000, n_photons_eq_th=n2_total, tau_mid=1.0e3,
+                                  cache=os.path.join(ROOT, "data_cache", "g5_1000000.npz"))
     P = S.ref41_like(n_photons_eq_th=n2_total, dark_zone=False)      # L_packet_th = L_tot / (128 * n2_total)
     if walker_factory is not None:
         P.l_dark_zone = S.define_dark_zone(P, P.lambda_seuil, 1500.0, walker_factory(P))
@@ -134,7 +153,8 @@ def reference_arm(args):
         binding.build()
     from oracle.binding import Oracle
     n2 = args.cpu_n2
-    P = make_problem(n2, lambda P: Oracle(P).dark_zone_walker())
+    P = make_problem(n2, lambda P: Oracle(P).dark_zone_walker(), args.workload)
+    FLAGS.update(WORKLOADS[args.workload]["flags"])
     O = Oracle(P, fast=True)
     nthr = args.cpu_threads or host_threads(O)
     cpu_run(O, max(1, n2 // 50), nthr, args.mrw)           # warm-up (thread pool, page faults)
@@ -147,7 +167,7 @@ def reference_arm(args):
     val = packets / total
     # the budgets of the GPU arm's sweep, same packet counts (the largest is bounded by --cpu-sweep-max)
     sweep = []
-    for s2 in SWEEP_N2:
+    for s2 in (SWEEP_N2 if args.workload == "g1" else ()):
         if 128 * s2 > args.cpu_sweep_max:
             sweep.append({"packets": 128 * s2, "value": None, "note": "skipped: above --cpu-sweep-max (host time)"})
             continue
@@ -157,7 +177,7 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "packets_per_step": int(128 * n2), "lMRW": int(args.mrw)},
+            "config": {"workload": WORKLOADS[args.workload]["name"], "packets_per_step": int(128 * n2), "lMRW": int(args.mrw)},
             "sweep": sweep,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthr, "kind": "port",
                              "sample": f"oracle-OpenMP (reference restatement, the Fortran cannot be built here), {128 * n2} packets per step, schedule(dynamic,1) over 128 chunks"},
@@ -182,13 +202,16 @@ def gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    P = make_problem(args.n2 * world)
+    W = WORKLOADS[args.workload]
+    FLAGS.update(W["flags"])
+    P = make_problem(args.n2 * world, workload=args.workload)
     loop = api.PhotonLoop(P, device=local, rank=rank, n_ranks=world)
-    # dark zone via the library's own deterministic ray-walk kernel (define_dark_zone step 4)
-    P.l_dark_zone = S.define_dark_zone(P, P.lambda_seuil, 1500.0, loop.dark_zone_walker())
-    S.repartition_energie(P)
-    loop.upload_dark_zone(P.l_dark_zone)
-    loop.upload_emission(P)
+    if args.workload == "g1":
+        # dark zone via the library's own deterministic ray-walk kernel (define_dark_zone step 4)
+        P.l_dark_zone = S.define_dark_zone(P, P.lambda_seuil, 1500.0, loop.dark_zone_walker())
+        S.repartition_energie(P)
+        loop.upload_dark_zone(P.l_dark_zone)
+        loop.upload_emission(P)
     dev = torch.device("cuda", local)
     stream = torch.cuda.ExternalStream(loop.stream(), device=dev)
     flags = dict(FLAGS, lMRW=int(args.mrw))
@@ -236,7 +259,7 @@ def gpu_arm(args):
     dev_ms = timed(n2, args.steps, args.warmup)
     sampler.stop_flag = True
     d_last = loop.debug_counters()
-    launches_per_step = 4 if 128 * n2 // world > 2000000 else 1       # packet-per-warp + counter hand-over + packet-per-lane + packet-per-warp (stragglers); small budgets: packet-per-warp alone
+    launches_per_step = d_last["launches"]      # counted by the library: packet-per-lane kernel + counter hand-over + packet-per-warp kernel (small budgets: the latter alone)
     t_last = loop.download(want_xI=False)
     stats = t_last.stats.copy()                # whole-job counts after the all-reduce
     packets_per_step = 128 * args.n2 * world
@@ -295,7 +318,7 @@ def gpu_arm(args):
 
     # ---- budget sweep (N = 1): one blocking e2e call per budget, host buffers, best of 2 after one warm-up call
     sweep = None
-    if world == 1 and not args.no_sweep:
+    if world == 1 and not args.no_sweep and args.workload == "g1":
         sweep = []
         for s2 in SWEEP_N2:
             set_budget(P, s2)
@@ -312,12 +335,12 @@ def gpu_arm(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        nb = stats[1] * B_STEP + stats[3] * B_SCA + stats[4] * B_ABS + stats[0] * b_packet(P.n_cells)
+        nb = stats[1] * W["b_step"] + stats[3] * B_SCA + stats[4] * B_ABS + stats[0] * b_packet(P.n_cells)
         nb_per_gpu = nb / world
         hbm_achieved = nb_per_gpu / (last_ms * 1e-3) / 1e9
         atomics_per_s = stats[1] / world / (last_ms * 1e-3)            # one fp64 reduction per crossed cell
         l2 = _json("r02_l2_atomic.json")
-        traffic = _json("r02_traffic.json")
+        traffic = (_json("r02_traffic.json") or {}).get(args.workload)
         cpu = None
         if world == 1 and not args.no_cpu:
             from oracle import binding
@@ -335,7 +358,7 @@ def gpu_arm(args):
             pk, dt = cpu_run(O, args.cpu_n2, nthr, args.mrw)
             cpu = {"value": pk / dt, "unit": UNIT, "cores": nthr, "kind": "port",
                    "sample": f"oracle-OpenMP (reference restatement), same model, {int(pk)} packets in {dt:.2f} s wall on {nthr} threads"}
-        if l2 and "g1_hits" in l2:
+        if l2 and "g1_hits" in l2 and args.workload in ("g1", "g2"):
             l2_peak = float(l2["g1_hits"]["red_f64_per_s"])
             roof = {"bound": "l2_atomic", "achieved": atomics_per_s * 8e-9, "peak": l2_peak * 8e-9, "unit": "GB/s", "frac": atomics_per_s / l2_peak,
                     "peak_source": "measured: red.global.add.f64 into 7000 L2-resident doubles with G1's per-cell crossing distribution (tools/l2_atomic_peak.cu, profiles/r02_l2_atomic.json); payload bytes of the reductions"}
@@ -353,7 +376,7 @@ def gpu_arm(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "packets_per_step": int(packets_per_step), "lMRW": int(args.mrw),
+                "config": {"workload": W["name"], "packets_per_step": int(packets_per_step), "lMRW": int(args.mrw),
                            "parallelism": f"packets x{world} (replicated grid, 1 all-reduce/step)",
                            "calls": "one blocking call per step (launch + all-reduce + sync), nothing overlapped",
                            "l2_policy": "tallies are re-zeroed (memset) every step; working set is L2-resident by design (0.5 MB tables)"},
@@ -383,6 +406,7 @@ def main():
     ap.add_argument("--cpu-sweep-max", type=float, default=1.28e7, help="largest sweep budget the reference arm runs (1.28e8 takes minutes of host time)")
     ap.add_argument("--mrw", type=int, default=0, help="1: modified random walk on (both arms); the reference's own behaviour is off")
     ap.add_argument("--strong-steps", type=int, default=3)
+    ap.add_argument("--workload", default="g1", choices=sorted(WORKLOADS), help="g1 = the headline (ref4.1-like); g2 / g4 / g5: the other BASELINE configs")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
     args = ap.parse_args()

@@ -352,7 +352,8 @@ int mcfost_b200_last_kernel_ms(mcb_handle *h, float *ms);
  * {ms until the packet counter ran dry, kernel ms, chunk visits[4], valid lanes[4]
  * for the phases EMIT, ABSORB, SCATTER, FLY, packets handed to the straggler launch,
  * ms until the main launch ended, ms until the straggler launch ended,
- * device timer at the start of the main launch in ms}; out must hold 16 doubles */
+ * device timer at the start of the main launch in ms, ms until the straggler launch started, kernels launched by the
+ * last call}; out must hold 16 doubles */
 int mcfost_b200_debug_counters(mcb_handle *h, double *out);
 /* cudaStream_t of the handle, as an integer, so torch can wait on it */
 int mcfost_b200_stream(mcb_handle *h, uint64_t *stream);

@@ -231,7 +231,7 @@ class PhotonLoop:
         return {"steady_ms": v[0], "kernel_ms": v[1],
                 "chunk_fill": {n: (v[6 + i] / v[2 + i] if v[2 + i] else 0.0) for i, n in enumerate(names)},
                 "visits": {n: v[2 + i] for i, n in enumerate(names)}, "parked": v[10],
-                "main_end_ms": v[11], "straggler_end_ms": v[12], "t0_ms": v[13], "straggler_start_ms": v[14]}
+                "main_end_ms": v[11], "straggler_end_ms": v[12], "t0_ms": v[13], "straggler_start_ms": v[14], "launches": int(v[15])}
 
     def stream(self):
         s = C.c_uint64()

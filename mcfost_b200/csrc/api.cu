@@ -84,6 +84,7 @@ int mcfost_b200_debug_counters(mcb_handle* h, double* out) {
   out[11] = w[b + 11] ? ((double)w[b + 11] - t0) * 1e-6 : -1.0;      // ms until the last block of the main launch left
   out[12] = w[b + 13] ? ((double)w[b + 13] - t0) * 1e-6 : -1.0;      // ms until the straggler launch ended
   out[14] = w[b + 14] ? ((double)w[b + 14] - t0) * 1e-6 : -1.0;      // ms until the straggler launch started
+  out[15] = (double)h->launches_last_call;      // kernels the last mcfost_b200_launch started (photon-loop kernels + the counter hand-over)
   out[13] = t0 * 1e-6;      // device globaltimer at the start of the main launch, ms (to line up calls on two handles)
   if (getenv("MCB_DRAIN_PROBE_PRINT")) {      // development builds (-DMCB_DRAIN_PROBE) only
     for (int k = 0; k < 11; ++k) fprintf(stderr, "drain probe: live <= %4d  max %8.2f ms  mean %8.2f ms after dry\n", k < 10 ? (512 >> k) : 0, (double)w[b + 16 + k] * 1e-6, (double)w[b + 27 + k] * 1e-6 / (double)h->n_sm);
@@ -653,7 +654,10 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   dr.patience = 8;
   dr.park_live = 48;      // measured (profiles/r02_tail.md): the packet-per-lane kernel drains faster than the packet-per-warp kernel down to ~50 packets per SM
   dr.debug_abort_dry = 0;
-#ifdef MCB_DEV      // development builds only: a science library does not change its results on an environment variable
+  dr.patience_dry = 1; dr.drain_live_dry = 96;
+#ifdef MCB_DEV
+  { const char* e = getenv("MCB_PATIENCE_DRY"); if (e && atoi(e) >= 0) dr.patience_dry = atoi(e); }
+  { const char* e = getenv("MCB_DRAIN_LIVE_DRY"); if (e && atoi(e) > 0) dr.drain_live_dry = atoi(e); }      // development builds only: a science library does not change its results on an environment variable
   { const char* e = getenv("MCB_PATIENCE"); if (e && atoi(e) > 0 && atoi(e) <= 4096) dr.patience = atoi(e); }
   { const char* e = getenv("MCB_PARK_LIVE"); if (e && atoi(e) > 0 && atoi(e) <= 256) dr.park_live = atoi(e); }
   { const char* e = getenv("MCB_DEBUG_ABORT_DRY"); dr.debug_abort_dry = (e && e[0] == '1') ? 1 : 0; }   // profiling aid: tallies are incomplete

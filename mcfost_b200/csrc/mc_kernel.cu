@@ -86,11 +86,6 @@ static int launch_bank(mcb_handle* h, DevRun dr) {
     h->m.park = (double*)pk;
   }
   if (dr.lMRW) {
-    void*& c0 = h->bufs["mrw_c0"];
-    const size_t bytes = (size_t)h->n_sm * NP * sizeof(int);
-    if (c0 && h->buf_bytes["mrw_c0"] != bytes) { cudaFree(c0); c0 = nullptr; }
-    if (!c0) { CK(cudaMalloc(&c0, bytes)); h->buf_bytes["mrw_c0"] = bytes; }
-    h->m.mrw_c0 = (int*)c0;
     void*& lr = h->bufs["mrw_lR"];
     const size_t bytes_lr = (size_t)h->m.n_cells * 2 * sizeof(float);
     if (lr && h->buf_bytes["mrw_lR"] != bytes_lr) { cudaFree(lr); lr = nullptr; }

@@ -127,7 +127,6 @@ struct DevModel {
   double *park;             // parked stragglers: (PARK_REC doubles) x capacity, see transport.cuh
   // modified random walk (MRW.f90): zeta(1:n_zeta), mean opacities A, B, C (n_T, p_n_cells), flight-start cell ids
   const double *zeta, *mrw_A, *mrw_B, *mrw_C;
-  int *mrw_c0;              // (n_blocks, NP): cell id the flight in progress started in (dust_transfer.f90:1242)
   float *mrw_lR;            // (2, n_cells): mean free path of the last walk evaluated in the cell (0 = none yet) and the temperature index it was evaluated at, see mrw_worth_trying
   SmemLayout sm;
   DevGrains gr;
@@ -162,6 +161,7 @@ struct DevRun {
   int mc_maps, lorigine, capt_interet, lonly_capt_interet, capt_inf, npix_x, npix_y, l_sym_ima;
   double zoom, map_size, cos_disk, sin_disk;
   int patience;                         // polls (250 ns each) a warp waits for a full 32-packet chunk before it takes a partial one
+  int patience_dry, drain_live_dry;     // the same two thresholds once the packet counter ran dry
   int park_live;                        // hand over when at most this many packets of a block are in flight (<= PARK_LIVE)
   int park_enable;                      // hand stragglers over to a second small launch (count_sent modes only)
   int debug_abort_dry;                  // profiling aid, development builds (-DMCB_DEV) only: stop when the packet counter runs dry

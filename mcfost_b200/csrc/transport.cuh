@@ -55,7 +55,7 @@ __constant__ DevRun c_rr[MCB_BANKS];
 // rarely used options; every such branch that merely sat behind a run-time flag cost instruction-cache footprint
 // and registers of the hot loop.
 enum { VAR_THERMAL = 0, VAR_GENERIC = 1, VAR_EXTRAS = 2 };
-enum { Q_EMIT = 0, Q_ABS = 1, Q_SCAT = 2, Q_FLY = 3, Q_MRW = 4, NQ = 5, Q_NONE = 7 };
+enum { Q_EMIT = 0, Q_ABS = 1, Q_SCAT = 2, Q_FLY = 3, NQ = 4, Q_NONE = 7 };     // queue order = claim order
 enum { CTL_LIVE = 2 * NQ, CTL_BUSY, CTL_PARK, CTL_DRY, CTL_SENT };      // Pool::ctl: [0, NQ) heads, [NQ, 2 NQ) tails, then these
 enum { STAT_PACKETS = 0, STAT_STEPS, STAT_INTERACT, STAT_SCATT, STAT_ABS, STAT_KILLED, STAT_ESCAPED, STAT_BOUNCE, STAT_MRW_WALKS, STAT_MRW_STEPS };
 
@@ -870,23 +870,22 @@ __device__ __forceinline__ float tau_of_rand(float rand) {
   if (rand > 1.0e-6f) return -logf(1.0f - rand);       // `real` arithmetic in the reference (dust_transfer.f90:1212)
   return rand;
 }
-#define MRW_C0(slot) (c_m.mrw_c0[(size_t)blockIdx.x * NP + (slot)])
-template <int BANK, class CellT>
+template <int BANK>
 __device__ __forceinline__ void start_flight(const Pool& P, int slot, double x, double y, double z, double u, double v, double w,
-                                             const uint4 b /* Philox block 2*ev of this packet */, uint32_t& misc, CellT cell) {
-  const DevModel& m = c_m; const DevRun& r = c_r;
+                                             const uint4 b /* Philox block 2*ev of this packet */, uint32_t& misc) {
+  const DevModel& m = c_m;
   P.F(F_EXTR, slot) = (double)tau_of_rand(u01(b.x));
   P.U(U_RALB, slot) = __float_as_uint(u01(b.y));
   P.F(F_OX, slot) = x; P.F(F_OY, slot) = y; P.F(F_OZ, slot) = z;
   P.U(U_COA, slot) = 0xFFFFFFF9u; P.U(U_COB, slot) = 0;          // null previous cell
   const int istar = intersect_stars(m, x, y, z, u, v, w);
   misc = misc_set_istar(misc, istar);
-  if (r.lMRW) MRW_C0(slot) = id_of_cell(m, cell);               // icell_old of dust_transfer.f90:1242
 }
 
 // =============================================================================
 // Modified random walk (MRW.f90, call site dust_transfer.f90:1222-1239; Min et al. 2009, Robitaille 2010).
-// WARP = false: one packet per lane (phase_absorb / phase_scatter).  WARP = true: the packet-per-warp kernel, where all
+// The walk runs in the packet-per-warp kernel only (WARP = true; the packet-per-lane kernel skips it: a skipped walk is
+// made of ordinary flights, and inside a 32-packet warp it stalled 31 packets for ~10 us).  There all
 // 32 lanes run this for the SAME packet: mutable global memory is read by lane 0 and broadcast (so that the lanes stay
 // bit-identical) and only lane 0 deposits.
 // `ev` is the number of the flight about to start; every step and the closing re-emission take one event number each,
@@ -1111,7 +1110,7 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
       P.U(U_C0A, slot) = ca_; P.U(U_C0B, slot) = cb_;
       P.U(U_PKLO, slot) = pk_lo; P.U(U_PKHI, slot) = pk_hi; P.U(U_EV, slot) = 1u;
       uint32_t misc = pack_misc(lambda, e.flag_star, false, e.flag_ISM, 0, 0);
-      start_flight<BANK>(P, slot, e.x, e.y, e.z, e.u, e.v, e.w, philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u, pk_lo, pk_hi, r.call_index), misc, e.cell);
+      start_flight<BANK>(P, slot, e.x, e.y, e.z, e.u, e.v, e.w, philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u, pk_lo, pk_hi, r.call_index), misc);
       if (GR && r.capt_full) { POS0(0, slot) = e.x; POS0(1, slot) = e.y; POS0(2, slot) = e.z; POS0(3, slot) = (double)tally_index(m, e.cell); }
       P.U(U_MISC, slot) = misc;
       nextq = Q_FLY;
@@ -1267,10 +1266,6 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
         nextq = (__uint_as_float(P.U(U_RALB, slot)) < t_albedo<SM>(m, p_icell, lambda)) ? Q_SCAT : Q_ABS;
       }
       P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;       // (reversed on a bounce)
-      if (TH && r.lMRW) {      // n_iteractions_in_cell (dust_transfer.f90:1242-1249): flights in a row that ended in the cell they started in
-        const bool same = id_of_cell(m, c0) == MRW_C0(slot);
-        P.U(U_MISC, slot) = misc_set_n_in_cell(misc, same ? misc_n_in_cell(misc) + 1 : 0);
-      }
     }
     if (nextq != Q_EMIT) {
       P.F(F_PX, slot) = x0; P.F(F_PY, slot) = y0; P.F(F_PZ, slot) = z0;
@@ -1347,14 +1342,9 @@ __device__ __noinline__ int phase_scatter(int slot, bool valid, Stats& st) {
       P.F(F_U, slot) = u1; P.F(F_V, slot) = v1; P.F(F_W, slot) = w1;
       if ((!TH && r.lmono) || POLA) { P.F(F_S0, slot) = S[0]; if (POLA) { QUV(0, slot) = S[1]; QUV(1, slot) = S[2]; QUV(2, slot) = S[3]; } }
       P.U(U_EV, slot) = ev + 1u;
-      if (TH && r.lMRW && misc_n_in_cell(misc) > 5 && idx >= 0 &&
-          mrw_worth_trying<G, BANK>(cell, idx, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot))) {
-        nextq = Q_MRW;      // dust_transfer.f90:1222-1239: the walk has its own phase (MRW queue), which also starts the flight
-      } else {
-        start_flight<BANK>(P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u1, v1, w1, bnext, misc, cell);
-        if (GR && r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
-        nextq = Q_FLY;
-      }
+      start_flight<BANK>(P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u1, v1, w1, bnext, misc);
+      if (GR && r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
+      nextq = Q_FLY;
       P.U(U_MISC, slot) = misc;
     }
   }
@@ -1415,61 +1405,15 @@ __device__ __noinline__ int phase_absorb(int slot, bool valid, Stats& st) {
       misc = pack_misc(lambda, false, false, false, 0, misc_n_in_cell(misc));      // flag_star = flag_scatt = flag_ISM = .false.
       P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;
       P.U(U_EV, slot) = ev + 1u;
-      if (TH && r.lMRW && misc_n_in_cell(misc) > 5 &&
-          mrw_worth_trying<G, BANK>(cell, idx, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot))) {
-        nextq = Q_MRW;      // dust_transfer.f90:1222-1239: the walk has its own phase (MRW queue), which also starts the flight
-      } else {
-        start_flight<BANK>(P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u, v, w, bnext, misc, cell);
-        if (GR && r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
-        nextq = Q_FLY;
-      }
+      start_flight<BANK>(P, slot, P.F(F_PX, slot), P.F(F_PY, slot), P.F(F_PZ, slot), u, v, w, bnext, misc);
+      if (GR && r.capt_full) { POS0(0, slot) = P.F(F_PX, slot); POS0(1, slot) = P.F(F_PY, slot); POS0(2, slot) = P.F(F_PZ, slot); POS0(3, slot) = (double)idx; }
+      nextq = Q_FLY;
       P.U(U_MISC, slot) = misc;
     }
   }
   if (GR && r.lnRE) {      // E_abs_nRE (omp reduction in the reference, dust_transfer.f90:489): one atomic per warp
     for (int o = 16; o > 0; o >>= 1) e_nRE += __shfl_down_sync(0xffffffffu, e_nRE, o);
     if (lane == 0 && e_nRE != 0.0) atomicAdd(m.tally + m.lay.E_abs_nRE, e_nRE);
-  }
-  return nextq;
-}
-
-// =============================================================================
-// MRW: the modified random walk of packets phase_absorb / phase_scatter found worth trying (dust_transfer.f90:1222-1239),
-// then the start of the next flight.  A phase of its own so that the 32 lanes of a warp all walk: inside ABSORB it
-// stalled the 31 other packets of the warp for the ~10 us of a walk.
-// =============================================================================
-template <class G, bool SM, int BANK, int VAR>
-__device__ __noinline__ int phase_mrw(int slot, bool valid, Stats& st) {
-  const DevModel& m = c_m; const DevRun& r = c_r;
-  const bool POLA = r.lsepar_pola != 0;
-  const Pool P = make_pool<SM, BANK>();
-  using CellT = typename G::CellT;
-  int nextq = Q_NONE;
-  if (valid) {
-    uint32_t misc = P.U(U_MISC, slot);
-    CellT cell; unpack_cell(P.U(U_C0A, slot), P.U(U_C0B, slot), cell);
-    const int idx = tally_index(m, cell);
-    const bool variable_dust = !SM && m.p_n_cells != 1;
-    const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
-    const uint32_t pk_lo = P.U(U_PKLO, slot), pk_hi = P.U(U_PKHI, slot);
-    uint32_t ev = P.U(U_EV, slot);                    // number of the flight about to start
-    double px = P.F(F_PX, slot), py = P.F(F_PY, slot), pz = P.F(F_PZ, slot);
-    double u = P.F(F_U, slot), v = P.F(F_V, slot), w = P.F(F_W, slot);
-    if (idx >= 0) {
-      const MrwOut o = mrw_walk<G, SM, BANK, false>(cell, idx, p_icell, px, py, pz, P.F(F_S0, slot), pk_lo, pk_hi, ev);
-      if (o.steps) {
-        px = o.x; py = o.y; pz = o.z; u = o.u; v = o.v; w = o.w; ev = o.ev;
-        P.F(F_PX, slot) = px; P.F(F_PY, slot) = py; P.F(F_PZ, slot) = pz;
-        P.F(F_U, slot) = u; P.F(F_V, slot) = v; P.F(F_W, slot) = w;
-        if (POLA) { QUV(0, slot) = 0.0; QUV(1, slot) = 0.0; QUV(2, slot) = 0.0; }
-        misc = pack_misc(o.lambda, false, false, false, 0, misc_n_in_cell(misc));
-        P.U(U_EV, slot) = ev;
-        ++st.mrw_w; st.mrw_s += o.steps;
-      }
-    }
-    start_flight<BANK>(P, slot, px, py, pz, u, v, w, philox_block((uint32_t)r.seed, (uint32_t)(r.seed >> 32), 2u * ev, pk_lo, pk_hi, r.call_index), misc, cell);
-    P.U(U_MISC, slot) = misc;
-    nextq = Q_FLY;
   }
   return nextq;
 }
@@ -1538,11 +1482,11 @@ mc_photon_loop_kernel(const int adopt) {
   const bool park_ok = r.park_enable && !adopt;
   // preferred queue order of this warp, one nibble per rank (see the scheduling loop); EMIT stays first everywhere:
   // free slots are refilled at once
-  const unsigned q_order = ((threadIdx.x >> 5) & 3u) == 0u ? (unsigned)(Q_EMIT | (Q_MRW << 4) | (Q_ABS << 8) | (Q_SCAT << 12) | (Q_FLY << 16))
-                         : ((threadIdx.x >> 5) & 3u) == 1u ? (unsigned)(Q_EMIT | (Q_MRW << 4) | (Q_SCAT << 8) | (Q_ABS << 12) | (Q_FLY << 16))
-                                                           : (unsigned)(Q_EMIT | (Q_FLY << 4) | (Q_ABS << 8) | (Q_SCAT << 12) | (Q_MRW << 16));
+  const unsigned q_order = ((threadIdx.x >> 5) & 3u) == 0u ? (unsigned)(Q_EMIT | (Q_ABS << 4) | (Q_SCAT << 8) | (Q_FLY << 12))
+                         : ((threadIdx.x >> 5) & 3u) == 1u ? (unsigned)(Q_EMIT | (Q_SCAT << 4) | (Q_ABS << 8) | (Q_FLY << 12))
+                                                           : (unsigned)(Q_EMIT | (Q_FLY << 4) | (Q_ABS << 8) | (Q_SCAT << 12));
   Stats st = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  SchedStats ss = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+  SchedStats ss = {{0, 0, 0, 0}, {0, 0, 0, 0}};
 #ifdef MCB_DRAIN_PROBE
   int probe_k = 0;
 #endif
@@ -1576,7 +1520,7 @@ mc_photon_loop_kernel(const int adopt) {
 #ifndef MCB_NO_PHASE_AFFINITY
         const unsigned order = q_order;
 #else
-        const unsigned order = 0x43210u;
+        const unsigned order = 0x3210u;
 #endif
 #pragma unroll
         for (int kk = 0; kk < NQ; ++kk) {
@@ -1590,7 +1534,10 @@ mc_photon_loop_kernel(const int adopt) {
         if (threadIdx.x == 0 && P.DRYF()) drain_probe(c_m.work, c_r.n_photons_loop, live, probe_k);
 #endif
         if (park_ok && live <= (unsigned)r.park_live && live > 0u && P.DRYF()) { P.PARK() = 1u; break; }
-        if (best >= 0 && (best_n == 32u || live <= DRAIN_LIVE || polls >= c_r.patience)) {
+        // after the packet counter ran dry nothing refills the queues: waiting for full chunks only adds latency to the
+        // long packet chains the call is now waiting for
+        const bool dry = P.DRYF() != 0u;
+        if (best >= 0 && (best_n == 32u || live <= (dry ? (unsigned)c_r.drain_live_dry : DRAIN_LIVE) || polls >= (dry ? c_r.patience_dry : c_r.patience))) {
           const unsigned hh = P.HEAD(best);
           unsigned av = P.TAIL(best) - hh;
           if (best == Q_EMIT && av > emit_allow) av = emit_allow;
@@ -1599,7 +1546,7 @@ mc_photon_loop_kernel(const int adopt) {
           continue;
         }
         if (best_n == 0u && live == 0u) break;       // every packet of this block is done
-        __nanosleep(250);
+        __nanosleep(dry ? 60 : 250);
       }
     }
     qi = __shfl_sync(0xffffffffu, qi, 0);
@@ -1627,7 +1574,6 @@ mc_photon_loop_kernel(const int adopt) {
         case Q_EMIT: nextq = adopt ? phase_adopt<SM, BANK>(slot, mine) : phase_emit<G, SM, BANK, VAR>(slot, mine, st); break;
         case Q_ABS:  nextq = phase_absorb<G, SM, BANK, VAR>(slot, mine, st); break;
         case Q_SCAT: nextq = phase_scatter<G, SM, BANK, VAR>(slot, mine, st); break;
-        case Q_MRW:  if constexpr (VAR == VAR_THERMAL) nextq = phase_mrw<G, SM, BANK, VAR>(slot, mine, st); else nextq = Q_NONE; break;
         default:     nextq = phase_fly<G, SM, BANK, VAR>(slot, mine, st); break;
       }
       if (!mine) nextq = Q_NONE;
@@ -1644,7 +1590,7 @@ mc_photon_loop_kernel(const int adopt) {
       if (threadIdx.x == 0 && P.DRYF() && live_now != 0xFFFFFFFFu) drain_probe(c_m.work, c_r.n_photons_loop, live_now, probe_k);
 #endif
       live_now = __shfl_sync(0xffffffffu, live_now, 0);                      // warp-uniform decision
-      const bool cont = keep_n > 0 && live_now != 0xFFFFFFFFu && (keep_n >= 28 || live_now <= DRAIN_LIVE);
+      const bool cont = keep_n > 0 && live_now != 0xFFFFFFFFu && (keep_n >= 28 || live_now <= (P.DRYF() ? (unsigned)c_r.drain_live_dry : DRAIN_LIVE));
       const int pushq = (cont && nextq == keep) ? Q_NONE + 1 : nextq;      // kept lanes are not pushed
       push_next(P, slot, pushq, mine, lane);
       if (!cont) break;
@@ -1671,7 +1617,6 @@ mc_photon_loop_kernel(const int adopt) {
           for (int f = 0; f < NU32; ++f) ru[f] = P.U(f, slot);
           ru[NU32] = (uint32_t)k;
           if (POLA_) { rec[16] = QUV(0, slot); rec[17] = QUV(1, slot); rec[18] = QUV(2, slot); }
-          *reinterpret_cast<uint32_t*>(rec + 19) = r.lMRW ? (uint32_t)MRW_C0(slot) : 0u;      // cell the flight in progress started in
         }
       }
     }

@@ -119,7 +119,7 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt, cons
       ralb = __uint_as_float(__ldcg(ru + U_RALB));
       entry = (int)__ldcg(ru + NU32);
       if (POLA) { Sq = __ldcg(rec + 16); Su = __ldcg(rec + 17); Sv = __ldcg(rec + 18); }
-      cell_of_id(m, (int)__ldcg(reinterpret_cast<const uint32_t*>(rec + 19)), c_start);
+      c_start = c0;      // n_iteractions_in_cell restarts with the hand-over (the packet-per-lane kernel does not keep it)
     } else {
       unsigned long long g = 0;
       if (lane == 0) g = atomicAdd(emit_counter, 1ull);
@@ -228,10 +228,7 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt, cons
       const int idx = tally_index(m, c0);
       const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
       if (idx < 0) { ++n_kill; break; }      // interaction in a virtual cell (inconsistent dark-zone mask): drop the packet
-      if (entry == Q_MRW) {      // parked after its interaction, waiting for the walk: straight to the MRW test below
-        entry = Q_FLY;
-        la_base = ev; la_have = true; L = look_ahead<SM, BANK>(pk_lo, pk_hi, la_base, lane);
-      } else {
+      {
       if (!la_have || ev - la_base >= (uint32_t)ENG_LOOK) { la_base = ev; la_have = true; L = look_ahead<SM, BANK>(pk_lo, pk_hi, la_base, lane); }
       const int k = (int)(ev - la_base);
       const bool scatter = (entry == Q_FLY) ? (ralb < t_albedo<SM>(m, p_icell, lambda)) : (entry == Q_SCAT);

@@ -136,8 +136,9 @@ def test_three_launch_call_matches_oracle():
 
 @pytest.mark.parametrize("n2", [1500, 12000])
 def test_modified_random_walk_matches_oracle_and_plain_run(n2):
-    """lMRW on an optically thick disk, small budget (packet-per-warp kernel) and three-launch budget: same physics as
-    the oracle's MRW and as the run without it."""
+    """lMRW on an optically thick disk, small budget (packet-per-warp kernel: every eligible packet walks) and three-launch
+    budget (the packet-per-lane kernel skips the walk, which is always allowed): same physics as the oracle's MRW and as
+    the run without it."""
     P = S.ref41_like(n_photons_eq_th=n2, dark_zone=False, n_rad=40, nz=20, n_rad_in=5, tau_mid=1.0e4)
     O = Oracle(P, fast=True)
     P.l_dark_zone = S.define_dark_zone(P, P.lambda_seuil, 1500.0, O.dark_zone_walker())
@@ -153,10 +154,12 @@ def test_modified_random_walk_matches_oracle_and_plain_run(n2):
     assert t0.stats[8] == 0 and t1.stats[8] > 0 and t1.stats[9] >= t1.stats[8]
     for t in (t0, t1):
         assert t.stats[0] == 128 * n2 and t.stats[5] + t.stats[6] == t.stats[0]
-    assert t1.stats[2] < 0.97 * t0.stats[2]
-    # walks and steps per packet like the oracle's
-    assert abs(t1.stats[8] / to.stats[8] - 1) < 0.1 and abs(t1.stats[9] / to.stats[9] - 1) < 0.1
-    assert abs(t1.stats[2] / to.stats[2] - 1) < 0.05
+    if 128 * n2 <= 1000000:      # the packet-per-warp kernel runs the whole call: walks and steps per packet like the oracle's
+        assert t1.stats[2] < 0.97 * t0.stats[2]
+        assert abs(t1.stats[8] / to.stats[8] - 1) < 0.1 and abs(t1.stats[9] / to.stats[9] - 1) < 0.1
+        assert abs(t1.stats[2] / to.stats[2] - 1) < 0.05
+    else:                        # three launches: only the packets the packet-per-warp kernel finishes walk (MRW)
+        assert t1.stats[8] < to.stats[8]
     lit = (np.asarray(P.l_dark_zone) == 0) & (t0.xKJ_abs > 0) & (t1.xKJ_abs > 0) & (to.xKJ_abs > 0) & (To > 1.5)
     for Ta, Tb in ((T1, To), (T1, T0)):
         rel = np.abs(Ta[lit] - Tb[lit]) / Tb[lit]
