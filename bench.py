@@ -97,7 +97,7 @@ WORKLOADS = {
     "g2": dict(name="G2 Pascucci-like (Pascucci_3.0.para): cylindrical 100x70x1, 61 lambda, one 0.12 um grain, isotropic scattering, tau_V = 100, thermal step",
                b_step=112.0, flags=dict(lisotropic=1)),
     "g4": dict(name="G4 ref4.1_3D-like: cylindrical 100x50x72 two-sided = 720 000 cells, 50 lambda, thermal step, tau_mid(0.81um)=1e3",
-               b_step=120.0, flags={}),
+               b_step=120.0, flags=dict(lsepar_pola=0, lsepar_contrib=0)),
     "g5": dict(name="G5 Voronoi mesh of a synthetic 1M-particle SPH disk (997 016 cells, 15.5 neighbours per cell), 50 lambda, thermal step, tau_mid=1e3",
                b_step=332.0, flags=dict(lsepar_pola=0, lsepar_contrib=0)),
 }
