@@ -121,6 +121,14 @@ class Oracle:
         self._check(self.lib.oracle_temp_finale(self.h, _p(T)))
         return T
 
+    def temp_finale_of(self, xKJ_abs, xT_ech):
+        """Temp_finale (thermal_emission.f90:870-906) of caller-supplied tallies, e.g. the ones downloaded from the GPU"""
+        T = np.zeros(self.P.n_cells, np.float32)
+        a = np.ascontiguousarray(xKJ_abs, np.float64); b = np.ascontiguousarray(xT_ech, np.int32)
+        self.lib.oracle_temp_finale_of.argtypes = [C.c_void_p] * 4
+        self._check(self.lib.oracle_temp_finale_of(self.h, _p(a), _p(b), _p(T)))
+        return T
+
     def temp_finale_nlte(self):
         P = self.P
         T = np.zeros((P.grain_RE_nLTE_end - P.grain_RE_nLTE_start + 1, P.n_cells), np.float32, order="F")

@@ -2190,6 +2190,15 @@ int oracle_run(void* h, const mcb_run_params* r, mcb_tallies* out, int n_threads
   return MCB_OK;
 }
 
+// Temp_finale on tallies supplied by the caller (e.g. downloaded from the GPU): they become thread 0's tallies
+int oracle_temp_finale_of(void* h, const double* xKJ_abs, const int32_t* xT_ech, float* Tdust) {
+  Oracle* O = (Oracle*)h;
+  if (!O->has_grid || !O->has_op || !O->has_em) return MCB_ERR_STATE;
+  O->alloc_tallies(1, true);
+  for (int i = 0; i < O->g.n_cells; ++i) { O->T[0].xKJ_abs[i] = xKJ_abs[i]; O->T[0].xT_ech[i] = xT_ech[i]; }
+  O->Temp_finale(Tdust);
+  return MCB_OK;
+}
 int oracle_temp_finale(void* h, float* Tdust) { Oracle* O = (Oracle*)h; if (O->T.empty()) return MCB_ERR_STATE; O->Temp_finale(Tdust); return MCB_OK; }
 int oracle_temp_finale_nlte(void* h, float* T1g) { Oracle* O = (Oracle*)h; if (O->T.empty() || O->T[0].xT_ech_1grain.empty() || O->T[0].xJ_abs.empty()) return MCB_ERR_STATE; O->Temp_finale_nLTE(T1g); return MCB_OK; }
 

@@ -264,3 +264,17 @@ def test_multi_gpu_behind_the_abi_equals_one_gpu(n_gpus):
     lit = (th1.xKJ_abs > 0) & (thn.xKJ_abs > 0) & (T1 > 1.5)
     assert np.median(np.abs(Tn[lit] - T1[lit]) / T1[lit]) < 0.02
     assert (thn.xT_ech >= 2).all()
+
+
+@pytest.mark.parametrize("name", ["cyl2D", "sph3D"])
+def test_device_temp_finale_equals_the_oracles_on_the_same_tallies(name):
+    """mcfost_b200_temp_finale against the ORACLE's Temp_finale (thermal_emission.f90:870-906, oracle.cpp) fed with the very
+    tallies the device holds: same table walk, `real` output equal to libm rounding."""
+    P = small_problems()[name]()
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(1, 1, 500, 1.0e30, 1, False)
+    Tg = G.temp_finale()
+    G.close()
+    To = Oracle(P).temp_finale_of(tg.xKJ_abs, tg.xT_ech)
+    assert np.allclose(Tg, To, rtol=5e-6, atol=0)
+    assert (Tg > P.T_min).sum() > 0.5 * P.n_cells
