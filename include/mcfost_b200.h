@@ -274,6 +274,11 @@ typedef struct mcb_run_params {
    * immediate re-emission sees running tallies the way a host run with a few threads does.  <= 0 selects the
    * default (1/32). */
   float   max_inflight_fraction;
+  /* The interstellar-radiation-field side loop of run_sed_mc (dust_transfer.f90:941-985, lProDiMo / lML): every packet is
+   * emitted by emit_packet_ISM, a chunk ends when n_photons2 packets that ENTER the model were sent (packets that miss it
+   * are counted in n_phot_envoyes -- the reference's n_phot_envoyes_ISM -- but not towards the chunk), the ray-tracing
+   * accumulators are off.  Not the thermal step. */
+  int32_t lISM_loop;
 } mcb_run_params;
 
 /* ------------------------------------------------------------------------

@@ -130,6 +130,7 @@ class mcb_run_params(C.Structure):
         ("T_spot", C.c_float), ("surf_fraction_spot", C.c_float), ("theta_spot", C.c_float), ("phi_spot", C.c_float),
         ("star1_T", C.c_double), ("tab_lambda", c_double_p), ("lxN_abs", C.c_int32),
         ("lMRW", C.c_int32), ("gamma_MRW", C.c_float), ("lcount_sent", C.c_int32), ("max_inflight_fraction", C.c_float),
+        ("lISM_loop", C.c_int32),
     ]
 
 
@@ -289,7 +290,7 @@ def make_run(**kw) -> Holder:
              lonly_capt_interet=0, capt_inf=1, lorigine=0, capt_interet=1,
              low_mem_th_emission=0, lweight_emission=0, lspot=0, T_spot=0.0, surf_fraction_spot=0.0, theta_spot=0.0,
              phi_spot=0.0, star1_T=0.0, tab_lambda=None, lxN_abs=0,
-             lMRW=0, gamma_MRW=2.0, lcount_sent=0, max_inflight_fraction=0.0)
+             lMRW=0, gamma_MRW=2.0, lcount_sent=0, max_inflight_fraction=0.0, lISM_loop=0)
     unknown = set(kw) - set(d)
     if unknown:
         raise TypeError(f"unknown run parameter(s): {sorted(unknown)}")

@@ -662,6 +662,13 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   { const char* e = getenv("MCB_PARK_LIVE"); if (e && atoi(e) > 0 && atoi(e) <= 256) dr.park_live = atoi(e); }
   { const char* e = getenv("MCB_DEBUG_ABORT_DRY"); dr.debug_abort_dry = (e && e[0] == '1') ? 1 : 0; }   // profiling aid: tallies are incomplete
 #endif
+  dr.lism = r->lISM_loop ? 1 : 0;
+  if (dr.lism) {
+    if (r->letape_th) return fail(h, MCB_ERR_BAD_ARG, "lISM_loop is a side loop of the SED step, not of the thermal step");
+    if (!(m.R_ISM > 0.0)) return fail(h, MCB_ERR_BAD_ARG, "lISM_loop: R_ISM missing (upload_emission)");
+    dr.rt1 = 0; dr.rt2 = 0; dr.n_rt = 0;      // lscatt_ray_tracing1/2 are switched off around the loop (:942-945)
+    dr.count_sent = 0; dr.n_packets_total = 0ull;
+  }
   dr.lMRW = r->lMRW ? 1 : 0;
   dr.gamma_MRW = (r->gamma_MRW > 0.0f) ? (double)r->gamma_MRW : 2.0;
   // concurrency window: immediate re-emission reads RUNNING tallies, so the packets in flight are kept a small

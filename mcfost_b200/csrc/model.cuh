@@ -166,6 +166,7 @@ struct DevRun {
   int park_enable;                      // hand stragglers over to a second small launch (count_sent modes only)
   int debug_abort_dry;                  // profiling aid, development builds (-DMCB_DEV) only: stop when the packet counter runs dry
   int lMRW;                             // modified random walk in the thermal step
+  int lism;                             // ISM side loop (dust_transfer.f90:941-985): every packet from emit_packet_ISM, chunks count the packets that enter the model
   double gamma_MRW;
   unsigned inflight_floor;              // packets in flight per block: never capped below this,
   float inflight_frac_per_block;        // else max_inflight_fraction * packets sent so far / blocks

@@ -992,7 +992,8 @@ __device__ __forceinline__ Emitted<typename G::CellT> emit_packet_core(uint32_t 
   CellT cell; null_cell(cell);
   bool lintersect = true;
   float rand = nextf();
-  if ((double)rand <= t_frac_star<SM>(m, lambda)) {
+  const bool ism_only = !TH && r.lism;      // ISM side loop: emit_packet_ISM for every packet (dust_transfer.f90:967)
+  if (!ism_only && (double)rand <= t_frac_star<SM>(m, lambda)) {
     e.flag_star = true; e.flag_ISM = false;
     const int i_star = select_star(m, lambda, nextf());
     const float rand1 = nextf(), rand2 = nextf(), rand3 = nextf(), rand4 = nextf();
@@ -1017,7 +1018,7 @@ __device__ __forceinline__ Emitted<typename G::CellT> emit_packet_core(uint32_t 
         S0 = S0 * correct_spot;
       }
     }
-  } else if ((double)rand <= t_frac_disk<SM>(m, lambda)) {
+  } else if (!ism_only && (double)rand <= t_frac_disk<SM>(m, lambda)) {
     e.flag_star = false; e.flag_ISM = false;
     const int ic = select_cellule(m, lambda, nextf());
     cell_of_id(m, ic, cell);
@@ -1101,6 +1102,7 @@ __device__ __noinline__ int phase_emit(int slot, bool valid, Stats& st) {
     const Emitted<CellT> e = emit_packet_core<G, SM, BANK, VAR>(pk_lo, pk_hi);
     const int lambda = e.lambda;
     atomicAdd(m.tally + m.lay.n_env + (lambda - 1), 1.0);
+    if (!TH && r.lism && e.lintersect) atomicAdd(m.work + 3 + 2 * my_chunk, 1ull);      // nnfot2 counts the packets that enter the model (:973-976)
     if (e.lintersect) {
       P.F(F_PX, slot) = e.x; P.F(F_PY, slot) = e.y; P.F(F_PZ, slot) = e.z;
       P.F(F_U, slot) = e.u; P.F(F_V, slot) = e.v; P.F(F_W, slot) = e.w;

@@ -25,7 +25,10 @@
 
 namespace mcb {
 
-constexpr int ENG_BLOCK = 512;          // 16 warps per SM, <= 128 registers per thread
+#ifndef MCB_ENG_BLOCK
+#define MCB_ENG_BLOCK 512
+#endif
+constexpr int ENG_BLOCK = MCB_ENG_BLOCK;          // 16 warps per SM, <= 128 registers per thread
 constexpr int ENG_LOOK = 16;            // events of look-ahead
 
 // what one lane of the look-ahead holds for event (base + lane % 16)

@@ -2012,7 +2012,7 @@ struct Oracle {
       for (int nnfot1 = r.nnfot1_start; nnfot1 <= r.n_photons_loop; ++nnfot1) {
         if (((nnfot1 - 1) % n_ranks) != r.rank) continue;       // multi-GPU style chunk partition
         double nnfot2 = 0.0, n_phot_envoyes_in_loop = 0.0, n_phot_sed2 = 0.0;
-        const bool count_sent = r.letape_th || r.lmono0;        // :503-518 (lProDiMo/lML not built)
+        const bool count_sent = (r.letape_th || r.lmono0 || r.lcount_sent) && !r.lISM_loop;        // :503-518; lISM_loop: the side loop of :941-985 counts packets that enter the model
         for (;;) {
           double p_nnfot2 = count_sent ? nnfot2 : n_phot_sed2;
           if (!((p_nnfot2 < (double)n_photons2_local) && (n_phot_envoyes_in_loop < (double)n_phot_lim))) break;
@@ -2026,7 +2026,12 @@ struct Oracle {
           Packet p;
           if (!r.lmono) { float rand = (float)rng_next(&rng); select_wl_em(rand, lambda_local); }
           p.lambda = lambda_local;
-          emit_packet(rng, p);
+          if (r.lISM_loop) {      // dust_transfer.f90:967-970
+            (void)rng_next(&rng);      // (the source-choice draw of emit_packet: keeps the ISM draws on the words the device uses)
+            emit_packet_ISM(rng, p.icell, p.x, p.y, p.z, p.u, p.v, p.w, p.S, p.lintersect);
+            p.flag_ISM = true; p.flag_star = false;
+            if (p.lintersect) n_phot_sed2 += 1.0;
+          } else emit_packet(rng, p);
           p.alive = true; p.flag_scatt = false;
           if (p.lintersect) { propagate_packet(rng, t, lambda_local, p_lambda_local, p); }
           if (p.alive && (!p.flag_ISM)) {
@@ -2180,6 +2185,10 @@ int oracle_run(void* h, const mcb_run_params* r, mcb_tallies* out, int n_threads
   O->r = *r;
   int rc = check_run(O, r); if (rc) return rc;
   if (rec) n_threads = 1;
+  if (r->lISM_loop) {      // dust_transfer.f90:941-945: the ray-tracing accumulators are switched off around the side loop
+    if (r->letape_th) { snprintf(O->err, sizeof O->err, "lISM_loop is not a thermal-step mode"); return MCB_ERR_BAD_ARG; }
+    O->r.lscatt_ray_tracing1 = 0; O->r.lscatt_ray_tracing2 = 0;
+  }
   if (r->lMRW) {
     if (!r->letape_th || !r->lonly_LTE || r->low_mem_th_emission || r->lxJ_abs_step1) { snprintf(O->err, sizeof O->err, "lMRW: thermal step with lonly_LTE only"); return MCB_ERR_UNSUPPORTED; }
     if (O->zeta_tab.empty()) O->initialize_cumulative_zeta();

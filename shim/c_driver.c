@@ -108,6 +108,7 @@ int main(int argc, char **argv) {
   r.T_spot = 0.0f; r.surf_fraction_spot = 0.0f; r.theta_spot = 0.0f; r.phi_spot = 0.0f; r.star1_T = 0.0; r.tab_lambda = NULL;
   r.lxN_abs = 0;
   r.lMRW = 0; r.gamma_MRW = 2.0f; r.lcount_sent = 0; r.max_inflight_fraction = 0.0f;
+  r.lISM_loop = 0;
 
   /* ---- mcb_tallies: caller-allocated, the id = 1 slices of the reference's (..., nb_proc) arrays ---- */
   const size_t nc = (size_t)g.n_cells, nl = (size_t)o.n_lambda, nsed = nl * (size_t)r.N_thet * (size_t)r.N_phi;

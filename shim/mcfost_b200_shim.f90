@@ -107,6 +107,7 @@ module mcfost_b200_shim
      real(c_float)      :: gamma_MRW
      integer(c_int32_t) :: lcount_sent
      real(c_float)      :: max_inflight_fraction
+     integer(c_int32_t) :: lISM_loop
   end type mcb_run_params
 
   type, bind(C) :: mcb_tallies
@@ -356,6 +357,7 @@ contains
     r%lMRW = l2i(lMRW) ; r%gamma_MRW = 2.0                                                   ! MRW.f90:11
     r%lcount_sent = l2i((lProDiMo .or. lML) .and. .not.letape_th)                            ! dust_transfer.f90:512-516
     r%max_inflight_fraction = 0.0
+    r%lISM_loop = 0            ! 1 in the call that replaces the ISM side loop of run_sed_mc (dust_transfer.f90:941-985)
 
     ! the id = 1 slices receive the merged tallies; the other slices are zeroed so that the untouched Fortran reducers
     ! (sum(xKJ_abs(icell,:)) thermal_emission.f90:668, sum(sed(lambda,:,:,:),dim=3) output.f90:3102, sum(n_phot_envoyes(lambda,:))
