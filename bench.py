@@ -93,20 +93,41 @@ FLAGS = dict(lsepar_pola=1, lsepar_contrib=1)
 
 # the other BASELINE configs (bench lines on request: --workload g2|g4|g5; the driver's default line is G1)
 WORKLOADS = {
-    "g1": dict(name=WORKLOAD, b_step=112.0, flags={}),
+    "g1": dict(name=WORKLOAD, b_step=112.0, flags={}, n2=1000000),
     "g2": dict(name="G2 Pascucci-like (Pascucci_3.0.para): cylindrical 100x70x1, 61 lambda, one 0.12 um grain, isotropic scattering, tau_V = 100, thermal step",
-               b_step=112.0, flags=dict(lisotropic=1)),
+               b_step=112.0, flags=dict(lisotropic=1), n2=10000),
+    "g3": dict(name="G3 ref4.1_multi-like (LTE part): cylindrical 100x70x1, two zones with different dust, every opacity / phase-function / emission table per cell (280 MB of emission CDFs in global memory), 50 lambda, thermal step, tau_mid(0.81um)=1e5",
+               b_step=128.0, flags=dict(lsepar_pola=0, lsepar_contrib=0), n2=100000),
     "g4": dict(name="G4 ref4.1_3D-like: cylindrical 100x50x72 two-sided = 720 000 cells, 50 lambda, thermal step, tau_mid(0.81um)=1e3",
-               b_step=120.0, flags=dict(lsepar_pola=0, lsepar_contrib=0)),
+               b_step=120.0, flags=dict(lsepar_pola=0, lsepar_contrib=0), n2=100000),
     "g5": dict(name="G5 Voronoi mesh of a synthetic 1M-particle SPH disk (997 016 cells, 15.5 neighbours per cell), 50 lambda, thermal step, tau_mid=1e3",
-               b_step=332.0, flags=dict(lsepar_pola=0, lsepar_contrib=0)),
+               b_step=332.0, flags=dict(lsepar_pola=0, lsepar_contrib=0), n2=20000),
 }
+
+
+_LANE = "mc_photon_loop_kernel<%s,%d,BANK,0> (packet per lane; calls above 1.2e6 packets end with a launch of mc_warp_engine_kernel, packet per warp, on the parked stragglers; smaller calls run on mc_warp_engine_kernel alone)"
+KERNELS = {"g1": _LANE % ("GeomCyl<0,1>", 1), "g2": _LANE % ("GeomCyl<0,1>", 1), "g3": _LANE % ("GeomCyl<0,0>", 0),
+           "g4": _LANE % ("GeomCyl<1,1>", 1), "g5": _LANE % ("GeomVor", 0)}
+_RESIDENT = ("tables and tallies are L2 / shared-memory resident (DRAM traffic ~ 1e-4 of the algorithmic bytes): the ceiling is the L2 reduction "
+             "rate and the issue rate of a divergent fp64 code, not HBM; hbm_frac is the formal algorithmic-bytes figure")
+_STREAMED = ("per-cell data (%s) exceed shared memory and are read through L2 (126 MB) / HBM with data-dependent addresses: "
+             "roofline against the measured copy bandwidth with SURVEY 8d's algorithmic bytes per step")
+NOTES = {"g1": _RESIDENT, "g2": _RESIDENT,
+         "g3": _STREAMED % "7000 cells x 50 x 100 emission CDFs = 280 MB, per-cell opacities and phase functions",
+         "g4": _STREAMED % "720 000 cells: kappa_factor, tallies, xT_ech = 17 MB, L2-resident",
+         "g5": _STREAMED % "997 016 cells: seeds, neighbour lists (15.5 per cell), kappa_factor, tallies = 110 MB"}
+_ZERO = "tallies are re-zeroed (memset) every step; "
+L2_POLICY = {"g1": _ZERO + "working set is L2-resident by design (0.5 MB tables)", "g2": _ZERO + "working set is L2-resident by design (0.5 MB tables)",
+             "g3": _ZERO + "per-cell tables (300 MB) are larger than L2", "g4": _ZERO + "per-cell data 17 MB, L2-resident; every packet takes its own path",
+             "g5": _ZERO + "mesh and per-cell data (110 MB) are of the order of L2; every packet takes its own path"}
 
 
 def make_problem(n2_total, walker_factory=None, workload="g1"):
     from mcfost_b200 import synthetic as S
     if workload == "g2":
         return S.pascucci_like(tau_V=100.0, n_photons_eq_th=n2_total)
+    if workload == "g3":
+        return S.ref41_multi_like(n_photons_eq_th=n2_total, n_rad=100, nz=70, n_rad_in=20, tau_mid=1.0e5)
     if workload == "g4":
         return S.ref41_3d_like(n_photons_eq_th=n2_total, tau_mid=1.0e3, n_rad=100, nz=50, n_az=72)
     if workload == "g5":
@@ -366,11 +387,11 @@ def gpu_arm(args):
             roof = {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak, "peak_source": peak_src}
         roof.update({"traffic": (traffic or {}).get("dram_bytes_per_launch"),
                      "algorithmic_bytes_per_launch": nb_per_gpu, "hbm_algorithmic_GBps": hbm_achieved, "hbm_frac": hbm_achieved / peak,
-                     "kernel": "mc_photon_loop_kernel<GeomCyl<0,1>,1,BANK,0> (packet per lane) between two launches of mc_warp_engine_kernel (packet per warp)",
+                     "kernel": KERNELS[args.workload],
                      "kernel_ms": last_ms,
                      "phases_ms_last_call": {"packet_per_lane_dry": d_last["steady_ms"], "packet_per_lane_end": d_last["main_end_ms"],
                                              "stragglers_start": d_last["straggler_start_ms"], "stragglers_end": d_last["straggler_end_ms"], "parked": d_last["parked"]},
-                     "note": "tables and tallies are L2 / shared-memory resident (DRAM traffic ~ 1e-4 of the algorithmic bytes): the ceiling is the L2 reduction rate and the issue rate of a divergent fp64 code, not HBM; hbm_frac is the formal algorithmic-bytes figure",
+                     "note": NOTES[args.workload],
                      "fp64_reductions_per_s": atomics_per_s, "steps_per_s": stats[1] / world / (last_ms * 1e-3), "interactions_per_s": stats[2] / world / (last_ms * 1e-3),
                      "steps_per_packet": stats[1] / stats[0], "interactions_per_packet": stats[2] / stats[0], "mrw_steps_per_packet": stats[9] / stats[0]})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -379,7 +400,7 @@ def gpu_arm(args):
                 "config": {"workload": W["name"], "packets_per_step": int(packets_per_step), "lMRW": int(args.mrw),
                            "parallelism": f"packets x{world} (replicated grid, 1 all-reduce/step)",
                            "calls": "one blocking call per step (launch + all-reduce + sync), nothing overlapped",
-                           "l2_policy": "tallies are re-zeroed (memset) every step; working set is L2-resident by design (0.5 MB tables)"},
+                           "l2_policy": L2_POLICY[args.workload]},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "host_buffers": "emission tables in pinned host memory (%d pinned arrays), tallies into host numpy arrays" % len(pinned_keep)},
                 "gpu_launches": int(args.steps * (launches_per_step + 1)),   # + fill_int_kernel (xT_ech reset)
@@ -400,16 +421,20 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n2", type=int, default=1000000, help="packets per chunk per GPU (128 chunks): 1.28e8 packets per step per GPU")
+    ap.add_argument("--n2", type=int, default=0, help="packets per chunk per GPU (128 chunks); default: 1000000 for g1 (1.28e8 packets per step per GPU), "
+                    "10000 for g2 (the Pascucci_3.0.para budget), 100000 for g3 / g4, 20000 for g5")
     ap.add_argument("--cpu-n2", type=int, default=8000, help="packets per chunk of the bounded CPU sample")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--cpu-sweep-max", type=float, default=1.28e7, help="largest sweep budget the reference arm runs (1.28e8 takes minutes of host time)")
     ap.add_argument("--mrw", type=int, default=0, help="1: modified random walk on (both arms); the reference's own behaviour is off")
     ap.add_argument("--strong-steps", type=int, default=3)
-    ap.add_argument("--workload", default="g1", choices=sorted(WORKLOADS), help="g1 = the headline (ref4.1-like); g2 / g4 / g5: the other BASELINE configs")
+    ap.add_argument("--workload", default="g1", choices=sorted(WORKLOADS), help="g1 = the headline (ref4.1-like); g2 / g3 / g4 / g5: the other BASELINE configs")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
     args = ap.parse_args()
+    if args.n2 <= 0:
+        args.n2 = WORKLOADS[args.workload]["n2"]
+    args.cpu_n2 = min(args.cpu_n2, args.n2)
     if args.impl == "reference":
         reference_arm(args)
     else:

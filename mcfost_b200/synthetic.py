@@ -391,22 +391,22 @@ def init_reemission(P):
     cdf = np.zeros((n_lambda, n_T, pnc), order="F")
     kabs = P.kappa_abs_LTE.reshape(pnc, n_lambda)
     tiny_dp = np.finfo(np.float64).tiny
-    for ic in range(pnc):
-        Qcool0 = 0.0
-        for t in range(n_T):
-            integ = 0.0
-            for l in range(n_lambda):
-                integ = integ + kabs[ic, l] * B[l, t]
-            Qcool = integ * cst_E
-            if t == 0:
-                Qcool0 = Qcool
-            q = Qcool - Qcool0
-            logQ[t, ic] = np.log(q) if q > tiny_dp else -1000.0
-            integ3 = np.zeros(n_lambda + 1)
-            for l in range(1, n_lambda + 1):
-                integ3[l] = integ3[l - 1] + kabs[ic, l - 1] * dB[l - 1, t]
-            if integ3[n_lambda] > tiny_dp:
-                cdf[:, t, ic] = integ3[1:] / integ3[n_lambda]
+    # vectorised over the cells; every cell keeps the reference's left-to-right summation order over lambda
+    Qcool0 = np.zeros(pnc)
+    for t in range(n_T):
+        integ = np.zeros(pnc)
+        for l in range(n_lambda):
+            integ = integ + kabs[:, l] * B[l, t]
+        Qcool = integ * cst_E
+        if t == 0:
+            Qcool0 = Qcool
+        q = Qcool - Qcool0
+        pos = q > tiny_dp
+        logQ[t, :] = np.where(pos, np.log(np.where(pos, q, 1.0)), -1000.0)
+        integ3 = np.cumsum(kabs * dB[None, :, t], axis=1)            # (pnc, n_lambda), sequential along lambda
+        tot = integ3[:, n_lambda - 1]
+        ok = tot > tiny_dp
+        cdf[:, t, :] = np.where(ok[None, :], integ3.T / np.where(ok, tot, 1.0)[None, :], 0.0)
     P.log_Qcool_minus_extra_heating = logQ
     P.kdB_dT_CDF = cdf
     return P

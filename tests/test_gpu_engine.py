@@ -283,11 +283,11 @@ def test_device_temp_finale_equals_the_oracles_on_the_same_tallies(name):
 def test_interstellar_side_loop_matches_oracle():
     """lISM_loop: the ISM side loop of run_sed_mc (dust_transfer.f90:941-985, lProDiMo / lML): every packet from
     emit_packet_ISM, chunks end when n_photons2 packets ENTERED the model, n_phot_envoyes counts all of them, xJ_abs is the
-    tally of interest.  The device lets the packets in flight complete when a chunk is full (a few more packets than the
-    oracle), so the comparison is per packet sent."""
+    tally of interest.  The device lets the packets in flight complete when a chunk is full (a few hundred more packets per
+    chunk than the oracle, whatever n_photons2), so the comparison is per packet sent."""
     P = S.ref41_like(n_photons_eq_th=100, dark_zone=False, n_rad=40, nz=20, n_rad_in=5, tau_mid=1.0e3)
     P.R_ISM = 1.2 * np.sqrt(P.Rmax2 + P.zmaxmax ** 2); P.centre_ISM = (0.0, 0.0, 0.0)
-    kw = dict(letape_th=0, lmono=1, lISM_loop=1, lxJ_abs=1, lambda_in=20, p_lambda_in=20, n_photons2=400, n_phot_lim=1.0e30)
+    kw = dict(letape_th=0, lmono=1, lISM_loop=1, lxJ_abs=1, lambda_in=20, p_lambda_in=20, n_photons2=4000, n_phot_lim=1.0e30)
     G = api.PhotonLoop(P)
     k2 = dict(kw)
     tg = G.mc_photon_loop(k2.pop("lambda_in"), k2.pop("p_lambda_in"), k2.pop("n_photons2"), k2.pop("n_phot_lim"), 1, False, **k2)
@@ -298,8 +298,8 @@ def test_interstellar_side_loop_matches_oracle():
     lam = 20
     assert to.n_phot_envoyes[lam - 1] == to.stats[0] and tg.n_phot_envoyes[lam - 1] == tg.stats[0]
     assert tg.sed.sum() == 0 and to.sed.sum() == 0                          # ISM packets are never detected (:548)
-    assert tg.stats[0] >= 128 * 400 and to.stats[0] >= 128 * 400            # packets that miss the model are sent again
-    assert abs(tg.stats[0] / to.stats[0] - 1) < 0.1
+    assert tg.stats[0] >= 128 * 4000 and to.stats[0] >= 128 * 4000           # packets that miss the model are sent again
+    assert 0.99 < tg.stats[0] / to.stats[0] < 1.15
     jg, jo = tg.xJ_abs[:, lam - 1].sum() / tg.stats[0], to.xJ_abs[:, lam - 1].sum() / to.stats[0]
     assert abs(jg / jo - 1) < 0.03
     assert abs(tg.stats[1] / tg.stats[0] / (to.stats[1] / to.stats[0]) - 1) < 0.03
