@@ -365,7 +365,7 @@ int mcfost_b200_stream(mcb_handle *h, uint64_t *stream);
 
 /* ---- post-MC temperature solves on the device-resident tallies of the last call:
  * Temp_finale (thermal_emission.f90:870-906, Temp_LTE with id = 0) -> Tdust(n_cells), `real`;
- * Temp_finale_nLTE (:1010-1075) -> Tdust_1grain(grain_RE_nLTE_start:grain_RE_nLTE_end, n_cells), `real`.
+ * Temp_finale_nLTE (:932-1014) -> Tdust_1grain(grain_RE_nLTE_start:grain_RE_nLTE_end, n_cells), `real`.
  * They read xKJ_abs / xJ_abs / xT_ech* where the photon loop (and the multi-GPU all-reduce) left them, so only
  * the temperatures cross the bus.  Host output pointers. */
 int mcfost_b200_temp_finale(mcb_handle *h, float *Tdust);
@@ -396,6 +396,19 @@ int mcfost_b200_optical_length_tot(mcb_handle *h, int64_t n, int32_t lambda,
         const double *u, const double *v, const double *w,
         const int32_t *icell, double *tau_tot, double *lmin, double *lmax,
         int32_t *n_steps);
+/* compute_column (optical_depth.f90:328-415): from the centre of every cell,
+ * along 4 directions (1: towards the star at the origin, 2: +z, 3: -z, 4:
+ * radially outwards), the sum of l_contrib * factor over the cells crossed.
+ * factor == NULL: the optical depth at wavelength index lambda (type 2:
+ * kappa(lambda) * kappa_factor); else factor[n_cells] is the caller's per-cell
+ * weight (types 1 and 3: CD_units * gas_density [* tab_abundance]) and lambda
+ * is ignored.  centre_x/y/z[n_cells]: the caller's r_grid cos(phi_grid),
+ * r_grid sin(phi_grid), z_grid (or the Voronoi seeds), :362-370.
+ * column: real(n_cells, 4), column-major.  With lvariable_dust the opacity of a
+ * cell is the cell's own (the reference reads the previous cell's, :391-393). */
+int mcfost_b200_compute_column(mcb_handle *h, int32_t lambda, const double *factor,
+        const double *centre_x, const double *centre_y, const double *centre_z,
+        float *column);
 /* physical_length (optical_depth.f90:21-182) with Stokes = 0 (no tallies), as
  * define_dark_zone uses it (optical_depth.f90:1536): walk to optical depth
  * tau. x,y,z,u,v,w,icell updated in place like the reference's inout args. */

@@ -28,7 +28,7 @@ EXPORTS = (
     "mcfost_b200_tally_buffers", "mcfost_b200_download", "mcfost_b200_last_kernel_ms", "mcfost_b200_stream",
     "mcfost_b200_debug_counters", "mcfost_b200_set_overlap", "mcfost_b200_temp_finale", "mcfost_b200_temp_finale_nlte",
     "mcfost_b200_cross_cell", "mcfost_b200_index_cell", "mcfost_b200_move_to_grid",
-    "mcfost_b200_optical_length_tot", "mcfost_b200_physical_length",
+    "mcfost_b200_optical_length_tot", "mcfost_b200_physical_length", "mcfost_b200_compute_column",
     "mcfost_b200_distance_to_closest_wall", "mcfost_b200_mrw_tables",
     "mcfost_b200_multi_init", "mcfost_b200_multi_finalize", "mcfost_b200_multi_last_error", "mcfost_b200_multi_n_gpus",
     "mcfost_b200_multi_handle", "mcfost_b200_multi_upload_grid", "mcfost_b200_multi_upload_dark_zone",
@@ -284,6 +284,14 @@ class PhotonLoop:
         self._check(self.lib.mcfost_b200_optical_length_tot(self.h, C.c_int64(n), C.c_int32(lam), _p(x), _p(y), _p(z), _p(u), _p(v), _p(w),
                                                             _p(icell), _p(tau), _p(lmin), _p(lmax), _p(ns)))
         return dict(tau_tot=tau, lmin=lmin, lmax=lmax, n_steps=ns)
+
+    def compute_column(self, lam, cx, cy, cz, factor=None):
+        """compute_column (optical_depth.f90:328-415): (n_cells, 4) real, column-major; factor None = optical depth at lam"""
+        cx, cy, cz = self._f64(cx, cy, cz)
+        f = None if factor is None else np.ascontiguousarray(factor, np.float64)
+        col = np.zeros((self.P.n_cells, 4), np.float32, order="F")
+        self._check(self.lib.mcfost_b200_compute_column(self.h, C.c_int32(lam), _p(f), _p(cx), _p(cy), _p(cz), _p(col)))
+        return col
 
     def physical_length(self, lam, x, y, z, u, v, w, icell, tau, dark=None):
         if dark is not None:

@@ -961,6 +961,42 @@ __global__ void optical_length_tot_kernel(const __grid_constant__ DevModel m, in
   if (nsteps) nsteps[i] = ns;
 }
 
+// optical_depth.f90:328-415 compute_column: one thread per (cell, direction)
+template <class G>
+__global__ void compute_column_kernel(const __grid_constant__ DevModel m, int lambda, const double* factor, const double* cx, const double* cy,
+                                      const double* cz, float* column) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= 4 * (int64_t)m.n_cells) return;
+  const int icell = (int)(i % m.n_cells) + 1, direction = (int)(i / m.n_cells) + 1;
+  double x0 = cx[icell - 1], y0 = cy[icell - 1], z0 = cz[icell - 1], uu, vv, ww;
+  if (direction == 1) { const double norm = 1.0 / sqrt(x0 * x0 + y0 * y0 + z0 * z0); uu = -x0 * norm; vv = -y0 * norm; ww = -z0 * norm; }
+  else if (direction == 2) { uu = 0.0; vv = 0.0; ww = 1.0; }
+  else if (direction == 3) { uu = 0.0; vv = 0.0; ww = -1.0; }
+  else { uu = x0; vv = y0; ww = 0.0; const double norm = 1.0 / sqrt(uu * uu + vv * vv); uu = uu * norm; vv = vv * norm; }
+  typename G::CellT c0, c_prev, c1;
+  cell_of_id(m, icell, c0); null_cell(c_prev);
+  const DirInv d = dir_invariants(uu, vv, ww);
+  const bool variable_dust = m.p_n_cells != 1;
+  double sum = 0.0;
+  for (int ns = 0; ns < 100000000; ++ns) {
+    if (G::test_exit(m, c0, x0, y0, z0)) break;
+    double x1, y1, z1, lcon, lvoid;
+    G::cross(m, d, x0, y0, z0, uu, vv, ww, c0, c_prev, x1, y1, z1, c1, lcon, lvoid);
+    const int idx = tally_index(m, c0);
+    if (idx >= 0) {
+      double f;
+      if (factor) f = __ldg(factor + idx);
+      else {
+        const int p_icell = variable_dust ? idx + 1 : 1;
+        f = __ldg(m.kappa + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)) * __ldg(m.kappa_factor + idx);
+      }
+      sum = sum + lcon * f;
+    }
+    c_prev = c0; c0 = c1; x0 = x1; y0 = y1; z0 = z1;
+  }
+  column[i] = (float)sum;
+}
+
 // optical_depth.f90:21-182 with Stokes = 0 (no tallies)
 template <class G>
 __global__ void physical_length_kernel(const __grid_constant__ DevModel m, int64_t n, int lambda, double* x, double* y, double* z,
@@ -1152,6 +1188,30 @@ int mcfost_b200_optical_length_tot(mcb_handle* h, int64_t n, int32_t lambda, con
   DISPATCH(optical_length_tot_kernel, h->m, n, lambda, dx, dy, dz, du, dv, dw, dic, dt, dmin, dmax, dns);
   CK(cudaGetLastError());
   s.out(tau_tot, dt, n); s.out(lmin, dmin, n); s.out(lmax, dmax, n); s.out(n_steps, dns, n);
+  CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
+}
+
+int mcfost_b200_compute_column(mcb_handle* h, int32_t lambda, const double* factor, const double* centre_x, const double* centre_y,
+                               const double* centre_z, float* column) {
+  if (!h || !centre_x || !centre_y || !centre_z || !column) return MCB_ERR_BAD_ARG;
+  if (!h->has_grid) return fail(h, MCB_ERR_STATE, "compute_column before upload_grid");
+  if (!factor) {
+    if (!h->has_op) return fail(h, MCB_ERR_STATE, "compute_column (optical depth) before upload_opacity");
+    if (lambda < 1 || lambda > h->m.n_lambda) return fail(h, MCB_ERR_BAD_ARG, "lambda out of range");
+  }
+  const int64_t nc = h->m.n_cells, n = 4 * nc;
+  if (nc == 0) return MCB_OK;
+  CK(cudaSetDevice(h->device));
+  Scratch s{h};
+  const double *dx = s.in(centre_x, nc), *dy = s.in(centre_y, nc), *dz = s.in(centre_z, nc);
+  const double* df = factor ? s.in(factor, nc) : nullptr;
+  float* dcol = s.in<float>(nullptr, n);
+  if (!dx || !dy || !dz || !dcol || (factor && !df)) return fail(h, MCB_ERR_CUDA, "scratch allocation failed");
+  const unsigned nb = (unsigned)((n + 127) / 128);
+  DISPATCH(compute_column_kernel, h->m, lambda, df, dx, dy, dz, dcol);
+  CK(cudaGetLastError());
+  s.out(column, dcol, n);
   CK(cudaStreamSynchronize(h->stream));
   return MCB_OK;
 }

@@ -536,6 +536,13 @@ def define_dark_zone(P, lambda_idx, tau_max=1500.0, physical_length=None):
 # ---------------------------------------------------------------------------
 # the benchmark configurations
 # ---------------------------------------------------------------------------
+def cell_centres(P):
+    """Cartesian centre of every cell, as compute_column builds it (optical_depth.f90:362-370)."""
+    if P.kind == MCB_GRID_VORONOI:
+        return P.vor_xyz[0].copy(), P.vor_xyz[1].copy(), P.vor_xyz[2].copy()
+    return P.r_grid * np.cos(P.phi_grid), P.r_grid * np.sin(P.phi_grid), P.z_grid.copy()
+
+
 def envelope_density(P, azimuthal=0.0):
     """Synthetic envelope for the spherical grids: rho ~ r^-1.5 (1 + cos^2(colatitude))
     with an optional m=1 azimuthal modulation so that phi walls matter in 3D."""

@@ -175,6 +175,15 @@ class Oracle:
                                                        _p(icell), _p(tau), _p(lmin), _p(lmax), _p(ns)))
         return dict(tau_tot=tau, lmin=lmin, lmax=lmax, n_steps=ns)
 
+    def compute_column(self, lam, cx, cy, cz, factor=None):
+        """compute_column (optical_depth.f90:328-415): (n_cells, 4) real, column-major; factor None = optical depth at lam"""
+        cx, cy, cz = self._f64(cx, cy, cz)
+        n = len(cx)
+        f = None if factor is None else np.ascontiguousarray(factor, np.float64)
+        col = np.zeros((n, 4), np.float32, order="F")
+        self._check(self.lib.oracle_compute_column(self.h, C.c_int32(lam), _p(f), _p(cx), _p(cy), _p(cz), _p(col)))
+        return col
+
     def physical_length(self, lam, x, y, z, u, v, w, icell, tau, dark=None):
         if dark is not None:
             self.set_dark_zone(dark)

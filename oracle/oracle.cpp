@@ -1242,6 +1242,41 @@ struct Oracle {
   }
 
   // =====================================================================
+  // optical_depth.f90:328-415  compute_column: from the centre of every cell along 4 directions (towards the star at the
+  // origin, +z, -z, radially outwards), the sum of l_contrib * factor, factor = kappa(lambda) * kappa_factor (type 2) or
+  // the caller's per-cell array (types 1 and 3: CD_units * gas_density [* tab_abundance]).  The centres are the caller's
+  // r_grid cos(phi_grid), r_grid sin(phi_grid), z_grid (or the Voronoi seeds), :362-370.
+  // Deviation, on purpose: with lvariable_dust the reference takes p_icell from the PREVIOUS cell (:391 runs before :393;
+  // index 0 on the first step, out of bounds); the cell itself is used here, as optical_length_tot does (:303-304).
+  // =====================================================================
+  void compute_column(int lambda, const double* factor, const double* cx, const double* cy, const double* cz, float* column) {
+    const int n = g.n_cells;
+    for (int direction = 1; direction <= 4; ++direction) {
+      for (int icell = 1; icell <= n; ++icell) {
+        double x1 = cx[icell - 1], y1 = cy[icell - 1], z1 = cz[icell - 1], u, v, w, norm;
+        if (direction == 1) { norm = 1.0 / std::sqrt(x1 * x1 + y1 * y1 + z1 * z1); u = -x1 * norm; v = -y1 * norm; w = -z1 * norm; }
+        else if (direction == 2) { u = 0.0; v = 0.0; w = 1.0; }
+        else if (direction == 3) { u = 0.0; v = 0.0; w = -1.0; }
+        else { u = x1; v = y1; w = 0.0; norm = 1.0 / std::sqrt(u * u + v * v); u = u * norm; v = v * norm; }
+        int next_cell = icell, icell0 = 0, previous_cell;
+        double sum = 0.0, x0, y0, z0, l, l_contrib, l_void_before;
+        for (;;) {
+          previous_cell = icell0; icell0 = next_cell;
+          x0 = x1; y0 = y1; z0 = z1;
+          if (test_exit_grid(icell0, x0, y0, z0)) break;
+          cross_cell(x0, y0, z0, u, v, w, icell0, previous_cell, x1, y1, z1, next_cell, l, l_contrib, l_void_before);
+          if (icell0 <= n) {
+            const int p_icell = lvariable_dust() ? icell0 : 1;
+            const double f = factor ? factor[icell0 - 1] : kappa(p_icell, lambda) * kappa_factor(icell0);
+            sum = sum + l_contrib * f;
+          }
+        }
+        column[(size_t)(icell - 1) + (size_t)n * (direction - 1)] = (float)sum;
+      }
+    }
+  }
+
+  // =====================================================================
   // scattering.f90:1354-1383  hg
   // =====================================================================
   static void hg(float g_, float rand, int& itheta, double& cospsi) {
@@ -2071,7 +2106,7 @@ struct Oracle {
     }
   }
   // =====================================================================
-  // thermal_emission.f90:1010-1075 Temp_finale_nLTE
+  // thermal_emission.f90:932-1014 Temp_finale_nLTE
   // =====================================================================
   void Temp_finale_nLTE(float* T1g) {
     const int nk = nk_nLTE();
@@ -2259,6 +2294,10 @@ int oracle_optical_length_tot(void* h, int64_t n, int32_t lambda, const double* 
                               const int32_t* icell, double* tau_tot, double* lmin, double* lmax, int32_t* n_steps) {
   Oracle* O = (Oracle*)h;
   for (int64_t i = 0; i < n; ++i) { float tt; int ns; O->optical_length_tot(lambda, icell[i], x[i], y[i], z[i], u[i], v[i], w[i], tt, lmin[i], lmax[i], ns); tau_tot[i] = tt; if (n_steps) n_steps[i] = ns; }
+  return MCB_OK;
+}
+int oracle_compute_column(void* h, int32_t lambda, const double* factor, const double* cx, const double* cy, const double* cz, float* column) {
+  ((Oracle*)h)->compute_column(lambda, factor, cx, cy, cz, column);
   return MCB_OK;
 }
 int oracle_physical_length(void* h, int64_t n, int32_t lambda, double* x, double* y, double* z, double* u, double* v, double* w,

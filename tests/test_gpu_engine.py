@@ -303,3 +303,25 @@ def test_interstellar_side_loop_matches_oracle():
     jg, jo = tg.xJ_abs[:, lam - 1].sum() / tg.stats[0], to.xJ_abs[:, lam - 1].sum() / to.stats[0]
     assert abs(jg / jo - 1) < 0.03
     assert abs(tg.stats[1] / tg.stats[0] / (to.stats[1] / to.stats[0]) - 1) < 0.03
+
+
+@pytest.mark.parametrize("name", ["cyl2D", "cyl3D", "sph2D", "sph3D", "voronoi", "variable_dust"])
+def test_compute_column_bit_exact(name):
+    """compute_column (optical_depth.f90:328-415): optical depth and weighted column from every cell centre along the four
+    directions, `real` output identical to the oracle's (same cross_cell sequence, same summation order)."""
+    if name == "voronoi":
+        P = S.voronoi_disk(n_points=1500, n_photons_eq_th=10)
+    elif name == "variable_dust":
+        P = S.ref41_multi_like(n_photons_eq_th=10)
+    else:
+        P = small_problems()[name]()
+    cx, cy, cz = S.cell_centres(P)
+    O, G = Oracle(P), api.PhotonLoop(P)
+    weight = np.random.default_rng(3).uniform(0.5, 2.0, P.n_cells)
+    for lam, f in ((P.lambda_seuil, None), (1, None), (1, weight)):
+        o, g = O.compute_column(lam, cx, cy, cz, f), G.compute_column(lam, cx, cy, cz, f)
+        assert o.shape == g.shape == (P.n_cells, 4) and np.array_equal(o, g)
+        assert np.isfinite(g).all() and (g >= 0).all() and g[:, 1:3].max() > 0
+    with pytest.raises(api.McfostB200Error):
+        G.compute_column(P.n_lambda + 1, cx, cy, cz)
+    G.close()

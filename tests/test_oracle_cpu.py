@@ -300,3 +300,22 @@ def test_interstellar_radiation_field_packets():
     # the outer disk is heated from outside: more absorbed energy per stellar packet than without the ISM field
     outer = base.r_grid > 0.5 * base.r_grid.max()
     assert t.xKJ_abs[outer].sum() / t.stats[6] > 1.2 * t0.xKJ_abs[outer].sum() / t0.stats[6]
+
+
+def test_compute_column_properties():
+    """compute_column (optical_depth.f90:328-415) of the oracle: the two vertical directions add up to the same column for
+    every cell of a radial ring, direction 1 equals optical_length_tot towards the origin, unit weights give path lengths."""
+    P = small_problems()["cyl2D"]()
+    O = Oracle(P)
+    cx, cy, cz = S.cell_centres(P)
+    lam = P.lambda_seuil
+    col = O.compute_column(lam, cx, cy, cz).astype(np.float64)
+    assert col.shape == (P.n_cells, 4)
+    vert = (col[:, 1] + col[:, 2]).reshape(P.nz, P.n_rad)              # (j, i)
+    assert np.allclose(vert, vert[0][None, :], rtol=2e-6)
+    n = np.sqrt(cx ** 2 + cy ** 2 + cz ** 2)
+    t = O.optical_length_tot(lam, cx, cy, cz, -cx / n, -cy / n, -cz / n, np.arange(1, P.n_cells + 1))
+    assert np.allclose(col[:, 0], t["tau_tot"], rtol=1e-6, atol=1e-30)
+    ones = O.compute_column(1, cx, cy, cz, np.ones(P.n_cells)).astype(np.float64)
+    assert (ones[:, 3] > 0).all() and np.allclose(ones[:, 3] + np.hypot(cx, cy), P.r_lim[-1], rtol=1e-6)      # radial path to the outer edge
+    assert np.allclose((ones[:, 1] + ones[:, 2]).reshape(P.nz, P.n_rad), 2.0 * P.zmax[None, :], rtol=1e-6)           # full height of the column

@@ -11,8 +11,11 @@ t = G.mc_photon_loop(1, 1, 20)                                                  
 print("thermal", t.stats[:7])
 t = G.mc_photon_loop(1, 1, 2000, lsepar_pola=1, max_inflight_fraction=1.0)           # packet-per-lane kernel, parking, adopt launch
 print("three launches", t.stats[:7], G.debug_counters()["parked"], G.debug_counters()["launches"])
-t = G.mc_photon_loop(1, 1, 60, lMRW=1, gamma_MRW=2.0)                                # modified random walk in the packet-per-warp kernel
+Pm = S.ref41_like(n_photons_eq_th=20, dark_zone=False, n_rad=12, nz=8, n_rad_in=3, tau_mid=3.0e5)
+Gm = api.PhotonLoop(Pm)
+t = Gm.mc_photon_loop(1, 1, 20, lMRW=1, gamma_MRW=2.0)                               # modified random walk in the packet-per-warp kernel
 print("mrw", t.stats[:10])
+Gm.close()
 print("closest wall", G.distance_to_closest_wall(np.arange(1, 9), np.full(8, 3.0), np.zeros(8), np.full(8, 0.1)))
 G.set_overlap(2, 2)
 t = G.mc_photon_loop(1, 1, 2000, lsepar_pola=1, max_inflight_fraction=1.0)           # reserved SMs, high-priority adopt launch
@@ -41,8 +44,9 @@ M = api.MultiPhotonLoop(Pi, 1)
 t = M.mc_photon_loop(1, 1, 20)
 print("multi handle", t.stats[:7], M.temp_finale().max())
 M.close()
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from helpers import small_problems
 for name in ("sph2D", "cyl3D", "sph3D"):
-    from tests.helpers import small_problems
     Pg = small_problems()[name]()
     Gg = api.PhotonLoop(Pg)
     print(name, Gg.mc_photon_loop(1, 1, 10).stats[:7], Gg.mc_photon_loop(1, 1, 400, max_inflight_fraction=1.0).stats[:7])
