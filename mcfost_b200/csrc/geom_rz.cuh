@@ -22,6 +22,24 @@ namespace mcb {
 
 struct Cell { int ri, zj, k; };
 
+// Reciprocal / division of the Monte Carlo kernels.  mc_kernel.cu defines MCB_MC_FAST_MATH: MUFU seed (>= 20 bits) + two
+// Newton steps, 5 instructions and <= 2 ulp, instead of the IEEE division sequence (~25 instructions and a slow-path
+// call) -- the photon loop is compared statistically and already contracts FMAs.  api.cu (deterministic kernels, results
+// bit-identical to the reference's arithmetic) does not define it: IEEE division.  Arguments are normal, non-zero numbers.
+#ifdef MCB_MC_FAST_MATH
+__device__ __forceinline__ double mc_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+__device__ __forceinline__ double mc_div(double a, double b) { return a * mc_rcp(b); }
+#else
+__device__ __forceinline__ double mc_rcp(double x) { return 1.0 / x; }
+__device__ __forceinline__ double mc_div(double a, double b) { return a / b; }
+#endif
+
 __device__ __forceinline__ float max_int_f() { return (float)2147483647 * (1.0f - 1.0e-5f); }   // constants.f90:159
 
 // Fortran MODULO(a, p) for p > 0
@@ -83,20 +101,26 @@ __device__ __host__ __forceinline__ Cell cell_from_id(const DevModel& m, int id)
 // SM = false: read-only global loads.
 extern __shared__ __align__(16) unsigned char mcb_smem_raw[];
 __device__ __forceinline__ const double* smd() { return reinterpret_cast<const double*>(mcb_smem_raw); }
-template <bool SM> __device__ __forceinline__ double r_lim_2(const DevModel& m, int i) { return SM ? smd()[m.sm.r_lim_2 + i] : __ldg(m.r_lim_2 + i); }
-template <bool SM> __device__ __forceinline__ double zmax(const DevModel& m, int i) { return SM ? smd()[m.sm.zmax + i - 1] : __ldg(m.zmax + (i - 1)); }
+// Read-only loads from the tables staged in shared memory.  (Measured and dropped in round 2: nvcc rebuilds the address of
+// the dynamic shared array from %cluster_ctarank on every access, S2R + MOV + LEA in front of the LDS; replacing that by
+// `ld.shared` inline asm on a host-provided window base removed the three instructions but, being opaque to the scheduler,
+// cost the packet-per-lane kernel 5 % and gained the packet-per-warp kernel 1 %.)
+__device__ __forceinline__ double smd_ld(const DevModel&, int word) { return smd()[word]; }
+__device__ __forceinline__ float smf_ld(const DevModel&, int word, int k) { return reinterpret_cast<const float*>(smd() + word)[k]; }
+template <bool SM> __device__ __forceinline__ double r_lim_2(const DevModel& m, int i) { return SM ? smd_ld(m, m.sm.r_lim_2 + i) : __ldg(m.r_lim_2 + i); }
+template <bool SM> __device__ __forceinline__ double zmax(const DevModel& m, int i) { return SM ? smd_ld(m, m.sm.zmax + i - 1) : __ldg(m.zmax + (i - 1)); }
 // z_lim(i,j), j = 1..nz+1.  For the default grid z_lim(i,j) = (j-1)*cell_height(i) and z_lim(i,nz+1) = zmax(i)
 // (cylindrical_grid.f90:458-465); upload_grid verifies that bit-for-bit and then only cell_height is kept.
 template <bool SM> __device__ __forceinline__ double z_lim(const DevModel& m, int i, int j) {
   if (m.z_regular) {
     if (j == m.nz + 1) return zmax<SM>(m, i);
-    const double ch = SM ? smd()[m.sm.zl + i - 1] : __ldg(m.cell_height + (i - 1));
+    const double ch = SM ? smd_ld(m, m.sm.zl + i - 1) : __ldg(m.cell_height + (i - 1));
     return (double)(j - 1) * ch;
   }
-  return SM ? smd()[m.sm.zl + (i - 1) + m.n_rad * (j - 1)] : __ldg(m.z_lim + (i - 1) + m.n_rad * (j - 1));
+  return SM ? smd_ld(m, m.sm.zl + (i - 1) + m.n_rad * (j - 1)) : __ldg(m.z_lim + (i - 1) + m.n_rad * (j - 1));
 }
-template <bool SM> __device__ __forceinline__ double tan_phi_lim(const DevModel& m, int k) { return SM ? smd()[m.sm.tan_phi + k - 1] : __ldg(m.tan_phi_lim + (k - 1)); }
-template <bool SM> __device__ __forceinline__ double tan_theta_lim(const DevModel& m, int j) { return SM ? smd()[m.sm.tan_theta + j] : __ldg(m.tan_theta_lim + j); }
+template <bool SM> __device__ __forceinline__ double tan_phi_lim(const DevModel& m, int k) { return SM ? smd_ld(m, m.sm.tan_phi + k - 1) : __ldg(m.tan_phi_lim + (k - 1)); }
+template <bool SM> __device__ __forceinline__ double tan_theta_lim(const DevModel& m, int j) { return SM ? smd_ld(m, m.sm.tan_theta + j) : __ldg(m.tan_theta_lim + j); }
 
 // result of the wall-distance half of a crossing (the next-cell half is only needed when the flight goes on)
 struct HitRZ {
@@ -113,8 +137,8 @@ struct DirInv { double inv_a, inv_w; };
 __device__ __forceinline__ DirInv dir_invariants(double u, double v, double w) {
   DirInv d;
   double a = u * u + v * v;
-  d.inv_a = (a > MCB_TINY_REAL) ? 1.0 / a : MCB_HUGE_REAL;
-  d.inv_w = (fabs(w) > MCB_TINY_REAL) ? 1.0 / w : copysign(MCB_HUGE_DP, w);
+  d.inv_a = (a > MCB_TINY_REAL) ? mc_rcp(a) : MCB_HUGE_REAL;
+  d.inv_w = (fabs(w) > MCB_TINY_REAL) ? mc_rcp(w) : copysign(MCB_HUGE_DP, w);
   return d;
 }
 
@@ -149,7 +173,7 @@ struct GeomCyl {
 
   static __device__ __forceinline__ int z_index_f32(const DevModel& m, double z, int ri) {
     // floor(min(real(abs(z)/zmax(ri)*nz), max_int)) + 1   (cylindrical_grid.f90:868,1116: fp32 cast)
-    float q = (float)(fabs(z) / zmax<SM>(m, ri) * m.nz);
+    float q = (float)(mc_div(fabs(z), zmax<SM>(m, ri)) * m.nz);
     return (int)floorf(fminf(q, max_int_f())) + 1;
   }
 
@@ -333,9 +357,9 @@ struct GeomCyl {
         h.d_phi = par ? 0 : (fwd ? 1 : -1);
         const double tan_angle_lim = tan_phi_lim<SM>(m, kw);
         const double den = v - u * tan_angle_lim;
-        const double t_a = (fabs(u) > (double)1e-6f) ? -x0 / u : (double)1.0e30f;
-        const double t_b = (fabs(den) > (double)1.0e-6f) ? -(y0 - x0 * tan_angle_lim) / den : (double)1.0e30f;
-        t_phi = (tan_angle_lim > 1.0e299) ? t_a : t_b;
+        const bool plane_x0 = tan_angle_lim > 1.0e299;          // wall at phi = pi/2 (mod pi): the plane x = 0
+        const double num = plane_x0 ? -x0 : -(y0 - x0 * tan_angle_lim), dsel = plane_x0 ? u : den;
+        t_phi = (fabs(dsel) > (double)1.0e-6f) ? mc_div(num, dsel) : (double)1.0e30f;      // (one division for both forms)
         if (t_phi < 0.0) t_phi = (double)1.0e30f;
         if (par) t_phi = (double)1.0e30f;
       } else t_phi = MCB_HUGE_REAL;
@@ -383,7 +407,7 @@ struct GeomCyl {
       nxt.ri = ri0; nxt.zj = zj0 + h.d_j; nxt.k = k0;
     } else {
       nxt.ri = ri0;
-      int zj1 = (int)floor(fabs(z1) / zmax<SM>(m, ri0) * m.nz) + 1;       // fp64 here (:1150)
+      int zj1 = (int)floor(mc_div(fabs(z1), zmax<SM>(m, ri0)) * m.nz) + 1;       // fp64 here (:1150)
       if (zj1 > m.nz) zj1 = m.nz + 1;
       if (z1 < 0.0) zj1 = -zj1;
       nxt.zj = zj1;

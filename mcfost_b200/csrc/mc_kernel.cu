@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <mutex>
+#define MCB_MC_FAST_MATH 1      // see geom_rz.cuh (mc_rcp / mc_div): the Monte Carlo kernels only
 #include "handle.cuh"
 #include "transport.cuh"
 #include "warp_engine.cuh"

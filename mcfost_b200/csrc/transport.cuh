@@ -60,26 +60,25 @@ enum { CTL_LIVE = 2 * NQ, CTL_BUSY, CTL_PARK, CTL_DRY, CTL_SENT };      // Pool:
 enum { STAT_PACKETS = 0, STAT_STEPS, STAT_INTERACT, STAT_SCATT, STAT_ABS, STAT_KILLED, STAT_ESCAPED, STAT_BOUNCE, STAT_MRW_WALKS, STAT_MRW_STEPS };
 
 // ---- opacity / thermal table accessors (SM: shared-memory staging, p_n_cells == 1) ----
-__device__ __forceinline__ const float* smf(int word_off) { return reinterpret_cast<const float*>(smd() + word_off); }
 template <bool SM> __device__ __forceinline__ double t_kappa(const DevModel& m, int p_icell, int lambda) {
-  return SM ? smd()[m.sm.kappa + lambda - 1] : __ldg(m.kappa + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)); }
+  return SM ? smd_ld(m, m.sm.kappa + lambda - 1) : __ldg(m.kappa + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)); }
 template <bool SM> __device__ __forceinline__ double t_kappa_abs(const DevModel& m, int p_icell, int lambda) {
-  return SM ? smd()[m.sm.kappa_abs + lambda - 1] : __ldg(m.kappa_abs + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)); }
+  return SM ? smd_ld(m, m.sm.kappa_abs + lambda - 1) : __ldg(m.kappa_abs + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)); }
 template <bool SM> __device__ __forceinline__ float t_albedo(const DevModel& m, int p_icell, int lambda) {
-  return SM ? smf(m.sm.albedo)[lambda - 1] : __ldg(m.albedo + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)); }
+  return SM ? smf_ld(m, m.sm.albedo, lambda - 1) : __ldg(m.albedo + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)); }
 template <bool SM> __device__ __forceinline__ float t_gfac(const DevModel& m, int p_icell, int lambda) {
-  return SM ? smf(m.sm.gfac)[lambda - 1] : __ldg(m.gfac + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)); }
+  return SM ? smf_ld(m, m.sm.gfac, lambda - 1) : __ldg(m.gfac + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)); }
 template <bool SM> __device__ __forceinline__ double t_logQ(const DevModel& m, int t, int p_icell) {      // t 1-based
-  return SM ? smd()[m.sm.logQ + t - 1] : __ldg(m.logQ + (size_t)m.n_T * (p_icell - 1) + t - 1); }
+  return SM ? smd_ld(m, m.sm.logQ + t - 1) : __ldg(m.logQ + (size_t)m.n_T * (p_icell - 1) + t - 1); }
 template <bool SM> __device__ __forceinline__ double t_kdB(const DevModel& m, int l, int t, int p_icell) {  // l, t 1-based
-  return (SM && m.sm.kdB >= 0) ? smd()[m.sm.kdB + (l - 1) + m.n_lambda * (t - 1)]
+  return (SM && m.sm.kdB >= 0) ? smd_ld(m, m.sm.kdB + (l - 1) + m.n_lambda * (t - 1))
             : __ldg(m.kdB + (size_t)m.n_lambda * ((t - 1) + (size_t)m.n_T * (p_icell - 1)) + (l - 1)); }
-template <bool SM> __device__ __forceinline__ double t_cos(const DevModel& m, int k) { return SM ? smd()[m.sm.cos_tab + k] : __ldg(m.cos_tab + k); }
+template <bool SM> __device__ __forceinline__ double t_cos(const DevModel& m, int k) { return SM ? smd_ld(m, m.sm.cos_tab + k) : __ldg(m.cos_tab + k); }
 template <bool SM> __device__ __forceinline__ float t_prob_s11(const DevModel& m, int k, int p_icell, int p_lambda) {
-  return SM ? smf(m.sm.prob_s11)[k] : __ldg(m.prob_s11 + (size_t)(NANG + 1) * ((p_icell - 1) + (size_t)m.p_n_cells * (p_lambda - 1)) + k); }
-template <bool SM> __device__ __forceinline__ double t_spec_cumul(const DevModel& m, int k) { return SM ? smd()[m.sm.spec_cumul + k] : __ldg(m.spec_cumul + k); }
-template <bool SM> __device__ __forceinline__ double t_frac_star(const DevModel& m, int lambda) { return SM ? smd()[m.sm.frac_star + lambda - 1] : __ldg(m.frac_star + lambda - 1); }
-template <bool SM> __device__ __forceinline__ double t_frac_disk(const DevModel& m, int lambda) { return SM ? smd()[m.sm.frac_disk + lambda - 1] : __ldg(m.frac_disk + lambda - 1); }
+  return SM ? smf_ld(m, m.sm.prob_s11, k) : __ldg(m.prob_s11 + (size_t)(NANG + 1) * ((p_icell - 1) + (size_t)m.p_n_cells * (p_lambda - 1)) + k); }
+template <bool SM> __device__ __forceinline__ double t_spec_cumul(const DevModel& m, int k) { return SM ? smd_ld(m, m.sm.spec_cumul + k) : __ldg(m.spec_cumul + k); }
+template <bool SM> __device__ __forceinline__ double t_frac_star(const DevModel& m, int lambda) { return SM ? smd_ld(m, m.sm.frac_star + lambda - 1) : __ldg(m.frac_star + lambda - 1); }
+template <bool SM> __device__ __forceinline__ double t_frac_disk(const DevModel& m, int lambda) { return SM ? smd_ld(m, m.sm.frac_disk + lambda - 1) : __ldg(m.frac_disk + lambda - 1); }
 
 // one block-wide copy of the staged tables into shared memory
 __device__ __forceinline__ void stage_tables(const DevModel& m, int p_lambda_in) {
@@ -106,7 +105,7 @@ __device__ __forceinline__ void cdapres(double cospsi, double sphi, double cphi,
   double spsi = sqrt(1.0 - cospsi * cospsi);
   double a = spsi * cphi, b = spsi * sphi;
   if (fabs(w0) <= (double)0.999999f) {
-    double c = sqrt(1.0 - w0 * w0), cm1 = 1.0 / c, aw0 = a * w0;
+    const double q = 1.0 - w0 * w0, cm1 = rsqrt(q), c = q * cm1, aw0 = a * w0;      // (sqrt and its reciprocal from one rsqrt)
     u1 = (aw0 * u0 - b * v0) * cm1 + cospsi * u0;
     v1 = (aw0 * v0 + b * u0) * cm1 + cospsi * v0;
     w1 = cospsi * w0 - a * c;
@@ -128,6 +127,15 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long l
 
 // ---- heavy libm entry points, not inlined: one copy each in the instruction stream ----
 __device__ __noinline__ double mcb_log(double x) { return log(x); }
+// log of a positive normal number to ~2e-7 absolute: exponent * ln 2 + MUFU.LG2 of the mantissa.  Used where the result is
+// compared with a 100-point cooling table (Temp_LTE: 2e-7 in log Q is 2e-7 / 0.3 of a temperature bin, a relative error of
+// 1e-7 on T) -- ~12 instructions instead of the ~60 of the double-precision log on the latency-critical chain.
+__device__ __forceinline__ double mc_log_table(double x) {
+  const long long b = __double_as_longlong(x);
+  const int e = (int)((b >> 52) & 0x7ff) - 1023;
+  const double mant = __longlong_as_double((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);      // [1, 2)
+  return fma((double)e, 0.6931471805599453, (double)(__log2f((float)mant) * 0.69314718f));
+}
 __device__ __noinline__ void mcb_sincospi(double x, double* s, double* c) { sincospi(x, s, c); }
 
 // ---- random_numbers.f90:32-51 (the two draws are passed in) -------------------
@@ -173,10 +181,10 @@ __device__ __forceinline__ void hg(float g, float rand, int& itheta, double& cos
   double rand_dp = fmin((double)rand, 1.0 - 1e-6);
   if (fabsf(g) > FLT_MIN) {
     double g1 = g, g2 = g1 * g1;
-    double q = (1.0 - g2) / (1.0 - g1 + 2.0 * g1 * rand_dp);
-    cospsi = (1.0 + g2 - q * q) / (2.0 * g1);
+    double q = mc_div(1.0 - g2, 1.0 - g1 + 2.0 * g1 * rand_dp);
+    cospsi = mc_div(1.0 + g2 - q * q, 2.0 * g1);
   } else cospsi = 2.0 * rand_dp - 1.0;
-  itheta = (int)floor(acos(cospsi) * 180.0 / MCB_PI) + 1;
+  itheta = (int)floor(acos(cospsi) * (180.0 / MCB_PI)) + 1;
   if (itheta > NANG) itheta = NANG;
 }
 // ---- scattering.f90:1433-1475 angle_diff_theta_pos ------------------------------
@@ -215,7 +223,7 @@ __device__ __forceinline__ void stokes_update(double M11, double M12, double M22
   const float xnyp = (float)sqrt(v1pk * v1pk + v1pj * v1pj);
   float costhet;
   if (xnyp < 1e-10f) costhet = 1.0f;
-  else costhet = (float)(-1.0 * v1pj / (double)xnyp);
+  else costhet = (float)mc_div(-1.0 * v1pj, (double)xnyp);
   costhet = fminf(1.0f, fmaxf(-1.0f, costhet));
   float cosw = 1.0f - 2.0f * costhet * costhet;                          // cos(2 theta + pi)
   float sinw = -2.0f * costhet * sqrtf(fmaxf(0.0f, 1.0f - costhet * costhet));   // sin(2 theta + pi), theta in [0, pi]
@@ -231,7 +239,7 @@ __device__ __forceinline__ void stokes_update(double M11, double M12, double M22
   // S = RPO.D ; RPO(2,2)=cw RPO(2,3)=sw RPO(3,2)=-sw RPO(3,3)=cw
   S[0] = D0; S[1] = cw * D1 + sw * D2; S[2] = (-sw) * D1 + cw * D2; S[3] = D3;
   if (S[0] > MCB_TINY_REAL) {
-    const double f = M11 * S1_0 / S[0];
+    const double f = mc_div(M11 * S1_0, S[0]);
     S[0] *= f; S[1] *= f; S[2] *= f; S[3] *= f;
   }
 }
@@ -270,21 +278,21 @@ __device__ __forceinline__ LtePre lte_prefetch(const DevModel& m, int idx) {
 // Temp_LTE (thermal_emission.f90:649-706): temperature index and interpolation fraction of the cell
 template <bool SM>
 __device__ __forceinline__ void temp_lte(const DevModel& m, const DevRun& r, int idx, int p_icell, const LtePre pre, int& Ti_out, double& frac_out) {
-  double Qheat = pre.xkj * r.nb_proc_equiv * m.L_packet_th / pre.vol;
+  double Qheat = mc_div(pre.xkj * r.nb_proc_equiv * m.L_packet_th, pre.vol);
   int Ti = 2;
   double frac_T2 = 0.0;       // `frac` is left undefined by the reference at T_min; 0 chosen (same as the oracle)
   if (!(Qheat < MCB_TINY_DP)) {
-    double log_Qheat = mcb_log(Qheat);
+    double log_Qheat = mc_log_table(Qheat);
     if (!(log_Qheat < t_logQ<SM>(m, 1, p_icell))) {
       Ti = pre.Ti;
       while ((t_logQ<SM>(m, Ti, p_icell) < log_Qheat) && (Ti < m.n_T)) ++Ti;
       // another warp may have cached an index computed from a larger running tally: step back down
       while (Ti > 2 && !(t_logQ<SM>(m, Ti - 1, p_icell) < log_Qheat)) --Ti;
       double q1 = t_logQ<SM>(m, Ti - 1, p_icell), q2 = t_logQ<SM>(m, Ti, p_icell);
-      frac_T2 = (log_Qheat - q1) / (q2 - q1);
+      frac_T2 = mc_div(log_Qheat - q1, q2 - q1);
     }
   }
-  atomicMax(m.xT_ech + idx, Ti);
+  if (Ti > pre.Ti) atomicMax(m.xT_ech + idx, Ti);      // (the cache only grows: nothing to write for a packet that finds it current)
   Ti_out = Ti; frac_out = frac_T2;
 }
 template <bool SM>
@@ -1165,6 +1173,9 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
     if (rt1_on) angles_scatt_rt1<BANK>(u, v, w, rt1);       // recomputed per visit (same values as once per flight)
     nextq = Q_FLY;
   }
+  int idx_c = valid ? tally_index(m, c0) : -1;      // tally index of c0 (-1: virtual cell), updated wherever c0 changes
+  CellT c_star; null_cell(c_star);
+  if (i_star_hit > 0) cell_of_id(m, m.star_icell[i_star_hit - 1], c_star);      // the cell of the star this flight points at
   const int n_in = __popc(__ballot_sync(0xffffffffu, valid));
   bool flying = valid, interact = false;
 #pragma unroll 1
@@ -1174,7 +1185,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
     const int n_fly = __popc(__ballot_sync(0xffffffffu, flying));
     if (n_fly == 0 || (it > 0 && 2 * n_fly < n_in)) break;
     if (!flying) continue;
-    if (G::test_exit(m, c0, x0, y0, z0)) {
+    if (idx_c < 0 && G::test_exit(m, c0, x0, y0, z0)) {      // (a real cell is never an exit)
       if (!misc_ism(misc)) {       // the packet leaves the model: detector (capteur, output.f90:294)
         double S[4] = {S0, 0.0, 0.0, 0.0};
         if (POLA) { S[1] = QUV(0, slot); S[2] = QUV(1, slot); S[3] = QUV(2, slot); }
@@ -1186,11 +1197,8 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
       nextq = Q_EMIT; flying = false;
       continue;
     }
-    if (i_star_hit > 0) {
-      CellT cs; cell_of_id(m, m.star_icell[i_star_hit - 1], cs);
-      if (same_cell(c0, cs)) { ++st.kill; nextq = Q_EMIT; flying = false; continue; }     // packet absorbed by the star
-    }
-    const int idx = tally_index(m, c0);
+    if (i_star_hit > 0 && same_cell(c0, c_star)) { ++st.kill; nextq = Q_EMIT; flying = false; continue; }     // packet absorbed by the star
+    const int idx = idx_c;
     double opacity = 0.0;
     int p_icell = 1;
     if (idx >= 0) {
@@ -1199,7 +1207,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
       if (signbit(kf)) {
         // dark-zone bounce (optical_depth.f90:104-112): back to the previous cell's entry point, reversed
         u = -u; v = -v; w = -w;
-        c0 = c_old; x0 = xo; y0 = yo; z0 = zo;
+        c0 = c_old; x0 = xo; y0 = yo; z0 = zo; idx_c = tally_index(m, c0);
         ++st.bounce;
         interact = true; flying = false;
         continue;
@@ -1213,7 +1221,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
     bool lstop = false;
     if (tau_c > extr) {
       lstop = true;
-      l_contrib = l_contrib * (extr / tau_c);
+      l_contrib = l_contrib * mc_div(extr, tau_c);
       l = hit_l_void(h) + l_contrib;
     } else extr = extr - tau_c;
     if (idx >= 0) {
@@ -1247,7 +1255,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
     }
     if (lstop) {
       x0 = x0 + l * u; y0 = y0 + l * v; z0 = z0 + l * w;                               // interaction point
-      if (!G::is_vor && m.l3D && m.kind == 1) c0 = G::index(m, x0, y0, z0);            // optical_depth.f90:162-165
+      if (!G::is_vor && m.l3D && m.kind == 1) { c0 = G::index(m, x0, y0, z0); idx_c = tally_index(m, c0); }      // optical_depth.f90:162-165
       interact = true; flying = false;
       continue;
     }
@@ -1255,7 +1263,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
     CellT c1;
     G::advance(m, h, x0, y0, z0, u, v, w, c0, x1, y1, z1, c1);
     xo = x0; yo = y0; zo = z0; c_old = c0;
-    x0 = x1; y0 = y1; z0 = z1; c0 = c1;
+    x0 = x1; y0 = y1; z0 = z1; c0 = c1; idx_c = tally_index(m, c1);
   }
   if (valid) {
     if (interact) {
@@ -1263,7 +1271,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
       ++st.inter;
       if (!TH && r.lmono) nextq = Q_SCAT;       // forced scattering; the dark-zone / energy tests are done in the SCATTER phase
       else {
-        const int idx = tally_index(m, c0);
+        const int idx = idx_c;
         const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
         nextq = (__uint_as_float(P.U(U_RALB, slot)) < t_albedo<SM>(m, p_icell, lambda)) ? Q_SCAT : Q_ABS;
       }

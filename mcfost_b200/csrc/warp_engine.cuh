@@ -88,9 +88,9 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt, cons
     if (sm_kdB >= 0) for (int i = threadIdx.x; i < m.n_lambda * m.n_T; i += blockDim.x) sd[sm_kdB + i] = m.kdB[i];
     __syncthreads();
   }
-  auto kf_of = [&](int idx) -> double { return sm_kf >= 0 ? smd()[sm_kf + idx] : __ldg(m.kf_dark + idx); };
+  auto kf_of = [&](int idx) -> double { return sm_kf >= 0 ? smd_ld(m, sm_kf + idx) : __ldg(m.kf_dark + idx); };
   auto kdB_of = [&](int l, int t, int p_icell) -> double {      // l, t 1-based
-    return sm_kdB >= 0 ? smd()[sm_kdB + (l - 1) + m.n_lambda * (t - 1)] : t_kdB<SM>(m, l, t, p_icell); };
+    return sm_kdB >= 0 ? smd_ld(m, sm_kdB + (l - 1) + m.n_lambda * (t - 1)) : t_kdB<SM>(m, l, t, p_icell); };
   const int b0 = 2 + 2 * r.n_photons_loop;
   unsigned long long* park_count = m.work + (b0 + 10);
   unsigned long long* park_head = m.work + (b0 + 12);
@@ -153,6 +153,7 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt, cons
     }
     int lambda = misc_lambda(misc);
     int n_in_cell = misc_n_in_cell(misc);
+    int idx_c = tally_index(m, c0);          // tally index of c0 (-1: virtual cell), kept up to date wherever c0 changes
     uint32_t la_base = 0u; bool la_have = false;
     int pre_idx = -1; LtePre pre_raw; pre_raw.xkj = 0.0; pre_raw.vol = 1.0; pre_raw.Ti = 2; double dep_own = 0.0;
     Look L; L.tau = 0; L.ralb = 0; L.rand2 = 0; L.iu = 0; L.iv = 0; L.iw = 1; L.cpsi = 1; L.sphi = 0; L.cphi = 1; L.itheta = 1;
@@ -164,13 +165,18 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt, cons
       if (entry == Q_FLY) {
         const DirInv dinv = dir_invariants(u, v, w);
         const int i_star_hit = misc_istar(misc);
+        CellT c_star; null_cell(c_star);
+        if (i_star_hit > 0) cell_of_id(m, m.star_icell[i_star_hit - 1], c_star);      // the cell of the star this flight points at
         // running tally / temperature index / volume of the cell the flight starts in, requested now and used by the
         // absorption if the flight ends in the same cell (the rule for a trapped packet): the L2 round trip overlaps the flight
-        pre_idx = tally_index(m, c0);
+        pre_idx = idx_c;
         if (pre_idx >= 0) pre_raw = lte_prefetch(m, pre_idx);
         dep_own = 0.0;
+        // opacities of the flight's wavelength (constant dust: one shared-memory read per flight instead of two per cell)
+        const double kap_l = variable_dust ? 0.0 : t_kappa<SM>(m, 1, lambda);
+        const double kabs_S0 = variable_dust ? 0.0 : t_kappa_abs<SM>(m, 1, lambda) * S0;
         for (;;) {
-          if (G::test_exit(m, c0, x0, y0, z0)) {
+          if (idx_c < 0 && G::test_exit(m, c0, x0, y0, z0)) {      // (a real cell is never an exit)
             if (!misc_ism(misc)) {
               const double S[4] = {S0, Sq, Su, Sv};
               if (lane == 0) capteur<BANK>(lambda, u, v, w, S, misc_star(misc), misc_scatt(misc));
@@ -178,35 +184,32 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt, cons
             }
             finished = true; break;
           }
-          if (i_star_hit > 0) {
-            CellT cs; cell_of_id(m, m.star_icell[i_star_hit - 1], cs);
-            if (same_cell(c0, cs)) { ++n_kill; finished = true; break; }
-          }
-          const int idx = tally_index(m, c0);
+          if (i_star_hit > 0 && same_cell(c0, c_star)) { ++n_kill; finished = true; break; }
+          const int idx = idx_c;
           double opacity = 0.0, kf = 0.0;
           int p_icell = 1;
           if (idx >= 0) {
             p_icell = variable_dust ? idx + 1 : 1;
             kf = kf_of(idx);
           }
-          const Hit h = G::distance(m, dinv, x0, y0, z0, u, v, w, c0, c_old);      // (does not depend on kf: overlaps its load)
           if (idx >= 0) {
             if (signbit(kf)) {      // dark-zone bounce (optical_depth.f90:104-112)
               u = -u; v = -v; w = -w;
-              c0 = c_old; x0 = xo; y0 = yo; z0 = zo;
+              c0 = c_old; x0 = xo; y0 = yo; z0 = zo; idx_c = tally_index(m, c0);
               ++n_bounce;
               break;
             }
-            opacity = t_kappa<SM>(m, p_icell, lambda) * kf;
+            opacity = (variable_dust ? t_kappa<SM>(m, p_icell, lambda) : kap_l) * kf;
           }
           ++n_steps;
+          const Hit h = G::distance(m, dinv, x0, y0, z0, u, v, w, c0, c_old);
           double l_contrib = hit_l_contrib(h), l = h.l;
           const double tau_c = l_contrib * opacity;
           bool lstop = false;
-          if (tau_c > extr) { lstop = true; l_contrib = l_contrib * (extr / tau_c); l = hit_l_void(h) + l_contrib; }
+          if (tau_c > extr) { lstop = true; l_contrib = l_contrib * mc_div(extr, tau_c); l = hit_l_void(h) + l_contrib; }
           else extr = extr - tau_c;
           if (idx >= 0) {      // save_radiation_field (radiation_field.f90:53-54)
-            const double dep = t_kappa_abs<SM>(m, p_icell, lambda) * l_contrib * S0;
+            const double dep = variable_dust ? t_kappa_abs<SM>(m, p_icell, lambda) * l_contrib * S0 : kabs_S0 * l_contrib;
             if (idx == pre_idx) dep_own += dep;
             if (lane == 0) {
               atomicAdd(m.tally + m.lay.xKJ + idx, dep);
@@ -215,20 +218,20 @@ mc_warp_engine_kernel(const unsigned long long emit_limit, const int adopt, cons
           }
           if (lstop) {
             x0 = x0 + l * u; y0 = y0 + l * v; z0 = z0 + l * w;
-            if (!G::is_vor && m.l3D && m.kind == 1) c0 = G::index(m, x0, y0, z0);
+            if (!G::is_vor && m.l3D && m.kind == 1) { c0 = G::index(m, x0, y0, z0); idx_c = tally_index(m, c0); }
             break;
           }
           double x1, y1, z1; CellT c1;
           G::advance(m, h, x0, y0, z0, u, v, w, c0, x1, y1, z1, c1);
           xo = x0; yo = y0; zo = z0; c_old = c0;
-          x0 = x1; y0 = y1; z0 = z1; c0 = c1;
+          x0 = x1; y0 = y1; z0 = z1; c0 = c1; idx_c = tally_index(m, c1);
         }
         if (finished) break;
         ++n_inter;
         n_in_cell = same_cell(c0, c_start) ? min(n_in_cell + 1, 255) : 0;      // dust_transfer.f90:1242-1249
       }
       // ---- interaction ending flight ev (dust_transfer.f90:1260-1402)
-      const int idx = tally_index(m, c0);
+      const int idx = idx_c;
       const int p_icell = (variable_dust && idx >= 0) ? idx + 1 : 1;
       if (idx < 0) { ++n_kill; break; }      // interaction in a virtual cell (inconsistent dark-zone mask): drop the packet
       {
