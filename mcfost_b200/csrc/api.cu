@@ -655,7 +655,9 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   dr.park_live = 48;      // measured (profiles/r02_tail.md): the packet-per-lane kernel drains faster than the packet-per-warp kernel down to ~50 packets per SM
   dr.debug_abort_dry = 0;
   dr.patience_dry = 1; dr.drain_live_dry = 96;
+  dr.min_chunk = 32;
 #ifdef MCB_DEV
+  { const char* e = getenv("MCB_MIN_CHUNK"); if (e && atoi(e) > 0 && atoi(e) <= 32) dr.min_chunk = atoi(e); }
   { const char* e = getenv("MCB_PATIENCE_DRY"); if (e && atoi(e) >= 0) dr.patience_dry = atoi(e); }
   { const char* e = getenv("MCB_DRAIN_LIVE_DRY"); if (e && atoi(e) > 0) dr.drain_live_dry = atoi(e); }      // development builds only: a science library does not change its results on an environment variable
   { const char* e = getenv("MCB_PATIENCE"); if (e && atoi(e) > 0 && atoi(e) <= 4096) dr.patience = atoi(e); }

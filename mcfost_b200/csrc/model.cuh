@@ -162,6 +162,7 @@ struct DevRun {
   double zoom, map_size, cos_disk, sin_disk;
   int patience;                         // polls (250 ns each) a warp waits for a full 32-packet chunk before it takes a partial one
   int patience_dry, drain_live_dry;     // the same two thresholds once the packet counter ran dry
+  int min_chunk;                        // a chunk of at least this many packets is taken without waiting (32: only full chunks)
   int park_live;                        // hand over when at most this many packets of a block are in flight (<= PARK_LIVE)
   int park_enable;                      // hand stragglers over to a second small launch (count_sent modes only)
   int debug_abort_dry;                  // profiling aid, development builds (-DMCB_DEV) only: stop when the packet counter runs dry

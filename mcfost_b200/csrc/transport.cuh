@@ -1547,7 +1547,7 @@ mc_photon_loop_kernel(const int adopt) {
         // after the packet counter ran dry nothing refills the queues: waiting for full chunks only adds latency to the
         // long packet chains the call is now waiting for
         const bool dry = P.DRYF() != 0u;
-        if (best >= 0 && (best_n == 32u || live <= (dry ? (unsigned)c_r.drain_live_dry : DRAIN_LIVE) || polls >= (dry ? c_r.patience_dry : c_r.patience))) {
+        if (best >= 0 && (best_n >= (unsigned)c_r.min_chunk || live <= (dry ? (unsigned)c_r.drain_live_dry : DRAIN_LIVE) || polls >= (dry ? c_r.patience_dry : c_r.patience))) {
           const unsigned hh = P.HEAD(best);
           unsigned av = P.TAIL(best) - hh;
           if (best == Q_EMIT && av > emit_allow) av = emit_allow;
