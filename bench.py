@@ -229,8 +229,8 @@ def gpu_arm(args):
     P = make_problem(args.n2 * world, workload=args.workload)
     loop = api.PhotonLoop(P, device=local, rank=rank, n_ranks=world)
     if args.workload == "g1":
-        # dark zone via the library's own deterministic ray-walk kernel (define_dark_zone step 4)
-        P.l_dark_zone = S.define_dark_zone(P, P.lambda_seuil, 1500.0, loop.dark_zone_walker())
+        # dark zone by the library (mcfost_b200_define_dark_zone, optical_depth.f90:1425-1651), which also installs it
+        P.l_dark_zone = loop.define_dark_zone(P.lambda_seuil, 1500.0, P.r_grid, P.z_grid, [(1, P.n_rad)])["l_dark_zone"]
         S.repartition_energie(P)
         loop.upload_dark_zone(P.l_dark_zone)
         loop.upload_emission(P)

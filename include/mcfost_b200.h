@@ -396,6 +396,28 @@ int mcfost_b200_optical_length_tot(mcb_handle *h, int64_t n, int32_t lambda,
         const double *u, const double *v, const double *w,
         const int32_t *icell, double *tau_tot, double *lmin, double *lmax,
         int32_t *n_steps);
+/* define_dark_zone(lambda, p_lambda, tau_max, ldiff_approx) (optical_depth.f90:
+ * 1425-1651) on structured grids: radial and vertical optical-depth sums
+ * (`real` accumulators as in the Fortran), then 11 rays of optical depth
+ * tau_max from the centre of every candidate cell, column after column, each
+ * column seeing the cells the previous ones made dark.  r_grid, z_grid:
+ * (n_cells) cell centres.  regions: (iRmin, iRmax) of regions(:), whose edge
+ * columns are never dark (:1640-1645).  dust_density_sum: NULL, or
+ * sum(dust_density_o_n_grains(:,icell)) when n_zones > 1 (:1634-1638).
+ * Outputs: l_dark_zone(n_cells) as int32, ri_in / ri_out_dark_zone(n_az),
+ * l_is_dark_zone; zj_sup / zj_inf_dark_zone(n_rad, n_az) are IN-OUT (module
+ * arrays that keep their values between calls, zero-initialised in mem.f90:
+ * 162-170; zj_inf may be NULL on a 2D grid).  The `first cell is in diffusion
+ * approximation zone` check (:1629-1632) is the caller's, on ri_in_dark_zone.
+ * The result is also installed as the handle's dark zone (as
+ * mcfost_b200_upload_dark_zone would).  Kept as in the reference: the lower-
+ * half loop of the 3D branch marks nothing (:1607-1610 runs zero times). */
+int mcfost_b200_define_dark_zone(mcb_handle *h, int32_t lambda, float tau_max,
+        const double *r_grid, const double *z_grid,
+        int32_t n_regions, const int32_t *region_iRmin, const int32_t *region_iRmax,
+        const double *dust_density_sum,
+        int32_t *l_dark_zone, int32_t *ri_in_dark_zone, int32_t *ri_out_dark_zone,
+        int32_t *zj_sup_dark_zone, int32_t *zj_inf_dark_zone, int32_t *l_is_dark_zone);
 /* compute_column (optical_depth.f90:328-415): from the centre of every cell,
  * along 4 directions (1: towards the star at the origin, 2: +z, 3: -z, 4:
  * radially outwards), the sum of l_contrib * factor over the cells crossed.

@@ -28,7 +28,7 @@ EXPORTS = (
     "mcfost_b200_tally_buffers", "mcfost_b200_download", "mcfost_b200_last_kernel_ms", "mcfost_b200_stream",
     "mcfost_b200_debug_counters", "mcfost_b200_set_overlap", "mcfost_b200_temp_finale", "mcfost_b200_temp_finale_nlte",
     "mcfost_b200_cross_cell", "mcfost_b200_index_cell", "mcfost_b200_move_to_grid",
-    "mcfost_b200_optical_length_tot", "mcfost_b200_physical_length", "mcfost_b200_compute_column",
+    "mcfost_b200_optical_length_tot", "mcfost_b200_physical_length", "mcfost_b200_compute_column", "mcfost_b200_define_dark_zone",
     "mcfost_b200_distance_to_closest_wall", "mcfost_b200_mrw_tables",
     "mcfost_b200_multi_init", "mcfost_b200_multi_finalize", "mcfost_b200_multi_last_error", "mcfost_b200_multi_n_gpus",
     "mcfost_b200_multi_handle", "mcfost_b200_multi_upload_grid", "mcfost_b200_multi_upload_dark_zone",
@@ -284,6 +284,22 @@ class PhotonLoop:
         self._check(self.lib.mcfost_b200_optical_length_tot(self.h, C.c_int64(n), C.c_int32(lam), _p(x), _p(y), _p(z), _p(u), _p(v), _p(w),
                                                             _p(icell), _p(tau), _p(lmin), _p(lmax), _p(ns)))
         return dict(tau_tot=tau, lmin=lmin, lmax=lmax, n_steps=ns)
+
+    def define_dark_zone(self, lam, tau_max, r_grid, z_grid, regions=(), dust_sum=None, zj_sup=None, zj_inf=None):
+        """define_dark_zone (optical_depth.f90:1425-1651); the result also becomes this handle's dark zone"""
+        P = self.P
+        n_az = max(1, P.n_az)
+        rg, zg = self._f64(r_grid, z_grid)
+        imin = np.ascontiguousarray([r[0] for r in regions], np.int32); imax = np.ascontiguousarray([r[1] for r in regions], np.int32)
+        ds = None if dust_sum is None else np.ascontiguousarray(dust_sum, np.float64)
+        dark = np.zeros(P.n_cells, np.int32); ri_in = np.zeros(n_az, np.int32); ri_out = np.zeros(n_az, np.int32)
+        zs = np.zeros((P.n_rad, n_az), np.int32, order="F") if zj_sup is None else np.asfortranarray(zj_sup, np.int32)
+        zi = np.zeros((P.n_rad, n_az), np.int32, order="F") if zj_inf is None else np.asfortranarray(zj_inf, np.int32)
+        flag = np.zeros(1, np.int32)
+        self._check(self.lib.mcfost_b200_define_dark_zone(self.h, C.c_int32(lam), C.c_float(tau_max), _p(rg), _p(zg), C.c_int32(len(regions)),
+                                                          _p(imin) if len(regions) else None, _p(imax) if len(regions) else None, _p(ds),
+                                                          _p(dark), _p(ri_in), _p(ri_out), _p(zs), _p(zi), _p(flag)))
+        return dict(l_dark_zone=dark, ri_in=ri_in, ri_out=ri_out, zj_sup=zs, zj_inf=zi, l_is_dark_zone=int(flag[0]))
 
     def compute_column(self, lam, cx, cy, cz, factor=None):
         """compute_column (optical_depth.f90:328-415): (n_cells, 4) real, column-major; factor None = optical depth at lam"""

@@ -999,6 +999,156 @@ __global__ void compute_column_kernel(const __grid_constant__ DevModel m, int la
   column[i] = (float)sum;
 }
 
+// ---- define_dark_zone (optical_depth.f90:1425-1651) in ONE block -----------------------------------------------
+// The columns are a sequential chain (the rays of column i bounce off the cells that columns < i made dark), the
+// <= nz x 11 rays of a column are independent: one thread per ray, a block-wide maximum picks the row the reference's
+// nested loops would stop at, then the column is marked and the block moves on.  `real` sums as in the Fortran;
+// cos / sin of the `real` angles come from the host's libm (the compiler's own single-precision cos / sin).
+template <class G>
+__device__ bool dark_walk_exits(const DevModel& m, const int* dark, int lambda, int icell, double x0, double y0, double z0,
+                                double uu, double vv, double ww, float tau) {
+  typename G::CellT c0, c_old, c1;
+  cell_of_id(m, icell, c0); null_cell(c_old);
+  const DirInv d = dir_invariants(uu, vv, ww);
+  double extr = (double)tau;
+  const int i_star_hit = intersect_stars(m, x0, y0, z0, uu, vv, ww);
+  const bool variable_dust = m.p_n_cells != 1;
+  for (int ns = 0; ns < 100000000; ++ns) {
+    if (G::test_exit(m, c0, x0, y0, z0)) return true;
+    if (i_star_hit > 0) {
+      typename G::CellT cs; cell_of_id(m, m.star_icell[i_star_hit - 1], cs);
+      if (same_cell(c0, cs)) return true;
+    }
+    const int idx = tally_index(m, c0);
+    double opacity = 0.0;
+    if (idx >= 0) {
+      const int p_icell = variable_dust ? idx + 1 : 1;
+      opacity = __ldg(m.kappa + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)) * __ldg(m.kappa_factor + idx);
+      if (__ldcg(dark + idx)) return false;
+    }
+    double x1, y1, z1, lcon, lvoid;
+    G::cross(m, d, x0, y0, z0, uu, vv, ww, c0, c_old, x1, y1, z1, c1, lcon, lvoid);
+    const double tau_c = lcon * opacity;
+    if (tau_c > extr) return false;
+    extr = extr - tau_c;
+    c_old = c0; x0 = x1; y0 = y1; z0 = z1; c0 = c1;
+  }
+  return false;
+}
+
+template <class G>
+__global__ void __launch_bounds__(1024, 1)
+define_dark_zone_kernel(const __grid_constant__ DevModel m, int lambda, float tau_max, const double* r_grid, const double* z_grid,
+                        const float* cs_ang, const float* cs_phi, const double* dust_sum, int n_regions, const int* iRmin,
+                        const int* iRmax, int* dark, int* ri_in, int* ri_out, int* zj_sup, int* zj_inf, int* l_is_dark) {
+  constexpr int NA = 11;
+  __shared__ int s_top, s_flag;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int n_rad = m.n_rad, nz = m.nz, n_az = m.n_az;
+  const bool l3D = m.l3D != 0, lcyl = m.kind == MCB_GRID_CYL;
+  const bool variable_dust = m.p_n_cells != 1;
+  auto idx_of = [&](int i, int j, int pk) { Cell c; c.ri = i; c.zj = j; c.k = pk; return real_index(m, c); };
+  auto kap = [&](int idx) {
+    const int p_icell = variable_dust ? idx + 1 : 1;
+    return __ldg(m.kappa + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)) * __ldg(m.kappa_factor + idx);
+  };
+  auto ZS = [&](int i, int pk) -> int& { return zj_sup[(size_t)(i - 1) + (size_t)n_rad * (pk - 1)]; };
+  auto ZI = [&](int i, int pk) -> int& { return zj_inf[(size_t)(i - 1) + (size_t)n_rad * (pk - 1)]; };
+  if (tid == 0) { s_top = 0; s_flag = 0; }
+  for (int i = tid; i < m.n_cells; i += nt) dark[i] = 0;
+  // ---- steps 1 - 3.5: where the optical depth exceeds tau_max radially (both ways) and vertically
+  for (int pk = 1; pk <= n_az; ++pk) {
+    if (tid == 0) {
+      int rin = n_rad, rout = 1;
+      float total_sum = 0.0f;
+      for (int i = 1; i <= n_rad; ++i) {
+        total_sum = (float)((double)total_sum + kap(idx_of(i, 1, pk)) * (m.r_lim[i] - m.r_lim[i - 1]));
+        if (total_sum > tau_max) { rin = i; break; }
+      }
+      total_sum = 0.0f;
+      for (int i = n_rad; i >= 1; --i) {
+        total_sum = (float)((double)total_sum + kap(idx_of(i, 1, pk)) * (m.r_lim[i] - m.r_lim[i - 1]));
+        if (total_sum > tau_max) { rout = i; break; }
+      }
+      if (rout == n_rad) rout = n_rad - 1;
+      ri_in[pk - 1] = rin; ri_out[pk - 1] = rout;
+    }
+    __syncthreads();
+    const int rin = ri_in[pk - 1], rout = ri_out[pk - 1];
+    if (lcyl) {
+      for (int i = rin + tid; i <= rout; i += nt) {
+        float total_sum = 0.0f;
+        for (int j = nz; j >= 1; --j) {
+          total_sum = (float)((double)total_sum + kap(idx_of(i, j, pk)) * (z_lim<false>(m, i, j + 1) - z_lim<false>(m, i, j)));
+          if (total_sum > tau_max) { ZS(i, pk) = j; break; }
+        }
+        if (l3D) {
+          total_sum = 0.0f;
+          for (int j = -nz; j <= -1; ++j) {
+            total_sum = (float)((double)total_sum + kap(idx_of(i, j, pk)) * (z_lim<false>(m, i, -j + 1) - z_lim<false>(m, i, -j)));
+            if (total_sum > tau_max) { ZI(i, pk) = j; break; }
+          }
+        }
+      }
+    } else {
+      for (int i = 1 + tid; i <= n_rad; i += nt) ZS(i, pk) = nz;
+    }
+    __syncthreads();
+  }
+  __threadfence_block();
+  __syncthreads();
+  // ---- step 4: 11 rays from the centre of every candidate cell, column after column
+  for (int pk = 1; pk <= n_az; ++pk) {
+    const float cphi = l3D ? cs_phi[2 * (pk - 1)] : 1.0f, sphi = l3D ? cs_phi[2 * (pk - 1) + 1] : 0.0f;
+    const int rin = max(ri_in[pk - 1], 2), rout = ri_out[pk - 1];
+    for (int half = 0; half < (l3D ? 2 : 1); ++half) {
+      for (int i = rin; i <= rout; ++i) {
+        // upper half: rows j = zj_sup .. 1 (descending); lower half (3D): rows j = zj_inf .. -1 (ascending)
+        const int jfirst = half == 0 ? ZS(i, pk) : max(ZI(i, pk), -nz);
+        const int nrows = half == 0 ? jfirst : (ZI(i, pk) == 0 ? 0 : -jfirst);
+        for (int t = tid; t < nrows * NA; t += nt) {
+          const int row = t / NA, n = t % NA + 1;
+          const int j = half == 0 ? jfirst - row : jfirst + row;
+          const int idx = idx_of(i, j, pk);
+          double x0, y0, z0;
+          if (l3D) {
+            const float r0 = (float)r_grid[idx];
+            x0 = (double)(r0 * cphi); y0 = (double)(r0 * sphi); z0 = half == 0 ? z_grid[idx] : -z_grid[idx];
+          } else { x0 = r_grid[idx]; y0 = 0.0; z0 = z_grid[idx]; }
+          const double u0 = (double)cs_ang[2 * (n - 1)], w0 = (double)cs_ang[2 * (n - 1) + 1];
+          if (!dark_walk_exits<G>(m, dark, lambda, idx + 1, x0, y0, z0, u0, 0.0, w0, tau_max)) {
+            if (half == 0) atomicMax(&s_top, j); else s_flag = 1;
+          }
+        }
+        __syncthreads();
+        const int top = s_top;
+        if (half == 0 && top > 0) {
+          for (int jj = 1 + tid; jj <= top; jj += nt) __stcg(dark + idx_of(i, jj, pk), 1);
+          if (!l3D && tid == 0) s_flag = 1;        // (the 3D upper-half loop does not set l_is_dark_zone, :1575-1582)
+        }
+        __threadfence_block();
+        __syncthreads();
+        if (tid == 0) s_top = 0;
+        __syncthreads();
+      }
+    }
+  }
+  // ---- tidy up (:1620-1648)
+  for (int pk = 1 + tid; pk <= n_az; pk += nt) {
+    for (int i = 1; i <= ri_in[pk - 1] - 1; ++i) ZS(i, pk) = ZS(ri_in[pk - 1], pk);
+    for (int i = ri_out[pk - 1] + 1; i <= n_rad; ++i) ZS(i, pk) = ZS(ri_out[pk - 1], pk);
+    if (l3D) {
+      for (int i = 1; i <= ri_in[pk - 1] - 1; ++i) ZI(i, pk) = ZI(ri_in[pk - 1], pk);
+      for (int i = ri_out[pk - 1] + 1; i <= n_rad; ++i) ZI(i, pk) = ZI(ri_out[pk - 1], pk);
+    }
+  }
+  if (dust_sum) for (int i = tid; i < m.n_cells; i += nt) if (dust_sum[i] < MCB_TINY_REAL) dark[i] = 0;
+  __syncthreads();
+  for (int q = 0; q < n_regions; ++q)
+    for (int j = 1 + tid; j <= nz; j += nt) { dark[idx_of(iRmin[q], j, 1)] = 0; dark[idx_of(iRmax[q], j, 1)] = 0; }
+  if (tid == 0) *l_is_dark = s_flag;
+}
+
 // optical_depth.f90:21-182 with Stokes = 0 (no tallies)
 template <class G>
 __global__ void physical_length_kernel(const __grid_constant__ DevModel m, int64_t n, int lambda, double* x, double* y, double* z,
@@ -1192,6 +1342,64 @@ int mcfost_b200_optical_length_tot(mcb_handle* h, int64_t n, int32_t lambda, con
   s.out(tau_tot, dt, n); s.out(lmin, dmin, n); s.out(lmax, dmax, n); s.out(n_steps, dns, n);
   CK(cudaStreamSynchronize(h->stream));
   return MCB_OK;
+}
+
+int mcfost_b200_define_dark_zone(mcb_handle* h, int32_t lambda, float tau_max, const double* r_grid, const double* z_grid,
+                                 int32_t n_regions, const int32_t* region_iRmin, const int32_t* region_iRmax, const double* dust_density_sum,
+                                 int32_t* l_dark_zone, int32_t* ri_in_dark_zone, int32_t* ri_out_dark_zone, int32_t* zj_sup_dark_zone,
+                                 int32_t* zj_inf_dark_zone, int32_t* l_is_dark_zone) {
+  if (!h || !r_grid || !z_grid || !l_dark_zone || !ri_in_dark_zone || !ri_out_dark_zone || !zj_sup_dark_zone) return MCB_ERR_BAD_ARG;
+  if (!h->has_grid || !h->has_op) return fail(h, MCB_ERR_STATE, "define_dark_zone before upload_grid/opacity");
+  if (h->gk == GK_VOR) return fail(h, MCB_ERR_UNSUPPORTED, "define_dark_zone: structured grids only (the reference has no dark zone on a Voronoi mesh)");
+  const DevModel& m = h->m;
+  if (lambda < 1 || lambda > m.n_lambda) return fail(h, MCB_ERR_BAD_ARG, "lambda out of range");
+  if (n_regions < 0 || (n_regions > 0 && (!region_iRmin || !region_iRmax))) return fail(h, MCB_ERR_BAD_ARG, "regions");
+  for (int q = 0; q < n_regions; ++q)
+    if (region_iRmin[q] < 1 || region_iRmin[q] > m.n_rad || region_iRmax[q] < 1 || region_iRmax[q] > m.n_rad) return fail(h, MCB_ERR_BAD_ARG, "region radius index out of range");
+  if (m.l3D && !zj_inf_dark_zone) return fail(h, MCB_ERR_BAD_ARG, "zj_inf_dark_zone is needed on a 3D grid");
+  if (!m.r_lim) return fail(h, MCB_ERR_STATE, "define_dark_zone: r_lim was not uploaded (mcb_grid::r_lim)");
+  CK(cudaSetDevice(h->device));
+  const int n_az = m.n_az > 0 ? m.n_az : 1;
+  const int64_t nc = m.n_cells, nzs = (int64_t)m.n_rad * n_az;
+  // cos / sin of the `real` angles (optical_depth.f90:1532,1557) with the host's single-precision libm
+  std::vector<float> cs_ang(22), cs_phi(2 * (size_t)n_az);
+  for (int n = 1; n <= 11; ++n) {
+    const float angle = (float)(MCB_PI * (double)(float)n / (double)(float)12);
+    cs_ang[2 * (n - 1)] = cosf(angle); cs_ang[2 * (n - 1) + 1] = sinf(angle);
+  }
+  for (int pk = 1; pk <= n_az; ++pk) {
+    const float phi = (float)(2.0 * MCB_PI * (double)((float)pk - 0.5f) / (double)(float)n_az);
+    cs_phi[2 * (pk - 1)] = cosf(phi); cs_phi[2 * (pk - 1) + 1] = sinf(phi);
+  }
+  std::vector<int32_t> zero_inf;
+  if (!zj_inf_dark_zone) zero_inf.assign((size_t)nzs, 0);
+  Scratch s{h};
+  const double *drg = s.in(r_grid, nc), *dzg = s.in(z_grid, nc);
+  const double* dds = dust_density_sum ? s.in(dust_density_sum, nc) : nullptr;
+  const float *dang = s.in(cs_ang.data(), 22), *dphi = s.in(cs_phi.data(), 2 * (int64_t)n_az);
+  const int *dmin = n_regions ? s.in(region_iRmin, n_regions) : nullptr, *dmax = n_regions ? s.in(region_iRmax, n_regions) : nullptr;
+  int *ddark = s.in<int>(nullptr, nc), *drin = s.in<int>(nullptr, n_az), *drout = s.in<int>(nullptr, n_az);
+  int *dzs = s.in(zj_sup_dark_zone, nzs), *dzi = s.in(zj_inf_dark_zone ? zj_inf_dark_zone : zero_inf.data(), nzs);
+  int* dflag = s.in<int>(nullptr, 1);
+  if (!drg || !dzg || !dang || !dphi || !ddark || !drin || !drout || !dzs || !dzi || !dflag) return fail(h, MCB_ERR_CUDA, "scratch allocation failed");
+#define DDZ(GEOM) define_dark_zone_kernel<GEOM><<<1, 1024, 0, h->stream>>>(h->m, lambda, tau_max, drg, dzg, dang, dphi, dds, n_regions, dmin, dmax, ddark, drin, drout, dzs, dzi, dflag)
+  switch (h->gk) {
+    case GK_CYL2D: DDZ(GeomCyl<false>); break;
+    case GK_CYL3D: DDZ(GeomCyl<true>); break;
+    case GK_SPH2D: DDZ(GeomSph<false>); break;
+    case GK_SPH3D: DDZ(GeomSph<true>); break;
+    default: break;
+  }
+#undef DDZ
+  CK(cudaGetLastError());
+  s.out(l_dark_zone, ddark, nc); s.out(ri_in_dark_zone, drin, n_az); s.out(ri_out_dark_zone, drout, n_az);
+  s.out(zj_sup_dark_zone, dzs, nzs);
+  if (zj_inf_dark_zone) s.out(zj_inf_dark_zone, dzi, nzs);
+  int flag = 0;
+  CK(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (l_is_dark_zone) *l_is_dark_zone = flag;
+  return mcfost_b200_upload_dark_zone(h, l_dark_zone);      // the photon loop of this handle uses the new dark zone from now on
 }
 
 int mcfost_b200_compute_column(mcb_handle* h, int32_t lambda, const double* factor, const double* centre_x, const double* centre_y,

@@ -175,6 +175,21 @@ class Oracle:
                                                        _p(icell), _p(tau), _p(lmin), _p(lmax), _p(ns)))
         return dict(tau_tot=tau, lmin=lmin, lmax=lmax, n_steps=ns)
 
+    def define_dark_zone(self, lam, tau_max, r_grid, z_grid, regions=(), dust_sum=None, zj_sup=None, zj_inf=None):
+        """define_dark_zone (optical_depth.f90:1425-1651); the result also becomes the oracle's dark zone"""
+        P = self.P
+        n_az = max(1, P.n_az)
+        rg, zg = self._f64(r_grid, z_grid)
+        imin = np.ascontiguousarray([r[0] for r in regions], np.int32); imax = np.ascontiguousarray([r[1] for r in regions], np.int32)
+        ds = None if dust_sum is None else np.ascontiguousarray(dust_sum, np.float64)
+        dark = np.zeros(P.n_cells, np.int32); ri_in = np.zeros(n_az, np.int32); ri_out = np.zeros(n_az, np.int32)
+        zs = np.zeros((P.n_rad, n_az), np.int32, order="F") if zj_sup is None else np.asfortranarray(zj_sup, np.int32)
+        zi = np.zeros((P.n_rad, n_az), np.int32, order="F") if zj_inf is None else np.asfortranarray(zj_inf, np.int32)
+        flag = np.zeros(1, np.int32)
+        self._check(self.lib.oracle_define_dark_zone(self.h, C.c_int32(lam), C.c_float(tau_max), _p(rg), _p(zg), C.c_int32(len(regions)),
+                                                     _p(imin), _p(imax), _p(ds), _p(dark), _p(ri_in), _p(ri_out), _p(zs), _p(zi), _p(flag)))
+        return dict(l_dark_zone=dark, ri_in=ri_in, ri_out=ri_out, zj_sup=zs, zj_inf=zi, l_is_dark_zone=int(flag[0]))
+
     def compute_column(self, lam, cx, cy, cz, factor=None):
         """compute_column (optical_depth.f90:328-415): (n_cells, 4) real, column-major; factor None = optical depth at lam"""
         cx, cy, cz = self._f64(cx, cy, cz)

@@ -1277,6 +1277,132 @@ struct Oracle {
   }
 
   // =====================================================================
+  // optical_depth.f90:1425-1651  define_dark_zone.  `real` sums and angles as in the Fortran; r_grid / z_grid are the
+  // caller's cell centres; zj_sup / zj_inf are in-out (module arrays that keep their values between calls, mem.f90:162-170);
+  // dust_sum = sum(dust_density_o_n_grains(:,icell)) when n_zones > 1, else null; regions as (iRmin, iRmax) pairs.
+  // Kept as they are: the lower-half loop of the 3D branch marks nothing (`do jj=1,-1` runs zero times, :1607-1610) and
+  // starts its rays at z0 = -z_grid of a cell below the midplane (:1597); a stale zj_inf = 0 would index row 0 (:1591),
+  // those rows are skipped here.
+  // =====================================================================
+  void define_dark_zone(int lambda, float tau_max, const double* r_grid, const double* z_grid, int n_regions, const int* iRmin,
+                        const int* iRmax, const double* dust_sum, int* dark_out, int* ri_in, int* ri_out, int* zj_sup, int* zj_inf,
+                        int* l_is_dark) {
+    const int nbre_angle = 11;
+    const int n_rad = g.n_rad, nz = g.nz, n_az = g.n_az;
+    const bool l3D = g.l3D != 0, lcyl = g.kind == MCB_GRID_CYL;
+    auto ZS = [&](int i, int pk) -> int& { return zj_sup[(size_t)(i - 1) + (size_t)n_rad * (pk - 1)]; };
+    auto ZI = [&](int i, int pk) -> int& { return zj_inf[(size_t)(i - 1) + (size_t)n_rad * (pk - 1)]; };
+    auto kap = [&](int icell) { const int p_icell = lvariable_dust() ? icell : 1; return kappa(p_icell, lambda) * kappa_factor(icell); };
+    for (int pk = 1; pk <= n_az; ++pk) {
+      ri_in[pk - 1] = n_rad; ri_out[pk - 1] = 1;
+      float total_sum = 0.0f;
+      for (int i = 1; i <= n_rad; ++i) {
+        const int icell = cell_map(i, 1, pk);
+        total_sum = (float)((double)total_sum + kap(icell) * (r_lim(i) - r_lim(i - 1)));
+        if (total_sum > tau_max) { ri_in[pk - 1] = i; break; }
+      }
+      total_sum = 0.0f;
+      for (int i = n_rad; i >= 1; --i) {
+        const int icell = cell_map(i, 1, pk);
+        total_sum = (float)((double)total_sum + kap(icell) * (r_lim(i) - r_lim(i - 1)));
+        if (total_sum > tau_max) { ri_out[pk - 1] = i; break; }
+      }
+      if (ri_out[pk - 1] == n_rad) ri_out[pk - 1] = n_rad - 1;
+      if (lcyl) {
+        for (int i = ri_in[pk - 1]; i <= ri_out[pk - 1]; ++i) {
+          total_sum = 0.0f;
+          for (int j = nz; j >= 1; --j) {
+            const int icell = cell_map(i, j, pk);
+            total_sum = (float)((double)total_sum + kap(icell) * (z_lim(i, j + 1) - z_lim(i, j)));
+            if (total_sum > tau_max) { ZS(i, pk) = j; break; }
+          }
+        }
+        if (l3D) {
+          for (int i = ri_in[pk - 1]; i <= ri_out[pk - 1]; ++i) {
+            total_sum = 0.0f;
+            for (int j = -nz; j <= -1; ++j) {
+              const int icell = cell_map(i, j, pk);
+              total_sum = (float)((double)total_sum + kap(icell) * (z_lim(i, -j + 1) - z_lim(i, -j)));
+              if (total_sum > tau_max) { ZI(i, pk) = j; break; }
+            }
+          }
+        }
+      } else {
+        for (int i = 1; i <= n_rad; ++i) ZS(i, pk) = nz;
+      }
+    }
+    *l_is_dark = 0;
+    std::fill(dark.begin(), dark.end(), 0);
+    ThreadTallies t; for (double& q : t.stats) q = 0;
+    const double Stokes[4] = {0, 0, 0, 0};
+    // one ray (optical_depth.f90:1531-1541); returns flag_sortie
+    auto ray = [&](int icell, double x0, double y0, double z0, int n) {
+      const float angle = (float)(pi * (double)(float)n / (double)(float)(nbre_angle + 1));      // pi * real(n) / real(nbre_angle+1) -> real
+      double u0 = (double)std::cos(angle), v0 = 0.0, w0 = (double)std::sin(angle);
+      int ic = icell; bool fs = false, alive = true; float lt = 0;
+      physical_length(t, lambda, 1, Stokes, ic, x0, y0, z0, u0, v0, w0, false, false, tau_max, lt, fs, alive, false);
+      return fs;
+    };
+    if (!l3D) {
+      for (int i = std::max(ri_in[0], 2); i <= ri_out[0]; ++i) {
+        bool done = false;
+        for (int j = ZS(i, 1); j >= 1 && !done; --j) {
+          const int icell = cell_map(i, j, 1);
+          for (int n = 1; n <= nbre_angle; ++n) {
+            if (!ray(icell, r_grid[icell - 1], 0.0, z_grid[icell - 1], n)) {
+              for (int jj = 1; jj <= j; ++jj) dark[cell_map(i, jj, 1)] = 1;
+              *l_is_dark = 1;
+              done = true; break;
+            }
+          }
+        }
+      }
+    } else {
+      for (int pk = 1; pk <= n_az; ++pk) {
+        const float phi = (float)(2.0 * pi * (double)((float)pk - 0.5f) / (double)(float)n_az);
+        for (int i = std::max(ri_in[pk - 1], 2); i <= ri_out[pk - 1]; ++i) {
+          bool done = false;
+          for (int j = ZS(i, pk); j >= 1 && !done; --j) {
+            const int icell = cell_map(i, j, pk);
+            for (int n = 1; n <= nbre_angle; ++n) {
+              const float r0 = (float)r_grid[icell - 1];
+              const double x0 = (double)(r0 * std::cos(phi)), y0 = (double)(r0 * std::sin(phi)), z0 = z_grid[icell - 1];
+              if (!ray(icell, x0, y0, z0, n)) {
+                for (int jj = 1; jj <= j; ++jj) dark[cell_map(i, jj, pk)] = 1;
+                done = true; break;
+              }
+            }
+          }
+        }
+        for (int i = std::max(ri_in[pk - 1], 2); i <= ri_out[pk - 1]; ++i) {
+          bool done = false;
+          for (int j = ZI(i, pk); j <= -1 && !done; ++j) {
+            if (j < -nz) continue;
+            const int icell = cell_map(i, j, pk);
+            for (int n = 1; n <= nbre_angle; ++n) {
+              const float r0 = (float)r_grid[icell - 1];
+              const double x0 = (double)(r0 * std::cos(phi)), y0 = (double)(r0 * std::sin(phi)), z0 = -z_grid[icell - 1];
+              if (!ray(icell, x0, y0, z0, n)) { *l_is_dark = 1; done = true; break; }      // (`do jj=1,-1`: nothing is marked)
+            }
+          }
+        }
+      }
+    }
+    for (int pk = 1; pk <= n_az; ++pk) {
+      for (int i = 1; i <= ri_in[pk - 1] - 1; ++i) ZS(i, pk) = ZS(ri_in[pk - 1], pk);
+      for (int i = ri_out[pk - 1] + 1; i <= n_rad; ++i) ZS(i, pk) = ZS(ri_out[pk - 1], pk);
+      if (l3D) {
+        for (int i = 1; i <= ri_in[pk - 1] - 1; ++i) ZI(i, pk) = ZI(ri_in[pk - 1], pk);
+        for (int i = ri_out[pk - 1] + 1; i <= n_rad; ++i) ZI(i, pk) = ZI(ri_out[pk - 1], pk);
+      }
+    }
+    if (dust_sum) for (int icell = 1; icell <= g.n_cells; ++icell) if (dust_sum[icell - 1] < tiny_real) dark[icell] = 0;
+    for (int q = 0; q < n_regions; ++q)
+      for (int j = 1; j <= nz; ++j) { dark[cell_map(iRmin[q], j, 1)] = 0; dark[cell_map(iRmax[q], j, 1)] = 0; }
+    for (int icell = 1; icell <= g.n_cells; ++icell) dark_out[icell - 1] = dark[icell];
+  }
+
+  // =====================================================================
   // scattering.f90:1354-1383  hg
   // =====================================================================
   static void hg(float g_, float rand, int& itheta, double& cospsi) {
@@ -2294,6 +2420,12 @@ int oracle_optical_length_tot(void* h, int64_t n, int32_t lambda, const double* 
                               const int32_t* icell, double* tau_tot, double* lmin, double* lmax, int32_t* n_steps) {
   Oracle* O = (Oracle*)h;
   for (int64_t i = 0; i < n; ++i) { float tt; int ns; O->optical_length_tot(lambda, icell[i], x[i], y[i], z[i], u[i], v[i], w[i], tt, lmin[i], lmax[i], ns); tau_tot[i] = tt; if (n_steps) n_steps[i] = ns; }
+  return MCB_OK;
+}
+int oracle_define_dark_zone(void* h, int32_t lambda, float tau_max, const double* r_grid, const double* z_grid, int32_t n_regions,
+                            const int32_t* iRmin, const int32_t* iRmax, const double* dust_sum, int32_t* dark, int32_t* ri_in, int32_t* ri_out,
+                            int32_t* zj_sup, int32_t* zj_inf, int32_t* l_is_dark) {
+  ((Oracle*)h)->define_dark_zone(lambda, tau_max, r_grid, z_grid, n_regions, iRmin, iRmax, dust_sum, dark, ri_in, ri_out, zj_sup, zj_inf, l_is_dark);
   return MCB_OK;
 }
 int oracle_compute_column(void* h, int32_t lambda, const double* factor, const double* cx, const double* cy, const double* cz, float* column) {

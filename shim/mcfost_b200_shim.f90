@@ -146,6 +146,28 @@ module mcfost_b200_shim
      integer(c_int) function mcfost_b200_multi_run(m, r, t) bind(C, name='mcfost_b200_multi_run')
        import ; type(c_ptr), value :: m ; type(mcb_run_params) :: r ; type(mcb_tallies) :: t
      end function
+     type(c_ptr) function mcfost_b200_multi_handle(m, i) bind(C, name='mcfost_b200_multi_handle')
+       import ; type(c_ptr), value :: m ; integer(c_int), value :: i
+     end function
+     integer(c_int) function mcfost_b200_define_dark_zone(h, lambda, tau_max, r_grid, z_grid, n_regions, iRmin, iRmax, dust_sum, &
+          l_dark, ri_in, ri_out, zj_sup, zj_inf, l_is_dark) bind(C, name='mcfost_b200_define_dark_zone')
+       import
+       type(c_ptr), value :: h
+       integer(c_int32_t), value :: lambda, n_regions
+       real(c_float), value :: tau_max
+       real(c_double), intent(in) :: r_grid(*), z_grid(*)
+       integer(c_int32_t), intent(in) :: iRmin(*), iRmax(*)
+       type(c_ptr), value :: dust_sum
+       integer(c_int32_t) :: l_dark(*), ri_in(*), ri_out(*), zj_sup(*), zj_inf(*)
+       integer(c_int32_t) :: l_is_dark
+     end function
+     integer(c_int) function mcfost_b200_compute_column(h, lambda, factor, cx, cy, cz, column) bind(C, name='mcfost_b200_compute_column')
+       import
+       type(c_ptr), value :: h, factor
+       integer(c_int32_t), value :: lambda
+       real(c_double), intent(in) :: cx(*), cy(*), cz(*)
+       real(c_float) :: column(*)
+     end function
   end interface
 
   type(c_ptr), save :: b200 = c_null_ptr          ! the multi-GPU object (n_gpus = 1 is the single-GPU case)
@@ -255,6 +277,51 @@ contains
     dark_i32 = merge(1_c_int32_t, 0_c_int32_t, l_dark_zone(1:n_cells))
     call b200_check(mcfost_b200_multi_upload_dark_zone(b200, dark_i32), "upload_dark_zone")
   end subroutine b200_upload_dark_zone
+
+  ! Replaces  call define_dark_zone(lambda, p_lambda, tau_max, ldiff_approx)  (optical_depth.f90:1425-1651; call sites
+  ! dust_transfer.f90:293,919) on structured grids: GPU 0 of the node does the sums and the ray walks, the result goes
+  ! into the reference's own module variables and is installed on every GPU.
+  subroutine define_dark_zone_b200(lambda, p_lambda, tau_max, ldiff_approx)
+    integer, intent(in) :: lambda, p_lambda
+    real, intent(in) :: tau_max
+    logical, intent(in) :: ldiff_approx
+    integer(c_int32_t), allocatable :: iRmin(:), iRmax(:), zinf(:,:)
+    real(c_double), allocatable, target :: dust_sum(:)
+    integer(c_int32_t) :: flag
+    type(c_ptr) :: pds
+    integer :: i
+    allocate(iRmin(max(n_regions,1)), iRmax(max(n_regions,1)))
+    do i = 1, n_regions
+       iRmin(i) = regions(i)%iRmin ; iRmax(i) = regions(i)%iRmax
+    enddo
+    pds = c_null_ptr
+    if (n_zones > 1) then
+       allocate(dust_sum(n_cells))
+       do i = 1, n_cells
+          dust_sum(i) = sum(dust_density_o_n_grains(:,i))
+       enddo
+       pds = c_loc(dust_sum)
+    endif
+    if (allocated(dark_i32)) deallocate(dark_i32)
+    allocate(dark_i32(n_cells))
+    if (l3D) then
+       call b200_check(mcfost_b200_define_dark_zone(mcfost_b200_multi_handle(b200, 0_c_int), int(lambda, c_int32_t), tau_max, &
+            r_grid, z_grid, int(n_regions, c_int32_t), iRmin, iRmax, pds, dark_i32, ri_in_dark_zone, ri_out_dark_zone, &
+            zj_sup_dark_zone, zj_inf_dark_zone, flag), "define_dark_zone")
+    else      ! zj_inf_dark_zone is not used on a 2D grid (a scratch array of the same shape is passed)
+       allocate(zinf(n_rad, n_az)) ; zinf = 0
+       call b200_check(mcfost_b200_define_dark_zone(mcfost_b200_multi_handle(b200, 0_c_int), int(lambda, c_int32_t), tau_max, &
+            r_grid, z_grid, int(n_regions, c_int32_t), iRmin, iRmax, pds, dark_i32, ri_in_dark_zone, ri_out_dark_zone, &
+            zj_sup_dark_zone, zinf, flag), "define_dark_zone")
+    endif
+    l_dark_zone(1:n_cells) = dark_i32 /= 0
+    l_is_dark_zone = flag /= 0
+    if ((ldiff_approx).and.(n_rad > 1)) then      ! optical_depth.f90:1629-1632
+       if (minval(ri_in_dark_zone(:))==1) call error("first cell is in diffusion approximation zone", &
+            msg2="Increase spatial grid resolution")
+    endif
+    call b200_check(mcfost_b200_multi_upload_dark_zone(b200, dark_i32), "upload_dark_zone")      ! the other GPUs of the node
+  end subroutine define_dark_zone_b200
 
   ! after init_reemission / opacite when a per-grain mode is on, and again after every update_proba_abs_nRE
   ! (thermal_emission.f90:1518), which changes l_RE, kappa_abs_RE and the three probabilities

@@ -325,3 +325,48 @@ def test_compute_column_bit_exact(name):
     with pytest.raises(api.McfostB200Error):
         G.compute_column(P.n_lambda + 1, cx, cy, cz)
     G.close()
+
+
+@pytest.mark.parametrize("name", ["cyl2D_full", "cyl2D_small", "cyl3D", "sph2D", "variable_dust"])
+def test_define_dark_zone_in_the_library_equals_oracle(name):
+    """mcfost_b200_define_dark_zone (optical_depth.f90:1425-1651, one block: the columns in sequence, the rays of a column in
+    parallel) against the oracle's nested loops: identical l_dark_zone, ri_in / ri_out, zj_sup / zj_inf and flag."""
+    if name == "cyl2D_full":
+        P = S.ref41_like(n_photons_eq_th=10, dark_zone=False); tau_max = 1500.0
+    elif name == "cyl2D_small":
+        P = small_problems()["cyl2D"](); tau_max = 30.0
+    elif name == "cyl3D":
+        P = S.ref41_3d_like(n_photons_eq_th=10, n_rad=30, nz=10, n_az=12, n_rad_in=4, tau_mid=3000.0); tau_max = 100.0
+    elif name == "sph2D":
+        P = S.spherical_shell(n_photons_eq_th=10, tau_mid=3000.0); tau_max = 50.0
+    else:
+        P = S.ref41_multi_like(n_photons_eq_th=10, tau_mid=3.0e4); tau_max = 300.0
+    lam = P.lambda_seuil
+    regions = [(1, P.n_rad)]
+    O, G = Oracle(P), api.PhotonLoop(P)
+    o = O.define_dark_zone(lam, tau_max, P.r_grid, P.z_grid, regions)
+    g = G.define_dark_zone(lam, tau_max, P.r_grid, P.z_grid, regions)
+    for k in ("l_dark_zone", "ri_in", "ri_out", "zj_sup", "zj_inf"):
+        assert np.array_equal(o[k], g[k]), k
+    assert o["l_is_dark_zone"] == g["l_is_dark_zone"]
+    assert g["l_dark_zone"].sum() > 0, "the model has no dark zone: the test would be empty"
+    if name == "cyl2D_full":      # the path bench.py takes (numpy logic + the library's ray walker)
+        assert np.array_equal(g["l_dark_zone"], S.define_dark_zone(P, lam, tau_max, G.dark_zone_walker()))
+    # the result is installed: packets bounce off the dark cells (not on the shell: its dark zone encloses the star, no
+    # packet could ever leave -- in the reference as well)
+    if name != "sph2D":
+        t = G.mc_photon_loop(1, 1, 50, 1.0e30, 1, False)
+        assert t.stats[0] == 128 * 50 and t.stats[5] + t.stats[6] == t.stats[0]
+        if name == "cyl2D_full":
+            assert t.stats[7] > 0          # bounces
+    # dust-free cells (n_zones > 1, :1634-1638)
+    ds = np.ones(P.n_cells); ds[np.flatnonzero(g["l_dark_zone"])[:3]] = 0.0
+    o2 = O.define_dark_zone(lam, tau_max, P.r_grid, P.z_grid, regions, dust_sum=ds)
+    g2 = G.define_dark_zone(lam, tau_max, P.r_grid, P.z_grid, regions, dust_sum=ds)
+    assert np.array_equal(o2["l_dark_zone"], g2["l_dark_zone"]) and g2["l_dark_zone"].sum() == g["l_dark_zone"].sum() - 3
+    # stale in-out arrays (the module arrays keep the values of the previous call where no sum reaches tau_max)
+    zs = np.full_like(g["zj_sup"], 2)
+    o3 = O.define_dark_zone(lam, tau_max, P.r_grid, P.z_grid, regions, zj_sup=zs.copy())
+    g3 = G.define_dark_zone(lam, tau_max, P.r_grid, P.z_grid, regions, zj_sup=zs.copy())
+    assert np.array_equal(o3["l_dark_zone"], g3["l_dark_zone"]) and np.array_equal(o3["zj_sup"], g3["zj_sup"])
+    G.close()

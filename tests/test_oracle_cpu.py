@@ -319,3 +319,17 @@ def test_compute_column_properties():
     ones = O.compute_column(1, cx, cy, cz, np.ones(P.n_cells)).astype(np.float64)
     assert (ones[:, 3] > 0).all() and np.allclose(ones[:, 3] + np.hypot(cx, cy), P.r_lim[-1], rtol=1e-6)      # radial path to the outer edge
     assert np.allclose((ones[:, 1] + ones[:, 2]).reshape(P.nz, P.n_rad), 2.0 * P.zmax[None, :], rtol=1e-6)           # full height of the column
+
+
+def test_define_dark_zone_oracle_matches_the_numpy_restatement():
+    """The oracle's define_dark_zone (optical_depth.f90:1425-1651, nested loops as in the Fortran) against the generator's
+    numpy version driven by the oracle's own ray walker (2D cylindrical): same dark cells."""
+    P = S.ref41_like(n_photons_eq_th=10, dark_zone=False)
+    O = Oracle(P)
+    d = O.define_dark_zone(P.lambda_seuil, 1500.0, P.r_grid, P.z_grid, [(1, P.n_rad)])
+    ref = S.define_dark_zone(P, P.lambda_seuil, 1500.0, Oracle(P).dark_zone_walker())
+    assert d["l_dark_zone"].sum() > 100 and np.array_equal(d["l_dark_zone"], ref)
+    assert d["l_is_dark_zone"] == 1 and 1 < d["ri_in"][0] < d["ri_out"][0] < P.n_rad
+    dark2d = d["l_dark_zone"].reshape(P.nz, P.n_rad)
+    assert (np.diff(dark2d, axis=0) <= 0).all()          # a column is dark from the midplane up to one row
+    assert dark2d[:, 0].sum() == 0 and dark2d[:, -1].sum() == 0      # region edges
