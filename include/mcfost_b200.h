@@ -396,6 +396,33 @@ int mcfost_b200_optical_length_tot(mcb_handle *h, int64_t n, int32_t lambda,
         const double *u, const double *v, const double *w,
         const int32_t *icell, double *tau_tot, double *lmin, double *lmax,
         int32_t *n_steps);
+/* init_reemission (thermal_emission.f90:404-550), LTE cells, high-memory branch,
+ * no extra heating: the Planck function and its temperature derivative per
+ * (lambda, T) with the reference's constants, then per (T, p_icell) the cooling
+ * table log(Qcool(T) - Qcool(T_min)) and the emission CDF
+ * sum_lambda kappa_abs_LTE dB/dT, computed ON THE DEVICE from the
+ * kappa_abs_LTE and tab_Temp of the last mcfost_b200_upload_opacity (whose
+ * log_Qcool_minus_extra_heating / kdB_dT_CDF may then be NULL) and installed as
+ * the handle's thermal tables: with cell-dependent dust the CDF is n_lambda x
+ * n_T x n_cells doubles (280 MB for 7000 cells) that never cross PCIe.
+ * tab_lambda, tab_delta_lambda: (n_lambda), micron.  Outputs (may be NULL):
+ * log_Qcool_minus_extra_heating(n_T, p_n_cells), kdB_dT_CDF(n_lambda, n_T,
+ * p_n_cells) for the caller's own use (Temp_finale on the host, FITS output). */
+int mcfost_b200_init_reemission(mcb_handle *h, const double *tab_lambda,
+        const double *tab_delta_lambda,
+        double *log_Qcool_minus_extra_heating, double *kdB_dT_CDF);
+/* The per-grain tables of init_reemission for grains k_start..k_end (1-based,
+ * inclusive) of C_abs_norm(n_grains_tot, n_lambda) (`real`):
+ * log_E_em_1grain(k_start:k_end, n_T) (:551-567 for the nLTE grains, :585-603
+ * for the nRE grains, whose E_em_1grain_nRE is the optional E_em_1grain) and
+ * kdB_dT_1grain_*_CDF(n_lambda, k_start:k_end, n_T) (:569-581, :605-618, also
+ * the low-memory LTE table :519-533).  Pure function of its arguments and of
+ * the handle's n_lambda / n_T / tab_Temp; the caller passes the results on in
+ * mcb_grains. */
+int mcfost_b200_init_reemission_grains(mcb_handle *h, const double *tab_lambda,
+        const double *tab_delta_lambda, const float *C_abs_norm,
+        int32_t n_grains_tot, int32_t k_start, int32_t k_end,
+        double *log_E_em_1grain, double *E_em_1grain, double *kdB_dT_1grain_CDF);
 /* define_dark_zone(lambda, p_lambda, tau_max, ldiff_approx) (optical_depth.f90:
  * 1425-1651) on structured grids: radial and vertical optical-depth sums
  * (`real` accumulators as in the Fortran), then 11 rays of optical depth

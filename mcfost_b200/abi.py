@@ -220,8 +220,10 @@ def make_opacity(P) -> Holder:
     o.n_lambda, o.p_n_cells = int(P.n_lambda), int(P.p_n_cells)
     o.p_n_lambda_pos, o.n_T = int(P.p_n_lambda_pos), int(P.n_T)
     for name in ("kappa", "kappa_abs_LTE", "kappa_factor", "log_Qcool_minus_extra_heating", "kdB_dT_CDF"):
-        a = farray(getattr(P, name), np.float64)
-        keep[name] = a
+        a = getattr(P, name)
+        if a is not None:      # (the two thermal tables may be left to mcfost_b200_init_reemission)
+            a = farray(a, np.float64)
+            keep[name] = a
         setattr(o, name, ptr(a, np.float64))
     for name in ("tab_albedo_pos", "tab_g_pos", "prob_s11_pos", "tab_s11_pos", "tab_s12_o_s11_pos",
                  "tab_s22_o_s11_pos", "tab_s33_o_s11_pos", "tab_s34_o_s11_pos", "tab_s44_o_s11_pos", "tab_Temp"):

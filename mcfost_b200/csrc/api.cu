@@ -1149,6 +1149,60 @@ define_dark_zone_kernel(const __grid_constant__ DevModel m, int lambda, float ta
   if (tid == 0) *l_is_dark = s_flag;
 }
 
+// ---- init_reemission (thermal_emission.f90:404-644) on the device ---------------------------------------------
+// B(lambda, T) and dB/dT(lambda, T) with the reference's constants (`thermal_const` is a `real` parameter, 1.e-6 and 500.0
+// are `real` literals), then one thread per (T, row): the cooling sum and the emission CDF of a row of absorption
+// coefficients -- the LTE cells (kappa_abs_LTE(p_icell, :), CDF from lambda = 1) or single grains (C_abs_norm(k, :), `real`,
+// CDF starting at 0 for lambda = 1).
+__global__ void planck_tables_kernel(int n_lambda, int n_T, const double* tab_lambda, const double* tab_delta_lambda, const float* tab_Temp,
+                                     double* B, double* dB) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_lambda * n_T) return;
+  const int lambda = q % n_lambda, t = q / n_lambda;
+  const float thermal_const = (float)(299792458.0 * 6.626070040e-34 / 1.38064852e-23);
+  const double Temp = (double)tab_Temp[t];
+  const double cst = (double)thermal_const / Temp;
+  const double wl = tab_lambda[lambda] * (double)1.e-6f, delta_wl = tab_delta_lambda[lambda] * (double)1.e-6f;
+  const double cst_wl = cst / wl;
+  double b = 0.0, db = 0.0;
+  if (cst_wl < 500.0) {
+    const double coeff_exp = exp(cst_wl);
+    const double wl2 = wl * wl, wl5 = (wl2 * wl2) * wl;
+    b = 1.0 / (wl5 * (coeff_exp - 1.0)) * delta_wl;
+    db = b * cst_wl * coeff_exp / (coeff_exp - 1.0);
+  }
+  B[q] = b; dB[q] = db;
+}
+template <bool GRAINS>
+__global__ void init_reemission_rows_kernel(int n_lambda, int n_T, int n_rows, const double* a_cells, int stride_cells, const float* a_grains,
+                                            int stride_grains, int k0, const double* B, const double* dB, double* logQ, double* E_em, double* cdf) {
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= (int64_t)n_T * n_rows) return;
+  // cells: logQ(T, icell), cdf(lambda, T, icell);  grains: logE(k, T), cdf(lambda, k, T)
+  const int t = GRAINS ? (int)(q / n_rows) : (int)(q % n_T), row = GRAINS ? (int)(q % n_rows) : (int)(q / n_T);
+  auto a = [&](int l) { return GRAINS ? (double)a_grains[(size_t)(k0 + row) + (size_t)stride_grains * l] : a_cells[(size_t)row + (size_t)stride_cells * l]; };
+  const double cst_E = 2.0 * 6.626070040e-34 * (299792458.0 * 299792458.0) * (4.0 * MCB_PI);
+  double integ = 0.0, integ0 = 0.0;
+  for (int l = 0; l < n_lambda; ++l) { integ = integ + a(l) * B[l + (size_t)n_lambda * t]; if (!GRAINS) integ0 = integ0 + a(l) * B[l]; }
+  const size_t o = GRAINS ? (size_t)row + (size_t)n_rows * t : (size_t)t + (size_t)n_T * row;
+  if (GRAINS) {
+    logQ[o] = (integ > MCB_TINY_DP) ? log(integ * cst_E) : -1000.0;
+    if (E_em) E_em[o] = integ * cst_E;
+  } else {
+    const double qc = integ * cst_E - integ0 * cst_E;      // Qcool - Qcool0 (no extra heating: the cloud at T_min, :467-470)
+    logQ[o] = (qc > MCB_TINY_DP) ? log(qc) : -1000.0;
+  }
+  double* c = cdf + (size_t)n_lambda * o;
+  double run = 0.0;
+  for (int l = GRAINS ? 1 : 0; l < n_lambda; ++l) run = run + a(l) * dB[l + (size_t)n_lambda * t];
+  const double tot = run;
+  run = 0.0;
+  if (tot > MCB_TINY_DP) {
+    if (GRAINS) c[0] = 0.0 / tot;
+    for (int l = GRAINS ? 1 : 0; l < n_lambda; ++l) { run = run + a(l) * dB[l + (size_t)n_lambda * t]; c[l] = run / tot; }
+  } else for (int l = 0; l < n_lambda; ++l) c[l] = 0.0;
+}
+
 // optical_depth.f90:21-182 with Stokes = 0 (no tallies)
 template <class G>
 __global__ void physical_length_kernel(const __grid_constant__ DevModel m, int64_t n, int lambda, double* x, double* y, double* z,
@@ -1400,6 +1454,60 @@ int mcfost_b200_define_dark_zone(mcb_handle* h, int32_t lambda, float tau_max, c
   CK(cudaStreamSynchronize(h->stream));
   if (l_is_dark_zone) *l_is_dark_zone = flag;
   return mcfost_b200_upload_dark_zone(h, l_dark_zone);      // the photon loop of this handle uses the new dark zone from now on
+}
+
+int mcfost_b200_init_reemission(mcb_handle* h, const double* tab_lambda, const double* tab_delta_lambda,
+                                double* log_Qcool_minus_extra_heating, double* kdB_dT_CDF) {
+  if (!h || !tab_lambda || !tab_delta_lambda) return MCB_ERR_BAD_ARG;
+  if (!h->has_op) return fail(h, MCB_ERR_STATE, "init_reemission before upload_opacity (kappa_abs_LTE, tab_Temp)");
+  DevModel& m = h->m;
+  if (!m.kappa_abs || !m.tab_Temp) return fail(h, MCB_ERR_STATE, "init_reemission: kappa_abs_LTE / tab_Temp missing");
+  CK(cudaSetDevice(h->device));
+  const int nl = m.n_lambda, nT = m.n_T, pnc = m.p_n_cells;
+  Scratch s{h};
+  const double *dl = s.in(tab_lambda, nl), *dd = s.in(tab_delta_lambda, nl);
+  double *dB_ = s.in<double>(nullptr, (int64_t)nl * nT), *ddB = s.in<double>(nullptr, (int64_t)nl * nT);
+  if (!dl || !dd || !dB_ || !ddB) return fail(h, MCB_ERR_CUDA, "scratch allocation failed");
+  double *dlogQ = nullptr, *dcdf = nullptr;
+  int rc;
+  if ((rc = reserve(h, "logQ", (size_t)nT * pnc, &dlogQ))) return rc;
+  if ((rc = reserve(h, "kdB", (size_t)nl * nT * pnc, &dcdf))) return rc;
+  planck_tables_kernel<<<(nl * nT + 127) / 128, 128, 0, h->stream>>>(nl, nT, dl, dd, m.tab_Temp, dB_, ddB);
+  CK(cudaGetLastError());
+  const int64_t n = (int64_t)nT * pnc;
+  init_reemission_rows_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(nl, nT, pnc, m.kappa_abs, pnc, nullptr, 0, 0, dB_, ddB, dlogQ, nullptr, dcdf);
+  CK(cudaGetLastError());
+  m.logQ = dlogQ; m.kdB = dcdf;      // the thermal tables of this handle from now on (as upload_opacity would have set them)
+  h->mrw_ready = false;
+  if (log_Qcool_minus_extra_heating) CK(cudaMemcpyAsync(log_Qcool_minus_extra_heating, dlogQ, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (kdB_dT_CDF) CK(cudaMemcpyAsync(kdB_dT_CDF, dcdf, (size_t)n * nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
+}
+
+int mcfost_b200_init_reemission_grains(mcb_handle* h, const double* tab_lambda, const double* tab_delta_lambda, const float* C_abs_norm,
+                                       int32_t n_grains_tot, int32_t k_start, int32_t k_end, double* log_E_em_1grain, double* E_em_1grain,
+                                       double* kdB_dT_1grain_CDF) {
+  if (!h || !tab_lambda || !tab_delta_lambda || !C_abs_norm || !log_E_em_1grain || !kdB_dT_1grain_CDF) return MCB_ERR_BAD_ARG;
+  if (!h->has_op) return fail(h, MCB_ERR_STATE, "init_reemission_grains before upload_opacity (n_lambda, tab_Temp)");
+  const DevModel& m = h->m;
+  if (k_start < 1 || k_end < k_start || k_end > n_grains_tot) return fail(h, MCB_ERR_BAD_ARG, "grain range");
+  CK(cudaSetDevice(h->device));
+  const int nl = m.n_lambda, nT = m.n_T, nk = k_end - k_start + 1;
+  Scratch s{h};
+  const double *dl = s.in(tab_lambda, nl), *dd = s.in(tab_delta_lambda, nl);
+  const float* dca = s.in(C_abs_norm, (int64_t)n_grains_tot * nl);
+  double *dB_ = s.in<double>(nullptr, (int64_t)nl * nT), *ddB = s.in<double>(nullptr, (int64_t)nl * nT);
+  const int64_t n = (int64_t)nT * nk;
+  double *dlogE = s.in<double>(nullptr, n), *dE = s.in<double>(nullptr, n), *dcdf = s.in<double>(nullptr, n * nl);
+  if (!dl || !dd || !dca || !dB_ || !ddB || !dlogE || !dE || !dcdf) return fail(h, MCB_ERR_CUDA, "scratch allocation failed");
+  planck_tables_kernel<<<(nl * nT + 127) / 128, 128, 0, h->stream>>>(nl, nT, dl, dd, m.tab_Temp, dB_, ddB);
+  CK(cudaGetLastError());
+  init_reemission_rows_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(nl, nT, nk, nullptr, 0, dca, n_grains_tot, k_start - 1, dB_, ddB, dlogE, dE, dcdf);
+  CK(cudaGetLastError());
+  s.out(log_E_em_1grain, dlogE, n); s.out(E_em_1grain, dE, n); s.out(kdB_dT_1grain_CDF, dcdf, n * nl);
+  CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
 }
 
 int mcfost_b200_compute_column(mcb_handle* h, int32_t lambda, const double* factor, const double* centre_x, const double* centre_y,

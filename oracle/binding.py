@@ -190,6 +190,26 @@ class Oracle:
                                                      _p(imin), _p(imax), _p(ds), _p(dark), _p(ri_in), _p(ri_out), _p(zs), _p(zi), _p(flag)))
         return dict(l_dark_zone=dark, ri_in=ri_in, ri_out=ri_out, zj_sup=zs, zj_inf=zi, l_is_dark_zone=int(flag[0]))
 
+    def init_reemission(self, tab_lambda, tab_delta_lambda):
+        """init_reemission (thermal_emission.f90:404-550, LTE cells): log_Qcool_minus_extra_heating (n_T, p_n_cells), kdB_dT_CDF"""
+        P = self.P
+        tl, td = self._f64(tab_lambda, tab_delta_lambda)
+        logQ = np.zeros((P.n_T, P.p_n_cells), np.float64, order="F"); cdf = np.zeros((P.n_lambda, P.n_T, P.p_n_cells), np.float64, order="F")
+        self._check(self.lib.oracle_init_reemission(self.h, _p(tl), _p(td), _p(logQ), _p(cdf)))
+        return logQ, cdf
+
+    def init_reemission_grains(self, tab_lambda, tab_delta_lambda, C_abs_norm, k_start, k_end):
+        """per-grain tables (thermal_emission.f90:551-618): log_E_em (nk, n_T), E_em (nk, n_T), CDF (n_lambda, nk, n_T)"""
+        P = self.P
+        tl, td = self._f64(tab_lambda, tab_delta_lambda)
+        ca = np.asfortranarray(C_abs_norm, np.float32)
+        nk = k_end - k_start + 1
+        logE = np.zeros((nk, P.n_T), np.float64, order="F"); Eem = np.zeros((nk, P.n_T), np.float64, order="F")
+        cdf = np.zeros((P.n_lambda, nk, P.n_T), np.float64, order="F")
+        self._check(self.lib.oracle_init_reemission_grains(self.h, _p(tl), _p(td), _p(ca), C.c_int32(ca.shape[0]), C.c_int32(k_start), C.c_int32(k_end),
+                                                           _p(logE), _p(Eem), _p(cdf)))
+        return logE, Eem, cdf
+
     def compute_column(self, lam, cx, cy, cz, factor=None):
         """compute_column (optical_depth.f90:328-415): (n_cells, 4) real, column-major; factor None = optical depth at lam"""
         cx, cy, cz = self._f64(cx, cy, cz)

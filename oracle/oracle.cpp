@@ -1403,6 +1403,79 @@ struct Oracle {
   }
 
   // =====================================================================
+  // thermal_emission.f90:404-644  init_reemission: Planck function and its temperature derivative per (lambda, T), the
+  // cooling table log(Qcool - Qcool(T_min)) and the emission CDF of the LTE cells (high-memory branch, no extra heating),
+  // and the per-grain tables of the nLTE / nRE grains.  `thermal_const` is a `real` parameter (constants.f90:24), 1.e-6
+  // and 500.0 are `real` literals.
+  // =====================================================================
+  void planck_tables(const double* tab_lambda, const double* tab_delta_lambda, std::vector<double>& B, std::vector<double>& dB) const {
+    const int n_lambda = o.n_lambda, n_T = o.n_T;
+    const float thermal_const = (float)(299792458.0 * 6.626070040e-34 / 1.38064852e-23);
+    B.assign((size_t)n_lambda * n_T, 0.0); dB.assign((size_t)n_lambda * n_T, 0.0);
+    for (int t = 1; t <= n_T; ++t) {
+      const double Temp = tab_Temp(t);
+      const double cst = (double)thermal_const / Temp;
+      for (int lambda = 1; lambda <= n_lambda; ++lambda) {
+        const double wl = tab_lambda[lambda - 1] * (double)1.e-6f;
+        const double delta_wl = tab_delta_lambda[lambda - 1] * (double)1.e-6f;
+        const double cst_wl = cst / wl;
+        if (cst_wl < 500.0) {
+          const double coeff_exp = std::exp(cst_wl);
+          const double wl2 = wl * wl, wl5 = (wl2 * wl2) * wl;      // wl**5 as the compiler expands a small integer power (square, square, multiply)
+          const double b = 1.0 / (wl5 * (coeff_exp - 1.0)) * delta_wl;
+          B[(size_t)(lambda - 1) + (size_t)n_lambda * (t - 1)] = b;
+          dB[(size_t)(lambda - 1) + (size_t)n_lambda * (t - 1)] = b * cst_wl * coeff_exp / (coeff_exp - 1.0);
+        }
+      }
+    }
+  }
+  void init_reemission(const double* tab_lambda, const double* tab_delta_lambda, double* logQ, double* cdf) const {
+    const int n_lambda = o.n_lambda, n_T = o.n_T, pnc = o.p_n_cells;
+    const double cst_E = 2.0 * 6.626070040e-34 * (299792458.0 * 299792458.0) * (4.0 * pi);
+    std::vector<double> B, dB; planck_tables(tab_lambda, tab_delta_lambda, B, dB);
+    std::vector<double> integ3(n_lambda + 1);
+    for (int icell = 1; icell <= pnc; ++icell) {
+      double Qcool0 = 0.0;
+      for (int t = 1; t <= n_T; ++t) {
+        double integ = 0.0;
+        for (int lambda = 1; lambda <= n_lambda; ++lambda) integ = integ + kappa_abs_LTE(icell, lambda) * B[(size_t)(lambda - 1) + (size_t)n_lambda * (t - 1)];
+        const double Qcool = integ * cst_E;
+        if (t == 1) Qcool0 = Qcool;
+        const double q = Qcool - Qcool0;
+        logQ[(size_t)(t - 1) + (size_t)n_T * (icell - 1)] = (q > tiny_dp) ? std::log(q) : -1000.0;
+        integ3[0] = 0.0;
+        for (int lambda = 1; lambda <= n_lambda; ++lambda) integ3[lambda] = integ3[lambda - 1] + kappa_abs_LTE(icell, lambda) * dB[(size_t)(lambda - 1) + (size_t)n_lambda * (t - 1)];
+        double* c = cdf + (size_t)n_lambda * ((size_t)(t - 1) + (size_t)n_T * (icell - 1));
+        if (integ3[n_lambda] > tiny_dp) for (int lambda = 1; lambda <= n_lambda; ++lambda) c[lambda - 1] = integ3[lambda] / integ3[n_lambda];
+        else for (int lambda = 1; lambda <= n_lambda; ++lambda) c[lambda - 1] = 0.0;      // (left as allocated by the reference: zero)
+      }
+    }
+  }
+  // grains k_start..k_end (1-based): log_E_em_1grain(k, T) (:551-567 nLTE, :585-603 nRE) and kdB_dT_1grain_*_CDF(lambda, k, T)
+  // (:569-581, :605-618; the CDF starts at 0 for lambda = 1)
+  void init_reemission_grains(const double* tab_lambda, const double* tab_delta_lambda, const float* C_abs_norm, int n_grains_tot, int k_start,
+                              int k_end, double* logE, double* E_em, double* cdf) const {
+    const int n_lambda = o.n_lambda, n_T = o.n_T, nk = k_end - k_start + 1;
+    const double cst_E = 2.0 * 6.626070040e-34 * (299792458.0 * 299792458.0) * (4.0 * pi);
+    std::vector<double> B, dB; planck_tables(tab_lambda, tab_delta_lambda, B, dB);
+    std::vector<double> integ3(n_lambda + 1);
+    for (int t = 1; t <= n_T; ++t)
+      for (int k = k_start; k <= k_end; ++k) {
+        auto ca = [&](int lambda) { return (double)C_abs_norm[(size_t)(k - 1) + (size_t)n_grains_tot * (lambda - 1)]; };
+        double integ = 0.0;
+        for (int lambda = 1; lambda <= n_lambda; ++lambda) integ = integ + ca(lambda) * B[(size_t)(lambda - 1) + (size_t)n_lambda * (t - 1)];
+        const size_t kt = (size_t)(k - k_start) + (size_t)nk * (t - 1);
+        logE[kt] = (integ > tiny_dp) ? std::log(integ * cst_E) : -1000.0;
+        if (E_em) E_em[kt] = integ * cst_E;
+        integ3[1] = 0.0;
+        for (int lambda = 2; lambda <= n_lambda; ++lambda) integ3[lambda] = integ3[lambda - 1] + ca(lambda) * dB[(size_t)(lambda - 1) + (size_t)n_lambda * (t - 1)];
+        double* c = cdf + (size_t)n_lambda * kt;
+        if (integ3[n_lambda] > tiny_dp) for (int lambda = 1; lambda <= n_lambda; ++lambda) c[lambda - 1] = integ3[lambda] / integ3[n_lambda];
+        else for (int lambda = 1; lambda <= n_lambda; ++lambda) c[lambda - 1] = 0.0;
+      }
+  }
+
+  // =====================================================================
   // scattering.f90:1354-1383  hg
   // =====================================================================
   static void hg(float g_, float rand, int& itheta, double& cospsi) {
@@ -2426,6 +2499,15 @@ int oracle_define_dark_zone(void* h, int32_t lambda, float tau_max, const double
                             const int32_t* iRmin, const int32_t* iRmax, const double* dust_sum, int32_t* dark, int32_t* ri_in, int32_t* ri_out,
                             int32_t* zj_sup, int32_t* zj_inf, int32_t* l_is_dark) {
   ((Oracle*)h)->define_dark_zone(lambda, tau_max, r_grid, z_grid, n_regions, iRmin, iRmax, dust_sum, dark, ri_in, ri_out, zj_sup, zj_inf, l_is_dark);
+  return MCB_OK;
+}
+int oracle_init_reemission(void* h, const double* tab_lambda, const double* tab_delta_lambda, double* logQ, double* cdf) {
+  ((Oracle*)h)->init_reemission(tab_lambda, tab_delta_lambda, logQ, cdf);
+  return MCB_OK;
+}
+int oracle_init_reemission_grains(void* h, const double* tab_lambda, const double* tab_delta_lambda, const float* C_abs_norm, int32_t n_grains_tot,
+                                  int32_t k_start, int32_t k_end, double* logE, double* E_em, double* cdf) {
+  ((Oracle*)h)->init_reemission_grains(tab_lambda, tab_delta_lambda, C_abs_norm, n_grains_tot, k_start, k_end, logE, E_em, cdf);
   return MCB_OK;
 }
 int oracle_compute_column(void* h, int32_t lambda, const double* factor, const double* cx, const double* cy, const double* cz, float* column) {

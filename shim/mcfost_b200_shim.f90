@@ -25,7 +25,7 @@ module mcfost_b200_shim
   use Temperature, only : tab_Temp, T_min
   use radiation_field
   use stars
-  use wavelengths, only : n_lambda, tab_lambda
+  use wavelengths, only : n_lambda, tab_lambda, tab_delta_lambda
   use dust_ray_tracing
   use output
   use naleat, only : seed
@@ -160,6 +160,14 @@ module mcfost_b200_shim
        type(c_ptr), value :: dust_sum
        integer(c_int32_t) :: l_dark(*), ri_in(*), ri_out(*), zj_sup(*), zj_inf(*)
        integer(c_int32_t) :: l_is_dark
+     end function
+     integer(c_int) function mcfost_b200_multi_n_gpus(m) bind(C, name='mcfost_b200_multi_n_gpus')
+       import ; type(c_ptr), value :: m
+     end function
+     integer(c_int) function mcfost_b200_init_reemission(h, tab_lambda, tab_delta_lambda, logQ, cdf) bind(C, name='mcfost_b200_init_reemission')
+       import
+       type(c_ptr), value :: h, logQ, cdf
+       real(c_double), intent(in) :: tab_lambda(*), tab_delta_lambda(*)
      end function
      integer(c_int) function mcfost_b200_compute_column(h, lambda, factor, cx, cy, cz, column) bind(C, name='mcfost_b200_compute_column')
        import
@@ -322,6 +330,24 @@ contains
     endif
     call b200_check(mcfost_b200_multi_upload_dark_zone(b200, dark_i32), "upload_dark_zone")      ! the other GPUs of the node
   end subroutine define_dark_zone_b200
+
+  ! Replaces the LTE part of  call init_reemission(lheating, dudt)  (thermal_emission.f90:404-550, high-memory branch, no
+  ! extra heating) after b200_upload_model: every GPU builds log_Qcool_minus_extra_heating and kdB_dT_CDF from the
+  ! kappa_abs_LTE it already holds; GPU 0's copies come back into the reference's module arrays (Temp_finale, outputs).
+  ! With cell-dependent dust kdB_dT_CDF is n_lambda x n_T x n_cells doubles that no longer cross PCIe once per GPU.
+  subroutine init_reemission_b200()
+    integer :: i
+    type(c_ptr) :: pq, pc
+    if (lextra_heating .or. low_mem_th_emission) call error("mcfost_b200: init_reemission_b200 covers the high-memory LTE branch without extra heating")
+    do i = 0, mcfost_b200_multi_n_gpus(b200) - 1
+       pq = c_null_ptr ; pc = c_null_ptr
+       if (i == 0) then
+          pq = c_loc(log_Qcool_minus_extra_heating) ; pc = c_loc(kdB_dT_CDF)
+       endif
+       call b200_check(mcfost_b200_init_reemission(mcfost_b200_multi_handle(b200, int(i, c_int)), tab_lambda, tab_delta_lambda, pq, pc), &
+            "init_reemission")
+    enddo
+  end subroutine init_reemission_b200
 
   ! after init_reemission / opacite when a per-grain mode is on, and again after every update_proba_abs_nRE
   ! (thermal_emission.f90:1518), which changes l_RE, kappa_abs_RE and the three probabilities

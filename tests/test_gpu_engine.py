@@ -370,3 +370,36 @@ def test_define_dark_zone_in_the_library_equals_oracle(name):
     g3 = G.define_dark_zone(lam, tau_max, P.r_grid, P.z_grid, regions, zj_sup=zs.copy())
     assert np.array_equal(o3["l_dark_zone"], g3["l_dark_zone"]) and np.array_equal(o3["zj_sup"], g3["zj_sup"])
     G.close()
+
+
+def test_init_reemission_on_the_device_equals_oracle():
+    """mcfost_b200_init_reemission / _grains (thermal_emission.f90:404-618) against the oracle: same operations in the same
+    order, exp / log from CUDA instead of glibc (<= 1 ulp each): 1e-12.  The tables are installed: a thermal step run on them
+    equals the step run on uploaded tables."""
+    P = S.ref41_multi_like(n_photons_eq_th=300)
+    O, G = Oracle(P), api.PhotonLoop(P)
+    t_up = G.mc_photon_loop(1, 1, 300, 1.0e30, 1, False)
+    lo, co = O.init_reemission(P.tab_lambda, P.tab_delta_lambda)
+    lg, cg = G.init_reemission(P.tab_lambda, P.tab_delta_lambda)
+    assert np.array_equal(lo == -1000.0, lg == -1000.0)
+    assert np.allclose(lg, lo, rtol=1e-12, atol=1e-12) and np.allclose(cg, co, rtol=1e-12, atol=1e-15)
+    t_dev = G.mc_photon_loop(1, 1, 300, 1.0e30, 1, False)
+    assert t_dev.stats[0] == t_up.stats[0] and t_dev.stats[5] + t_dev.stats[6] == t_dev.stats[0]
+    assert abs(t_dev.xKJ_abs.sum() / t_up.xKJ_abs.sum() - 1) < 0.02 and abs(t_dev.stats[4] / t_up.stats[4] - 1) < 0.05
+    G.close()
+    # a handle that never received the two tables from the host
+    import copy
+    P2 = copy.copy(P); P2.log_Qcool_minus_extra_heating = None; P2.kdB_dT_CDF = None
+    G2 = api.PhotonLoop(P2)
+    G2.init_reemission(P.tab_lambda, P.tab_delta_lambda, download=False)
+    t2 = G2.mc_photon_loop(1, 1, 300, 1.0e30, 1, False)
+    assert np.array_equal(t2.xKJ_abs, t_dev.xKJ_abs) or abs(t2.xKJ_abs.sum() / t_dev.xKJ_abs.sum() - 1) < 0.02
+    G2.close()
+    Pg = S.multi_grain_like(n_photons_eq_th=10)
+    Og, Gg = Oracle(Pg), api.PhotonLoop(Pg)
+    for (k0, k1) in ((Pg.grain_RE_nLTE_start, Pg.grain_RE_nLTE_end), (Pg.grain_nRE_start, Pg.grain_nRE_end), (Pg.grain_RE_LTE_start, Pg.grain_RE_LTE_end)):
+        eo = Og.init_reemission_grains(Pg.tab_lambda, Pg.tab_delta_lambda, Pg.C_abs_norm, k0, k1)
+        eg = Gg.init_reemission_grains(Pg.tab_lambda, Pg.tab_delta_lambda, Pg.C_abs_norm, k0, k1)
+        for a, b in zip(eo, eg):
+            assert a.shape == b.shape and np.allclose(b, a, rtol=1e-12, atol=1e-15)
+    Gg.close()

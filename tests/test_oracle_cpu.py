@@ -333,3 +333,24 @@ def test_define_dark_zone_oracle_matches_the_numpy_restatement():
     dark2d = d["l_dark_zone"].reshape(P.nz, P.n_rad)
     assert (np.diff(dark2d, axis=0) <= 0).all()          # a column is dark from the midplane up to one row
     assert dark2d[:, 0].sum() == 0 and dark2d[:, -1].sum() == 0      # region edges
+
+
+def test_init_reemission_oracle_matches_the_generators_tables():
+    """The oracle's init_reemission (thermal_emission.f90:404-618, with the reference's `real` constants) against the tables
+    the generators build in numpy with double-precision constants: equal to the 1e-8 the `1.e-6` literal is worth."""
+    P = S.ref41_multi_like(n_photons_eq_th=10)
+    O = Oracle(P)
+    logQ, cdf = O.init_reemission(P.tab_lambda, P.tab_delta_lambda)
+    ref = P.log_Qcool_minus_extra_heating
+    assert np.array_equal(logQ == -1000.0, ref == -1000.0)
+    ok = ref > -999.0
+    assert np.abs(logQ[ok] - ref[ok]).max() < 1e-7 and np.abs(cdf - P.kdB_dT_CDF).max() < 1e-7
+    assert (np.diff(cdf, axis=0) >= 0).all() and np.allclose(cdf[-1][cdf[-1] > 0], 1.0)
+    Pg = S.multi_grain_like(n_photons_eq_th=10)
+    Og = Oracle(Pg)
+    for (k0, k1, lE, cd) in ((Pg.grain_RE_nLTE_start, Pg.grain_RE_nLTE_end, Pg.log_E_em_1grain, Pg.kdB_dT_1grain_nLTE_CDF),
+                             (Pg.grain_nRE_start, Pg.grain_nRE_end, Pg.log_E_em_1grain_nRE, Pg.kdB_dT_1grain_nRE_CDF)):
+        logE, Eem, c = Og.init_reemission_grains(Pg.tab_lambda, Pg.tab_delta_lambda, Pg.C_abs_norm, k0, k1)
+        assert logE.shape == np.asarray(lE).shape and c.shape == np.asarray(cd).shape
+        assert np.abs(logE - lE).max() < 1e-6 and np.abs(c - cd).max() < 1e-6
+        assert np.allclose(np.log(Eem), logE, rtol=0, atol=1e-12) and (c[0] == 0).all()
