@@ -396,6 +396,32 @@ int mcfost_b200_optical_length_tot(mcb_handle *h, int64_t n, int32_t lambda,
         const double *u, const double *v, const double *w,
         const int32_t *icell, double *tau_tot, double *lmin, double *lmax,
         int32_t *n_steps);
+/* Ray-tracing method 1, the core of the formal solution.
+ *
+ * init_dust_source_fct1(lambda, ibin, iaz) (dust_ray_tracing.f90:636-708): the
+ * source function eps_dust1(n_az_rt, n_theta_rt, N_type_flux, n_cells) from the
+ * scattered specific intensity xI_scatt that the last mcfost_b200_run with
+ * lscatt_ray_tracing1 LEFT ON THE DEVICE (no download / upload of the tally),
+ * for the observer direction iRT = RT2d_to_RT1d(ibin, iaz) (1-based).
+ * photon_energy: the caller's (:657-664).  J_th(n_cells): the caller's calc_Jth
+ * (thermal emissivity at lambda).  N_type_flux, lsepar_pola, lsepar_contrib are
+ * those of that run.  The table stays on the device for
+ * mcfost_b200_integ_ray_dust; eps_dust1 (may be NULL) receives a copy with
+ * extents (45, 2, N_type_flux, n_cells) (on a 3D grid only (1, 1, :, :) is
+ * used, n_az_rt = n_theta_rt = 1).
+ *
+ * integ_ray_dust(lambda, icell, x, y, z, u, v, w) (optical_depth.f90:1327-1421)
+ * with dust_source_fct of method 1 (dust_ray_tracing.f90:1458-1485) for n rays
+ * followed backwards from the observer's side: I(N_type_flux, n) = sum over the
+ * cells of exp(-tau) (1 - exp(-dtau)) eps_dust1(k(phi), psup(z), :, icell), down
+ * to tau_dark_zone_obs.  The pixel loops above it (dust_map, intensite_pixel_dust)
+ * stay with the caller. */
+int mcfost_b200_init_dust_source_fct1(mcb_handle *h, int32_t lambda, int32_t iRT,
+        double photon_energy, const double *J_th, double *eps_dust1);
+int mcfost_b200_integ_ray_dust(mcb_handle *h, int32_t lambda, int64_t n,
+        const double *x, const double *y, const double *z,
+        const double *u, const double *v, const double *w,
+        const int32_t *icell, float tau_dark_zone_obs, double *I);
 /* init_reemission (thermal_emission.f90:404-550), LTE cells, high-memory branch,
  * no extra heating: the Planck function and its temperature derivative per
  * (lambda, T) with the reference's constants, then per (T, p_icell) the cooling

@@ -30,6 +30,7 @@ EXPORTS = (
     "mcfost_b200_cross_cell", "mcfost_b200_index_cell", "mcfost_b200_move_to_grid",
     "mcfost_b200_optical_length_tot", "mcfost_b200_physical_length", "mcfost_b200_compute_column", "mcfost_b200_define_dark_zone",
     "mcfost_b200_init_reemission", "mcfost_b200_init_reemission_grains",
+    "mcfost_b200_init_dust_source_fct1", "mcfost_b200_integ_ray_dust",
     "mcfost_b200_distance_to_closest_wall", "mcfost_b200_mrw_tables",
     "mcfost_b200_multi_init", "mcfost_b200_multi_finalize", "mcfost_b200_multi_last_error", "mcfost_b200_multi_n_gpus",
     "mcfost_b200_multi_handle", "mcfost_b200_multi_upload_grid", "mcfost_b200_multi_upload_dark_zone",
@@ -323,6 +324,23 @@ class PhotonLoop:
         self._check(self.lib.mcfost_b200_init_reemission_grains(self.h, _p(tl), _p(td), _p(ca), C.c_int32(ca.shape[0]), C.c_int32(k_start),
                                                                 C.c_int32(k_end), _p(logE), _p(Eem), _p(cdf)))
         return logE, Eem, cdf
+
+    def init_dust_source_fct1(self, lam, iRT, photon_energy, J_th, n_type_flux, download=True):
+        """init_dust_source_fct1 (dust_ray_tracing.f90:636-708) from the xI_scatt tally on the device; eps (45, 2, ntf, n_cells)"""
+        J = np.ascontiguousarray(J_th, np.float64)
+        eps = np.zeros((45, 2, n_type_flux, self.P.n_cells), np.float64, order="F") if download else None
+        self._check(self.lib.mcfost_b200_init_dust_source_fct1(self.h, C.c_int32(lam), C.c_int32(iRT), C.c_double(photon_energy), _p(J), _p(eps)))
+        return eps
+
+    def integ_ray_dust(self, lam, x, y, z, u, v, w, icell, tau_dark_zone_obs, n_type_flux):
+        """integ_ray_dust (optical_depth.f90:1327-1421), method-1 source function: (n_type_flux, n)"""
+        x, y, z, u, v, w = self._f64(x, y, z, u, v, w)
+        n = len(x)
+        icell = np.ascontiguousarray(icell, np.int32)
+        out = np.zeros((n_type_flux, n), np.float64, order="F")
+        self._check(self.lib.mcfost_b200_integ_ray_dust(self.h, C.c_int32(lam), C.c_int64(n), _p(x), _p(y), _p(z), _p(u), _p(v), _p(w), _p(icell),
+                                                        C.c_float(tau_dark_zone_obs), _p(out)))
+        return out
 
     def compute_column(self, lam, cx, cy, cz, factor=None):
         """compute_column (optical_depth.f90:328-415): (n_cells, 4) real, column-major; factor None = optical depth at lam"""

@@ -100,7 +100,7 @@ int mcfost_b200_upload_grid(mcb_handle* h, const mcb_grid* g) {
   CK(cudaSetDevice(h->device));
   DevModel& m = h->m;
   if (g->kind < MCB_GRID_CYL || g->kind > MCB_GRID_VORONOI) return fail(h, MCB_ERR_BAD_ARG, "unknown grid kind");
-  if (g->n_stars > MAX_STARS) return fail(h, MCB_ERR_UNSUPPORTED, "more than 8 stars");
+  if (g->n_stars > MAX_STARS) return fail(h, MCB_ERR_UNSUPPORTED, "more than 15 stars (4 bits of the packed packet state)");
   // limits of the packed packet state (transport.cuh pack_cell: zj in 16 signed bits, k in 16 bits)
   if (g->kind != MCB_GRID_VORONOI && (g->nz > 32766 || g->n_az > 65535)) return fail(h, MCB_ERR_UNSUPPORTED, "nz > 32766 or n_az > 65535");
   m.kind = g->kind; m.l3D = g->l3D; m.n_rad = g->n_rad; m.nz = g->nz; m.n_az = g->n_az; m.n_cells = g->n_cells;
@@ -510,6 +510,7 @@ static int setup_tallies(mcb_handle* h, const mcb_run_params* r, bool lxJ, bool 
   h->n_1g = n_1g; h->n_1g_nRE = n_1g_nRE;
   if ((rc = reserve(h, "work", (size_t)(48 + 2 * r->n_photons_loop), &m.work))) return rc;
   h->n_tally = L.total; h->n_xI = n_xI; h->lay_xJ = lxJ; h->lay_nsed = n_sed; h->n_type_flux = n_type_flux;
+  h->rt1_n_rt = rt1 ? n_rt : 0; h->rt1_pola = r->lsepar_pola ? 1 : 0; h->rt1_contrib = r->lsepar_contrib ? 1 : 0;
   if (realloc_ || r->reset_tallies) {
     CK(cudaMemsetAsync(m.tally, 0, (size_t)L.total * sizeof(double), h->stream));
     if (n_xI) CK(cudaMemsetAsync(m.xI, 0, (size_t)n_xI * sizeof(float), h->stream));
@@ -1203,6 +1204,84 @@ __global__ void init_reemission_rows_kernel(int n_lambda, int n_T, int n_rows, c
   } else for (int l = 0; l < n_lambda; ++l) c[l] = 0.0;
 }
 
+// ---- ray-tracing method 1: source function and formal solution (dust_ray_tracing.f90:636-708,1458-1485; optical_depth.f90:1327-1421)
+// eps_dust1(k, psup, itype, icell) with the storage extents of the xI_scatt tally (N_AZ_RT x 2); on a 3D grid only (1, 1) is used.
+__global__ void init_dust_source_fct1_kernel(const __grid_constant__ DevModel m, int lambda, int iRT, int n_RT, double photon_energy,
+                                             const double* J_th, const float* xI, int n_az_rt, int n_theta_rt, int ntf, int n_stokes, int pola,
+                                             int contrib, double* eps) {
+  const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= (int64_t)N_AZ_RT * 2 * m.n_cells) return;
+  const int k = (int)(q % N_AZ_RT) + 1, psup = (int)((q / N_AZ_RT) % 2) + 1, idx = (int)(q / (2 * N_AZ_RT));
+  double* e = eps + (size_t)(k - 1) + (size_t)N_AZ_RT * ((size_t)(psup - 1) + 2 * ((size_t)ntf * (size_t)idx));
+  const size_t stride = (size_t)N_AZ_RT * 2;
+  for (int it = 0; it < ntf; ++it) e[stride * it] = 0.0;
+  if (k > n_az_rt || psup > n_theta_rt) return;
+  const int p_icell = (m.p_n_cells != 1) ? idx + 1 : 1;
+  const double factor = photon_energy / m.volume[idx] * n_az_rt * n_theta_rt;
+  const double kappa_ext = m.kappa[(p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)] * m.kappa_factor[idx];
+  const double kappa_sca = kappa_ext * m.albedo[(p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)];
+  if (!(kappa_ext > MCB_TINY_DP)) return;
+  const float* xi = xI + (size_t)(k - 1) + (size_t)N_AZ_RT * ((size_t)(psup - 1) + 2 * ((size_t)ntf * ((size_t)(iRT - 1) + (size_t)n_RT * (size_t)idx)));
+  auto I_scatt = [&](int itype) { return (double)xi[stride * (itype - 1)] * factor * kappa_sca; };
+  e[0] = (I_scatt(1) + J_th[idx]) / kappa_ext;
+  if (pola) for (int it = 2; it <= 4; ++it) e[stride * (it - 1)] = I_scatt(it) / kappa_ext;
+  if (contrib) {
+    e[stride * (n_stokes + 1)] = I_scatt(n_stokes + 2) / kappa_ext;
+    e[stride * (n_stokes + 2)] = J_th[idx] / kappa_ext;
+    e[stride * (n_stokes + 3)] = I_scatt(n_stokes + 4) / kappa_ext;
+  }
+}
+
+template <class G>
+__global__ void integ_ray_dust_kernel(const __grid_constant__ DevModel m, int64_t n, int lambda, const double* x, const double* y, const double* z,
+                                      const double* u, const double* v, const double* w, const int* icell, float tau_dark_zone_obs,
+                                      const double* eps, int n_az_rt, int ntf, double* out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  typename G::CellT c0, c_prev, c1;
+  cell_of_id(m, icell[i], c0); null_cell(c_prev);
+  const double uu = u[i], vv = v[i], ww = w[i];
+  const DirInv d = dir_invariants(uu, vv, ww);
+  double x0 = x[i], y0 = y[i], z0 = z[i];
+  const int i_star_hit = intersect_stars(m, x0, y0, z0, uu, vv, ww);
+  const bool variable_dust = m.p_n_cells != 1;
+  double acc[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) acc[it] = 0.0;
+  double tau = 0.0;
+  const size_t stride = (size_t)N_AZ_RT * 2;
+  for (int ns = 0; ns < 100000000; ++ns) {
+    if (G::test_exit(m, c0, x0, y0, z0)) break;
+    if (i_star_hit > 0) {
+      typename G::CellT cs; cell_of_id(m, m.star_icell[i_star_hit - 1], cs);
+      if (same_cell(c0, cs)) break;
+    }
+    double x1, y1, z1, lcon, lvoid;
+    G::cross(m, d, x0, y0, z0, uu, vv, ww, c0, c_prev, x1, y1, z1, c1, lcon, lvoid);      // (previous_cell = 0 at every step, :1388)
+    const int idx = tally_index(m, c0);
+    if (idx >= 0) {
+      const int p_icell = variable_dust ? idx + 1 : 1;
+      const double dtau = lcon * __ldg(m.kappa + (p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)) * __ldg(m.kappa_factor + idx);
+      const double xm = 0.5 * (x0 + x1), ym = 0.5 * (y0 + y1), zm = 0.5 * (z0 + z1);
+      int k = 1, psup = 1;
+      if (!m.l3D) {
+        psup = (zm > 0.0) ? 1 : 2;
+        const double phi_pos = atan2(xm, ym);
+        k = (int)floor(fmodulo(phi_pos, MCB_TWO_PI) / MCB_TWO_PI * n_az_rt) + 1;
+        if (k > n_az_rt) k = n_az_rt;
+      }
+      const double wgt = exp(-tau) * (1.0 - exp(-dtau));
+      const double* e = eps + (size_t)(k - 1) + (size_t)N_AZ_RT * ((size_t)(psup - 1) + 2 * ((size_t)ntf * (size_t)idx));
+#pragma unroll
+      for (int it = 0; it < 8; ++it) if (it < ntf) acc[it] = acc[it] + wgt * __ldg(e + stride * it);
+      tau = tau + dtau;
+      if (tau > (double)tau_dark_zone_obs) break;
+    }
+    x0 = x1; y0 = y1; z0 = z1; c0 = c1;
+  }
+  for (int it = 0; it < ntf; ++it) out[(size_t)ntf * i + it] = acc[it];
+}
+
 // optical_depth.f90:21-182 with Stokes = 0 (no tallies)
 template <class G>
 __global__ void physical_length_kernel(const __grid_constant__ DevModel m, int64_t n, int lambda, double* x, double* y, double* z,
@@ -1506,6 +1585,60 @@ int mcfost_b200_init_reemission_grains(mcb_handle* h, const double* tab_lambda, 
   init_reemission_rows_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(nl, nT, nk, nullptr, 0, dca, n_grains_tot, k_start - 1, dB_, ddB, dlogE, dE, dcdf);
   CK(cudaGetLastError());
   s.out(log_E_em_1grain, dlogE, n); s.out(E_em_1grain, dE, n); s.out(kdB_dT_1grain_CDF, dcdf, n * nl);
+  CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
+}
+
+int mcfost_b200_init_dust_source_fct1(mcb_handle* h, int32_t lambda, int32_t iRT, double photon_energy, const double* J_th, double* eps_dust1) {
+  if (!h || !J_th) return MCB_ERR_BAD_ARG;
+  if (!h->has_grid || !h->has_op) return fail(h, MCB_ERR_STATE, "init_dust_source_fct1 before upload_grid/opacity");
+  if (h->gk == GK_VOR) return fail(h, MCB_ERR_UNSUPPORTED, "init_dust_source_fct1: structured grids (the rt1 tally is tabulated on them)");
+  DevModel& m = h->m;
+  if (!h->n_xI || !h->rt1_n_rt) return fail(h, MCB_ERR_STATE, "init_dust_source_fct1: no xI_scatt tally on the device (run a step with lscatt_ray_tracing1 first)");
+  if (lambda < 1 || lambda > m.n_lambda) return fail(h, MCB_ERR_BAD_ARG, "lambda out of range");
+  if (iRT < 1 || iRT > h->rt1_n_rt) return fail(h, MCB_ERR_BAD_ARG, "iRT out of range (RT2d_to_RT1d(ibin, iaz), 1-based)");
+  CK(cudaSetDevice(h->device));
+  const int ntf = h->n_type_flux, n_stokes = h->rt1_pola ? 4 : 1;
+  const int n_az_rt = m.l3D ? 1 : N_AZ_RT, n_theta_rt = m.l3D ? 1 : 2;
+  const int64_t ne = (int64_t)N_AZ_RT * 2 * ntf * m.n_cells;
+  double* deps = nullptr;
+  int rc;
+  if ((rc = reserve(h, "eps_dust1", (size_t)ne, &deps))) return rc;
+  Scratch s{h};
+  const double* dJ = s.in(J_th, m.n_cells);
+  if (!dJ) return fail(h, MCB_ERR_CUDA, "scratch allocation failed");
+  const int64_t nq = (int64_t)N_AZ_RT * 2 * m.n_cells;
+  init_dust_source_fct1_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, h->stream>>>(m, lambda, iRT, h->rt1_n_rt, photon_energy, dJ, m.xI, n_az_rt,
+                                                                                  n_theta_rt, ntf, n_stokes, h->rt1_pola, h->rt1_contrib, deps);
+  CK(cudaGetLastError());
+  if (eps_dust1) CK(cudaMemcpyAsync(eps_dust1, deps, (size_t)ne * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->eps_ntf = ntf; h->eps_lambda = lambda;
+  return MCB_OK;
+}
+
+int mcfost_b200_integ_ray_dust(mcb_handle* h, int32_t lambda, int64_t n, const double* x, const double* y, const double* z, const double* u,
+                               const double* v, const double* w, const int32_t* icell, float tau_dark_zone_obs, double* I) {
+  if (!h || n < 0) return MCB_ERR_BAD_ARG;
+  if (!h->has_grid || !h->has_op) return fail(h, MCB_ERR_STATE, "integ_ray_dust before upload_grid/opacity");
+  if (h->gk == GK_VOR) return fail(h, MCB_ERR_UNSUPPORTED, "integ_ray_dust: structured grids");
+  if (!h->eps_ntf || !h->bufs.count("eps_dust1")) return fail(h, MCB_ERR_STATE, "integ_ray_dust before init_dust_source_fct1");
+  if (lambda != h->eps_lambda) return fail(h, MCB_ERR_BAD_ARG, "integ_ray_dust: the source function on the device was built for another wavelength");
+  if (n == 0) return MCB_OK;
+  if (!x || !y || !z || !u || !v || !w || !icell || !I) return MCB_ERR_BAD_ARG;
+  CK(cudaSetDevice(h->device));
+  const int ntf = h->eps_ntf;
+  Scratch s{h};
+  const double *dx = s.in(x, n), *dy = s.in(y, n), *dz = s.in(z, n), *du = s.in(u, n), *dv = s.in(v, n), *dw = s.in(w, n);
+  const int* dic = s.in(icell, n);
+  double* dout = s.in<double>(nullptr, n * ntf);
+  if (!dx || !dy || !dz || !du || !dv || !dw || !dic || !dout) return fail(h, MCB_ERR_CUDA, "scratch allocation failed");
+  const double* deps = (const double*)h->bufs["eps_dust1"];
+  const int n_az_rt = h->m.l3D ? 1 : N_AZ_RT;
+  const unsigned nb = (unsigned)((n + 127) / 128);
+  DISPATCH(integ_ray_dust_kernel, h->m, n, lambda, dx, dy, dz, du, dv, dw, dic, tau_dark_zone_obs, deps, n_az_rt, ntf, dout);
+  CK(cudaGetLastError());
+  s.out(I, dout, n * ntf);
   CK(cudaStreamSynchronize(h->stream));
   return MCB_OK;
 }

@@ -33,6 +33,8 @@ struct mcb_handle {
   int lay_nsed = -1;
   int n_photons_loop_alloc = 0;
   int n_type_flux = 1;
+  int eps_ntf = 0, eps_lambda = 0;                     // eps_dust1 on the device: N_type_flux and wavelength it was built for
+  int rt1_n_rt = 0, rt1_pola = 0, rt1_contrib = 0;      // shape of the xI_scatt tally of the last rt1 launch (init_dust_source_fct1)
   int straggler_sms = 0;                  // (kept for the set_overlap signature)
   int launches_last_call = 0;             // kernels of this library launched by the last mcfost_b200_launch
   int overlap_sms = 0;                    // mcfost_b200_set_overlap: SMs reserved for straggler launches (0 = off)

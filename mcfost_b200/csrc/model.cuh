@@ -7,7 +7,7 @@
 
 namespace mcb {
 
-constexpr int MAX_STARS = 8;
+constexpr int MAX_STARS = 15;      // the index of the star a flight points at has 4 bits in the packed packet state (0 = none)
 constexpr int NANG = 180;      // nang_scatt
 constexpr int N_AZ_RT = 45;    // n_az_rt
 constexpr int MAX_RT = 16;     // max RT_n_incl * RT_n_az observer directions

@@ -210,6 +210,32 @@ class Oracle:
                                                            _p(logE), _p(Eem), _p(cdf)))
         return logE, Eem, cdf
 
+    def init_dust_source_fct1(self, lam, iRT, n_RT, photon_energy, J_th, xI, n_type_flux, pola, contrib):
+        """init_dust_source_fct1 (dust_ray_tracing.f90:636-708): eps (45, 2, ntf, n_cells) from xI_scatt (45, 2, ntf, n_RT, n_cells)"""
+        P = self.P
+        J = np.ascontiguousarray(J_th, np.float64)
+        xi = np.ascontiguousarray(np.asarray(xI, np.float32).reshape(-1))
+        n_az, n_th = (1, 1) if P.l3D else (45, 2)
+        eps = np.zeros((45, 2, n_type_flux, P.n_cells), np.float64, order="F")
+        self._check(self.lib.oracle_init_dust_source_fct1(self.h, C.c_int32(lam), C.c_int32(iRT), C.c_int32(n_RT), C.c_double(photon_energy), _p(J), _p(xi),
+                                                          C.c_int32(45), C.c_int32(2), C.c_int32(n_az), C.c_int32(n_th), C.c_int32(n_type_flux),
+                                                          C.c_int32(4 if pola else 1), C.c_int32(int(pola)), C.c_int32(int(contrib)), _p(eps)))
+        return eps
+
+    def integ_ray_dust(self, lam, x, y, z, u, v, w, icell, tau_dark_zone_obs, eps):
+        """integ_ray_dust (optical_depth.f90:1327-1421) with the method-1 source function eps (45, 2, ntf, n_cells): (ntf, n)"""
+        P = self.P
+        x, y, z, u, v, w = self._f64(x, y, z, u, v, w)
+        n = len(x)
+        icell = np.ascontiguousarray(icell, np.int32)
+        e = np.asfortranarray(eps, np.float64)
+        ntf = e.shape[2]
+        out = np.zeros((ntf, n), np.float64, order="F")
+        self._check(self.lib.oracle_integ_ray_dust(self.h, C.c_int32(lam), C.c_int64(n), _p(x), _p(y), _p(z), _p(u), _p(v), _p(w), _p(icell),
+                                                   C.c_float(tau_dark_zone_obs), _p(e), C.c_int32(45), C.c_int32(2), C.c_int32(1 if P.l3D else 45),
+                                                   C.c_int32(ntf), _p(out)))
+        return out
+
     def compute_column(self, lam, cx, cy, cz, factor=None):
         """compute_column (optical_depth.f90:328-415): (n_cells, 4) real, column-major; factor None = optical depth at lam"""
         cx, cy, cz = self._f64(cx, cy, cz)

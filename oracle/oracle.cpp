@@ -1476,6 +1476,78 @@ struct Oracle {
   }
 
   // =====================================================================
+  // dust_ray_tracing.f90:636-708  init_dust_source_fct1: the source function of ray-tracing method 1 from the scattered
+  // specific intensity.  xI is xI_scatt(n_az_rt, n_theta_rt, N_type_flux, n_RT, n_cells) already summed over the threads
+  // (`real`); storage extents are az_dim x th_dim (45 x 2), of which n_az_rt x n_theta_rt are used (1 x 1 on a 3D grid).
+  // =====================================================================
+  void init_dust_source_fct1(int lambda, int iRT, int n_RT, double photon_energy, const double* J_th, const float* xI, int az_dim, int th_dim,
+                             int n_az_rt, int n_theta_rt, int N_type_flux, int n_Stokes, bool lsepar_pola, bool lsepar_contrib, double* eps) const {
+    const size_t per_cell = (size_t)az_dim * th_dim * N_type_flux;
+    std::fill(eps, eps + per_cell * (size_t)g.n_cells, 0.0);
+    for (int icell = 1; icell <= g.n_cells; ++icell) {
+      const int p_icell = lvariable_dust() ? icell : 1;
+      const double factor = photon_energy / volume(icell) * n_az_rt * n_theta_rt;
+      const double kappa_ext = kappa(p_icell, lambda) * kappa_factor(icell);
+      const double kappa_sca = kappa_ext * tab_albedo_pos(p_icell, lambda);
+      if (!(kappa_ext > tiny_dp)) continue;
+      for (int psup = 1; psup <= n_theta_rt; ++psup)
+        for (int k = 1; k <= n_az_rt; ++k) {
+          auto I_scatt = [&](int itype) {
+            const size_t q = (size_t)(k - 1) + (size_t)az_dim * ((size_t)(psup - 1) + (size_t)th_dim * ((size_t)(itype - 1) + (size_t)N_type_flux * ((size_t)(iRT - 1) + (size_t)n_RT * (size_t)(icell - 1))));
+            return (double)xI[q] * factor * kappa_sca;
+          };
+          auto E = [&](int itype) -> double& { return eps[(size_t)(k - 1) + (size_t)az_dim * ((size_t)(psup - 1) + (size_t)th_dim * ((size_t)(itype - 1) + (size_t)N_type_flux * (size_t)(icell - 1)))]; };
+          E(1) = (I_scatt(1) + J_th[icell - 1]) / kappa_ext;
+          if (lsepar_pola) for (int it = 2; it <= 4; ++it) E(it) = I_scatt(it) / kappa_ext;
+          if (lsepar_contrib) {
+            E(n_Stokes + 2) = I_scatt(n_Stokes + 2) / kappa_ext;
+            E(n_Stokes + 3) = J_th[icell - 1] / kappa_ext;
+            E(n_Stokes + 4) = I_scatt(n_Stokes + 4) / kappa_ext;
+          }
+        }
+    }
+  }
+  // =====================================================================
+  // optical_depth.f90:1327-1421  integ_ray_dust with dust_source_fct of method 1 (dust_ray_tracing.f90:1458-1485): the
+  // formal solution along a ray that is followed backwards from the observer's side
+  // =====================================================================
+  void integ_ray_dust(int lambda, int icell_in, double x, double y, double z, double u, double v, double w, float tau_dark_zone_obs,
+                      const double* eps, int az_dim, int th_dim, int n_az_rt, int N_type_flux, double* out) {
+    double x0 = x, y0 = y, z0 = z, x1 = x, y1 = y, z1 = z, l, l_contrib, l_void_before;
+    int next_cell = icell_in, icell, previous_cell, icell_star = 0, i_star = 0;
+    bool lintersect_stars = false;
+    double tau = 0.0;
+    for (int it = 0; it < N_type_flux; ++it) out[it] = 0.0;
+    intersect_stars(x, y, z, u, v, w, lintersect_stars, i_star, icell_star);
+    for (;;) {
+      icell = next_cell;
+      x0 = x1; y0 = y1; z0 = z1;
+      const bool lcell_not_empty = icell <= g.n_cells;
+      if (test_exit_grid(icell, x0, y0, z0)) return;
+      if (lintersect_stars && icell == icell_star) return;
+      previous_cell = 0;
+      cross_cell(x0, y0, z0, u, v, w, icell, previous_cell, x1, y1, z1, next_cell, l, l_contrib, l_void_before);
+      if (lcell_not_empty) {
+        const int p_icell = lvariable_dust() ? icell : 1;
+        const double dtau = l_contrib * kappa(p_icell, lambda) * kappa_factor(icell);
+        const double xm = 0.5 * (x0 + x1), ym = 0.5 * (y0 + y1), zm = 0.5 * (z0 + z1);
+        int k = 1, psup = 1;
+        if (!g.l3D) {
+          psup = (zm > 0.0) ? 1 : 2;
+          const double phi_pos = std::atan2(xm, ym);
+          k = (int)std::floor(fmodulo(phi_pos, two_pi) / two_pi * n_az_rt) + 1;
+          if (k > n_az_rt) k = n_az_rt;
+        }
+        const double wgt = std::exp(-tau) * (1.0 - std::exp(-dtau));
+        for (int it = 1; it <= N_type_flux; ++it)
+          out[it - 1] = out[it - 1] + wgt * eps[(size_t)(k - 1) + (size_t)az_dim * ((size_t)(psup - 1) + (size_t)th_dim * ((size_t)(it - 1) + (size_t)N_type_flux * (size_t)(icell - 1)))];
+        tau = tau + dtau;
+        if (tau > tau_dark_zone_obs) return;
+      }
+    }
+  }
+
+  // =====================================================================
   // scattering.f90:1354-1383  hg
   // =====================================================================
   static void hg(float g_, float rand, int& itheta, double& cospsi) {
@@ -2508,6 +2580,21 @@ int oracle_init_reemission(void* h, const double* tab_lambda, const double* tab_
 int oracle_init_reemission_grains(void* h, const double* tab_lambda, const double* tab_delta_lambda, const float* C_abs_norm, int32_t n_grains_tot,
                                   int32_t k_start, int32_t k_end, double* logE, double* E_em, double* cdf) {
   ((Oracle*)h)->init_reemission_grains(tab_lambda, tab_delta_lambda, C_abs_norm, n_grains_tot, k_start, k_end, logE, E_em, cdf);
+  return MCB_OK;
+}
+int oracle_init_dust_source_fct1(void* h, int32_t lambda, int32_t iRT, int32_t n_RT, double photon_energy, const double* J_th, const float* xI,
+                                 int32_t az_dim, int32_t th_dim, int32_t n_az_rt, int32_t n_theta_rt, int32_t N_type_flux, int32_t n_Stokes,
+                                 int32_t lsepar_pola, int32_t lsepar_contrib, double* eps) {
+  ((Oracle*)h)->init_dust_source_fct1(lambda, iRT, n_RT, photon_energy, J_th, xI, az_dim, th_dim, n_az_rt, n_theta_rt, N_type_flux, n_Stokes,
+                                      lsepar_pola != 0, lsepar_contrib != 0, eps);
+  return MCB_OK;
+}
+int oracle_integ_ray_dust(void* h, int32_t lambda, int64_t n, const double* x, const double* y, const double* z, const double* u, const double* v,
+                          const double* w, const int32_t* icell, float tau_dark_zone_obs, const double* eps, int32_t az_dim, int32_t th_dim,
+                          int32_t n_az_rt, int32_t N_type_flux, double* out) {
+  Oracle* O = (Oracle*)h;
+  for (int64_t i = 0; i < n; ++i)
+    O->integ_ray_dust(lambda, icell[i], x[i], y[i], z[i], u[i], v[i], w[i], tau_dark_zone_obs, eps, az_dim, th_dim, n_az_rt, N_type_flux, out + (size_t)N_type_flux * i);
   return MCB_OK;
 }
 int oracle_compute_column(void* h, int32_t lambda, const double* factor, const double* cx, const double* cy, const double* cz, float* column) {

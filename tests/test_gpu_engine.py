@@ -403,3 +403,81 @@ def test_init_reemission_on_the_device_equals_oracle():
         for a, b in zip(eo, eg):
             assert a.shape == b.shape and np.allclose(b, a, rtol=1e-12, atol=1e-15)
     Gg.close()
+
+
+@pytest.mark.parametrize("n_stars", [3, 12])
+def test_several_stars_packet_by_packet(n_stars):
+    """Several stars (stars.f90:581-605 CDF_E_star, emit_packet :select_etoile, intersect_stars :812-884): a compact multiple
+    system inside the inner cavity.  Forced-scattering mode has no feedback, so with shared Philox streams the GPU follows the
+    oracle's packets; then a thermal step, statistically.  12 stars: above the 8 of round 1 (15 fit the packed state)."""
+    P = small_problems()["cyl2D"]()
+    rng = np.random.default_rng(7)
+    P.n_stars = n_stars
+    xyz = rng.uniform(-0.35, 0.35, (3, n_stars)); xyz[2] *= 0.3; xyz[:, 0] = 0.0
+    rad = rng.uniform(1.0, 3.0, n_stars) * S.RSUN_TO_AU
+    P.star_xyzr = np.asfortranarray(np.vstack([xyz, rad[None, :]]))
+    P.star_T = rng.uniform(3500.0, 9000.0, n_stars); P.star_out_model = np.zeros(n_stars, np.int32)
+    S.locate_stars(P, Oracle(P).index_cell)
+    S.star_energy(P); S.repartition_energie(P)
+    assert P.CDF_E_star.shape == (P.n_lambda, n_stars + 1)
+    from test_gpu_parity import _sed_kwargs
+    kw = _sed_kwargs(False)
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(kw.pop("lambda_in"), kw.pop("p_lambda_in"), kw.pop("n_photons2"), kw.pop("n_phot_lim"), 1, False, **kw)
+    to = Oracle(P).run(n_threads=0, n_xI=45 * 2 * 5 * 3 * P.n_cells, **_sed_kwargs(False))
+    assert tg.stats[0] == to.stats[0]
+    assert abs(tg.stats[1] - to.stats[1]) <= 1e-4 * to.stats[1] and abs(tg.stats[2] - to.stats[2]) <= 1e-4 * to.stats[2]
+    assert abs(tg.stats[5] - to.stats[5]) <= 3                            # packets that end on a star (or fade out)
+    assert np.allclose(tg.n_phot_sed, to.n_phot_sed, atol=3) and np.allclose(tg.sed.sum(axis=0), to.sed.sum(axis=0), rtol=2e-3)
+    assert np.allclose(tg.sed_star.sum(axis=0), to.sed_star.sum(axis=0), rtol=2e-3)
+    # thermal step
+    th_g = G.mc_photon_loop(1, 1, 800, 1.0e30, 1, False)
+    G.close()
+    th_o = Oracle(P, fast=True).run(n_threads=0, n_photons2=800)
+    assert th_g.stats[0] == th_o.stats[0] == 128 * 800
+    assert abs(th_g.xKJ_abs.sum() / th_o.xKJ_abs.sum() - 1) < 0.02 and abs(th_g.stats[5] / max(th_o.stats[5], 1) - 1) < 0.3
+    To, Tg = S.temp_finale(P, th_o.xKJ_abs), S.temp_finale(P, th_g.xKJ_abs)
+    lit = (th_o.xKJ_abs > 0) & (th_g.xKJ_abs > 0)
+    assert np.median(np.abs(Tg[lit] - To[lit]) / To[lit]) < 0.02
+    Pbad = small_problems()["cyl2D"]()
+    Pbad.n_stars = 16
+    Pbad.star_xyzr = np.asfortranarray(np.tile(Pbad.star_xyzr, (1, 16))); Pbad.star_T = np.full(16, 5000.0)
+    Pbad.star_out_model = np.zeros(16, np.int32); Pbad.star_icell = np.full(16, Pbad.star_icell[0], np.int32)
+    S.star_energy(Pbad)
+    with pytest.raises(api.McfostB200Error):
+        api.PhotonLoop(Pbad)
+
+
+@pytest.mark.parametrize("pola", [False, True])
+def test_rt1_source_function_and_formal_solution_match_oracle(pola):
+    """Ray-tracing method 1 after an SED step: init_dust_source_fct1 (dust_ray_tracing.f90:636-708) on the xI_scatt tally that
+    the step left on the device, then integ_ray_dust (optical_depth.f90:1327-1421) along random rays, against the oracle fed
+    with the same tally: eps_dust1 is pure arithmetic (identical), the formal solution has exp / atan2 (1e-11)."""
+    from test_gpu_parity import _sed_kwargs
+    P = small_problems()["cyl2D"]()
+    kw = _sed_kwargs(pola)
+    lam = kw["lambda_in"]
+    ntf = (4 if pola else 1) + 4
+    G = api.PhotonLoop(P)
+    tg = G.mc_photon_loop(kw.pop("lambda_in"), kw.pop("p_lambda_in"), kw.pop("n_photons2"), kw.pop("n_phot_lim"), 1, False, **kw)
+    assert tg.xI_scatt.size == 45 * 2 * ntf * 3 * P.n_cells and np.abs(tg.xI_scatt).sum() > 0
+    J = np.random.default_rng(2).uniform(0.0, 1.0e-3, P.n_cells) * np.abs(tg.xI_scatt).max()
+    O = Oracle(P)
+    ic, x, y, z, u, v, w = rays_in_cells(P, 20000, seed=9)
+    for iRT in (1, 3):
+        eg = G.init_dust_source_fct1(lam, iRT, 2.5e-3, J, ntf)
+        eo = O.init_dust_source_fct1(lam, iRT, 3, 2.5e-3, J, tg.xI_scatt, ntf, pola, True)
+        assert np.array_equal(eg, eo) and np.abs(eg[:, :, 0]).sum() > 0
+        assert (eg[:, :, (4 if pola else 1)] == 0).all()                   # direct stellar light is not part of the source function
+        for tau_obs in (1.0e30, 3.0):
+            Ig = G.integ_ray_dust(lam, x, y, z, u, v, w, ic, tau_obs, ntf)
+            Io = O.integ_ray_dust(lam, x, y, z, u, v, w, ic, tau_obs, eo)
+            scale = np.abs(Io).max(axis=1, keepdims=True) + 1e-300
+            assert np.abs(Ig - Io).max() / scale.max() < 1e-9
+            assert np.mean(np.abs(Ig - Io) <= 1e-11 * scale) > 0.9999          # (a ray on an azimuthal bin edge may flip with atan2's last bit)
+            assert (Ig[0] > 0).mean() > 0.9
+    with pytest.raises(api.McfostB200Error):
+        G.init_dust_source_fct1(lam, 4, 1.0, J, ntf)                      # only 3 observer directions were tallied
+    with pytest.raises(api.McfostB200Error):
+        G.integ_ray_dust(lam + 1, x, y, z, u, v, w, ic, 1.0e30, ntf)      # source function of another wavelength
+    G.close()

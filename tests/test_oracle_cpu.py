@@ -354,3 +354,25 @@ def test_init_reemission_oracle_matches_the_generators_tables():
         assert logE.shape == np.asarray(lE).shape and c.shape == np.asarray(cd).shape
         assert np.abs(logE - lE).max() < 1e-6 and np.abs(c - cd).max() < 1e-6
         assert np.allclose(np.log(Eem), logE, rtol=0, atol=1e-12) and (c[0] == 0).all()
+
+
+def test_integ_ray_dust_telescopes_for_a_uniform_source_function():
+    """integ_ray_dust (optical_depth.f90:1327-1421) of the oracle: with eps_dust1 = 1 everywhere the sum of
+    exp(-tau)(1 - exp(-dtau)) telescopes to 1 - exp(-tau_tot), tau_tot from optical_length_tot; with tau_dark_zone_obs
+    small the integration stops early; init_dust_source_fct1 without scattered light gives J_th / kappa."""
+    P = small_problems()["cyl2D"]()
+    O = Oracle(P)
+    ic, x, y, z, u, v, w = rays_in_cells(P, 2000, seed=5)
+    lam = 20
+    eps = np.ones((45, 2, 1, P.n_cells), order="F")
+    I = O.integ_ray_dust(lam, x, y, z, u, v, w, ic, 1.0e30, eps)
+    tau = O.optical_length_tot(lam, x, y, z, u, v, w, ic)["tau_tot"]
+    assert I.shape == (1, 2000) and np.allclose(I[0], 1.0 - np.exp(-tau), rtol=1e-6, atol=1e-7)
+    I2 = O.integ_ray_dust(lam, x, y, z, u, v, w, ic, 0.5, eps)
+    deep = tau > 5.0
+    assert deep.sum() > 10 and (I2[0][deep] < I[0][deep]).all() and (I2[0][deep] > 1.0 - np.exp(-0.5) - 1e-12).all()
+    J = np.random.default_rng(1).uniform(1.0, 2.0, P.n_cells)
+    e = O.init_dust_source_fct1(lam, 1, 1, 1.0, J, np.zeros((45, 2, 1, 1, P.n_cells), np.float32), 1, False, False)
+    kap = P.kappa.reshape(P.p_n_cells, P.n_lambda)[0, lam - 1] * P.kappa_factor
+    ok = kap > 0
+    assert np.allclose(e[3, 1, 0][ok], (J / np.where(ok, kap, 1.0))[ok], rtol=1e-14) and (e[:, :, 0][:, :, ~ok] == 0).all()
