@@ -1178,7 +1178,6 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
   if (i_star_hit > 0) cell_of_id(m, m.star_icell[i_star_hit - 1], c_star);      // the cell of the star this flight points at
   const int n_in = __popc(__ballot_sync(0xffffffffu, valid));
   bool flying = valid, interact = false;
-  unsigned n_steps = 0;      // (Stats lives in local memory, it is passed by reference to the phases: counted in a register, added once)
 #pragma unroll 1
   for (int it = 0; it < FLY_STEPS; ++it) {
     // leave the loop once fewer than half of this chunk's packets are still in flight: the rest of the
@@ -1216,7 +1215,7 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
       opacity = t_kappa<SM>(m, p_icell, lambda) * kf;
     }
     const Hit h = G::distance(m, dinv, x0, y0, z0, u, v, w, c0, c_old);
-    ++n_steps;
+    ++st.steps;
     double l_contrib = hit_l_contrib(h), l = h.l;
     const double tau_c = l_contrib * opacity;
     bool lstop = false;
@@ -1266,7 +1265,6 @@ __device__ __noinline__ int phase_fly(int slot, bool valid, Stats& st) {
     xo = x0; yo = y0; zo = z0; c_old = c0;
     x0 = x1; y0 = y1; z0 = z1; c0 = c1; idx_c = tally_index(m, c1);
   }
-  st.steps += n_steps;
   if (valid) {
     if (interact) {
       // the flight ended with an interaction at (x0,y0,z0) in cell c0 (dust_transfer.f90:1260-1284)
