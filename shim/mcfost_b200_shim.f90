@@ -331,6 +331,44 @@ contains
     call b200_check(mcfost_b200_multi_upload_dark_zone(b200, dark_i32), "upload_dark_zone")      ! the other GPUs of the node
   end subroutine define_dark_zone_b200
 
+  ! Replaces  call compute_column(type, column, lambda)  (optical_depth.f90:328-415) on GPU 0: type 2 = optical depth at
+  ! lambda, types 1 / 3 = (molecular) column density with the per-cell weight formed here exactly as the reference forms it.
+  subroutine compute_column_b200(type, column, lambda)
+    use density, only : gas_density
+    use molecular_emission, only : tab_abundance
+    integer, intent(in) :: type
+    integer, intent(in), optional :: lambda
+    real, dimension(n_cells,4), intent(out) :: column
+    real(c_double), allocatable, target :: cx(:), cy(:), cz(:), factor(:)
+    real(c_double) :: CD_units
+    type(c_ptr) :: pf
+    integer :: icell, lam
+    allocate(cx(n_cells), cy(n_cells), cz(n_cells))
+    do icell = 1, n_cells
+       if (lVoronoi) then
+          cx(icell) = Voronoi(icell)%xyz(1) ; cy(icell) = Voronoi(icell)%xyz(2) ; cz(icell) = Voronoi(icell)%xyz(3)
+       else
+          cx(icell) = r_grid(icell) * cos(phi_grid(icell)) ; cy(icell) = r_grid(icell) * sin(phi_grid(icell)) ; cz(icell) = z_grid(icell)
+       endif
+    enddo
+    pf = c_null_ptr ; lam = 1
+    if (type == 2) then
+       lam = lambda
+    else
+       allocate(factor(n_cells))
+       if (type == 1) then
+          CD_units = AU_to_m * mu_mH / (m_to_cm)**2
+          factor(:) = CD_units * gas_density(1:n_cells)
+       else
+          CD_units = AU_to_m / (m_to_cm)**2
+          factor(:) = CD_units * gas_density(1:n_cells) * tab_abundance(1:n_cells)
+       endif
+       pf = c_loc(factor)
+    endif
+    call b200_check(mcfost_b200_compute_column(mcfost_b200_multi_handle(b200, 0_c_int), int(lam, c_int32_t), pf, cx, cy, cz, column), &
+         "compute_column")
+  end subroutine compute_column_b200
+
   ! Replaces the LTE part of  call init_reemission(lheating, dudt)  (thermal_emission.f90:404-550, high-memory branch, no
   ! extra heating) after b200_upload_model: every GPU builds log_Qcool_minus_extra_heating and kdB_dT_CDF from the
   ! kappa_abs_LTE it already holds; GPU 0's copies come back into the reference's module arrays (Temp_finale, outputs).
