@@ -123,6 +123,19 @@ L2_POLICY = {"g1": _ZERO + "working set is L2-resident by design (0.5 MB tables)
              "g5": _ZERO + "mesh and per-cell data (110 MB) are of the order of L2; every packet takes its own path"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the one JSON line, on the process's real stdout (see main)"""
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.buffer.write(data); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def make_problem(n2_total, walker_factory=None, workload="g1"):
     from mcfost_b200 import synthetic as S
     if workload == "g2":
@@ -204,7 +217,7 @@ def reference_arm(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthr, "kind": "port",
                              "sample": f"oracle-OpenMP (reference restatement, the Fortran cannot be built here), {128 * n2} packets per step, schedule(dynamic,1) over 128 chunks"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def gpu_arm(args):
@@ -410,7 +423,7 @@ def gpu_arm(args):
             line["sweep"] = sweep
         if strong is not None:
             line["strong"] = strong
-        print(json.dumps(line))
+        emit(line)
     loop.close()
     if world > 1:
         dist.destroy_process_group()
@@ -433,6 +446,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: libraries that write there themselves (NCCL prints its version line to
+    # stdout when the first communicator is created) are sent to stderr; the JSON line goes to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.n2 <= 0:
         args.n2 = WORKLOADS[args.workload]["n2"]
     args.cpu_n2 = min(args.cpu_n2, args.n2)
