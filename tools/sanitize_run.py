@@ -55,4 +55,30 @@ V = S.voronoi_disk(n_points=300, n_photons_eq_th=10)
 GV = api.PhotonLoop(V)
 print("voronoi", GV.mc_photon_loop(1, 1, 10).stats[:7])
 GV.close()
+# round-2 neighbours of the path: dark zone, column densities, emission tables, rt1 source function and formal solution
+Pd = S.ref41_like(n_photons_eq_th=10, dark_zone=False, n_rad=30, nz=16, n_rad_in=5, tau_mid=1.0e5)
+Gd = api.PhotonLoop(Pd)
+d = Gd.define_dark_zone(Pd.lambda_seuil, 300.0, Pd.r_grid, Pd.z_grid, [(1, Pd.n_rad)])
+print("define_dark_zone", d["l_dark_zone"].sum(), d["ri_in"], d["ri_out"])
+cx, cy, cz = S.cell_centres(Pd)
+print("compute_column", Gd.compute_column(Pd.lambda_seuil, cx, cy, cz).max(), Gd.compute_column(1, cx, cy, cz, np.ones(Pd.n_cells)).max())
+lq, cdf = Gd.init_reemission(Pd.tab_lambda, Pd.tab_delta_lambda)
+print("init_reemission", lq.max(), cdf.max())
+kw = dict(letape_th=0, lmono=1, lscatt_ray_tracing1=1, lsepar_pola=1, lsepar_contrib=1, RT_n_incl=2, RT_n_az=1,
+          tab_u_rt=np.array([[0.0], [0.5]]), tab_v_rt=np.zeros((2, 1)), tab_w_rt=np.array([1.0, np.sqrt(0.75)]))
+t = Gd.mc_photon_loop(6, 6, 10 ** 9, 20.0, **kw)
+eps = Gd.init_dust_source_fct1(6, 2, 1.0e-3, np.full(Pd.n_cells, 1.0e-6), 8)
+from helpers import rays_in_cells
+ic, x, y, z, u, v, w = rays_in_cells(Pd, 500, seed=3)
+print("rt1", np.abs(eps).sum(), Gd.integ_ray_dust(6, x, y, z, u, v, w, ic, 100.0, 8).sum())
+Gd.close()
+P3 = small_problems()["cyl3D"]()
+G3 = api.PhotonLoop(P3)
+d3 = G3.define_dark_zone(P3.lambda_seuil, 20.0, P3.r_grid, P3.z_grid, [(1, P3.n_rad)])
+print("define_dark_zone 3D", d3["l_dark_zone"].sum())
+G3.close()
+Pg = S.multi_grain_like(n_photons_eq_th=10)
+Gg = api.PhotonLoop(Pg)
+print("init_reemission_grains", Gg.init_reemission_grains(Pg.tab_lambda, Pg.tab_delta_lambda, Pg.C_abs_norm, Pg.grain_nRE_start, Pg.grain_nRE_end)[0].max())
+Gg.close()
 print("sanitize run done")
