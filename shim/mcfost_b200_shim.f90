@@ -169,6 +169,23 @@ module mcfost_b200_shim
        type(c_ptr), value :: h, logQ, cdf
        real(c_double), intent(in) :: tab_lambda(*), tab_delta_lambda(*)
      end function
+     integer(c_int) function mcfost_b200_index_cell(h, n, x, y, z, icell) bind(C, name='mcfost_b200_index_cell')
+       import
+       type(c_ptr), value :: h
+       integer(c_int64_t), value :: n
+       real(c_double), intent(in) :: x(*), y(*), z(*)
+       integer(c_int32_t) :: icell(*)
+     end function
+     integer(c_int) function mcfost_b200_optical_length_tot(h, n, lambda, x, y, z, u, v, w, icell, tau_tot, lmin, lmax, n_steps) &
+          bind(C, name='mcfost_b200_optical_length_tot')
+       import
+       type(c_ptr), value :: h, n_steps
+       integer(c_int64_t), value :: n
+       integer(c_int32_t), value :: lambda
+       real(c_double), intent(in) :: x(*), y(*), z(*), u(*), v(*), w(*)
+       integer(c_int32_t), intent(in) :: icell(*)
+       real(c_double) :: tau_tot(*), lmin(*), lmax(*)
+     end function
      integer(c_int) function mcfost_b200_compute_column(h, lambda, factor, cx, cy, cz, column) bind(C, name='mcfost_b200_compute_column')
        import
        type(c_ptr), value :: h, factor
@@ -330,6 +347,37 @@ contains
     endif
     call b200_check(mcfost_b200_multi_upload_dark_zone(b200, dark_i32), "upload_dark_zone")      ! the other GPUs of the node
   end subroutine define_dark_zone_b200
+
+  ! Replaces  call integ_tau(lambda)  (optical_depth.f90:186-244): the optical depth from the star through the midplane and
+  ! along the inclination of interest, two rays through mcfost_b200_optical_length_tot, same messages.
+  subroutine integ_tau_b200(lambda)
+    integer, intent(in) :: lambda
+    real(c_double) :: x0(2), y0(2), z0(2), u0(2), v0(2), w0(2), tau(2), lmin(2), lmax(2)
+    integer(c_int32_t) :: icell(2)
+    type(c_ptr) :: h0
+    integer :: k, ic
+    h0 = mcfost_b200_multi_handle(b200, 0_c_int)
+    x0 = 0.0 ; y0 = 0.0 ; z0 = 0.0 ; v0 = 0.0
+    u0(1) = 1.0 ; w0(1) = 0.0
+    w0(2) = cos((angle_interet)*pi/180.) ; u0(2) = sqrt(1.0-w0(2)*w0(2))
+    call b200_check(mcfost_b200_index_cell(h0, 2_c_int64_t, x0, y0, z0, icell), "index_cell")
+    call b200_check(mcfost_b200_optical_length_tot(h0, 2_c_int64_t, int(lambda, c_int32_t), x0, y0, z0, u0, v0, w0, icell, &
+         tau, lmin, lmax, c_null_ptr), "optical_length_tot")
+    do k = 1, 2
+       if (k == 1) then
+          write(*,*) 'Integ tau in midplane = ', real(tau(1))
+       else
+          write(*,fmt='(" Integ tau (i =",f4.1," deg)   = ",E12.5)') angle_interet, real(tau(2))
+       endif
+       if (.not.lvariable_dust) then
+          ic = icell_not_empty
+          if (kappa(icell1,lambda) * kappa_factor(ic) > tiny_real) then
+             write(*,*) " Column density (g/cm^2)   = ", real(tau(k)*(dust_mass(ic)/(volume(ic)*AU_to_cm**3))/ &
+                  (kappa(icell1,lambda) * kappa_factor(ic)/AU_to_cm))
+          endif
+       endif
+    enddo
+  end subroutine integ_tau_b200
 
   ! Replaces  call compute_column(type, column, lambda)  (optical_depth.f90:328-415) on GPU 0: type 2 = optical depth at
   ! lambda, types 1 / 3 = (molecular) column density with the per-cell weight formed here exactly as the reference forms it.

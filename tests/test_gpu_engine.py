@@ -481,3 +481,21 @@ def test_rt1_source_function_and_formal_solution_match_oracle(pola):
     with pytest.raises(api.McfostB200Error):
         G.integ_ray_dust(lam + 1, x, y, z, u, v, w, ic, 1.0e30, ntf)      # source function of another wavelength
     G.close()
+
+
+@pytest.mark.parametrize("name", ["cyl2D", "cyl3D", "sph2D"])
+def test_integ_tau_rays_from_the_star_bit_exact(name):
+    """integ_tau (optical_depth.f90:186-244): the two rays it sends from the origin (midplane; the inclination of interest)
+    through index_cell + optical_length_tot, identical to the oracle's."""
+    P = small_problems()[name]()
+    O, G = Oracle(P), api.PhotonLoop(P)
+    w0 = np.array([0.0, np.cos(np.float32(60.0) * np.pi / 180.0)]); u0 = np.sqrt(1.0 - w0 * w0); u0[0] = 1.0
+    z = np.zeros(2)
+    ico, icg = O.index_cell(z, z, z), G.index_cell(z, z, z)
+    assert np.array_equal(ico, icg)
+    for lam in (1, P.lambda_seuil, P.n_lambda):
+        o = O.optical_length_tot(lam, z, z, z, u0, z, w0, ico)
+        g = G.optical_length_tot(lam, z, z, z, u0, z, w0, icg)
+        assert np.array_equal(o["tau_tot"], g["tau_tot"]) and np.array_equal(o["n_steps"], g["n_steps"]) and np.array_equal(o["lmax"], g["lmax"])
+        assert g["tau_tot"][0] > g["tau_tot"][1] > 0 or name == "sph2D"
+    G.close()
