@@ -449,6 +449,29 @@ int mcfost_b200_init_reemission_grains(mcb_handle *h, const double *tab_lambda,
         const double *tab_delta_lambda, const float *C_abs_norm,
         int32_t n_grains_tot, int32_t k_start, int32_t k_end,
         double *log_E_em_1grain, double *E_em_1grain, double *kdB_dT_1grain_CDF);
+/* repartition_energie(lambda) (thermal_emission.f90:1771-1949), LTE case, for
+ * lambda_first..lambda_last (1-based, inclusive), on the device: the thermal
+ * emission of every cell from Tdust(n_cells) (`real`) with the reference's
+ * constants, E_disk(lambda) = its sum, prob_E_cell(0:n_cells, lambda) = its
+ * cumulative sum (times weight_proba_emission(n_cells) when given,
+ * lweight_emission), normalised; dark cells (the handle's dark zone) do not
+ * emit.  The sums are parallel reductions / scans (1e-12 from the sequential
+ * sums of the reference).  tab_lambda(n_lambda) in micron; E_stars, E_ISM
+ * (n_lambda; E_ISM may be NULL).  Outputs for the wavelengths of the range:
+ * E_disk, frac_E_stars, frac_E_disk (n_lambda arrays), weight_norm (may be
+ * NULL: prob_E_cell(n_cells) / E_disk before normalisation, the factor of
+ * :1932-1934), prob_E_cell (may be NULL: a host copy of the columns).
+ * prob_E_cell, frac_E_stars and frac_E_disk STAY ON THE DEVICE as the handle's
+ * emission tables: a following mcfost_b200_upload_emission may pass NULL for
+ * those three (with 1e6 cells prob_E_cell is 8 MB per wavelength that is
+ * neither built nor uploaded by the host).  E_totale and repartition_wl_em
+ * (n_lambda-long loops on E_disk) stay with the caller.  Returns an error when
+ * a wavelength has no energy at all (the reference exits, :1900-1904). */
+int mcfost_b200_repartition_energie(mcb_handle *h, int32_t lambda_first, int32_t lambda_last,
+        const float *Tdust, const double *tab_lambda,
+        const double *E_stars, const double *E_ISM, const double *weight_proba_emission,
+        double *E_disk, double *frac_E_stars, double *frac_E_disk, double *weight_norm,
+        double *prob_E_cell);
 /* define_dark_zone(lambda, p_lambda, tau_max, ldiff_approx) (optical_depth.f90:
  * 1425-1651) on structured grids: radial and vertical optical-depth sums
  * (`real` accumulators as in the Fortran), then 11 rays of optical depth

@@ -240,8 +240,10 @@ def make_emission(P) -> Holder:
     e = mcb_emission()
     keep = {}
     for name in ("spectre_emission_cumul", "frac_E_stars", "frac_E_disk", "prob_E_cell"):
-        a = farray(getattr(P, name), np.float64)
-        keep[name] = a
+        a = getattr(P, name)
+        if a is not None:      # (the last three may be left to mcfost_b200_repartition_energie)
+            a = farray(a, np.float64)
+            keep[name] = a
         setattr(e, name, ptr(a, np.float64))
     a = farray(P.CDF_E_star, np.float32)
     keep["CDF_E_star"] = a

@@ -30,7 +30,7 @@ EXPORTS = (
     "mcfost_b200_cross_cell", "mcfost_b200_index_cell", "mcfost_b200_move_to_grid",
     "mcfost_b200_optical_length_tot", "mcfost_b200_physical_length", "mcfost_b200_compute_column", "mcfost_b200_define_dark_zone",
     "mcfost_b200_init_reemission", "mcfost_b200_init_reemission_grains",
-    "mcfost_b200_init_dust_source_fct1", "mcfost_b200_integ_ray_dust",
+    "mcfost_b200_init_dust_source_fct1", "mcfost_b200_integ_ray_dust", "mcfost_b200_repartition_energie",
     "mcfost_b200_distance_to_closest_wall", "mcfost_b200_mrw_tables",
     "mcfost_b200_multi_init", "mcfost_b200_multi_finalize", "mcfost_b200_multi_last_error", "mcfost_b200_multi_n_gpus",
     "mcfost_b200_multi_handle", "mcfost_b200_multi_upload_grid", "mcfost_b200_multi_upload_dark_zone",
@@ -341,6 +341,20 @@ class PhotonLoop:
         self._check(self.lib.mcfost_b200_integ_ray_dust(self.h, C.c_int32(lam), C.c_int64(n), _p(x), _p(y), _p(z), _p(u), _p(v), _p(w), _p(icell),
                                                         C.c_float(tau_dark_zone_obs), _p(out)))
         return out
+
+    def repartition_energie(self, Tdust, tab_lambda, E_stars, E_ISM=None, weight=None, lambda_first=1, lambda_last=None, download=True):
+        """repartition_energie (thermal_emission.f90:1771-1949, LTE) on the device; the tables become the handle's emission tables"""
+        P = self.P
+        lambda_last = lambda_last or P.n_lambda
+        T = np.ascontiguousarray(Tdust, np.float32); tl = np.ascontiguousarray(tab_lambda, np.float64)
+        Es = np.ascontiguousarray(E_stars, np.float64)
+        Ei = None if E_ISM is None else np.ascontiguousarray(E_ISM, np.float64)
+        wt = None if weight is None else np.ascontiguousarray(weight, np.float64)
+        E_disk, fs, fd, wn = (np.zeros(P.n_lambda) for _ in range(4))
+        prob = np.zeros((P.n_cells + 1, P.n_lambda), np.float64, order="F") if download else None
+        self._check(self.lib.mcfost_b200_repartition_energie(self.h, C.c_int32(lambda_first), C.c_int32(lambda_last), _p(T), _p(tl), _p(Es), _p(Ei),
+                                                             _p(wt), _p(E_disk), _p(fs), _p(fd), _p(wn), _p(prob)))
+        return dict(E_disk=E_disk, frac_E_stars=fs, frac_E_disk=fd, weight_norm=wn, prob_E_cell=prob)
 
     def compute_column(self, lam, cx, cy, cz, factor=None):
         """compute_column (optical_depth.f90:328-415): (n_cells, 4) real, column-major; factor None = optical depth at lam"""

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 
+#include <cub/cub.cuh>
 #include "handle.cuh"
 #include "cells.cuh"
 
@@ -294,11 +295,16 @@ int mcfost_b200_upload_emission(mcb_handle* h, const mcb_emission* e) {
   CK(cudaSetDevice(h->device));
   DevModel& m = h->m;
   int rc;
-  if (!e->frac_E_stars || !e->frac_E_disk || !e->prob_E_cell || !e->CDF_E_star) return fail(h, MCB_ERR_BAD_ARG, "emission tables missing");
+  // frac_E_stars, frac_E_disk and prob_E_cell may be NULL when mcfost_b200_repartition_energie built them on the device
+  const bool dev_tables = h->em_on_device && !e->frac_E_stars && !e->frac_E_disk && !e->prob_E_cell;
+  if (!e->CDF_E_star || (!dev_tables && (!e->frac_E_stars || !e->frac_E_disk || !e->prob_E_cell))) return fail(h, MCB_ERR_BAD_ARG, "emission tables missing");
   if ((rc = put(h, "spec_cumul", e->spectre_emission_cumul, (size_t)m.n_lambda + 1, &m.spec_cumul))) return rc;
-  if ((rc = put(h, "frac_star", e->frac_E_stars, (size_t)m.n_lambda, &m.frac_star))) return rc;
-  if ((rc = put(h, "frac_disk", e->frac_E_disk, (size_t)m.n_lambda, &m.frac_disk))) return rc;
-  if ((rc = put(h, "prob_E_cell", e->prob_E_cell, (size_t)(m.n_cells + 1) * m.n_lambda, &m.prob_E_cell))) return rc;
+  if (!dev_tables) {
+    if ((rc = put(h, "frac_star", e->frac_E_stars, (size_t)m.n_lambda, &m.frac_star))) return rc;
+    if ((rc = put(h, "frac_disk", e->frac_E_disk, (size_t)m.n_lambda, &m.frac_disk))) return rc;
+    if ((rc = put(h, "prob_E_cell", e->prob_E_cell, (size_t)(m.n_cells + 1) * m.n_lambda, &m.prob_E_cell))) return rc;
+    h->em_on_device = false;
+  }
   if ((rc = put(h, "CDF_E_star", e->CDF_E_star, (size_t)m.n_lambda * (m.n_stars + 1), &m.CDF_E_star))) return rc;
   if ((rc = put(h, "correct_E", e->correct_E_emission, (size_t)m.n_cells, &m.correct_E))) return rc;
   m.L_packet_th = e->L_packet_th; m.E_paquet = e->E_paquet; m.R_ISM = e->R_ISM;
@@ -1282,6 +1288,38 @@ __global__ void integ_ray_dust_kernel(const __grid_constant__ DevModel m, int64_
   for (int it = 0; it < ntf; ++it) out[(size_t)ntf * i + it] = acc[it];
 }
 
+// ---- repartition_energie (thermal_emission.f90:1771-1949), LTE case, on the device ------------------------------
+// E_cell(icell) = 4 kappa_abs_LTE kappa_factor volume / (wl^5 (exp(hc / (k T wl)) - 1)) from Tdust (`real`); its sum is
+// E_disk(lambda), its cumulative sum (weighted by weight_proba_emission when given) prob_E_cell(0:n_cells, lambda).
+__global__ void emission_cells_kernel(const __grid_constant__ DevModel m, int lambda, double wl, const float* Tdust, const double* weight,
+                                      double* E_cell, double* E_corr) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m.n_cells) return;
+  const float thermal_const = (float)(299792458.0 * 6.626070040e-34 / 1.38064852e-23);
+  const double cst_wl_max = (double)(logf(FLT_MAX) - 1.0e-4f);
+  const double wl2 = wl * wl, wl5 = (wl2 * wl2) * wl;
+  double E = 0.0;
+  if (!(m.dark && m.dark[idx])) {
+    const double Temp = (double)Tdust[idx];
+    if (!(Temp < MCB_TINY_REAL)) {
+      const double cst_wl = (double)thermal_const / (Temp * wl);
+      if (cst_wl < cst_wl_max) {
+        const int p_icell = (m.p_n_cells != 1) ? idx + 1 : 1;
+        E = 4.0 * m.kappa_abs[(p_icell - 1) + (size_t)m.p_n_cells * (lambda - 1)] * m.kappa_factor[idx] * m.volume[idx] / (wl5 * (exp(cst_wl) - 1.0));
+      }
+    }
+  }
+  E_cell[idx] = E;
+  E_corr[idx] = weight ? E * weight[idx] : E;
+}
+// prob(0:n_cells) of one wavelength from the inclusive sums cum(1:n_cells) (:1923-1941)
+__global__ void normalise_cdf_kernel(const double* cum, int n_cells, double* prob) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n_cells) return;
+  const double tot = cum[n_cells - 1];
+  prob[i] = (tot > MCB_TINY_DP && i > 0) ? cum[i - 1] / tot : 0.0;
+}
+
 // optical_depth.f90:21-182 with Stokes = 0 (no tallies)
 template <class G>
 __global__ void physical_length_kernel(const __grid_constant__ DevModel m, int64_t n, int lambda, double* x, double* y, double* z,
@@ -1640,6 +1678,75 @@ int mcfost_b200_integ_ray_dust(mcb_handle* h, int32_t lambda, int64_t n, const d
   CK(cudaGetLastError());
   s.out(I, dout, n * ntf);
   CK(cudaStreamSynchronize(h->stream));
+  return MCB_OK;
+}
+
+int mcfost_b200_repartition_energie(mcb_handle* h, int32_t lambda_first, int32_t lambda_last, const float* Tdust, const double* tab_lambda,
+                                    const double* E_stars, const double* E_ISM, const double* weight_proba_emission, double* E_disk,
+                                    double* frac_E_stars, double* frac_E_disk, double* weight_norm, double* prob_E_cell) {
+  if (!h || !Tdust || !tab_lambda || !E_stars || !E_disk || !frac_E_stars || !frac_E_disk) return MCB_ERR_BAD_ARG;
+  if (!h->has_grid || !h->has_op) return fail(h, MCB_ERR_STATE, "repartition_energie before upload_grid/opacity");
+  DevModel& m = h->m;
+  if (lambda_first < 1 || lambda_last > m.n_lambda || lambda_last < lambda_first) return fail(h, MCB_ERR_BAD_ARG, "wavelength range");
+  if (!m.volume) return fail(h, MCB_ERR_STATE, "repartition_energie: cell volumes were not uploaded");
+  CK(cudaSetDevice(h->device));
+  const int nc = m.n_cells, nl = m.n_lambda;
+  int rc;
+  double *dprob = nullptr, *dfs = nullptr, *dfd = nullptr;
+  // the emission tables of the handle (what upload_emission fills); created on first use
+  const bool had = h->bufs.count("prob_E_cell") && h->buf_bytes["prob_E_cell"] == (size_t)(nc + 1) * nl * sizeof(double);
+  if ((rc = reserve(h, "prob_E_cell", (size_t)(nc + 1) * nl, &dprob))) return rc;
+  if ((rc = reserve(h, "frac_star", (size_t)nl, &dfs))) return rc;
+  if ((rc = reserve(h, "frac_disk", (size_t)nl, &dfd))) return rc;
+  if (!had) CK(cudaMemsetAsync(dprob, 0, (size_t)(nc + 1) * nl * sizeof(double), h->stream));
+  Scratch s{h};
+  const float* dT = s.in(Tdust, nc);
+  const double* dw = weight_proba_emission ? s.in(weight_proba_emission, nc) : nullptr;
+  double *dE = s.in<double>(nullptr, nc), *dEc = s.in<double>(nullptr, nc), *dcum = s.in<double>(nullptr, nc), *dsum = s.in<double>(nullptr, 2);
+  if (!dT || !dE || !dEc || !dcum || !dsum || (weight_proba_emission && !dw)) return fail(h, MCB_ERR_CUDA, "scratch allocation failed");
+  size_t tmp_scan = 0, tmp_red = 0, tmp_max = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, dEc, dcum, nc, h->stream);
+  cub::DeviceScan::InclusiveScan(nullptr, tmp_max, dcum, dE, cub::Max(), nc, h->stream);
+  if (tmp_max > tmp_scan) tmp_scan = tmp_max;
+  cub::DeviceReduce::Sum(nullptr, tmp_red, dE, dsum, nc, h->stream);
+  void* dtmp = nullptr;
+  CK(cudaMalloc(&dtmp, tmp_scan > tmp_red ? tmp_scan : tmp_red));
+  s.d.push_back(dtmp);
+  const unsigned nb = (unsigned)((nc + 127) / 128), nb1 = (unsigned)((nc + 1 + 127) / 128);
+  std::vector<double> fs((size_t)nl), fd((size_t)nl);
+  CK(cudaMemcpyAsync(fs.data(), dfs, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));      // keep the wavelengths outside the range
+  CK(cudaMemcpyAsync(fd.data(), dfd, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int l = lambda_first; l <= lambda_last; ++l) {
+    const double wl = tab_lambda[l - 1] * (double)1.e-6f;
+    emission_cells_kernel<<<nb, 128, 0, h->stream>>>(m, l, wl, dT, dw, dE, dEc);
+    CK(cudaGetLastError());
+    size_t t1 = tmp_scan, t2 = tmp_red;
+    cub::DeviceScan::InclusiveSum(dtmp, t1, dEc, dcum, nc, h->stream);
+    cub::DeviceReduce::Sum(dtmp, t2, dE, dsum, nc, h->stream);
+    // a parallel prefix sum is not monotone to the last bit (each element has its own association order): a running
+    // maximum makes the distribution function non-decreasing again (dE is free once its sum is taken)
+    size_t t3 = tmp_scan;
+    cub::DeviceScan::InclusiveScan(dtmp, t3, dcum, dE, cub::Max(), nc, h->stream);
+    normalise_cdf_kernel<<<nb1, 128, 0, h->stream>>>(dE, nc, dprob + (size_t)(nc + 1) * (l - 1));
+    CK(cudaGetLastError());
+    double sums[2] = {0.0, 0.0};
+    CK(cudaMemcpyAsync(&sums[0], dsum, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&sums[1], dE + (nc - 1), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const double Ed = sums[0], Es = E_stars[l - 1], Ei = E_ISM ? E_ISM[l - 1] : 0.0;
+    if (Es + Ed + Ei < MCB_TINY_DP) return fail(h, MCB_ERR_BAD_ARG, "repartition_energie: no energy at this wavelength (the reference exits, thermal_emission.f90:1900)");
+    E_disk[l - 1] = Ed;
+    frac_E_stars[l - 1] = fs[l - 1] = Es / (Es + Ed + Ei);
+    frac_E_disk[l - 1] = fd[l - 1] = (Es + Ed) / (Es + Ed + Ei);
+    if (weight_norm) weight_norm[l - 1] = Ed > 0.0 ? sums[1] / Ed : 0.0;
+    if (prob_E_cell) CK(cudaMemcpyAsync(prob_E_cell + (size_t)(nc + 1) * (l - 1), dprob + (size_t)(nc + 1) * (l - 1), (size_t)(nc + 1) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaMemcpyAsync(dfs, fs.data(), (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(dfd, fd.data(), (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  m.prob_E_cell = dprob; m.frac_star = dfs; m.frac_disk = dfd;
+  h->em_on_device = true;
   return MCB_OK;
 }
 

@@ -41,6 +41,7 @@ struct mcb_handle {
   std::vector<double> host_kappa_factor;  // host copies used to build kf_dark (kappa_factor | dark flag)
   std::vector<uint8_t> host_dark;
   bool kf_dark_stale = true;
+  bool em_on_device = false;              // prob_E_cell / frac_E_stars / frac_E_disk were built by mcfost_b200_repartition_energie
   bool mrw_ready = false;                 // zeta table + mean opacities of the modified random walk are on the device
   char err[512] = {0};
 };

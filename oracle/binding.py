@@ -236,6 +236,20 @@ class Oracle:
                                                    C.c_int32(ntf), _p(out)))
         return out
 
+    def repartition_energie(self, Tdust, tab_lambda, E_stars, E_ISM=None, weight=None, lambda_first=1, lambda_last=None):
+        """repartition_energie (thermal_emission.f90:1771-1949, LTE) for a range of wavelengths; uses the oracle's dark zone"""
+        P = self.P
+        lambda_last = lambda_last or P.n_lambda
+        T = np.ascontiguousarray(Tdust, np.float32); tl = np.ascontiguousarray(tab_lambda, np.float64)
+        Es = np.ascontiguousarray(E_stars, np.float64)
+        Ei = None if E_ISM is None else np.ascontiguousarray(E_ISM, np.float64)
+        wt = None if weight is None else np.ascontiguousarray(weight, np.float64)
+        E_disk, fs, fd, wn = (np.zeros(P.n_lambda) for _ in range(4))
+        prob = np.zeros((P.n_cells + 1, P.n_lambda), np.float64, order="F")
+        self._check(self.lib.oracle_repartition_energie(self.h, C.c_int32(lambda_first), C.c_int32(lambda_last), _p(T), _p(tl), _p(Es), _p(Ei), _p(wt),
+                                                        _p(E_disk), _p(fs), _p(fd), _p(wn), _p(prob)))
+        return dict(E_disk=E_disk, frac_E_stars=fs, frac_E_disk=fd, weight_norm=wn, prob_E_cell=prob)
+
     def compute_column(self, lam, cx, cy, cz, factor=None):
         """compute_column (optical_depth.f90:328-415): (n_cells, 4) real, column-major; factor None = optical depth at lam"""
         cx, cy, cz = self._f64(cx, cy, cz)

@@ -1548,6 +1548,47 @@ struct Oracle {
   }
 
   // =====================================================================
+  // thermal_emission.f90:1771-1949  repartition_energie(lambda), LTE case: thermal emission of every cell at wavelength
+  // lambda from Tdust (`real`), the cumulative emission probability of the cells and the star / disk / ISM fractions.
+  // prob: prob_E_cell(0:n_cells) of this wavelength.  weight: weight_proba_emission or null; *weight_norm receives
+  // prob_E_cell(n_cells) / E_disk before the normalisation (the factor correct_E_emission is multiplied by, :1932-1934).
+  // Returns false when there is no energy at this wavelength (the reference exits, :1900-1904).
+  // =====================================================================
+  bool repartition_energie(int lambda, const float* Tdust, const double* tab_lambda, double E_star, double E_ISM, const double* weight,
+                           double* prob, double& E_disk, double& frac_E_stars, double& frac_E_disk, double* weight_norm) const {
+    const float thermal_const = (float)(299792458.0 * 6.626070040e-34 / 1.38064852e-23);
+    const double cst_wl_max = (double)(std::log(std::numeric_limits<float>::max()) - 1.0e-4f);
+    const double wl = tab_lambda[lambda - 1] * (double)1.e-6f;
+    const double wl2 = wl * wl, wl5 = (wl2 * wl2) * wl;
+    const int n = g.n_cells;
+    E_disk = 0.0;
+    prob[0] = 0.0;
+    for (int icell = 1; icell <= n; ++icell) {
+      double E = 0.0;
+      if (!dark[icell]) {
+        const double Temp = (double)Tdust[icell - 1];
+        if (!(Temp < tiny_real)) {
+          const double cst_wl = (double)thermal_const / (Temp * wl);
+          if (cst_wl < cst_wl_max) {
+            const int p_icell = lvariable_dust() ? icell : 1;
+            E = 4.0 * kappa_abs_LTE(p_icell, lambda) * kappa_factor(icell) * volume(icell) / (wl5 * (std::exp(cst_wl) - 1.0));
+          }
+        }
+      }
+      E_disk = E_disk + E;
+      prob[icell] = prob[icell - 1] + (weight ? E * weight[icell - 1] : E);
+    }
+    if (E_star + E_disk + E_ISM < tiny_dp) return false;
+    frac_E_stars = E_star / (E_star + E_disk + E_ISM);
+    frac_E_disk = (E_star + E_disk) / (E_star + E_disk + E_ISM);
+    if (weight_norm) *weight_norm = E_disk > 0.0 ? prob[n] / E_disk : 0.0;
+    const double tot = prob[n];
+    if (tot > tiny_dp) for (int icell = 0; icell <= n; ++icell) prob[icell] = prob[icell] / tot;
+    else for (int icell = 0; icell <= n; ++icell) prob[icell] = 0.0;
+    return true;
+  }
+
+  // =====================================================================
   // scattering.f90:1354-1383  hg
   // =====================================================================
   static void hg(float g_, float rand, int& itheta, double& cospsi) {
@@ -2595,6 +2636,19 @@ int oracle_integ_ray_dust(void* h, int32_t lambda, int64_t n, const double* x, c
   Oracle* O = (Oracle*)h;
   for (int64_t i = 0; i < n; ++i)
     O->integ_ray_dust(lambda, icell[i], x[i], y[i], z[i], u[i], v[i], w[i], tau_dark_zone_obs, eps, az_dim, th_dim, n_az_rt, N_type_flux, out + (size_t)N_type_flux * i);
+  return MCB_OK;
+}
+int oracle_repartition_energie(void* h, int32_t lambda_first, int32_t lambda_last, const float* Tdust, const double* tab_lambda, const double* E_stars,
+                               const double* E_ISM, const double* weight, double* E_disk, double* frac_E_stars, double* frac_E_disk,
+                               double* weight_norm, double* prob_E_cell) {
+  Oracle* O = (Oracle*)h;
+  const size_t n1 = (size_t)O->g.n_cells + 1;
+  for (int l = lambda_first; l <= lambda_last; ++l) {
+    double wn = 0.0;
+    if (!O->repartition_energie(l, Tdust, tab_lambda, E_stars[l - 1], E_ISM ? E_ISM[l - 1] : 0.0, weight, prob_E_cell + n1 * (size_t)(l - 1),
+                                E_disk[l - 1], frac_E_stars[l - 1], frac_E_disk[l - 1], &wn)) return MCB_ERR_BAD_ARG;
+    if (weight_norm) weight_norm[l - 1] = wn;
+  }
   return MCB_OK;
 }
 int oracle_compute_column(void* h, int32_t lambda, const double* factor, const double* cx, const double* cy, const double* cz, float* column) {

@@ -169,6 +169,15 @@ module mcfost_b200_shim
        type(c_ptr), value :: h, logQ, cdf
        real(c_double), intent(in) :: tab_lambda(*), tab_delta_lambda(*)
      end function
+     integer(c_int) function mcfost_b200_repartition_energie(h, lambda_first, lambda_last, Tdust, tab_lambda, E_stars, E_ISM, weight, &
+          E_disk, frac_E_stars, frac_E_disk, weight_norm, prob_E_cell) bind(C, name='mcfost_b200_repartition_energie')
+       import
+       type(c_ptr), value :: h, weight, weight_norm, prob_E_cell
+       integer(c_int32_t), value :: lambda_first, lambda_last
+       real(c_float), intent(in) :: Tdust(*)
+       real(c_double), intent(in) :: tab_lambda(*), E_stars(*), E_ISM(*)
+       real(c_double) :: E_disk(*), frac_E_stars(*), frac_E_disk(*)
+     end function
      integer(c_int) function mcfost_b200_index_cell(h, n, x, y, z, icell) bind(C, name='mcfost_b200_index_cell')
        import
        type(c_ptr), value :: h
@@ -347,6 +356,35 @@ contains
     endif
     call b200_check(mcfost_b200_multi_upload_dark_zone(b200, dark_i32), "upload_dark_zone")      ! the other GPUs of the node
   end subroutine define_dark_zone_b200
+
+  ! Replaces  call repartition_energie(lambda)  (thermal_emission.f90:1771-1949) for the LTE case without lweight_emission:
+  ! every GPU builds prob_E_cell(:,lambda), frac_E_stars(lambda), frac_E_disk(lambda) where the photon loop reads them (the
+  ! host copy of prob_E_cell is only fetched from GPU 0 when the caller needs it: lwant_prob); E_disk, the fractions and
+  ! E_totale come back as the reference computes them.  mc_photon_loop_b200 then passes NULL for the three tables.
+  subroutine repartition_energie_b200(lambda, lwant_prob)
+    integer, intent(in) :: lambda
+    logical, intent(in) :: lwant_prob
+    real(c_double) :: surface
+    type(c_ptr) :: pp
+    integer :: i
+    if (.not.lRE_LTE .or. lRE_nLTE .or. lnRE .or. lweight_emission) &
+         call error("mcfost_b200: repartition_energie_b200 covers the LTE case without lweight_emission")
+    do i = 0, mcfost_b200_multi_n_gpus(b200) - 1
+       pp = c_null_ptr
+       if (i == 0 .and. lwant_prob) pp = c_loc(prob_E_cell(0,lambda))
+       ! (prob_E_cell argument of the C entry point: host copy of the columns lambda_first..lambda_last, addressed from column 1)
+       if (c_associated(pp)) pp = c_loc(prob_E_cell(0,1))
+       call b200_check(mcfost_b200_repartition_energie(mcfost_b200_multi_handle(b200, int(i, c_int)), int(lambda, c_int32_t), &
+            int(lambda, c_int32_t), Tdust, tab_lambda, E_stars, E_ISM, c_null_ptr, E_disk, frac_E_stars, frac_E_disk, c_null_ptr, pp), &
+            "repartition_energie")
+    enddo
+    surface=4*pi*(pc_to_AU*distance)**2
+    if (l_sym_centrale) then
+       E_totale(lambda) = 2.0*pi*hp*c_light**2/surface * (E_stars(lambda)+E_disk(lambda)+E_ISM(lambda)) * real(N_thet)*real(N_phi)
+    else
+       E_totale(lambda) = 2.0*pi*hp*c_light**2/surface * (E_stars(lambda)+E_disk(lambda)+E_ISM(lambda)) * real(2*N_thet)*real(N_phi)
+    endif
+  end subroutine repartition_energie_b200
 
   ! Replaces  call integ_tau(lambda)  (optical_depth.f90:186-244): the optical depth from the star through the midplane and
   ! along the inclination of interest, two rays through mcfost_b200_optical_length_tot, same messages.

@@ -499,3 +499,41 @@ def test_integ_tau_rays_from_the_star_bit_exact(name):
         assert np.array_equal(o["tau_tot"], g["tau_tot"]) and np.array_equal(o["n_steps"], g["n_steps"]) and np.array_equal(o["lmax"], g["lmax"])
         assert g["tau_tot"][0] > g["tau_tot"][1] > 0 or name == "sph2D"
     G.close()
+
+
+@pytest.mark.parametrize("name", ["cyl2D", "variable_dust", "cyl3D"])
+def test_repartition_energie_on_the_device_matches_oracle(name):
+    """mcfost_b200_repartition_energie (thermal_emission.f90:1771-1949, LTE case): E_disk, the star / disk fractions and
+    prob_E_cell(0:n_cells, lambda) from a temperature field, against the oracle's sequential sums (parallel scan on the device:
+    1e-11; CUDA exp); with a dark zone, with weights, on a wavelength range; then an SED-like step whose disk emission samples
+    the device-built table equals the step on uploaded tables."""
+    P = S.ref41_multi_like(n_photons_eq_th=100) if name == "variable_dust" else small_problems()[name]()
+    rng = np.random.default_rng(4)
+    T = rng.uniform(15.0, 900.0, P.n_cells).astype(np.float32); T[::17] = 0.0
+    dark = np.zeros(P.n_cells, np.int32); dark[5::11] = 1
+    O, G = Oracle(P), api.PhotonLoop(P)
+    O.set_dark_zone(dark); G.upload_dark_zone(dark)
+    for weight, (l0, l1) in ((None, (1, P.n_lambda)), (rng.uniform(0.5, 2.0, P.n_cells), (7, 19))):
+        o = O.repartition_energie(T, P.tab_lambda, P.E_stars, None, weight, l0, l1)
+        g = G.repartition_energie(T, P.tab_lambda, P.E_stars, None, weight, l0, l1)
+        sl = slice(l0 - 1, l1)
+        for k in ("E_disk", "frac_E_stars", "frac_E_disk", "weight_norm"):
+            assert np.allclose(g[k][sl], o[k][sl], rtol=1e-11, atol=1e-300), k
+        assert np.abs(g["prob_E_cell"][:, sl] - o["prob_E_cell"][:, sl]).max() < 1e-11
+        assert (g["prob_E_cell"][0, sl] == 0).all() and np.allclose(g["prob_E_cell"][-1, sl][o["E_disk"][sl] > 0], 1.0, rtol=1e-12)
+        assert (np.diff(g["prob_E_cell"][:, sl], axis=0) >= 0).all()
+    # the device tables drive the emission: a monochromatic step at a thermal wavelength, disk emission on
+    full = G.repartition_energie(T, P.tab_lambda, P.E_stars)
+    import copy
+    P2 = copy.copy(P); P2.prob_E_cell = None; P2.frac_E_stars = None; P2.frac_E_disk = None
+    G.upload_emission(P2)                                # NULL for the three tables: the device-built ones stay
+    lam = P.n_lambda - 8
+    kw = dict(letape_th=0, lmono=1, lcount_sent=1, n_phot_lim=1.0e30)      # chunks end on packets sent: the same packets in both runs
+    p_lam = lam if P.p_n_lambda_pos > 1 else 1
+    t_dev = G.mc_photon_loop(lam, p_lam, 300, call_index=5, **kw)
+    P3 = copy.copy(P); P3.prob_E_cell = full["prob_E_cell"]; P3.frac_E_stars = full["frac_E_stars"]; P3.frac_E_disk = full["frac_E_disk"]
+    G.upload_emission(P3)                                # the same tables through the host
+    t_up = G.mc_photon_loop(lam, p_lam, 300, call_index=5, **kw)
+    assert t_dev.stats[0] == t_up.stats[0] == 128 * 300 and full["frac_E_stars"][lam - 1] < 0.9      # the disk does emit here
+    assert np.array_equal(t_dev.stats[:7], t_up.stats[:7]) and np.allclose(t_dev.sed, t_up.sed, rtol=1e-9, atol=0)
+    G.close()

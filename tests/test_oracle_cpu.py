@@ -376,3 +376,26 @@ def test_integ_ray_dust_telescopes_for_a_uniform_source_function():
     kap = P.kappa.reshape(P.p_n_cells, P.n_lambda)[0, lam - 1] * P.kappa_factor
     ok = kap > 0
     assert np.allclose(e[3, 1, 0][ok], (J / np.where(ok, kap, 1.0))[ok], rtol=1e-14) and (e[:, :, 0][:, :, ~ok] == 0).all()
+
+
+def test_repartition_energie_oracle_matches_the_generator():
+    """The oracle's repartition_energie (thermal_emission.f90:1771-1949, LTE case) against the generator's numpy version
+    (double-precision constants: the 1e-8 the `1.e-6` literal is worth on the wavelength, up to 1e-6 on the Wien side where
+    hc / (k T lambda) ~ 80), with dark cells and cold cells."""
+    P = S.ref41_like(n_photons_eq_th=10, dark_zone=False, n_rad=30, nz=16, n_rad_in=5)
+    T = np.random.default_rng(1).uniform(20.0, 800.0, P.n_cells).astype(np.float32)
+    T[::13] = 0.0
+    dark = np.zeros(P.n_cells, np.int32); dark[3::7] = 1
+    S.repartition_energie(P, Tdust=T)                      # (no dark zone)
+    O = Oracle(P)
+    r0 = O.repartition_energie(T, P.tab_lambda, P.E_stars)
+    ok = P.E_disk > 0
+    assert ok.sum() > 20 and np.allclose(r0["E_disk"][ok], P.E_disk[ok], rtol=1e-5)
+    assert np.abs(r0["prob_E_cell"] - P.prob_E_cell).max() < 1e-6 and np.allclose(r0["frac_E_stars"], P.frac_E_stars, rtol=1e-5)
+    O.set_dark_zone(dark)
+    r = O.repartition_energie(T, P.tab_lambda, P.E_stars)
+    inc = np.diff(r["prob_E_cell"], axis=0)
+    assert (inc[dark == 1] == 0).all() and (inc[T == 0] == 0).all() and (r["E_disk"][ok] < r0["E_disk"][ok]).all()
+    w = np.linspace(0.5, 1.5, P.n_cells)
+    rw = O.repartition_energie(T, P.tab_lambda, P.E_stars, weight=w, lambda_first=10, lambda_last=12)
+    assert np.allclose(rw["E_disk"][9:12], r["E_disk"][9:12]) and (rw["E_disk"][:9] == 0).all() and np.all(rw["weight_norm"][9:12] > 0)
