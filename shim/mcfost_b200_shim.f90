@@ -371,9 +371,8 @@ contains
          call error("mcfost_b200: repartition_energie_b200 covers the LTE case without lweight_emission")
     do i = 0, mcfost_b200_multi_n_gpus(b200) - 1
        pp = c_null_ptr
-       if (i == 0 .and. lwant_prob) pp = c_loc(prob_E_cell(0,lambda))
-       ! (prob_E_cell argument of the C entry point: host copy of the columns lambda_first..lambda_last, addressed from column 1)
-       if (c_associated(pp)) pp = c_loc(prob_E_cell(0,1))
+       ! (the C entry point takes the base of prob_E_cell(0:n_cells, n_lambda) and fills the columns of its wavelength range)
+       if (i == 0 .and. lwant_prob) pp = c_loc(prob_E_cell(0,1))
        call b200_check(mcfost_b200_repartition_energie(mcfost_b200_multi_handle(b200, int(i, c_int)), int(lambda, c_int32_t), &
             int(lambda, c_int32_t), Tdust, tab_lambda, E_stars, E_ISM, c_null_ptr, E_disk, frac_E_stars, frac_E_disk, c_null_ptr, pp), &
             "repartition_energie")
