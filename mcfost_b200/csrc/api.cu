@@ -659,7 +659,7 @@ int mcfost_b200_launch(mcb_handle* h, const mcb_run_params* r) {
   // (the flight-start slab of capteur_full is not part of a parked packet: no hand-over in those modes)
   dr.park_enable = 0;      // set by mcb_launch_mc for the kernels that hand their last packets over
   dr.patience = 8;
-  dr.park_live = 48;      // measured (profiles/r02_tail.md): the packet-per-lane kernel drains faster than the packet-per-warp kernel down to ~50 packets per SM
+  dr.park_live = 128;     // measured (profiles/r02_latency_and_tail.md section 7): hand-over at 96 .. 192 live packets per SM is a flat optimum with the round's final packet-per-warp kernel (48 before its instruction diet)
   dr.debug_abort_dry = 0;
   dr.patience_dry = 1; dr.drain_live_dry = 96;
   dr.min_chunk = 32;
