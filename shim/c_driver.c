@@ -129,6 +129,27 @@ int main(int argc, char **argv) {
   CHECK(mcfost_b200_temp_finale(h, Tdust), "temp_finale");
   float tmax = 0; for (size_t i = 0; i < nc; ++i) if (Tdust[i] > tmax) tmax = Tdust[i];
   printf("Tdust max %.2f K\n", tmax);
+
+  /* ---- the neighbours of the path a caller binds the same way ---- */
+  /* define_dark_zone(lambda, p_lambda, tau_max, ldiff_approx), optical_depth.f90:1425-1651 */
+  const int lam = geti("lambda_seuil");
+  int32_t *dark = calloc(nc, 4), *zj_sup = calloc((size_t)g.n_rad, 4), ri_in = 0, ri_out = 0, is_dark = 0;
+  int32_t iRmin = 1, iRmax = g.n_rad;
+  CHECK(mcfost_b200_define_dark_zone(h, lam, 30.0f, arr("r_grid"), arr("z_grid"), 1, &iRmin, &iRmax, NULL, dark, &ri_in, &ri_out, zj_sup, NULL, &is_dark),
+        "define_dark_zone");
+  long n_dark = 0; for (size_t i = 0; i < nc; ++i) n_dark += dark[i];
+  printf("dark zone: %ld cells, ri_in %d ri_out %d l_is_dark_zone %d\n", n_dark, ri_in, ri_out, is_dark);
+  /* compute_column(2, column, lambda), optical_depth.f90:328-415 (2D grid: the cell centres are (r_grid, 0, z_grid)) */
+  double *cy = calloc(nc, 8);
+  float *column = calloc(4 * nc, 4);
+  CHECK(mcfost_b200_compute_column(h, lam, NULL, arr("r_grid"), cy, arr("z_grid"), column), "compute_column");
+  float cmax = 0; for (size_t i = 0; i < 4 * nc; ++i) if (column[i] > cmax) cmax = column[i];
+  printf("column: max optical depth %.4e\n", cmax);
+  /* init_reemission, thermal_emission.f90:404-550: the tables on the device against the uploaded ones */
+  double *logQ = calloc((size_t)o.n_T * o.p_n_cells, 8);
+  CHECK(mcfost_b200_init_reemission(h, arr("tab_lambda"), arr("tab_delta_lambda"), logQ, NULL), "init_reemission");
+  double dq = 0; for (int k = 1; k < o.n_T * o.p_n_cells; ++k) { double d = logQ[k] - o.log_Qcool_minus_extra_heating[k]; if (d < 0) d = -d; if (d > dq) dq = d; }
+  printf("init_reemission: max |log Qcool - uploaded| %.3e\n", dq);
   mcfost_b200_finalize(h);
-  return ok && tmax > 10.0f ? 0 : 1;
+  return ok && tmax > 10.0f && n_dark > 0 && is_dark == 1 && cmax > 100.0f && dq < 1.0e-6 ? 0 : 1;
 }

@@ -41,3 +41,17 @@ def test_c_driver_runs_the_thermal_step(tmp_path):
     r = subprocess.run([exe, prob, "100"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "packets 12800 " in r.stdout and "Tdust max" in r.stdout
+    # the neighbours of the path, bound from C the same way: against the host mirror on the same problem
+    import re
+    import numpy as np
+    from mcfost_b200 import synthetic as S, api
+    P = S.ref41_like(n_photons_eq_th=100, dark_zone=False, n_rad=40, nz=20, n_rad_in=5, tau_mid=1.0e3)
+    G = api.PhotonLoop(P)
+    d = G.define_dark_zone(P.lambda_seuil, 30.0, P.r_grid, P.z_grid, [(1, P.n_rad)])
+    col = G.compute_column(P.lambda_seuil, P.r_grid, np.zeros(P.n_cells), P.z_grid)
+    G.close()
+    m = re.search(r"dark zone: (\d+) cells, ri_in (\d+) ri_out (\d+) l_is_dark_zone (\d)", r.stdout)
+    assert m and int(m.group(1)) == d["l_dark_zone"].sum() > 0 and int(m.group(2)) == d["ri_in"][0] and int(m.group(3)) == d["ri_out"][0]
+    m = re.search(r"column: max optical depth ([0-9.e+-]+)", r.stdout)
+    assert m and abs(float(m.group(1)) / col.max() - 1) < 1e-4
+    assert "init_reemission: max |log Qcool - uploaded|" in r.stdout

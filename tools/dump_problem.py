@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from mcfost_b200 import synthetic as S
 
-GRID = ("r_lim", "r_lim_2", "r_lim_3", "z_lim", "zmax", "tan_phi_lim", "volume", "star_xyzr")
+GRID = ("r_lim", "r_lim_2", "r_lim_3", "z_lim", "zmax", "tan_phi_lim", "volume", "star_xyzr", "r_grid", "z_grid", "tab_lambda", "tab_delta_lambda")
 GRID_I = ("cell_map_i", "cell_map_j", "cell_map_k", "star_icell", "star_out_model")
 OPA = ("kappa", "kappa_abs_LTE", "kappa_factor", "log_Qcool_minus_extra_heating", "kdB_dT_CDF")
 OPA_F = ("tab_albedo_pos", "tab_g_pos", "prob_s11_pos", "tab_s11_pos", "tab_s12_o_s11_pos", "tab_s22_o_s11_pos",
@@ -19,7 +19,7 @@ def dump(P, path):
             dt = (np.float64, np.float32, np.int32)[code]
             a = np.asfortranarray(np.asarray(a, dtype=dt))
             f.write(name.encode().ljust(32, b"\0")); f.write(struct.pack("<iq", code, a.size)); f.write(a.tobytes(order="F"))
-        for k in ("kind", "l3D", "n_rad", "nz", "n_az", "n_cells", "n_cells_tot", "n_stars", "n_lambda", "p_n_cells", "p_n_lambda_pos", "n_T"):
+        for k in ("kind", "l3D", "n_rad", "nz", "n_az", "n_cells", "n_cells_tot", "n_stars", "n_lambda", "p_n_cells", "p_n_lambda_pos", "n_T", "lambda_seuil"):
             rec(k, [int(getattr(P, k))], 2)
         for k in ("Rmax2", "zmaxmax", "L_packet_th", "E_paquet", "T_min"):
             rec(k, [float(getattr(P, k))], 0)
