@@ -342,7 +342,7 @@ int mcfost_b200_sync(mcb_handle *h);
  * dry, ~15 % of the packets in flight belong to the longest-lived 0.1 % (length-biased sampling): ~2 % of the
  * call's events, but up to 3e5 sequential events per packet, i.e. ~1 s during which most SMs idle.  With
  * n_sms_reserved > 0 the main launch of every following call uses all but n_sms_reserved SMs and, once its
- * counter is dry, hands its last packets (<= 256 per SM) to a second launch of n_sms_straggler blocks, so that
+ * counter is dry, hands its last packets (<= 128 per SM) to a second launch of n_sms_straggler blocks, so that
  * calls issued on OTHER handles (own streams) can start on the rest of the GPU while this one finishes.
  * With k handles used in turn, n_sms_straggler = n_sms_reserved / (k - 1) keeps every launch resident.
  * Results are unchanged; (0, 0) (default) turns it off.  n_sms_straggler <= n_sms_reserved <= half the SMs;
