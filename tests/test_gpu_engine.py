@@ -155,9 +155,11 @@ def test_modified_random_walk_matches_oracle_and_plain_run(n2):
     for t in (t0, t1):
         assert t.stats[0] == 128 * n2 and t.stats[5] + t.stats[6] == t.stats[0]
     if 128 * n2 <= 1000000:      # the packet-per-warp kernel runs the whole call: walks and steps per packet like the oracle's
+        # (seed-to-seed spread of the oracle at this budget: interactions 2.5 %, walks 5.4 %, walk steps 6.3 % -- a handful of
+        # trapped packets make most of them; the ratio of interactions with / without the walk is 0.87 +- 0.02)
         assert t1.stats[2] < 0.97 * t0.stats[2]
-        assert abs(t1.stats[8] / to.stats[8] - 1) < 0.1 and abs(t1.stats[9] / to.stats[9] - 1) < 0.1
-        assert abs(t1.stats[2] / to.stats[2] - 1) < 0.05
+        assert abs(t1.stats[8] / to.stats[8] - 1) < 0.2 and abs(t1.stats[9] / to.stats[9] - 1) < 0.25
+        assert abs(t1.stats[2] / to.stats[2] - 1) < 0.1
     else:                        # three launches: only the packets the packet-per-warp kernel finishes walk (MRW)
         assert t1.stats[8] < to.stats[8]
     lit = (np.asarray(P.l_dark_zone) == 0) & (t0.xKJ_abs > 0) & (t1.xKJ_abs > 0) & (to.xKJ_abs > 0) & (To > 1.5)
